@@ -1,0 +1,135 @@
+"""Distribution oracle (log_prob, reparameterised sample from given noise) -- NumPy, test infrastructure only.
+
+Follows
+  * `vaemolsim/dists.py:28-87`   (`make_param_transform`: parameter_properties bijectors; von Mises atan2 + SoftClip)
+  * `vaemolsim/dists.py:197-217` (`IndependentBlockwise.call`: split by param_nums, per-dof dist, Blockwise)
+  * `vaemolsim/dists.py:307-340` (`AutoregressiveBlockwise.call`: raw = inputs + MADE(samples, cond); Autoregressive)
+  * `vaemolsim/dists.py:589-610` (`IndependentVonMises.new`: split 3, atan2, softplus concentration)
+  * `vaemolsim/dists.py:688-704` (`IndependentDeterministic.new`)
+  * `vaemolsim/dists.py:414-439` (`FlowedDistribution.call`) with TFP `TransformedDistribution`
+and tensorflow-probability v0.23.0 `distributions/normal.py::_log_prob`, `von_mises.py::_log_prob`,
+`blockwise.py`, `autoregressive.py::_sample_n/_log_prob`, `layers/distribution_layer.py::IndependentNormal.new`
+(third-party, not vendored).
+"""
+import numpy as np
+
+from . import nets
+from .rqs import softplus_tf
+
+EPS32 = np.float32(np.finfo(np.float32).eps)
+HALF_LOG_2PI = 0.5 * np.log(2.0 * np.pi)
+LOG_2PI = np.log(2.0 * np.pi)
+
+
+def i0e(x):
+    from scipy.special import i0e as _i0e
+    return _i0e(np.asarray(x, dtype=np.float64))
+
+
+# ----------------------------------------------------------------------------- Normal
+def normal_log_prob(x, loc, scale):
+    """TFP Normal._log_prob, elementwise: -0.5 (x/s - m/s)^2 - (0.5 log 2pi + log s)."""
+    dt = np.result_type(x, loc, scale)
+    x, loc, scale = (np.asarray(a, dtype=dt) for a in (x, loc, scale))
+    z = x / scale - loc / scale
+    return (dt.type(-0.5) * z * z - (dt.type(HALF_LOG_2PI) + np.log(scale))).astype(dt)
+
+
+def independent_normal_params(params, event_size):
+    """tfp.layers.IndependentNormal.new: loc, scale = split(params, 2); scale = softplus(raw)."""
+    loc, raw = params[..., :event_size], params[..., event_size:2 * event_size]
+    return loc, softplus_tf(raw)
+
+
+def independent_normal_log_prob(x, params):
+    D = x.shape[-1]
+    loc, scale = independent_normal_params(params, D)
+    return normal_log_prob(x, loc, scale).sum(axis=-1).astype(x.dtype)
+
+
+def normal_sample(loc, scale, eps):
+    """TFP Normal._sample_n: eps * scale + loc."""
+    return (eps * scale + loc).astype(loc.dtype)
+
+
+# ----------------------------------------------------------------------------- von Mises
+def vonmises_log_prob(x, loc, conc):
+    """TFP VonMises._log_prob: conc (cos(x - loc) - 1) - log(2 pi) - log(i0e(conc))."""
+    dt = np.result_type(x, loc, conc)
+    z = np.asarray(x, dt) - np.asarray(loc, dt)
+    return (np.asarray(conc, dt) * (np.cos(z) - 1) - dt.type(LOG_2PI) - np.log(i0e(conc)).astype(dt)).astype(dt)
+
+
+def independent_vonmises_params(params, event_size):
+    """dists.py:602-607: sine, cosine, scale = split(params, 3); loc = atan2(sine, cosine); conc = softplus."""
+    s, c, k = (params[..., i * event_size:(i + 1) * event_size] for i in range(3))
+    return np.arctan2(s, c).astype(params.dtype), softplus_tf(k)
+
+
+def independent_vonmises_log_prob(x, params):
+    loc, conc = independent_vonmises_params(params, x.shape[-1])
+    return vonmises_log_prob(x, loc, conc).sum(axis=-1).astype(x.dtype)
+
+
+# ----------------------------------------------------------------------------- make_param_transform / Blockwise
+def param_transform(kind, p):
+    """dists.py:56-78.  kind in {'normal','vonmises'}; p [..., n_params] -> dict of constrained parameters.
+
+    Normal: parameter_properties => loc identity, scale Softplus(low=eps) i.e. softplus(x) + eps32.
+    VonMises: loc = atan2(p0, p1); concentration = SoftClip(low=eps32, high=sqrt(max32)/2)(p2), restated as
+    softplus(x) + eps32 -- the soft upper clip at 9.2e18 is unreachable in fp32 practice [unverified vs TFP].
+    """
+    if kind == 'normal':
+        return dict(loc=p[..., 0], scale=(softplus_tf(p[..., 1]) + EPS32).astype(p.dtype))
+    if kind == 'vonmises':
+        return dict(loc=np.arctan2(p[..., 0], p[..., 1]).astype(p.dtype),
+                    concentration=(softplus_tf(p[..., 2]) + EPS32).astype(p.dtype))
+    raise ValueError(kind)
+
+
+PARAM_NUMS = {'normal': 2, 'vonmises': 3}  # dists.py:164-173 (+1 for von Mises)
+
+
+def blockwise_log_prob_split(x, params_per_dof, kinds):
+    """x [B, D]; params_per_dof: list of D arrays [B, n_i].  Blockwise log_prob = sum over dofs."""
+    lp = np.zeros(x.shape[0], x.dtype)
+    for i, kind in enumerate(kinds):
+        t = param_transform(kind, params_per_dof[i])
+        if kind == 'normal':
+            lp = lp + normal_log_prob(x[:, i], t['loc'], t['scale'])
+        else:
+            lp = lp + vonmises_log_prob(x[:, i], t['loc'], t['concentration'])
+    return lp.astype(x.dtype)
+
+
+def independent_blockwise_log_prob(x, params, kinds):
+    """dists.py:210-217: params [B, sum(param_nums)] split contiguously per dof."""
+    nums = [PARAM_NUMS[k] for k in kinds]
+    offs = np.concatenate([[0], np.cumsum(nums)])
+    return blockwise_log_prob_split(x, [params[:, offs[i]:offs[i + 1]] for i in range(len(kinds))], kinds)
+
+
+def autoregressive_blockwise_log_prob(x, inputs, made_layers, kinds, cond=None, activation=None):
+    """dists.py:326-340 + TFP Autoregressive._log_prob: distribution_fn(x).log_prob(x).
+
+    inputs [B, D, Pmax]; raw = inputs + MADE(x, cond); dof i uses raw[:, i, :param_nums[i]] -- note the
+    reference passes the full Pmax-wide slice and the transform reads only the leading entries.
+    `activation` is the AutoregressiveNetwork hidden activation (TFP default None = linear; the MC notebook
+    passes only hidden_units, `MC_Moves_with_VAEs.ipynb` cell 17).
+    """
+    pmax = inputs.shape[-1]
+    raw = inputs + nets.made_forward(x, made_layers, pmax, cond, activation=activation)
+    return blockwise_log_prob_split(x, [raw[:, i, :] for i in range(len(kinds))], kinds)
+
+
+def autoregressive_blockwise_sample_normal(inputs, made_layers, eps, cond=None, activation=None):
+    """TFP Autoregressive._sample_n for all-Normal dofs with FIXED noise eps [B, D] reused every step:
+    samples0 = dist_fn(ones).sample(); then num_steps = D times samples = dist_fn(samples).sample()."""
+    B, D, pmax = inputs.shape
+    s = np.ones((B, D), inputs.dtype)
+    for _ in range(D + 1):
+        raw = inputs + nets.made_forward(s, made_layers, pmax, cond, activation=activation)
+        loc = raw[..., 0]
+        scale = softplus_tf(raw[..., 1]) + EPS32
+        s = normal_sample(loc, scale, eps)
+    return s
