@@ -1,0 +1,279 @@
+/*
+ * vms_b200.h -- C ABI of libvms_b200.so: sm_100a kernels for the vaemolsim hot path.
+ *
+ * The reference (Monroe-Molecular-Simulation-Group/vae-mol-sim) is pure Python over TensorFlow /
+ * TensorFlow-Probability and has no FFI of its own.  The seam this library plugs into is the set of
+ * object protocols its layers return and its losses / models / MCMC driver consume (Bijector,
+ * Distribution, Tensor-with-.numpy()).  Each entry point below names the reference call site whose
+ * arithmetic it replaces (paths are relative to the reference root, `vaemolsim/...`).
+ *
+ * Conventions
+ *   - every pointer marked "device" is CUDA device memory owned by the caller; the library never frees or
+ *     retains a caller pointer past the call (plans own only what they allocate themselves);
+ *   - row-major, float32 unless stated; `ld_*` are leading dimensions (row strides) in elements;
+ *   - all compute entry points are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream); launch errors are returned synchronously, execution errors at the next sync;
+ *   - return value: 0 = OK, >0 = vms_status code; `vms_last_error()` gives a thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns VMS_ERR_CUDA.
+ */
+#ifndef VMS_B200_H
+#define VMS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int vms_status;
+enum {
+  VMS_OK = 0,
+  VMS_ERR_INVALID_ARG = 1, /* Python host maps to ValueError */
+  VMS_ERR_SHAPE = 2,       /* ValueError */
+  VMS_ERR_CUDA = 3,        /* RuntimeError */
+  VMS_ERR_NCCL = 4,        /* RuntimeError */
+  VMS_ERR_UNSUPPORTED = 5  /* NotImplementedError */
+};
+
+typedef void* vms_stream; /* cudaStream_t */
+typedef void* vms_event;  /* cudaEvent_t  */
+
+/* ------------------------------------------------------------------------------------------------ runtime */
+const char* vms_last_error(void);
+int vms_abi_version(void);
+vms_status vms_device_count(int* count);
+vms_status vms_set_device(int device);
+/* out[0]=SM count, out[1]=cc major, out[2]=cc minor, out[3]=max opt-in smem/block (bytes), out[4]=L2 bytes */
+vms_status vms_device_info(int device, int64_t out[5]);
+vms_status vms_malloc(void** device_ptr, size_t bytes);
+vms_status vms_free(void* device_ptr);
+vms_status vms_malloc_host(void** pinned_ptr, size_t bytes);
+vms_status vms_free_host(void* pinned_ptr);
+vms_status vms_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes, vms_stream stream);
+vms_status vms_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes, vms_stream stream);
+vms_status vms_memcpy_d2d(void* dst_device, const void* src_device, size_t bytes, vms_stream stream);
+/* strided 2-D copy (rows x width_bytes), device to device: column slices of [B, D] tensors */
+vms_status vms_memcpy2d_d2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                            size_t rows, vms_stream stream);
+vms_status vms_memset(void* device_ptr, int value, size_t bytes, vms_stream stream);
+vms_status vms_stream_create(vms_stream* stream);
+vms_status vms_stream_destroy(vms_stream stream);
+vms_status vms_stream_synchronize(vms_stream stream);
+vms_status vms_device_synchronize(void);
+vms_status vms_event_create(vms_event* ev);
+vms_status vms_event_destroy(vms_event ev);
+vms_status vms_event_record(vms_event ev, vms_stream stream);
+vms_status vms_event_synchronize(vms_event ev);
+vms_status vms_event_elapsed_ms(vms_event start, vms_event stop, float* ms);
+/* counts kernels launched by this library in this process (bench.py's `gpu_launches`) */
+unsigned long long vms_launch_count(void);
+
+/* ------------------------------------------------------------------------------------- K1: RQS bijector
+ * Replaces  flows.py:86-101 (`SplineBijector._bin_positions/_slopes` activations), flows.py:394-409 (same for
+ * `MaskedSplineBijector`) and the `tfp.bijectors.RationalQuadraticSpline(bin_widths, bin_heights, knot_slopes,
+ * range_min)` object built at flows.py:204-207 / :512-515: its `_forward`, `_inverse` and
+ * `_forward_log_det_jacobian` (ildj = -fldj(inverse)).  Activations are fused: inputs are the RAW Dense / MADE
+ * outputs.  One "element" = one transformed scalar with its K + K + (K-1) raw logits.
+ *
+ * Contiguous form (the op boundary of SURVEY 8b):  x [n_elem], raw_w/raw_h [n_elem, K], raw_s [n_elem, K-1],
+ * y [n_elem], ldj [n_elem] (nullable).  2 <= K <= 64.
+ */
+vms_status vms_rqs_forward(const float* x, const float* raw_w, const float* raw_h, const float* raw_s,
+                           int64_t n_elem, int K, float bin_min, float bin_max, float* y, float* ldj,
+                           vms_stream stream);
+vms_status vms_rqs_inverse(const float* y, const float* raw_w, const float* raw_h, const float* raw_s,
+                           int64_t n_elem, int K, float bin_min, float bin_max, float* x, float* ldj,
+                           vms_stream stream);
+/* Reverse mode of the two ops above.  `inverse_dir` selects which op is differentiated.
+ * v_in is that op's input (x for forward, y for inverse); g_out / g_ldj are upstream gradients of its two
+ * outputs (g_ldj nullable = 0).  Outputs: g_in [n_elem], g_raw_w/h [n_elem,K], g_raw_s [n_elem,K-1].
+ * tf.where semantics out of range: g_in = g_out, parameter gradients 0. */
+vms_status vms_rqs_backward(const float* v_in, const float* raw_w, const float* raw_h, const float* raw_s,
+                            int64_t n_elem, int K, float bin_min, float bin_max, int inverse_dir,
+                            const float* g_out, const float* g_ldj, float* g_in, float* g_raw_w, float* g_raw_h,
+                            float* g_raw_s, vms_stream stream);
+
+/* Strided form used by the coupling layers (flows.py:312 RealNVP, :628-637 MAF): rows of a [B, D] tensor,
+ * `n_dims` transformed columns starting at v_in / v_out, raw logits as [B, n_dims*K] row blocks inside wider
+ * buffers (e.g. the fused [w|h|s] output of one conditioner GEMM).  ldj_sum [B] (nullable) receives the
+ * event-summed log-det (`event_ndims=1`), added to the existing value when accumulate != 0. */
+typedef struct {
+  int64_t n_rows;
+  int32_t n_dims;
+  int32_t num_bins;
+  float bin_min, bin_max;
+  const float* v_in;   int64_t ld_in;
+  const float* raw_w;  int64_t ld_w;
+  const float* raw_h;  int64_t ld_h;
+  const float* raw_s;  int64_t ld_s;
+  float* v_out;        int64_t ld_out;
+  float* ldj;          /* [n_rows, n_dims] contiguous, nullable */
+  float* ldj_sum;      /* [n_rows], nullable */
+  int32_t accumulate;  /* ldj_sum += instead of = */
+  int32_t inverse_dir; /* 0: forward + fldj, 1: inverse + ildj */
+} vms_rqs_args;
+vms_status vms_rqs_apply(const vms_rqs_args* args, vms_stream stream);
+
+typedef struct {
+  vms_rqs_args fwd;       /* same geometry / inputs as the forward call being differentiated (outputs unused) */
+  const float* g_out;  int64_t ld_g_out;  /* upstream grad of v_out */
+  const float* g_ldj_sum;                 /* [n_rows] upstream grad of the event-summed ldj, nullable */
+  float* g_in;         int64_t ld_g_in;
+  float* g_raw_w;      int64_t ld_gw;
+  float* g_raw_h;      int64_t ld_gh;
+  float* g_raw_s;      int64_t ld_gs;
+} vms_rqs_bwd_args;
+vms_status vms_rqs_apply_backward(const vms_rqs_bwd_args* args, vms_stream stream);
+
+/* --------------------------------------------------------------------------------- K2/K3: dense layers
+ * Replaces Keras Dense at mappings.py:107-121 (`FCDeepNN.build`), flows.py:136-152 (`SplineBijector` nets) and
+ * the pre-masked Dense layers of `tfp.bijectors.AutoregressiveNetwork` (flows.py:454-487, dists.py:301-305;
+ * masks are baked into W by the host exactly as TFP's masked initializer + constraint do).
+ *   out[B,N] = act( x[B,K] @ W[K,N] + b[N] (+ cond[B,C] @ Wc[C,N]) )      act: 0 none, 1 relu, 2 tanh
+ * `ones_input` != 0 replaces x by ones([B,1]) (flows.py:184-185: empty RealNVP conditioner input).          */
+enum { VMS_ACT_NONE = 0, VMS_ACT_RELU = 1, VMS_ACT_TANH = 2 };
+vms_status vms_dense_forward(const float* x, int64_t ld_x, const float* W, const float* b, int64_t B, int K,
+                             int N, int act, const float* cond, int64_t ld_c, const float* Wc, int C,
+                             float* out, int64_t ld_out, vms_stream stream);
+/* Reverse mode.  g_out is the gradient w.r.t. the layer OUTPUT (post-activation); `out` is the saved output
+ * (needed for relu / tanh; may be NULL for act none).  Any of g_x, g_W, g_b, g_cond, g_Wc may be NULL.
+ * g_W / g_b / g_Wc are ACCUMULATED (+=) when accumulate != 0, else overwritten; g_x likewise via accumulate_x.
+ * workspace: device scratch of at least vms_dense_backward_workspace(B, K, N, C) bytes.                      */
+size_t vms_dense_backward_workspace(int64_t B, int K, int N, int C);
+vms_status vms_dense_backward(const float* x, int64_t ld_x, const float* W, int64_t B, int K, int N, int act,
+                              const float* out, int64_t ld_out, const float* g_out, int64_t ld_g,
+                              const float* cond, int64_t ld_c, const float* Wc, int C, float* g_x, int64_t ld_gx,
+                              int accumulate_x, float* g_W, float* g_b, float* g_cond, int64_t ld_gc, float* g_Wc,
+                              int accumulate, void* workspace, vms_stream stream);
+/* mappings.py:144-149: out = concat([x[:, ~periodic], cos(x[:, periodic]), sin(x[:, periodic])]).
+ * periodic: device uint8 [D].  out is [B, D + n_periodic]. */
+vms_status vms_periodic_featurise(const float* x, int64_t B, int D, const uint8_t* periodic, float* out,
+                                  vms_stream stream);
+
+/* --------------------------------------------------------------------------- K4: distributions (log_prob)
+ * kinds per degree of freedom (dists.py:164-173): */
+enum { VMS_DIST_NORMAL = 0, VMS_DIST_VONMISES = 1 };
+/* scale / concentration transform applied to the raw parameter */
+enum {
+  VMS_SCALE_IDENTITY = 0,     /* parameter already constrained */
+  VMS_SCALE_SOFTPLUS = 1,     /* tfp.layers.IndependentNormal (tests/test_models.py:167-170); dists.py:607 */
+  VMS_SCALE_SOFTPLUS_EPS = 2  /* parameter_properties bijector Softplus(low=eps32): dists.py:56-78 */
+};
+/* Generic blockwise log_prob -- replaces `IndependentBlockwise.call` dists.py:210-217 + `tfp.distributions.Blockwise.
+ * log_prob`, `IndependentVonMises.new` dists.py:602-610, tfp.layers.IndependentNormal, and the per-dof distributions
+ * built inside `AutoregressiveBlockwise.call` dists.py:326-336.
+ *   x [B, D] (ld_x); params [B, ld_p]; for dof i: kind[i], column offsets loc_off[i] (Normal loc, or von Mises
+ *   sine), loc2_off[i] (von Mises cosine; ignored for Normal), scale_off[i]; loc = p[loc_off] or atan2(p[loc_off],
+ *   p[loc2_off]).  lp[B] = sum_i log_prob_i  (added to the existing value if accumulate).
+ * The four int arrays are HOST pointers (D <= 64), copied into kernel arguments.                               */
+vms_status vms_blockwise_log_prob(const float* x, int64_t ld_x, const float* params, int64_t ld_p, int64_t B, int D,
+                                  const int32_t* kind, const int32_t* loc_off, const int32_t* loc2_off,
+                                  const int32_t* scale_off, int scale_mode, float* lp, int accumulate,
+                                  vms_stream stream);
+/* The constrained parameters themselves (`make_param_transform`, dists.py:28-87): loc [B, D], scale [B, D].
+ * A von Mises dof with loc2_off[i] < 0 (or loc2_off NULL) takes loc = p[loc_off[i]] directly (no atan2).         */
+vms_status vms_blockwise_params(const float* params, int64_t ld_p, int64_t B, int D, const int32_t* kind,
+                                const int32_t* loc_off, const int32_t* loc2_off, const int32_t* scale_off,
+                                int scale_mode, float* loc, float* scale, vms_stream stream);
+/* Standard-normal base density used by every flowed prior in the reference's tests / notebooks
+ * (tests/test_models.py:172-175): lp[B] (+)= sum_d -0.5 x^2 - 0.5 log 2pi.                                     */
+vms_status vms_std_normal_log_prob(const float* x, int64_t ld_x, int64_t B, int D, float* lp, int accumulate,
+                                   vms_stream stream);
+/* Reparameterised Normal sample + log_prob in one pass (models.py:310 `encode_dist.sample()`, mcmc.py:100
+ * `experimental_sample_and_log_prob`): params [B, ld_p] with loc at column loc_off + d, raw scale at scale_off + d;
+ * z = eps * scale + loc (TFP Normal._sample_n);  lp = log N(z; loc, scale) summed over D.  z, lp nullable.       */
+vms_status vms_normal_sample_log_prob(const float* params, int64_t ld_p, int loc_off, int scale_off, int scale_mode,
+                                      const float* eps, int64_t B, int D, float* z, int64_t ld_z, float* lp,
+                                      vms_stream stream);
+/* Reverse mode of sum_d log N(x_d; loc_d, scale(raw_d)) for Normal dofs with per-row upstream g_lp [B]:
+ *   g_x (nullable, += if accumulate_x), g_params [B, ld_gp] written at loc_off/scale_off columns (overwritten).
+ * Replaces TF autodiff through `Normal._log_prob`.                                                              */
+vms_status vms_normal_log_prob_backward(const float* x, int64_t ld_x, const float* params, int64_t ld_p, int loc_off,
+                                        int scale_off, int scale_mode, const float* g_lp, int64_t B, int D,
+                                        float* g_x, int64_t ld_gx, int accumulate_x, float* g_params, int64_t ld_gp,
+                                        vms_stream stream);
+
+/* ------------------------------------------------------------------------------- K5: ELBO / KL reductions
+ * losses.py:253 `KLDivergenceEstimate.call` (weight applied as in `InfoRegularizer.__call__` :174-194):
+ *   out[0] = weight * mean_B(lq - lp).   lp_b NULL => out = weight * mean(lq)  (LogProbRegularizer :296 uses
+ *   sign = -1).  Deterministic (fixed-order two-level reduction).                                               */
+vms_status vms_kl_mean(const float* lq, const float* lp, int64_t B, float weight, float* out, vms_stream stream);
+/* losses.py:58 `LogProbLoss.call` + Keras mean reduction: out[0] = scale * mean_B(v) (scale = -1 for the NLL).  */
+vms_status vms_scaled_mean(const float* v, int64_t B, float scale, float* out, vms_stream stream);
+/* out = a*x + b*y elementwise (y nullable); the `+` of mcmc.py:103,109 on device tensors.                      */
+vms_status vms_axpby(const float* x, const float* y, float a, float b, int64_t n, float* out, vms_stream stream);
+
+/* Column-wise affine map of tfp.bijectors.Shift / Scale (flows.py:53-58, `make_domain_transform`):
+ *   shift_first == 0: out[b,d] = x[b,d] * scale[d] + shift[d];   shift_first != 0: out = (x + shift) * scale.
+ * scale / shift are device float32 [D]; either may be NULL (1 / 0).                                             */
+vms_status vms_affine_cols(const float* x, int64_t ld_x, int64_t B, int D, const float* scale, const float* shift,
+                           int shift_first, float* out, int64_t ld_out, vms_stream stream);
+
+/* ------------------------------------------------------------------------------- K6: DistanceSelection
+ * Replaces `DistanceSelection.call` mappings.py:362-455 (TF sub / div / round / mul / reduce_sum / top_k / gather):
+ *   local = coords - ref;  if box: local -= box * rint(local / box);  d2 = (lx^2 + ly^2) + lz^2 (no FMA);
+ *   the k = max_included smallest d2 (ties -> lower index), sorted ascending;  rows with d2 > cutoff^2 zeroed.
+ * coords: dense [B, N, 3] (row_splits NULL) or ragged values [sum N_i, 3] with row_splits int64 [B+1] (device).
+ * ref [B, 3]; box: NULL, [3] (box_per_row = 0) or [B, 3] (box_per_row = 1); info [B, N, P] / ragged [sum N_i, P]
+ * (nullable).  Outputs out_xyz [B, k, 3], out_info [B, k, P] (nullable), out_idx int32 [B, k] (nullable; exact
+ * top-k indices including beyond-cutoff and padding slots, as tf.math.top_k would return them).
+ * Rows shorter than k behave as if padded with float32.max coordinates (mappings.py:417-426).                  */
+vms_status vms_dist_select(const float* coords, const int64_t* row_splits, int64_t B, int64_t N, const float* ref,
+                           const float* box, int box_per_row, float cutoff_sq, int k, const float* info, int P,
+                           float* out_xyz, float* out_info, int32_t* out_idx, vms_stream stream);
+
+/* ------------------------------------------------------------------------------- K7: MC acceptance
+ * Replaces mcmc.py:116-128:  log_acc = E_new + rev - E_old - fwd (float64; log-probs float32 promoted);
+ * acc = log_acc >= log_u;  rejected rows restore x_old / E_old.  x_new_inout [B, D] is overwritten in place,
+ * E_out [B] receives the selected energies, acc [B] uint8 (nullable), n_acc += number accepted (device u64).   */
+vms_status vms_mc_accept(const double* E_new, const double* E_old, const float* fwd, const float* rev,
+                         const double* log_u, int64_t B, int D, const float* x_old, float* x_new_inout,
+                         double* E_out, uint8_t* acc, unsigned long long* n_acc, vms_stream stream);
+/* Device-resident energies so the MC loop is not PCIe-bound (SURVEY 7 "hard parts"):
+ *   kind 0: tests/test_mcmc.py:28-32  E = sum_d (x_d - means_d)^2, evaluated in float64 like the NumPy callback. */
+vms_status vms_energy_quadratic(const float* x, int64_t B, int D, const double* means, double* E, vms_stream stream);
+
+/* ------------------------------------------------------------------------------- K8: optimiser
+ * Keras Adam (tests/test_models.py:181: lr 1e-3, beta 0.9 / 0.999, eps 1e-7), on a flat parameter buffer:
+ *   lr_t = lr sqrt(1 - b2^t) / (1 - b1^t);  m += (g - m)(1 - b1);  v += (g^2 - v)(1 - b2);
+ *   theta -= lr_t m / (sqrt(v) + eps).   `grad_scale` multiplies g first (1/world_size after an allreduce-sum).
+ * g may be a stack of `n_partials` partial gradients [n_partials, n] that are summed in fixed order first.      */
+vms_status vms_adam_step(float* theta, const float* g, int n_partials, float grad_scale, float* m, float* v,
+                         int64_t n, int64_t t, double lr, double beta1, double beta2, double eps, vms_stream stream);
+vms_status vms_sum_partials(const float* g, int n_partials, int64_t n, float scale, float* out, vms_stream stream);
+
+/* ------------------------------------------------------------------------------- fused ELBO step (C1 / C2)
+ * One handle = one VAE of the family used by the reference's tests (tests/test_models.py:161-228):
+ *   encoder  FCDeepNN dx -> hidden(relu) -> 2 dz  + tfp.layers.IndependentNormal(dz)
+ *   prior    N(0, I)  (num_blocks = 0)  or  FlowedDistribution(RQSSplineRealNVP(num_blocks, K, flow_hidden), N(0,I))
+ *   decoder  FCDeepNN dz -> hidden(relu) -> 2 dx  + tfp.layers.IndependentNormal(dx)
+ *   loss     LogProbLoss (mean) + weight * KLDivergenceEstimate          (models.py:289-322, losses.py:58,:253)
+ * Parameters live in ONE flat float32 device buffer owned by the caller, in the order
+ *   enc.0.W enc.0.b enc.1.W enc.1.b dec.0.W dec.0.b dec.1.W dec.1.b  then per flow block: d1.W d1.b heads.W heads.b
+ * (all W row-major [in, out], the Keras layout).  heads.W [flow_hidden, Dt*(3K-1)] is the column-wise concatenation
+ * [bin_widths.W | bin_heights.W | knot_slopes.W] of the three Dense heads of flows.py:140-152 (heads.b likewise), so
+ * one GEMM produces a block's raw spline parameters; the Python host converts from / to per-layer Keras arrays.   */
+typedef struct {
+  int32_t dx, dz, hidden;
+  int32_t num_blocks, num_bins, flow_hidden; /* num_blocks = 0 => N(0, I) prior */
+  float bin_min, bin_max;
+  float kl_weight;
+  int64_t max_batch;
+} vms_elbo_desc;
+typedef struct vms_elbo_plan_s* vms_elbo_plan;
+vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan);
+vms_status vms_elbo_plan_destroy(vms_elbo_plan plan);
+int64_t vms_elbo_param_count(const vms_elbo_desc* desc);
+/* Forward only.  x [B, dx], eps [B, dz] (the reparameterisation noise is an INPUT in parity mode).  Outputs (any
+ * nullable): z [B, dz], logq [B], logpz [B], logpx [B], scalars[3] = {loss, nll, kl} (kl unweighted mean).      */
+vms_status vms_elbo_forward(vms_elbo_plan plan, const float* theta, const float* x, const float* eps, int64_t B,
+                            float* z, float* logq, float* logpz, float* logpx, float* scalars, vms_stream stream);
+/* Forward + backward: additionally writes the flat gradient of `loss` w.r.t. theta into grad [param_count].     */
+vms_status vms_elbo_forward_backward(vms_elbo_plan plan, const float* theta, const float* x, const float* eps,
+                                     int64_t B, float* grad, float* scalars, vms_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMS_B200_H */

@@ -1,0 +1,481 @@
+// elbo.cu -- whole-VAE ELBO forward / forward+backward for the model family of the reference's tests (C1 / C2).
+//
+// Replaces the Python/TF orchestration of
+//   models.py:289-322  VAE.call   (encoder -> sample -> prior -> regulariser -> decoder)
+//   models.py:206-229  MappingToDistribution.call (FCDeepNN + distribution layer)
+//   dists.py:414-439   FlowedDistribution.call + tfp TransformedDistribution.log_prob
+//   flows.py:281-355   RQSSplineRealNVP (chain of RealNVP blocks, density direction = chain inverse)
+//   losses.py:58, :253 LogProbLoss (batch mean) and KLDivergenceEstimate
+// and TF autodiff (GradientTape) through all of it.
+//
+// The plan owns every intermediate (activations kept for the backward pass, split-K gradient partials) in HBM --
+// sized once for max_batch -- and replays the whole step as ONE CUDA graph per (batch, pointer set): the step is
+// ~60 small kernels whose launch overhead would otherwise dominate at the named batch of 4096.
+#include "dense.cuh"
+#include <math.h>
+#include <vector>
+#include <map>
+#include <array>
+
+namespace vms {
+
+vms_status rqs_prepare();  // rqs.cu
+
+struct FlowBlock {
+  int cs0, cs1, ts0, ts1;  // conditioner / transformed column ranges (flows.py:290-306 + tfp RealNVP reverse mask)
+  int cin, dt, ldr;        // conditioner input width (>=1: ones input when empty), transformed dims, raw row width
+  int64_t off_d1W, off_d1b, off_hW, off_hb;
+};
+
+struct Offsets {
+  int64_t enc0W, enc0b, enc1W, enc1b, dec0W, dec0b, dec1W, dec1b, total;
+};
+
+static void realnvp_split(int i, int D, int& cs0, int& cs1, int& ts0, int& ts1) {
+  if (D == 1) { cs0 = cs1 = 0; ts0 = 0; ts1 = 1; return; }
+  if (i % 2 == 0) { int m = D / 2; cs0 = 0; cs1 = m; ts0 = m; ts1 = D; return; }
+  int m = D - D / 2;
+  cs0 = D - m; cs1 = D; ts0 = 0; ts1 = D - m;
+}
+
+static Offsets layout(const vms_elbo_desc& d, std::vector<FlowBlock>* blocks) {
+  Offsets o;
+  int64_t p = 0;
+  o.enc0W = p; p += (int64_t)d.dx * d.hidden;
+  o.enc0b = p; p += d.hidden;
+  o.enc1W = p; p += (int64_t)d.hidden * 2 * d.dz;
+  o.enc1b = p; p += 2 * d.dz;
+  o.dec0W = p; p += (int64_t)d.dz * d.hidden;
+  o.dec0b = p; p += d.hidden;
+  o.dec1W = p; p += (int64_t)d.hidden * 2 * d.dx;
+  o.dec1b = p; p += 2 * d.dx;
+  for (int i = 0; i < d.num_blocks; ++i) {
+    FlowBlock b;
+    realnvp_split(i, d.dz, b.cs0, b.cs1, b.ts0, b.ts1);
+    b.cin = b.cs1 - b.cs0 > 0 ? b.cs1 - b.cs0 : 1;
+    b.dt = b.ts1 - b.ts0;
+    b.ldr = b.dt * (3 * d.num_bins - 1);
+    b.off_d1W = p; p += (int64_t)b.cin * d.flow_hidden;
+    b.off_d1b = p; p += d.flow_hidden;
+    b.off_hW = p; p += (int64_t)d.flow_hidden * b.ldr;
+    b.off_hb = p; p += b.ldr;
+    if (blocks) blocks->push_back(b);
+  }
+  o.total = p;
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// scalars[0] = loss = nll + w kl, [1] = nll = mean(-logpx), [2] = kl = mean(logq - logpz); fixed-order reduction
+__global__ void __launch_bounds__(256) elbo_partial_kernel(const float* __restrict__ logq, const float* __restrict__ logpz,
+                                                           const float* __restrict__ logpx, int64_t B,
+                                                           float* __restrict__ partial) {
+  __shared__ float sh[2][8];
+  const int64_t beg = (int64_t)blockIdx.x * 8192, end = min(B, beg + 8192);
+  float a = 0.f, c = 0.f;
+  for (int64_t i = beg + threadIdx.x; i < end; i += 256) {
+    a += logq[i] - logpz[i];
+    c += -logpx[i];
+  }
+  a = warp_sum(a);
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sa = 0.f, sc = 0.f;
+    for (int w = 0; w < 8; ++w) { sa += sh[0][w]; sc += sh[1][w]; }
+    partial[2 * blockIdx.x] = sa;
+    partial[2 * blockIdx.x + 1] = sc;
+  }
+}
+__global__ void elbo_final_kernel(const float* __restrict__ partial, int nb, int64_t B, float w, float* scalars) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float sa = 0.f, sc = 0.f;
+  for (int i = 0; i < nb; ++i) { sa += partial[2 * i]; sc += partial[2 * i + 1]; }
+  const float kl = sa / (float)B, nll = sc / (float)B;
+  scalars[0] = nll + w * kl;
+  scalars[1] = nll;
+  scalars[2] = kl;
+}
+
+// dst[b, c] (+)= a * src[b, c] over a column block
+__global__ void axpy2d_kernel(const float* __restrict__ src, int64_t ld_s, float a, float* dst, int64_t ld_d, int64_t B,
+                              int cols, int accumulate) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * cols) return;
+  const int64_t b = i / cols;
+  const int c = (int)(i - b * cols);
+  const float v = a * src[b * ld_s + c];
+  float* d = dst + b * ld_d + c;
+  *d = accumulate ? *d + v : v;
+}
+__global__ void fill_kernel(float* p, float v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// decoder head: d/d params of g * sum_d log N(x_d; loc_d, softplus(raw_d)), params = [loc | raw]
+__global__ void decoder_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pd, int64_t B, int D,
+                                        float g, float* __restrict__ g_pd) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int64_t b = i / D;
+  const int d = (int)(i - b * D);
+  const float loc = pd[b * 2 * D + d], raw = pd[b * 2 * D + D + d];
+  const float sc = softplus_tf(raw);
+  const float u = x[i] / sc - loc / sc;
+  g_pd[b * 2 * D + d] = g * (u / sc);
+  g_pd[b * 2 * D + D + d] = g * ((u * u - 1.f) / sc) * sigmoidf_(raw);
+}
+
+// encoder head: log q(z|x) terms (explicit z path + parameter path) and the reparameterisation z = eps * s + loc.
+// g_z holds d loss / d z from decoder + prior on entry.
+__global__ void encoder_head_bwd_kernel(const float* __restrict__ z, const float* __restrict__ pe,
+                                        const float* __restrict__ eps, const float* __restrict__ g_z, int64_t B, int D,
+                                        float gq, float* __restrict__ g_pe) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int64_t b = i / D;
+  const int d = (int)(i - b * D);
+  const float loc = pe[b * 2 * D + d], raw = pe[b * 2 * D + D + d];
+  const float sc = softplus_tf(raw);
+  const float u = z[i] / sc - loc / sc;
+  const float gz = g_z[i] + gq * (-u / sc);
+  g_pe[b * 2 * D + d] = gq * (u / sc) + gz;
+  g_pe[b * 2 * D + D + d] = (gq * ((u * u - 1.f) / sc) + gz * eps[i]) * sigmoidf_(raw);
+}
+
+}  // namespace vms
+
+using namespace vms;
+
+struct vms_elbo_plan_s {
+  vms_elbo_desc d;
+  Offsets off;
+  std::vector<FlowBlock> blocks;
+  int64_t maxB;
+  int splits_max;
+  // forward intermediates
+  float *he, *pe, *z, *logq, *logpz, *logpx, *hd, *pd, *scalars, *partial;
+  std::vector<float*> u;    // u[i], i = 0..num_blocks: chain-inverse states, u[num_blocks] = z, u[0] = base sample
+  std::vector<float*> hid;  // [B, flow_hidden] per block
+  std::vector<float*> raw;  // [B, ldr] per block
+  // backward scratch
+  float *g_pd, *g_hd, *g_z, *g_pe, *g_he, *g_ua, *g_ub, *g_raw, *g_hid, *g_ldj, *gpart;
+  std::vector<void*> allocs;
+  // graph cache: key = (mode, B, theta, x, eps, out pointers...)
+  std::map<std::array<uintptr_t, 10>, std::pair<cudaGraphExec_t, int>> graphs;
+};
+
+namespace {
+
+vms_status alloc(vms_elbo_plan_s* pl, float** p, size_t n_floats) {
+  void* v = nullptr;
+  VMS_CUDA(cudaMalloc(&v, (n_floats ? n_floats : 4) * sizeof(float)));
+  pl->allocs.push_back(v);
+  *p = (float*)v;
+  return VMS_OK;
+}
+
+vms_status dense_fwd(const float* x, int64_t ldx, const float* W, const float* b, int64_t B, int K, int N, int act,
+                     float* out, int64_t ldo, cudaStream_t st) {
+  return vms_dense_forward(x, ldx, W, b, B, K, N, act, nullptr, 0, nullptr, 0, out, ldo, (vms_stream)st);
+}
+
+// weight + bias gradient partials of one Dense layer written straight into the flat partial-gradient stack:
+// [W; b] is a contiguous [K+1, N] block at `off` (the Keras "kernel then bias" order).
+vms_status dense_wgrad(vms_elbo_plan_s* pl, const float* x, int64_t ldx, int64_t B, int K, int N, int act,
+                       const float* out, int64_t ldo, const float* g_out, int64_t ldg, int64_t off, int splits,
+                       cudaStream_t st) {
+  GemmParams p = {};
+  p.M = K + 1; p.N = N; p.K = (int)B;
+  p.A = x; p.lda = ldx; p.ta = 1; p.a_ones = (x == nullptr); p.a_ones_row = K;
+  p.Bm = g_out; p.ldb = ldg; p.Bo = out; p.ldbo = ldo; p.b_act = act;
+  p.C = pl->gpart + off; p.ldc = N;
+  p.k_per_split = (int)((B + splits - 1) / splits);
+  p.split_stride = pl->off.total;
+  return gemm_launch(p, splits, st);
+}
+vms_status dense_xgrad(const float* W, int64_t B, int K, int N, int act, const float* out, int64_t ldo,
+                       const float* g_out, int64_t ldg, float* g_x, int64_t ldgx, int accumulate, cudaStream_t st) {
+  GemmParams p = {};
+  p.M = (int)B; p.N = K; p.K = N;
+  p.A = g_out; p.lda = ldg; p.Ao = out; p.ldao = ldo; p.a_act = act; p.a_ones_row = -1;
+  p.Bm = W; p.ldb = N; p.tb = 1;
+  p.C = g_x; p.ldc = ldgx; p.accumulate = accumulate;
+  return gemm_launch(p, 0, st);
+}
+
+#define VMS_TRY(expr)          \
+  do {                         \
+    vms_status _s = (expr);    \
+    if (_s) return _s;         \
+  } while (0)
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+vms_status forward_body(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B,
+                        float* scalars, cudaStream_t st) {
+  const vms_elbo_desc& d = pl->d;
+  const Offsets& o = pl->off;
+  const int nb = d.num_blocks;
+  // encoder: FCDeepNN dx -> H (relu) -> 2 dz ; IndependentNormal: loc | softplus(raw)
+  VMS_TRY(dense_fwd(x, d.dx, theta + o.enc0W, theta + o.enc0b, B, d.dx, d.hidden, VMS_ACT_RELU, pl->he, d.hidden, st));
+  VMS_TRY(dense_fwd(pl->he, d.hidden, theta + o.enc1W, theta + o.enc1b, B, d.hidden, 2 * d.dz, VMS_ACT_NONE, pl->pe,
+                    2 * d.dz, st));
+  float* zbuf = pl->u[nb];
+  VMS_TRY(vms_normal_sample_log_prob(pl->pe, 2 * d.dz, 0, d.dz, VMS_SCALE_SOFTPLUS, eps, B, d.dz, zbuf, d.dz, pl->logq,
+                                     (vms_stream)st));
+  // prior log p(z): chain inverse, block n-1 first (flows.py:323 reverses the list for tfp Chain)
+  for (int i = nb - 1; i >= 0; --i) {
+    const FlowBlock& fb = pl->blocks[i];
+    const float* uin = pl->u[i + 1];
+    float* uout = pl->u[i];
+    const float* cond = fb.cs1 > fb.cs0 ? uin + fb.cs0 : nullptr;  // NULL => ones((B,1)) (flows.py:184-185)
+    VMS_TRY(dense_fwd(cond, d.dz, theta + fb.off_d1W, theta + fb.off_d1b, B, fb.cin, d.flow_hidden, VMS_ACT_TANH,
+                      pl->hid[i], d.flow_hidden, st));
+    VMS_TRY(dense_fwd(pl->hid[i], d.flow_hidden, theta + fb.off_hW, theta + fb.off_hb, B, d.flow_hidden, fb.ldr,
+                      VMS_ACT_NONE, pl->raw[i], fb.ldr, st));
+    if (fb.cs1 > fb.cs0)
+      VMS_CUDA(cudaMemcpy2DAsync(uout + fb.cs0, d.dz * sizeof(float), uin + fb.cs0, d.dz * sizeof(float),
+                                 (fb.cs1 - fb.cs0) * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    vms_rqs_args a = {};
+    a.n_rows = B; a.n_dims = fb.dt; a.num_bins = d.num_bins; a.bin_min = d.bin_min; a.bin_max = d.bin_max;
+    a.v_in = uin + fb.ts0; a.ld_in = d.dz;
+    a.raw_w = pl->raw[i]; a.ld_w = fb.ldr;
+    a.raw_h = pl->raw[i] + fb.dt * d.num_bins; a.ld_h = fb.ldr;
+    a.raw_s = pl->raw[i] + 2 * fb.dt * d.num_bins; a.ld_s = fb.ldr;
+    a.v_out = uout + fb.ts0; a.ld_out = d.dz;
+    a.ldj = nullptr; a.ldj_sum = pl->logpz; a.accumulate = (i != nb - 1); a.inverse_dir = 1;
+    VMS_TRY(vms_rqs_apply(&a, (vms_stream)st));
+  }
+  VMS_TRY(vms_std_normal_log_prob(pl->u[0], d.dz, B, d.dz, pl->logpz, nb > 0, (vms_stream)st));
+  // decoder
+  VMS_TRY(dense_fwd(zbuf, d.dz, theta + o.dec0W, theta + o.dec0b, B, d.dz, d.hidden, VMS_ACT_RELU, pl->hd, d.hidden, st));
+  VMS_TRY(dense_fwd(pl->hd, d.hidden, theta + o.dec1W, theta + o.dec1b, B, d.hidden, 2 * d.dx, VMS_ACT_NONE, pl->pd,
+                    2 * d.dx, st));
+  {
+    int32_t kind[64], loc[64], sc[64];
+    for (int j = 0; j < d.dx; ++j) { kind[j] = VMS_DIST_NORMAL; loc[j] = j; sc[j] = d.dx + j; }
+    VMS_TRY(vms_blockwise_log_prob(x, d.dx, pl->pd, 2 * d.dx, B, d.dx, kind, loc, nullptr, sc, VMS_SCALE_SOFTPLUS,
+                                   pl->logpx, 0, (vms_stream)st));
+  }
+  const int nbk = (int)((B + 8191) / 8192);
+  elbo_partial_kernel<<<nbk, 256, 0, st>>>(pl->logq, pl->logpz, pl->logpx, B, pl->partial);
+  VMS_LAUNCH_CHECK("elbo_partial_kernel");
+  elbo_final_kernel<<<1, 32, 0, st>>>(pl->partial, nbk, B, d.kl_weight, scalars ? scalars : pl->scalars);
+  VMS_LAUNCH_CHECK("elbo_final_kernel");
+  return VMS_OK;
+}
+
+vms_status backward_body(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B,
+                         float* grad, cudaStream_t st) {
+  const vms_elbo_desc& d = pl->d;
+  const Offsets& o = pl->off;
+  const int nb = d.num_blocks;
+  const int splits = dense_splits(B);
+  const float invB = 1.0f / (float)B;
+  const float g_logpx = -invB, g_logq = d.kl_weight * invB, g_logpz = -d.kl_weight * invB;
+  const float* z = pl->u[nb];
+  // decoder head and MLP
+  decoder_head_bwd_kernel<<<nblk(B * d.dx, 256), 256, 0, st>>>(x, pl->pd, B, d.dx, g_logpx, pl->g_pd);
+  VMS_LAUNCH_CHECK("decoder_head_bwd_kernel");
+  VMS_TRY(dense_wgrad(pl, pl->hd, d.hidden, B, d.hidden, 2 * d.dx, VMS_ACT_NONE, nullptr, 0, pl->g_pd, 2 * d.dx,
+                      o.dec1W, splits, st));
+  VMS_TRY(dense_xgrad(theta + o.dec1W, B, d.hidden, 2 * d.dx, VMS_ACT_NONE, nullptr, 0, pl->g_pd, 2 * d.dx, pl->g_hd,
+                      d.hidden, 0, st));
+  VMS_TRY(dense_wgrad(pl, z, d.dz, B, d.dz, d.hidden, VMS_ACT_RELU, pl->hd, d.hidden, pl->g_hd, d.hidden, o.dec0W,
+                      splits, st));
+  VMS_TRY(dense_xgrad(theta + o.dec0W, B, d.dz, d.hidden, VMS_ACT_RELU, pl->hd, d.hidden, pl->g_hd, d.hidden, pl->g_z,
+                      d.dz, 0, st));
+  // prior
+  if (nb == 0) {
+    // d/dz [ g_logpz * sum(-0.5 z^2) ] = -g_logpz * z
+    axpy2d_kernel<<<nblk(B * d.dz, 256), 256, 0, st>>>(z, d.dz, -g_logpz, pl->g_z, d.dz, B, d.dz, 1);
+    VMS_LAUNCH_CHECK("axpy2d_kernel");
+  } else {
+    float* g_cur = pl->g_ua;
+    float* g_nxt = pl->g_ub;
+    axpy2d_kernel<<<nblk(B * d.dz, 256), 256, 0, st>>>(pl->u[0], d.dz, -g_logpz, g_cur, d.dz, B, d.dz, 0);
+    VMS_LAUNCH_CHECK("axpy2d_kernel");
+    fill_kernel<<<nblk(B, 256), 256, 0, st>>>(pl->g_ldj, g_logpz, B);
+    VMS_LAUNCH_CHECK("fill_kernel");
+    for (int i = 0; i < nb; ++i) {
+      const FlowBlock& fb = pl->blocks[i];
+      const float* uin = pl->u[i + 1];
+      const int nc = fb.cs1 - fb.cs0;
+      if (nc > 0)
+        VMS_CUDA(cudaMemcpy2DAsync(g_nxt + fb.cs0, d.dz * sizeof(float), g_cur + fb.cs0, d.dz * sizeof(float),
+                                   nc * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+      vms_rqs_bwd_args a = {};
+      a.fwd.n_rows = B; a.fwd.n_dims = fb.dt; a.fwd.num_bins = d.num_bins; a.fwd.bin_min = d.bin_min;
+      a.fwd.bin_max = d.bin_max;
+      a.fwd.v_in = uin + fb.ts0; a.fwd.ld_in = d.dz;
+      a.fwd.raw_w = pl->raw[i]; a.fwd.ld_w = fb.ldr;
+      a.fwd.raw_h = pl->raw[i] + fb.dt * d.num_bins; a.fwd.ld_h = fb.ldr;
+      a.fwd.raw_s = pl->raw[i] + 2 * fb.dt * d.num_bins; a.fwd.ld_s = fb.ldr;
+      a.fwd.inverse_dir = 1;
+      a.g_out = g_cur + fb.ts0; a.ld_g_out = d.dz;
+      a.g_ldj_sum = pl->g_ldj;
+      a.g_in = g_nxt + fb.ts0; a.ld_g_in = d.dz;
+      a.g_raw_w = pl->g_raw; a.ld_gw = fb.ldr;
+      a.g_raw_h = pl->g_raw + fb.dt * d.num_bins; a.ld_gh = fb.ldr;
+      a.g_raw_s = pl->g_raw + 2 * fb.dt * d.num_bins; a.ld_gs = fb.ldr;
+      VMS_TRY(vms_rqs_apply_backward(&a, (vms_stream)st));
+      // heads: raw = hid @ hW + hb
+      VMS_TRY(dense_wgrad(pl, pl->hid[i], d.flow_hidden, B, d.flow_hidden, fb.ldr, VMS_ACT_NONE, nullptr, 0, pl->g_raw,
+                          fb.ldr, fb.off_hW, splits, st));
+      VMS_TRY(dense_xgrad(theta + fb.off_hW, B, d.flow_hidden, fb.ldr, VMS_ACT_NONE, nullptr, 0, pl->g_raw, fb.ldr,
+                          pl->g_hid, d.flow_hidden, 0, st));
+      // d1: hid = tanh(cond @ d1W + d1b)
+      const float* cond = nc > 0 ? uin + fb.cs0 : nullptr;
+      VMS_TRY(dense_wgrad(pl, cond, d.dz, B, fb.cin, d.flow_hidden, VMS_ACT_TANH, pl->hid[i], d.flow_hidden, pl->g_hid,
+                          d.flow_hidden, fb.off_d1W, splits, st));
+      if (nc > 0)
+        VMS_TRY(dense_xgrad(theta + fb.off_d1W, B, fb.cin, d.flow_hidden, VMS_ACT_TANH, pl->hid[i], d.flow_hidden,
+                            pl->g_hid, d.flow_hidden, g_nxt + fb.cs0, d.dz, 1, st));
+      float* t = g_cur; g_cur = g_nxt; g_nxt = t;
+    }
+    axpy2d_kernel<<<nblk(B * d.dz, 256), 256, 0, st>>>(g_cur, d.dz, 1.f, pl->g_z, d.dz, B, d.dz, 1);
+    VMS_LAUNCH_CHECK("axpy2d_kernel");
+  }
+  // encoder head + MLP
+  encoder_head_bwd_kernel<<<nblk(B * d.dz, 256), 256, 0, st>>>(z, pl->pe, eps, pl->g_z, B, d.dz, g_logq, pl->g_pe);
+  VMS_LAUNCH_CHECK("encoder_head_bwd_kernel");
+  VMS_TRY(dense_wgrad(pl, pl->he, d.hidden, B, d.hidden, 2 * d.dz, VMS_ACT_NONE, nullptr, 0, pl->g_pe, 2 * d.dz,
+                      o.enc1W, splits, st));
+  VMS_TRY(dense_xgrad(theta + o.enc1W, B, d.hidden, 2 * d.dz, VMS_ACT_NONE, nullptr, 0, pl->g_pe, 2 * d.dz, pl->g_he,
+                      d.hidden, 0, st));
+  VMS_TRY(dense_wgrad(pl, x, d.dx, B, d.dx, d.hidden, VMS_ACT_RELU, pl->he, d.hidden, pl->g_he, d.hidden, o.enc0W,
+                      splits, st));
+  // flat gradient = fixed-order sum of the split partials
+  VMS_TRY(sum_partials_launch(pl->gpart, splits, o.total, o.total, grad, 0, nullptr, 1.f, 0, st));
+  return VMS_OK;
+}
+
+// Run `body` through a cached CUDA graph when the stream allows capture (non-default stream).
+template <typename F>
+vms_status run_graphed(vms_elbo_plan_s* pl, const std::array<uintptr_t, 10>& key, cudaStream_t st, F body) {
+  if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return body();
+  auto it = pl->graphs.find(key);
+  if (it == pl->graphs.end()) {
+    const unsigned long long before = vms_launch_count();
+    cudaGraph_t g = nullptr;
+    VMS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    vms_status s = body();
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (s) { if (g) cudaGraphDestroy(g); return s; }
+    if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return VMS_ERR_CUDA; }
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(e)); return VMS_ERR_CUDA; }
+    if (pl->graphs.size() >= 16) {  // bounded cache
+      for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.first);
+      pl->graphs.clear();
+    }
+    // kernels recorded during capture did not run: un-count them, and count them per replay instead
+    const int n_kernels = (int)(vms_launch_count() - before);
+    count_launch(-n_kernels);
+    it = pl->graphs.emplace(key, std::make_pair(ex, n_kernels)).first;
+  }
+  VMS_CUDA(cudaGraphLaunch(it->second.first, st));
+  count_launch(it->second.second);
+  return VMS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t vms_elbo_param_count(const vms_elbo_desc* desc) {
+  if (!desc) return -1;
+  return layout(*desc, nullptr).total;
+}
+
+vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan) {
+  VMS_REQUIRE(desc && plan, VMS_ERR_INVALID_ARG, "elbo_plan_create: NULL argument");
+  const vms_elbo_desc& d = *desc;
+  VMS_REQUIRE(d.dx >= 1 && d.dx <= 64 && d.dz >= 1 && d.dz <= 64 && d.hidden >= 1, VMS_ERR_SHAPE,
+              "elbo_plan_create: dx, dz must be in [1, 64] and hidden >= 1");
+  VMS_REQUIRE(d.num_blocks >= 0 && d.max_batch >= 1, VMS_ERR_INVALID_ARG, "elbo_plan_create: bad num_blocks / max_batch");
+  VMS_REQUIRE(d.num_blocks == 0 || (d.num_bins >= 2 && d.num_bins <= 64 && d.flow_hidden >= 1 && d.bin_max > d.bin_min),
+              VMS_ERR_INVALID_ARG, "elbo_plan_create: bad flow parameters");
+  {
+    vms_status ps = rqs_prepare();
+    if (ps) return ps;
+  }
+  vms_elbo_plan_s* pl = new vms_elbo_plan_s();
+  pl->d = d;
+  pl->off = layout(d, &pl->blocks);
+  pl->maxB = d.max_batch;
+  pl->splits_max = dense_splits(d.max_batch);
+  const size_t B = (size_t)d.max_batch;
+  int max_ldr = 1;
+  for (auto& b : pl->blocks) max_ldr = b.ldr > max_ldr ? b.ldr : max_ldr;
+  vms_status s = VMS_OK;
+#define A_(ptr, n) if (!s) s = alloc(pl, &(ptr), (n))
+  A_(pl->he, B * d.hidden); A_(pl->pe, B * 2 * d.dz); A_(pl->logq, B); A_(pl->logpz, B); A_(pl->logpx, B);
+  A_(pl->hd, B * d.hidden); A_(pl->pd, B * 2 * d.dx); A_(pl->scalars, 4); A_(pl->partial, 2 * ((B + 8191) / 8192) + 2);
+  pl->u.resize(d.num_blocks + 1); pl->hid.resize(d.num_blocks); pl->raw.resize(d.num_blocks);
+  for (int i = 0; i <= d.num_blocks; ++i) A_(pl->u[i], B * d.dz);
+  for (int i = 0; i < d.num_blocks; ++i) { A_(pl->hid[i], B * d.flow_hidden); A_(pl->raw[i], B * pl->blocks[i].ldr); }
+  A_(pl->g_pd, B * 2 * d.dx); A_(pl->g_hd, B * d.hidden); A_(pl->g_z, B * d.dz); A_(pl->g_pe, B * 2 * d.dz);
+  A_(pl->g_he, B * d.hidden); A_(pl->g_ua, B * d.dz); A_(pl->g_ub, B * d.dz);
+  A_(pl->g_raw, B * max_ldr); A_(pl->g_hid, B * (d.num_blocks ? d.flow_hidden : 1)); A_(pl->g_ldj, B);
+  A_(pl->gpart, (size_t)pl->splits_max * pl->off.total);
+#undef A_
+  if (s) { vms_elbo_plan_destroy(pl); return s; }
+  *plan = pl;
+  return VMS_OK;
+}
+
+vms_status vms_elbo_plan_destroy(vms_elbo_plan pl) {
+  if (!pl) return VMS_OK;
+  for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.first);
+  for (void* p : pl->allocs) cudaFree(p);
+  delete pl;
+  return VMS_OK;
+}
+
+static vms_status check_call(vms_elbo_plan pl, const float* theta, const float* x, const float* eps, int64_t B) {
+  VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "elbo: NULL plan");
+  VMS_REQUIRE(theta && x && eps, VMS_ERR_INVALID_ARG, "elbo: NULL tensor pointer");
+  VMS_REQUIRE(B >= 1 && B <= pl->maxB, VMS_ERR_SHAPE, "elbo: batch %lld outside [1, max_batch=%lld]", (long long)B,
+              (long long)pl->maxB);
+  return VMS_OK;
+}
+
+vms_status vms_elbo_forward(vms_elbo_plan pl, const float* theta, const float* x, const float* eps, int64_t B, float* z,
+                            float* logq, float* logpz, float* logpx, float* scalars, vms_stream stream) {
+  vms_status s = check_call(pl, theta, x, eps, B);
+  if (s) return s;
+  cudaStream_t st = as_stream(stream);
+  std::array<uintptr_t, 10> key = {0, (uintptr_t)B, (uintptr_t)theta, (uintptr_t)x, (uintptr_t)eps, (uintptr_t)z,
+                                   (uintptr_t)logq, (uintptr_t)logpz, (uintptr_t)logpx, (uintptr_t)scalars};
+  const vms_elbo_desc& d = pl->d;
+  return run_graphed(pl, key, st, [&]() -> vms_status {
+    VMS_TRY(forward_body(pl, theta, x, eps, B, scalars, st));
+    if (z) VMS_CUDA(cudaMemcpyAsync(z, pl->u[d.num_blocks], B * d.dz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (logq) VMS_CUDA(cudaMemcpyAsync(logq, pl->logq, B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (logpz) VMS_CUDA(cudaMemcpyAsync(logpz, pl->logpz, B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (logpx) VMS_CUDA(cudaMemcpyAsync(logpx, pl->logpx, B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return VMS_OK;
+  });
+}
+
+vms_status vms_elbo_forward_backward(vms_elbo_plan pl, const float* theta, const float* x, const float* eps, int64_t B,
+                                     float* grad, float* scalars, vms_stream stream) {
+  vms_status s = check_call(pl, theta, x, eps, B);
+  if (s) return s;
+  VMS_REQUIRE(grad, VMS_ERR_INVALID_ARG, "elbo_forward_backward: NULL grad");
+  cudaStream_t st = as_stream(stream);
+  std::array<uintptr_t, 10> key = {1, (uintptr_t)B, (uintptr_t)theta, (uintptr_t)x, (uintptr_t)eps, (uintptr_t)grad,
+                                   (uintptr_t)scalars, 0, 0, 0};
+  return run_graphed(pl, key, st, [&]() -> vms_status {
+    VMS_TRY(forward_body(pl, theta, x, eps, B, scalars, st));
+    return backward_body(pl, theta, x, eps, B, grad, st);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+// logprob.cu -- K4: distribution log_prob / reparameterised sample kernels and their reverse mode.
+//
+// Replaces (third-party arithmetic reached from the reference at the cited call sites):
+//   tfp Normal._log_prob      = -0.5 (x/s - m/s)^2 - (0.5 log 2pi + log s)        dists.py:213-217, tests/test_models.py:167-170
+//   tfp VonMises._log_prob    = k (cos(x - m) - 1) - log 2pi - log i0e(k)         dists.py:602-610, :64-71
+//   tfp Normal._sample_n      = eps * s + m                                        models.py:310, mcmc.py:100-102
+//   parameter transforms      softplus / softplus + eps32 / atan2                  dists.py:56-78, :603-607
+// One thread per row: the event size is 1..64 and the op is HBM-bound (3*D*4 + 4 bytes per row).
+#include "common.cuh"
+#include <math.h>
+
+namespace vms {
+
+constexpr int kMaxDof = 64;
+struct BlockwiseSpec {
+  int8_t kind[kMaxDof];
+  int16_t loc[kMaxDof], loc2[kMaxDof], scale[kMaxDof];
+};
+
+// Cephes single-precision exponentially scaled modified Bessel function I0 (i0ef), the routine behind
+// tf.math.bessel_i0e for float32 (Eigen generic_i0e<float>): Chebyshev series on [0,8] and (8,inf).
+__device__ __forceinline__ float i0e_f(float x) {
+  const float A[18] = {-1.30002500998624804212E-8f, 6.04699502254191894932E-8f,  -2.67079385394061173391E-7f,
+                       1.11738753912010371815E-6f,  -4.41673835845875056359E-6f, 1.64484480707288970893E-5f,
+                       -5.75419501008210370398E-5f, 1.88502885095841655729E-4f,  -5.76375574538582365885E-4f,
+                       1.63947561694133579842E-3f,  -4.32430999505057594430E-3f, 1.05464603945949983183E-2f,
+                       -2.37374148058994688156E-2f, 4.93052842396707084878E-2f,  -9.49010970480476444210E-2f,
+                       1.71620901522208775349E-1f,  -3.04682672343198398683E-1f, 6.76795274409476084995E-1f};
+  const float Bc[7] = {3.39623202570838634515E-9f, 2.26666899049817806459E-8f, 2.04891858946906374183E-7f,
+                       2.89137052083475648297E-6f, 6.88975834691682398426E-5f, 3.36911647825569408990E-3f,
+                       8.04490411014108831608E-1f};
+  x = fabsf(x);
+  if (x <= 8.0f) {
+    float y = 0.5f * x - 2.0f, b0 = A[0], b1 = 0.f, b2 = 0.f;
+#pragma unroll
+    for (int i = 1; i < 18; ++i) { b2 = b1; b1 = b0; b0 = y * b1 - b2 + A[i]; }
+    return 0.5f * (b0 - b2);
+  }
+  float y = 32.0f / x - 2.0f, b0 = Bc[0], b1 = 0.f, b2 = 0.f;
+#pragma unroll
+  for (int i = 1; i < 7; ++i) { b2 = b1; b1 = b0; b0 = y * b1 - b2 + Bc[i]; }
+  return 0.5f * (b0 - b2) / sqrtf(x);
+}
+
+__device__ __forceinline__ float normal_lp(float x, float loc, float scale) {
+  float z = x / scale - loc / scale;
+  return -0.5f * z * z - (VMS_HALF_LOG_2PI + logf(scale));
+}
+
+__global__ void blockwise_lp_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ params,
+                                    int64_t ld_p, int64_t B, int D, const BlockwiseSpec spec, int scale_mode,
+                                    float* __restrict__ lp, int accumulate) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* xr = x + b * ld_x;
+  const float* pr = params + b * ld_p;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float sc = apply_scale(pr[spec.scale[d]], scale_mode);
+    if (spec.kind[d] == VMS_DIST_NORMAL) {
+      s += normal_lp(xr[d], pr[spec.loc[d]], sc);
+    } else {
+      const float loc = spec.loc2[d] >= 0 ? atan2f(pr[spec.loc[d]], pr[spec.loc2[d]]) : pr[spec.loc[d]];
+      s += sc * (cosf(xr[d] - loc) - 1.0f) - VMS_LOG_2PI - logf(i0e_f(sc));
+    }
+  }
+  lp[b] = accumulate ? lp[b] + s : s;
+}
+
+// constrained parameters of every dof: loc [B, D] and scale / concentration [B, D] (make_param_transform, dists.py:28-87)
+__global__ void blockwise_params_kernel(const float* __restrict__ params, int64_t ld_p, int64_t B, int D,
+                                        const BlockwiseSpec spec, int scale_mode, float* __restrict__ loc,
+                                        float* __restrict__ scale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int64_t b = i / D;
+  const int d = (int)(i - b * D);
+  const float* pr = params + b * ld_p;
+  scale[i] = apply_scale(pr[spec.scale[d]], scale_mode);
+  loc[i] = (spec.kind[d] == VMS_DIST_VONMISES && spec.loc2[d] >= 0) ? atan2f(pr[spec.loc[d]], pr[spec.loc2[d]])
+                                                                   : pr[spec.loc[d]];
+}
+
+__global__ void std_normal_lp_kernel(const float* __restrict__ x, int64_t ld_x, int64_t B, int D,
+                                     float* __restrict__ lp, int accumulate) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* xr = x + b * ld_x;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) s += normal_lp(xr[d], 0.f, 1.f);
+  lp[b] = accumulate ? lp[b] + s : s;
+}
+
+__global__ void normal_sample_lp_kernel(const float* __restrict__ params, int64_t ld_p, int loc_off, int scale_off,
+                                        int scale_mode, const float* __restrict__ eps, int64_t B, int D,
+                                        float* __restrict__ z, int64_t ld_z, float* __restrict__ lp) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* pr = params + b * ld_p;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float loc = pr[loc_off + d], sc = apply_scale(pr[scale_off + d], scale_mode);
+    const float zz = __fadd_rn(__fmul_rn(eps[b * D + d], sc), loc);  // separate TF mul and add ops: no FMA contraction
+    if (z) z[b * ld_z + d] = zz;
+    s += normal_lp(zz, loc, sc);
+  }
+  if (lp) lp[b] = s;
+}
+
+__global__ void normal_lp_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ params,
+                                     int64_t ld_p, int loc_off, int scale_off, int scale_mode,
+                                     const float* __restrict__ g_lp, int64_t B, int D, float* g_x, int64_t ld_gx,
+                                     int accumulate_x, float* __restrict__ g_params, int64_t ld_gp) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float g = g_lp[b];
+  const float* pr = params + b * ld_p;
+  for (int d = 0; d < D; ++d) {
+    const float raw = pr[scale_off + d];
+    const float loc = pr[loc_off + d], sc = apply_scale(raw, scale_mode);
+    const float u = x[b * ld_x + d] / sc - loc / sc;
+    if (g_x) {
+      float* dst = g_x + b * ld_gx + d;
+      const float v = g * (-u / sc);
+      *dst = accumulate_x ? *dst + v : v;
+    }
+    if (g_params) {
+      g_params[b * ld_gp + loc_off + d] = g * (u / sc);
+      g_params[b * ld_gp + scale_off + d] = g * ((u * u - 1.0f) / sc) * apply_scale_grad(raw, scale_mode);
+    }
+  }
+}
+
+}  // namespace vms
+
+using namespace vms;
+
+extern "C" {
+
+static vms_status make_spec(BlockwiseSpec& spec, int64_t B, int D, const int32_t* kind, const int32_t* loc_off,
+                            const int32_t* loc2_off, const int32_t* scale_off, int scale_mode) {
+  VMS_REQUIRE(B >= 0 && D >= 1 && D <= kMaxDof, VMS_ERR_SHAPE, "blockwise: D must be in [1, %d]", kMaxDof);
+  VMS_REQUIRE(kind && loc_off && scale_off, VMS_ERR_INVALID_ARG, "blockwise: NULL offset table");
+  VMS_REQUIRE(scale_mode >= 0 && scale_mode <= 2, VMS_ERR_INVALID_ARG, "blockwise: bad scale_mode");
+  for (int d = 0; d < D; ++d) {
+    VMS_REQUIRE(kind[d] == VMS_DIST_NORMAL || kind[d] == VMS_DIST_VONMISES, VMS_ERR_UNSUPPORTED,
+                "blockwise: unsupported distribution kind %d", kind[d]);
+    spec.kind[d] = (int8_t)kind[d];
+    spec.loc[d] = (int16_t)loc_off[d];
+    spec.loc2[d] = (int16_t)(loc2_off ? loc2_off[d] : -1);
+    spec.scale[d] = (int16_t)scale_off[d];
+  }
+  return VMS_OK;
+}
+
+vms_status vms_blockwise_params(const float* params, int64_t ld_p, int64_t B, int D, const int32_t* kind,
+                                const int32_t* loc_off, const int32_t* loc2_off, const int32_t* scale_off,
+                                int scale_mode, float* loc, float* scale, vms_stream stream) {
+  BlockwiseSpec spec = {};
+  vms_status s = make_spec(spec, B, D, kind, loc_off, loc2_off, scale_off, scale_mode);
+  if (s) return s;
+  VMS_REQUIRE(params && loc && scale, VMS_ERR_INVALID_ARG, "blockwise_params: NULL pointer");
+  if (B == 0) return VMS_OK;
+  blockwise_params_kernel<<<(unsigned)((B * D + 255) / 256), 256, 0, as_stream(stream)>>>(params, ld_p, B, D, spec,
+                                                                                         scale_mode, loc, scale);
+  VMS_LAUNCH_CHECK("blockwise_params_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_blockwise_log_prob(const float* x, int64_t ld_x, const float* params, int64_t ld_p, int64_t B, int D,
+                                  const int32_t* kind, const int32_t* loc_off, const int32_t* loc2_off,
+                                  const int32_t* scale_off, int scale_mode, float* lp, int accumulate,
+                                  vms_stream stream) {
+  BlockwiseSpec spec = {};
+  vms_status s = make_spec(spec, B, D, kind, loc_off, loc2_off, scale_off, scale_mode);
+  if (s) return s;
+  VMS_REQUIRE(x && params && lp, VMS_ERR_INVALID_ARG, "blockwise_log_prob: NULL pointer");
+  if (B == 0) return VMS_OK;
+  blockwise_lp_kernel<<<(unsigned)((B + 127) / 128), 128, 0, as_stream(stream)>>>(x, ld_x, params, ld_p, B, D, spec,
+                                                                                 scale_mode, lp, accumulate);
+  VMS_LAUNCH_CHECK("blockwise_lp_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_std_normal_log_prob(const float* x, int64_t ld_x, int64_t B, int D, float* lp, int accumulate,
+                                   vms_stream stream) {
+  VMS_REQUIRE(B >= 0 && D >= 1, VMS_ERR_SHAPE, "std_normal_log_prob: bad shape");
+  VMS_REQUIRE(x && lp, VMS_ERR_INVALID_ARG, "std_normal_log_prob: NULL pointer");
+  if (B == 0) return VMS_OK;
+  std_normal_lp_kernel<<<(unsigned)((B + 127) / 128), 128, 0, as_stream(stream)>>>(x, ld_x, B, D, lp, accumulate);
+  VMS_LAUNCH_CHECK("std_normal_lp_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_normal_sample_log_prob(const float* params, int64_t ld_p, int loc_off, int scale_off, int scale_mode,
+                                      const float* eps, int64_t B, int D, float* z, int64_t ld_z, float* lp,
+                                      vms_stream stream) {
+  VMS_REQUIRE(B >= 0 && D >= 1, VMS_ERR_SHAPE, "normal_sample_log_prob: bad shape");
+  VMS_REQUIRE(params && eps, VMS_ERR_INVALID_ARG, "normal_sample_log_prob: NULL pointer");
+  if (B == 0) return VMS_OK;
+  normal_sample_lp_kernel<<<(unsigned)((B + 127) / 128), 128, 0, as_stream(stream)>>>(
+      params, ld_p, loc_off, scale_off, scale_mode, eps, B, D, z, ld_z, lp);
+  VMS_LAUNCH_CHECK("normal_sample_lp_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_normal_log_prob_backward(const float* x, int64_t ld_x, const float* params, int64_t ld_p, int loc_off,
+                                        int scale_off, int scale_mode, const float* g_lp, int64_t B, int D,
+                                        float* g_x, int64_t ld_gx, int accumulate_x, float* g_params, int64_t ld_gp,
+                                        vms_stream stream) {
+  VMS_REQUIRE(B >= 0 && D >= 1, VMS_ERR_SHAPE, "normal_log_prob_backward: bad shape");
+  VMS_REQUIRE(x && params && g_lp, VMS_ERR_INVALID_ARG, "normal_log_prob_backward: NULL pointer");
+  if (B == 0) return VMS_OK;
+  normal_lp_bwd_kernel<<<(unsigned)((B + 127) / 128), 128, 0, as_stream(stream)>>>(
+      x, ld_x, params, ld_p, loc_off, scale_off, scale_mode, g_lp, B, D, g_x, ld_gx, accumulate_x, g_params, ld_gp);
+  VMS_LAUNCH_CHECK("normal_lp_bwd_kernel");
+  return VMS_OK;
+}
+
+}  // extern "C"

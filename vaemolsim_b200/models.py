@@ -1,0 +1,282 @@
+"""Models -- host-side mirror of `vaemolsim/models.py` over sm_100a kernels.
+
+Same names / keywords as the reference (models.py:16 `FlowModel`, :153 `MappingToDistribution`, :242 `VAE`).  Calling a
+model builds distribution objects exactly as the reference does (op-by-op kernels); TRAINING (Keras `fit` /
+GradientTape / Adam in the reference, tests/test_models.py:181-182) goes through the fused ELBO plan of `csrc/elbo.cu`
+for the model family of the reference's tests (IndependentNormal encoder / decoder over one-hidden-layer FCDeepNNs,
+N(0, I) or RealNVP-RQS-flowed prior, KLDivergenceEstimate + LogProbLoss) and raises NotImplementedError for
+compositions whose backward kernels are not built yet.  `VAEDualELBO` (models.py:335, cannot be
+constructed in the reference) and `BackmappingOnly` (needs the out-of-scope GAA embedding) are not mirrored.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, dists, flows, losses, mappings
+from . import _protocols as P
+from ._abi import Tensor, as_tensor, ctx
+
+
+class Adam(object):
+    """tf.keras.optimizers.Adam hyper-parameters (Keras defaults; tests/test_models.py:181 uses lr 1e-3)."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+
+
+class Model(P.Layer):
+    """The slice of tf.keras.Model the reference's tests use: compile / fit / evaluate / predict."""
+
+    def compile(self, optimizer=None, loss=None, **kwargs):
+        self.optimizer = optimizer if optimizer is not None else Adam()
+        self.loss = loss
+
+    def predict_step(self, inputs):
+        return self(inputs, training=False).sample()
+
+    def predict(self, x, batch_size=32, verbose=0):
+        x = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
+        outs = [self.predict_step(Tensor.from_numpy(x[i:i + batch_size])).numpy() for i in range(0, len(x), batch_size)]
+        return np.concatenate(outs, axis=0)
+
+
+class FlowModel(Model):
+    """models.py:16-150: (optional mapping) -> FlowedDistribution."""
+
+    def __init__(self, flow, latent_dist, mapping=None, name='flow_model', **kwargs):
+        super(FlowModel, self).__init__(name=name, **kwargs)
+        self.flowed_dist = dists.FlowedDistribution(flow, latent_dist)
+        static = isinstance(latent_dist, P.DistributionLambda)  # models.py:74-83
+        if mapping is None:
+            self.mapping = None if static else mappings.FCDeepNN(self.flowed_dist.params_size())
+        elif static:
+            print("Warning: for static distribution (DistributionLambda as latent distribution), cannot have "
+                  "mapping, so setting to None.")
+            self.mapping = None
+        else:
+            self.mapping = mapping  # the reference forgets this assignment
+
+    def call(self, inputs, training=False):
+        mapped = self.mapping(inputs, training=training) if self.mapping is not None else inputs
+        if self.flowed_dist.conditional:
+            return self.flowed_dist(mapped, conditional_input=inputs, training=training)
+        return self.flowed_dist(mapped, training=training)
+
+    def get_config(self):
+        config = super(FlowModel, self).get_config()
+        config.update({"flow": self.flowed_dist.flow, "latent_dist": self.flowed_dist.latent_dist,
+                       "mapping": self.mapping})
+        return config
+
+
+class MappingToDistribution(Model):
+    """models.py:153-239: mapping network (FCDeepNN by default) followed by a distribution layer."""
+
+    def __init__(self, distribution, mapping=None, name='map_to_dist', **kwargs):
+        super(MappingToDistribution, self).__init__(name=name, **kwargs)
+        self.distribution = distribution
+        self.conditional = getattr(self.distribution, 'conditional', False)
+        if mapping is None:
+            if isinstance(self.distribution, P.DistributionLambda):
+                self.mapping = mappings.FCDeepNN(self.distribution.params_size(self.distribution.event_size))
+            else:
+                self.mapping = mappings.FCDeepNN(self.distribution.params_size())
+        else:
+            self.mapping = mapping
+
+    def call(self, inputs, training=False):
+        mapped = self.mapping(inputs, training=training)
+        if self.conditional:
+            return self.distribution(mapped, training=training, conditional_input=inputs)
+        return self.distribution(mapped, training=training)
+
+    def get_config(self):
+        config = super(MappingToDistribution, self).get_config()
+        config.update({"distribution": self.distribution, "mapping": self.mapping})
+        return config
+
+
+class VAE(Model):
+    """models.py:242-332: encoder -> sample -> prior -> regulariser -> decoder."""
+
+    def __init__(self, encoder, decoder, prior, regularizer=None, name='vae', **kwargs):
+        super(VAE, self).__init__(name=name, **kwargs)
+        self.encoder = encoder
+        self.decoder = decoder
+        self.prior = prior
+        self.regularizer = regularizer if regularizer is not None else losses.KLDivergenceEstimate()
+        self.losses = []
+        self.metrics = {}
+        self._fused = None
+
+    def call(self, inputs, training=False):
+        inputs = as_tensor(inputs)
+        encode_dist = self.encoder(inputs, training=training)
+        encode_sample = encode_dist.sample()
+        prior_dist = self.prior(encode_sample, training=training)
+        reg_loss = self.regularizer(encode_dist, prior_dist, encode_sample)
+        self.losses = [reg_loss]
+        self.metrics = {'kl_div': reg_loss / float(self.regularizer.weight), 'regularizer_loss': reg_loss}
+        return self.decoder(encode_sample, training=training)
+
+    # ------------------------------------------------------------------ fused ELBO path (csrc/elbo.cu)
+    def fused(self, max_batch=4096):
+        """The fused ELBO plan for this model (built on first use; rebuilt if max_batch grows)."""
+        if self._fused is None or self._fused.max_batch < max_batch:
+            self._fused = FusedELBO(self, max_batch)
+        return self._fused
+
+    def train_step(self, x, eps=None):
+        """One Adam step on a batch; returns dict(loss, nll, kl) as floats."""
+        x = as_tensor(x)
+        f = self.fused(x.shape[0])
+        if eps is None:
+            eps = P.rng().standard_normal((x.shape[0], f.dz), dtype=np.float32)
+        scal = f.train_step(x, as_tensor(eps), getattr(self, 'optimizer', None) or Adam())
+        return dict(zip(('loss', 'nll', 'kl'), scal.numpy()[:3].tolist()))
+
+    def fit(self, x, y=None, epochs=1, batch_size=32, verbose=0, shuffle=True):
+        if getattr(self, 'loss', None) is not None and not isinstance(self.loss, losses.LogProbLoss):
+            raise NotImplementedError('VAE.fit: only LogProbLoss has a fused backward (SURVEY.md 8f)')
+        x = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
+        hist = {'loss': [], 'kl_div': []}
+        for _ in range(epochs):
+            order = P.rng().permutation(len(x)) if shuffle else np.arange(len(x))
+            tot, klt, n = 0.0, 0.0, 0
+            for i in range(0, len(x), batch_size):
+                xb = x[order[i:i + batch_size]]
+                out = self.train_step(Tensor.from_numpy(xb))
+                tot, klt, n = tot + out['loss'] * len(xb), klt + out['kl'] * len(xb), n + len(xb)
+            hist['loss'].append(tot / n)
+            hist['kl_div'].append(klt / n)
+        return hist
+
+    def evaluate(self, x, y=None, batch_size=32, verbose=0):
+        x = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
+        f = self.fused(min(batch_size, len(x)))
+        tot, n = 0.0, 0
+        for i in range(0, len(x), batch_size):
+            xb = Tensor.from_numpy(x[i:i + batch_size])
+            eps = Tensor.from_numpy(P.rng().standard_normal((xb.shape[0], f.dz), dtype=np.float32))
+            tot, n = tot + float(f.forward(xb, eps)['scalars'].numpy()[0]) * xb.shape[0], n + xb.shape[0]
+        return tot / n
+
+    def get_config(self):
+        config = super(VAE, self).get_config()
+        config.update({"encoder": self.encoder, "decoder": self.decoder, "prior": self.prior,
+                       "regularizer": self.regularizer})
+        return config
+
+
+class FusedELBO(object):
+    """Binds a VAE of the supported family to a `vms_elbo_plan`: ONE flat parameter buffer (the layers' kernels / biases
+    become views into it), whole-step CUDA graph, flat gradient, Adam state.
+
+    Supported: encoder / decoder = MappingToDistribution(IndependentNormal, FCDeepNN with one relu hidden layer, no
+    periodic dofs); prior = DistributionLambda -> StandardNormal, or FlowedDistribution(RQSSplineRealNVP without batch
+    norm / before / after transforms, StandardNormal latent); regulariser KLDivergenceEstimate sampled from dist_a.
+    """
+
+    def __init__(self, vae, max_batch):
+        self.vae = vae
+        self.max_batch = int(max_batch)
+        enc_layers, self.dx, self.dz, hidden = self._check_mlp(vae.encoder, 'encoder')
+        dec_layers, dz2, dx2, hidden2 = self._check_mlp(vae.decoder, 'decoder')
+        if (dz2, dx2, hidden2) != (self.dz, self.dx, hidden):
+            raise NotImplementedError('fused ELBO: encoder / decoder shapes must mirror each other')
+        reg = vae.regularizer
+        if type(reg) is not losses.KLDivergenceEstimate or reg.sample_dist != 'dist_a':
+            raise NotImplementedError('fused ELBO: only KLDivergenceEstimate (samples from dist_a) is built')
+        blocks, nbins, fh, lo, hi = self._check_prior(vae.prior)
+        self.desc = _abi.ElboDesc(self.dx, self.dz, hidden, len(blocks), nbins, fh, lo, hi, float(reg.weight),
+                                  self.max_batch)
+        c = ctx()
+        self.n_params = int(c.lib.vms_elbo_param_count(C.byref(self.desc)))
+        self.theta = Tensor((self.n_params, ))
+        self.grad = Tensor((self.n_params, ))
+        self.m = Tensor.zeros((self.n_params, ))
+        self.v = Tensor.zeros((self.n_params, ))
+        self.scalars = Tensor((4, ))
+        self.t = 0
+        # flat order: enc.0 enc.1 dec.0 dec.1, then per flow block d1, heads (include/vms_b200.h)
+        off = 0
+        for lay in enc_layers + dec_layers + [l for b in blocks for l in (b.d1, b.heads)]:
+            W, b = lay.get_weights()
+            kW = Tensor(W.shape, _ptr=self.theta.ptr + 4 * off, _base=self.theta)
+            off += W.size
+            kb = Tensor(b.shape, _ptr=self.theta.ptr + 4 * off, _base=self.theta)
+            off += b.size
+            lay.rebind(kW, kb)
+            lay.assign(W, b)
+        if off != self.n_params:
+            raise RuntimeError('fused ELBO: parameter layout mismatch (%d != %d)' % (off, self.n_params))
+        h = C.c_void_p()
+        c.lib.vms_elbo_plan_create(C.byref(self.desc), C.byref(h))
+        self.handle = h.value
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                _abi.load().vms_elbo_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+    @staticmethod
+    def _check_mlp(m, what):
+        ok = (isinstance(m, MappingToDistribution) and isinstance(m.distribution, P.IndependentNormal)
+              and isinstance(m.mapping, mappings.FCDeepNN))
+        if not ok:
+            raise NotImplementedError('fused ELBO: %s must be MappingToDistribution(IndependentNormal, FCDeepNN)' % what)
+        fc = m.mapping
+        if not fc.built:
+            raise RuntimeError('fused ELBO: call the model once on data before training so its layers are built')
+        if fc.any_periodic or len(fc.layer_list) != 2 or fc.layer_list[0].act != P.ACT['relu']:
+            raise NotImplementedError('fused ELBO: %s FCDeepNN must have one relu hidden layer, no periodic dofs' % what)
+        l0, l1 = fc.layer_list
+        return [l0, l1], l0.kernel.shape[0], l1.units // 2, l0.units
+
+    @staticmethod
+    def _check_prior(prior):
+        if isinstance(prior, dists.FlowedDistribution):
+            flow, latent = prior.flow, prior.latent_dist
+            if not isinstance(flow, flows.RQSSplineRealNVP) or flow.batch_norm or flow.before_flow_transform is not None \
+                    or flow.after_flow_transform is not None:
+                raise NotImplementedError('fused ELBO: prior flow must be a plain RQSSplineRealNVP')
+            if not flow.built:
+                raise RuntimeError('fused ELBO: call the model once on data before training so the flow is built')
+            blocks = [b.bijector_fn for b in flow.chain.bijectors[::-1]]  # chain list is reversed (flows.py:323)
+            b0 = blocks[0]
+            return blocks, b0.num_bins, b0.hidden_dim, float(b0.bin_min), float(b0.bin_max)
+        if isinstance(prior, P.DistributionLambda):
+            return [], 2, 1, -1.0, 1.0
+        raise NotImplementedError('fused ELBO: prior must be a static N(0, I) DistributionLambda or a FlowedDistribution')
+
+    def forward(self, x, eps, want=('z', 'logq', 'logpz', 'logpx')):
+        c = ctx()
+        B = x.shape[0]
+        out = {'z': Tensor((B, self.dz)) if 'z' in want else None}
+        for k in ('logq', 'logpz', 'logpx'):
+            out[k] = Tensor((B, )) if k in want else None
+        out['scalars'] = Tensor((4, ))
+        P_ = P._ptr
+        c.lib.vms_elbo_forward(self.handle, self.theta.ptr, x.ptr, eps.ptr, B, P_(out['z']), P_(out['logq']),
+                               P_(out['logpz']), P_(out['logpx']), out['scalars'].ptr, c.stream)
+        return out
+
+    def forward_backward(self, x, eps):
+        """Writes the flat gradient into self.grad and {loss, nll, kl} into self.scalars (device)."""
+        c = ctx()
+        c.lib.vms_elbo_forward_backward(self.handle, self.theta.ptr, x.ptr, eps.ptr, x.shape[0], self.grad.ptr,
+                                        self.scalars.ptr, c.stream)
+        return self.scalars
+
+    def adam_step(self, opt, grad_scale=1.0):
+        c = ctx()
+        self.t += 1
+        c.lib.vms_adam_step(self.theta.ptr, self.grad.ptr, 1, grad_scale, self.m.ptr, self.v.ptr, self.n_params, self.t,
+                            opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon, c.stream)
+
+    def train_step(self, x, eps, opt):
+        self.forward_backward(x, eps)
+        self.adam_step(opt)
+        return self.scalars
