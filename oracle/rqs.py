@@ -222,7 +222,7 @@ def rqs_backward_raw(v_in, raw_w, raw_h, raw_s, bin_min, bin_max, g_out, g_ldj, 
     g_dk = gy * y_dk + gL * L_dk
     g_dk1 = gy * y_dk1 + gL * L_dk1
     g_h = gy * y_h + g_s / w
-    g_yk = gy
+    g_yk = np.array(gy, dtype=dt, copy=True)  # never alias the caller's g_out (masked in place below)
     g_w = -g_s * s / w - g_r * r / w
     g_xk = -g_r / w
     zero = dt.type(0)

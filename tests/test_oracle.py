@@ -1,0 +1,347 @@
+"""CPU: pins the oracle (the checker of the CUDA path) against everything the reference offers for this path
+(SURVEY 8c): golden outputs of the reference's own mcmc.py, MAF-order goldens, notebook parameter counts, the
+known-answer / identity tests of the reference suite, and analytic properties (round trip, log-det vs finite
+differences, normalisation, gradient finite differences in float64)."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy import special, stats
+
+from oracle import dists, flows, mappings, nets, rqs, vae
+from oracle import mcmc as omc
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _raw(rng, n, K, dtype, scale=1.5):
+    return (rng.normal(0, scale, (n, K)).astype(dtype), rng.normal(0, scale, (n, K)).astype(dtype),
+            rng.normal(0, scale, (n, K - 1)).astype(dtype))
+
+
+# ------------------------------------------------------------------------------------------------ RQS
+@pytest.mark.parametrize('K', [8, 20, 32])
+def test_rqs_round_trip_and_identity_outside(K):
+    rng = np.random.default_rng(0)
+    n = 2000
+    rw, rh, rs = _raw(rng, n, K, np.float64)
+    x = rng.uniform(-12, 12, n)
+    y, fl = rqs.rqs_forward_raw(x, rw, rh, rs, -10.0, 10.0)
+    xb, il = rqs.rqs_inverse_raw(y, rw, rh, rs, -10.0, 10.0)
+    np.testing.assert_allclose(xb, x, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(il, -fl, rtol=0, atol=1e-8)
+    out = np.abs(x) >= 10
+    assert np.array_equal(y[out], x[out]) and np.all(fl[out] == 0)
+    assert np.all(np.diff(np.sort(y)) >= 0) and np.all(np.abs(y[~out]) < 10)
+
+
+def test_rqs_logdet_matches_finite_difference():
+    rng = np.random.default_rng(1)
+    n, K = 500, 16
+    rw, rh, rs = _raw(rng, n, K, np.float64)
+    x = rng.uniform(-9.5, 9.5, n)
+    h = 1e-6
+    yp, _ = rqs.rqs_forward_raw(x + h, rw, rh, rs, -10.0, 10.0)
+    ym, _ = rqs.rqs_forward_raw(x - h, rw, rh, rs, -10.0, 10.0)
+    _, fl = rqs.rqs_forward_raw(x, rw, rh, rs, -10.0, 10.0)
+    np.testing.assert_allclose(np.exp(fl), (yp - ym) / (2 * h), rtol=2e-5)
+
+
+def test_rqs_density_normalises_in_1d():
+    """integral of exp(base_lp(inv(y)) + ildj(y)) dy = 1 for a single spline over N(0,1)."""
+    rng = np.random.default_rng(2)
+    K = 12
+    rw, rh, rs = _raw(rng, 1, K, np.float64)
+    y = np.linspace(-14, 14, 200001)
+    t = lambda a: np.repeat(a, y.size, axis=0)
+    x, il = rqs.rqs_inverse_raw(y, t(rw), t(rh), t(rs), -10.0, 10.0)
+    p = np.exp(stats.norm.logpdf(x) + il)
+    assert abs(np.trapezoid(p, y) - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize('inverse_dir', [False, True])
+def test_rqs_backward_matches_float64_finite_differences(inverse_dir):
+    rng = np.random.default_rng(3)
+    n, K = 40, 6
+    rw, rh, rs = _raw(rng, n, K, np.float64, 1.0)
+    v = rng.uniform(-9, 9, n)
+    v[:3] = [-11.0, 12.0, 10.5]  # out of range: identity, zero parameter gradients
+    g_out, g_ldj = rng.normal(size=n), rng.normal(size=n)
+    fn = rqs.rqs_inverse_raw if inverse_dir else rqs.rqs_forward_raw
+
+    def loss(v_, rw_, rh_, rs_):
+        o, l = fn(v_, rw_, rh_, rs_, -10.0, 10.0)
+        return o * g_out + l * g_ldj  # per element
+
+    g_in, g_rw, g_rh, g_rs = rqs.rqs_backward_raw(v, rw, rh, rs, -10.0, 10.0, g_out, g_ldj, inverse_dir=inverse_dir)
+    h = 1e-6
+    np.testing.assert_allclose(g_in, (loss(v + h, rw, rh, rs) - loss(v - h, rw, rh, rs)) / (2 * h), rtol=1e-4, atol=1e-6)
+    for arr, g in ((rw, g_rw), (rh, g_rh), (rs, g_rs)):
+        for j in range(arr.shape[1]):
+            ap, am = arr.copy(), arr.copy()
+            ap[:, j] += h
+            am[:, j] -= h
+            args_p = [ap if a is arr else a for a in (rw, rh, rs)]
+            args_m = [am if a is arr else a for a in (rw, rh, rs)]
+            fd = (loss(v, *args_p) - loss(v, *args_m)) / (2 * h)
+            np.testing.assert_allclose(g[:, j], fd, rtol=2e-4, atol=2e-6)
+    assert np.all(g_rw[:3] == 0) and np.all(g_rs[:3] == 0) and np.array_equal(g_in[:3], g_out[:3])
+
+
+def test_softplus_softmax_known_answers():
+    assert rqs.softplus_tf(np.float32(0)) == np.float32(np.log(2.0))
+    assert rqs.softplus_tf(np.float32(20)) == np.float32(20)
+    np.testing.assert_allclose(rqs.softplus_tf(np.float32(-20)), np.exp(-20.0), rtol=1e-6)
+    bw = rqs.bin_positions(np.zeros((1, 32), np.float32), -10.0, 10.0)
+    np.testing.assert_allclose(bw.sum(), 20.0, rtol=1e-6)  # widths tile the range exactly
+    np.testing.assert_allclose(bw, (20 - 0.32) / 32 + 0.01, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ nets / flows
+def test_maf_orders_match_reference_recipe():
+    gold = json.load(open(os.path.join(GOLD, 'maf_orders.json')))
+    assert gold['3_3_42'] == ['right-to-left', [3, 2, 1], 'left-to-right']
+    assert gold['4_6_42'][1:3] == [[4, 3, 6, 5, 2, 1], [3, 5, 1, 2, 4, 6]]
+    for key, val in gold.items():
+        nb, D, seed = (int(v) for v in key.split('_'))
+        got = [o if isinstance(o, str) else [int(v) for v in o] for o in nets.maf_block_orders(nb, D, seed)]
+        assert got == val
+
+
+def test_notebook_parameter_counts_pin_made_structure():
+    """Keras summary() counts of the example notebooks."""
+    rng = np.random.default_rng(0)
+    # Training_VAEs_and_Decoders cell 26: prior = 4-block MAF-RQS, K=32, H=64 over Dz... 26,236 parameters
+    blocks = flows.maf_init(rng, 1, num_blocks=4, order_seed=42, num_bins=32, hidden_dim=64)
+    n_prior = sum(nets.made_param_count(b[k]) for b in blocks for k in ('w', 'h', 's'))
+    assert n_prior == 26236
+    # cell 43: decoder = FCDeepNN 1,606 + conditional MADE 2,332 = 3,938
+    fc = nets.fcdeepnn_init(rng, 1, [200], (2, 3))
+    assert sum(W.size + b.size for W, b in fc) == 1606
+    made = nets.made_init(rng, 3, 2, [10, 100, 10], cond_size=1)  # notebook line 297-302
+    assert nets.made_param_count(made) == 2332
+    # MC_Moves_with_VAEs cell 22: 1,002 / 3,512 / 10,636
+    enc = nets.fcdeepnn_init(rng, 2, [200], (2, ))
+    assert sum(W.size + b.size for W, b in enc) == 1002
+    blocks = flows.maf_init(rng, 1, num_blocks=4, order_seed=None, num_bins=20, hidden_dim=40)
+    assert sum(nets.made_param_count(b[k]) for b in blocks for k in ('w', 'h', 's')) == 10636
+    dec_fc = nets.fcdeepnn_init(rng, 1, [200], (2, 2))
+    dec_made = nets.made_init(rng, 2, 2, [10, 100, 10], cond_size=1)
+    assert sum(W.size + b.size for W, b in dec_fc) + nets.made_param_count(dec_made) == 3512
+
+
+def test_made_is_autoregressive():
+    rng = np.random.default_rng(5)
+    D, params = 5, 3
+    for order in ('left-to-right', 'right-to-left', [3, 1, 5, 2, 4]):
+        layers = nets.made_init(rng, params, D, [17], order, cond_size=2, kernel_init='truncated_normal',
+                                dtype=np.float64)
+        for L in layers:
+            L['b'] = rng.normal(size=L['b'].shape)
+        x = rng.normal(size=(1, D))
+        c = rng.normal(size=(1, 2))
+        base = nets.made_forward(x, layers, params, c)
+        deg = nets.create_input_order(D, order)
+        for j in range(D):
+            xp = x.copy()
+            xp[0, j] += 1.0
+            changed = np.any(nets.made_forward(xp, layers, params, c) != base, axis=-1)[0]
+            # output dof i may depend on input j only if degree(j) < degree(i)
+            assert np.array_equal(changed, deg > deg[j]) or np.all(changed <= (deg > deg[j]))
+    with pytest.raises(ValueError, match='conditional_input'):
+        nets.made_forward(x, layers, params, None)
+
+
+def test_realnvp_chain_round_trip_and_split():
+    assert flows.realnvp_split(0, 1) == (slice(0, 0), slice(0, 1))
+    assert flows.realnvp_split(0, 5) == (slice(0, 2), slice(2, 5))
+    assert flows.realnvp_split(1, 5) == (slice(2, 5), slice(0, 2))
+    rng = np.random.default_rng(6)
+    for D in (1, 2, 3):
+        blocks = flows.realnvp_init(rng, D, 4, 8, 16, np.float64)
+        x = rng.normal(size=(50, D)) * 3
+        y, fl = flows.realnvp_forward(x, blocks, 8, (-10.0, 10.0))
+        xb, il = flows.realnvp_inverse(y, blocks, 8, (-10.0, 10.0))
+        np.testing.assert_allclose(xb, x, atol=1e-9)
+        np.testing.assert_allclose(il, -fl, atol=1e-8)
+
+
+def test_maf_forward_inverts_inverse():
+    rng = np.random.default_rng(7)
+    D = 3
+    blocks = flows.maf_init(rng, D, 3, 42, 8, 12, cond_size=2, dtype=np.float64)
+    cond = rng.normal(size=(20, 2))
+    x = rng.normal(size=(20, D)) * 2
+    y, fl = flows.maf_forward(x, blocks, 8, (-10.0, 10.0), cond)
+    xb, il = flows.maf_inverse(y, blocks, 8, (-10.0, 10.0), cond)
+    np.testing.assert_allclose(xb, x, atol=1e-8)
+    np.testing.assert_allclose(il, -fl, atol=1e-7)
+
+
+def test_domain_transform_identities():
+    """tests/test_flows.py:15-31: column min -> 0, max -> 1, and the round trip."""
+    dom = [(-np.pi, np.pi), (0.0, 10.0), (-5.0, 1.0)]
+    prm = flows.domain_transform_params(dom, (0.0, 1.0))
+    lo = flows.domain_transform_forward(np.array([[a for a, _ in dom]], np.float32), prm)
+    hi = flows.domain_transform_forward(np.array([[b for _, b in dom]], np.float32), prm)
+    np.testing.assert_allclose(lo, 0.0, atol=1e-6)
+    np.testing.assert_allclose(hi, 1.0, atol=1e-6)
+    x = np.random.default_rng(0).uniform(-3, 1, (10, 3)).astype(np.float32)
+    np.testing.assert_allclose(flows.domain_transform_inverse(flows.domain_transform_forward(x, prm), prm), x, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ dists / losses
+def test_param_transform_known_answers():
+    """tests/test_dists.py:15-30."""
+    t = dists.param_transform('normal', np.zeros((1, 2), np.float32))
+    assert t['loc'][0] == 0 and np.isclose(t['scale'][0], np.log(2.0), rtol=1e-6)
+    t = dists.param_transform('vonmises', np.array([[0.0, -1.0, 0.0]], np.float32))
+    assert np.isclose(t['loc'][0], np.pi, rtol=1e-6) and np.isclose(t['concentration'][0], np.log(2.0), rtol=1e-6)
+
+
+def test_log_probs_match_scipy():
+    rng = np.random.default_rng(8)
+    x, loc = rng.normal(size=(30, 4)), rng.normal(size=(30, 4))
+    sc = rng.uniform(0.2, 3, (30, 4))
+    np.testing.assert_allclose(dists.normal_log_prob(x, loc, sc), stats.norm.logpdf(x, loc, sc), rtol=1e-10)
+    k = rng.uniform(0.01, 50, (30, 4))
+    np.testing.assert_allclose(dists.vonmises_log_prob(x, loc, k), stats.vonmises.logpdf(x, k, loc=loc), rtol=1e-8, atol=1e-9)
+
+
+def test_cephes_i0e_coefficients_used_by_the_kernel():
+    """The float32 Chebyshev series hard-coded in csrc/logprob.cu reproduces scipy's i0e to float32 accuracy."""
+    A = np.array([-1.30002500998624804212E-8, 6.04699502254191894932E-8, -2.67079385394061173391E-7,
+                  1.11738753912010371815E-6, -4.41673835845875056359E-6, 1.64484480707288970893E-5,
+                  -5.75419501008210370398E-5, 1.88502885095841655729E-4, -5.76375574538582365885E-4,
+                  1.63947561694133579842E-3, -4.32430999505057594430E-3, 1.05464603945949983183E-2,
+                  -2.37374148058994688156E-2, 4.93052842396707084878E-2, -9.49010970480476444210E-2,
+                  1.71620901522208775349E-1, -3.04682672343198398683E-1, 6.76795274409476084995E-1], np.float32)
+    Bc = np.array([3.39623202570838634515E-9, 2.26666899049817806459E-8, 2.04891858946906374183E-7,
+                   2.89137052083475648297E-6, 6.88975834691682398426E-5, 3.36911647825569408990E-3,
+                   8.04490411014108831608E-1], np.float32)
+
+    def chb(y, c):
+        b0, b1, b2 = c[0], np.float32(0), np.float32(0)
+        for ci in c[1:]:
+            b2, b1 = b1, b0
+            b0 = np.float32(y * b1 - b2 + ci)
+        return np.float32(0.5) * (b0 - b2)
+
+    for x in np.concatenate([np.linspace(0, 8, 41), np.linspace(8.01, 500, 60)]).astype(np.float32):
+        got = chb(np.float32(0.5) * x - 2, A) if x <= 8 else chb(np.float32(32) / x - 2, Bc) / np.sqrt(x)
+        assert abs(got - special.i0e(float(x))) <= 4e-7 * special.i0e(float(x)) + 1e-9
+
+
+def test_loss_identities():
+    """tests/test_losses.py:29-36,55-95 restated on the oracle: weight linearity, deterministic-encoder KL, symmetry."""
+    rng = np.random.default_rng(9)
+    z = rng.normal(size=(100, 2)).astype(np.float32)
+    la = dists.normal_log_prob(z, np.float32(1), np.float32(1)).sum(-1)
+    lb = dists.normal_log_prob(z, np.float32(0), np.float32(1)).sum(-1)
+    kl = np.mean(la - lb, dtype=np.float32)
+    assert np.float32(100.0) * kl == np.float32(100.0 * kl)
+    assert np.mean(lb - la, dtype=np.float32) == -kl
+    assert np.mean(-lb, dtype=np.float32) == -np.mean(lb, dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ DistanceSelection
+def test_distance_selection_identities():
+    """tests/test_mappings.py:56-98: sq_cut, shapes, stored box == per-batch box, periodic != non-periodic, ragged."""
+    rng = np.random.default_rng(10)
+    B, N = 6, 100
+    coords = rng.uniform(0, 10, (B, N, 3)).astype(np.float32)
+    ref = rng.uniform(0, 10, (B, 3)).astype(np.float32)
+    box = np.array([10.0, 10.0, 10.0], np.float32)
+    info = rng.normal(size=(B, N, 2)).astype(np.float32)
+    a = mappings.distance_selection(coords, ref, 3.0, 50, box_lengths=box)
+    b = mappings.distance_selection(coords, ref, 3.0, 50, box_lengths=np.tile(box, (B, 1)))
+    c = mappings.distance_selection(coords, ref, 3.0, 50)
+    assert a.shape == (B, 50, 3) and np.array_equal(a, b) and not np.array_equal(a, c)
+    d2 = (a * a).sum(-1)
+    assert np.all(d2 <= 9.0 + 1e-5)
+    nz = d2 > 0
+    for r in range(B):  # ascending distance then zero padding
+        k = nz[r].sum()
+        assert np.all(nz[r, :k]) and np.all(np.diff(d2[r, :k]) >= 0)
+    sel, sinfo, idx = mappings.distance_selection(coords, ref, 3.0, 10, box_lengths=box, particle_info=info,
+                                                  return_indices=True)
+    assert sinfo.shape == (B, 10, 2) and idx.dtype == np.int32
+    keep = (sel != 0).any(-1)
+    assert np.array_equal(sinfo[keep], np.take_along_axis(info, idx[..., None], 1)[keep])
+    rows = [coords[0, :7], coords[1, :0], coords[2, :60]]
+    r = mappings.distance_selection(rows, ref[:3], 3.0, 50, box_lengths=box)
+    assert r.shape == (3, 50, 3) and np.all(r[1] == 0)
+    # brute force, float64
+    loc = coords[3].astype(np.float64) - ref[3]
+    loc -= 10.0 * np.rint(loc / 10.0)
+    dd = (loc**2).sum(-1)
+    want = np.sort(dd[dd <= 9.0])[:50]
+    np.testing.assert_allclose((a[3]**2).sum(-1)[:len(want)], want, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ VAE ELBO
+def test_elbo_backward_matches_float64_finite_differences():
+    for prior in ('normal', 'realnvp'):
+        P = vae.cast_params(vae.init_vae(11, dx=3, dz=2, hidden=7, prior=prior, num_blocks=3, num_bins=5,
+                                         flow_hidden=6), np.float64)
+        rng = np.random.default_rng(12)
+        x, eps = rng.normal(size=(9, 3)), rng.normal(size=(9, 2))
+        _, G = vae.elbo_backward(P, x, eps, weight=0.7)
+        g = vae.flatten(vae.grad_list(P, G))
+        names = vae.param_list(P)
+        flat = vae.flatten(names)
+        idx = rng.choice(flat.size, 40, replace=False)
+
+        def loss_at(theta):
+            Q = {k: v for k, v in P.items()}
+            off = 0
+            new = {}
+            for nm, a in names:
+                new[nm] = theta[off:off + a.size].reshape(a.shape)
+                off += a.size
+            Q['enc'] = [(new['enc.%d.W' % i], new['enc.%d.b' % i]) for i in range(2)]
+            Q['dec'] = [(new['dec.%d.W' % i], new['dec.%d.b' % i]) for i in range(2)]
+            if 'flow' in P:
+                Q['flow'] = [{k: (new['flow.%d.%s.W' % (b, k)], new['flow.%d.%s.b' % (b, k)]) for k in ('d1', 'w', 'h', 's')}
+                             for b in range(len(P['flow']))]
+            return vae.elbo_forward(Q, x, eps, weight=0.7)['loss']
+
+        for i in idx:
+            tp, tm = flat.copy(), flat.copy()
+            tp[i] += 1e-6
+            tm[i] -= 1e-6
+            fd = (loss_at(tp) - loss_at(tm)) / 2e-6
+            assert abs(fd - g[i]) <= 1e-5 * max(1.0, abs(fd)), (prior, names, i, fd, g[i])
+
+
+def test_elbo_goldens_are_stable():
+    from helpers import flat_from_oracle, flat_grad_from_oracle  # noqa: F401
+    for tag, prior in (('c1', 'normal'), ('c2', 'realnvp')):
+        g = np.load(os.path.join(GOLD, 'elbo_%s.npz' % tag))
+        P = vae.init_vae(1003, prior=prior, flow_hidden=16, num_bins=8, hidden=32)
+        out, G = vae.elbo_backward(P, g['x'], g['eps'])
+        np.testing.assert_array_equal(vae.flatten(vae.param_list(P)), g['theta'])
+        np.testing.assert_allclose(out['logpz'], g['logpz'], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(vae.flatten(vae.grad_list(P, G)), g['grad'], rtol=1e-5, atol=1e-7)
+    assert vae.param_count(vae.init_vae(0)) == 5216  # C1
+    assert vae.param_count(vae.init_vae(0, prior='realnvp', flow_hidden=100)) == 44396  # C2
+
+
+# ------------------------------------------------------------------------------------------------ MC acceptance
+@pytest.mark.parametrize('tag,prior', [('c4a', 'normal'), ('flow', 'realnvp')])
+def test_mc_oracle_matches_reference_mcmc_py(tag, prior):
+    """Golden decisions were produced by the REFERENCE's own vaemolsim/mcmc.py (tests/golden/make_goldens.py)."""
+    g = np.load(os.path.join(GOLD, 'mcmc_reference_%s.npz' % tag))
+    P = vae.init_vae(1003, prior=prior, flow_hidden=16, num_bins=8, hidden=32)
+    model = omc.OracleVAE(P, noise_seed=777)
+    rng = np.random.default_rng(4002)
+    configs, energies, n_acc = g['x0'], None, 0
+    for s in range(5):
+        configs, energies, acc = omc.single_step(model, omc.quadratic_energy, rng, configs, energies)
+        assert np.array_equal(acc, g['acc_%d' % s])
+        assert np.array_equal(configs, g['configs_%d' % s]) and np.array_equal(energies, g['energies_%d' % s])
+        assert np.array_equal(omc.accept(g['e_new_%d' % s], g['e_old_%d' % s], g['fwd_%d' % s], g['rev_%d' % s],
+                                         g['log_rand_%d' % s]), acc)
+        n_acc += acc.sum()
+    assert float(g['num_trials']) == 5 * 64 and float(g['num_acc']) == n_acc
