@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""Benchmark of the vaemolsim hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c1]
+
+Workload (BASELINE.json configs[1], SURVEY 8d "C2"): flow-prior VAE -- encoder FCDeepNN 6->200->4 + IndependentNormal,
+prior = RQSSplineRealNVP(4 blocks, 32 bins, hidden 100) over N(0, I_2), decoder FCDeepNN 2->200->12 + IndependentNormal,
+KLDivergenceEstimate + LogProbLoss -- batch 4096 configurations PER GPU (weak scaling), synthetic N(0,1) inputs,
+random-init weights (44,396 parameters).  One step = ELBO forward + backward (+ the single gradient allreduce when
+N > 1) + Adam update.  Metric: configs/sec, whole job.
+
+Lines printed (one JSON object, rank 0):
+  value        inputs resident in HBM; per-step CUDA events on the launching stream; L2 flushed between timed steps
+  e2e          same step through the public API (`VAE.train_step`) from PINNED HOST buffers: H2D of x and eps, D2H of
+               the loss scalars, wall clock, every step
+  roofline     the dominant kernel of the step, timed alone with CUDA events at the workload's shape
+  cpu_baseline the NumPy oracle (CPU restatement; TF/TFP are not installable here) on a bounded sample, rank 0
+`--impl reference` times that CPU restatement as the reference arm (the reference's TF path cannot run in this image).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (dx, dz, hidden, prior, num_blocks, num_bins, flow_hidden, batch per GPU)
+    'c2': dict(dx=6, dz=2, hidden=200, prior='realnvp', num_blocks=4, num_bins=32, flow_hidden=100, batch=4096,
+               label='C2 flow-prior VAE (RealNVP-RQS 4 blocks K=32 H=100 over N(0,I_2); enc 6-200-4, dec 2-200-12), '
+               'ELBO fwd+bwd+Adam, batch 4096 per GPU'),
+    'c1': dict(dx=6, dz=2, hidden=200, prior='normal', num_blocks=0, num_bins=32, flow_hidden=100, batch=4096,
+               label='C1 Gaussian VAE (N(0,I) prior; enc 6-200-4, dec 2-200-12), ELBO fwd+bwd+Adam, batch 4096 per GPU'),
+}
+METRIC = 'configs/sec ELBO fwd+bwd'
+UNIT = 'configs/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0, help='rows per GPU (default: the named config, 4096)')
+    ap.add_argument('--no-extras', action='store_true', help='skip roofline microbenchmarks and the CPU baseline')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def oracle_step_fn(w):
+    """One CPU step of the same workload on the NumPy oracle: ELBO forward + analytic backward + Adam."""
+    from oracle import vae as ovae
+    P = ovae.init_vae(2003, dx=w['dx'], dz=w['dz'], hidden=w['hidden'], prior=w['prior'], num_blocks=w['num_blocks'],
+                      num_bins=w['num_bins'], flow_hidden=w['flow_hidden'])
+    theta = ovae.flatten(ovae.param_list(P))
+    m, v = np.zeros_like(theta), np.zeros_like(theta)
+    state = {'t': 0}
+
+    def step(x, eps):
+        out, G = ovae.elbo_backward(P, x, eps)
+        state['t'] += 1
+        g = ovae.flatten(ovae.grad_list(P, G))
+        ovae.adam_step(theta, g, m, v, state['t'])  # (the oracle keeps per-layer arrays; the flat update is timed too)
+        return float(out['loss'])
+
+    return step
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def time_cpu(w, rows, steps, warmup):
+    step = oracle_step_fn(w)
+    rng = np.random.default_rng(1001)
+    x = rng.standard_normal((rows, w['dx']), dtype=np.float32)
+    eps = rng.standard_normal((rows, w['dz']), dtype=np.float32)
+    for _ in range(warmup):
+        step(x, eps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(x, eps)
+    dt = time.perf_counter() - t0
+    return rows * steps / dt, dt / steps
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    batch = args.batch or w['batch']
+    # bounded sample: probe one full batch, then size the per-step sample so the whole run stays within ~2 minutes
+    _, t_full = time_cpu(w, batch, 1, 1)
+    budget = 120.0
+    rows = batch
+    total = (args.steps + args.warmup) * t_full
+    if total > budget:
+        rows = max(32, int(batch * budget / total) // 32 * 32)
+    value, sec = time_cpu(w, rows, args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': w['label'], 'rows_per_step': rows,
+                   'note': 'CPU NumPy restatement of the reference path (oracle/); TF<=2.15 / TFP<=0.23 are not '
+                           'installable in this image (Python 3.12, no network)'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
+                         'sample': '%d steps of %d configs (of the %d-config batch)' % (args.steps, rows, batch)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def count(self):
+        return len(self.rows)
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, ln in self.rows:
+            if t < t0 or t > t1:
+                continue
+            f = [s.strip() for s in ln.split(',')]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def pinned_array(lib, shape, dtype=np.float32):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    lib.vms_malloc_host(C.byref(p), n)
+    buf = (C.c_byte * n).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+class Events(object):
+
+    def __init__(self, c, n):
+        self.c = c
+        self.ev = []
+        for _ in range(2 * n):
+            e = C.c_void_p()
+            c.lib.vms_event_create(C.byref(e))
+            self.ev.append(e.value)
+
+    def record(self, i):
+        self.c.lib.vms_event_record(self.ev[i], self.c.stream)
+
+    def elapsed_ms(self, i, j):
+        ms = C.c_float(0)
+        self.c.lib.vms_event_elapsed_ms(self.ev[i], self.ev[j], C.byref(ms))
+        return ms.value
+
+
+def build_model(v, w, batch):
+    from vaemolsim_b200 import dists, flows, losses, models
+    import vaemolsim_b200._protocols as PR
+    v.set_seed(2003)
+    enc = models.MappingToDistribution(PR.IndependentNormal(w['dz']), name='encoder')
+    dec = models.MappingToDistribution(PR.IndependentNormal(w['dx']), name='decoder')
+    enc.mapping.hidden_dim = [w['hidden']]
+    dec.mapping.hidden_dim = [w['hidden']]
+    latent = PR.DistributionLambda(lambda t: PR.StandardNormal(t.shape[0], w['dz']))
+    if w['prior'] == 'normal':
+        prior = latent
+    else:
+        flow = flows.RQSSplineRealNVP(num_blocks=w['num_blocks'],
+                                      rqs_params=dict(bin_range=[-10.0, 10.0], num_bins=w['num_bins'],
+                                                      hidden_dim=w['flow_hidden']))
+        prior = dists.FlowedDistribution(flow, latent)
+    model = models.VAE(enc, dec, prior, regularizer=losses.KLDivergenceEstimate())
+    model(np.zeros((2, w['dx']), np.float32))  # builds every layer (reference idiom: call once on data)
+    model.compile(optimizer=models.Adam(learning_rate=1e-3), loss=losses.LogProbLoss())
+    model.fused(batch)
+    return model
+
+
+def kernel_microbench(v, w, batch, reps=20):
+    """CUDA-event timings of the HBM-bound kernels, alone: at the workload's shape (cold L2) and at a streaming size."""
+    c = v._abi.ctx()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_kind = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+    K = w['num_bins']
+    flush = v.Tensor((64 << 20, ))  # 256 MiB > 126 MB L2
+    ev = Events(c, 1)
+    rng = np.random.default_rng(5)
+    res = {}
+
+    def timed(fn, n_rep, do_flush):
+        ts = []
+        for _ in range(n_rep):
+            if do_flush:
+                c.lib.vms_memset(flush.ptr, 0, flush.nbytes, c.stream)
+            ev.record(0)
+            fn()
+            ev.record(1)
+            c.synchronize()
+            ts.append(ev.elapsed_ms(0, 1))
+        return float(np.mean(ts[2:])) if len(ts) > 4 else float(np.mean(ts))
+
+    for tag, n in (('workload', batch), ('stream', 1 << 21)):
+        rw = v.Tensor.from_numpy(rng.standard_normal((n, K), dtype=np.float32))
+        rh = v.Tensor.from_numpy(rng.standard_normal((n, K), dtype=np.float32))
+        rs = v.Tensor.from_numpy(rng.standard_normal((n, K - 1), dtype=np.float32))
+        x = v.Tensor.from_numpy(rng.uniform(-10, 10, n).astype(np.float32))
+        g = v.Tensor.from_numpy(rng.standard_normal(n, dtype=np.float32))
+        y, l = v.Tensor((n, )), v.Tensor((n, ))
+        gi, gw, gh, gs = v.Tensor((n, )), v.Tensor((n, K)), v.Tensor((n, K)), v.Tensor((n, K - 1))
+        fwd_bytes = n * (4 * (3 * K - 1) + 12)
+        bwd_bytes = n * (2 * 4 * (3 * K - 1) + 4 + 8 + 4)
+        for name, nbytes, fn in (
+            ('rqs_forward', fwd_bytes, lambda: c.lib.vms_rqs_forward(x.ptr, rw.ptr, rh.ptr, rs.ptr, n, K, -10.0, 10.0,
+                                                                     y.ptr, l.ptr, c.stream)),
+            ('rqs_inverse', fwd_bytes, lambda: c.lib.vms_rqs_inverse(x.ptr, rw.ptr, rh.ptr, rs.ptr, n, K, -10.0, 10.0,
+                                                                     y.ptr, l.ptr, c.stream)),
+            ('rqs_backward', bwd_bytes, lambda: c.lib.vms_rqs_backward(x.ptr, rw.ptr, rh.ptr, rs.ptr, n, K, -10.0, 10.0,
+                                                                       1, g.ptr, g.ptr, gi.ptr, gw.ptr, gh.ptr, gs.ptr,
+                                                                       c.stream)),
+        ):
+            ms = timed(fn, reps, True)
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            res['%s@%s' % (name, tag)] = {'n_elem': n, 'ms': ms, 'bytes': nbytes, 'gbs': gbs, 'frac': gbs / peak}
+    # decoder-distribution log_prob (K4) and neighbour selection (K6) at streaming sizes
+    n, D = 1 << 22, w['dx']
+    xx = v.Tensor.from_numpy(rng.standard_normal((n, D), dtype=np.float32))
+    pp = v.Tensor.from_numpy(rng.standard_normal((n, 2 * D), dtype=np.float32))
+    lp = v.Tensor((n, ))
+    i32 = lambda a: (C.c_int32 * len(a))(*a)
+    kind, loc, loc2, sc = i32([0] * D), i32(list(range(D))), i32([-1] * D), i32(list(range(D, 2 * D)))
+    ms = timed(lambda: c.lib.vms_blockwise_log_prob(xx.ptr, D, pp.ptr, 2 * D, n, D, kind, loc, loc2, sc, 1, lp.ptr, 0,
+                                                    c.stream), reps, True)
+    nbytes = n * (3 * D * 4 + 4)
+    res['normal_log_prob@stream'] = {'n_rows': n, 'ms': ms, 'bytes': nbytes, 'gbs': nbytes / ms / 1e6,
+                                     'frac': nbytes / ms / 1e6 / peak}
+    Bs, N, k = 1024, 10000, 50  # C3 shape, 1024 reference rows (coords replicated per row as the API requires)
+    coords = v.Tensor.from_numpy(np.broadcast_to(rng.uniform(-23.2, 23.2, (1, N, 3)).astype(np.float32), (Bs, N, 3)))
+    ref = v.Tensor.from_numpy(rng.uniform(-23.2, 23.2, (Bs, 3)).astype(np.float32))
+    box = v.Tensor.from_numpy(np.full(3, 46.416, np.float32))
+    oxyz = v.Tensor((Bs, k, 3))
+    ms = timed(lambda: c.lib.vms_dist_select(coords.ptr, None, Bs, N, ref.ptr, box.ptr, 0, 9.0, k, None, 0, oxyz.ptr,
+                                             None, None, c.stream), reps, True)
+    nbytes = Bs * (12 * N + 12 + k * 12)
+    res['dist_select@C3x1024'] = {'rows': Bs, 'N': N, 'k': k, 'ms': ms, 'bytes': nbytes, 'gbs': nbytes / ms / 1e6,
+                                  'frac': nbytes / ms / 1e6 / peak}
+    return res, peak, peak_kind
+
+
+def run_b200(args, w):
+    import vaemolsim_b200 as v
+    from vaemolsim_b200 import parallel
+    grp = parallel.Group()
+    rank, world = grp.rank, grp.world
+    c = v._abi.ctx()
+    lib = c.lib
+    batch = args.batch or w['batch']
+    K, W = args.steps, args.warmup
+    model = build_model(v, w, batch)
+    f = model.fused(batch)
+    opt = model.optimizer
+    # synthetic inputs keyed by the GLOBAL row index of this rank's shard (results independent of the rank count)
+    row0 = rank * batch
+    rng = parallel.global_row_seed(1001, row0)
+    n_sets = 4  # rotate a few input sets so consecutive steps do not see identical data
+    xs_host = [pinned_array(lib, (batch, w['dx'])) for _ in range(n_sets)]
+    es_host = [pinned_array(lib, (batch, w['dz'])) for _ in range(n_sets)]
+    for a in xs_host + es_host:
+        a[...] = rng.standard_normal(a.shape, dtype=np.float32)
+    xs = [v.Tensor.from_numpy(a) for a in xs_host]
+    es = [v.Tensor.from_numpy(a) for a in es_host]
+    flush = v.Tensor((64 << 20, ))  # 256 MiB float32 > 126 MB L2
+    gt = ext = None
+    if world > 1:
+        gt, ext = grp.wrap_device_buffer(f.grad.ptr, f.n_params, c.stream)
+
+    def step(i):
+        f.forward_backward(xs[i % n_sets], es[i % n_sets])
+        if world > 1:
+            grp.allreduce_sum_(gt, ext)  # the single data-path collective (NCCL over NVLink), in place
+        f.adam_step(opt, grad_scale=1.0 / world)
+
+    sampler = ClockSampler(c.device)
+    sampler.start()
+    for i in range(max(W, 3)):
+        step(i)
+    c.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM, per-step CUDA events, L2 flushed (untimed) between steps
+    ev = Events(c, K)
+    grp.barrier()
+    c.synchronize()
+    launches0 = v._abi.launch_count()
+    t_clock0 = time.perf_counter()
+    wall0 = time.perf_counter()
+    for i in range(K):
+        lib.vms_memset(flush.ptr, 0, flush.nbytes, c.stream)
+        ev.record(2 * i)
+        step(i)
+        ev.record(2 * i + 1)
+    c.synchronize()
+    grp.barrier()
+    wall1 = time.perf_counter()
+    launches = v._abi.launch_count() - launches0
+    dev_ms = sum(ev.elapsed_ms(2 * i, 2 * i + 1) for i in range(K))
+    dev_ms = grp.max(dev_ms)
+    ms_per_step = dev_ms / K
+    value = world * batch * K / (dev_ms * 1e-3)
+
+    # ---- timed region 2: end to end through the public API from pinned host memory
+    def e2e_step(i):
+        xd = v.Tensor.from_numpy(xs_host[i % n_sets])  # H2D (pinned)
+        ed = v.Tensor.from_numpy(es_host[i % n_sets])
+        f.forward_backward(xd, ed)
+        if world > 1:
+            grp.allreduce_sum_(gt, ext)
+        f.adam_step(opt, grad_scale=1.0 / world)
+        return f.scalars.numpy()  # D2H of {loss, nll, kl}: synchronises the step
+
+    for i in range(3):
+        e2e_step(i)
+    grp.barrier()
+    c.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        last = e2e_step(i)
+    c.synchronize()
+    e2e_s = grp.max(time.perf_counter() - t0)
+    e2e_value = world * batch * K / e2e_s
+    # keep the same load going until the clock sampler has a few samples inside a loaded window
+    t_load = time.perf_counter()
+    while sampler.count() < 8 and time.perf_counter() - t_load < 3.0:
+        for i in range(50):
+            step(i)
+        c.synchronize()
+    t_clock1 = time.perf_counter()
+    clocks = sampler.stop(t_clock0, t_clock1)
+
+    if rank != 0:
+        grp.close()
+        return
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': w['label'], 'global_batch': world * batch, 'params': f.n_params,
+                   'parallelism': 'dp%d' % world if world > 1 else 'single',
+                   'collective': 'one NCCL allreduce(sum) of the flat gradient per step' if world > 1 else 'none',
+                   'l2': 'flushed between timed steps (256 MiB memset, outside the per-step events)',
+                   'timing': 'sum of per-step CUDA-event intervals on the launching stream, max over ranks',
+                   'wall_s_timed_region_incl_flush': wall1 - wall0},
+        'e2e': {'value': e2e_value, 'unit': UNIT,
+                'h2d_bytes_per_step': int(xs_host[0].nbytes + es_host[0].nbytes), 'd2h_bytes_per_step': 16,
+                'ms_per_step': e2e_s / K * 1e3, 'api': 'FusedELBO.forward_backward + adam_step (VAE.train_step path)',
+                'last_loss': float(last[0])},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+    }
+    if not args.no_extras:
+        micro, peak, peak_kind = kernel_microbench(v, w, batch)
+        dom = micro['rqs_backward@workload']
+        line['roofline'] = {'bound': 'hbm', 'kernel': 'rqs_backward_kernel<%d>' % w['num_bins'],
+                            'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s', 'frac': dom['gbs'] / peak,
+                            'traffic': None, 'peak_kind': peak_kind,
+                            'algorithmic_bytes_per_launch': dom['bytes'], 'launch_ms': dom['ms'],
+                            'note': 'timed alone with CUDA events at the workload shape (%d elements, cold L2); '
+                                    'streaming-size fractions are under "kernels"' % batch}
+        line['roofline_step'] = {'algorithmic_bytes_per_config': 40 + (4 * (392 + 776) if w['prior'] != 'normal' else 0),
+                                 'gbs': (40 + (4 * (392 + 776) if w['prior'] != 'normal' else 0)) * batch /
+                                 (ms_per_step * 1e-3) / 1e9}
+        line['kernels'] = micro
+        rows = batch
+        cpu_val, cpu_sec = time_cpu(w, rows, 10, 2)
+        line['cpu_baseline'] = {'value': cpu_val, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
+                                'sample': '10 steps of %d configs, NumPy oracle (ELBO fwd + analytic bwd + Adam)' % rows,
+                                'ms_per_step': cpu_sec * 1e3}
+    print(json.dumps(line), flush=True)
+    grp.close()
+
+
+def main():
+    args = parse()
+    w = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,401 @@
+"""GPU parity tests of the individual kernels THROUGH THE C ABI (ctypes) against the CPU oracle.
+
+Tolerances: 1e-5 relative (+1e-6 absolute near zero) for float32 log-probs / log-dets / gradients (north_star);
+bit-exact for neighbour-selection outputs / indices and MC accept / reject decisions.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_close
+from oracle import dists as odists
+from oracle import mappings as omap
+from oracle import mcmc as omc
+from oracle import rqs as orqs
+from oracle import vae as ovae
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def T(v, a, dtype=np.float32):
+    return v.Tensor.from_numpy(np.ascontiguousarray(a, dtype=dtype))
+
+
+def _raw(rng, n, K, scale=1.5):
+    return (rng.normal(0, scale, (n, K)).astype(np.float32), rng.normal(0, scale, (n, K)).astype(np.float32),
+            rng.normal(0, scale, (n, K - 1)).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------------ K1: RQS
+@pytest.mark.parametrize('K', [32, 20, 8, 47, 2])
+@pytest.mark.parametrize('n', [1, 127, 129, 1000])
+def test_rqs_forward_inverse_match_oracle(vms, K, n):
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(K * 1000 + n)
+    rw, rh, rs = _raw(rng, n, K)
+    x = rng.uniform(-11, 11, n).astype(np.float32)
+    x[::17] = 10.0  # exactly on the upper boundary: identity
+    d = [T(v, a) for a in (x, rw, rh, rs)]
+    for name, ofn in (('vms_rqs_forward', orqs.rqs_forward_raw), ('vms_rqs_inverse', orqs.rqs_inverse_raw)):
+        y, l = v.Tensor((n, )), v.Tensor((n, ))
+        getattr(c.lib, name)(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, n, K, -10.0, 10.0, y.ptr, l.ptr, c.stream)
+        # reference in float64 from the same float32 logits: the float32 oracle itself carries ~1e-6 rounding noise
+        yo, lo = ofn(x.astype(np.float64), rw.astype(np.float64), rh.astype(np.float64), rs.astype(np.float64), -10.0, 10.0)
+        assert_close(y.numpy(), yo, rtol=1e-5, atol=2e-6, what='%s value K=%d' % (name, K))
+        assert_close(l.numpy(), lo, rtol=1e-5, atol=3e-6, what='%s ldj K=%d' % (name, K))
+        y32, l32 = ofn(x, rw, rh, rs, -10.0, 10.0)
+        assert_close(y.numpy(), y32, rtol=2e-5, atol=2e-5, what='%s vs float32 oracle' % name)
+        oob = (x <= -10) | (x >= 10)
+        assert np.array_equal(y.numpy()[oob], x[oob]) and np.all(l.numpy()[oob] == 0)
+
+
+def test_rqs_round_trip_at_scale(vms):
+    """Size-independent property at 2M elements: inverse(forward(x)) == x, ildj == -fldj, monotone."""
+    v = vms
+    c = v._abi.ctx()
+    n, K = 1 << 21, 32
+    rng = np.random.default_rng(0)
+    rw, rh, rs = _raw(rng, n, K)
+    x = rng.uniform(-10.5, 10.5, n).astype(np.float32)
+    dx, dw, dh, ds = (T(v, a) for a in (x, rw, rh, rs))
+    y, fl, xb, il = v.Tensor((n, )), v.Tensor((n, )), v.Tensor((n, )), v.Tensor((n, ))
+    c.lib.vms_rqs_forward(dx.ptr, dw.ptr, dh.ptr, ds.ptr, n, K, -10.0, 10.0, y.ptr, fl.ptr, c.stream)
+    c.lib.vms_rqs_inverse(y.ptr, dw.ptr, dh.ptr, ds.ptr, n, K, -10.0, 10.0, xb.ptr, il.ptr, c.stream)
+    xb, fl, il = xb.numpy(), fl.numpy(), il.numpy()
+    # a float32 round trip through a bin of slope s loses ~ulp(10)/s; bound the error by the local derivative
+    err = np.abs(xb - x)
+    assert np.all(err <= 4e-6 * (1 + np.exp(-fl)) + 2e-5), err.max()
+    assert np.median(err) < 2e-6
+    assert np.all(np.abs(il + fl) <= 2e-4 + 1e-4 * np.abs(fl)), np.abs(il + fl).max()
+
+
+@pytest.mark.parametrize('Dt,K', [(1, 32), (2, 20), (3, 8), (5, 32)])
+def test_rqs_strided_event_sum(vms, Dt, K):
+    """Coupling-layer form: column slices of a [B, D] tensor, fused [w|h|s] parameter rows, event-summed ldj."""
+    v = vms
+    c = v._abi.ctx()
+    B, D = 333, Dt + 2
+    rng = np.random.default_rng(Dt * 100 + K)
+    ldr = Dt * (3 * K - 1)
+    raw = rng.normal(0, 1.5, (B, ldr)).astype(np.float32)
+    x = rng.uniform(-11, 11, (B, D)).astype(np.float32)
+    prev = rng.normal(size=B).astype(np.float32)
+    nw = Dt * K
+    rw, rh, rs = raw[:, :nw].reshape(B, Dt, K), raw[:, nw:2 * nw].reshape(B, Dt, K), raw[:, 2 * nw:].reshape(B, Dt, K - 1)
+    dX, dR = T(v, x), T(v, raw)
+    for inv, ofn in ((0, orqs.rqs_forward_raw), (1, orqs.rqs_inverse_raw)):
+        out = T(v, x)
+        lsum = T(v, prev)
+        lel = v.Tensor((B, Dt))
+        a = v._abi.RqsArgs(B, Dt, K, -10.0, 10.0, dX.ptr + 4, D, dR.ptr, ldr, dR.ptr + 4 * nw, ldr, dR.ptr + 8 * nw, ldr,
+                           out.ptr + 4, D, lel.ptr, lsum.ptr, 1, inv)
+        c.lib.vms_rqs_apply(C.byref(a), c.stream)
+        yo, lo = ofn(x[:, 1:1 + Dt].astype(np.float64), rw.astype(np.float64), rh.astype(np.float64), rs.astype(np.float64),
+                     -10.0, 10.0)
+        got = out.numpy()
+        assert np.array_equal(got[:, 0], x[:, 0]) and np.array_equal(got[:, 1 + Dt:], x[:, 1 + Dt:])
+        assert_close(got[:, 1:1 + Dt], yo, rtol=1e-5, atol=2e-6, what='strided value')
+        assert_close(lel.numpy(), lo, rtol=1e-5, atol=3e-6, what='strided per-element ldj')
+        assert_close(lsum.numpy(), prev + lo.sum(-1), rtol=1e-5, atol=5e-6, what='accumulated event sum')
+
+
+@pytest.mark.parametrize('K', [32, 20, 6])
+@pytest.mark.parametrize('inverse_dir', [0, 1])
+def test_rqs_backward_matches_oracle(vms, K, inverse_dir):
+    v = vms
+    c = v._abi.ctx()
+    n = 777
+    rng = np.random.default_rng(K + inverse_dir)
+    rw, rh, rs = _raw(rng, n, K, 1.0)
+    x = rng.uniform(-10.5, 10.5, n).astype(np.float32)
+    g_out, g_ldj = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
+    d = [T(v, a) for a in (x, rw, rh, rs, g_out, g_ldj)]
+    g_in, g_w, g_h, g_s = v.Tensor((n, )), v.Tensor((n, K)), v.Tensor((n, K)), v.Tensor((n, K - 1))
+    c.lib.vms_rqs_backward(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, n, K, -10.0, 10.0, inverse_dir, d[4].ptr, d[5].ptr,
+                           g_in.ptr, g_w.ptr, g_h.ptr, g_s.ptr, c.stream)
+    f64 = lambda a: a.astype(np.float64)
+    o = orqs.rqs_backward_raw(f64(x), f64(rw), f64(rh), f64(rs), -10.0, 10.0, f64(g_out), f64(g_ldj),
+                              inverse_dir=bool(inverse_dir))
+    for got, want, nm in zip((g_in, g_w, g_h, g_s), o, ('g_in', 'g_raw_w', 'g_raw_h', 'g_raw_s')):
+        scale = np.abs(want).max()
+        assert_close(got.numpy(), want, rtol=1e-5, atol=2e-6 * max(1.0, scale), what='%s K=%d inv=%d' % (nm, K, inverse_dir))
+
+
+# ------------------------------------------------------------------------------------------------ K2/K3: dense
+@pytest.mark.parametrize('B,K,N,act', [(4096, 6, 200, 1), (4096, 200, 4, 0), (1000, 100, 95, 0), (130, 1, 100, 2),
+                                       (65, 17, 130, 2), (1, 3, 5, 1)])
+def test_dense_forward_backward(vms, B, K, N, act):
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(B + K + N)
+    x = rng.normal(size=(B, K)).astype(np.float32)
+    W = (rng.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    g = rng.normal(size=(B, N)).astype(np.float32)
+    dx, dW, db, dg = (T(v, a) for a in (x, W, b, g))
+    out = v.Tensor((B, N))
+    c.lib.vms_dense_forward(dx.ptr, K, dW.ptr, db.ptr, B, K, N, act, None, 0, None, 0, out.ptr, N, c.stream)
+    pre = x.astype(np.float64) @ W.astype(np.float64) + b
+    want = [pre, np.maximum(pre, 0), np.tanh(pre)][act]
+    assert_close(out.numpy(), want, rtol=1e-5, atol=1e-5, what='dense forward')
+    ws = v.Tensor((max(1, c.lib.vms_dense_backward_workspace(B, K, N, 0) // 4), ))
+    gx, gW, gb = v.Tensor((B, K)), v.Tensor((K, N)), v.Tensor((N, ))
+    c.lib.vms_dense_backward(dx.ptr, K, dW.ptr, B, K, N, act, out.ptr, N, dg.ptr, N, None, 0, None, 0, gx.ptr, K, 0,
+                             gW.ptr, gb.ptr, None, 0, None, 0, ws.ptr, c.stream)
+    o = out.numpy().astype(np.float64)
+    gpre = g * [np.ones_like(o), (o > 0).astype(np.float64), 1 - o * o][act]
+    sc = np.sqrt(B)
+    assert_close(gx.numpy(), gpre @ W.T.astype(np.float64), rtol=1e-5, atol=2e-5, what='dense g_x')
+    assert_close(gW.numpy(), x.T.astype(np.float64) @ gpre, rtol=1e-5, atol=2e-6 * sc, what='dense g_W')
+    assert_close(gb.numpy(), gpre.sum(0), rtol=1e-5, atol=2e-6 * sc, what='dense g_b')
+
+
+def test_dense_ones_input_and_conditional(vms):
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(5)
+    B, N, Cn = 300, 70, 3
+    W = rng.normal(size=(1, N)).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    cond = rng.normal(size=(B, Cn)).astype(np.float32)
+    Wc = rng.normal(size=(Cn, N)).astype(np.float32)
+    dW, db, dc, dWc = (T(v, a) for a in (W, b, cond, Wc))
+    out = v.Tensor((B, N))
+    c.lib.vms_dense_forward(None, 1, dW.ptr, db.ptr, B, 1, N, 2, dc.ptr, Cn, dWc.ptr, Cn, out.ptr, N, c.stream)
+    assert_close(out.numpy(), np.tanh(W[0] + b + cond.astype(np.float64) @ Wc), rtol=1e-5, atol=1e-6, what='ones+cond')
+    with pytest.raises(ValueError):
+        c.lib.vms_dense_forward(None, 1, dW.ptr, db.ptr, B, 2, N, 0, None, 0, None, 0, out.ptr, N, c.stream)
+
+
+# ------------------------------------------------------------------------------------------------ K4/K5: log-probs
+def test_blockwise_log_prob_and_params(vms):
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(6)
+    B = 5000
+    # dofs: Normal, VonMises, Normal, VonMises, contiguous per-dof parameter groups (dists.py:210)
+    kinds = ['normal', 'vonmises', 'normal', 'vonmises']
+    params = rng.normal(0, 2, (B, 10)).astype(np.float32)
+    params[:50, 4] = rng.uniform(5, 60, 50)  # large concentrations: second Chebyshev branch of i0e
+    x = rng.uniform(-np.pi, np.pi, (B, 4)).astype(np.float32)
+    want = odists.independent_blockwise_log_prob(x.astype(np.float64), params.astype(np.float64), kinds)
+    i32 = lambda a: (C.c_int32 * len(a))(*a)
+    kind, loc, loc2, sc = i32([0, 1, 0, 1]), i32([0, 2, 5, 7]), i32([-1, 3, -1, 8]), i32([1, 4, 6, 9])
+    dX, dP = T(v, x), T(v, params)
+    lp = v.Tensor((B, ))
+    c.lib.vms_blockwise_log_prob(dX.ptr, 4, dP.ptr, 10, B, 4, kind, loc, loc2, sc, 2, lp.ptr, 0, c.stream)
+    assert_close(lp.numpy(), want, rtol=1e-5, atol=1e-5, what='blockwise log_prob')
+    L, S = v.Tensor((B, 4)), v.Tensor((B, 4))
+    c.lib.vms_blockwise_params(dP.ptr, 10, B, 4, kind, loc, loc2, sc, 2, L.ptr, S.ptr, c.stream)
+    t = odists.param_transform('vonmises', params[:, 2:5].astype(np.float64))
+    assert_close(L.numpy()[:, 1], t['loc'], rtol=1e-6, atol=1e-6, what='vonmises loc')
+    assert_close(S.numpy()[:, 1], t['concentration'], rtol=1e-6, atol=1e-7, what='vonmises concentration')
+
+
+def test_param_transform_known_answers(vms):
+    """tests/test_dists.py:15-30 through the host API."""
+    d = vms.dists
+    t = d.make_param_transform(d.Normal)(np.zeros((1, 2), np.float32))
+    assert t['loc'].numpy()[0] == 0 and np.isclose(t['scale'].numpy()[0], np.log(2.0), rtol=1e-6)
+    t = d.make_param_transform(d.VonMises)(np.array([[0.0, -1.0, 0.0]], np.float32))
+    assert np.isclose(t['loc'].numpy()[0], np.pi, rtol=1e-6)
+    assert np.isclose(t['concentration'].numpy()[0], np.log(2.0), rtol=1e-6)
+
+
+def test_normal_sample_log_prob_and_backward(vms):
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(7)
+    B, D = 4097, 6
+    p = rng.normal(size=(B, 2 * D)).astype(np.float32)
+    eps = rng.normal(size=(B, D)).astype(np.float32)
+    dP, dE = T(v, p), T(v, eps)
+    z, lp = v.Tensor((B, D)), v.Tensor((B, ))
+    c.lib.vms_normal_sample_log_prob(dP.ptr, 2 * D, 0, D, 1, dE.ptr, B, D, z.ptr, D, lp.ptr, c.stream)
+    loc, scale = odists.independent_normal_params(p, D)
+    zo = odists.normal_sample(loc, scale, eps)
+    assert_close(z.numpy(), zo, rtol=1e-6, atol=1e-6, what='reparameterised sample')
+    assert_close(lp.numpy(), odists.normal_log_prob(zo.astype(np.float64), loc.astype(np.float64),
+                                                    scale.astype(np.float64)).sum(-1), rtol=1e-5, atol=1e-5, what='logq')
+    g = rng.normal(size=B).astype(np.float32)
+    x = rng.normal(size=(B, D)).astype(np.float32)
+    dG, dX = T(v, g), T(v, x)
+    gx, gp = v.Tensor((B, D)), v.Tensor((B, 2 * D))
+    c.lib.vms_normal_log_prob_backward(dX.ptr, D, dP.ptr, 2 * D, 0, D, 1, dG.ptr, B, D, gx.ptr, D, 0, gp.ptr, 2 * D,
+                                       c.stream)
+    ox, ol, os_ = ovae._normal_lp_bwd(x.astype(np.float64), loc.astype(np.float64), scale.astype(np.float64),
+                                      g.astype(np.float64))
+    assert_close(gx.numpy(), ox, rtol=1e-5, atol=1e-5, what='d logp / dx')
+    assert_close(gp.numpy()[:, :D], ol, rtol=1e-5, atol=1e-5, what='d logp / dloc')
+    assert_close(gp.numpy()[:, D:], os_ * orqs.sigmoid(p[:, D:].astype(np.float64)), rtol=1e-5, atol=1e-5, what='d/draw')
+
+
+@pytest.mark.parametrize('B', [1, 100, 8192, 8193, 300000])
+def test_kl_and_mean_reductions(vms, B):
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(B)
+    a, b = rng.normal(size=B).astype(np.float32), rng.normal(size=B).astype(np.float32)
+    dA, dB = T(v, a), T(v, b)
+    out = v.Tensor((1, ))
+    c.lib.vms_kl_mean(dA.ptr, dB.ptr, B, 2.5, out.ptr, c.stream)
+    ref = 2.5 * np.mean(a.astype(np.float64) - b)
+    assert abs(out.numpy()[0] - ref) <= 1e-5 * max(1.0, abs(ref)) + 3e-7 * np.sqrt(B)
+    first = out.numpy()[0]
+    c.lib.vms_kl_mean(dA.ptr, dB.ptr, B, 2.5, out.ptr, c.stream)
+    assert out.numpy()[0] == first  # deterministic
+    c.lib.vms_scaled_mean(dA.ptr, B, -1.0, out.ptr, c.stream)
+    assert abs(out.numpy()[0] + np.mean(a.astype(np.float64))) <= 1e-5 + 3e-7 * np.sqrt(B)
+    # exact identities of tests/test_losses.py:55-70: weight linearity is a single float32 multiply of the same mean
+    o1, o100 = v.Tensor((1, )), v.Tensor((1, ))
+    c.lib.vms_kl_mean(dA.ptr, dB.ptr, B, 1.0, o1.ptr, c.stream)
+    c.lib.vms_kl_mean(dA.ptr, dB.ptr, B, 100.0, o100.ptr, c.stream)
+    assert o100.numpy()[0] == np.float32(100.0) * o1.numpy()[0]
+
+
+# ------------------------------------------------------------------------------------------------ K6: selection
+def _select(v, coords, ref, cutoff, k, box=None, info=None, splits=None, per_row=False):
+    c = v._abi.ctx()
+    if splits is None:
+        B, N = coords.shape[0], coords.shape[1]
+    else:
+        B, N = len(splits) - 1, 0
+    dC = T(v, coords.reshape(-1, 3))
+    dS = None if splits is None else T(v, splits, np.int64)
+    dR = T(v, ref)
+    dB = None if box is None else T(v, box)
+    dI = None if info is None else T(v, info.reshape(-1, info.shape[-1]))
+    P = 0 if info is None else info.shape[-1]
+    oxyz, oidx = v.Tensor((B, k, 3)), v.Tensor((B, k), np.int32)
+    oinfo = None if info is None else v.Tensor((B, k, P))
+    c.lib.vms_dist_select(dC.ptr, None if dS is None else dS.ptr, B, N, dR.ptr, None if dB is None else dB.ptr,
+                          1 if per_row else 0, float(np.float32(cutoff**2)), k, None if dI is None else dI.ptr, P, oxyz.ptr,
+                          None if oinfo is None else oinfo.ptr, oidx.ptr, c.stream)
+    fast = v.Tensor((B, k, 3))  # same call without indices: the single-pass candidate path
+    c.lib.vms_dist_select(dC.ptr, None if dS is None else dS.ptr, B, N, dR.ptr, None if dB is None else dB.ptr,
+                          1 if per_row else 0, float(np.float32(cutoff**2)), k, None, 0, fast.ptr, None, None, c.stream)
+    return oxyz.numpy(), (None if oinfo is None else oinfo.numpy()), oidx.numpy(), fast.numpy()
+
+
+@pytest.mark.parametrize('N,k,cutoff', [(100, 50, 3.0), (1000, 10, 3.0), (1000, 50, 1.0), (5000, 64, 6.0), (30, 50, 3.0),
+                                        (3000, 50, 100.0)])
+def test_dist_select_bit_exact(vms, N, k, cutoff):
+    rng = np.random.default_rng(N + k)
+    B, L = 24, 10.0
+    coords = rng.uniform(0, L, (B, N, 3)).astype(np.float32)
+    coords[:, 5] = coords[:, 3]  # exact duplicates: ties resolved by the lower index
+    ref = rng.uniform(0, L, (B, 3)).astype(np.float32)
+    info = rng.normal(size=(B, N, 2)).astype(np.float32)
+    box = np.array([L, L, L], np.float32)
+    for bx, per_row in ((None, False), (box, False), (np.tile(box * np.float32(1.1), (B, 1)), True)):
+        want = omap.distance_selection(coords, ref, cutoff, k, box_lengths=bx, particle_info=info, return_indices=True)
+        xyz, oinfo, idx, fast = _select(vms, coords, ref, cutoff, k, box=bx, info=info, per_row=per_row)
+        assert np.array_equal(idx, want[2]), 'neighbour indices differ'
+        assert np.array_equal(xyz, want[0]) and np.array_equal(oinfo, want[1])
+        assert np.array_equal(fast, want[0])
+
+
+def test_dist_select_ragged_with_empty_row(vms):
+    """tests/test_mappings.py:88-98 and tests/test_models.py:265-308: 0..N particles per row."""
+    rng = np.random.default_rng(3)
+    lens = np.array([7, 0, 60, 49, 1, 0, 200, 50])
+    rows = [rng.uniform(0, 10, (n, 3)).astype(np.float32) for n in lens]
+    irows = [rng.normal(size=(n, 3)).astype(np.float32) for n in lens]
+    ref = rng.uniform(0, 10, (len(lens), 3)).astype(np.float32)
+    box = np.array([10.0, 10.0, 10.0], np.float32)
+    splits = np.concatenate([[0], np.cumsum(lens)])
+    want = omap.distance_selection(rows, ref, 3.0, 50, box_lengths=box, particle_info=irows, return_indices=True)
+    xyz, oinfo, idx, fast = _select(vms, np.concatenate(rows), ref, 3.0, 50, box=box, info=np.concatenate(irows),
+                                    splits=splits)
+    assert np.array_equal(xyz, want[0]) and np.array_equal(oinfo, want[1]) and np.array_equal(fast, want[0])
+    assert np.array_equal(idx, want[2])
+    assert np.all(xyz[1] == 0) and np.all(xyz[5] == 0)
+
+
+def test_dist_select_layer_identities(vms):
+    """Reference test identities through the layer API (tests/test_mappings.py:62-86)."""
+    m = vms.mappings
+    rng = np.random.default_rng(4)
+    coords = rng.uniform(0, 10, (8, 100, 3)).astype(np.float32)
+    ref = rng.uniform(0, 10, (8, 1, 3)).astype(np.float32)
+    box = np.array([10.0, 10.0, 10.0], np.float32)
+    ds = m.DistanceSelection(3.0)
+    assert ds.sq_cut == 9.0
+    out = ds(coords, ref).numpy()
+    assert out.shape == (8, 50, 3)
+    stored = m.DistanceSelection(3.0, box_lengths=box)(coords, ref).numpy()
+    per_call = ds(coords, ref, box_lengths=np.tile(box, (8, 1))).numpy()
+    assert np.array_equal(stored, per_call) and not np.array_equal(stored, out)
+    info = rng.normal(size=(8, 100, 2)).astype(np.float32)
+    sel, sinfo = m.DistanceSelection(3.0, max_included=10)(coords, ref, particle_info=info)
+    assert sel.shape == (8, 10, 3) and sinfo.shape == (8, 10, 2)
+    rag = m.DistanceSelection(3.0)([coords[0, :5], coords[1, :0], coords[2]], ref[:3]).numpy()
+    assert rag.shape == (3, 50, 3) and np.all(rag[1] == 0)
+
+
+# ------------------------------------------------------------------------------------------------ K7: MC acceptance
+@pytest.mark.parametrize('tag', ['c4a', 'flow'])
+def test_mc_accept_bit_exact_vs_reference_mcmc(vms, tag):
+    """Decisions from the reference's own mcmc.py (golden) reproduced by vms_mc_accept from the same inputs."""
+    v = vms
+    c = v._abi.ctx()
+    g = np.load(os.path.join(GOLD, 'mcmc_reference_%s.npz' % tag))
+    n_acc = v.Tensor.zeros((1, ), np.uint64)
+    for s in range(5):
+        B, D = g['x_old_%d' % s].shape
+        d = dict(e_new=T(v, g['e_new_%d' % s], np.float64), e_old=T(v, g['e_old_%d' % s], np.float64),
+                 fwd=T(v, g['fwd_%d' % s]), rev=T(v, g['rev_%d' % s]), lr=T(v, g['log_rand_%d' % s], np.float64),
+                 x_old=T(v, g['x_old_%d' % s]), x_new=T(v, g['x_new_%d' % s]))
+        e_out, acc = v.Tensor((B, ), np.float64), v.Tensor((B, ), np.uint8)
+        c.lib.vms_mc_accept(d['e_new'].ptr, d['e_old'].ptr, d['fwd'].ptr, d['rev'].ptr, d['lr'].ptr, B, D,
+                            d['x_old'].ptr, d['x_new'].ptr, e_out.ptr, acc.ptr, n_acc.ptr, c.stream)
+        assert np.array_equal(acc.numpy().astype(bool), g['acc_%d' % s])
+        assert np.array_equal(d['x_new'].numpy(), g['configs_%d' % s])
+        assert np.array_equal(e_out.numpy(), g['energies_%d' % s])
+    assert float(n_acc.numpy()[0]) == float(g['num_acc'])
+
+
+def test_mc_accept_random_and_energy(vms):
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(11)
+    B, D = 100003, 6
+    x_old, x_new = rng.normal(size=(B, D)).astype(np.float32), rng.normal(size=(B, D)).astype(np.float32)
+    means = np.linspace(-2, 2, D)
+    dE_old, dE_new = v.Tensor((B, ), np.float64), v.Tensor((B, ), np.float64)
+    dXo, dXn, dM = T(v, x_old), T(v, x_new), T(v, means, np.float64)
+    c.lib.vms_energy_quadratic(dXo.ptr, B, D, dM.ptr, dE_old.ptr, c.stream)
+    c.lib.vms_energy_quadratic(dXn.ptr, B, D, dM.ptr, dE_new.ptr, c.stream)
+    e_old, e_new = omc.quadratic_energy(x_old), omc.quadratic_energy(x_new)
+    assert np.array_equal(dE_old.numpy(), e_old) and np.array_equal(dE_new.numpy(), e_new)
+    fwd, rev = rng.normal(size=B).astype(np.float32) * 5, rng.normal(size=B).astype(np.float32) * 5
+    log_u = np.log(rng.random(B))
+    want = omc.accept(e_new, e_old, fwd, rev, log_u)
+    acc, e_out, n_acc = v.Tensor((B, ), np.uint8), v.Tensor((B, ), np.float64), v.Tensor.zeros((1, ), np.uint64)
+    c.lib.vms_mc_accept(dE_new.ptr, dE_old.ptr, T(v, fwd).ptr, T(v, rev).ptr, T(v, log_u, np.float64).ptr, B, D, dXo.ptr,
+                        dXn.ptr, e_out.ptr, acc.ptr, n_acc.ptr, c.stream)
+    assert np.array_equal(acc.numpy().astype(bool), want) and int(n_acc.numpy()[0]) == int(want.sum())
+    assert np.array_equal(dXn.numpy(), np.where(want[:, None], x_new, x_old))
+    assert np.array_equal(e_out.numpy(), np.where(want, e_new, e_old))
+
+
+# ------------------------------------------------------------------------------------------------ K8: Adam
+def test_adam_matches_oracle(vms):
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(12)
+    n = 44396
+    theta = rng.normal(size=n).astype(np.float32)
+    th_o, m_o, v_o = theta.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    dT, dM, dV = T(v, theta), v.Tensor.zeros((n, )), v.Tensor.zeros((n, ))
+    for t in range(1, 4):
+        parts = rng.normal(size=(3, n)).astype(np.float32)
+        c.lib.vms_adam_step(dT.ptr, T(v, parts).ptr, 3, 0.5, dM.ptr, dV.ptr, n, t, 1e-3, 0.9, 0.999, 1e-7, c.stream)
+        g = ((parts[0] + parts[1]) + parts[2]) * np.float32(0.5)
+        ovae.adam_step(th_o, g, m_o, v_o, t)
+    assert_close(dT.numpy(), th_o, rtol=1e-6, atol=1e-7, what='adam theta')
+    assert_close(dM.numpy(), m_o, rtol=1e-6, atol=1e-8, what='adam m')

@@ -1,0 +1,378 @@
+"""GPU parity tests of the host API (the reference's layer / model / MCMC interface) and of the fused ELBO plan against
+the CPU oracle, plus ports of the reference's own behavioural tests (shapes, errors, counters)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, flat_from_oracle, flat_grad_from_oracle, vae_from_oracle
+from oracle import dists as odists
+from oracle import flows as oflows
+from oracle import mcmc as omc
+from oracle import nets as onets
+from oracle import vae as ovae
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _std(v, B, D):
+    import vaemolsim_b200._protocols as PR
+    return PR.DistributionLambda(lambda t: PR.StandardNormal(B if t is None else t.shape[0], D))
+
+
+# ------------------------------------------------------------------------------------------------ flows
+@pytest.mark.parametrize('D', [1, 2, 3, 5])
+def test_realnvp_flow_matches_oracle(vms, D):
+    v = vms
+    rng = np.random.default_rng(D)
+    K, H, nb = 8, 16, 4
+    flow = v.flows.RQSSplineRealNVP(num_blocks=nb, rqs_params=dict(num_bins=K, hidden_dim=H))
+    x = rng.normal(0, 3, (257, D)).astype(np.float32)
+    y = flow(x)  # builds
+    assert len(flow.chain.bijectors) == nb
+    blocks = []
+    for bij in flow.chain.bijectors[::-1]:
+        sb = bij.bijector_fn
+        W, b = sb.heads.get_weights()
+        W = W + rng.normal(0, 0.3, W.shape).astype(np.float32)  # make the splines non-trivial
+        sb.heads.assign(W, b)
+        d1W, d1b = sb.d1.get_weights()
+        nw = sb.data_dim * K
+        blocks.append(dict(d1=(d1W, d1b), w=(W[:, :nw], b[:nw]), h=(W[:, nw:2 * nw], b[nw:2 * nw]),
+                           s=(W[:, 2 * nw:], b[2 * nw:])))
+    f64 = [{k: (a.astype(np.float64), c.astype(np.float64)) for k, (a, c) in blk.items()} for blk in blocks]
+    yo, flo = oflows.realnvp_forward(x.astype(np.float64), f64, K, (-10.0, 10.0))
+    y = flow(x).numpy()
+    assert_close(y, yo, rtol=1e-5, atol=1e-5, what='RealNVP forward')
+    assert_close(flow.chain.forward_log_det_jacobian(x).numpy(), flo, rtol=1e-5, atol=2e-5, what='RealNVP fldj')
+    xb = flow.chain.inverse(y).numpy()
+    assert_close(xb, x, rtol=1e-5, atol=5e-5, what='RealNVP round trip')
+    # TransformedDistribution.log_prob = base.log_prob(inverse) + ildj  (flows.py:352-353)
+    td = flow(_std(v, 257, D)(v.as_tensor(x)))
+    xo, ilo = oflows.realnvp_inverse(y.astype(np.float64), f64, K, (-10.0, 10.0))
+    want = odists.normal_log_prob(xo, 0.0, 1.0).sum(-1) + ilo
+    assert_close(td.log_prob(y).numpy(), want, rtol=1e-5, atol=2e-5, what='flowed log_prob')
+    s, lp = td.experimental_sample_and_log_prob()
+    assert s.shape == (257, D)
+    assert_close(lp.numpy(), td.log_prob(s).numpy(), rtol=1e-4, atol=2e-4, what='sample_and_log_prob consistency')
+    # without batch norm training=True is bit-equal to training=False (tests/test_flows.py:176)
+    assert np.array_equal(flow(x, training=True).numpy(), flow(x, training=False).numpy())
+
+
+@pytest.mark.parametrize('D,cond', [(1, 0), (3, 0), (3, 2), (6, 0)])
+def test_maf_flow_matches_oracle(vms, D, cond):
+    v = vms
+    rng = np.random.default_rng(10 * D + cond)
+    K, H, nb = 8, 12, 3
+    params = dict(num_bins=K, hidden_dim=H)
+    if cond:
+        params.update(conditional=True, conditional_event_shape=cond)
+    flow = v.flows.RQSSplineMAF(num_blocks=nb, order_seed=42, rqs_params=params)
+    assert flow.conditional == bool(cond)
+    x = rng.normal(0, 2, (130, D)).astype(np.float32)
+    cin = rng.normal(size=(130, cond)).astype(np.float32) if cond else None
+    kw = dict(conditional_input=cin) if cond else {}
+    flow(x, **kw)  # build
+    orders = onets.maf_block_orders(nb, D, 42)
+    blocks = []
+    for bij, order in zip(flow.chain.bijectors[::-1], orders):
+        msb = bij.bijector_fn
+        blk = {}
+        for key, net in (('w', msb.bin_widths), ('h', msb.bin_heights), ('s', msb.knot_slopes)):
+            masks = onets.made_masks(net.params, D, [H], order)
+            layers = []
+            new = []
+            for k, lay in enumerate(net.layers):
+                W = (rng.normal(0, 0.4, lay.kernel.shape) * masks[k]).astype(np.float32)
+                b = rng.normal(0, 0.2, lay.units).astype(np.float32)
+                Wc = rng.normal(0, 0.3, (cond, lay.units)).astype(np.float32) if cond else None
+                new += [W, b] + ([Wc] if cond else [])
+                assert np.array_equal(net.masks[k], masks[k])  # same MADE masks / input orders as the oracle
+                layers.append(dict(W=W.astype(np.float64), b=b.astype(np.float64),
+                                   Wc=None if Wc is None else Wc.astype(np.float64), mask=masks[k]))
+            net.set_weights(new)
+            blk[key] = layers
+        blocks.append(blk)
+    c64 = None if cin is None else cin.astype(np.float64)
+    y = flow(x, **kw).numpy()
+    yo, flo = oflows.maf_forward(x.astype(np.float64), blocks, K, (-10.0, 10.0), c64)
+    assert_close(y, yo, rtol=1e-5, atol=2e-5, what='MAF forward (D passes)')
+    xo, ilo = oflows.maf_inverse(y.astype(np.float64), blocks, K, (-10.0, 10.0), c64)
+    td = flow(_std(v, 130, D)(v.as_tensor(x)), **kw)
+    want = odists.normal_log_prob(xo, 0.0, 1.0).sum(-1) + ilo
+    assert_close(td.log_prob(y).numpy(), want, rtol=1e-5, atol=3e-5, what='MAF flowed log_prob')
+    assert td.sample().shape == (130, D)
+    if cond:
+        with pytest.raises(ValueError, match='conditional_input'):
+            flow(x)
+
+
+def test_domain_transform(vms):
+    """tests/test_flows.py:15-31."""
+    dom = [(-np.pi, np.pi), (0.0, 10.0), (-5.0, 1.0)]
+    to = vms.flows.make_domain_transform(dom, (0.0, 1.0))
+    back = vms.flows.make_domain_transform(dom, (0.0, 1.0), from_target=True)
+    lo = to.forward(np.array([[a for a, _ in dom]], np.float32)).numpy()
+    hi = to.forward(np.array([[b for _, b in dom]], np.float32)).numpy()
+    np.testing.assert_allclose(lo, 0.0, atol=1e-6)
+    np.testing.assert_allclose(hi, 1.0, atol=1e-6)
+    x = np.random.default_rng(0).uniform(-3, 1, (10, 3)).astype(np.float32)
+    np.testing.assert_allclose(back.forward(to.forward(x)).numpy(), x, atol=1e-5)
+    np.testing.assert_allclose(to.inverse(to.forward(x)).numpy(), x, atol=1e-5)
+    prm = oflows.domain_transform_params(dom, (0.0, 1.0))
+    np.testing.assert_allclose(to.forward_log_det_jacobian(x).numpy(), oflows.domain_transform_fldj(prm), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ dists / losses
+def test_distribution_layers_and_losses(vms):
+    v = vms
+    d, L = v.dists, v.losses
+    rng = np.random.default_rng(1)
+    B = 100
+    # conftest.py fixtures of the reference
+    normal_dist = d.Normal(np.linspace(-2.0, 2.0, 5, dtype='float32'), 1.0)
+    sample = normal_dist.sample(10)
+    assert sample.shape == (10, 5)
+    lp = normal_dist.log_prob(sample).numpy()
+    assert_close(lp, odists.normal_log_prob(sample.numpy().astype(np.float64), np.linspace(-2, 2, 5), 1.0).sum(-1),
+                 rtol=1e-5, atol=1e-5, what='Normal log_prob')
+    loss = L.LogProbLoss()(sample, normal_dist)
+    assert loss.shape == tuple()
+    assert abs(float(loss.numpy()) + lp.astype(np.float64).mean()) < 1e-5
+    assert L.LogProbLoss(reduction='none')(sample, normal_dist).shape == (10, )
+    # tests/test_losses.py:16-27: two unit Gaussians offset by 1 in 2-D => KL = 1
+    dist_a = d.Normal(np.ones((B, 2), np.float32), np.ones((B, 2), np.float32))
+    dist_b = d.Normal(np.zeros((B, 2), np.float32), np.ones((B, 2), np.float32))
+    kl = L.KLDivergenceEstimate()
+    out = kl(dist_a, dist_b)
+    assert out.shape == tuple()
+    s = dist_a.sample()
+    o1 = float(kl(dist_a, dist_b, samples=s).numpy())
+    o100 = float(L.KLDivergenceEstimate(weight=100.0)(dist_a, dist_b, samples=s).numpy())
+    assert np.float32(o100) == np.float32(100.0) * np.float32(o1)
+    sn = s.numpy().astype(np.float64)
+    want = np.mean(odists.normal_log_prob(sn, 1.0, 1.0).sum(-1) - odists.normal_log_prob(sn, 0.0, 1.0).sum(-1))
+    assert abs(o1 - want) < 1e-5
+    rk = float(L.ReverseKLDivergenceEstimate()(dist_a, dist_b, samples=s).numpy())
+    assert np.float32(rk) == np.float32(float(kl(dist_b, dist_a, samples=s).numpy()))
+    det = d.IndependentDeterministic(2)(np.ones((B, 2), np.float32))
+    assert np.allclose(det.sample().numpy(), 1.0)
+    o_det = float(kl(det, dist_b).numpy())
+    assert abs(o_det + float(np.mean(dist_b.log_prob(np.ones((B, 2), np.float32)).numpy()))) < 1e-6
+    lr = float(L.LogProbRegularizer()(dist_a, dist_b, samples=s).numpy())
+    assert abs(lr + np.mean(odists.normal_log_prob(sn, 0.0, 1.0).sum(-1))) < 1e-5
+    assert L.NonRegularizer()(dist_a, dist_b) == 0.0
+    with pytest.raises(NotImplementedError, match='In any subclass'):
+        L.InfoRegularizer()(dist_a, dist_b)
+    with pytest.raises(ValueError, match='sample_dist'):
+        L.InfoRegularizer(sample_dist='dist_c')
+    # params_size contracts (tests/test_dists.py:228-242, tests/test_models.py:102-123)
+    assert d.IndependentVonMises.params_size(2) == 6 and d.IndependentDeterministic.params_size(3) == 3
+    assert d.IndependentBlockwise(3, [d.Normal, d.VonMises, d.Normal]).params_size() == 7
+    assert d.AutoregressiveBlockwise(3, d.VonMises).params_size() == (3, 3)
+    with pytest.raises(TypeError):
+        d.IndependentBlockwise(3, 'Normal')
+    with pytest.raises(ValueError):
+        d.IndependentBlockwise(3, [d.Normal, d.Normal])
+    # von Mises layer: log_prob against the oracle
+    p = rng.normal(size=(B, 6)).astype(np.float32)
+    vm = d.IndependentVonMises(2)(p)
+    xs = vm.sample()
+    assert xs.shape == (B, 2)
+    assert_close(vm.log_prob(xs).numpy(), odists.independent_vonmises_log_prob(xs.numpy().astype(np.float64),
+                                                                               p.astype(np.float64)),
+                 rtol=1e-5, atol=1e-5, what='IndependentVonMises log_prob')
+
+
+def test_autoregressive_blockwise_matches_oracle(vms):
+    v = vms
+    d = v.dists
+    rng = np.random.default_rng(2)
+    B, D = 64, 2
+    layer = d.AutoregressiveBlockwise(D, d.Normal, conditional=True, conditional_event_shape=1,
+                                      auto_net_params={'hidden_units': [10, 100, 10]})
+    inputs = rng.normal(size=(B, D, 2)).astype(np.float32)
+    cond = rng.normal(size=(B, 1)).astype(np.float32)
+    with pytest.raises(ValueError, match='conditional_input'):
+        layer(inputs)
+    dist = layer(inputs, conditional_input=cond)
+    assert layer.auto_net.count_params() == 2308  # same structure that gives the notebook's 2,332 for 3 parameters
+    net = layer.auto_net
+    masks = onets.made_masks(2, D, [10, 100, 10], 'left-to-right')
+    layers, new = [], []
+    for k, lay in enumerate(net.layers):
+        W = (rng.normal(0, 0.3, lay.kernel.shape) * masks[k]).astype(np.float32)
+        b = rng.normal(0, 0.1, lay.units).astype(np.float32)
+        Wc = rng.normal(0, 0.3, (1, lay.units)).astype(np.float32)
+        new += [W, b, Wc]
+        layers.append(dict(W=W.astype(np.float64), b=b.astype(np.float64), Wc=Wc.astype(np.float64), mask=masks[k]))
+    net.set_weights(new)
+    x = rng.normal(size=(B, D)).astype(np.float32)
+    want = odists.autoregressive_blockwise_log_prob(x.astype(np.float64), inputs.astype(np.float64), layers,
+                                                    ['normal'] * D, cond.astype(np.float64))
+    assert_close(dist.log_prob(x).numpy(), want, rtol=1e-5, atol=1e-5, what='AutoregressiveBlockwise log_prob')
+    s = dist.sample()
+    assert s.shape == (B, D)
+    with pytest.raises(ValueError):
+        d.AutoregressiveBlockwise(3, d.Normal)(inputs)
+
+
+# ------------------------------------------------------------------------------------------------ fused ELBO
+@pytest.mark.parametrize('tag,prior', [('c1', 'normal'), ('c2', 'realnvp')])
+def test_fused_elbo_matches_golden(vms, tag, prior):
+    v = vms
+    g = np.load(os.path.join(GOLD, 'elbo_%s.npz' % tag))
+    P = ovae.init_vae(1003, prior=prior, flow_hidden=16, num_bins=8, hidden=32)
+    model = vae_from_oracle(v, P)
+    f = model.fused(256)
+    assert f.n_params == g['theta'].size
+    assert np.array_equal(f.theta.numpy(), flat_from_oracle(P))
+    x, eps = v.as_tensor(g['x']), v.as_tensor(g['eps'])
+    out = f.forward(x, eps)
+    for k in ('z', 'logq', 'logpz', 'logpx'):
+        assert_close(out[k].numpy(), g[k], rtol=1e-5, atol=2e-5, what='%s %s' % (tag, k))
+    assert_close(out['scalars'].numpy()[:3], g['scalars'], rtol=1e-5, atol=1e-5, what='scalars')
+
+
+@pytest.mark.parametrize('prior,dz,B', [('normal', 2, 300), ('realnvp', 2, 300), ('realnvp', 1, 129), ('realnvp', 3, 64),
+                                        ('realnvp', 2, 4096)])
+def test_fused_elbo_forward_backward_matches_oracle(vms, prior, dz, B):
+    v = vms
+    P = ovae.init_vae(21 + dz, dx=6, dz=dz, hidden=40, prior=prior, num_blocks=4, num_bins=32 if B > 1000 else 10,
+                      flow_hidden=24)
+    rng = np.random.default_rng(B)
+    if prior == 'realnvp':  # widen the spline heads so bins / slopes vary
+        for blk in P['flow']:
+            for k in ('w', 'h', 's'):
+                blk[k] = ((blk[k][0] * 8).astype(np.float32), rng.normal(0, 0.5, blk[k][1].shape).astype(np.float32))
+    x = rng.normal(size=(B, 6)).astype(np.float32)
+    eps = rng.normal(size=(B, dz)).astype(np.float32)
+    P64 = ovae.cast_params(P, np.float64)
+    out, G = ovae.elbo_backward(P64, x.astype(np.float64), eps.astype(np.float64), weight=0.7)
+    model = vae_from_oracle(v, P, weight=0.7)
+    f = model.fused(B)
+    scal = f.forward_backward(v.as_tensor(x), v.as_tensor(eps)).numpy()
+    assert_close(scal[:3], [out['loss'], out['nll'], out['kl']], rtol=1e-5, atol=1e-5, what='loss / nll / kl')
+    want = flat_grad_from_oracle(P64, G)
+    got = f.grad.numpy()
+    scale = np.abs(want).max()
+    assert_close(got, want, rtol=1e-4, atol=2e-6 * max(scale, 1e-3), what='flat gradient (%s dz=%d)' % (prior, dz))
+    rel = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert rel < 1e-5, rel
+    # graph replay is deterministic
+    f.forward_backward(v.as_tensor(x), v.as_tensor(eps))
+    assert np.array_equal(f.grad.numpy(), got)
+
+
+def test_generic_model_path_agrees_with_fused(vms):
+    """VAE.call (op-by-op, the reference's code path) and the fused plan evaluate the same ELBO."""
+    v = vms
+    P = ovae.init_vae(5, prior='realnvp', flow_hidden=16, num_bins=8, hidden=32)
+    model = vae_from_oracle(v, P)
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(200, 6)).astype(np.float32)
+    eps = rng.normal(size=(200, 2)).astype(np.float32)
+    f = model.fused(200)
+    out = f.forward(v.as_tensor(x), v.as_tensor(eps))
+    enc = model.encoder(v.as_tensor(x))
+    z, lq = enc.sample_with_noise(v.as_tensor(eps))
+    assert_close(z.numpy(), out['z'].numpy(), rtol=1e-6, atol=1e-6, what='z')
+    assert_close(lq.numpy(), out['logq'].numpy(), rtol=1e-5, atol=1e-5, what='logq')
+    assert_close(model.prior(z).log_prob(z).numpy(), out['logpz'].numpy(), rtol=1e-5, atol=2e-5, what='logpz')
+    assert_close(model.decoder(z).log_prob(x).numpy(), out['logpx'].numpy(), rtol=1e-5, atol=2e-5, what='logpx')
+    dec = model(x)  # reference-style call: registers the KL loss / metrics (models.py:315-318)
+    assert dec.log_prob(x).shape == (200, ) and dec.sample().shape == (200, 6)
+    assert set(model.metrics) == {'kl_div', 'regularizer_loss'} and len(model.losses) == 1
+
+
+def test_training_reduces_loss_and_matches_oracle_adam(vms):
+    v = vms
+    P = ovae.init_vae(9, prior='realnvp', flow_hidden=16, num_bins=8, hidden=32)
+    model = vae_from_oracle(v, P)
+    model.compile(optimizer=v.models.Adam(learning_rate=1e-3), loss=v.losses.LogProbLoss())
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(256, 6)).astype(np.float32)
+    eps = rng.normal(size=(256, 2)).astype(np.float32)
+    # three oracle steps
+    theta = flat_from_oracle(P).astype(np.float64)
+    P64 = ovae.cast_params(P, np.float64)
+    first = model.train_step(x, eps)
+    out, G = ovae.elbo_backward(P64, x.astype(np.float64), eps.astype(np.float64))
+    m, vv = np.zeros_like(theta), np.zeros_like(theta)
+    ovae.adam_step(theta, flat_grad_from_oracle(P64, G).astype(np.float64), m, vv, 1)
+    assert abs(first['loss'] - out['loss']) < 1e-4 * abs(out['loss'])
+    assert_close(model.fused().theta.numpy(), theta, rtol=1e-5, atol=2e-6, what='theta after one Adam step')
+    hist = model.fit(x, x, epochs=3, batch_size=64)
+    assert hist['loss'][-1] < first['loss']
+    assert np.isfinite(model.evaluate(x, x, batch_size=128))
+    assert model.predict(x[:10]).shape == (10, 6)
+
+
+# ------------------------------------------------------------------------------------------------ MCMC
+def test_mcmc_counters_and_shapes(vms):
+    """tests/test_mcmc.py:34-59."""
+    v = vms
+    P = ovae.init_vae(3, prior='normal', hidden=32)
+    model = vae_from_oracle(v, P)
+    x = np.random.default_rng(0).normal(size=(10, 6)).astype(np.float32)
+    mc = v.mcmc.MCMC(model, omc.quadratic_energy)
+    assert mc._num_trials == 0 and mc._num_acc == 0
+    out_x, out_e = mc.single_step(x)
+    assert out_x.shape == x.shape and out_e.shape[0] == 10 and mc._num_trials == 10
+    out_x, out_e = mc.single_step(out_x, energies=out_e)
+    assert mc._num_trials == 20
+    mc.reset()
+    out_x, out_e = mc.run(x, n_steps=10)
+    assert out_x.shape == x.shape and mc._num_trials == 100
+    assert mc.acceptance_rate == mc._num_acc / mc._num_trials <= 1.0
+
+
+@pytest.mark.parametrize('prior', ['normal', 'realnvp'])
+def test_mcmc_log_probs_and_decisions_match_oracle(vms, prior):
+    """One MC step with injected noise: the six log-probabilities agree with the oracle to 1e-5 and the device
+    decisions are bit-exact given those log-probabilities; the end-to-end flip rate is reported."""
+    v = vms
+    import vaemolsim_b200._protocols as PR
+    P = ovae.init_vae(1003, prior=prior, flow_hidden=16, num_bins=8, hidden=32)
+    model = vae_from_oracle(v, P)
+    B = 2048
+    rng = np.random.default_rng(4001)
+    x1 = rng.normal(size=(B, 6)).astype(np.float32)
+    e1, e2, e3 = (rng.standard_normal((B, d), dtype=np.float32) for d in (2, 2, 6))
+    # oracle
+    loc, sc, _, _ = ovae.encoder_dist(P, x1)
+    z1 = odists.normal_sample(loc, sc, e1)
+    lq1 = odists.normal_log_prob(z1, loc, sc).sum(-1)
+    z2, lz2 = ovae.prior_sample_and_log_prob(P, e2)
+    locx, scx, _, _ = ovae.decoder_dist(P, z2)
+    x2 = odists.normal_sample(locx, scx, e3)
+    lx2 = odists.normal_log_prob(x2, locx, scx).sum(-1)
+    fwd_o = (lq1 + lz2 + lx2).astype(np.float32)
+    l2, s2, _, _ = ovae.encoder_dist(P, x2)
+    lo1, so1, _, _ = ovae.decoder_dist(P, z1)
+    rev_o = (odists.normal_log_prob(z2, l2, s2).sum(-1) + ovae.prior_log_prob(P, z1) +
+             odists.normal_log_prob(x1, lo1, so1).sum(-1)).astype(np.float32)
+    # device, same noise
+    T = v.as_tensor
+    dz1, dlq1 = model.encoder(T(x1)).sample_with_noise(T(e1))
+    pr = model.prior(dz1)
+    if prior == 'normal':
+        dz2, dlz2 = T(e2), pr.log_prob(T(e2))
+    else:
+        y, fldj = pr.bijector._fwd(T(e2))
+        dz2, dlz2 = y, pr.distribution.log_prob(T(e2)) - fldj
+    dx2, dlx2 = model.decoder(dz2).sample_with_noise(T(e3))
+    fwd = dlq1 + dlz2 + dlx2
+    rev = model.encoder(dx2).log_prob(dz2) + model.prior(dz2).log_prob(dz1) + model.decoder(dz1).log_prob(T(x1))
+    assert_close(dz2.numpy(), z2, rtol=1e-5, atol=2e-5, what='z2')
+    assert_close(dx2.numpy(), x2, rtol=1e-5, atol=5e-5, what='x2')
+    assert_close(fwd.numpy(), fwd_o, rtol=1e-5, atol=5e-5, what='forward log p')
+    assert_close(rev.numpy(), rev_o, rtol=1e-5, atol=5e-5, what='reverse log p')
+    e_old, e_new = omc.quadratic_energy(x1), omc.quadratic_energy(x2)
+    log_u = np.log(np.random.default_rng(4002).random(B))
+    want = omc.accept(e_new, e_old, fwd_o, rev_o, log_u)
+    end_to_end = omc.accept(omc.quadratic_energy(dx2.numpy()), e_old, fwd.numpy(), rev.numpy(), log_u)
+    flips = int((want != end_to_end).sum())
+    print('end-to-end decision flips: %d / %d' % (flips, B))
+    assert flips <= max(2, B // 500)

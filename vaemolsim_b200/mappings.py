@@ -165,7 +165,7 @@ class DistanceSelection(P.Layer):
         out_xyz = Tensor((B, k, 3))
         out_idx = Tensor((B, k), np.int32) if return_indices else None
         c.lib.vms_dist_select(cvals.ptr, None if splits is None else splits.ptr, B, N, ref.ptr, box_ptr, per_row,
-                              np.float32(self.sq_cut), k, info_ptr, P_, out_xyz.ptr,
+                              float(np.float32(self.sq_cut)), k, info_ptr, P_, out_xyz.ptr,
                               None if out_info is None else out_info.ptr, None if out_idx is None else out_idx.ptr,
                               c.stream)
         outs = [out_xyz] + ([out_info] if out_info is not None else []) + ([out_idx] if return_indices else [])
