@@ -364,6 +364,7 @@ vms_status run_graphed(vms_elbo_plan_s* pl, const std::array<uintptr_t, 10>& key
     VMS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     vms_status s = body();
     cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (s || e != cudaSuccess) cudaGetLastError();  // an invalidated capture must not poison later launch checks
     if (s) { if (g) cudaGraphDestroy(g); return s; }
     if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return VMS_ERR_CUDA; }
     cudaGraphExec_t ex = nullptr;

@@ -4,29 +4,29 @@
 // tfp.bijectors.RationalQuadraticSpline object built at flows.py:204-207 / :512-515 (forward, inverse, fldj,
 // ildj = -fldj(inverse)), plus TF autodiff through both (backward kernel).
 //
-// Design (B200): the op is HBM-bound -- (3K-1) raw logits in, 2 scalars out per element (392 B @ K=32).
-//   * one THREAD per element, so the softmax / cumulative-sum / bin search are plain sequential loops with no
-//     shuffles (a warp-per-element layout costs ~100 warp instructions per element and becomes issue-bound);
-//   * logits are streamed HBM -> shared memory with cp.async (LDGSTS) in a 2-stage pipeline, warps copy whole
-//     rows so global reads are 128-byte coalesced; the shared row stride is odd so thread-per-row reads are
-//     bank-conflict free for any K;
-//   * persistent grid: 2 CTAs per SM x SM count, grid-stride over tiles of ~128 elements;
-//   * backward writes the (3K-1) logit gradients in place into the staged tile and stores them coalesced.
+// Design (B200).  The op is HBM-bound: (3K-1) raw logits in, 2 scalars out per element (392 B @ K=32), so the kernel
+// is built around coalesced 16-byte loads and a small instruction count per element:
+//   * 8 lanes ("octet") cooperate on one element; each lane owns K/8 consecutive bins (4 bins @ K<=32: ONE float4
+//     load per logit array per lane, 128 contiguous bytes per element, 4 elements per warp instruction);
+//   * softmax max / sum and the cumulative sum are 3-step shuffles inside the octet (not 5-step warp scans), the
+//     per-lane part is a 4-iteration sequential loop;
+//   * no shared memory and ~64 registers => full occupancy, memory-level parallelism comes from resident warps;
+//   * exactly one lane finds the bin; it evaluates the spline and writes y / log-det; it alone reads the TWO knot
+//     slopes the element needs (the other K-3 raw slopes never leave HBM);
+//   * prefix sums and knot positions are accumulated in float64 (B200 runs FP64 at half the FP32 rate): float32 knots
+//     (what TFP computes) carry ~ulp(range) error that narrow bins amplify to 1e-4 in the log-det (parity).
 #include "common.cuh"
 #include <math.h>
 
 namespace {
 
-constexpr int kThreads = 128;
-constexpr int kWarps = kThreads / 32;
-constexpr int kStages = 2;
+constexpr int kThreads = 256;
+constexpr int kOct = 8;
 
 struct RqsParams {
   int64_t n_rows;
-  int n_dims;   // Dt
+  int n_dims;  // Dt: transformed dims per row, processed sequentially by the row's octet
   int K;
-  int tile_rows;  // rows per tile
-  int lds;        // shared row stride (floats), odd
   float bin_min, bin_max, scale;  // scale = bin_max - bin_min - K*1e-2 (flows.py:92)
   const float* v_in;  int64_t ld_in;
   const float* raw_w; int64_t ld_w;
@@ -46,242 +46,239 @@ struct RqsParams {
   float* g_s; int64_t ld_gs;
 };
 
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc));
+__device__ __forceinline__ float oct_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  return v;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+// inclusive prefix sum over the 8 lanes of an octet
+__device__ __forceinline__ double oct_scan(double v, int j) {
+#pragma unroll
+  for (int d = 1; d < kOct; d <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, d, kOct);
+    if (j >= d) v += t;
+  }
+  return v;
 }
 
-// Stage one tile of raw logits: rows [row0, row0+rows) of the three arrays into smem rows of stride lds.
-__device__ __forceinline__ void load_tile(const RqsParams& p, float* st, int64_t row0, int rows) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwh = p.n_dims * p.K, ns = p.n_dims * (p.K - 1);
-  for (int r = warp; r < rows; r += kWarps) {
-    float* dst = st + (size_t)r * p.lds;
-    const float* gw = p.raw_w + (row0 + r) * p.ld_w;
-    const float* gh = p.raw_h + (row0 + r) * p.ld_h;
-    const float* gs = p.raw_s + (row0 + r) * p.ld_s;
-    for (int c = lane; c < nwh; c += 32) cp_async4(dst + c, gw + c);
-    for (int c = lane; c < nwh; c += 32) cp_async4(dst + nwh + c, gh + c);
-    for (int c = lane; c < ns; c += 32) cp_async4(dst + 2 * nwh + c, gs + c);
+// logits of this lane's BPL consecutive bins (bins >= K read as -inf)
+template <int BPL, bool VEC>
+__device__ __forceinline__ void load_bins(const float* __restrict__ row, int j, int K, float (&out)[BPL]) {
+  if (VEC) {
+#pragma unroll
+    for (int q = 0; q < BPL / 4; ++q) {
+      const int k0 = j * BPL + 4 * q;
+      if (k0 < K) {  // K % 4 == 0 on the vector path: a 4-bin group is entirely valid or entirely padding
+        const float4 t = __ldg(reinterpret_cast<const float4*>(row + k0));
+        out[4 * q] = t.x; out[4 * q + 1] = t.y; out[4 * q + 2] = t.z; out[4 * q + 3] = t.w;
+      } else {
+        out[4 * q] = out[4 * q + 1] = out[4 * q + 2] = out[4 * q + 3] = -INFINITY;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < BPL; ++i) {
+      const int k = j * BPL + i;
+      out[i] = k < K ? __ldg(row + k) : -INFINITY;
+    }
   }
 }
 
-__device__ __forceinline__ void store_tile(const RqsParams& p, const float* st, int64_t row0, int rows) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwh = p.n_dims * p.K, ns = p.n_dims * (p.K - 1);
-  for (int r = warp; r < rows; r += kWarps) {
-    const float* src = st + (size_t)r * p.lds;
-    float* gw = p.g_w + (row0 + r) * p.ld_gw;
-    float* gh = p.g_h + (row0 + r) * p.ld_gh;
-    float* gs = p.g_s + (row0 + r) * p.ld_gs;
-    for (int c = lane; c < nwh; c += 32) gw[c] = src[c];
-    for (int c = lane; c < nwh; c += 32) gh[c] = src[nwh + c];
-    for (int c = lane; c < ns; c += 32) gs[c] = src[2 * nwh + c];
+template <int BPL, bool VEC>
+__device__ __forceinline__ void store_bins(float* __restrict__ row, int j, int K, const float (&v)[BPL]) {
+  if (VEC) {
+#pragma unroll
+    for (int q = 0; q < BPL / 4; ++q) {
+      const int k0 = j * BPL + 4 * q;
+      if (k0 < K) *reinterpret_cast<float4*>(row + k0) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < BPL; ++i) {
+      const int k = j * BPL + i;
+      if (k < K) row[k] = v[i];
+    }
   }
 }
 
-// Per-element spline state after the bin search.
+// What the owning lane knows about the element's bin.
 struct Bin {
-  float xk, yk, wk, hk, sk, dk, dk1;
-  float cw, ch;        // scale / sum(exp)
-  float elt_w, elt_h;  // sum_{j<idx} exp_j (backward: softmax-Jacobian dot products)
+  double lo_x, lo_y;      // lower knots
+  float wk, hk;           // bin width / height
+  float e_w, e_h;         // exp(logit - max) of the bin
+  float elt_w, elt_h;     // sum of exps of all lower bins
   int idx;
-  bool oob;
+  bool found;
 };
 
-// Softmax statistics + sequential knot walk.  pw / ph are overwritten with exp(logit - max).
-template <int KT>
-__device__ __forceinline__ Bin find_bin(float* pw, float* ph, const float* ps, int Krt, float v, bool inverse_dir,
-                                        float bin_min, float scale) {
-  const int K = KT ? KT : Krt;
-  Bin b;
+// Softmax statistics, octet scan, knot walk over this lane's bins.  On return ew / eh hold exp(logit - max),
+// inv_tot_* = 1 / sum(exp), c* = scale / sum(exp).
+template <int BPL>
+__device__ __forceinline__ Bin find_bin(float (&ew)[BPL], float (&eh)[BPL], int j, int K, double vd, bool inverse_dir,
+                                        float bin_min, float scale, double& cwd, double& chd, double& totw,
+                                        double& toth) {
   float mw = -INFINITY, mh = -INFINITY;
-#pragma unroll 8
-  for (int k = 0; k < K; ++k) {
-    mw = fmaxf(mw, pw[k]);
-    mh = fmaxf(mh, ph[k]);
+#pragma unroll
+  for (int i = 0; i < BPL; ++i) { mw = fmaxf(mw, ew[i]); mh = fmaxf(mh, eh[i]); }
+  mw = oct_max(mw);
+  mh = oct_max(mh);
+  double sw = 0.0, sh = 0.0;
+#pragma unroll
+  for (int i = 0; i < BPL; ++i) {
+    ew[i] = expf(ew[i] - mw);  // exp(-inf) = 0 for padding bins
+    eh[i] = expf(eh[i] - mh);
+    sw += (double)ew[i];
+    sh += (double)eh[i];
   }
-  float sw = 0.f, sh = 0.f;
-#pragma unroll 8
-  for (int k = 0; k < K; ++k) {
-    float ew = expf(pw[k] - mw), eh = expf(ph[k] - mh);
-    sw += ew;
-    sh += eh;
-    pw[k] = ew;
-    ph[k] = eh;
-  }
-  b.cw = scale / sw;
-  b.ch = scale / sh;
-  // knots: kx[0] = bin_min, kx[k+1] = cumsum(bw)[k] + bin_min (TFP _knot_positions); same for ky.
-  float cx = 0.f, cy = 0.f, ex = 0.f, ey = 0.f;
-  float cx_i = 0.f, cy_i = 0.f, ex_i = 0.f, ey_i = 0.f;
-  int idx = 0;
-#pragma unroll 8
-  for (int k = 0; k < K; ++k) {
-    float knot = (inverse_dir ? cy : cx) + bin_min;
-    if (k == 0 || v >= knot) {  // largest k with knot_k <= v, floored at 0 (searchsorted 'right' - 1)
-      idx = k;
-      cx_i = cx; cy_i = cy; ex_i = ex; ey_i = ey;
+  const double iw = oct_scan(sw, j), ih = oct_scan(sh, j);
+  totw = __shfl_sync(0xffffffffu, iw, kOct - 1, kOct);
+  toth = __shfl_sync(0xffffffffu, ih, kOct - 1, kOct);
+  cwd = (double)scale / totw;
+  chd = (double)scale / toth;
+  // knots: k-th lower knot = bin_min + (scale * E_k / total + 1e-2 k), E_k = sum of exps of bins < k
+  Bin b;
+  b.found = false;
+  b.idx = 0;
+  b.lo_x = b.lo_y = 0.0; b.wk = b.hk = 1.f; b.e_w = b.e_h = 0.f; b.elt_w = b.elt_h = 0.f;
+  // a lane's first lower knot and its left neighbour's last upper knot are computed from the SAME scan value, so the
+  // bins tile the range without gaps or overlaps
+  double Ex = __shfl_up_sync(0xffffffffu, iw, 1, kOct), Ey = __shfl_up_sync(0xffffffffu, ih, 1, kOct);
+  if (j == 0) { Ex = 0.0; Ey = 0.0; }
+  const double bm = (double)bin_min;
+  double lox = bm + fma(cwd, Ex, 1e-2 * (double)(j * BPL));
+  double loy = bm + fma(chd, Ey, 1e-2 * (double)(j * BPL));
+#pragma unroll
+  for (int i = 0; i < BPL; ++i) {
+    const int k = j * BPL + i;
+    const double Ex1 = i == BPL - 1 ? iw : Ex + (double)ew[i];
+    const double Ey1 = i == BPL - 1 ? ih : Ey + (double)eh[i];
+    const double hix = bm + fma(cwd, Ex1, 1e-2 * (double)(k + 1));
+    const double hiy = bm + fma(chd, Ey1, 1e-2 * (double)(k + 1));
+    const double lo = inverse_dir ? loy : lox, hi = inverse_dir ? hiy : hix;
+    // bin k covers [lo, hi); the range edge itself is outside (TFP: x <= kx[0] or x >= kx[K] => identity)
+    if (k < K && vd >= lo && vd < hi && vd > bm) {
+      b.found = true;
+      b.idx = k;
+      b.lo_x = lox; b.lo_y = loy;
+      b.wk = (float)(hix - lox); b.hk = (float)(hiy - loy);
+      b.e_w = ew[i]; b.e_h = eh[i];
+      b.elt_w = (float)Ex; b.elt_h = (float)Ey;
     }
-    float ew = pw[k], eh = ph[k];
-    cx += fmaf(ew, b.cw, 1e-2f);
-    cy += fmaf(eh, b.ch, 1e-2f);
-    ex += ew;
-    ey += eh;
+    Ex = Ex1; Ey = Ey1; lox = hix; loy = hiy;
   }
-  float vmax = (inverse_dir ? cy : cx) + bin_min;
-  b.oob = (v <= bin_min) || (v >= vmax);
-  if (b.oob) { idx = 0; cx_i = cy_i = ex_i = ey_i = 0.f; }
-  b.idx = idx;
-  b.elt_w = ex_i;
-  b.elt_h = ey_i;
-  float bw = fmaf(pw[idx], b.cw, 1e-2f), bh = fmaf(ph[idx], b.ch, 1e-2f);
-  b.xk = cx_i + bin_min;
-  b.yk = cy_i + bin_min;
-  b.wk = ((cx_i + bw) + bin_min) - b.xk;
-  b.hk = ((cy_i + bh) + bin_min) - b.yk;
-  b.sk = b.hk / b.wk;
-  b.dk = idx == 0 ? 1.0f : vms::softplus_tf(ps[idx - 1]) + 1e-2f;
-  b.dk1 = idx == K - 1 ? 1.0f : vms::softplus_tf(ps[idx]) + 1e-2f;
   return b;
 }
 
 // relative position r in the bin for either direction (TFP _forward / _inverse)
-__device__ __forceinline__ float rel_pos(const Bin& b, float v, bool inverse_dir) {
-  if (!inverse_dir) return (v - b.xk) / b.wk;
-  float ry = v - b.yk;
-  float t2 = ry * (b.dk1 + b.dk - 2.f * b.sk);
-  float a = b.hk * (b.sk - b.dk) + t2;
-  float bb = b.hk * b.dk - t2;
-  float c = -b.sk * ry;
-  float disc = bb * bb - 4.f * a * c;
-  float r = (2.f * c) / (-bb - sqrtf(disc));
+__device__ __forceinline__ float rel_pos(const Bin& b, double vd, float sk, float dk, float dk1, bool inverse_dir) {
+  if (!inverse_dir) return (float)(vd - b.lo_x) / b.wk;
+  const float ry = (float)(vd - b.lo_y);
+  const float t2 = ry * (dk1 + dk - 2.f * sk);
+  const float a = b.hk * (sk - dk) + t2;
+  const float bb = b.hk * dk - t2;
+  const float c = -sk * ry;
+  const float disc = bb * bb - 4.f * a * c;
+  const float r = (2.f * c) / (-bb - sqrtf(disc));
   return ry == 0.f ? 0.f : r;
 }
 
-template <int KT>
-__global__ void __launch_bounds__(kThreads) rqs_apply_kernel(const RqsParams p) {
-  extern __shared__ float smem[];
-  const int stage_floats = p.tile_rows * p.lds;
-  float* ldj_s = smem + kStages * stage_floats;  // [tile_rows * Dt] scratch for the event sum
-  const int64_t n_tiles = (p.n_rows + p.tile_rows - 1) / p.tile_rows;
-  const int K = KT ? KT : p.K;
-  const int nwh = p.n_dims * K;
-  const bool inv = p.inverse_dir != 0;
-
-  int64_t tile = blockIdx.x;
-  int stage = 0;
-  if (tile < n_tiles) {
-    int64_t row0 = tile * p.tile_rows;
-    int rows = (int)min((int64_t)p.tile_rows, p.n_rows - row0);
-    load_tile(p, smem, row0, rows);
-  }
-  cp_async_commit();
-  for (; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * p.tile_rows;
-    const int rows = (int)min((int64_t)p.tile_rows, p.n_rows - row0);
-    const int64_t next = tile + gridDim.x;
-    if (next < n_tiles) {
-      int64_t nrow0 = next * p.tile_rows;
-      int nrows = (int)min((int64_t)p.tile_rows, p.n_rows - nrow0);
-      load_tile(p, smem + (stage ^ 1) * stage_floats, nrow0, nrows);
-    }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    float* st = smem + stage * stage_floats;
-    const int n_el = rows * p.n_dims;
-    for (int e = threadIdx.x; e < n_el; e += kThreads) {
-      const int r = e / p.n_dims, d = e - r * p.n_dims;
-      float* row = st + (size_t)r * p.lds;
-      const float v = p.v_in[(row0 + r) * p.ld_in + d];
-      Bin b = find_bin<KT>(row + d * K, row + nwh + d * K, row + 2 * nwh + d * (K - 1), K, v, inv, p.bin_min, p.scale);
-      float out = v, ldj = 0.f;
-      if (!b.oob) {
-        float rr = rel_pos(b, v, inv);
-        float omr = 1.f - rr, u = rr * omr;
-        float den = b.sk + (b.dk1 + b.dk - 2.f * b.sk) * u;
-        if (!inv) {
-          float num = b.hk * (b.sk * rr * rr + b.dk * u);
-          out = b.yk + num / den;
-        } else {
-          out = rr * b.wk + b.xk;
-        }
-        float P = b.dk1 * rr * rr + 2.f * b.sk * u + b.dk * omr * omr;
-        ldj = logf((b.sk * b.sk) * P / (den * den));
-        if (inv) ldj = -ldj;
-      }
-      p.v_out[(row0 + r) * p.ld_out + d] = out;
-      if (p.ldj) p.ldj[(row0 + r) * p.n_dims + d] = ldj;
-      if (p.ldj_sum) ldj_s[e] = ldj;
-    }
-    __syncthreads();  // tile consumed (and ldj_s complete) before the stage is refilled
-    if (p.ldj_sum) {
-      for (int r = threadIdx.x; r < rows; r += kThreads) {
-        float s = 0.f;
-        for (int d = 0; d < p.n_dims; ++d) s += ldj_s[r * p.n_dims + d];
-        float* dst = p.ldj_sum + row0 + r;
-        *dst = p.accumulate ? *dst + s : s;
-      }
-      // ldj_s is rewritten only after the next iteration's first __syncthreads
-    }
-    stage ^= 1;
-  }
-  cp_async_wait<0>();
+__device__ __forceinline__ void load_slopes(const float* __restrict__ ps, int idx, int K, float& s_lo, float& s_hi,
+                                            float& dk, float& dk1) {
+  s_lo = idx > 0 ? __ldg(ps + idx - 1) : 0.f;
+  s_hi = idx < K - 1 ? __ldg(ps + idx) : 0.f;
+  dk = idx == 0 ? 1.0f : vms::softplus_tf(s_lo) + 1e-2f;
+  dk1 = idx == K - 1 ? 1.0f : vms::softplus_tf(s_hi) + 1e-2f;
 }
 
-template <int KT>
-__global__ void __launch_bounds__(kThreads) rqs_backward_kernel(const RqsParams p) {
-  extern __shared__ float smem[];
-  const int stage_floats = p.tile_rows * p.lds;
-  const int64_t n_tiles = (p.n_rows + p.tile_rows - 1) / p.tile_rows;
-  const int K = KT ? KT : p.K;
-  const int nwh = p.n_dims * K;
+template <int BPL, bool VEC>
+__global__ void __launch_bounds__(kThreads) rqs_apply_kernel(const RqsParams p) {
+  const int j = threadIdx.x & (kOct - 1);
+  const int64_t oct0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / kOct;
+  const int64_t n_oct = (int64_t)gridDim.x * (kThreads / kOct);
+  const int K = p.K;
   const bool inv = p.inverse_dir != 0;
-
-  int64_t tile = blockIdx.x;
-  int stage = 0;
-  if (tile < n_tiles) {
-    int64_t row0 = tile * p.tile_rows;
-    int rows = (int)min((int64_t)p.tile_rows, p.n_rows - row0);
-    load_tile(p, smem, row0, rows);
-  }
-  cp_async_commit();
-  for (; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * p.tile_rows;
-    const int rows = (int)min((int64_t)p.tile_rows, p.n_rows - row0);
-    const int64_t next = tile + gridDim.x;
-    if (next < n_tiles) {
-      int64_t nrow0 = next * p.tile_rows;
-      int nrows = (int)min((int64_t)p.tile_rows, p.n_rows - nrow0);
-      load_tile(p, smem + (stage ^ 1) * stage_floats, nrow0, nrows);
+  const int64_t n_iter = (p.n_rows + n_oct - 1) / n_oct;  // uniform trip count: shuffles need all lanes present
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t row = oct0 + it * n_oct;
+    const bool active = row < p.n_rows;
+    const int64_t r = active ? row : p.n_rows - 1;  // inactive octets redo the last row, writes predicated off
+    float ldj_acc = 0.f;
+    for (int d = 0; d < p.n_dims; ++d) {
+      float ew[BPL], eh[BPL];
+      load_bins<BPL, VEC>(p.raw_w + r * p.ld_w + (int64_t)d * K, j, K, ew);
+      load_bins<BPL, VEC>(p.raw_h + r * p.ld_h + (int64_t)d * K, j, K, eh);
+      const float v = __ldg(p.v_in + r * p.ld_in + d);
+      const double vd = (double)v;
+      double cwd, chd, totw, toth;
+      const Bin b = find_bin<BPL>(ew, eh, j, K, vd, inv, p.bin_min, p.scale, cwd, chd, totw, toth);
+      float out = v, ldj = 0.f;
+      if (b.found) {
+        float s_lo, s_hi, dk, dk1;
+        load_slopes(p.raw_s + r * p.ld_s + (int64_t)d * (K - 1), b.idx, K, s_lo, s_hi, dk, dk1);
+        const float sk = b.hk / b.wk;
+        const float rr = rel_pos(b, vd, sk, dk, dk1, inv);
+        const float omr = 1.f - rr, u = rr * omr;
+        const float den = sk + (dk1 + dk - 2.f * sk) * u;
+        if (!inv) {
+          const float num = b.hk * (sk * rr * rr + dk * u);
+          out = (float)(b.lo_y + (double)(num / den));
+        } else {
+          out = (float)(b.lo_x + (double)(rr * b.wk));
+        }
+        const float P = dk1 * rr * rr + 2.f * sk * u + dk * omr * omr;
+        ldj = logf((sk * sk) * P / (den * den));
+        if (inv) ldj = -ldj;
+      }
+      const unsigned found_mask = __ballot_sync(0xffffffffu, b.found);
+      const unsigned oct_mask = (found_mask >> ((threadIdx.x & 31) & ~(kOct - 1))) & 0xffu;
+      const bool writer = oct_mask ? b.found : (j == 0);  // out-of-range: lane 0 writes the identity
+      if (writer && active) {
+        p.v_out[r * p.ld_out + d] = out;
+        if (p.ldj) p.ldj[r * p.n_dims + d] = ldj;
+      }
+      if (p.ldj_sum) {
+        const int src = oct_mask ? (__ffs(oct_mask) - 1) : 0;
+        ldj_acc += __shfl_sync(0xffffffffu, ldj, src, kOct);
+      }
     }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    float* st = smem + stage * stage_floats;
-    const int n_el = rows * p.n_dims;
-    for (int e = threadIdx.x; e < n_el; e += kThreads) {
-      const int r = e / p.n_dims, d = e - r * p.n_dims;
-      float* row = st + (size_t)r * p.lds;
-      float* pw = row + d * K;
-      float* ph = row + nwh + d * K;
-      float* ps = row + 2 * nwh + d * (K - 1);
-      const float v = p.v_in[(row0 + r) * p.ld_in + d];
-      const float g_out = p.g_out[(row0 + r) * p.ld_g_out + d];
-      const float g_ldj = p.g_ldj_sum ? p.g_ldj_sum[row0 + r] : 0.f;
-      Bin b = find_bin<KT>(pw, ph, ps, K, v, inv, p.bin_min, p.scale);
-      float g_in = g_out;
-      float g_xk = 0.f, g_w = 0.f, g_yk = 0.f, g_h = 0.f, g_dk = 0.f, g_dk1 = 0.f;
-      if (!b.oob) {
+    if (p.ldj_sum && j == 0 && active) {
+      float* dst = p.ldj_sum + r;
+      *dst = p.accumulate ? *dst + ldj_acc : ldj_acc;
+    }
+  }
+}
+
+template <int BPL, bool VEC>
+__global__ void __launch_bounds__(kThreads) rqs_backward_kernel(const RqsParams p) {
+  const int j = threadIdx.x & (kOct - 1);
+  const int64_t oct0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / kOct;
+  const int64_t n_oct = (int64_t)gridDim.x * (kThreads / kOct);
+  const int K = p.K;
+  const bool inv = p.inverse_dir != 0;
+  const int64_t n_iter = (p.n_rows + n_oct - 1) / n_oct;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t row = oct0 + it * n_oct;
+    const bool active = row < p.n_rows;
+    const int64_t r = active ? row : p.n_rows - 1;
+    const float g_ldj = p.g_ldj_sum ? __ldg(p.g_ldj_sum + r) : 0.f;
+    for (int d = 0; d < p.n_dims; ++d) {
+      float ew[BPL], eh[BPL];
+      load_bins<BPL, VEC>(p.raw_w + r * p.ld_w + (int64_t)d * K, j, K, ew);
+      load_bins<BPL, VEC>(p.raw_h + r * p.ld_h + (int64_t)d * K, j, K, eh);
+      const float v = __ldg(p.v_in + r * p.ld_in + d);
+      const float g_out = __ldg(p.g_out + r * p.ld_g_out + d);
+      const double vd = (double)v;
+      double cwd, chd, totw, toth;
+      const Bin b = find_bin<BPL>(ew, eh, j, K, vd, inv, p.bin_min, p.scale, cwd, chd, totw, toth);
+      // owner-lane results, broadcast to the octet below
+      float g_in = g_out, g_xk = 0.f, g_w = 0.f, g_yk = 0.f, g_h = 0.f, gs_lo = 0.f, gs_hi = 0.f, dotw = 0.f, doth = 0.f;
+      if (b.found) {
+        float s_lo, s_hi, dk, dk1;
+        load_slopes(p.raw_s + r * p.ld_s + (int64_t)d * (K - 1), b.idx, K, s_lo, s_hi, dk, dk1);
         // local derivatives: y = yk + h N/Q, L = log(s^2 P / Q^2)
-        const float rr = rel_pos(b, v, inv);
-        const float s = b.sk, dk = b.dk, dk1 = b.dk1, h = b.hk, w = b.wk;
+        const float h = b.hk, w = b.wk, s = h / w;
+        const float rr = rel_pos(b, vd, s, dk, dk1, inv);
         const float omr = 1.f - rr, u = rr * omr, tm = 1.f - 2.f * rr;
         const float dd = dk1 + dk - 2.f * s;
         const float N = s * rr * rr + dk * u;
@@ -315,108 +312,101 @@ __global__ void __launch_bounds__(kThreads) rqs_backward_kernel(const RqsParams 
         }
         const float g_r = gy * y_r + gL * L_r;
         const float g_s = gy * y_s + gL * L_s;
-        g_dk = gy * y_dk + gL * L_dk;
-        g_dk1 = gy * y_dk1 + gL * L_dk1;
+        const float g_dk = gy * y_dk + gL * L_dk;
+        const float g_dk1 = gy * y_dk1 + gL * L_dk1;
         g_h = gy * y_h + g_s * iw;
         g_yk = gy;
         g_w = -(g_s * s + g_r * rr) * iw;
         g_xk = -g_r * iw;
+        if (b.idx > 0) gs_lo = g_dk * vms::sigmoidf_(s_lo);
+        if (b.idx < K - 1) gs_hi = g_dk1 * vms::sigmoidf_(s_hi);
+        // softmax Jacobian dot products: sum_i p_i g_b[i] with g_b[i] = [i<idx] g_k + [i==idx] g_bin
+        dotw = (g_xk * b.elt_w + g_w * b.e_w) * (float)(1.0 / totw);
+        doth = (g_yk * b.elt_h + g_h * b.e_h) * (float)(1.0 / toth);
       }
-      p.g_in[(row0 + r) * p.ld_g_in + d] = g_in;
-      // softmax Jacobian: g_raw[j] = c e_j (g_b[j] - sum_i p_i g_b[i]),  g_b[j] = [j<idx] g_k + [j==idx] g_bin
-      const int idx = b.idx;
-      const float ew_i = pw[idx], eh_i = ph[idx];
-      const float dotw = (g_xk * b.elt_w + g_w * ew_i) * (b.cw / p.scale);
-      const float doth = (g_yk * b.elt_h + g_h * eh_i) * (b.ch / p.scale);
-      const float s_lo = idx > 0 ? ps[idx - 1] : 0.f, s_hi = idx < K - 1 ? ps[idx] : 0.f;
-#pragma unroll 8
-      for (int k = 0; k < K; ++k) {
-        float gbw = k < idx ? g_xk : (k == idx ? g_w : 0.f);
-        float gbh = k < idx ? g_yk : (k == idx ? g_h : 0.f);
-        pw[k] = b.cw * pw[k] * (gbw - dotw);
-        ph[k] = b.ch * ph[k] * (gbh - doth);
+      const unsigned found_mask = __ballot_sync(0xffffffffu, b.found);
+      const unsigned oct_mask = (found_mask >> ((threadIdx.x & 31) & ~(kOct - 1))) & 0xffu;
+      const int src = oct_mask ? (__ffs(oct_mask) - 1) : 0;
+      if ((oct_mask ? b.found : (j == 0)) && active) p.g_in[r * p.ld_g_in + d] = g_in;
+      const int idx = oct_mask ? __shfl_sync(0xffffffffu, b.idx, src, kOct) : -2;  // -2: no bin matches any k
+      g_xk = __shfl_sync(0xffffffffu, g_xk, src, kOct);
+      g_w = __shfl_sync(0xffffffffu, g_w, src, kOct);
+      g_yk = __shfl_sync(0xffffffffu, g_yk, src, kOct);
+      g_h = __shfl_sync(0xffffffffu, g_h, src, kOct);
+      dotw = __shfl_sync(0xffffffffu, dotw, src, kOct);
+      doth = __shfl_sync(0xffffffffu, doth, src, kOct);
+      gs_lo = __shfl_sync(0xffffffffu, gs_lo, src, kOct);
+      gs_hi = __shfl_sync(0xffffffffu, gs_hi, src, kOct);
+      const float cw = (float)cwd, ch = (float)chd;
+      float gw[BPL], gh[BPL], gs[BPL];
+#pragma unroll
+      for (int i = 0; i < BPL; ++i) {
+        const int k = j * BPL + i;
+        const float gbw = k < idx ? g_xk : (k == idx ? g_w : 0.f);
+        const float gbh = k < idx ? g_yk : (k == idx ? g_h : 0.f);
+        gw[i] = cw * ew[i] * (gbw - dotw);  // out of range: every factor in brackets is 0
+        gh[i] = ch * eh[i] * (gbh - doth);
+        gs[i] = k == idx - 1 ? gs_lo : (k == idx ? gs_hi : 0.f);
       }
-#pragma unroll 8
-      for (int k = 0; k < K - 1; ++k) ps[k] = 0.f;
-      if (!b.oob) {
-        if (idx > 0) ps[idx - 1] = g_dk * vms::sigmoidf_(s_lo);
-        if (idx < K - 1) ps[idx] = g_dk1 * vms::sigmoidf_(s_hi);
+      if (active) {
+        store_bins<BPL, VEC>(p.g_w + r * p.ld_gw + (int64_t)d * K, j, K, gw);
+        store_bins<BPL, VEC>(p.g_h + r * p.ld_gh + (int64_t)d * K, j, K, gh);
+        store_bins<BPL, false>(p.g_s + r * p.ld_gs + (int64_t)d * (K - 1), j, K - 1, gs);
       }
     }
-    __syncthreads();
-    store_tile(p, st, row0, rows);
-    __syncthreads();  // stores read the stage; it is refilled by the next iteration's prefetch
-    stage ^= 1;
   }
-  cp_async_wait<0>();
 }
 
-vms_status configure(RqsParams& p, size_t& smem_bytes, int& grid, bool need_ldj_scratch) {
+inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+vms_status configure(RqsParams& p, int& grid) {
   VMS_REQUIRE(p.K >= 2 && p.K <= 64, VMS_ERR_INVALID_ARG, "num_bins must be in [2, 64], got %d", p.K);
-  VMS_REQUIRE(p.n_dims >= 1 && p.n_dims <= 128, VMS_ERR_INVALID_ARG, "n_dims must be in [1, 128], got %d", p.n_dims);
+  VMS_REQUIRE(p.n_dims >= 1 && p.n_dims <= 4096, VMS_ERR_INVALID_ARG, "n_dims must be in [1, 4096], got %d", p.n_dims);
   VMS_REQUIRE(p.n_rows >= 0, VMS_ERR_INVALID_ARG, "n_rows < 0");
   VMS_REQUIRE(p.bin_max > p.bin_min, VMS_ERR_INVALID_ARG, "bin_range must be increasing");
   // flows.py:92: Python float arithmetic, then one cast to float32
   p.scale = (float)((double)p.bin_max - (double)p.bin_min - (double)p.K * 1e-2);
   VMS_REQUIRE(p.scale > 0.f, VMS_ERR_INVALID_ARG, "bin_range too narrow for %d bins", p.K);
-  const int width = p.n_dims * (3 * p.K - 1);
-  p.lds = width | 1;
-  int tr = kThreads / p.n_dims;
-  if (tr < 1) tr = 1;
-  const size_t budget = 96 * 1024;  // two stages <= 96 KB => 2 CTAs / SM
-  while (tr > 1 && (size_t)kStages * tr * p.lds * 4 + (size_t)tr * p.n_dims * 4 > budget) tr >>= 1;
-  p.tile_rows = tr;
-  smem_bytes = (size_t)kStages * tr * p.lds * 4 + (need_ldj_scratch ? (size_t)tr * p.n_dims * 4 : 0);
-  VMS_REQUIRE(smem_bytes <= (size_t)vms::max_smem_optin(), VMS_ERR_UNSUPPORTED,
-              "RQS tile needs %zu bytes of shared memory", smem_bytes);
-  const int64_t n_tiles = (p.n_rows + tr - 1) / tr;
-  const int64_t cap = 2LL * vms::sm_count();
-  grid = (int)(n_tiles < cap ? n_tiles : cap);
+  const int64_t n_blocks = (p.n_rows + (kThreads / kOct) - 1) / (kThreads / kOct);
+  const int64_t cap = 16LL * vms::sm_count();
+  grid = (int)(n_blocks < cap ? n_blocks : cap);
   return VMS_OK;
 }
 
-// Opt in to > 48 KB of dynamic shared memory once per kernel instantiation (never inside a graph capture after
-// vms::rqs_prepare() has run).
-template <typename KernelT>
-vms_status prepare_kernel(KernelT kern) {
-  static bool done[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (!done[dev]) {
-    VMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, vms::max_smem_optin()));
-    done[dev] = true;
-  }
-  return VMS_OK;
+bool vector_ok(const RqsParams& p, bool backward) {
+  if (p.K % 4) return false;
+  bool ok = aligned16(p.raw_w) && aligned16(p.raw_h) && p.ld_w % 4 == 0 && p.ld_h % 4 == 0;
+  if (backward) ok = ok && aligned16(p.g_w) && aligned16(p.g_h) && p.ld_gw % 4 == 0 && p.ld_gh % 4 == 0;
+  return ok;
 }
 
-template <typename KernelT>
-vms_status launch(KernelT kern, const RqsParams& p, size_t smem_bytes, int grid, cudaStream_t st, const char* name) {
-  if (p.n_rows == 0) return VMS_OK;
-  vms_status s = prepare_kernel(kern);
-  if (s) return s;
-  kern<<<grid, kThreads, smem_bytes, st>>>(p);
-  VMS_LAUNCH_CHECK(name);
-  return VMS_OK;
-}
+#define VMS_RQS_DISPATCH(KERNEL, name)                                                    \
+  do {                                                                                    \
+    if (p.n_rows == 0) return VMS_OK;                                                     \
+    if (p.K <= 32) {                                                                      \
+      if (vec) KERNEL<4, true><<<grid, kThreads, 0, st>>>(p);                             \
+      else KERNEL<4, false><<<grid, kThreads, 0, st>>>(p);                                \
+    } else {                                                                              \
+      if (vec) KERNEL<8, true><<<grid, kThreads, 0, st>>>(p);                             \
+      else KERNEL<8, false><<<grid, kThreads, 0, st>>>(p);                                \
+    }                                                                                     \
+    VMS_LAUNCH_CHECK(name);                                                               \
+    return VMS_OK;                                                                        \
+  } while (0)
 
 vms_status run_apply(RqsParams p, cudaStream_t st) {
-  size_t smem;
   int grid;
-  vms_status s = configure(p, smem, grid, p.ldj_sum != nullptr);
+  vms_status s = configure(p, grid);
   if (s) return s;
-  if (p.K == 32) return launch(rqs_apply_kernel<32>, p, smem, grid, st, "rqs_apply<32>");
-  if (p.K == 20) return launch(rqs_apply_kernel<20>, p, smem, grid, st, "rqs_apply<20>");
-  return launch(rqs_apply_kernel<0>, p, smem, grid, st, "rqs_apply<K>");
+  const bool vec = vector_ok(p, false);
+  VMS_RQS_DISPATCH(rqs_apply_kernel, "rqs_apply_kernel");
 }
 vms_status run_backward(RqsParams p, cudaStream_t st) {
-  size_t smem;
   int grid;
-  vms_status s = configure(p, smem, grid, false);
+  vms_status s = configure(p, grid);
   if (s) return s;
-  if (p.K == 32) return launch(rqs_backward_kernel<32>, p, smem, grid, st, "rqs_backward<32>");
-  if (p.K == 20) return launch(rqs_backward_kernel<20>, p, smem, grid, st, "rqs_backward<20>");
-  return launch(rqs_backward_kernel<0>, p, smem, grid, st, "rqs_backward<K>");
+  const bool vec = vector_ok(p, true);
+  VMS_RQS_DISPATCH(rqs_backward_kernel, "rqs_backward_kernel");
 }
 
 RqsParams from_args(const vms_rqs_args& a) {
@@ -436,15 +426,7 @@ RqsParams from_args(const vms_rqs_args& a) {
 }  // namespace
 
 namespace vms {
-vms_status rqs_prepare() {
-  vms_status s;
-  if ((s = prepare_kernel(rqs_apply_kernel<32>))) return s;
-  if ((s = prepare_kernel(rqs_apply_kernel<20>))) return s;
-  if ((s = prepare_kernel(rqs_apply_kernel<0>))) return s;
-  if ((s = prepare_kernel(rqs_backward_kernel<32>))) return s;
-  if ((s = prepare_kernel(rqs_backward_kernel<20>))) return s;
-  return prepare_kernel(rqs_backward_kernel<0>);
-}
+vms_status rqs_prepare() { return VMS_OK; }  // no opt-in shared memory any more; kept for elbo.cu
 }  // namespace vms
 
 extern "C" {
