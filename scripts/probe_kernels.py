@@ -55,7 +55,7 @@ for (K, N, act, tag) in [(6, 200, 1, 'enc0'), (200, 4, 0, 'enc1'), (2, 200, 1, '
         print('%-10s %-6s [%d x %d x %d]  median %7.2f us  min %7.2f us  %6.2f TFLOP/s' % (tag, nm, B, K, N, med, mn,
                                                                                         fl / med / 1e6))
 K = 32
-for n in (B, 1 << 21):
+for n in (B, 1 << 19, 1 << 21):
     rw, rh, rs = T(rng.normal(size=(n, K))), T(rng.normal(size=(n, K))), T(rng.normal(size=(n, K - 1)))
     x, g = T(rng.uniform(-10, 10, n)), T(rng.normal(size=n))
     y, l = v.Tensor((n, )), v.Tensor((n, ))

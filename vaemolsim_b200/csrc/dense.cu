@@ -1,5 +1,5 @@
 // dense.cu -- K2/K3: small dense layers (FCDeepNN, spline conditioners, pre-masked MADE layers), forward and
-// reverse mode, as FP32 FFMA tiled GEMMs.
+// reverse mode, as FP32 FFMA GEMMs.
 //
 // Replaces Keras Dense at mappings.py:107-121 (`FCDeepNN.build` / `.call` :151-153), flows.py:136-152 and :185-196
 // (`SplineBijector` d1 + three heads), and the masked Dense layers inside tfp AutoregressiveNetwork
@@ -7,106 +7,171 @@
 //
 // Why FFMA and not tcgen05 here: the reference is float32 and parity is 1e-5 relative; contraction lengths are
 // 1..200 and output widths 4..190, and at the named batch (4096 rows / 148 SMs = 28 rows per SM) no CTA owns a
-// 128-row MMA tile.  The shapes are latency-bound, not throughput-bound ("GEMMs").
+// 128-row MMA tile.  The shapes are latency-bound, so the kernels are built for short critical paths: a 32-row tile
+// per CTA (128+ CTAs at batch 4096), the WHOLE contraction staged in shared memory in at most two chunks, one
+// barrier pair per chunk, 4x4 register tiles fed by 128-bit shared loads.
 #include "dense.cuh"
 
 namespace vms {
 
-constexpr int BM = 64, BN = 64, BK = 16, GT = 256;
+// ------------------------------------------------------------------------------------------------ row-tile GEMM
+constexpr int TM = 32, TN = 64, RT = 128, KC = 112;  // KC * (TM+4 + TN+4) * 4 B = 46.6 KB of static shared memory
 
 __device__ __forceinline__ float act_grad(float out, int act) {
   return act == VMS_ACT_RELU ? (out > 0.f ? 1.f : 0.f) : (act == VMS_ACT_TANH ? 1.f - out * out : 1.f);
 }
 
-__device__ __forceinline__ float load_a(const GemmParams& p, int m, int k) {
-  if (m >= p.M || k >= p.K) return 0.f;
-  if (p.a_ones) return 1.f;
-  if (p.ta) return m == p.a_ones_row ? 1.f : p.A[(int64_t)k * p.lda + m];
-  float v = p.A[(int64_t)m * p.lda + k];
-  if (p.a_act) v *= act_grad(p.Ao[(int64_t)m * p.ldao + k], p.a_act);
-  return v;
-}
-__device__ __forceinline__ float load_b(const GemmParams& p, int k, int n) {
-  if (n >= p.N || k >= p.K) return 0.f;
-  if (p.tb) return p.Bm[(int64_t)n * p.ldb + k];
-  float v = p.Bm[(int64_t)k * p.ldb + n];
-  if (p.b_act) v *= act_grad(p.Bo[(int64_t)k * p.ldbo + n], p.b_act);
-  return v;
-}
-
-__global__ void __launch_bounds__(GT) gemm_kernel(const GemmParams p) {
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
-  const int t = threadIdx.x;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int tm = (t / 16) * 4, tn = (t % 16) * 4;
+__global__ void __launch_bounds__(RT) gemm_rowtile_kernel(const RowTileParams p) {
+  __shared__ __align__(16) float As[KC][TM + 4];
+  __shared__ __align__(16) float Bs[KC][TN + 4];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int ty = t >> 4, tx = t & 15;
   float acc[4][4] = {};
-  int k_begin = 0, k_end = p.K;
-  if (p.k_per_split > 0) {
-    k_begin = blockIdx.z * p.k_per_split;
-    k_end = min(p.K, k_begin + p.k_per_split);
-  }
-  for (int phase = 0; phase < 2; ++phase) {
-    if (phase == 1 && (p.K2 <= 0 || blockIdx.z != 0)) break;
-    const int kb = phase ? 0 : k_begin, ke = phase ? p.K2 : k_end;
-    for (int k0 = kb; k0 < ke; k0 += BK) {
-      // stage A tile [BM x BK] and B tile [BK x BN]; thread mapping follows the contiguous axis of each operand
-#pragma unroll
-      for (int i = 0; i < (BM * BK) / GT; ++i) {
-        int e = t + i * GT, m, k;
-        if (phase == 0 && p.ta) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
-        float v;
-        if (phase == 0) v = (k0 + k < ke) ? load_a(p, m0 + m, k0 + k) : 0.f;
-        else v = (m0 + m < p.M && k0 + k < ke) ? p.A2[(int64_t)(m0 + m) * p.lda2 + k0 + k] : 0.f;
-        As[k][m] = v;
+  for (int seg = 0; seg < 2; ++seg) {
+    const int Kseg = seg == 0 ? p.K : p.K2;
+    if (Kseg <= 0) continue;
+    const float* A = seg == 0 ? p.A : p.A2;
+    const int64_t lda = seg == 0 ? p.lda : p.lda2;
+    const float* Bm = seg == 0 ? p.Bm : p.B2;
+    const int64_t ldb = seg == 0 ? p.ldb : p.ldb2;
+    const bool tb = seg == 0 && p.tb;
+    const bool ones = seg == 0 && p.a_ones;
+    const int a_act = seg == 0 ? p.a_act : 0;
+    for (int k0 = 0; k0 < Kseg; k0 += KC) {
+      const int kc = min(KC, Kseg - k0);
+      // A chunk: rows are contiguous along k => lanes walk k, warps walk rows; stored k-major for the 4-row loads
+      for (int m = warp; m < TM; m += RT / 32) {
+        const int gm = m0 + m;
+        for (int k = lane; k < kc; k += 32) {
+          float v = 0.f;
+          if (gm < p.M) {
+            if (ones) v = 1.f;
+            else {
+              v = A[(int64_t)gm * lda + k0 + k];
+              if (a_act) v *= act_grad(p.Ao[(int64_t)gm * p.ldao + k0 + k], a_act);
+            }
+          }
+          As[k][m] = v;
+        }
       }
-#pragma unroll
-      for (int i = 0; i < (BN * BK) / GT; ++i) {
-        int e = t + i * GT, n, k;
-        if (phase == 0 && p.tb) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
-        float v;
-        if (phase == 0) v = (k0 + k < ke) ? load_b(p, k0 + k, n0 + n) : 0.f;
-        else v = (n0 + n < p.N && k0 + k < ke) ? p.B2[(int64_t)(k0 + k) * p.ldb2 + n0 + n] : 0.f;
-        Bs[k][n] = v;
+      if (!tb) {  // B rows contiguous along n
+        for (int k = warp; k < kc; k += RT / 32) {
+          const float* src = Bm + (int64_t)(k0 + k) * ldb + n0;
+          for (int n = lane; n < TN; n += 32) Bs[k][n] = (n0 + n < p.N) ? src[n] : 0.f;
+        }
+      } else {  // B'(k, n) = Bm[n * ldb + k]: contiguous along k
+        for (int n = warp; n < TN; n += RT / 32) {
+          const bool ok = n0 + n < p.N;
+          const float* src = Bm + (int64_t)(n0 + n) * ldb + k0;
+          for (int k = lane; k < kc; k += 32) Bs[k][n] = ok ? src[k] : 0.f;
+        }
       }
       __syncthreads();
-#pragma unroll
-      for (int k = 0; k < BK; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(&As[k][tm]);
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tn]);
+#pragma unroll 4
+      for (int k = 0; k < kc; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
         const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+          for (int jn = 0; jn < 4; ++jn) acc[i][jn] = fmaf(av[i], bv[jn], acc[i][jn]);
       }
       __syncthreads();
     }
   }
-  float* C = p.C + (p.k_per_split > 0 ? (int64_t)blockIdx.z * p.split_stride : 0);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int m = m0 + tm + i;
+    const int m = m0 + ty * 4 + i;
     if (m >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tn + j;
+    for (int jn = 0; jn < 4; ++jn) {
+      const int n = n0 + tx * 4 + jn;
       if (n >= p.N) continue;
-      float v = acc[i][j];
+      float v = acc[i][jn];
       if (p.bias) v += p.bias[n];
       if (p.act == VMS_ACT_RELU) v = fmaxf(v, 0.f);
       else if (p.act == VMS_ACT_TANH) v = tanhf(v);
-      float* dst = C + (int64_t)m * p.ldc + n;
+      float* dst = p.C + (int64_t)m * p.ldc + n;
       *dst = p.accumulate ? *dst + v : v;
     }
   }
 }
 
-vms_status gemm_launch(const GemmParams& p, int splits, cudaStream_t st) {
+vms_status gemm_rowtile(const RowTileParams& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0) return VMS_OK;
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits > 0 ? splits : 1);
-  gemm_kernel<<<grid, GT, 0, st>>>(p);
-  VMS_LAUNCH_CHECK("gemm_kernel");
+  dim3 grid((p.N + TN - 1) / TN, (p.M + TM - 1) / TM);
+  gemm_rowtile_kernel<<<grid, RT, 0, st>>>(p);
+  VMS_LAUNCH_CHECK("gemm_rowtile_kernel");
+  return VMS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+constexpr int WM = 64, WN = 64, WT = 256, WR = 32;  // output tile 64 x 64, 32 batch rows per stage
+
+__global__ void __launch_bounds__(WT) gemm_wgrad_kernel(const WgradParams p) {
+  __shared__ __align__(16) float Xs[WR][WM + 4];
+  __shared__ __align__(16) float Gs[WR][WN + 4];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int i0 = blockIdx.y * WM, n0 = blockIdx.x * WN;
+  const int ty = t >> 4, tx = t & 15;
+  const int64_t rows_per_split = (p.B + p.splits - 1) / p.splits;
+  const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t r_end = min(p.B, r_begin + rows_per_split);
+  float acc[4][4] = {};
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += WR) {
+    const int rc = (int)min((int64_t)WR, r_end - r0);
+    for (int r = warp; r < WR; r += WT / 32) {
+      const bool ok = r < rc;
+      const int64_t gr = r0 + r;
+      for (int c = lane; c < WM; c += 32) {
+        const int i = i0 + c;
+        float v = 0.f;
+        if (ok && i <= p.Kin) v = (i == p.Kin || p.x == nullptr) ? 1.f : p.x[gr * p.ldx + i];
+        Xs[r][c] = v;
+      }
+      for (int c = lane; c < WN; c += 32) {
+        const int n = n0 + c;
+        float v = 0.f;
+        if (ok && n < p.N) {
+          v = p.g[gr * p.ldg + n];
+          if (p.act) v *= act_grad(p.out[gr * p.ldo + n], p.act);
+        }
+        Gs[r][c] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < WR; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(&Xs[r][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Gs[r][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) acc[i][jn] = fmaf(av[i], bv[jn], acc[i][jn]);
+    }
+    __syncthreads();
+  }
+  float* C = p.part + (int64_t)blockIdx.z * p.split_stride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = i0 + ty * 4 + i;
+    if (gi > p.Kin) continue;
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn) {
+      const int n = n0 + tx * 4 + jn;
+      if (n < p.N) C[(int64_t)gi * p.N + n] = acc[i][jn];
+    }
+  }
+}
+
+vms_status gemm_wgrad(const WgradParams& p, cudaStream_t st) {
+  if (p.B <= 0 || p.N <= 0) return VMS_OK;
+  dim3 grid((p.N + WN - 1) / WN, (p.Kin + 1 + WM - 1) / WM, p.splits);
+  gemm_wgrad_kernel<<<grid, WT, 0, st>>>(p);
+  VMS_LAUNCH_CHECK("gemm_wgrad_kernel");
   return VMS_OK;
 }
 
@@ -136,7 +201,7 @@ vms_status sum_partials_launch(const float* part, int n_partials, int64_t stride
 }
 
 int dense_splits(int64_t B) {
-  int64_t s = (B + 255) / 256;
+  int64_t s = (B + 127) / 128;
   if (s < 1) s = 1;
   if (s > 64) s = 64;
   return (int)s;
@@ -178,21 +243,21 @@ vms_status vms_dense_forward(const float* x, int64_t ld_x, const float* W, const
   VMS_REQUIRE(B < (1LL << 31), VMS_ERR_SHAPE, "dense_forward: batch too large");
   VMS_REQUIRE(W && out, VMS_ERR_INVALID_ARG, "dense_forward: NULL W / out");
   VMS_REQUIRE(act >= 0 && act <= 2, VMS_ERR_INVALID_ARG, "dense_forward: unknown activation %d", act);
-  VMS_REQUIRE((C > 0) == (cond != nullptr && Wc != nullptr) || C == 0, VMS_ERR_INVALID_ARG,
+  VMS_REQUIRE(C == 0 || (cond != nullptr && Wc != nullptr), VMS_ERR_INVALID_ARG,
               "dense_forward: conditional_input missing");
-  if (B == 0) return VMS_OK;
-  GemmParams p = {};
-  p.M = (int)B; p.N = N; p.K = K;
-  p.A = x; p.lda = ld_x; p.a_ones = (x == nullptr); p.a_ones_row = -1;
   VMS_REQUIRE(x != nullptr || K == 1, VMS_ERR_INVALID_ARG, "dense_forward: NULL x is only valid for the ones input (K=1)");
+  if (B == 0) return VMS_OK;
+  RowTileParams p = {};
+  p.M = (int)B; p.N = N; p.K = K;
+  p.A = x; p.lda = ld_x; p.a_ones = (x == nullptr);
   p.Bm = W; p.ldb = N;
   if (C > 0) { p.A2 = cond; p.lda2 = ld_c; p.B2 = Wc; p.ldb2 = N; p.K2 = C; }
   p.bias = b; p.act = act; p.C = out; p.ldc = ld_out;
-  return gemm_launch(p, 0, as_stream(stream));
+  return gemm_rowtile(p, as_stream(stream));
 }
 
 size_t vms_dense_backward_workspace(int64_t B, int K, int N, int C) {
-  size_t rows = (size_t)(K + 1) + (size_t)(C > 0 ? C : 0);
+  size_t rows = (size_t)(K + 1) + (size_t)(C > 0 ? C + 1 : 0);
   return (size_t)dense_splits(B) * rows * (size_t)N * sizeof(float);
 }
 
@@ -210,49 +275,44 @@ vms_status vms_dense_backward(const float* x, int64_t ld_x, const float* W, int6
   vms_status s;
   if (g_x) {  // g_x = (g_out * act') @ W^T
     VMS_REQUIRE(W, VMS_ERR_INVALID_ARG, "dense_backward: W required for g_x");
-    GemmParams p = {};
+    RowTileParams p = {};
     p.M = (int)B; p.N = K; p.K = N;
-    p.A = g_out; p.lda = ld_g; p.Ao = out; p.ldao = ld_out; p.a_act = act; p.a_ones_row = -1;
+    p.A = g_out; p.lda = ld_g; p.Ao = out; p.ldao = ld_out; p.a_act = act;
     p.Bm = W; p.ldb = N; p.tb = 1;
     p.C = g_x; p.ldc = ld_gx; p.accumulate = accumulate_x;
-    if ((s = gemm_launch(p, 0, st))) return s;
+    if ((s = gemm_rowtile(p, st))) return s;
   }
   if (g_cond) {
     VMS_REQUIRE(Wc && C > 0, VMS_ERR_INVALID_ARG, "dense_backward: Wc required for g_cond");
-    GemmParams p = {};
+    RowTileParams p = {};
     p.M = (int)B; p.N = C; p.K = N;
-    p.A = g_out; p.lda = ld_g; p.Ao = out; p.ldao = ld_out; p.a_act = act; p.a_ones_row = -1;
+    p.A = g_out; p.lda = ld_g; p.Ao = out; p.ldao = ld_out; p.a_act = act;
     p.Bm = Wc; p.ldb = N; p.tb = 1;
     p.C = g_cond; p.ldc = ld_gc;
-    if ((s = gemm_launch(p, 0, st))) return s;
+    if ((s = gemm_rowtile(p, st))) return s;
   }
+  const int splits = dense_splits(B);
   if (g_W || g_b) {  // [g_W; g_b] = [x^T; 1^T] @ (g_out * act'), split over the batch, partials summed in order
     VMS_REQUIRE(workspace, VMS_ERR_INVALID_ARG, "dense_backward: workspace required");
-    const int splits = dense_splits(B);
-    GemmParams p = {};
-    p.M = K + 1; p.N = N; p.K = (int)B;
-    p.A = x; p.lda = ld_x; p.ta = 1; p.a_ones = (x == nullptr); p.a_ones_row = K;
-    p.Bm = g_out; p.ldb = ld_g; p.Bo = out; p.ldbo = ld_out; p.b_act = act;
-    p.C = (float*)workspace; p.ldc = N;
-    p.k_per_split = (int)((B + splits - 1) / splits);
-    p.split_stride = (int64_t)(K + 1) * N;
-    if ((s = gemm_launch(p, splits, st))) return s;
+    WgradParams p = {};
+    p.B = B; p.Kin = K; p.N = N;
+    p.x = x; p.ldx = ld_x;
+    p.g = g_out; p.ldg = ld_g; p.out = out; p.ldo = ld_out; p.act = act;
+    p.part = (float*)workspace; p.split_stride = (int64_t)(K + 1) * N; p.splits = splits;
+    if ((s = gemm_wgrad(p, st))) return s;
     if ((s = sum_partials_launch((const float*)workspace, splits, p.split_stride, (int64_t)K * N, g_W, N, g_b, 1.f,
                                  accumulate, st)))
       return s;
   }
   if (g_Wc) {
     VMS_REQUIRE(workspace && cond && C > 0, VMS_ERR_INVALID_ARG, "dense_backward: cond / workspace required for g_Wc");
-    const int splits = dense_splits(B);
     float* ws = (float*)workspace + (size_t)splits * (K + 1) * N;
-    GemmParams p = {};
-    p.M = C; p.N = N; p.K = (int)B;
-    p.A = cond; p.lda = ld_c; p.ta = 1; p.a_ones_row = -1;
-    p.Bm = g_out; p.ldb = ld_g; p.Bo = out; p.ldbo = ld_out; p.b_act = act;
-    p.C = ws; p.ldc = N;
-    p.k_per_split = (int)((B + splits - 1) / splits);
-    p.split_stride = (int64_t)C * N;
-    if ((s = gemm_launch(p, splits, st))) return s;
+    WgradParams p = {};
+    p.B = B; p.Kin = C; p.N = N;
+    p.x = cond; p.ldx = ld_c;
+    p.g = g_out; p.ldg = ld_g; p.out = out; p.ldo = ld_out; p.act = act;
+    p.part = ws; p.split_stride = (int64_t)(C + 1) * N; p.splits = splits;
+    if ((s = gemm_wgrad(p, st))) return s;
     if ((s = sum_partials_launch(ws, splits, p.split_stride, (int64_t)C * N, g_Wc, 0, nullptr, 1.f, accumulate, st)))
       return s;
   }

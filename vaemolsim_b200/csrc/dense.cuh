@@ -1,29 +1,37 @@
-// dense.cuh -- internal interface of the FFMA GEMM used by dense.cu and the fused ELBO plan (elbo.cu).
+// dense.cuh -- internal interface of the FFMA GEMMs used by dense.cu and the fused ELBO plan (elbo.cu).
 #pragma once
 #include "common.cuh"
 
 namespace vms {
 
-struct GemmParams {
+// C[M,N] (+)= act( A'[M,K] @ B'[K,N] (+ A2[M,K2] @ B2[K2,N]) + bias ),   one row tile of 32 x 64 per CTA.
+//   A'(m,k) = A[m*lda + k] * act'(Ao[m*ldao + k])   (a_act != 0: reverse mode through the layer's activation)
+//           = 1                                      (a_ones: the ones((B,1)) conditioner input, flows.py:184-185)
+//   B'(k,n) = Bm[k*ldb + n]  or, with tb,  Bm[n*ldb + k]   (weight matrix used transposed for the input gradient)
+struct RowTileParams {
   int M, N, K;
-  // A operand: value(m,k)
-  const float* A; int64_t lda; int ta;          // ta: A[k*lda+m] else A[m*lda+k]
-  const float* Ao; int64_t ldao; int a_act;     // multiply by act'(Ao[same index]) (never used with ta)
-  int a_ones;                                   // A == 1 everywhere
-  int a_ones_row;                               // with ta: row m == a_ones_row reads as 1 (bias gradient), -1 = off
-  // B operand: value(k,n)
-  const float* Bm; int64_t ldb; int tb;         // tb: B[n*ldb+k] else B[k*ldb+n]
-  const float* Bo; int64_t ldbo; int b_act;     // multiply by act'(Bo[same index]) (never used with tb)
-  // optional second product accumulated into the same tile (conditional input): A2[M,K2] @ B2[K2,N]
+  const float* A; int64_t lda; int a_ones;
+  const float* Ao; int64_t ldao; int a_act;
+  const float* Bm; int64_t ldb; int tb;
   const float* A2; int64_t lda2; const float* B2; int64_t ldb2; int K2;
-  // epilogue
   const float* bias; int act; int accumulate;
   float* C; int64_t ldc;
-  // split-K: blockIdx.z handles k in [z*k_per_split, ...); partial z written at C + z*split_stride
-  int k_per_split; int64_t split_stride;
 };
+vms_status gemm_rowtile(const RowTileParams& p, cudaStream_t st);
 
-vms_status gemm_launch(const GemmParams& p, int splits, cudaStream_t st);
+// Weight + bias gradient of one Dense layer, split over the batch:
+//   part[s][i][n] = sum_{r in split s} X'(r,i) * G'(r,n),   i in [0, Kin] (row Kin = ones: the bias gradient),
+//   X'(r,i) = x[r*ldx + i] (or 1 when x == NULL),  G'(r,n) = g[r*ldg + n] * act'(out[r*ldo + n]).
+// Partials are written to part + s*split_stride as a dense [Kin+1, N] block (the Keras "kernel then bias" order).
+struct WgradParams {
+  int64_t B; int Kin, N;
+  const float* x; int64_t ldx;
+  const float* g; int64_t ldg;
+  const float* out; int64_t ldo; int act;
+  float* part; int64_t split_stride; int splits;
+};
+vms_status gemm_wgrad(const WgradParams& p, cudaStream_t st);
+
 vms_status sum_partials_launch(const float* part, int n_partials, int64_t stride, int64_t n0, float* out0, int64_t n1,
                                float* out1, float scale, int accumulate, cudaStream_t st);
 int dense_splits(int64_t B);

@@ -187,23 +187,21 @@ vms_status dense_fwd(const float* x, int64_t ldx, const float* W, const float* b
 vms_status dense_wgrad(vms_elbo_plan_s* pl, const float* x, int64_t ldx, int64_t B, int K, int N, int act,
                        const float* out, int64_t ldo, const float* g_out, int64_t ldg, int64_t off, int splits,
                        cudaStream_t st) {
-  GemmParams p = {};
-  p.M = K + 1; p.N = N; p.K = (int)B;
-  p.A = x; p.lda = ldx; p.ta = 1; p.a_ones = (x == nullptr); p.a_ones_row = K;
-  p.Bm = g_out; p.ldb = ldg; p.Bo = out; p.ldbo = ldo; p.b_act = act;
-  p.C = pl->gpart + off; p.ldc = N;
-  p.k_per_split = (int)((B + splits - 1) / splits);
-  p.split_stride = pl->off.total;
-  return gemm_launch(p, splits, st);
+  WgradParams p = {};
+  p.B = B; p.Kin = K; p.N = N;
+  p.x = x; p.ldx = ldx;
+  p.g = g_out; p.ldg = ldg; p.out = out; p.ldo = ldo; p.act = act;
+  p.part = pl->gpart + off; p.split_stride = pl->off.total; p.splits = splits;
+  return gemm_wgrad(p, st);
 }
 vms_status dense_xgrad(const float* W, int64_t B, int K, int N, int act, const float* out, int64_t ldo,
                        const float* g_out, int64_t ldg, float* g_x, int64_t ldgx, int accumulate, cudaStream_t st) {
-  GemmParams p = {};
+  RowTileParams p = {};
   p.M = (int)B; p.N = K; p.K = N;
-  p.A = g_out; p.lda = ldg; p.Ao = out; p.ldao = ldo; p.a_act = act; p.a_ones_row = -1;
+  p.A = g_out; p.lda = ldg; p.Ao = out; p.ldao = ldo; p.a_act = act;
   p.Bm = W; p.ldb = N; p.tb = 1;
   p.C = g_x; p.ldc = ldgx; p.accumulate = accumulate;
-  return gemm_launch(p, 0, st);
+  return gemm_rowtile(p, st);
 }
 
 #define VMS_TRY(expr)          \

@@ -328,7 +328,9 @@ __global__ void __launch_bounds__(kThreads) rqs_backward_kernel(const RqsParams 
       const unsigned oct_mask = (found_mask >> ((threadIdx.x & 31) & ~(kOct - 1))) & 0xffu;
       const int src = oct_mask ? (__ffs(oct_mask) - 1) : 0;
       if ((oct_mask ? b.found : (j == 0)) && active) p.g_in[r * p.ld_g_in + d] = g_in;
-      const int idx = oct_mask ? __shfl_sync(0xffffffffu, b.idx, src, kOct) : -2;  // -2: no bin matches any k
+      // the shuffle must be executed by every lane of the warp (octets diverge on oct_mask): select afterwards
+      const int idx_owner = __shfl_sync(0xffffffffu, b.idx, src, kOct);
+      const int idx = oct_mask ? idx_owner : -2;  // -2: no bin matches any k
       g_xk = __shfl_sync(0xffffffffu, g_xk, src, kOct);
       g_w = __shfl_sync(0xffffffffu, g_w, src, kOct);
       g_yk = __shfl_sync(0xffffffffu, g_yk, src, kOct);

@@ -146,6 +146,8 @@ class AutoregressiveBlockwise(IndependentBlockwise):
         self.auto_net = P.AutoregressiveNetwork(max(self.param_nums), self.num_dofs, conditional=self.conditional,
                                                 conditional_event_shape=self.conditional_event_shape,
                                                 **self.auto_net_params)
+        self.auto_net.build((None, self.num_dofs))  # Keras builds sub-layers on first use; weights exist from here on
+        self.auto_net.built = True
 
     def call(self, inputs, conditional_input=None):
         inputs = as_tensor(inputs)
