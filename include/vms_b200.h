@@ -265,6 +265,12 @@ typedef struct vms_elbo_plan_s* vms_elbo_plan;
 vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan);
 vms_status vms_elbo_plan_destroy(vms_elbo_plan plan);
 int64_t vms_elbo_param_count(const vms_elbo_desc* desc);
+/* Two implementations sit behind the plan: a FUSED one (a single persistent kernel, 32-row tiles resident in shared
+ * memory; chosen automatically when the shape fits: dx, dz <= 8, num_bins <= 32 and a multiple of 4, shared memory
+ * <= 227 KB) and an UNFUSED one (per-layer kernels replayed as a CUDA graph; any shape).  mode 0 = auto, 1 = force
+ * the unfused path (used by the tests to cross-check the two on the device).                                      */
+vms_status vms_elbo_plan_set_mode(vms_elbo_plan plan, int mode);
+int vms_elbo_plan_is_fused(vms_elbo_plan plan);
 /* Forward only.  x [B, dx], eps [B, dz] (the reparameterisation noise is an INPUT in parity mode).  Outputs (any
  * nullable): z [B, dz], logq [B], logpz [B], logpx [B], scalars[3] = {loss, nll, kl} (kl unweighted mean).      */
 vms_status vms_elbo_forward(vms_elbo_plan plan, const float* theta, const float* x, const float* eps, int64_t B,

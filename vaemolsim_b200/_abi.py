@@ -104,6 +104,8 @@ _SIGS = {
     'vms_elbo_plan_create': (None, [C.POINTER(ElboDesc), C.POINTER(c_vp)]),
     'vms_elbo_plan_destroy': (None, [c_vp]),
     'vms_elbo_param_count': (c_i64, [C.POINTER(ElboDesc)]),
+    'vms_elbo_plan_set_mode': (None, [c_vp, c_int]),
+    'vms_elbo_plan_is_fused': (c_int, [c_vp]),
     'vms_elbo_forward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_elbo_forward_backward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
 }

@@ -75,6 +75,12 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 #define VMS_HALF_LOG_2PI 0.91893853320467274178f
 #define VMS_LOG_2PI 1.83787706640934548356f
 
+// tfp Normal._log_prob: -0.5 (x/s - m/s)^2 - (0.5 log 2pi + log s)
+__device__ __forceinline__ float normal_lp(float x, float loc, float scale) {
+  float z = x / scale - loc / scale;
+  return -0.5f * z * z - (VMS_HALF_LOG_2PI + logf(scale));
+}
+
 __device__ __forceinline__ float apply_scale(float raw, int mode) {
   if (mode == VMS_SCALE_IDENTITY) return raw;
   float s = softplus_tf(raw);

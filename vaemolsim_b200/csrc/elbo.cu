@@ -11,59 +11,12 @@
 // The plan owns every intermediate (activations kept for the backward pass, split-K gradient partials) in HBM --
 // sized once for max_batch -- and replays the whole step as ONE CUDA graph per (batch, pointer set): the step is
 // ~60 small kernels whose launch overhead would otherwise dominate at the named batch of 4096.
-#include "dense.cuh"
+#include "elbo_plan.cuh"
 #include <math.h>
-#include <vector>
-#include <map>
-#include <array>
 
 namespace vms {
 
 vms_status rqs_prepare();  // rqs.cu
-
-struct FlowBlock {
-  int cs0, cs1, ts0, ts1;  // conditioner / transformed column ranges (flows.py:290-306 + tfp RealNVP reverse mask)
-  int cin, dt, ldr;        // conditioner input width (>=1: ones input when empty), transformed dims, raw row width
-  int64_t off_d1W, off_d1b, off_hW, off_hb;
-};
-
-struct Offsets {
-  int64_t enc0W, enc0b, enc1W, enc1b, dec0W, dec0b, dec1W, dec1b, total;
-};
-
-static void realnvp_split(int i, int D, int& cs0, int& cs1, int& ts0, int& ts1) {
-  if (D == 1) { cs0 = cs1 = 0; ts0 = 0; ts1 = 1; return; }
-  if (i % 2 == 0) { int m = D / 2; cs0 = 0; cs1 = m; ts0 = m; ts1 = D; return; }
-  int m = D - D / 2;
-  cs0 = D - m; cs1 = D; ts0 = 0; ts1 = D - m;
-}
-
-static Offsets layout(const vms_elbo_desc& d, std::vector<FlowBlock>* blocks) {
-  Offsets o;
-  int64_t p = 0;
-  o.enc0W = p; p += (int64_t)d.dx * d.hidden;
-  o.enc0b = p; p += d.hidden;
-  o.enc1W = p; p += (int64_t)d.hidden * 2 * d.dz;
-  o.enc1b = p; p += 2 * d.dz;
-  o.dec0W = p; p += (int64_t)d.dz * d.hidden;
-  o.dec0b = p; p += d.hidden;
-  o.dec1W = p; p += (int64_t)d.hidden * 2 * d.dx;
-  o.dec1b = p; p += 2 * d.dx;
-  for (int i = 0; i < d.num_blocks; ++i) {
-    FlowBlock b;
-    realnvp_split(i, d.dz, b.cs0, b.cs1, b.ts0, b.ts1);
-    b.cin = b.cs1 - b.cs0 > 0 ? b.cs1 - b.cs0 : 1;
-    b.dt = b.ts1 - b.ts0;
-    b.ldr = b.dt * (3 * d.num_bins - 1);
-    b.off_d1W = p; p += (int64_t)b.cin * d.flow_hidden;
-    b.off_d1b = p; p += d.flow_hidden;
-    b.off_hW = p; p += (int64_t)d.flow_hidden * b.ldr;
-    b.off_hb = p; p += b.ldr;
-    if (blocks) blocks->push_back(b);
-  }
-  o.total = p;
-  return o;
-}
 
 // ------------------------------------------------------------------------------------------------ small kernels
 // scalars[0] = loss = nll + w kl, [1] = nll = mean(-logpx), [2] = kl = mean(logq - logpz); fixed-order reduction
@@ -148,24 +101,6 @@ __global__ void encoder_head_bwd_kernel(const float* __restrict__ z, const float
 }  // namespace vms
 
 using namespace vms;
-
-struct vms_elbo_plan_s {
-  vms_elbo_desc d;
-  Offsets off;
-  std::vector<FlowBlock> blocks;
-  int64_t maxB;
-  int splits_max;
-  // forward intermediates
-  float *he, *pe, *z, *logq, *logpz, *logpx, *hd, *pd, *scalars, *partial;
-  std::vector<float*> u;    // u[i], i = 0..num_blocks: chain-inverse states, u[num_blocks] = z, u[0] = base sample
-  std::vector<float*> hid;  // [B, flow_hidden] per block
-  std::vector<float*> raw;  // [B, ldr] per block
-  // backward scratch
-  float *g_pd, *g_hd, *g_z, *g_pe, *g_he, *g_ua, *g_ub, *g_raw, *g_hid, *g_ldj, *gpart;
-  std::vector<void*> allocs;
-  // graph cache: key = (mode, B, theta, x, eps, out pointers...)
-  std::map<std::array<uintptr_t, 10>, std::pair<cudaGraphExec_t, int>> graphs;
-};
 
 namespace {
 
@@ -424,6 +359,7 @@ vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan) 
   A_(pl->g_raw, B * max_ldr); A_(pl->g_hid, B * (d.num_blocks ? d.flow_hidden : 1)); A_(pl->g_ldj, B);
   A_(pl->gpart, (size_t)pl->splits_max * pl->off.total);
 #undef A_
+  if (!s) s = fused_create(pl);
   if (s) { vms_elbo_plan_destroy(pl); return s; }
   *plan = pl;
   return VMS_OK;
@@ -433,6 +369,7 @@ vms_status vms_elbo_plan_destroy(vms_elbo_plan pl) {
   if (!pl) return VMS_OK;
   for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.first);
   for (void* p : pl->allocs) cudaFree(p);
+  fused_destroy(pl);
   delete pl;
   return VMS_OK;
 }
@@ -445,11 +382,22 @@ static vms_status check_call(vms_elbo_plan pl, const float* theta, const float* 
   return VMS_OK;
 }
 
+vms_status vms_elbo_plan_set_mode(vms_elbo_plan pl, int mode) {
+  VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "elbo_plan_set_mode: NULL plan");
+  VMS_REQUIRE(mode == 0 || mode == 1, VMS_ERR_INVALID_ARG, "elbo_plan_set_mode: mode must be 0 (auto) or 1 (unfused)");
+  pl->mode = mode;
+  return VMS_OK;
+}
+
+int vms_elbo_plan_is_fused(vms_elbo_plan pl) { return pl && pl->fused && pl->mode == 0 ? 1 : 0; }
+
 vms_status vms_elbo_forward(vms_elbo_plan pl, const float* theta, const float* x, const float* eps, int64_t B, float* z,
                             float* logq, float* logpz, float* logpx, float* scalars, vms_stream stream) {
   vms_status s = check_call(pl, theta, x, eps, B);
   if (s) return s;
   cudaStream_t st = as_stream(stream);
+  if (pl->fused && pl->mode == 0)
+    return fused_run(pl, theta, x, eps, B, false, z, logq, logpz, logpx, nullptr, scalars, st);
   std::array<uintptr_t, 10> key = {0, (uintptr_t)B, (uintptr_t)theta, (uintptr_t)x, (uintptr_t)eps, (uintptr_t)z,
                                    (uintptr_t)logq, (uintptr_t)logpz, (uintptr_t)logpx, (uintptr_t)scalars};
   const vms_elbo_desc& d = pl->d;
@@ -469,6 +417,8 @@ vms_status vms_elbo_forward_backward(vms_elbo_plan pl, const float* theta, const
   if (s) return s;
   VMS_REQUIRE(grad, VMS_ERR_INVALID_ARG, "elbo_forward_backward: NULL grad");
   cudaStream_t st = as_stream(stream);
+  if (pl->fused && pl->mode == 0)
+    return fused_run(pl, theta, x, eps, B, true, nullptr, nullptr, nullptr, nullptr, grad, scalars, st);
   std::array<uintptr_t, 10> key = {1, (uintptr_t)B, (uintptr_t)theta, (uintptr_t)x, (uintptr_t)eps, (uintptr_t)grad,
                                    (uintptr_t)scalars, 0, 0, 0};
   return run_graphed(pl, key, st, [&]() -> vms_status {

@@ -42,11 +42,6 @@ __device__ __forceinline__ float i0e_f(float x) {
   return 0.5f * (b0 - b2) / sqrtf(x);
 }
 
-__device__ __forceinline__ float normal_lp(float x, float loc, float scale) {
-  float z = x / scale - loc / scale;
-  return -0.5f * z * z - (VMS_HALF_LOG_2PI + logf(scale));
-}
-
 __global__ void blockwise_lp_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ params,
                                     int64_t ld_p, int64_t B, int D, const BlockwiseSpec spec, int scale_mode,
                                     float* __restrict__ lp, int accumulate) {

@@ -251,6 +251,14 @@ class FusedELBO(object):
             return [], 2, 1, -1.0, 1.0
         raise NotImplementedError('fused ELBO: prior must be a static N(0, I) DistributionLambda or a FlowedDistribution')
 
+    def set_mode(self, mode):
+        """0 = auto (the single fused kernel when the shape fits), 1 = force the unfused per-layer graph path."""
+        ctx().lib.vms_elbo_plan_set_mode(self.handle, int(mode))
+
+    @property
+    def is_fused(self):
+        return bool(ctx().lib.vms_elbo_plan_is_fused(self.handle))
+
     def forward(self, x, eps, want=('z', 'logq', 'logpz', 'logpx')):
         c = ctx()
         B = x.shape[0]
