@@ -299,7 +299,7 @@ def test_fused_kernel_agrees_with_unfused_plan(vms, prior, dz, B, bins):
     assert_close(out_f['scalars'][:3], out_u['scalars'][:3], rtol=1e-5, atol=1e-5, what='forward scalars')
     assert_close(sc_f[:3], sc_u[:3], rtol=1e-5, atol=1e-5, what='fwd+bwd scalars')
     rel = np.linalg.norm(g_f - g_u) / np.linalg.norm(g_u)
-    assert rel < 2e-6, rel
+    assert rel < 1e-5, rel  # two float32 evaluations with different summation orders
     assert_close(g_f, g_u, rtol=1e-4, atol=5e-6 * max(np.abs(g_u).max(), 1e-3), what='flat gradient fused vs unfused')
 
 

@@ -13,7 +13,7 @@
 // activations that the unfused path round-trips through HBM/L2 between ~55 launches.  Here one CTA owns a tile of
 // 32 rows and keeps every activation of the tile in shared memory (~210 KB of the 227 KB) from the first encoder
 // layer to the last weight gradient:
-//   * grid = min(#tiles, #SMs) persistent CTAs of 256 threads (batch 4096 -> 128 CTAs, one tile each);
+//   * grid = min(#tiles, #SMs) persistent CTAs of 512 threads (batch 4096 -> 128 CTAs, one tile each);
 //   * wide layers (the 100 x 95 spline-parameter heads, the 200-wide MLP layers) are FP32 FFMA "outer-product" GEMMs:
 //     a lane owns output columns (coalesced / conflict-free operand), a warp owns a slab of 4..16 output rows whose
 //     operand is read by 128-bit shared-memory broadcast, accumulators stay in registers.  Forward, input-gradient
@@ -31,7 +31,7 @@
 namespace vms {
 
 constexpr int FR = 32;            // rows per tile
-constexpr int FT = 256;           // threads per CTA
+constexpr int FT = 512;           // threads per CTA (16 warps: the phases are latency-bound chains, TLP is what hides them)
 constexpr int FW = FT / 32;       // warps per CTA
 constexpr int kMaxBlocks = 8;
 constexpr int kMaxThin = 16;      // widest "thin" layer (2 dx, 2 dz, conditioner inputs)
@@ -45,15 +45,15 @@ struct FusedParams {
   int dx, dz, hidden, nb, K, fh;
   float bin_min, scale, klw;
   int64_t B;
-  int n_tiles, P;
+  int n_tiles, P, n_mlp;  // n_mlp: number of leading floats of theta (encoder + decoder) kept resident in shared memory
   int enc0W, enc0b, enc1W, enc1b, dec0W, dec0b, dec1W, dec1b;
   FBlk blk[kMaxBlocks];
   const float *theta, *x, *eps;
   float *z, *logq, *logpz, *logpx;  // optional per-row outputs
   float *gpart, *spart;             // [grid][P] partial gradients, [grid][2] partial loss sums
   // shared-memory pitches and offsets (floats)
-  int ldx, ldz, ldh, ldf, ldfp, ldpe, ldpd, ldc, ldrm, ldwt;
-  int o_xs, o_xT, o_eps, o_zR, o_zT, o_he, o_hd, o_pe, o_pd, o_u, o_lp, o_hidT, o_hidR, o_cond, o_raw, o_W, o_gz,
+  int ldx, ldz, ldh, ldf, ldfp, ldpe, ldpd, ldc, ldrm, ldwt, sb;
+  int o_xs, o_xT, o_eps, o_zR, o_zT, o_he, o_hd, o_pe, o_pd, o_u, o_lp, o_hid, o_cond, o_raw, o_W, o_Wp, o_B, o_gz,
       o_gua, o_gub, o_scr;
 };
 
@@ -64,172 +64,381 @@ struct FusedCfg {
   float *gpart, *spart;
 };
 
+// ------------------------------------------------------------------------------------------------ async staging
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM routines
-// out[i][j] = sum_t S[t * sSt + i] * Lop(t, j),   Lop(t, j) = 1 if j == ones_j else L[t * sLt + j * sLj]
-//   S : shared memory, i contiguous, 16-byte aligned rows; read as float4 broadcast (one slab of TI rows per warp)
-//   L : shared (LG = false) or global (LG = true) memory; lanes own j = j0 + 32 c, c < TJ
-// Work items (i-slab, j-group) are dealt round-robin to the 8 warps.  epi(i, j, value) consumes each output.
-template <int TI, int TJ, bool LG, class Epi>
-__device__ __forceinline__ void outer_gemm(const float* __restrict__ S, int sSt, const float* __restrict__ L, int sLt,
-                                           int sLj, int ones_j, int I, int J, int T, Epi epi) {
+// The kernel is a long chain of small phases, each executed once per tile: instruction FETCH, not issue, bounded the
+// first version (ncu: stall_no_instruction 1.8 per issue with every GEMM call site inlined and its epilogue fully
+// unrolled).  So the routines below are __noinline__, take shared-memory operands as OFFSETS into the dynamic
+// shared array (the compiler keeps LDS/STS addressing across the call) and a small POD epilogue descriptor instead
+// of a lambda: six GEMM instantiations serve the 12 call sites.
+struct Epi {
+  int kind;    // 0: out = act(v + bias[j]);  1: out = aux > 0 ? v : 0 (relu');  2: out = v (1 - aux^2) (tanh');
+               // 3: global partial gradient g[i * si + j * sj] (= or +=)
+  int out, ld;            // kinds 0-2: shared offset / pitch of out[i][j]
+  int bias, relu;         // kind 0: shared offset of bias[j] (-1: none), relu flag
+  int aux, ld_aux;        // kinds 1-2
+  float* g; int si, sj, first;  // kind 3
+};
+
+__device__ __forceinline__ void epi_apply(const Epi& e, float* sm, int i, int j, float v) {
+  if (e.kind == 0) {
+    if (e.bias >= 0) v += sm[e.bias + j];
+    sm[e.out + i * e.ld + j] = e.relu ? fmaxf(v, 0.f) : v;
+  } else if (e.kind == 1) {
+    sm[e.out + i * e.ld + j] = sm[e.aux + i * e.ld_aux + j] > 0.f ? v : 0.f;
+  } else if (e.kind == 2) {
+    const float h = sm[e.aux + i * e.ld_aux + j];
+    sm[e.out + i * e.ld + j] = v * (1.f - h * h);
+  } else {
+    float* d = e.g + i * e.si + j * e.sj;
+    *d = e.first ? v : *d + v;
+  }
+}
+
+// out[i][j] = sum_t S[t * sSt + i] * L[t * sLt + j * sLj]          (S, L: offsets into shared memory)
+//   S : i contiguous, rows 16-byte aligned; a warp reads its slab of TI rows as 128-bit broadcasts
+//   L : lanes own j = j0 + 32 c, c < TJ (conflict-free when sLj = 1)
+// Work items (i-slab, j-group) are dealt to the 16 warps.  The inner loop carries no predicates: out-of-range lanes
+// re-read column J - 1 and slabs may read a few rows past I (operands are padded); their results are discarded.
+// SPLIT: the contraction is halved between warps w and w + 8, the upper half hands its partial sums over through
+// `part` (pitch ldp, normally the destination itself) -- this doubles the slab height a warp can afford, which is what
+// moves the loop from shared-memory-bandwidth-bound (TI = 4: 3 FFMA per wavefront) to FFMA-bound (TI = 8: 4.8).
+// Contains __syncthreads() when SPLIT: call from uniform control flow.
+template <int TI, int TJ, bool SPLIT>
+__device__ __noinline__ void outer_gemm(int S, int sSt, int L, int sLt, int sLj, int I, int J, int T, int part, int ldp,
+                                        const Epi e) {
   static_assert(TI % 4 == 0, "slab height must be a multiple of 4");
+  extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_is = (I + TI - 1) / TI, n_jg = (J + 32 * TJ - 1) / (32 * TJ);
-  for (int item = warp; item < n_is * n_jg; item += FW) {
-    const int is = item % n_is, jg = item / n_is;
+  const int n_items = n_is * n_jg;
+  const int stride = SPLIT ? FW / 2 : FW;
+  const int ts = SPLIT ? warp / (FW / 2) : 0;
+  const int Th = SPLIT ? (T + 1) / 2 : T;
+  const int t0 = ts * Th, t1 = min(T, t0 + Th);
+  const int n_rounds = (n_items + stride - 1) / stride;
+#pragma unroll 1
+  for (int round = 0; round < n_rounds; ++round) {
+    const int item = round * stride + (SPLIT ? (warp & (FW / 2 - 1)) : warp);
+    const bool valid = item < n_items;
+    const int is = valid ? item % n_is : 0, jg = valid ? item / n_is : 0;
     const int i0 = is * TI, j0 = jg * 32 * TJ + lane;
     float acc[TI][TJ];
 #pragma unroll
     for (int i = 0; i < TI; ++i)
 #pragma unroll
       for (int c = 0; c < TJ; ++c) acc[i][c] = 0.f;
-    const float* Lp[TJ];
-    float lconst[TJ];
-    bool lload[TJ];
+    if (valid) {
+      int lo[TJ];
 #pragma unroll
-    for (int c = 0; c < TJ; ++c) {
-      const int j = j0 + 32 * c;
-      lload[c] = j < J && j != ones_j;
-      lconst[c] = j == ones_j ? 1.f : 0.f;
-      Lp[c] = L + (lload[c] ? (size_t)j * sLj : 0);
-    }
-    const float* sp = S + i0;
-#pragma unroll 4
-    for (int t = 0; t < T; ++t) {
-      float l[TJ];
-#pragma unroll
-      for (int c = 0; c < TJ; ++c) {
-        float v = lconst[c];
-        if (lload[c]) v = LG ? __ldg(Lp[c] + (size_t)t * sLt) : Lp[c][t * sLt];
-        l[c] = v;
-      }
-#pragma unroll
-      for (int q = 0; q < TI / 4; ++q) {
-        const float4 s4 = *reinterpret_cast<const float4*>(sp + t * sSt + 4 * q);
+      for (int c = 0; c < TJ; ++c) lo[c] = L + min(j0 + 32 * c, J - 1) * sLj + t0 * sLt;
+      int so = S + i0 + t0 * sSt;
+#pragma unroll 2
+      for (int t = t0; t < t1; ++t) {
+        float l[TJ];
 #pragma unroll
         for (int c = 0; c < TJ; ++c) {
-          acc[4 * q + 0][c] = fmaf(s4.x, l[c], acc[4 * q + 0][c]);
-          acc[4 * q + 1][c] = fmaf(s4.y, l[c], acc[4 * q + 1][c]);
-          acc[4 * q + 2][c] = fmaf(s4.z, l[c], acc[4 * q + 2][c]);
-          acc[4 * q + 3][c] = fmaf(s4.w, l[c], acc[4 * q + 3][c]);
+          l[c] = sm[lo[c]];
+          lo[c] += sLt;
         }
+#pragma unroll
+        for (int q = 0; q < TI / 4; ++q) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sm + so + 4 * q);
+#pragma unroll
+          for (int c = 0; c < TJ; ++c) {
+            acc[4 * q + 0][c] = fmaf(s4.x, l[c], acc[4 * q + 0][c]);
+            acc[4 * q + 1][c] = fmaf(s4.y, l[c], acc[4 * q + 1][c]);
+            acc[4 * q + 2][c] = fmaf(s4.z, l[c], acc[4 * q + 2][c]);
+            acc[4 * q + 3][c] = fmaf(s4.w, l[c], acc[4 * q + 3][c]);
+          }
+        }
+        so += sSt;
       }
     }
+    if (SPLIT) {
+      if (valid && ts == 1) {
 #pragma unroll
-    for (int c = 0; c < TJ; ++c) {
-      const int j = j0 + 32 * c;
-      if (j < J) {
+        for (int c = 0; c < TJ; ++c) {
+          const int j = j0 + 32 * c;
+          if (j < J) {
 #pragma unroll
-        for (int i = 0; i < TI; ++i)
-          if (i0 + i < I) epi(i0 + i, j, acc[i][c]);
+            for (int i = 0; i < TI; ++i)
+              if (i0 + i < I) sm[part + (i0 + i) * ldp + j] = acc[i][c];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (valid && ts == 0) {
+#pragma unroll
+      for (int c = 0; c < TJ; ++c) {
+        const int j = j0 + 32 * c;
+        if (j < J) {
+#pragma unroll
+          for (int i = 0; i < TI; ++i)
+            if (i0 + i < I) epi_apply(e, sm, i0 + i, j, SPLIT ? acc[i][c] + sm[part + (i0 + i) * ldp + j] : acc[i][c]);
+        }
       }
     }
   }
 }
 
-// Thin outputs: out[r][n] = sum_k X[r * ldx + k] * W[k * sWk + n * sWn], n < N <= kMaxThin.
-// Warp w owns rows 4 w .. 4 w + 3, lanes stride over k, totals by warp shuffle; epi(r, n, value) runs on lane 0.
-template <class Epi>
-__device__ __forceinline__ void rowdot(const float* __restrict__ X, int ldx, const float* __restrict__ W, int sWk, int sWn,
-                                       int Kd, int N, Epi epi) {
+// Thin outputs: out[r][n] (+)= sum_k X[r * ldx + k] * W[k * sWk + n * sWn] (+ bias[n]),  n < N <= kMaxThin; X, W, out,
+// bias are shared-memory offsets.  Warp w owns rows 2 w, 2 w + 1, lanes stride over k, totals by warp shuffle.
+__device__ __noinline__ void rowdot(int X, int ldx, int W, int sWk, int sWn, int Kd, int N, int out, int ldo, int bias,
+                                    int accumulate) {
+  extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int RW = FR / FW;
-  float acc[RW][kMaxThin];
+  constexpr int NB = 4;  // outputs per pass: small code (this routine runs once per call site and tile)
+#pragma unroll 1
+  for (int n0 = 0; n0 < N; n0 += NB) {
+    float acc[RW][NB];
 #pragma unroll
-  for (int rr = 0; rr < RW; ++rr)
+    for (int rr = 0; rr < RW; ++rr)
 #pragma unroll
-    for (int n = 0; n < kMaxThin; ++n) acc[rr][n] = 0.f;
-  for (int k = lane; k < Kd; k += 32) {
-    float xv[RW];
+      for (int n = 0; n < NB; ++n) acc[rr][n] = 0.f;
+#pragma unroll 1
+    for (int k = lane; k < Kd; k += 32) {
+      float xv[RW];
 #pragma unroll
-    for (int rr = 0; rr < RW; ++rr) xv[rr] = X[(warp * RW + rr) * ldx + k];
+      for (int rr = 0; rr < RW; ++rr) xv[rr] = sm[X + (warp * RW + rr) * ldx + k];
+      const int wo = W + k * sWk + n0 * sWn;
 #pragma unroll
-    for (int n = 0; n < kMaxThin; ++n) {
-      if (n < N) {
-        const float w = __ldg(W + (size_t)k * sWk + (size_t)n * sWn);
+      for (int n = 0; n < NB; ++n) {
+        const float w = sm[wo + min(n, N - 1 - n0) * sWn];
 #pragma unroll
         for (int rr = 0; rr < RW; ++rr) acc[rr][n] = fmaf(xv[rr], w, acc[rr][n]);
       }
     }
-  }
 #pragma unroll
-  for (int n = 0; n < kMaxThin; ++n) {
-    if (n < N) {
+    for (int n = 0; n < NB; ++n) {
 #pragma unroll
       for (int rr = 0; rr < RW; ++rr) {
-        const float v = warp_sum(acc[rr][n]);
-        if (lane == 0) epi(warp * RW + rr, n, v);
+        float v = warp_sum(acc[rr][n]);
+        if (lane == 0 && n0 + n < N) {
+          const int o = out + (warp * RW + rr) * ldo + n0 + n;
+          if (bias >= 0) v += sm[bias + n0 + n];
+          sm[o] = accumulate ? sm[o] + v : v;
+        }
       }
     }
   }
 }
 
-__device__ __forceinline__ void acc_store(float* dst, float v, bool first) { *dst = first ? v : *dst + v; }
+// Stage one flow block's weights into shared memory with 4-byte cp.async (rows of 3K-1 floats are not 16-byte aligned):
+//   Wst  <- hW as [k][ldrm] (transposed = false, forward) or hW^T as [c][ldwt] (transposed = true, input gradient)
+//   Bb   <- d1W [cin][fh] | d1b [fh] | hb [ldr]
+// A warp takes rows k = warp, warp + 16, ..., lanes take columns: no integer division, coalesced global reads.
+__device__ __noinline__ void stage_block(const FusedParams& p, int blk, bool transposed) {
+  extern __shared__ __align__(16) float sm[];
+  const FBlk& fb = p.blk[blk];
+  float* Wst = sm + p.o_W;
+  float* Bb = sm + p.o_B + (blk & 1) * p.sb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* hW = p.theta + fb.off_hW;
+#pragma unroll 1
+  for (int k = warp; k < p.fh; k += FW) {
+    const float* src = hW + k * fb.ldr;
+    if (!transposed) {
+      float* dst = Wst + k * p.ldrm;
+      for (int n = lane; n < fb.ldr; n += 32) cp_async4(dst + n, src + n);
+    } else {
+      for (int n = lane; n < fb.ldr; n += 32) cp_async4(Wst + n * p.ldwt + k, src + n);
+    }
+  }
+  const int n_small = fb.cin * p.fh + p.fh;  // d1W | d1b are contiguous in theta
+  for (int e = threadIdx.x; e < n_small; e += FT) cp_async4(Bb + e, p.theta + fb.off_d1W + e);
+  for (int e = threadIdx.x; e < fb.ldr; e += FT) cp_async4(Bb + n_small + e, p.theta + fb.off_hb + e);
+}
+
+// Conditioner hidden layer hid = tanh(cond d1W + d1b) of block `blk`; an empty conditioner input is ones((B,1))
+// (flows.py:184-185).  row_major = false: hidT [fh][FR] (operand of the forward GEMM);  true: hidR [FR][ldf] and the
+// row-major conditioner input condR (operands of the weight gradients).
+__device__ __noinline__ void hidden_layer(const FusedParams& p, int blk, bool row_major) {
+  extern __shared__ __align__(16) float sm[];
+  const FBlk& fb = p.blk[blk];
+  const int fh = p.fh, dz = p.dz;
+  const float* uin = sm + p.o_u + (blk + 1) * FR * dz;
+  const float* Bb = sm + p.o_B + (blk & 1) * p.sb;
+  const float* d1b = Bb + fb.cin * fh;
+  float* hid = sm + p.o_hid;
+  if (!row_major) {
+    // e = j * FR + r: consecutive threads take consecutive rows
+    int j = threadIdx.x / FR;
+    const int r = threadIdx.x - j * FR;
+#pragma unroll 1
+    for (; j < fh; j += FT / FR) {
+      float a = d1b[j];
+      for (int c = 0; c < fb.cin; ++c) a = fmaf(fb.nc > 0 ? uin[r * dz + fb.cs0 + c] : 1.f, Bb[c * fh + j], a);
+      hid[j * FR + r] = tanhf(a);
+    }
+  } else {
+    // a warp takes rows r = warp, warp + 16, ...; lanes take consecutive j
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int r = warp; r < FR; r += FW) {
+      for (int j = lane; j < fh; j += 32) {
+        float a = d1b[j];
+        for (int c = 0; c < fb.cin; ++c) a = fmaf(fb.nc > 0 ? uin[r * dz + fb.cs0 + c] : 1.f, Bb[c * fh + j], a);
+        hid[r * p.ldf + j] = tanhf(a);
+      }
+      if (lane <= fb.cin)
+        sm[p.o_cond + r * p.ldc + lane] = (lane == fb.cin || fb.nc == 0) ? 1.f : uin[r * dz + fb.cs0 + lane];
+    }
+  }
+}
+
+// Spline of block `blk` in the density direction (inverse), one octet per row: u[blk] <- inverse(u[blk+1]), lpz += ildj.
+__device__ __noinline__ void spline_forward(const FusedParams& p, int blk) {
+  extern __shared__ __align__(16) float sm[];
+  const FBlk& fb = p.blk[blk];
+  const int dz = p.dz, K = p.K;
+  const float* uin = sm + p.o_u + (blk + 1) * FR * dz;
+  float* uout = sm + p.o_u + blk * FR * dz;
+  const int r = threadIdx.x >> 3, j = threadIdx.x & 7;
+  if (r >= FR) return;  // whole warps: 4 rows per warp, FR rows in all
+  const float* rr = sm + p.o_raw + (blk * FR + r) * p.ldrm;
+  float ldj_acc = 0.f;
+  for (int d = 0; d < fb.dt; ++d) {
+    const float v = uin[r * dz + fb.ts0 + d];
+    float out, ldj, ldj_all;
+    bool writer;
+    rqsdev::octet_apply<4, true, false>(rr + d * K, rr + fb.dt * K + d * K, rr + 2 * fb.dt * K + d * (K - 1), v, j, K,
+                                        true, p.bin_min, p.scale, out, ldj, ldj_all, writer);
+    if (writer) uout[r * dz + fb.ts0 + d] = out;
+    ldj_acc += ldj_all;
+  }
+  if (j == 0) sm[p.o_lp + FR + r] += ldj_acc;
+  for (int c = j; c < fb.nc; c += 8) uout[r * dz + fb.cs0 + c] = uin[r * dz + fb.cs0 + c];
+}
+
+// Reverse mode of spline_forward: gnxt[ts] <- g_in, gnxt[cs] <- gcur[cs], raw-logit gradients in both layouts
+// (grawR [FR][ldrm] for the weight gradient, grawT [ldrm][FR] for the input gradient).
+__device__ __noinline__ void spline_backward(const FusedParams& p, int blk, int gcur, int gnxt, int nr, float g_logpz) {
+  extern __shared__ __align__(16) float sm[];
+  const FBlk& fb = p.blk[blk];
+  const int dz = p.dz, K = p.K, ldrm = p.ldrm;
+  const float* uin = sm + p.o_u + (blk + 1) * FR * dz;
+  const int r = threadIdx.x >> 3, j = threadIdx.x & 7;
+  if (r >= FR) return;  // whole warps
+  const float* rr = sm + p.o_raw + (blk * FR + r) * ldrm;
+  float* gr = sm + p.o_scr + r * ldrm;
+  float* grawT = sm + p.o_scr + FR * ldrm;
+  const float g_ldj = r < nr ? g_logpz : 0.f;
+  for (int d = 0; d < fb.dt; ++d) {
+    const float v = uin[r * dz + fb.ts0 + d];
+    const float g_out = sm[gcur + r * dz + fb.ts0 + d];
+    float g_in, gw[4], gh[4], gs[4];
+    bool writer;
+    const int ow = d * K, oh = fb.dt * K + d * K, os = 2 * fb.dt * K + d * (K - 1);
+    rqsdev::octet_backward<4, true, false>(rr + ow, rr + oh, rr + os, v, g_out, g_ldj, j, K, true, p.bin_min, p.scale,
+                                           g_in, writer, gw, gh, gs);
+    if (writer) sm[gnxt + r * dz + fb.ts0 + d] = g_in;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = 4 * j + q;
+      if (k < K) {
+        gr[ow + k] = gw[q];
+        gr[oh + k] = gh[q];
+        grawT[(ow + k) * FR + r] = gw[q];
+        grawT[(oh + k) * FR + r] = gh[q];
+      }
+      if (k < K - 1) {
+        gr[os + k] = gs[q];
+        grawT[(os + k) * FR + r] = gs[q];
+      }
+    }
+  }
+  for (int c = j; c < fb.nc; c += 8) sm[gnxt + r * dz + fb.cs0 + c] = sm[gcur + r * dz + fb.cs0 + c];
+}
+
+__device__ __forceinline__ Epi epi_store(int out, int ld, int bias, int relu) {
+  Epi e = {};
+  e.kind = 0; e.out = out; e.ld = ld; e.bias = bias; e.relu = relu;
+  return e;
+}
+__device__ __forceinline__ Epi epi_mask(int kind, int out, int ld, int aux, int ld_aux) {
+  Epi e = {};
+  e.kind = kind; e.out = out; e.ld = ld; e.aux = aux; e.ld_aux = ld_aux;
+  return e;
+}
+__device__ __forceinline__ Epi epi_grad(float* g, int si, int sj, bool first) {
+  Epi e = {};
+  e.kind = 3; e.g = g; e.si = si; e.sj = sj; e.first = first ? 1 : 0;
+  return e;
+}
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <bool BWD>
 __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int dx = p.dx, dz = p.dz, H = p.hidden, nb = p.nb, K = p.K, fh = p.fh;
-  const float* __restrict__ th = p.theta;
-  float* xs = sm + p.o_xs;      // [FR][ldx]   x row-major, column dx = 1 (bias row of the enc.0 weight gradient)
-  float* xT = sm + p.o_xT;      // [dx][FR]
-  float* epsS = sm + p.o_eps;   // [FR][dz]
-  float* zR = sm + p.o_zR;      // [FR][ldz]   z row-major, column dz = 1
-  float* zT = sm + p.o_zT;      // [dz][FR]
-  float* he = sm + p.o_he;      // [FR][ldh]
-  float* hd = sm + p.o_hd;      // [FR][ldh]
-  float* pe = sm + p.o_pe;      // [FR][ldpe]  encoder head: loc | raw scale
-  float* pd = sm + p.o_pd;      // [FR][ldpd]  decoder head
-  float* u = sm + p.o_u;        // [nb+1][FR][dz] chain-inverse states, u[nb] = z, u[0] = base sample
-  float* lq = sm + p.o_lp;      // [3][FR] log q(z|x), log p(z), log p(x|z)
+  const int tid = threadIdx.x;
+  const int dx = p.dx, dz = p.dz, H = p.hidden, nb = p.nb, fh = p.fh;
+  const int ldh = p.ldh, ldrm = p.ldrm;
+  // shared-memory map (offsets in floats; see fused_create):
+  //   xs [FR][ldx] x row-major, column dx = 1   xT [dx][FR]   eps [FR][dz]   zR [FR][ldz] column dz = 1   zT [dz][FR]
+  //   he, hd [FR][ldh] column H = 1 (bias rows of the enc.1 / dec.1 weight gradients)   pe [FR][ldpe]   pd [FR][ldpd]
+  //   u [nb+1][FR][dz] chain-inverse states (u[nb] = z, u[0] = base sample)   lp [3][FR] = log q, log p(z), log p(x|z)
+  //   hid: forward hidT [fh][FR]; backward (same storage) hidR [FR][ldf], column fh = 1      cond [FR][ldc]
+  //   raw [nb][FR][ldrm] raw spline parameters (kept for the backward pass)
+  //   W: staged heads weight [fh][ldrm] (forward) or its transpose [ldr][ldwt] (backward)
+  //   Wp: encoder + decoder weights, resident for the CTA's lifetime     B [2][sb]: d1W | d1b | hb by block parity
+  //   gz, gua, gub [FR][dz]      scr: backward scratch, re-carved per phase
+  float* xs = sm + p.o_xs;
+  float* epsS = sm + p.o_eps;
+  float* zR = sm + p.o_zR;
+  float* pe = sm + p.o_pe;
+  float* pd = sm + p.o_pd;
+  float* u = sm + p.o_u;
+  float* lq = sm + p.o_lp;
   float* lpz = lq + FR;
-  float* lpx = lq + 2 * FR;
-  float* hidT = sm + p.o_hidT;  // [fh][FR]
-  float* hidR = sm + p.o_hidR;  // [FR][ldf]   column fh = 1
-  float* condR = sm + p.o_cond; // [FR][ldc]   conditioner input row-major, column cin = 1
-  float* raw = sm + p.o_raw;    // [nb][FR][ldrm] raw spline parameters of every block (kept for the backward pass)
-  float* Wst = sm + p.o_W;      // staged heads weight: [fh][ldrm] (forward) or transposed [ldr][ldwt] (backward)
-  float* gz = sm + p.o_gz;      // [FR][dz]
-  float* gua = sm + p.o_gua;    // [FR][dz]
-  float* gub = sm + p.o_gub;    // [FR][dz]
-  float* scr = sm + p.o_scr;    // backward scratch, re-carved per phase
+  float* gz = sm + p.o_gz;
   float* gp = p.gpart + (size_t)blockIdx.x * p.P;
 
-  // constant columns / padding, written once
-  for (int i = tid; i < FR * p.ldf; i += FT) hidR[i] = (i % p.ldf) == fh ? 1.f : 0.f;
+  // CTA-lifetime state: resident MLP weights, constant columns
+  for (int i = tid; i < p.n_mlp; i += FT) cp_async4(sm + p.o_Wp + i, p.theta + i);
+  if (nb > 0) stage_block(p, nb - 1, false);
   for (int i = tid; i < FR * p.ldz; i += FT) zR[i] = (i % p.ldz) == dz ? 1.f : 0.f;
-  for (int i = tid; i < FR * p.ldc; i += FT) condR[i] = 0.f;
+  for (int i = tid; i < FR * p.ldc; i += FT) sm[p.o_cond + i] = 0.f;
+  for (int i = tid; i < FR; i += FT) {
+    sm[p.o_he + i * ldh + H] = 1.f;
+    sm[p.o_hd + i * ldh + H] = 1.f;
+  }
   float cta_kl = 0.f, cta_nll = 0.f;
   const float invB = 1.0f / (float)p.B;
   bool first = true;
-  __syncthreads();
 
+#pragma unroll 1
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int64_t row0 = (int64_t)tile * FR;
     const int nr = (int)min((int64_t)FR, p.B - row0);
+    const bool more = tile + (int)gridDim.x < p.n_tiles;
     // ---------------------------------------------------------------- F0: stage the tile's inputs
     for (int i = tid; i < FR * p.ldx; i += FT) {
       const int r = i / p.ldx, c = i - r * p.ldx;
       float v = c == dx ? 1.f : 0.f;
       if (c < dx && r < nr) v = __ldg(p.x + (row0 + r) * dx + c);
       xs[i] = v;
-    }
-    for (int i = tid; i < dx * FR; i += FT) {
-      const int k = i / FR, r = i - k * FR;
-      xT[i] = r < nr ? __ldg(p.x + (row0 + r) * dx + k) : 0.f;
+      if (c < dx) sm[p.o_xT + c * FR + r] = v;
     }
     for (int i = tid; i < FR * dz; i += FT) epsS[i] = i < nr * dz ? __ldg(p.eps + row0 * dz + i) : 0.f;
+    cp_async_commit_wait_all();
     __syncthreads();
     // ---------------------------------------------------------------- F1: he = relu(x W + b)   (mappings.py:151-153)
-    outer_gemm<8, 1, true>(xT, FR, th + p.enc0W, H, 1, -1, FR, H, dx, [&](int r, int n, float v) {
-      he[r * p.ldh + n] = fmaxf(v + __ldg(th + p.enc0b + n), 0.f);
-    });
+    outer_gemm<8, 2, false>(p.o_xT, FR, p.o_Wp + p.enc0W, H, 1, FR, H, dx, 0, 0,
+                             epi_store(p.o_he, ldh, p.o_Wp + p.enc0b, 1));
     __syncthreads();
     // ---------------------------------------------------------------- F2: encoder head parameters
-    rowdot(he, p.ldh, th + p.enc1W, 2 * dz, 1, H, 2 * dz,
-           [&](int r, int n, float v) { pe[r * p.ldpe + n] = v + __ldg(th + p.enc1b + n); });
+    rowdot(p.o_he, ldh, p.o_Wp + p.enc1W, 2 * dz, 1, H, 2 * dz, p.o_pe, p.ldpe, p.o_Wp + p.enc1b, 0);
     __syncthreads();
     // ---------------------------------------------------------------- F3: z = eps * softplus(raw) + loc, log q(z|x)
     if (tid < FR) {
@@ -241,54 +450,30 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
         s += normal_lp(zz, loc, sc);
         u[(nb * FR + r) * dz + d] = zz;
         zR[r * p.ldz + d] = zz;
-        zT[d * FR + r] = zz;
+        sm[p.o_zT + d * FR + r] = zz;
       }
       lq[r] = s;
       lpz[r] = 0.f;
     }
     __syncthreads();
     // ---------------------------------------------------------------- F4: prior log p(z), chain inverse (flows.py:323)
+#pragma unroll 1
     for (int i = nb - 1; i >= 0; --i) {
-      const FBlk& fb = p.blk[i];
-      const float* uin = u + (i + 1) * FR * dz;
-      float* uout = u + i * FR * dz;
-      float* raw_i = raw + (size_t)i * FR * p.ldrm;
-      // conditioner hidden layer hid = tanh(cond d1W + d1b); an empty conditioner input is ones((B,1)) (flows.py:184-185)
-      for (int e = tid; e < fh * FR; e += FT) {
-        const int j = e / FR, r = e - j * FR;
-        float a = __ldg(th + fb.off_d1b + j);
-        for (int c = 0; c < fb.cin; ++c) {
-          const float cv = fb.nc > 0 ? uin[r * dz + fb.cs0 + c] : 1.f;
-          a = fmaf(cv, __ldg(th + fb.off_d1W + c * fh + j), a);
-        }
-        hidT[e] = tanhf(a);
-      }
-      for (int e = tid; e < fh * fb.ldr; e += FT) {
-        const int k = e / fb.ldr, n = e - k * fb.ldr;
-        Wst[k * p.ldrm + n] = __ldg(th + fb.off_hW + e);
-      }
+      const int hb = p.o_B + (i & 1) * p.sb + p.blk[i].cin * fh + fh;
+      const int raw_i = p.o_raw + i * FR * ldrm;
+      hidden_layer(p, i, false);
       __syncthreads();
       // raw = hid hW + hb: the three Dense heads of flows.py:140-152 as one GEMM
-      outer_gemm<4, 3, false>(hidT, FR, Wst, p.ldrm, 1, -1, FR, fb.ldr, fh, [&](int r, int n, float v) {
-        raw_i[r * p.ldrm + n] = v + __ldg(th + fb.off_hb + n);
-      });
+      outer_gemm<4, 3, true>(p.o_hid, FR, p.o_W, ldrm, 1, FR, p.blk[i].ldr, fh, raw_i, ldrm, epi_store(raw_i, ldrm, hb, 0));
       __syncthreads();
-      {
-        const int r = tid >> 3, j = tid & 7;
-        const float* rr = raw_i + r * p.ldrm;
-        float ldj_acc = 0.f;
-        for (int d = 0; d < fb.dt; ++d) {
-          const float v = uin[r * dz + fb.ts0 + d];
-          float out, ldj, ldj_all;
-          bool writer;
-          rqsdev::octet_apply<4, true, false>(rr + d * K, rr + fb.dt * K + d * K, rr + 2 * fb.dt * K + d * (K - 1), v, j,
-                                              K, true, p.bin_min, p.scale, out, ldj, ldj_all, writer);
-          if (writer) uout[r * dz + fb.ts0 + d] = out;
-          ldj_acc += ldj_all;
-        }
-        if (j == 0) lpz[r] += ldj_acc;
-        for (int c = j; c < fb.nc; c += 8) uout[r * dz + fb.cs0 + c] = uin[r * dz + fb.cs0 + c];
-      }
+      // the staging buffer is free: fetch the next block's weights (or block 0's transposed, for the backward pass)
+      // while the spline runs
+      if (i > 0)
+        stage_block(p, i - 1, false);
+      else if (BWD)
+        stage_block(p, 0, true);
+      spline_forward(p, i);
+      cp_async_commit_wait_all();
       __syncthreads();
     }
     if (tid < FR) {
@@ -297,19 +482,16 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
       lpz[tid] = s;
     }
     // ---------------------------------------------------------------- F6-F8: decoder and log p(x|z)
-    outer_gemm<8, 1, true>(zT, FR, th + p.dec0W, H, 1, -1, FR, H, dz, [&](int r, int n, float v) {
-      hd[r * p.ldh + n] = fmaxf(v + __ldg(th + p.dec0b + n), 0.f);
-    });
+    outer_gemm<8, 2, false>(p.o_zT, FR, p.o_Wp + p.dec0W, H, 1, FR, H, dz, 0, 0,
+                             epi_store(p.o_hd, ldh, p.o_Wp + p.dec0b, 1));
     __syncthreads();
-    rowdot(hd, p.ldh, th + p.dec1W, 2 * dx, 1, H, 2 * dx,
-           [&](int r, int n, float v) { pd[r * p.ldpd + n] = v + __ldg(th + p.dec1b + n); });
+    rowdot(p.o_hd, ldh, p.o_Wp + p.dec1W, 2 * dx, 1, H, 2 * dx, p.o_pd, p.ldpd, p.o_Wp + p.dec1b, 0);
     __syncthreads();
     if (tid < FR) {
       const int r = tid;
       float s = 0.f;
       for (int d = 0; d < dx; ++d)
         s += normal_lp(xs[r * p.ldx + d], pd[r * p.ldpd + d], softplus_tf(pd[r * p.ldpd + dx + d]));
-      lpx[r] = s;
       // tile sums in row order on warp 0 (deterministic), optional per-row outputs
       const bool ok = r < nr;
       const float a = warp_sum(ok ? lq[r] - lpz[r] : 0.f), c = warp_sum(ok ? -s : 0.f);
@@ -324,6 +506,7 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
       }
     }
     if (!BWD) {
+      if (nb > 0 && more) stage_block(p, nb - 1, false);
       __syncthreads();
       continue;
     }
@@ -331,9 +514,9 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
     const float g_logpx = -invB, g_logq = p.klw * invB, g_logpz = -p.klw * invB;
     {
       // B1: decoder head, d/d params of g * sum_d log N(x_d; loc_d, softplus(raw_d))
-      float* gpd = scr;                    // [FR][ldpd]
-      float* gpdT = gpd + FR * p.ldpd;     // [2 dx][FR]
-      float* ghd = gpdT + 2 * dx * FR;     // [FR][ldh]
+      const int gpd = p.o_scr;                  // [FR][ldpd]
+      const int gpdT = gpd + FR * p.ldpd;       // [2 dx][FR]
+      const int ghd = gpdT + 2 * dx * FR;       // [FR][ldh]
       for (int e = tid; e < FR * dx; e += FT) {
         const int r = e / dx, d = e - r * dx;
         const float g = r < nr ? g_logpx : 0.f;
@@ -341,125 +524,69 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
         const float sc = softplus_tf(rawp);
         const float uu = xs[r * p.ldx + d] / sc - loc / sc;
         const float g1 = g * (uu / sc), g2 = g * ((uu * uu - 1.f) / sc) * sigmoidf_(rawp);
-        gpd[r * p.ldpd + d] = g1;
-        gpd[r * p.ldpd + dx + d] = g2;
-        gpdT[d * FR + r] = g1;
-        gpdT[(dx + d) * FR + r] = g2;
+        sm[gpd + r * p.ldpd + d] = g1;
+        sm[gpd + r * p.ldpd + dx + d] = g2;
+        sm[gpdT + d * FR + r] = g1;
+        sm[gpdT + (dx + d) * FR + r] = g2;
       }
       __syncthreads();
-      // B2: [W; b] gradient of dec.1:  g[k][n] = sum_r hd[r][k] gpd[r][n]   (row k = H is the bias)
-      outer_gemm<4, 1, false>(gpd, p.ldpd, hd, p.ldh, 1, H, 2 * dx, H + 1, FR, [&](int n, int k, float v) {
-        acc_store(gp + p.dec1W + k * 2 * dx + n, v, first);
-      });
+      // B2: [W; b] gradient of dec.1:  g[k][n] = sum_r hd[r][k] gpd[r][n]   (row k = H is the bias: hd[r][H] = 1)
+      outer_gemm<8, 1, false>(gpd, p.ldpd, p.o_hd, ldh, 1, 2 * dx, H + 1, FR, 0, 0, epi_grad(gp + p.dec1W, 1, 2 * dx, first));
       // B3: g_hd = (gpd W^T) * relu'
-      outer_gemm<8, 1, true>(gpdT, FR, th + p.dec1W, 1, 2 * dx, -1, FR, H, 2 * dx, [&](int r, int k, float v) {
-        ghd[r * p.ldh + k] = hd[r * p.ldh + k] > 0.f ? v : 0.f;
-      });
+      outer_gemm<8, 2, false>(gpdT, FR, p.o_Wp + p.dec1W, 1, 2 * dx, FR, H, 2 * dx, 0, 0,
+                               epi_mask(1, ghd, ldh, p.o_hd, ldh));
       __syncthreads();
       // B4: [W; b] gradient of dec.0;  B5: g_z = ghd W^T
-      outer_gemm<4, 1, false>(zR, p.ldz, ghd, p.ldh, 1, -1, dz + 1, H, FR, [&](int k, int n, float v) {
-        acc_store(gp + p.dec0W + k * H + n, v, first);
-      });
-      rowdot(ghd, p.ldh, th + p.dec0W, 1, H, H, dz, [&](int r, int k, float v) { gz[r * dz + k] = v; });
+      outer_gemm<4, 1, false>(p.o_zR, p.ldz, ghd, ldh, 1, dz + 1, H, FR, 0, 0, epi_grad(gp + p.dec0W, H, 1, first));
+      rowdot(ghd, ldh, p.o_Wp + p.dec0W, 1, H, H, dz, p.o_gz, dz, -1, 0);
       __syncthreads();
     }
     // ---------------------------------------------------------------- B6: prior
-    float* gcur = gua;
-    float* gnxt = gub;
+    int gcur = p.o_gua, gnxt = p.o_gub;
     if (nb == 0) {
       for (int e = tid; e < FR * dz; e += FT) gz[e] += -((e / dz) < nr ? g_logpz : 0.f) * u[e];
       __syncthreads();
     } else {
-      for (int e = tid; e < FR * dz; e += FT) gcur[e] = -((e / dz) < nr ? g_logpz : 0.f) * u[e];
+      for (int e = tid; e < FR * dz; e += FT) sm[gcur + e] = -((e / dz) < nr ? g_logpz : 0.f) * u[e];
+      const int grawR = p.o_scr;               // [FR][ldrm]
+      const int grawT = grawR + FR * ldrm;     // [ldrm][FR]
+      const int gpre = grawT + ldrm * FR;      // [FR][ldfp]
+      for (int e = tid; e < FR; e += FT) sm[p.o_hid + e * p.ldf + fh] = 1.f;  // bias row of the heads weight gradient
       __syncthreads();
-      float* grawR = scr;                      // [FR][ldrm]
-      float* grawT = grawR + FR * p.ldrm;      // [ldrm][FR]
-      float* gpre = grawT + p.ldrm * FR;       // [FR][ldfp]
+#pragma unroll 1
       for (int i = 0; i < nb; ++i) {
         const FBlk& fb = p.blk[i];
-        const float* uin = u + (i + 1) * FR * dz;
-        const float* raw_i = raw + (size_t)i * FR * p.ldrm;
-        // recompute the conditioner hidden layer (both layouts), stage hW transposed
-        for (int e = tid; e < fh * FR; e += FT) {
-          const int j = e / FR, r = e - j * FR;
-          float a = __ldg(th + fb.off_d1b + j);
-          for (int c = 0; c < fb.cin; ++c) {
-            const float cv = fb.nc > 0 ? uin[r * dz + fb.cs0 + c] : 1.f;
-            a = fmaf(cv, __ldg(th + fb.off_d1W + c * fh + j), a);
-          }
-          const float h = tanhf(a);
-          hidT[e] = h;
-          hidR[r * p.ldf + j] = h;
-        }
-        for (int e = tid; e < FR * (fb.cin + 1); e += FT) {
-          const int r = e / (fb.cin + 1), c = e - r * (fb.cin + 1);
-          condR[r * p.ldc + c] = (c == fb.cin || fb.nc == 0) ? 1.f : uin[r * dz + fb.cs0 + c];
-        }
-        for (int e = tid; e < fh * fb.ldr; e += FT) {
-          const int j = e / fb.ldr, c = e - j * fb.ldr;
-          Wst[c * p.ldwt + j] = __ldg(th + fb.off_hW + e);
-        }
-        {
-          // spline reverse mode: g_in -> gnxt[ts], raw-logit gradients in both layouts
-          const int r = tid >> 3, j = tid & 7;
-          const float* rr = raw_i + r * p.ldrm;
-          const float g_ldj = r < nr ? g_logpz : 0.f;
-          for (int d = 0; d < fb.dt; ++d) {
-            const float v = uin[r * dz + fb.ts0 + d];
-            const float g_out = gcur[r * dz + fb.ts0 + d];
-            float g_in, gw[4], gh[4], gs[4];
-            bool writer;
-            const int ow = d * K, oh = fb.dt * K + d * K, os = 2 * fb.dt * K + d * (K - 1);
-            rqsdev::octet_backward<4, true, false>(rr + ow, rr + oh, rr + os, v, g_out, g_ldj, j, K, true, p.bin_min,
-                                                   p.scale, g_in, writer, gw, gh, gs);
-            if (writer) gnxt[r * dz + fb.ts0 + d] = g_in;
-            float* gr = grawR + r * p.ldrm;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int k = 4 * j + q;
-              if (k < K) {
-                gr[ow + k] = gw[q];
-                gr[oh + k] = gh[q];
-                grawT[(ow + k) * FR + r] = gw[q];
-                grawT[(oh + k) * FR + r] = gh[q];
-              }
-              if (k < K - 1) {
-                gr[os + k] = gs[q];
-                grawT[(os + k) * FR + r] = gs[q];
-              }
-            }
-          }
-          for (int c = j; c < fb.nc; c += 8) gnxt[r * dz + fb.cs0 + c] = gcur[r * dz + fb.cs0 + c];
-        }
+        hidden_layer(p, i, true);
+        spline_backward(p, i, gcur, gnxt, nr, g_logpz);
         __syncthreads();
         // [hW; hb] gradient: g[k][n] = sum_r hid[r][k] graw[r][n]   (row k = fh is the bias)
-        outer_gemm<16, 3, false>(hidR, p.ldf, grawR, p.ldrm, 1, -1, fh + 1, fb.ldr, FR, [&](int k, int n, float v) {
-          acc_store(gp + fb.off_hW + k * fb.ldr + n, v, first);
-        });
+        outer_gemm<8, 3, false>(p.o_hid, p.ldf, grawR, ldrm, 1, fh + 1, fb.ldr, FR, 0, 0,
+                                 epi_grad(gp + fb.off_hW, fb.ldr, 1, first));
         // g_pre = (graw hW^T) * tanh'
-        outer_gemm<4, 4, false>(grawT, FR, Wst, p.ldwt, 1, -1, FR, fh, fb.ldr, [&](int r, int j, float v) {
-          const float h = hidR[r * p.ldf + j];
-          gpre[r * p.ldfp + j] = v * (1.f - h * h);
-        });
+        outer_gemm<4, 4, true>(grawT, FR, p.o_W, p.ldwt, 1, FR, fh, fb.ldr, gpre, p.ldfp,
+                               epi_mask(2, gpre, p.ldfp, p.o_hid, p.ldf));
         __syncthreads();
+        // the staging buffer is free again: next block's transposed weights, or the next tile's first forward block
+        if (i + 1 < nb)
+          stage_block(p, i + 1, true);
+        else if (more)
+          stage_block(p, nb - 1, false);
         // [d1W; d1b] gradient and the conditioner-input gradient
-        outer_gemm<4, 1, false>(condR, p.ldc, gpre, p.ldfp, 1, -1, fb.cin + 1, fh, FR, [&](int c, int j, float v) {
-          acc_store(gp + fb.off_d1W + c * fh + j, v, first);
-        });
-        if (fb.nc > 0)
-          rowdot(gpre, p.ldfp, th + fb.off_d1W, 1, fh, fh, fb.nc,
-                 [&](int r, int c, float v) { gnxt[r * dz + fb.cs0 + c] += v; });
+        outer_gemm<4, 1, false>(p.o_cond, p.ldc, gpre, p.ldfp, 1, fb.cin + 1, fh, FR, 0, 0,
+                                epi_grad(gp + fb.off_d1W, fh, 1, first));
+        if (fb.nc > 0) rowdot(gpre, p.ldfp, p.o_B + (i & 1) * p.sb, 1, fh, fh, fb.nc, gnxt + fb.cs0, dz, -1, 1);
+        cp_async_commit_wait_all();
         __syncthreads();
-        float* t = gcur;
+        const int t = gcur;
         gcur = gnxt;
         gnxt = t;
       }
     }
     {
       // B8: encoder head (explicit z path + parameter path + reparameterisation z = eps s + loc)
-      float* gpe = scr;                    // [FR][ldpe]
-      float* gpeT = gpe + FR * p.ldpe;     // [2 dz][FR]
-      float* ghe = gpeT + 2 * dz * FR;     // [FR][ldh]
+      const int gpe = p.o_scr;                  // [FR][ldpe]
+      const int gpeT = gpe + FR * p.ldpe;       // [2 dz][FR]
+      const int ghe = gpeT + 2 * dz * FR;       // [FR][ldh]
       for (int e = tid; e < FR * dz; e += FT) {
         const int r = e / dz, d = e - r * dz;
         const float gq = r < nr ? g_logq : 0.f;
@@ -467,55 +594,62 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
         const float sc = softplus_tf(rawp);
         const float zz = zR[r * p.ldz + d];
         const float uu = zz / sc - loc / sc;
-        const float gzz = gz[e] + (nb > 0 ? gcur[e] : 0.f) + gq * (-uu / sc);
+        const float gzz = gz[e] + (nb > 0 ? sm[gcur + e] : 0.f) + gq * (-uu / sc);
         const float g1 = gq * (uu / sc) + gzz;
         const float g2 = (gq * ((uu * uu - 1.f) / sc) + gzz * epsS[e]) * sigmoidf_(rawp);
-        gpe[r * p.ldpe + d] = g1;
-        gpe[r * p.ldpe + dz + d] = g2;
-        gpeT[d * FR + r] = g1;
-        gpeT[(dz + d) * FR + r] = g2;
+        sm[gpe + r * p.ldpe + d] = g1;
+        sm[gpe + r * p.ldpe + dz + d] = g2;
+        sm[gpeT + d * FR + r] = g1;
+        sm[gpeT + (dz + d) * FR + r] = g2;
       }
       __syncthreads();
-      outer_gemm<4, 1, false>(gpe, p.ldpe, he, p.ldh, 1, H, 2 * dz, H + 1, FR, [&](int n, int k, float v) {
-        acc_store(gp + p.enc1W + k * 2 * dz + n, v, first);
-      });
-      outer_gemm<8, 1, true>(gpeT, FR, th + p.enc1W, 1, 2 * dz, -1, FR, H, 2 * dz, [&](int r, int k, float v) {
-        ghe[r * p.ldh + k] = he[r * p.ldh + k] > 0.f ? v : 0.f;
-      });
+      outer_gemm<4, 1, false>(gpe, p.ldpe, p.o_he, ldh, 1, 2 * dz, H + 1, FR, 0, 0, epi_grad(gp + p.enc1W, 1, 2 * dz, first));
+      outer_gemm<8, 2, false>(gpeT, FR, p.o_Wp + p.enc1W, 1, 2 * dz, FR, H, 2 * dz, 0, 0,
+                               epi_mask(1, ghe, ldh, p.o_he, ldh));
       __syncthreads();
-      outer_gemm<4, 1, false>(xs, p.ldx, ghe, p.ldh, 1, -1, dx + 1, H, FR, [&](int k, int n, float v) {
-        acc_store(gp + p.enc0W + k * H + n, v, first);
-      });
+      outer_gemm<8, 1, false>(p.o_xs, p.ldx, ghe, ldh, 1, dx + 1, H, FR, 0, 0, epi_grad(gp + p.enc0W, H, 1, first));
       __syncthreads();
     }
     first = false;
   }
+  cp_async_commit_wait_all();
   if (tid == 0) {
     p.spart[2 * blockIdx.x] = cta_kl;
     p.spart[2 * blockIdx.x + 1] = cta_nll;
   }
 }
 
-// grad[i] = sum_c gpart[c][i] in fixed order (8 partial groups per block, combined in order), and the loss scalars.
-__global__ void __launch_bounds__(256) fused_finish_kernel(const float* __restrict__ gpart, int n_part, int P,
-                                                           float* __restrict__ grad, const float* __restrict__ spart,
-                                                           int64_t B, float klw, float* __restrict__ scalars) {
-  __shared__ float sh[8][32];
+// grad[i] = sum_c gpart[c][i] in a fixed order (16 partial groups per block, four independent running sums each,
+// combined in a fixed order: deterministic for a given grid), and the three loss scalars.
+constexpr int kFinGroups = 16;
+__global__ void __launch_bounds__(32 * kFinGroups) fused_finish_kernel(const float* __restrict__ gpart, int n_part, int P,
+                                                                       float* __restrict__ grad,
+                                                                       const float* __restrict__ spart, int64_t B,
+                                                                       float klw, float* __restrict__ scalars) {
+  __shared__ float sh[kFinGroups][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   if (grad) {
     const int i = blockIdx.x * 32 + lane;
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (i < P) {
-      const int per = (n_part + 7) / 8;
+      const int per = (n_part + kFinGroups - 1) / kFinGroups;
       const int c0 = grp * per, c1 = min(n_part, c0 + per);
-      for (int c = c0; c < c1; ++c) s += gpart[(size_t)c * P + i];
+      const float* g = gpart + i;
+      int c = c0;
+      for (; c + 4 <= c1; c += 4) {
+        s0 += g[(size_t)c * P];
+        s1 += g[(size_t)(c + 1) * P];
+        s2 += g[(size_t)(c + 2) * P];
+        s3 += g[(size_t)(c + 3) * P];
+      }
+      for (; c < c1; ++c) s0 += g[(size_t)c * P];
     }
-    sh[grp][lane] = s;
+    sh[grp][lane] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (grp == 0 && i < P) {
       float t = 0.f;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) t += sh[g][lane];
+      for (int g = 0; g < kFinGroups; ++g) t += sh[g][lane];
       grad[i] = t;
     }
   }
@@ -562,9 +696,11 @@ vms_status fused_create(vms_elbo_plan_s* pl) {
     max_cin = b.cin > max_cin ? b.cin : max_cin;
   }
   if (max_cin > kMaxThin) { delete f; return VMS_OK; }
-  p.ldx = r4(d.dx + 1); p.ldz = r4(d.dz + 1); p.ldh = r4(d.hidden); p.ldf = r4(p.fh + 1); p.ldfp = r4(p.fh);
+  p.ldx = r4(d.dx + 1); p.ldz = r4(d.dz + 1); p.ldh = d.hidden + 1; p.ldf = r4(p.fh + 1); p.ldfp = r4(p.fh);
   p.ldpe = r4(2 * d.dz); p.ldpd = r4(2 * d.dx); p.ldc = r4(max_cin + 1); p.ldrm = r4(max_ldr);
   p.ldwt = p.fh | 1;
+  p.sb = r4(max_cin * p.fh + p.fh + p.ldrm);
+  p.n_mlp = (int)o.dec1b + 2 * d.dx;
   int off = 0;
   auto take = [&](int n) { int o0 = off; off += r4(n); return o0; };
   p.o_xs = take(FR * p.ldx); p.o_xT = take(d.dx * FR); p.o_eps = take(FR * d.dz);
@@ -572,10 +708,11 @@ vms_status fused_create(vms_elbo_plan_s* pl) {
   p.o_he = take(FR * p.ldh); p.o_hd = take(FR * p.ldh);
   p.o_pe = take(FR * p.ldpe); p.o_pd = take(FR * p.ldpd);
   p.o_u = take((d.num_blocks + 1) * FR * d.dz); p.o_lp = take(3 * FR);
-  p.o_hidT = take(p.fh * FR); p.o_hidR = take(FR * p.ldf); p.o_cond = take(FR * p.ldc);
+  p.o_hid = take(p.fh * FR > FR * p.ldf ? p.fh * FR : FR * p.ldf); p.o_cond = take(FR * p.ldc);
   p.o_raw = take(d.num_blocks * FR * p.ldrm);
   const int w_fwd = p.fh * p.ldrm, w_bwd = max_ldr * p.ldwt;
   p.o_W = take(d.num_blocks ? (w_fwd > w_bwd ? w_fwd : w_bwd) : 4);
+  p.o_Wp = take(p.n_mlp); p.o_B = take(2 * p.sb);
   p.o_gz = take(FR * d.dz); p.o_gua = take(FR * d.dz); p.o_gub = take(FR * d.dz);
   const int scr_dec = FR * p.ldpd + 2 * d.dx * FR + FR * p.ldh;
   const int scr_enc = FR * p.ldpe + 2 * d.dz * FR + FR * p.ldh;
@@ -636,7 +773,7 @@ vms_status fused_run(vms_elbo_plan_s* pl, const float* theta, const float* x, co
   VMS_LAUNCH_CHECK("elbo_fused_kernel");
   float* sc = scalars ? scalars : pl->scalars;
   const int nblk = backward ? (p.P + 31) / 32 : 1;
-  fused_finish_kernel<<<nblk, 256, 0, st>>>(f->gpart, grid, p.P, backward ? grad : nullptr, f->spart, B, p.klw, sc);
+  fused_finish_kernel<<<nblk, 32 * kFinGroups, 0, st>>>(f->gpart, grid, p.P, backward ? grad : nullptr, f->spart, B, p.klw, sc);
   VMS_LAUNCH_CHECK("fused_finish_kernel");
   return VMS_OK;
 }
