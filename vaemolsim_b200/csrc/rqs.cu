@@ -179,6 +179,10 @@ RqsParams from_args(const vms_rqs_args& a) {
 
 namespace vms {
 vms_status rqs_prepare() { return VMS_OK; }  // no opt-in shared memory any more; kept for elbo.cu
+// rqs_stream.cu: thread-per-element streaming kernels for the contiguous, aligned form with K in {20, 32}
+bool rqs_stream_try(const float* v, const float* rw, const float* rh, const float* rs, int64_t n, int K, float bin_min,
+                    float bin_max, int inverse_dir, float* out, float* ldj, const float* g_out, const float* g_ldj,
+                    float* g_in, float* g_w, float* g_h, float* g_s, bool backward, cudaStream_t st, vms_status* status);
 }  // namespace vms
 
 extern "C" {
@@ -209,6 +213,14 @@ static vms_status contiguous(const float* v, const float* rw, const float* rh, c
                              float lo, float hi, float* out, float* ldj, int inverse_dir, vms_stream stream) {
   VMS_REQUIRE(n >= 0, VMS_ERR_INVALID_ARG, "n_elem < 0");
   VMS_REQUIRE(n == 0 || (v && rw && rh && rs && out), VMS_ERR_INVALID_ARG, "vms_rqs: NULL tensor pointer");
+  VMS_REQUIRE(K >= 2 && K <= 64, VMS_ERR_INVALID_ARG, "num_bins must be in [2, 64], got %d", K);
+  VMS_REQUIRE(hi > lo, VMS_ERR_INVALID_ARG, "bin_range must be increasing");
+  {
+    vms_status s = VMS_OK;
+    if (vms::rqs_stream_try(v, rw, rh, rs, n, K, lo, hi, inverse_dir, out, ldj, nullptr, nullptr, nullptr, nullptr, nullptr,
+                            nullptr, false, vms::as_stream(stream), &s))
+      return s;
+  }
   vms_rqs_args a = {};
   a.n_rows = n; a.n_dims = 1; a.num_bins = K; a.bin_min = lo; a.bin_max = hi;
   a.v_in = v; a.ld_in = 1;
@@ -233,6 +245,14 @@ vms_status vms_rqs_backward(const float* v_in, const float* rw, const float* rh,
   VMS_REQUIRE(n >= 0, VMS_ERR_INVALID_ARG, "n_elem < 0");
   VMS_REQUIRE(n == 0 || (v_in && rw && rh && rs && g_out && g_in && g_rw && g_rh && g_rs), VMS_ERR_INVALID_ARG,
               "vms_rqs_backward: NULL tensor pointer");
+  VMS_REQUIRE(K >= 2 && K <= 64, VMS_ERR_INVALID_ARG, "num_bins must be in [2, 64], got %d", K);
+  VMS_REQUIRE(hi > lo, VMS_ERR_INVALID_ARG, "bin_range must be increasing");
+  {
+    vms_status s = VMS_OK;
+    if (vms::rqs_stream_try(v_in, rw, rh, rs, n, K, lo, hi, inverse_dir, nullptr, nullptr, g_out, g_ldj, g_in, g_rw, g_rh,
+                            g_rs, true, vms::as_stream(stream), &s))
+      return s;
+  }
   RqsParams p = {};
   p.n_rows = n; p.n_dims = 1; p.K = K; p.bin_min = lo; p.bin_max = hi;
   p.v_in = v_in; p.ld_in = 1;
