@@ -279,6 +279,32 @@ vms_status vms_elbo_forward(vms_elbo_plan plan, const float* theta, const float*
 vms_status vms_elbo_forward_backward(vms_elbo_plan plan, const float* theta, const float* x, const float* eps,
                                      int64_t B, float* grad, float* scalars, vms_stream stream);
 
+/* ------------------------------------------------------------------------------- fused MC run (C4a)
+ * n_steps complete VAE-proposal MC steps (mcmc.py:68-130, the loop of mcmc.py:133-159) of B independent chains in ONE
+ * launch, for the Gaussian-VAE family of tests/test_mcmc.py:14-26: FCDeepNN dx -> hidden(relu) -> 2 dz encoder and
+ * dz -> hidden(relu) -> 2 dx decoder with tfp.layers.IndependentNormal heads, N(0, I) prior, and the quadratic energy
+ * of tests/test_mcmc.py:28-32 evaluated on the device in float64.  theta: the flat parameter buffer of the ELBO plan
+ * with num_blocks = 0 (enc.0.W enc.0.b enc.1.W enc.1.b dec.0.W dec.0.b dec.1.W dec.1.b).
+ *   x [B, dx] float32 and E [B] float64 are the chain state, updated in place (E is computed from x first when
+ *   energies_valid == 0);  log_u [n_steps, B] float64 = log of the host's PCG64 uniforms (mcmc.py:119), so decisions
+ *   are bit-identical to the reference under the same seed;  means [dx] float64.
+ *   noise: NULL => Philox4x32-10 + Box-Muller on the device keyed by (seed, global chain index, step0 + step): results
+ *   do not depend on the grid or on how chains are sharded over GPUs;  else float32 [n_steps, B, 2 dz + dx] =
+ *   eps(z1) | eps(z2) | eps(x2) per chain-step (parity mode: the reference draws in this order, mcmc.py:100-102).
+ *   n_acc (device u64) += number of accepted proposals.  Optional traces [n_steps, B]: acc (uint8), forward_log_p,
+ *   reverse_log_p (float32), proposal energies (float64).  All pointers are device pointers.                                                   */
+typedef struct {
+  int32_t dx, dz, hidden;
+} vms_mc_desc;
+typedef struct vms_mc_plan_s* vms_mc_plan;
+int64_t vms_mc_param_count(const vms_mc_desc* desc);
+vms_status vms_mc_plan_create(const vms_mc_desc* desc, vms_mc_plan* plan);
+vms_status vms_mc_plan_destroy(vms_mc_plan plan);
+vms_status vms_mc_run(vms_mc_plan plan, const float* theta, float* x, double* E, int energies_valid, const float* noise,
+                      unsigned long long seed, unsigned long long step0, const double* log_u, const double* means,
+                      int64_t B, int n_steps, unsigned long long* n_acc, uint8_t* acc_trace, float* fwd_trace,
+                      float* rev_trace, double* e_new_trace, vms_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -414,3 +414,85 @@ def test_mcmc_log_probs_and_decisions_match_oracle(vms, prior):
     flips = int((want != end_to_end).sum())
     print('end-to-end decision flips: %d / %d' % (flips, B))
     assert flips <= max(2, B // 500)
+
+
+# ------------------------------------------------------------------------------------------------ fused MC kernel
+def _mc_noise(seed, n_steps, B, dz, dx):
+    """Sampling noise in the order the reference's step draws it (mcmc.py:100-102): encoder, prior, decoder."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((n_steps, B, 2 * dz + dx), np.float32)
+    for s in range(n_steps):
+        out[s, :, :dz] = rng.standard_normal((B, dz), dtype=np.float32)
+        out[s, :, dz:2 * dz] = rng.standard_normal((B, dz), dtype=np.float32)
+        out[s, :, 2 * dz:] = rng.standard_normal((B, dx), dtype=np.float32)
+    return out
+
+
+def test_fused_mc_matches_reference_mcmc_py_goldens(vms):
+    """`vms_mc_run` against the decisions of the REFERENCE's own vaemolsim/mcmc.py (tests/golden/make_goldens.py):
+    every step restarted from the golden state, same sampling noise, same PCG64 uniform stream."""
+    v = vms
+    g = np.load(os.path.join(GOLD, 'mcmc_reference_c4a.npz'))
+    P = ovae.init_vae(1003, prior='normal', hidden=32)
+    model = vae_from_oracle(v, P)
+    noise = _mc_noise(777, 5, 64, 2, 6)
+    mc = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=4002)
+    safe_total = 0
+    for s in range(5):
+        x_old, e_old = g['x_old_%d' % s], g['e_old_%d' % s]
+        x_new, e_new = mc.run_fused(x_old, energies=e_old if s else None, n_steps=1, noise=noise[s:s + 1], trace=True)
+        tr = mc._last_trace
+        assert np.array_equal(tr['log_u'][0], g['log_rand_%d' % s])  # same PCG64 stream as the reference driver
+        assert_close(tr['fwd'][0], g['fwd_%d' % s], rtol=1e-5, atol=2e-5, what='forward_log_p step %d' % s)
+        assert_close(tr['rev'][0], g['rev_%d' % s], rtol=1e-5, atol=2e-5, what='reverse_log_p step %d' % s)
+        assert_close(tr['e_new'][0], g['e_new_%d' % s], rtol=1e-5, atol=1e-5, what='proposal energy step %d' % s)
+        # the kernel's acceptance arithmetic is bit-exact given ITS log-probabilities (mcmc.py:116-120, float64)
+        want = omc.accept(tr['e_new'][0], e_old, tr['fwd'][0], tr['rev'][0], tr['log_u'][0])
+        assert np.array_equal(tr['acc'][0].astype(bool), want)
+        # and equals the reference's decision wherever the margin exceeds the float32 log-prob noise
+        margin = np.abs(g['e_new_%d' % s] + g['rev_%d' % s] - g['e_old_%d' % s] - g['fwd_%d' % s] - g['log_rand_%d' % s])
+        safe = margin > 1e-3
+        safe_total += int(safe.sum())
+        acc = tr['acc'][0].astype(bool)
+        assert np.array_equal(acc[safe], g['acc_%d' % s][safe])
+        same = acc == g['acc_%d' % s]
+        assert_close(x_new[same], g['configs_%d' % s][same], rtol=1e-5, atol=2e-5, what='configs step %d' % s)
+        assert_close(e_new[same], g['energies_%d' % s][same], rtol=1e-5, atol=2e-5, what='energies step %d' % s)
+    assert safe_total > 300 and mc._num_trials == 5 * 64
+
+
+def test_fused_mc_multi_step_equals_single_steps_and_op_by_op_path(vms):
+    """100 steps in one launch == 100 launches of one step (same noise / uniforms), ragged last tile included; the
+    op-by-op MCMC path (per-layer kernels, vms_mc_accept) reproduces the same log-probabilities."""
+    v = vms
+    P = ovae.init_vae(11, prior='normal', hidden=200)
+    model = vae_from_oracle(v, P)
+    B, n_steps = 1000, 20
+    x0 = np.random.default_rng(5).normal(size=(B, 6)).astype(np.float32)
+    noise = _mc_noise(99, n_steps, B, 2, 6)
+    energy = v.mcmc.QuadraticEnergy(6)
+    a = v.mcmc.MCMC(model, energy, random_seed=1)
+    xa, ea = a.run_fused(x0, n_steps=n_steps, noise=noise, trace=True)
+    tra = a._last_trace
+    b = v.mcmc.MCMC(model, energy, random_seed=1)
+    xb, eb = x0, None
+    for s in range(n_steps):
+        xb, eb = b.run_fused(xb, energies=eb, n_steps=1, noise=noise[s:s + 1], trace=True)
+        assert np.array_equal(b._last_trace['acc'][0], tra['acc'][s])
+    assert np.array_equal(xa, xb) and np.array_equal(ea, eb)
+    assert a._num_acc == b._num_acc == float(tra['acc'].sum()) and a._num_trials == B * n_steps
+    assert np.array_equal(ea, energy(xa))  # carried energies are the energies of the carried configurations
+    # device RNG path: deterministic for a seed, independent of how the chains are split into calls
+    c1 = v.mcmc.MCMC(model, energy, random_seed=3)
+    c2 = v.mcmc.MCMC(model, energy, random_seed=3)
+    x1, e1 = c1.run(x0, n_steps=5)
+    assert c1._fused_plan() is not None
+    lo = np.log(np.random.default_rng(3).random(size=(5, B)))
+    x2a, _ = c2.run_fused(x0[:600], n_steps=5, log_u_dev=v.Tensor.from_numpy(np.ascontiguousarray(lo[:, :600])))
+    assert np.array_equal(x1[:600], x2a)
+    assert 0.0 < c1.acceptance_rate <= 1.0
+    # op-by-op path on the same first step: same six log-probabilities
+    z1, lq1 = model.encoder(v.as_tensor(x0)).sample_with_noise(v.as_tensor(noise[0, :, :2]))
+    assert_close(lq1.numpy() + model.prior(z1).log_prob(v.as_tensor(noise[0, :, 2:4])).numpy() +
+                 model.decoder(v.as_tensor(noise[0, :, 2:4])).sample_with_noise(v.as_tensor(noise[0, :, 4:]))[1].numpy(),
+                 tra['fwd'][0], rtol=1e-5, atol=3e-5, what='forward_log_p vs op-by-op path')

@@ -36,6 +36,10 @@ class RqsBwdArgs(C.Structure):
                 ('g_raw_s', c_vp), ('ld_gs', c_i64)]
 
 
+class McDesc(C.Structure):
+    _fields_ = [('dx', C.c_int32), ('dz', C.c_int32), ('hidden', C.c_int32)]
+
+
 class ElboDesc(C.Structure):
     _fields_ = [('dx', C.c_int32), ('dz', C.c_int32), ('hidden', C.c_int32), ('num_blocks', C.c_int32),
                 ('num_bins', C.c_int32), ('flow_hidden', C.c_int32), ('bin_min', c_f32), ('bin_max', c_f32),
@@ -106,6 +110,11 @@ _SIGS = {
     'vms_elbo_param_count': (c_i64, [C.POINTER(ElboDesc)]),
     'vms_elbo_plan_set_mode': (None, [c_vp, c_int]),
     'vms_elbo_plan_is_fused': (c_int, [c_vp]),
+    'vms_mc_param_count': (c_i64, [C.POINTER(McDesc)]),
+    'vms_mc_plan_create': (None, [C.POINTER(McDesc), C.POINTER(c_vp)]),
+    'vms_mc_plan_destroy': (None, [c_vp]),
+    'vms_mc_run': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, C.c_ulonglong, C.c_ulonglong, c_vp, c_vp, c_i64, c_int, c_vp,
+                          c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_elbo_forward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_elbo_forward_backward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
 }

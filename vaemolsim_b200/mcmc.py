@@ -6,9 +6,26 @@ Same class, methods and counters as the reference (mcmc.py:12 `MCMC`, :48 `accep
 operation order).  The uniform stream stays NumPy's PCG64 + `np.log` on the host (mcmc.py:119) so decisions are
 bit-identical to the reference under the same seed; 8 bytes per chain per step are uploaded.
 """
+import ctypes as C
+
 import numpy as np
 
+from . import _abi
 from ._abi import Tensor, as_tensor, ctx
+
+
+class QuadraticEnergy(object):
+    """The test energy of the reference (tests/test_mcmc.py:28-32): E(x) = sum_d (x_d - means_d)^2, means =
+    linspace(-2, 2, D) unless given.  Callable on NumPy arrays exactly like the reference's callback; an `MCMC` built on
+    a Gaussian VAE additionally recognises it and runs whole MC steps in the fused device kernel (`vms_mc_run`)."""
+
+    def __init__(self, n_dims=None, means=None):
+        if means is None:
+            means = np.linspace(-2, 2, int(n_dims))
+        self.means = np.asarray(means, dtype=np.float64).reshape(-1)
+
+    def __call__(self, configs):
+        return np.sum((np.asarray(configs) - self.means[np.newaxis, :])**2, axis=-1)
 
 
 class MCMC(object):
@@ -20,6 +37,10 @@ class MCMC(object):
         self._num_trials = 0.0
         self._num_acc = 0.0
         self._rng = np.random.default_rng(seed=random_seed)
+        self._fused = None
+        self._noise_seed = int(np.random.SeedSequence(random_seed).generate_state(2, np.uint32).astype(np.uint64) @
+                               np.array([1, 1 << 32], np.uint64))
+        self._step0 = 0
 
     @property
     def acceptance_rate(self):
@@ -29,6 +50,85 @@ class MCMC(object):
         self._num_trials = 0.0
         self._num_acc = 0.0
         self._rng = np.random.default_rng(seed=random_seed)
+        self._noise_seed = int(np.random.SeedSequence(random_seed).generate_state(2, np.uint32).astype(np.uint64) @
+                               np.array([1, 1 << 32], np.uint64))
+        self._step0 = 0
+
+    # ------------------------------------------------------------------------------------------ fused device path
+    def _fused_plan(self):
+        """`vms_mc_plan` for this (vae, energy) pair, or None when the pair is outside the fused kernel's family
+        (Gaussian VAE with N(0, I) prior + QuadraticEnergy); the op-by-op path below handles everything else."""
+        if self._fused is not None:
+            return self._fused or None
+        self._fused = False
+        if not isinstance(self.energy_func, QuadraticEnergy):
+            return None
+        try:
+            f = self.vae.fused()
+        except (NotImplementedError, RuntimeError, AttributeError):
+            return None
+        if f.desc.num_blocks != 0 or self.energy_func.means.size != f.dx:
+            return None
+        c = ctx()
+        desc = _abi.McDesc(f.dx, f.dz, f.desc.hidden)
+        h = C.c_void_p()
+        try:
+            c.lib.vms_mc_plan_create(C.byref(desc), C.byref(h))
+        except NotImplementedError:
+            return None
+        self._fused = dict(handle=h.value, elbo=f, means=Tensor.from_numpy(self.energy_func.means),
+                           n_acc=Tensor.zeros((1, ), np.uint64))
+        return self._fused
+
+    def run_fused(self, configs, energies=None, n_steps=1, noise=None, trace=False, configs_dev=None, energies_dev=None,
+                  log_u_dev=None):
+        """n_steps MC steps in one `vms_mc_run` launch.  `noise` [n_steps, B, 2 dz + dx] injects the sampling noise
+        (parity tests); otherwise the device Philox stream keyed by (seed, chain, step) is used.  With `*_dev` tensors the
+        chain state stays on the device (the bench's device-resident leg); log_u always comes from the host PCG64 stream."""
+        fp = self._fused_plan()
+        if fp is None:
+            raise NotImplementedError('run_fused: needs a Gaussian VAE (N(0, I) prior) and a QuadraticEnergy')
+        c = ctx()
+        f = fp['elbo']
+        if configs_dev is None:
+            configs = np.array(configs.numpy() if isinstance(configs, Tensor) else configs)
+            x = Tensor.from_numpy(configs.reshape(configs.shape[0], -1), dtype=np.float32)
+        else:
+            x = configs_dev
+        B = x.shape[0]
+        if energies_dev is not None:
+            e, valid = energies_dev, 1
+        elif energies is None:
+            e, valid = Tensor((B, ), np.float64), 0
+        else:
+            e, valid = as_tensor(np.asarray(energies, np.float64), dtype=np.float64), 1
+        if log_u_dev is None:
+            log_u_dev = Tensor.from_numpy(np.log(self._rng.random(size=(n_steps, B))))  # mcmc.py:119, step by step
+        nz = None if noise is None else Tensor.from_numpy(np.ascontiguousarray(noise, np.float32))
+        tr = {}
+        if trace:
+            tr = dict(acc=Tensor((n_steps, B), np.uint8), fwd=Tensor((n_steps, B)), rev=Tensor((n_steps, B)),
+                      e_new=Tensor((n_steps, B), np.float64), log_u=log_u_dev)
+        P_ = lambda t: None if t is None else t.ptr
+        before = int(fp['n_acc'].numpy()[0]) if configs_dev is None else None
+        c.lib.vms_mc_run(fp['handle'], f.theta.ptr, x.ptr, e.ptr, valid, P_(nz), self._noise_seed, self._step0,
+                         log_u_dev.ptr, fp['means'].ptr, B, n_steps, fp['n_acc'].ptr, P_(tr.get('acc')), P_(tr.get('fwd')),
+                         P_(tr.get('rev')), P_(tr.get('e_new')), c.stream)
+        self._step0 += n_steps
+        self._num_trials += B * n_steps
+        if configs_dev is not None:
+            return x, e
+        self._num_acc += float(int(fp['n_acc'].numpy()[0]) - before)
+        self._last_trace = {k: t.numpy() for k, t in tr.items()}
+        return x.numpy().reshape(configs.shape), e.numpy()
+
+    def sync_counters(self):
+        """Fold the device acceptance counter into `_num_acc` after device-resident `run_fused` calls."""
+        fp = self._fused_plan()
+        if fp is not None:
+            total = float(fp['n_acc'].numpy()[0])
+            self._num_acc += total - getattr(self, '_acc_folded', 0.0)
+            self._acc_folded = total
 
     def _energies(self, configs_host, configs_dev):
         """energy_func is the reference's host callable on NumPy arrays; a callable flagged `on_device` instead maps a
@@ -78,6 +178,8 @@ class MCMC(object):
         return x2.numpy().reshape(configs.shape), e_out.numpy()
 
     def run(self, configs, energies=None, n_steps=1):
+        if self._fused_plan() is not None:
+            return self.run_fused(configs, energies=energies, n_steps=n_steps)
         for n in range(n_steps):
             configs, energies = self.single_step(configs, energies=energies)
         return configs, energies
