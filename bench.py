@@ -13,7 +13,10 @@ Lines printed (one JSON object, rank 0):
   value        inputs resident in HBM; per-step CUDA events on the launching stream; L2 flushed between timed steps
   e2e          same step through the public API (`VAE.train_step`) from PINNED HOST buffers: H2D of x and eps, D2H of
                the loss scalars, wall clock, every step
-  roofline     the dominant kernel of the step, timed alone with CUDA events at the workload's shape
+  roofline     the dominant kernel of the step (elbo_fused_kernel), its device time measured with CUDA events around
+               every launch INSIDE the timed region (vms_elbo_plan_set_timing); HBM-bound kernels timed alone are under
+               "kernels"
+  mc           the second headline metric: MC proposals/sec (C4a: 65,536 chains over all GPUs, 100 steps, fused kernel)
   cpu_baseline the NumPy oracle (CPU restatement; TF/TFP are not installable here) on a bounded sample, rank 0
 `--impl reference` times that CPU restatement as the reference arm (the reference's TF path cannot run in this image).
 """
@@ -53,6 +56,7 @@ def parse():
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='rows per GPU (default: the named config, 4096)')
     ap.add_argument('--no-extras', action='store_true', help='skip roofline microbenchmarks and the CPU baseline')
+    ap.add_argument('--mc-only', action='store_true', help='development aid: run only the MC leg and print it')
     return ap.parse_args()
 
 
@@ -122,6 +126,9 @@ def run_reference(args, w):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    mcb = mc_cpu_baseline()
+    line['mc'] = {'metric': 'MC proposals/sec', 'value': mcb['value'], 'unit': 'proposals/s', 'workload': MC_LABEL,
+                  'cpu_baseline': mcb}
     print(json.dumps(line), flush=True)
 
 
@@ -298,6 +305,90 @@ def kernel_microbench(v, w, batch, reps=20):
     return res, peak, peak_kind
 
 
+# ---------------------------------------------------------------------------------------------------- MC leg (C4a)
+MC_CHAINS, MC_STEPS = 65536, 100
+MC_LABEL = ('C4a VAE-proposal MC: Gaussian VAE (enc 6-200-4, dec 2-200-12, N(0,I) prior), quadratic energy on device, '
+            '%d independent chains over all GPUs, %d steps per launch' % (MC_CHAINS, MC_STEPS))
+
+
+def mc_cpu_baseline(chains=4096, steps=3):
+    """The CPU restatement of MCMC.single_step (oracle/mcmc.py, pinned bit for bit by the reference's own mcmc.py
+    goldens) over the NumPy oracle VAE: proposals/sec on the host cores."""
+    from oracle import mcmc as omc
+    from oracle import vae as ovae
+    P = ovae.init_vae(2003, dx=6, dz=2, hidden=200, prior='normal')
+    model = omc.OracleVAE(P, noise_seed=1)
+    rng = np.random.default_rng(4002)
+    x = np.random.default_rng(4001).standard_normal((chains, 6)).astype(np.float32)
+    x, e, _ = omc.single_step(model, omc.quadratic_energy, rng, x, None)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        x, e, _ = omc.single_step(model, omc.quadratic_energy, rng, x, e)
+    dt = time.perf_counter() - t0
+    return {'value': chains * steps / dt, 'unit': 'proposals/s', 'cores': cpu_threads(), 'kind': 'port',
+            'sample': '%d steps of %d chains, oracle/mcmc.py (restatement of mcmc.py:68-130) over the NumPy oracle VAE' %
+                      (steps, chains)}
+
+
+def mc_bench(v, grp, reps=3):
+    """MC proposals/sec: chains sharded over ranks with no collective; the accept uniforms are ONE PCG64
+    stream sliced per rank, so decisions do not depend on the rank count."""
+    from vaemolsim_b200 import parallel
+    c = v._abi.ctx()
+    lo, hi = parallel.shard_rows(MC_CHAINS, grp.rank, grp.world)
+    B = hi - lo
+    model = build_model(v, WORKLOADS['c1'], 4096)
+    mc = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=4002)
+    if mc._fused_plan() is None:
+        raise RuntimeError('bench: the fused MC plan is unavailable')
+    x0 = np.random.default_rng(4001).standard_normal((MC_CHAINS, 6), dtype=np.float32)[lo:hi]
+    t_rng = time.perf_counter()
+    log_u = np.ascontiguousarray(np.log(np.random.default_rng(4002).random(size=(MC_STEPS, MC_CHAINS)))[:, lo:hi])
+    t_rng = time.perf_counter() - t_rng
+    # device-resident leg: chain state and the uniforms live in HBM; one launch = MC_STEPS steps of B chains
+    xd, lud = v.Tensor.from_numpy(np.ascontiguousarray(x0)), v.Tensor.from_numpy(log_u)
+    xd, ed = mc.run_fused(None, n_steps=MC_STEPS, configs_dev=xd, log_u_dev=lud)  # warm-up (also computes E)
+    for _ in range(2):
+        mc.run_fused(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed, log_u_dev=lud)
+    ev = Events(c, reps)
+    grp.barrier()
+    c.synchronize()
+    l0 = v._abi.launch_count()
+    for i in range(reps):
+        ev.record(2 * i)
+        mc.run_fused(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed, log_u_dev=lud)
+        ev.record(2 * i + 1)
+    c.synchronize()
+    grp.barrier()
+    launches = v._abi.launch_count() - l0
+    dev_ms = grp.max(sum(ev.elapsed_ms(2 * i, 2 * i + 1) for i in range(reps)))
+    mc.sync_counters()
+    acc_rate = mc.acceptance_rate
+    # end to end through the public API: MCMC.run(configs, n_steps) from host arrays -- host PCG64 + log for the
+    # uniforms (mcmc.py:119), H2D of x / log u, the launch, D2H of x / E
+    mc2 = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=4002)
+    mc2.run(x0, n_steps=2)
+    grp.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        xe, ee = mc2.run(x0, n_steps=MC_STEPS)
+    e2e_s = grp.max(time.perf_counter() - t0)
+    tot = MC_CHAINS * MC_STEPS * reps
+    return {'metric': 'MC proposals/sec', 'value': tot / (dev_ms * 1e-3), 'unit': 'proposals/s', 'workload': MC_LABEL,
+            'chains_global': MC_CHAINS, 'chains_per_gpu': B, 'steps_per_launch': MC_STEPS, 'launches_timed': reps,
+            'scaling': 'strong (65,536 chains split over the GPUs, no data-path collective)',
+            'ms_per_mc_step': dev_ms / (reps * MC_STEPS), 'gpu_launches': int(launches), 'acceptance_rate': acc_rate,
+            'e2e': {'value': tot / e2e_s, 'unit': 'proposals/s', 'h2d_bytes_per_step': int(B * 8 + B * 24 / MC_STEPS),
+                    'd2h_bytes_per_step': int(B * 32 / MC_STEPS), 'ms_per_mc_step': e2e_s / (reps * MC_STEPS) * 1e3,
+                    'api': 'MCMC.run(configs, n_steps=%d) from host arrays' % MC_STEPS,
+                    'note': 'includes NumPy PCG64 + log of the accept uniforms on the host (%.1f ms per %d x %d block '
+                            'on this box): the stream is kept on the host so decisions stay bit-identical to the '
+                            'reference under the same seed' % (t_rng * 1e3, MC_STEPS, B)},
+            'algorithmic_flop_per_proposal': 19200,
+            'tflops_fp32': tot * 19200 / (dev_ms * 1e-3) / 1e12}
+
+
+
 def run_b200(args, w):
     import vaemolsim_b200 as v
     from vaemolsim_b200 import parallel
@@ -305,6 +396,12 @@ def run_b200(args, w):
     rank, world = grp.rank, grp.world
     c = v._abi.ctx()
     lib = c.lib
+    if args.mc_only:
+        line = mc_bench(v, grp)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        grp.close()
+        return
     batch = args.batch or w['batch']
     K, W = args.steps, args.warmup
     model = build_model(v, w, batch)
@@ -339,6 +436,7 @@ def run_b200(args, w):
 
     # ---- timed region 1: inputs resident in HBM, per-step CUDA events, L2 flushed (untimed) between steps
     ev = Events(c, K)
+    lib.vms_elbo_plan_set_timing(f.handle, K)
     grp.barrier()
     c.synchronize()
     launches0 = v._abi.launch_count()
@@ -355,6 +453,9 @@ def run_b200(args, w):
     launches = v._abi.launch_count() - launches0
     dev_ms = sum(ev.elapsed_ms(2 * i, 2 * i + 1) for i in range(K))
     dev_ms = grp.max(dev_ms)
+    k_ms, k_n = C.c_double(0), C.c_int(0)
+    lib.vms_elbo_plan_kernel_ms(f.handle, C.byref(k_ms), C.byref(k_n))
+    lib.vms_elbo_plan_set_timing(f.handle, 0)
     ms_per_step = dev_ms / K
     value = world * batch * K / (dev_ms * 1e-3)
 
@@ -387,6 +488,7 @@ def run_b200(args, w):
     t_clock1 = time.perf_counter()
     clocks = sampler.stop(t_clock0, t_clock1)
 
+    mc_line = None if args.no_extras else mc_bench(v, grp)
     if rank != 0:
         grp.close()
         return
@@ -409,17 +511,38 @@ def run_b200(args, w):
     }
     if not args.no_extras:
         micro, peak, peak_kind = kernel_microbench(v, w, batch)
-        dom = micro['rqs_backward@workload']
-        line['roofline'] = {'bound': 'hbm', 'kernel': 'rqs_backward_kernel<%d>' % w['num_bins'],
-                            'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s', 'frac': dom['gbs'] / peak,
-                            'traffic': None, 'peak_kind': peak_kind,
-                            'algorithmic_bytes_per_launch': dom['bytes'], 'launch_ms': dom['ms'],
-                            'note': 'timed alone with CUDA events at the workload shape (%d elements, cold L2); '
-                                    'streaming-size fractions are under "kernels"' % batch}
-        line['roofline_step'] = {'algorithmic_bytes_per_config': 40 + (4 * (392 + 776) if w['prior'] != 'normal' else 0),
-                                 'gbs': (40 + (4 * (392 + 776) if w['prior'] != 'normal' else 0)) * batch /
-                                 (ms_per_step * 1e-3) / 1e9}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except (OSError, ValueError):
+            pass
+        flop_per_config = 259200 if w['prior'] != 'normal' else 28800  # GEMM FLOPs fwd + bwd per configuration
+        if k_n.value:
+            launch_ms = k_ms.value / k_n.value
+            tflops = flop_per_config * batch / (launch_ms * 1e-3) / 1e12
+            tens_peak = float(peaks.get('bf16_tflops', 1590.0))
+            line['roofline'] = {
+                'bound': 'tensor', 'kernel': 'elbo_fused_kernel<bwd>', 'achieved': tflops, 'peak': tens_peak,
+                'unit': 'TFLOP/s', 'frac': tflops / tens_peak, 'traffic': None,
+                'peak_kind': ('measured bf16 dense, burst (MEASURED_PEAKS.json)' if 'bf16_tflops' in peaks else
+                              'fallback (B200_PROFILING.md)'),
+                'algorithmic_flop_per_launch': flop_per_config * batch, 'launch_ms': launch_ms, 'launches_timed': k_n.value,
+                'share_of_step': launch_ms / ms_per_step,
+                'fp32_ffma_peak_nominal_tflops': 74.4, 'frac_of_fp32_ffma': tflops / 74.4,
+                'note': 'the step is one FP32-FFMA kernel (float32 parity forbids plain TF32 tensor-core inputs, DESIGN.md 6); '
+                        'it is bounded by per-phase latency at 32 rows per SM, not by a pipe: the math-pipe roofline is '
+                        'reported against the measured bf16 peak as the contract asks and against the nominal FP32 FFMA '
+                        'peak; HBM-bound kernels and their fractions of the measured copy peak are under "kernels"'}
+        line['roofline_hbm_kernels'] = {
+            'peak': peak, 'unit': 'GB/s', 'peak_kind': peak_kind,
+            'rqs_forward@stream': micro['rqs_forward@stream']['frac'],
+            'rqs_inverse@stream': micro['rqs_inverse@stream']['frac'],
+            'rqs_backward@stream': micro['rqs_backward@stream']['frac'],
+            'normal_log_prob@stream': micro['normal_log_prob@stream']['frac'],
+            'dist_select@C3x1024': micro['dist_select@C3x1024']['frac']}
         line['kernels'] = micro
+        line['mc'] = mc_line
+        line['mc']['cpu_baseline'] = mc_cpu_baseline()
         rows = batch
         cpu_val, cpu_sec = time_cpu(w, rows, 10, 2)
         line['cpu_baseline'] = {'value': cpu_val, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',

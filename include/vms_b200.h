@@ -271,6 +271,11 @@ int64_t vms_elbo_param_count(const vms_elbo_desc* desc);
  * the unfused path (used by the tests to cross-check the two on the device).                                      */
 vms_status vms_elbo_plan_set_mode(vms_elbo_plan plan, int mode);
 int vms_elbo_plan_is_fused(vms_elbo_plan plan);
+/* Measurement aid (bench.py's roofline leg): with max_launches > 0 the fused path brackets its main kernel with CUDA
+ * events on the launching stream for the next max_launches calls; vms_elbo_plan_kernel_ms synchronises, returns the
+ * summed device time of that kernel and the number of launches measured, and resets the counter. */
+vms_status vms_elbo_plan_set_timing(vms_elbo_plan plan, int max_launches);
+vms_status vms_elbo_plan_kernel_ms(vms_elbo_plan plan, double* total_ms, int* launches);
 /* Forward only.  x [B, dx], eps [B, dz] (the reparameterisation noise is an INPUT in parity mode).  Outputs (any
  * nullable): z [B, dz], logq [B], logpz [B], logpx [B], scalars[3] = {loss, nll, kl} (kl unweighted mean).      */
 vms_status vms_elbo_forward(vms_elbo_plan plan, const float* theta, const float* x, const float* eps, int64_t B,

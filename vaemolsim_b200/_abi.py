@@ -110,6 +110,8 @@ _SIGS = {
     'vms_elbo_param_count': (c_i64, [C.POINTER(ElboDesc)]),
     'vms_elbo_plan_set_mode': (None, [c_vp, c_int]),
     'vms_elbo_plan_is_fused': (c_int, [c_vp]),
+    'vms_elbo_plan_set_timing': (None, [c_vp, c_int]),
+    'vms_elbo_plan_kernel_ms': (None, [c_vp, C.POINTER(c_f64), C.POINTER(c_int)]),
     'vms_mc_param_count': (c_i64, [C.POINTER(McDesc)]),
     'vms_mc_plan_create': (None, [C.POINTER(McDesc), C.POINTER(c_vp)]),
     'vms_mc_plan_destroy': (None, [c_vp]),

@@ -389,6 +389,16 @@ vms_status vms_elbo_plan_set_mode(vms_elbo_plan pl, int mode) {
   return VMS_OK;
 }
 
+vms_status vms_elbo_plan_set_timing(vms_elbo_plan pl, int max_launches) {
+  VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "elbo_plan_set_timing: NULL plan");
+  return fused_set_timing(pl, max_launches);
+}
+
+vms_status vms_elbo_plan_kernel_ms(vms_elbo_plan pl, double* total_ms, int* launches) {
+  VMS_REQUIRE(pl && total_ms && launches, VMS_ERR_INVALID_ARG, "elbo_plan_kernel_ms: NULL argument");
+  return fused_kernel_ms(pl, total_ms, launches);
+}
+
 int vms_elbo_plan_is_fused(vms_elbo_plan pl) { return pl && pl->fused && pl->mode == 0 ? 1 : 0; }
 
 vms_status vms_elbo_forward(vms_elbo_plan pl, const float* theta, const float* x, const float* eps, int64_t B, float* z,

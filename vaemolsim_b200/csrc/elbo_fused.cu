@@ -18,7 +18,7 @@
 //     a lane owns output columns (coalesced / conflict-free operand), a warp owns a slab of 4..16 output rows whose
 //     operand is read by 128-bit shared-memory broadcast, accumulators stay in registers.  Forward, input-gradient
 //     and weight-gradient GEMMs are the same routine with different operand strides;
-//   * thin layers (2..12 outputs) are per-row dot products with a warp-shuffle reduction;
+//   * thin layers (2..12 outputs) split the contraction over the 16 warps and combine partial sums in shared memory;
 //   * the spline uses the octet routines of rqs_device.cuh on shared-memory logits (32 octets = 32 rows);
 //   * weight gradients leave the CTA once per tile, into a per-CTA partial gradient (plain stores, deterministic);
 //     a second small kernel sums the partials in fixed order and finishes the three loss scalars.
@@ -51,7 +51,7 @@ struct FusedParams {
   // shared-memory pitches and offsets (floats)
   int ldx, ldz, ldh, ldf, ldfp, ldpe, ldpd, ldc, ldrm, ldwt, sb;
   int o_xs, o_xT, o_eps, o_zR, o_zT, o_he, o_hd, o_pe, o_pd, o_u, o_lp, o_hid, o_cond, o_raw, o_W, o_Wp, o_B, o_gz,
-      o_gua, o_gub, o_scr;
+      o_gua, o_gub, o_scr, o_tsc;
 };
 
 struct FusedCfg {
@@ -59,6 +59,10 @@ struct FusedCfg {
   size_t smem_bytes;
   int max_grid;
   float *gpart, *spart;
+  // optional per-launch timing of the main kernel (bench.py's roofline leg): event pairs recorded around it
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  size_t ev_used = 0;
 };
 
 // Stage one flow block's weights into shared memory with 4-byte cp.async (rows of 3K-1 floats are not 16-byte aligned):
@@ -220,10 +224,6 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
   if (nb > 0) stage_block(p, nb - 1, false);
   for (int i = tid; i < FR * p.ldz; i += FT) zR[i] = (i % p.ldz) == dz ? 1.f : 0.f;
   for (int i = tid; i < FR * p.ldc; i += FT) sm[p.o_cond + i] = 0.f;
-  for (int i = tid; i < FR; i += FT) {
-    sm[p.o_he + i * ldh + H] = 1.f;
-    sm[p.o_hd + i * ldh + H] = 1.f;
-  }
   float cta_kl = 0.f, cta_nll = 0.f;
   const float invB = 1.0f / (float)p.B;
   bool first = true;
@@ -242,6 +242,10 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
       if (c < dx) sm[p.o_xT + c * FR + r] = v;
     }
     for (int i = tid; i < FR * dz; i += FT) epsS[i] = i < nr * dz ? __ldg(p.eps + row0 * dz + i) : 0.f;
+    for (int i = tid; i < FR; i += FT) {  // bias rows of the enc.1 / dec.1 weight gradients 
+      sm[p.o_he + i * ldh + H] = 1.f;
+      sm[p.o_hd + i * ldh + H] = 1.f;
+    }
     cp_async_commit_wait_all();
     __syncthreads();
     // ---------------------------------------------------------------- F1: he = relu(x W + b)   (mappings.py:151-153)
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
                              epi_store(p.o_he, ldh, p.o_Wp + p.enc0b, 1));
     __syncthreads();
     // ---------------------------------------------------------------- F2: encoder head parameters
-    rowdot(p.o_he, ldh, p.o_Wp + p.enc1W, 2 * dz, 1, H, 2 * dz, p.o_pe, p.ldpe, p.o_Wp + p.enc1b, 0);
+    thin_gemm(p.o_he, ldh, p.o_Wp + p.enc1W, 2 * dz, 1, H, 2 * dz, p.o_pe, p.ldpe, p.o_Wp + p.enc1b, 0, p.o_scr);
     __syncthreads();
     // ---------------------------------------------------------------- F3: z = eps * softplus(raw) + loc, log q(z|x)
     if (tid < FR) {
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
     outer_gemm<8, 2, false>(p.o_zT, FR, p.o_Wp + p.dec0W, H, 1, FR, H, dz, 0, 0,
                              epi_store(p.o_hd, ldh, p.o_Wp + p.dec0b, 1));
     __syncthreads();
-    rowdot(p.o_hd, ldh, p.o_Wp + p.dec1W, 2 * dx, 1, H, 2 * dx, p.o_pd, p.ldpd, p.o_Wp + p.dec1b, 0);
+    thin_gemm(p.o_hd, ldh, p.o_Wp + p.dec1W, 2 * dx, 1, H, 2 * dx, p.o_pd, p.ldpd, p.o_Wp + p.dec1b, 0, p.o_scr);
     __syncthreads();
     if (tid < FR) {
       const int r = tid;
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
       __syncthreads();
       // B4: [W; b] gradient of dec.0;  B5: g_z = ghd W^T
       outer_gemm<4, 1, false>(p.o_zR, p.ldz, ghd, ldh, 1, dz + 1, H, FR, 0, 0, epi_grad(gp + p.dec0W, H, 1, first));
-      rowdot(ghd, ldh, p.o_Wp + p.dec0W, 1, H, H, dz, p.o_gz, dz, -1, 0);
+      thin_gemm(ghd, ldh, p.o_Wp + p.dec0W, 1, H, H, dz, p.o_gz, dz, -1, 0, p.o_tsc);
       __syncthreads();
     }
     // ---------------------------------------------------------------- B6: prior
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
         // [d1W; d1b] gradient and the conditioner-input gradient
         outer_gemm<4, 1, false>(p.o_cond, p.ldc, gpre, p.ldfp, 1, fb.cin + 1, fh, FR, 0, 0,
                                 epi_grad(gp + fb.off_d1W, fh, 1, first));
-        if (fb.nc > 0) rowdot(gpre, p.ldfp, p.o_B + (i & 1) * p.sb, 1, fh, fh, fb.nc, gnxt + fb.cs0, dz, -1, 1);
+        if (fb.nc > 0) thin_gemm(gpre, p.ldfp, p.o_B + (i & 1) * p.sb, 1, fh, fh, fb.nc, gnxt + fb.cs0, dz, -1, 1, p.o_tsc);
         cp_async_commit_wait_all();
         __syncthreads();
         const int t = gcur;
@@ -507,7 +511,7 @@ vms_status fused_create(vms_elbo_plan_s* pl) {
     max_cin = b.cin > max_cin ? b.cin : max_cin;
   }
   if (max_cin > kMaxThin) { delete f; return VMS_OK; }
-  p.ldx = r4(d.dx + 1); p.ldz = r4(d.dz + 1); p.ldh = d.hidden + 1; p.ldf = r4(p.fh + 1); p.ldfp = r4(p.fh);
+  p.ldx = r4(d.dx + 1); p.ldz = r4(d.dz + 1); p.ldh = (d.hidden + 1) | 1; p.ldf = r4(p.fh + 1); p.ldfp = p.fh | 1;
   p.ldpe = r4(2 * d.dz); p.ldpd = r4(2 * d.dx); p.ldc = r4(max_cin + 1); p.ldrm = r4(max_ldr);
   p.ldwt = p.fh | 1;
   p.sb = r4(max_cin * p.fh + p.fh + p.ldrm);
@@ -530,6 +534,11 @@ vms_status fused_create(vms_elbo_plan_s* pl) {
   const int scr_flow = d.num_blocks ? 2 * FR * p.ldrm + FR * p.ldfp : 0;
   int scr = scr_dec > scr_enc ? scr_dec : scr_enc;
   scr = scr_flow > scr ? scr_flow : scr;
+  // thin_gemm scratch: the forward thin layers (2 dx / 2 dz outputs) borrow scr, the backward ones (dz / nc outputs)
+  // have a small region of their own
+  const int thin_fwd = FW * r4(2 * (d.dx > d.dz ? d.dx : d.dz)) * FR;
+  scr = thin_fwd > scr ? thin_fwd : scr;
+  p.o_tsc = take(FW * r4(d.dz > max_cin ? d.dz : max_cin) * FR);
   p.o_scr = take(scr);
   off += 64;  // slab reads may run a few floats past the last row of an operand
   f->smem_bytes = (size_t)off * sizeof(float);
@@ -559,8 +568,42 @@ vms_status fused_create(vms_elbo_plan_s* pl) {
   return VMS_OK;
 }
 
+vms_status fused_set_timing(vms_elbo_plan_s* pl, int max_launches) {
+  FusedCfg* f = pl->fused;
+  if (!f) return VMS_OK;
+  f->ev_used = 0;
+  f->timing = max_launches > 0;
+  while ((int)f->ev.size() < max_launches) {
+    cudaEvent_t a, b;
+    VMS_CUDA(cudaEventCreate(&a));
+    VMS_CUDA(cudaEventCreate(&b));
+    f->ev.emplace_back(a, b);
+  }
+  return VMS_OK;
+}
+
+vms_status fused_kernel_ms(vms_elbo_plan_s* pl, double* total_ms, int* launches) {
+  FusedCfg* f = pl->fused;
+  *total_ms = 0.0;
+  *launches = 0;
+  if (!f) return VMS_OK;
+  for (size_t i = 0; i < f->ev_used; ++i) {
+    float ms = 0.f;
+    VMS_CUDA(cudaEventSynchronize(f->ev[i].second));
+    VMS_CUDA(cudaEventElapsedTime(&ms, f->ev[i].first, f->ev[i].second));
+    *total_ms += ms;
+  }
+  *launches = (int)f->ev_used;
+  f->ev_used = 0;
+  return VMS_OK;
+}
+
 void fused_destroy(vms_elbo_plan_s* pl) {
   if (!pl->fused) return;
+  for (auto& e : pl->fused->ev) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
   cudaFree(pl->fused->gpart);
   cudaFree(pl->fused->spart);
   delete pl->fused;
@@ -577,11 +620,14 @@ vms_status fused_run(vms_elbo_plan_s* pl, const float* theta, const float* x, co
   p.z = z; p.logq = logq; p.logpz = logpz; p.logpx = logpx;
   p.gpart = f->gpart; p.spart = f->spart;
   const int grid = p.n_tiles < f->max_grid ? p.n_tiles : f->max_grid;
+  const bool timed = f->timing && f->ev_used < f->ev.size();
+  if (timed) VMS_CUDA(cudaEventRecord(f->ev[f->ev_used].first, st));
   if (backward)
     elbo_fused_kernel<true><<<grid, FT, f->smem_bytes, st>>>(p);
   else
     elbo_fused_kernel<false><<<grid, FT, f->smem_bytes, st>>>(p);
   VMS_LAUNCH_CHECK("elbo_fused_kernel");
+  if (timed) VMS_CUDA(cudaEventRecord(f->ev[f->ev_used++].second, st));
   float* sc = scalars ? scalars : pl->scalars;
   const int nblk = backward ? (p.P + 31) / 32 : 1;
   fused_finish_kernel<<<nblk, 32 * kFinGroups, 0, st>>>(f->gpart, grid, p.P, backward ? grad : nullptr, f->spart, B, p.klw, sc);

@@ -83,6 +83,8 @@ namespace vms {
 // elbo_fused.cu
 vms_status fused_create(vms_elbo_plan_s* pl);   // sets pl->fused (or leaves NULL when the shape does not fit)
 void fused_destroy(vms_elbo_plan_s* pl);
+vms_status fused_set_timing(vms_elbo_plan_s* pl, int max_launches);
+vms_status fused_kernel_ms(vms_elbo_plan_s* pl, double* total_ms, int* launches);
 vms_status fused_run(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B, bool backward,
                      float* z, float* logq, float* logpz, float* logpx, float* grad, float* scalars, cudaStream_t st);
 }  // namespace vms

@@ -17,7 +17,7 @@
 // per step a chain moves 8 bytes from HBM (its log u; the uniform stream stays NumPy's PCG64 on the host so decisions
 // are bit-identical to the reference under the same seed) and nothing else.  One step is four small MLP evaluations
 // arranged as two independent chains [enc(x1) -> z1 -> dec(z1)] and [z2 -> dec(z2) -> x2 -> enc(x2)], evaluated in
-// lock-step with the tile GEMM routines of tile_gemm.cuh (6 barriers per step).  Sampling noise is Philox4x32-10 +
+// lock-step with the tile GEMM routines of tile_gemm.cuh.  Sampling noise is Philox4x32-10 +
 // Box-Muller keyed by (seed, global chain, step), so results do not depend on the grid or the number of GPUs; in
 // parity mode the noise is an input instead.
 #include "tile_gemm.cuh"
@@ -46,7 +46,7 @@ struct McParams {
   // shared-memory pitches / offsets (floats)
   int ldx, ldz, ldh, ldpe, ldpd, ldn;
   int o_Wp, o_x1, o_x1T, o_x2, o_x2T, o_z1, o_z1T, o_z2, o_z2T, o_he1, o_he2, o_hd1, o_hd2, o_pe1, o_pe2, o_pd1, o_pd2,
-      o_nz, o_lp, o_E;
+      o_nz, o_lp, o_E, o_tq, o_tx, o_te, o_sc, o_sc2;
 };
 
 // Philox4x32-10 (Salmon et al. 2011): counter-based, so chain / step / slot index the stream directly.
@@ -83,6 +83,9 @@ __global__ void __launch_bounds__(FT, 1) mc_fused_kernel(const __grid_constant__
   float* nz = sm + p.o_nz;
   float* lp = sm + p.o_lp;   // [6][FR]: lq1, lz1, lz2, lx2, lx1, lq2
   double* Es = reinterpret_cast<double*>(sm + p.o_E);  // [2][FR]: E_old, E_new
+  float* tq = sm + p.o_tq;   // [3][FR][dz] per-dof log-prob terms (latent side)
+  float* tx = sm + p.o_tx;   // [FR][dx] per-dof log-prob terms (configuration side)
+  double* te = reinterpret_cast<double*>(sm + p.o_te);  // [FR][dx] per-dof energy terms
   for (int i = tid; i < p.n_mlp; i += FT) cp_async4(sm + p.o_Wp + i, p.theta + i);
   cp_async_commit_wait_all();
   unsigned long long cta_acc = 0;
@@ -154,38 +157,52 @@ __global__ void __launch_bounds__(FT, 1) mc_fused_kernel(const __grid_constant__
                               epi_store(p.o_hd2, ldh, p.o_Wp + p.dec0b, 1));
       __syncthreads();
       // ---------------------------------------------------------------- B: enc head(x1)  ||  dec head(z2)
-      rowdot(p.o_he1, ldh, p.o_Wp + p.enc1W, 2 * dz, 1, H, 2 * dz, p.o_pe1, p.ldpe, p.o_Wp + p.enc1b, 0);
-      rowdot(p.o_hd2, ldh, p.o_Wp + p.dec1W, 2 * dx, 1, H, 2 * dx, p.o_pd2, p.ldpd, p.o_Wp + p.dec1b, 0);
+      thin_gemm(p.o_he1, ldh, p.o_Wp + p.enc1W, 2 * dz, 1, H, 2 * dz, p.o_pe1, p.ldpe, p.o_Wp + p.enc1b, 0, p.o_sc);
+      thin_gemm(p.o_hd2, ldh, p.o_Wp + p.dec1W, 2 * dx, 1, H, 2 * dx, p.o_pd2, p.ldpd, p.o_Wp + p.dec1b, 0, p.o_sc2);
       __syncthreads();
-      // ---------------------------------------------------------------- C: samples z1, x2 and their log-probs
-      if (tid < FR) {
-        const int r = tid;
-        const float* pe = sm + p.o_pe1 + r * p.ldpe;
-        const float* pd = sm + p.o_pd2 + r * p.ldpd;
-        float lq1 = 0.f, lz1 = 0.f, lz2 = 0.f, lx2 = 0.f;
-        for (int d = 0; d < dz; ++d) {
+      // ---------------------------------------------------------------- C: samples z1, x2 and their log-prob terms
+      // one thread per (chain, dof): the per-dof terms go to shared memory and are summed in dof order afterwards
+      // (same summation order as the op-by-op kernels; a single warp doing all dofs was 8k cycles of dependent math)
+      for (int i = tid; i < FR * (dz + dx); i += FT) {
+        if (i < FR * dz) {
+          const int r = i / dz, d = i - r * dz;
+          const float* pe = sm + p.o_pe1 + r * p.ldpe;
           const float loc = pe[d], sc = softplus_tf(pe[dz + d]);
           const float zz = __fadd_rn(__fmul_rn(nz[r * p.ldn + d], sc), loc);  // separate TF mul and add ops
-          lq1 += normal_lp(zz, loc, sc);
-          lz1 += normal_lp(zz, 0.f, 1.f);
-          lz2 += normal_lp(z2[r * p.ldz + d], 0.f, 1.f);
           z1[r * p.ldz + d] = zz;
           sm[p.o_z1T + d * FR + r] = zz;
+          tq[r * dz + d] = normal_lp(zz, loc, sc);
+          tq[(FR + r) * dz + d] = normal_lp(zz, 0.f, 1.f);
+          tq[(2 * FR + r) * dz + d] = normal_lp(z2[r * p.ldz + d], 0.f, 1.f);
+        } else {
+          const int j = i - FR * dz, r = j / dx, d = j - r * dx;
+          const float* pd = sm + p.o_pd2 + r * p.ldpd;
+          const float loc = pd[d], sc = softplus_tf(pd[dx + d]);
+          const float xx = __fadd_rn(__fmul_rn(nz[r * p.ldn + 2 * dz + d], sc), loc);
+          x2[r * p.ldx + d] = xx;
+          sm[p.o_x2T + d * FR + r] = xx;
+          tx[r * dx + d] = normal_lp(xx, loc, sc);
+          const double t = __dsub_rn((double)xx, p.means[d]);
+          te[r * dx + d] = __dmul_rn(t, t);
+        }
+      }
+      __syncthreads();
+      if (tid < FR) {
+        const int r = tid;
+        float lq1 = 0.f, lz1 = 0.f, lz2 = 0.f, lx2 = 0.f;
+        for (int d = 0; d < dz; ++d) {
+          lq1 += tq[r * dz + d];
+          lz1 += tq[(FR + r) * dz + d];
+          lz2 += tq[(2 * FR + r) * dz + d];
         }
         double e_new = 0.0;
         for (int d = 0; d < dx; ++d) {
-          const float loc = pd[d], sc = softplus_tf(pd[dx + d]);
-          const float xx = __fadd_rn(__fmul_rn(nz[r * p.ldn + 2 * dz + d], sc), loc);
-          lx2 += normal_lp(xx, loc, sc);
-          x2[r * p.ldx + d] = xx;
-          sm[p.o_x2T + d * FR + r] = xx;
-          const double t = __dsub_rn((double)xx, p.means[d]);
-          e_new = __dadd_rn(e_new, __dmul_rn(t, t));
+          lx2 += tx[r * dx + d];
+          e_new = __dadd_rn(e_new, te[r * dx + d]);  // NumPy squares, then sums: no FMA contraction
         }
         lp[r] = lq1; lp[FR + r] = lz1; lp[2 * FR + r] = lz2; lp[3 * FR + r] = lx2;
         Es[FR + r] = e_new;
       }
-      __syncthreads();
       // ---------------------------------------------------------------- D: dec hidden(z1)  ||  enc hidden(x2)
       outer_gemm<8, 2, false>(p.o_z1T, FR, p.o_Wp + p.dec0W, H, 1, FR, H, dz, 0, 0,
                               epi_store(p.o_hd1, ldh, p.o_Wp + p.dec0b, 1));
@@ -193,17 +210,27 @@ __global__ void __launch_bounds__(FT, 1) mc_fused_kernel(const __grid_constant__
                               epi_store(p.o_he2, ldh, p.o_Wp + p.enc0b, 1));
       __syncthreads();
       // ---------------------------------------------------------------- E: dec head(z1)  ||  enc head(x2)
-      rowdot(p.o_hd1, ldh, p.o_Wp + p.dec1W, 2 * dx, 1, H, 2 * dx, p.o_pd1, p.ldpd, p.o_Wp + p.dec1b, 0);
-      rowdot(p.o_he2, ldh, p.o_Wp + p.enc1W, 2 * dz, 1, H, 2 * dz, p.o_pe2, p.ldpe, p.o_Wp + p.enc1b, 0);
+      thin_gemm(p.o_hd1, ldh, p.o_Wp + p.dec1W, 2 * dx, 1, H, 2 * dx, p.o_pd1, p.ldpd, p.o_Wp + p.dec1b, 0, p.o_sc2);
+      thin_gemm(p.o_he2, ldh, p.o_Wp + p.enc1W, 2 * dz, 1, H, 2 * dz, p.o_pe2, p.ldpe, p.o_Wp + p.enc1b, 0, p.o_sc);
       __syncthreads();
       // ---------------------------------------------------------------- F: reverse log-probs, accept / reject
+      for (int i = tid; i < FR * (dz + dx); i += FT) {
+        if (i < FR * dz) {
+          const int r = i / dz, d = i - r * dz;
+          const float* pe = sm + p.o_pe2 + r * p.ldpe;
+          tq[r * dz + d] = normal_lp(z2[r * p.ldz + d], pe[d], softplus_tf(pe[dz + d]));
+        } else {
+          const int j = i - FR * dz, r = j / dx, d = j - r * dx;
+          const float* pd = sm + p.o_pd1 + r * p.ldpd;
+          tx[r * dx + d] = normal_lp(x1[r * p.ldx + d], pd[d], softplus_tf(pd[dx + d]));
+        }
+      }
+      __syncthreads();
       if (tid < FR) {
         const int r = tid;
-        const float* pe = sm + p.o_pe2 + r * p.ldpe;
-        const float* pd = sm + p.o_pd1 + r * p.ldpd;
         float lq2 = 0.f, lx1 = 0.f;
-        for (int d = 0; d < dz; ++d) lq2 += normal_lp(z2[r * p.ldz + d], pe[d], softplus_tf(pe[dz + d]));
-        for (int d = 0; d < dx; ++d) lx1 += normal_lp(x1[r * p.ldx + d], pd[d], softplus_tf(pd[dx + d]));
+        for (int d = 0; d < dz; ++d) lq2 += tq[r * dz + d];
+        for (int d = 0; d < dx; ++d) lx1 += tx[r * dx + d];
         // mcmc.py:103, :109: float32 sums, left to right
         const float fwd = __fadd_rn(__fadd_rn(lp[r], lp[2 * FR + r]), lp[3 * FR + r]);
         const float rev = __fadd_rn(__fadd_rn(lq2, lp[FR + r]), lx1);
@@ -284,7 +311,7 @@ vms_status vms_mc_plan_create(const vms_mc_desc* desc, vms_mc_plan* plan) {
   p.dec1W = o; o += d.hidden * 2 * d.dx;
   p.dec1b = o; o += 2 * d.dx;
   p.n_mlp = o;
-  p.ldx = r4i(d.dx); p.ldz = r4i(d.dz); p.ldh = d.hidden + 1; p.ldpe = r4i(2 * d.dz); p.ldpd = r4i(2 * d.dx);
+  p.ldx = r4i(d.dx); p.ldz = r4i(d.dz); p.ldh = (d.hidden + 1) | 1; p.ldpe = r4i(2 * d.dz); p.ldpd = r4i(2 * d.dx);
   p.ldn = r4i(2 * d.dz + d.dx);
   int off = 0;
   auto take = [&](int n) { int o0 = off; off += r4i(n); return o0; };
@@ -295,6 +322,8 @@ vms_status vms_mc_plan_create(const vms_mc_desc* desc, vms_mc_plan* plan) {
   p.o_pe1 = take(FR * p.ldpe); p.o_pe2 = take(FR * p.ldpe); p.o_pd1 = take(FR * p.ldpd); p.o_pd2 = take(FR * p.ldpd);
   p.o_nz = take(FR * p.ldn); p.o_lp = take(6 * FR);
   p.o_E = take(4 * FR);  // 2 x FR doubles (offset is a multiple of 4 floats => 16-byte aligned)
+  p.o_sc = take(FW * r4i(2 * d.dz) * FR); p.o_sc2 = take(FW * r4i(2 * d.dx) * FR);
+  p.o_tq = take(3 * FR * d.dz); p.o_tx = take(FR * d.dx); p.o_te = take(2 * FR * d.dx);
   off += 64;
   pl->smem_bytes = (size_t)off * sizeof(float);
   if (pl->smem_bytes > (size_t)max_smem_optin()) {

@@ -1,7 +1,7 @@
 // tile_gemm.cuh -- CTA-level building blocks shared by the fused ELBO kernel (elbo_fused.cu) and the fused MC kernel
 // (mc_fused.cu): a 32-row tile of configurations lives in dynamic shared memory, 512 threads work on it.
 //   outer_gemm  FP32 FFMA "outer-product" GEMM for wide layers (forward, input-gradient and weight-gradient forms)
-//   rowdot      thin layers (<= 16 outputs) as per-row dot products with a warp-shuffle reduction
+//   thin_gemm   thin layers (<= 16 outputs): contraction split over the 16 warps, partial sums combined in shared memory
 //   Epi         POD epilogue descriptor (bias / activation / mask / partial-gradient accumulate)
 //   cp_async4   4-byte global -> shared copies for weight staging
 #pragma once
@@ -141,46 +141,53 @@ __device__ __noinline__ void outer_gemm(int S, int sSt, int L, int sLt, int sLj,
   }
 }
 
-// Thin outputs: out[r][n] (+)= sum_k X[r * ldx + k] * W[k * sWk + n * sWn] (+ bias[n]),  n < N <= kMaxThin; X, W, out,
-// bias are shared-memory offsets.  Warp w owns rows 2 w, 2 w + 1, lanes stride over k, totals by warp shuffle.
-static __device__ __noinline__ void rowdot(int X, int ldx, int W, int sWk, int sWn, int Kd, int N, int out, int ldo, int bias,
-                                    int accumulate) {
+// Thin outputs: out[r][n] (+)= sum_k X[r * ldx + k] * W[k * sWk + n * sWn] (+ bias[n]),  n < N <= kMaxThin, FR rows; X, W,
+// out, bias, scratch are shared-memory offsets.  The contraction is split 16 ways: warp w takes k in
+// [w Kd/16, (w+1) Kd/16), its lanes take the 32 rows (ldx odd => conflict-free), the weight row is a broadcast load
+// (128-bit when n is the contiguous index); the 16 partial sums meet in `scratch` (16 x round4(N) x 32 floats) and are
+// added in warp order.  (The first version reduced over lanes with shuffles: 60 % of the MC kernel's samples.)
+// Contains __syncthreads(): call from uniform control flow; the caller synchronises before using `out`.
+static __device__ __noinline__ void thin_gemm(int X, int ldx, int W, int sWk, int sWn, int Kd, int N, int out, int ldo,
+                                              int bias, int accumulate, int scratch) {
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int RW = FR / FW;
-  constexpr int NB = 4;  // outputs per pass: small code (this routine runs once per call site and tile)
+  const int kc = (Kd + FW - 1) / FW;
+  const int k0 = min(Kd, warp * kc), k1 = min(Kd, k0 + kc);
+  const int Np = (N + 3) & ~3;
+  const int xo = X + lane * ldx;
 #pragma unroll 1
-  for (int n0 = 0; n0 < N; n0 += NB) {
-    float acc[RW][NB];
-#pragma unroll
-    for (int rr = 0; rr < RW; ++rr)
-#pragma unroll
-      for (int n = 0; n < NB; ++n) acc[rr][n] = 0.f;
-#pragma unroll 1
-    for (int k = lane; k < Kd; k += 32) {
-      float xv[RW];
-#pragma unroll
-      for (int rr = 0; rr < RW; ++rr) xv[rr] = sm[X + (warp * RW + rr) * ldx + k];
-      const int wo = W + k * sWk + n0 * sWn;
-#pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        const float w = sm[wo + min(n, N - 1 - n0) * sWn];
-#pragma unroll
-        for (int rr = 0; rr < RW; ++rr) acc[rr][n] = fmaf(xv[rr], w, acc[rr][n]);
+  for (int n0 = 0; n0 < N; n0 += 4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const bool vec = sWn == 1 && ((W + n0) & 3) == 0 && (sWk & 3) == 0 && n0 + 4 <= N;
+    if (vec) {
+#pragma unroll 4
+      for (int k = k0; k < k1; ++k) {
+        const float x = sm[xo + k];
+        const float4 w = *reinterpret_cast<const float4*>(sm + W + k * sWk + n0);
+        a0 = fmaf(x, w.x, a0); a1 = fmaf(x, w.y, a1); a2 = fmaf(x, w.z, a2); a3 = fmaf(x, w.w, a3);
+      }
+    } else {
+      const int c1 = min(n0 + 1, N - 1) * sWn, c2 = min(n0 + 2, N - 1) * sWn, c3 = min(n0 + 3, N - 1) * sWn;
+#pragma unroll 4
+      for (int k = k0; k < k1; ++k) {
+        const float x = sm[xo + k];
+        const int wo = W + k * sWk;
+        a0 = fmaf(x, sm[wo + n0 * sWn], a0); a1 = fmaf(x, sm[wo + c1], a1);
+        a2 = fmaf(x, sm[wo + c2], a2); a3 = fmaf(x, sm[wo + c3], a3);
       }
     }
+    float* sc = sm + scratch + (warp * Np + n0) * FR + lane;
+    sc[0] = a0; sc[FR] = a1; sc[2 * FR] = a2; sc[3 * FR] = a3;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < N * FR; e += FT) {
+    const int n = e / FR, r = e - n * FR;
+    float v = 0.f;
 #pragma unroll
-    for (int n = 0; n < NB; ++n) {
-#pragma unroll
-      for (int rr = 0; rr < RW; ++rr) {
-        float v = warp_sum(acc[rr][n]);
-        if (lane == 0 && n0 + n < N) {
-          const int o = out + (warp * RW + rr) * ldo + n0 + n;
-          if (bias >= 0) v += sm[bias + n0 + n];
-          sm[o] = accumulate ? sm[o] + v : v;
-        }
-      }
-    }
+    for (int w = 0; w < FW; ++w) v += sm[scratch + (w * Np + n) * FR + r];
+    if (bias >= 0) v += sm[bias + n];
+    const int o = out + r * ldo + n;
+    sm[o] = accumulate ? sm[o] + v : v;
   }
 }
 
