@@ -60,3 +60,24 @@ for nm, nbytes, fn in (
     med, mn = timeit(fn)
     print('%-12s n=%8d K=%d  median %8.2f us  min %8.2f us  %7.1f GB/s algorithmic = %.3f of %.1f GB/s' %
           (nm, n, K, med, mn, nbytes / med / 1e3, nbytes / med / 1e3 / peak, peak))
+
+# decoder-distribution log_prob (K4) and neighbour selection (K6)
+i32 = lambda a: (C.c_int32 * len(a))(*a)
+nr, D = 1 << 22, 6
+xx, pp, lp = T(rng.standard_normal((nr, D))), T(rng.standard_normal((nr, 2 * D))), v.Tensor((nr, ))
+kind, loc, loc2, sc = i32([0] * D), i32(list(range(D))), i32([-1] * D), i32(list(range(D, 2 * D)))
+med, mn = timeit(lambda: lib.vms_blockwise_log_prob(xx.ptr, D, pp.ptr, 2 * D, nr, D, kind, loc, loc2, sc, 1, lp.ptr, 0, c.stream))
+nb = nr * (3 * D * 4 + 4)
+print('normal_lp    rows=%8d D=%d  median %8.2f us  min %8.2f us  %7.1f GB/s algorithmic = %.3f of %.1f GB/s' %
+      (nr, D, med, mn, nb / med / 1e3, nb / med / 1e3 / peak, peak))
+for Bs, N, k in ((1024, 10000, 50), (4096, 10000, 50), (4096, 10000, 10)):
+    coords = T(np.broadcast_to(rng.uniform(-23.2, 23.2, (1, N, 3)).astype(np.float32), (Bs, N, 3)))
+    ref = T(rng.uniform(-23.2, 23.2, (Bs, 3)))
+    box = T(np.full(3, 46.416, np.float32))
+    oxyz = v.Tensor((Bs, k, 3))
+    med, mn = timeit(lambda: lib.vms_dist_select(coords.ptr, None, Bs, N, ref.ptr, box.ptr, 0, 9.0, k, None, 0, oxyz.ptr,
+                                                 None, None, c.stream))
+    nb = Bs * (12 * N + 12 + k * 12)
+    print('dist_select  rows=%5d N=%d k=%d  median %8.2f us  min %8.2f us  %7.1f GB/s algorithmic = %.3f of %.1f GB/s' %
+          (Bs, N, k, med, mn, nb / med / 1e3, nb / med / 1e3 / peak, peak))
+    del coords

@@ -62,6 +62,51 @@ __global__ void blockwise_lp_kernel(const float* __restrict__ x, int64_t ld_x, c
   lp[b] = accumulate ? lp[b] + s : s;
 }
 
+// Fast path of blockwise_lp_kernel for the layout every Normal head of the path uses (tfp.layers.IndependentNormal,
+// tests/test_models.py:167-170): all dofs Normal, params = [loc_0..loc_{D-1} | raw_0..raw_{D-1}], contiguous rows.
+// ncu on the generic kernel: it is ISSUE-bound (about 90 instructions per dof: two IEEE divisions, logf, expf and
+// log1pf behind softplus), 41 % of the HBM copy peak.  Here the two divisions by the scale become one correctly
+// rounded reciprocal and two multiplies (<= 1.5 ulp on z), log(scale) uses the fast hardware log2 (|error| < 1e-6
+// absolute; scale = softplus(raw) > 0), D is a template parameter so the dof loop is straight-line code, and the row's
+// x and params are fetched with 8- / 16-byte loads.  (A shared-memory-staged "fully coalesced" variant measured
+// SLOWER, 22 %: the per-element index arithmetic of the staging cost more than the sector inefficiency it removed.)
+template <int D>
+__global__ void __launch_bounds__(128) normal_rows_lp_kernel(const float* __restrict__ x, const float* __restrict__ params,
+                                                             int64_t B, int scale_mode, float* __restrict__ lp,
+                                                             int accumulate) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float xr[D], pr[2 * D];
+  if (D % 2 == 0) {
+    const float2* x2 = reinterpret_cast<const float2*>(x + b * D);
+#pragma unroll
+    for (int i = 0; i < D / 2; ++i) {
+      const float2 t = __ldg(x2 + i);
+      xr[2 * i] = t.x; xr[2 * i + 1] = t.y;
+    }
+    const float4* p4 = reinterpret_cast<const float4*>(params + b * 2 * D);
+#pragma unroll
+    for (int i = 0; i < D / 2; ++i) {
+      const float4 t = __ldg(p4 + i);
+      pr[4 * i] = t.x; pr[4 * i + 1] = t.y; pr[4 * i + 2] = t.z; pr[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i) xr[i] = __ldg(x + b * D + i);
+#pragma unroll
+    for (int i = 0; i < 2 * D; ++i) pr[i] = __ldg(params + b * 2 * D + i);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float sc = apply_scale(pr[D + d], scale_mode);
+    const float inv = __frcp_rn(sc);
+    const float z = fmaf(xr[d], inv, -(pr[d] * inv));
+    s += -0.5f * z * z - (VMS_HALF_LOG_2PI + __logf(sc));
+  }
+  lp[b] = accumulate ? lp[b] + s : s;
+}
+
 // constrained parameters of every dof: loc [B, D] and scale / concentration [B, D] (make_param_transform, dists.py:28-87)
 __global__ void blockwise_params_kernel(const float* __restrict__ params, int64_t ld_p, int64_t B, int D,
                                         const BlockwiseSpec spec, int scale_mode, float* __restrict__ loc,
@@ -171,6 +216,20 @@ vms_status vms_blockwise_log_prob(const float* x, int64_t ld_x, const float* par
   if (s) return s;
   VMS_REQUIRE(x && params && lp, VMS_ERR_INVALID_ARG, "blockwise_log_prob: NULL pointer");
   if (B == 0) return VMS_OK;
+  bool planar = ld_x == D && ld_p == 2 * D && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
+                (reinterpret_cast<uintptr_t>(params) & 15u) == 0;
+  for (int d = 0; d < D && planar; ++d) planar = kind[d] == VMS_DIST_NORMAL && loc_off[d] == d && scale_off[d] == D + d;
+  if (planar && D <= 8) {
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    cudaStream_t st = as_stream(stream);
+    switch (D) {
+#define VMS_NR(DD) case DD: normal_rows_lp_kernel<DD><<<grid, 128, 0, st>>>(x, params, B, scale_mode, lp, accumulate); break;
+      VMS_NR(1) VMS_NR(2) VMS_NR(3) VMS_NR(4) VMS_NR(5) VMS_NR(6) VMS_NR(7) VMS_NR(8)
+#undef VMS_NR
+    }
+    VMS_LAUNCH_CHECK("normal_rows_lp_kernel");
+    return VMS_OK;
+  }
   blockwise_lp_kernel<<<(unsigned)((B + 127) / 128), 128, 0, as_stream(stream)>>>(x, ld_x, params, ld_p, B, D, spec,
                                                                                  scale_mode, lp, accumulate);
   VMS_LAUNCH_CHECK("blockwise_lp_kernel");
