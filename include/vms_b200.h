@@ -283,6 +283,13 @@ vms_status vms_elbo_forward(vms_elbo_plan plan, const float* theta, const float*
 /* Forward + backward: additionally writes the flat gradient of `loss` w.r.t. theta into grad [param_count].     */
 vms_status vms_elbo_forward_backward(vms_elbo_plan plan, const float* theta, const float* x, const float* eps,
                                      int64_t B, float* grad, float* scalars, vms_stream stream);
+/* One single-GPU training step: forward + backward + Adam (same update as vms_adam_step with grad_scale = 1).  On the
+ * fused path the update rides in the kernel that sums the per-CTA partial gradients: 2 launches per step.  grad
+ * [param_count] still receives the gradient.  (Data-parallel training keeps the three calls separate: the gradient
+ * allreduce sits between vms_elbo_forward_backward and vms_adam_step.)                                            */
+vms_status vms_elbo_train_step(vms_elbo_plan plan, float* theta, const float* x, const float* eps, int64_t B, float* grad,
+                               float* scalars, float* m, float* v, int64_t t, double lr, double beta1, double beta2,
+                               double eps_adam, vms_stream stream);
 
 /* ------------------------------------------------------------------------------- fused MC run (C4a)
  * n_steps complete VAE-proposal MC steps (mcmc.py:68-130, the loop of mcmc.py:133-159) of B independent chains in ONE

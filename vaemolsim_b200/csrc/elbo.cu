@@ -437,4 +437,27 @@ vms_status vms_elbo_forward_backward(vms_elbo_plan pl, const float* theta, const
   });
 }
 
+/* One training step: ELBO forward + backward + Keras Adam (tests/test_models.py:181) on the flat buffers.  On the fused
+ * path the optimiser update rides in the kernel that sums the partial gradients (2 launches per step in all); the
+ * unfused path runs vms_elbo_forward_backward followed by vms_adam_step. */
+vms_status vms_elbo_train_step(vms_elbo_plan pl, float* theta, const float* x, const float* eps, int64_t B, float* grad,
+                               float* scalars, float* m, float* v, int64_t t, double lr, double beta1, double beta2,
+                               double eps_adam, vms_stream stream) {
+  vms_status s = check_call(pl, theta, x, eps, B);
+  if (s) return s;
+  VMS_REQUIRE(grad && m && v && t >= 1, VMS_ERR_INVALID_ARG, "elbo_train_step: NULL grad / m / v or t < 1");
+  if (pl->fused && pl->mode == 0) {
+    FusedAdam ad;
+    ad.theta = theta; ad.m = m; ad.v = v;
+    ad.lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
+    ad.one_minus_b1 = (float)(1.0 - beta1);
+    ad.one_minus_b2 = (float)(1.0 - beta2);
+    ad.eps = (float)eps_adam;
+    return fused_run(pl, theta, x, eps, B, true, nullptr, nullptr, nullptr, nullptr, grad, scalars, as_stream(stream), &ad);
+  }
+  s = vms_elbo_forward_backward(pl, theta, x, eps, B, grad, scalars, stream);
+  if (s) return s;
+  return vms_adam_step(theta, grad, 1, 1.0f, m, v, pl->off.total, t, lr, beta1, beta2, eps_adam, stream);
+}
+
 }  // extern "C"

@@ -46,55 +46,103 @@ struct FusedParams {
   int enc0W, enc0b, enc1W, enc1b, dec0W, dec0b, dec1W, dec1b;
   FBlk blk[kMaxBlocks];
   const float *theta, *x, *eps;
+  const float* pack;                // re-packed flow-block weights (prepack_kernel)
+  int pack_stride, pack_wt, pack_small;
   float *z, *logq, *logpz, *logpx;  // optional per-row outputs
   float *gpart, *spart;             // [grid][P] partial gradients, [grid][2] partial loss sums
   // shared-memory pitches and offsets (floats)
   int ldx, ldz, ldh, ldf, ldfp, ldpe, ldpd, ldc, ldrm, ldwt, sb;
   int o_xs, o_xT, o_eps, o_zR, o_zT, o_he, o_hd, o_pe, o_pd, o_u, o_lp, o_hid, o_cond, o_raw, o_W, o_Wp, o_B, o_gz,
-      o_gua, o_gub, o_scr, o_tsc;
+      o_gua, o_gub, o_scr, o_tsc, o_bar;
 };
 
 struct FusedCfg {
   FusedParams p;
   size_t smem_bytes;
   int max_grid;
-  float *gpart, *spart;
+  float *gpart, *spart, *pack;
   // optional per-launch timing of the main kernel (bench.py's roofline leg): event pairs recorded around it
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
   size_t ev_used = 0;
 };
 
-// Stage one flow block's weights into shared memory with 4-byte cp.async (rows of 3K-1 floats are not 16-byte aligned):
-//   Wst  <- hW as [k][ldrm] (transposed = false, forward) or hW^T as [c][ldwt] (transposed = true, input gradient)
-//   Bb   <- d1W [cin][fh] | d1b [fh] | hb [ldr]
-// A warp takes rows k = warp, warp + 16, ..., lanes take columns: no integer division, coalesced global reads.
-__device__ __noinline__ void stage_block(const FusedParams& p, int blk, bool transposed) {
-  extern __shared__ __align__(16) float sm[];
-  const FBlk& fb = p.blk[blk];
-  float* Wst = sm + p.o_W;
-  float* Bb = sm + p.o_B + (blk & 1) * p.sb;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* hW = p.theta + fb.off_hW;
-#pragma unroll 1
-  for (int k = warp; k < p.fh; k += FW) {
-    const float* src = hW + k * fb.ldr;
-    if (!transposed) {
-      float* dst = Wst + k * p.ldrm;
-      for (int n = lane; n < fb.ldr; n += 32) cp_async4(dst + n, src + n);
-    } else {
-      for (int n = lane; n < fb.ldr; n += 32) cp_async4(Wst + n * p.ldwt + k, src + n);
-    }
-  }
-  const int n_small = fb.cin * p.fh + p.fh;  // d1W | d1b are contiguous in theta
-  for (int e = threadIdx.x; e < n_small; e += FT) cp_async4(Bb + e, p.theta + fb.off_d1W + e);
-  for (int e = threadIdx.x; e < fb.ldr; e += FT) cp_async4(Bb + n_small + e, p.theta + fb.off_hb + e);
+// ------------------------------------------------------------------------------------------------ bulk staging
+// Flow-block weights reach shared memory as ONE bulk asynchronous copy per block (cp.async.bulk, the 1-D TMA path,
+// completion signalled on an mbarrier): a single thread issues it, nobody spends instructions on it.  The first
+// version staged with 4-byte cp.async (rows of 3K-1 floats are not 16-byte aligned in theta) -- 9,500 LDGSTS per block
+// and 12 % of the kernel's samples stalled in that loop.  Bulk copies need 16-byte aligned, 16-byte-multiple blocks,
+// so a tiny kernel first re-packs theta's flow blocks into the plan's `pack` buffer, per block:
+//   [ hW as [fh][ldrm] | hW^T as [ldr][ldwt] | d1W d1b hb (sb floats) ]     (prepack_kernel, once per step)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
 }
 
+// Issue the copy of block `blk`'s packed weights (thread 0 only; callers make sure every earlier reader of the staging
+// buffers has passed a __syncthreads()).  W <- natural or transposed heads weight, B[blk & 1] <- d1W | d1b | hb.
+__device__ __forceinline__ void stage_block(const FusedParams& p, int blk, bool transposed) {
+  if (threadIdx.x != 0) return;
+  extern __shared__ __align__(16) float sm[];
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm + p.o_bar);
+  const float* src = p.pack + (size_t)blk * p.pack_stride;
+  const unsigned wn = (unsigned)(p.fh * p.ldrm) * 4u, wt = (unsigned)(p.blk[blk].ldr * p.ldwt) * 4u, sb = (unsigned)p.sb * 4u;
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy reads of the buffers are done
+  mbar_expect_tx(bar, (transposed ? wt : wn) + sb);
+  bulk_g2s(sm + p.o_W, transposed ? src + p.pack_wt : src, transposed ? wt : wn, bar);
+  bulk_g2s(sm + p.o_B + (blk & 1) * p.sb, src + p.pack_small, sb, bar);
+}
+
+// One thread per SOURCE element of a block's [hW | hb] and [d1W | d1b]: coalesced reads of theta, two scattered
+// writes (natural + transposed layouts).  The padding columns of `pack` are zeroed once, at plan creation.
+__global__ void __launch_bounds__(256) prepack_kernel(const FusedParams p, float* __restrict__ pack) {
+  const int blk = blockIdx.y;
+  const FBlk& fb = p.blk[blk];
+  float* dst = pack + (size_t)blk * p.pack_stride;
+  const float* th = p.theta;
+  const int n_hw = p.fh * fb.ldr, n_small = fb.cin * p.fh + p.fh;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n_hw) {
+    const float v = __ldg(th + fb.off_hW + e);
+    const int k = e / fb.ldr, n = e - k * fb.ldr;
+    dst[k * p.ldrm + n] = v;
+    dst[p.pack_wt + n * p.ldwt + k] = v;
+  } else if (e < n_hw + n_small) {
+    dst[p.pack_small + (e - n_hw)] = __ldg(th + fb.off_d1W + (e - n_hw));
+  } else if (e < n_hw + n_small + fb.ldr) {
+    dst[p.pack_small + (e - n_hw)] = __ldg(th + fb.off_hb + (e - n_hw - n_small));
+  }
+}
+
+// (A 6-instruction tanh built on ex2.approx / rcp.approx was tried here: |error| 3e-7 on hid moved log p(z) by up to
+// 7e-5 on the ill-conditioned test flows -- outside the 1e-5 parity budget -- so the accurate tanhf stays.)
 // Conditioner hidden layer hid = tanh(cond d1W + d1b) of block `blk`; an empty conditioner input is ones((B,1))
 // (flows.py:184-185).  row_major = false: hidT [fh][FR] (operand of the forward GEMM);  true: hidR [FR][ldf] and the
-// row-major conditioner input condR (operands of the weight gradients).
-__device__ __noinline__ void hidden_layer(const FusedParams& p, int blk, bool row_major) {
+// row-major conditioner input condR (operands of the weight gradients).  Executed by warps [w0, w0 + nw) only, so the
+// backward pass can run it beside the spline's reverse mode (which occupies 8 of the 16 warps).
+__device__ __noinline__ void hidden_layer(const FusedParams& p, int blk, bool row_major, int w0, int nw) {
   extern __shared__ __align__(16) float sm[];
   const FBlk& fb = p.blk[blk];
   const int fh = p.fh, dz = p.dz;
@@ -102,21 +150,22 @@ __device__ __noinline__ void hidden_layer(const FusedParams& p, int blk, bool ro
   const float* Bb = sm + p.o_B + (blk & 1) * p.sb;
   const float* d1b = Bb + fb.cin * fh;
   float* hid = sm + p.o_hid;
+  const int warp = (int)(threadIdx.x >> 5) - w0, lane = threadIdx.x & 31;
+  if (warp < 0 || warp >= nw) return;
   if (!row_major) {
-    // e = j * FR + r: consecutive threads take consecutive rows
-    int j = threadIdx.x / FR;
-    const int r = threadIdx.x - j * FR;
-#pragma unroll 1
-    for (; j < fh; j += FT / FR) {
+    // a warp takes features j = warp, warp + nw, ...; lanes take the 32 rows
+    const int r = lane;
+#pragma unroll 2
+    for (int j = warp; j < fh; j += nw) {
       float a = d1b[j];
       for (int c = 0; c < fb.cin; ++c) a = fmaf(fb.nc > 0 ? uin[r * dz + fb.cs0 + c] : 1.f, Bb[c * fh + j], a);
       hid[j * FR + r] = tanhf(a);
     }
   } else {
-    // a warp takes rows r = warp, warp + 16, ...; lanes take consecutive j
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // a warp takes rows r = warp, warp + nw, ...; lanes take consecutive j
 #pragma unroll 1
-    for (int r = warp; r < FR; r += FW) {
+    for (int r = warp; r < FR; r += nw) {
+#pragma unroll 4
       for (int j = lane; j < fh; j += 32) {
         float a = d1b[j];
         for (int c = 0; c < fb.cin; ++c) a = fmaf(fb.nc > 0 ? uin[r * dz + fb.cs0 + c] : 1.f, Bb[c * fh + j], a);
@@ -220,8 +269,19 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
   float* gp = p.gpart + (size_t)blockIdx.x * p.P;
 
   // CTA-lifetime state: resident MLP weights, constant columns
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm + p.o_bar);
+  unsigned phase = 0;   // parity of the staging mbarrier: one copy batch in flight at a time, every thread waits for each
+  bool pending = false;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
   for (int i = tid; i < p.n_mlp; i += FT) cp_async4(sm + p.o_Wp + i, p.theta + i);
-  if (nb > 0) stage_block(p, nb - 1, false);
+  if (nb > 0) {
+    stage_block(p, nb - 1, false);
+    pending = true;
+  }
   for (int i = tid; i < FR * p.ldz; i += FT) zR[i] = (i % p.ldz) == dz ? 1.f : 0.f;
   for (int i = tid; i < FR * p.ldc; i += FT) sm[p.o_cond + i] = 0.f;
   float cta_kl = 0.f, cta_nll = 0.f;
@@ -247,6 +307,11 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
       sm[p.o_hd + i * ldh + H] = 1.f;
     }
     cp_async_commit_wait_all();
+    if (pending) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      pending = false;
+    }
     __syncthreads();
     // ---------------------------------------------------------------- F1: he = relu(x W + b)   (mappings.py:151-153)
     outer_gemm<8, 2, false>(p.o_xT, FR, p.o_Wp + p.enc0W, H, 1, FR, H, dx, 0, 0,
@@ -276,19 +341,23 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
     for (int i = nb - 1; i >= 0; --i) {
       const int hb = p.o_B + (i & 1) * p.sb + p.blk[i].cin * fh + fh;
       const int raw_i = p.o_raw + i * FR * ldrm;
-      hidden_layer(p, i, false);
+      hidden_layer(p, i, false, 0, FW);
       __syncthreads();
       // raw = hid hW + hb: the three Dense heads of flows.py:140-152 as one GEMM
       outer_gemm<4, 3, true>(p.o_hid, FR, p.o_W, ldrm, 1, FR, p.blk[i].ldr, fh, raw_i, ldrm, epi_store(raw_i, ldrm, hb, 0));
       __syncthreads();
       // the staging buffer is free: fetch the next block's weights (or block 0's transposed, for the backward pass)
       // while the spline runs
-      if (i > 0)
-        stage_block(p, i - 1, false);
-      else if (BWD)
-        stage_block(p, 0, true);
+      if (i > 0 || BWD) {
+        stage_block(p, i > 0 ? i - 1 : 0, i == 0);
+        pending = true;
+      }
       spline_forward(p, i);
-      cp_async_commit_wait_all();
+      if (pending) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        pending = false;
+      }
       __syncthreads();
     }
     if (tid < FR) {
@@ -321,8 +390,11 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
       }
     }
     if (!BWD) {
-      if (nb > 0 && more) stage_block(p, nb - 1, false);
       __syncthreads();
+      if (nb > 0 && more) {
+        stage_block(p, nb - 1, false);
+        pending = true;
+      }
       continue;
     }
     // ================================================================ backward
@@ -371,8 +443,11 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
 #pragma unroll 1
       for (int i = 0; i < nb; ++i) {
         const FBlk& fb = p.blk[i];
-        hidden_layer(p, i, true);
-        spline_backward(p, i, gcur, gnxt, nr, g_logpz);
+        // the spline's reverse mode occupies warps 0-7 (one octet per row); warps 8-15 recompute the hidden layer
+        if ((tid >> 5) < FW / 2)
+          spline_backward(p, i, gcur, gnxt, nr, g_logpz);
+        else
+          hidden_layer(p, i, true, FW / 2, FW / 2);
         __syncthreads();
         // [hW; hb] gradient: g[k][n] = sum_r hid[r][k] graw[r][n]   (row k = fh is the bias)
         outer_gemm<8, 3, false>(p.o_hid, p.ldf, grawR, ldrm, 1, fh + 1, fb.ldr, FR, 0, 0,
@@ -382,15 +457,19 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
                                epi_mask(2, gpre, p.ldfp, p.o_hid, p.ldf));
         __syncthreads();
         // the staging buffer is free again: next block's transposed weights, or the next tile's first forward block
-        if (i + 1 < nb)
-          stage_block(p, i + 1, true);
-        else if (more)
-          stage_block(p, nb - 1, false);
+        if (i + 1 < nb || more) {
+          stage_block(p, i + 1 < nb ? i + 1 : nb - 1, i + 1 < nb);
+          pending = true;
+        }
         // [d1W; d1b] gradient and the conditioner-input gradient
         outer_gemm<4, 1, false>(p.o_cond, p.ldc, gpre, p.ldfp, 1, fb.cin + 1, fh, FR, 0, 0,
                                 epi_grad(gp + fb.off_d1W, fh, 1, first));
         if (fb.nc > 0) thin_gemm(gpre, p.ldfp, p.o_B + (i & 1) * p.sb, 1, fh, fh, fb.nc, gnxt + fb.cs0, dz, -1, 1, p.o_tsc);
-        cp_async_commit_wait_all();
+        if (pending && i + 1 < nb) {  // (the next tile's first block is waited for at the top of the tile loop)
+          mbar_wait(bar, phase);
+          phase ^= 1;
+          pending = false;
+        }
         __syncthreads();
         const int t = gcur;
         gcur = gnxt;
@@ -427,7 +506,6 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
     }
     first = false;
   }
-  cp_async_commit_wait_all();
   if (tid == 0) {
     p.spart[2 * blockIdx.x] = cta_kl;
     p.spart[2 * blockIdx.x + 1] = cta_nll;
@@ -437,10 +515,15 @@ __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant
 // grad[i] = sum_c gpart[c][i] in a fixed order (16 partial groups per block, four independent running sums each,
 // combined in a fixed order: deterministic for a given grid), and the three loss scalars.
 constexpr int kFinGroups = 16;
+struct AdamArgs {
+  float *theta, *m, *v;  // theta == NULL: no optimiser step
+  float lr_t, one_minus_b1, one_minus_b2, eps;
+};
 __global__ void __launch_bounds__(32 * kFinGroups) fused_finish_kernel(const float* __restrict__ gpart, int n_part, int P,
                                                                        float* __restrict__ grad,
                                                                        const float* __restrict__ spart, int64_t B,
-                                                                       float klw, float* __restrict__ scalars) {
+                                                                       float klw, float* __restrict__ scalars,
+                                                                       const AdamArgs ad) {
   __shared__ float sh[kFinGroups][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   if (grad) {
@@ -466,6 +549,13 @@ __global__ void __launch_bounds__(32 * kFinGroups) fused_finish_kernel(const flo
 #pragma unroll
       for (int g = 0; g < kFinGroups; ++g) t += sh[g][lane];
       grad[i] = t;
+      if (ad.theta) {  // Keras Adam on the flat buffer, same arithmetic as adam_kernel (adam.cu)
+        const float mi = ad.m[i] + (t - ad.m[i]) * ad.one_minus_b1;
+        const float vi = ad.v[i] + (t * t - ad.v[i]) * ad.one_minus_b2;
+        ad.m[i] = mi;
+        ad.v[i] = vi;
+        ad.theta[i] = ad.theta[i] - ad.lr_t * mi / (sqrtf(vi) + ad.eps);
+      }
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && scalars) {
@@ -513,7 +603,7 @@ vms_status fused_create(vms_elbo_plan_s* pl) {
   if (max_cin > kMaxThin) { delete f; return VMS_OK; }
   p.ldx = r4(d.dx + 1); p.ldz = r4(d.dz + 1); p.ldh = (d.hidden + 1) | 1; p.ldf = r4(p.fh + 1); p.ldfp = p.fh | 1;
   p.ldpe = r4(2 * d.dz); p.ldpd = r4(2 * d.dx); p.ldc = r4(max_cin + 1); p.ldrm = r4(max_ldr);
-  p.ldwt = p.fh | 1;
+  p.ldwt = r4(p.fh);
   p.sb = r4(max_cin * p.fh + p.fh + p.ldrm);
   p.n_mlp = (int)o.dec1b + 2 * d.dx;
   int off = 0;
@@ -540,6 +630,7 @@ vms_status fused_create(vms_elbo_plan_s* pl) {
   scr = thin_fwd > scr ? thin_fwd : scr;
   p.o_tsc = take(FW * r4(d.dz > max_cin ? d.dz : max_cin) * FR);
   p.o_scr = take(scr);
+  p.o_bar = take(4);
   off += 64;  // slab reads may run a few floats past the last row of an operand
   f->smem_bytes = (size_t)off * sizeof(float);
   if (f->smem_bytes > (size_t)max_smem_optin()) { delete f; return VMS_OK; }
@@ -564,6 +655,24 @@ vms_status fused_create(vms_elbo_plan_s* pl) {
   }
   f->gpart = (float*)g;
   f->spart = (float*)s;
+  // packed flow-block weights: [hW natural | hW transposed | small], each part a multiple of 16 bytes
+  p.pack_wt = p.fh * p.ldrm;
+  p.pack_small = p.pack_wt + r4(max_ldr * p.ldwt);
+  p.pack_stride = p.pack_small + p.sb;
+  f->pack = nullptr;
+  if (d.num_blocks > 0) {
+    void* pk = nullptr;
+    if (cudaMalloc(&pk, (size_t)d.num_blocks * p.pack_stride * sizeof(float)) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(g);
+      cudaFree(s);
+      delete f;
+      set_error("elbo_plan_create: cudaMalloc of the packed-weights buffer failed");
+      return VMS_ERR_CUDA;
+    }
+    f->pack = (float*)pk;
+    cudaMemset(pk, 0, (size_t)d.num_blocks * p.pack_stride * sizeof(float));
+  }
   pl->fused = f;
   return VMS_OK;
 }
@@ -605,20 +714,27 @@ void fused_destroy(vms_elbo_plan_s* pl) {
     cudaEventDestroy(e.second);
   }
   cudaFree(pl->fused->gpart);
+  cudaFree(pl->fused->pack);
   cudaFree(pl->fused->spart);
   delete pl->fused;
   pl->fused = nullptr;
 }
 
 vms_status fused_run(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B, bool backward,
-                     float* z, float* logq, float* logpz, float* logpx, float* grad, float* scalars, cudaStream_t st) {
+                     float* z, float* logq, float* logpz, float* logpx, float* grad, float* scalars, cudaStream_t st,
+                     const FusedAdam* adam) {
   FusedCfg* f = pl->fused;
   FusedParams p = f->p;
   p.B = B;
   p.n_tiles = (int)((B + FR - 1) / FR);
   p.theta = theta; p.x = x; p.eps = eps;
   p.z = z; p.logq = logq; p.logpz = logpz; p.logpx = logpx;
-  p.gpart = f->gpart; p.spart = f->spart;
+  p.gpart = f->gpart; p.spart = f->spart; p.pack = f->pack;
+  if (p.nb > 0) {
+    const int per_blk = p.fh * p.ldrm + p.sb;  // >= source elements of any block
+    prepack_kernel<<<dim3((per_blk + 255) / 256, p.nb), 256, 0, st>>>(p, f->pack);
+    VMS_LAUNCH_CHECK("prepack_kernel");
+  }
   const int grid = p.n_tiles < f->max_grid ? p.n_tiles : f->max_grid;
   const bool timed = f->timing && f->ev_used < f->ev.size();
   if (timed) VMS_CUDA(cudaEventRecord(f->ev[f->ev_used].first, st));
@@ -630,7 +746,13 @@ vms_status fused_run(vms_elbo_plan_s* pl, const float* theta, const float* x, co
   if (timed) VMS_CUDA(cudaEventRecord(f->ev[f->ev_used++].second, st));
   float* sc = scalars ? scalars : pl->scalars;
   const int nblk = backward ? (p.P + 31) / 32 : 1;
-  fused_finish_kernel<<<nblk, 32 * kFinGroups, 0, st>>>(f->gpart, grid, p.P, backward ? grad : nullptr, f->spart, B, p.klw, sc);
+  AdamArgs ad = {};
+  if (adam && backward) {
+    ad.theta = adam->theta; ad.m = adam->m; ad.v = adam->v;
+    ad.lr_t = adam->lr_t; ad.one_minus_b1 = adam->one_minus_b1; ad.one_minus_b2 = adam->one_minus_b2; ad.eps = adam->eps;
+  }
+  fused_finish_kernel<<<nblk, 32 * kFinGroups, 0, st>>>(f->gpart, grid, p.P, backward ? grad : nullptr, f->spart, B, p.klw, sc,
+                                                        ad);
   VMS_LAUNCH_CHECK("fused_finish_kernel");
   return VMS_OK;
 }

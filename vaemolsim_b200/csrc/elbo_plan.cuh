@@ -85,8 +85,13 @@ vms_status fused_create(vms_elbo_plan_s* pl);   // sets pl->fused (or leaves NUL
 void fused_destroy(vms_elbo_plan_s* pl);
 vms_status fused_set_timing(vms_elbo_plan_s* pl, int max_launches);
 vms_status fused_kernel_ms(vms_elbo_plan_s* pl, double* total_ms, int* launches);
+struct FusedAdam {  // optimiser step folded into the fused path's finishing kernel (vms_elbo_train_step)
+  float *theta, *m, *v;
+  float lr_t, one_minus_b1, one_minus_b2, eps;
+};
 vms_status fused_run(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B, bool backward,
-                     float* z, float* logq, float* logpz, float* logpx, float* grad, float* scalars, cudaStream_t st);
+                     float* z, float* logq, float* logpz, float* logpx, float* grad, float* scalars, cudaStream_t st,
+                     const FusedAdam* adam = nullptr);
 }  // namespace vms
 
 

@@ -285,6 +285,10 @@ class FusedELBO(object):
                             opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon, c.stream)
 
     def train_step(self, x, eps, opt):
-        self.forward_backward(x, eps)
-        self.adam_step(opt)
+        """Forward + backward + Adam in one C call (`vms_elbo_train_step`: 2 kernel launches on the fused path)."""
+        c = ctx()
+        self.t += 1
+        c.lib.vms_elbo_train_step(self.handle, self.theta.ptr, x.ptr, eps.ptr, x.shape[0], self.grad.ptr, self.scalars.ptr,
+                                  self.m.ptr, self.v.ptr, self.t, opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon,
+                                  c.stream)
         return self.scalars
