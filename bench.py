@@ -56,6 +56,8 @@ def parse():
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='rows per GPU (default: the named config, 4096)')
     ap.add_argument('--no-extras', action='store_true', help='skip roofline microbenchmarks and the CPU baseline')
+    ap.add_argument('--collective', default='auto', choices=['auto', 'peer', 'nccl'],
+                    help='N > 1: fused NVLink peer-memory allreduce+Adam kernel (peer), NCCL allreduce + Adam (nccl)')
     ap.add_argument('--mc-only', action='store_true', help='development aid: run only the MC leg and print it')
     return ap.parse_args()
 
@@ -418,13 +420,30 @@ def run_b200(args, w):
     xs = [v.Tensor.from_numpy(a) for a in xs_host]
     es = [v.Tensor.from_numpy(a) for a in es_host]
     flush = v.Tensor((64 << 20, ))  # 256 MiB float32 > 126 MB L2
-    gt = ext = None
+    gt = ext = peer = None
     if world > 1:
-        gt, ext = grp.wrap_device_buffer(f.grad.ptr, f.n_params, c.stream)
+        if args.collective in ('auto', 'peer'):
+            try:
+                peer = parallel.PeerExchange(grp, f.n_params)
+            except Exception as e:  # no P2P mapping between the ranks' GPUs: NCCL path
+                if args.collective == 'peer':
+                    raise
+                sys.stderr.write('bench: peer exchange unavailable (%s); using NCCL\n' % e)
+        # all ranks must agree on the path
+        if grp.sum(1.0 if peer is not None else 0.0) != world:
+            peer = None
+        if peer is None:
+            gt, ext = grp.wrap_device_buffer(f.grad.ptr, f.n_params, c.stream)
 
     def step(i):
         if world == 1:
             f.train_step(xs[i % n_sets], es[i % n_sets], opt)  # forward + backward + Adam: 2 launches
+            return
+        if peer is not None:
+            # gradient straight into this step's slot of the exchange buffer, then ONE kernel: flags + peer reads over
+            # NVLink + rank-ordered sum + Adam
+            f.forward_backward(xs[i % n_sets], es[i % n_sets], grad_ptr=peer.next_slot())
+            peer.allreduce_adam(f, opt)
             return
         f.forward_backward(xs[i % n_sets], es[i % n_sets])
         grp.allreduce_sum_(gt, ext)  # the single data-path collective (NCCL over NVLink), in place
@@ -467,6 +486,9 @@ def run_b200(args, w):
         ed = v.Tensor.from_numpy(es_host[i % n_sets])
         if world == 1:
             f.train_step(xd, ed, opt)
+        elif peer is not None:
+            f.forward_backward(xd, ed, grad_ptr=peer.next_slot())
+            peer.allreduce_adam(f, opt)
         else:
             f.forward_backward(xd, ed)
             grp.allreduce_sum_(gt, ext)
@@ -492,6 +514,14 @@ def run_b200(args, w):
     t_clock1 = time.perf_counter()
     clocks = sampler.stop(t_clock0, t_clock1)
 
+    replicas_ok = None
+    if world > 1:
+        # replicas must hold bit-identical parameters after the run (same reduced gradient on every rank)
+        digest = float(np.frombuffer(f.theta.numpy().tobytes(), np.uint32).astype(np.uint64).sum() % (1 << 40))
+        replicas_ok = grp.max(digest) == -grp.max(-digest)
+        if peer is not None:
+            replicas_ok = replicas_ok and grp.sum(1.0 if peer.timed_out() else 0.0) == 0.0
+            peer.close()
     mc_line = None if args.no_extras else mc_bench(v, grp)
     if rank != 0:
         grp.close()
@@ -502,7 +532,9 @@ def run_b200(args, w):
         'data': 'synthetic',
         'config': {'workload': w['label'], 'global_batch': world * batch, 'params': f.n_params,
                    'parallelism': 'dp%d' % world if world > 1 else 'single',
-                   'collective': 'one NCCL allreduce(sum) of the flat gradient per step' if world > 1 else 'none',
+                   'collective': ('none' if world == 1 else
+                                  'one fused kernel per step: NVLink peer-memory gradient allreduce + Adam (csrc/peer.cu)'
+                                  if peer is not None else 'one NCCL allreduce(sum) of the flat gradient per step'),
                    'l2': 'flushed between timed steps (256 MiB memset, outside the per-step events)',
                    'timing': 'sum of per-step CUDA-event intervals on the launching stream, max over ranks',
                    'wall_s_timed_region_incl_flush': wall1 - wall0},
@@ -513,6 +545,8 @@ def run_b200(args, w):
         'gpu_launches': int(launches),
         'clocks': clocks,
     }
+    if replicas_ok is not None:
+        line['config']['replicas_bit_identical'] = bool(replicas_ok)
     if not args.no_extras:
         micro, peak, peak_kind = kernel_microbench(v, w, batch)
         peaks = {}

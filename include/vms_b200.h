@@ -317,6 +317,25 @@ vms_status vms_mc_run(vms_mc_plan plan, const float* theta, float* x, double* E,
                       int64_t B, int n_steps, unsigned long long* n_acc, uint8_t* acc_trace, float* fwd_trace,
                       float* rev_trace, double* e_new_trace, vms_stream stream);
 
+/* ------------------------------------------------------------------------------- data-parallel exchange step
+ * The single collective of data-parallel training (north_star: one gradient allreduce per step) fused with the Adam
+ * update, as ONE kernel over NVLink peer memory.  Every rank owns a buffer of vms_peer_buffer_bytes(P) bytes
+ * ([2][P] float gradient slots, double-buffered by step parity, + flags), zero-initialised, shared with the other
+ * ranks of the node through CUDA IPC (handles are exchanged by the host: torch.distributed in this repo).
+ *   step s (1, 2, ...): the rank's gradient is written into slot (s & 1) of ITS buffer (pass base + (s & 1) * P as the
+ *   `grad` of vms_elbo_forward_backward), then every rank calls vms_peer_allreduce_adam(step = s): ranks signal and
+ *   wait through flags in peer memory, each thread pulls one parameter's gradient from all world buffers over NVLink,
+ *   sums in rank order (identical on every rank), scales by grad_scale (1 / world: the loss is a batch MEAN,
+ *   losses.py:253) and applies Keras Adam (same update as vms_adam_step) to the local theta / m / v.
+ *   peer_bases: HOST array of `world` device pointers (this rank's own buffer at index `rank`).  world <= 8.      */
+size_t vms_peer_buffer_bytes(int64_t n_params);
+vms_status vms_ipc_get_handle(void* device_ptr, unsigned char handle[64]);
+vms_status vms_ipc_open_handle(const unsigned char handle[64], void** device_ptr);
+vms_status vms_ipc_close_handle(void* device_ptr);
+vms_status vms_peer_allreduce_adam(int world, int rank, void* const* peer_bases, int64_t n_params, unsigned long long step,
+                                   float grad_scale, float* theta, float* m, float* v, int64_t t, double lr, double beta1,
+                                   double beta2, double eps, float* grad_out, vms_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,12 @@ _SIGS = {
     'vms_elbo_plan_kernel_ms': (None, [c_vp, C.POINTER(c_f64), C.POINTER(c_int)]),
     'vms_elbo_train_step': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64,
                                    c_vp]),
+    'vms_peer_buffer_bytes': (c_size, [c_i64]),
+    'vms_ipc_get_handle': (None, [c_vp, c_vp]),
+    'vms_ipc_open_handle': (None, [c_vp, C.POINTER(c_vp)]),
+    'vms_ipc_close_handle': (None, [c_vp]),
+    'vms_peer_allreduce_adam': (None, [c_int, c_int, C.POINTER(c_vp), c_i64, C.c_ulonglong, c_f32, c_vp, c_vp, c_vp, c_i64,
+                                       c_f64, c_f64, c_f64, c_f64, c_vp, c_vp]),
     'vms_mc_param_count': (c_i64, [C.POINTER(McDesc)]),
     'vms_mc_plan_create': (None, [C.POINTER(McDesc), C.POINTER(c_vp)]),
     'vms_mc_plan_destroy': (None, [c_vp]),

@@ -1,0 +1,145 @@
+// peer.cu -- data-parallel training's one exchange step as ONE kernel over NVLink peer memory:
+// gradient all-reduce (sum over ranks) fused with the Keras Adam update.
+//
+// The reference never distributes; the north_star adds "a single NCCL-over-NVLink gradient allreduce per
+// step".  The gradient is 44,396 floats (177 KB): an NCCL allreduce of that size is pure latency (~15-25 us: a launch,
+// a ring / tree protocol, a second launch for Adam), so here every rank
+//   1. publishes "my gradient of step s is in my buffer" by writing s into its flag slot in EVERY peer's buffer,
+//   2. spins until all ranks' flags in its OWN buffer reach s,
+//   3. reads each parameter's gradient from all peers' buffers directly over NVLink (one-shot all-gather-reduce: each
+//      GPU pulls world x 177 KB), sums in rank order -- the same order on every rank, so replicas stay bit-identical --
+//      and applies Adam to its local theta / m / v in the same thread.
+// No host round trip, no second kernel, and the sum is deterministic.
+//
+// Buffers: each rank owns one device allocation [2][P] floats (gradient slots, double-buffered by step parity) +
+// 64 x uint64 flags, shared with the peers through CUDA IPC (vms_ipc_*; handles travel over torch.distributed, which
+// stays the plumbing).  Double buffering is what makes a single barrier per step enough: a rank overwrites slot s & 1
+// at step s + 2, after it has passed the barrier of step s + 1, which every peer can only have signalled after its own
+// step-s kernel -- the last reader of slot s & 1 -- completed.
+// One process per GPU: the kernel waits on OTHER GPUs' kernels, never on another kernel of the same GPU.
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+
+namespace vms {
+
+constexpr int kMaxPeers = 8;
+constexpr int kFlagSlots = 64;
+
+struct PeerArgs {
+  int world, rank;
+  float* base[kMaxPeers];  // every rank's buffer as mapped into THIS process ([rank] = own allocation)
+  int64_t P;
+  unsigned long long step;  // 1, 2, 3, ... (monotonic)
+  float grad_scale;
+  float *theta, *m, *v;
+  float lr_t, one_minus_b1, one_minus_b2, eps;
+  float* grad_out;  // optional: the reduced, scaled gradient [P]
+};
+
+__device__ __forceinline__ unsigned long long* flags_of(float* base, int64_t P) {
+  return reinterpret_cast<unsigned long long*>(base + 2 * P);
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(const PeerArgs a) {
+  __shared__ int ready;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      // the gradient of this step was written by the preceding kernel on this stream; make it visible system-wide,
+      // then raise my flag in every rank's buffer (including my own)
+      __threadfence_system();
+      for (int r = 0; r < a.world; ++r) {
+        volatile unsigned long long* f = flags_of(a.base[r], a.P) + a.rank;
+        *f = a.step;
+      }
+      __threadfence_system();
+    }
+    // wait for every rank's flag in MY buffer.  Bounded: a rank that never arrives (crashed peer) must not hang this GPU;
+    // after ~2 s the kernel gives up, records the failure in flag slot 32 + rank of its own buffer and carries on.
+    volatile unsigned long long* mine = flags_of(a.base[a.rank], a.P);
+    const long long t0 = clock64();
+    for (int r = 0; r < a.world; ++r) {
+      while (mine[r] < a.step) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) {
+          mine[32 + a.rank] = a.step;
+          break;
+        }
+      }
+    }
+    __threadfence_system();
+    ready = 1;
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.P) return;
+  const int64_t off = (int64_t)(a.step & 1ull) * a.P + i;
+  float g = 0.f;
+  for (int r = 0; r < a.world; ++r) {
+    // peer memory over NVLink: volatile = never served from this SM's L1 (the slot is reused every second step)
+    g += *reinterpret_cast<volatile const float*>(a.base[r] + off);
+  }
+  g *= a.grad_scale;
+  if (a.grad_out) a.grad_out[i] = g;
+  const float mi = a.m[i] + (g - a.m[i]) * a.one_minus_b1;
+  const float vi = a.v[i] + (g * g - a.v[i]) * a.one_minus_b2;
+  a.m[i] = mi;
+  a.v[i] = vi;
+  a.theta[i] = a.theta[i] - a.lr_t * mi / (sqrtf(vi) + a.eps);
+}
+
+}  // namespace vms
+
+using namespace vms;
+
+extern "C" {
+
+size_t vms_peer_buffer_bytes(int64_t n_params) { return (size_t)(2 * n_params) * sizeof(float) + kFlagSlots * sizeof(unsigned long long); }
+
+vms_status vms_ipc_get_handle(void* device_ptr, unsigned char handle[64]) {
+  VMS_REQUIRE(device_ptr && handle, VMS_ERR_INVALID_ARG, "ipc_get_handle: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  VMS_CUDA(cudaIpcGetMemHandle(&h, device_ptr));
+  memcpy(handle, &h, 64);
+  return VMS_OK;
+}
+
+vms_status vms_ipc_open_handle(const unsigned char handle[64], void** device_ptr) {
+  VMS_REQUIRE(handle && device_ptr, VMS_ERR_INVALID_ARG, "ipc_open_handle: NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  VMS_CUDA(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return VMS_OK;
+}
+
+vms_status vms_ipc_close_handle(void* device_ptr) {
+  if (!device_ptr) return VMS_OK;
+  VMS_CUDA(cudaIpcCloseMemHandle(device_ptr));
+  return VMS_OK;
+}
+
+vms_status vms_peer_allreduce_adam(int world, int rank, void* const* peer_bases, int64_t n_params, unsigned long long step,
+                                   float grad_scale, float* theta, float* m, float* v, int64_t t, double lr, double beta1,
+                                   double beta2, double eps, float* grad_out, vms_stream stream) {
+  VMS_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, VMS_ERR_INVALID_ARG,
+              "peer_allreduce_adam: world must be in [1, %d] and 0 <= rank < world", kMaxPeers);
+  VMS_REQUIRE(peer_bases && theta && m && v && n_params >= 1 && step >= 1 && t >= 1, VMS_ERR_INVALID_ARG,
+              "peer_allreduce_adam: bad arguments");
+  PeerArgs a = {};
+  a.world = world; a.rank = rank; a.P = n_params; a.step = step; a.grad_scale = grad_scale;
+  for (int r = 0; r < world; ++r) {
+    VMS_REQUIRE(peer_bases[r], VMS_ERR_INVALID_ARG, "peer_allreduce_adam: NULL peer buffer %d", r);
+    a.base[r] = (float*)peer_bases[r];
+  }
+  a.theta = theta; a.m = m; a.v = v; a.grad_out = grad_out;
+  a.lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
+  a.one_minus_b1 = (float)(1.0 - beta1);
+  a.one_minus_b2 = (float)(1.0 - beta2);
+  a.eps = (float)eps;
+  peer_allreduce_adam_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, as_stream(stream)>>>(a);
+  VMS_LAUNCH_CHECK("peer_allreduce_adam_kernel");
+  return VMS_OK;
+}
+
+}  // extern "C"

@@ -271,11 +271,12 @@ class FusedELBO(object):
                                P_(out['logpz']), P_(out['logpx']), out['scalars'].ptr, c.stream)
         return out
 
-    def forward_backward(self, x, eps):
-        """Writes the flat gradient into self.grad and {loss, nll, kl} into self.scalars (device)."""
+    def forward_backward(self, x, eps, grad_ptr=None):
+        """Writes the flat gradient into self.grad (or to the device address `grad_ptr`, e.g. a slot of the peer
+        exchange buffer) and {loss, nll, kl} into self.scalars (device)."""
         c = ctx()
-        c.lib.vms_elbo_forward_backward(self.handle, self.theta.ptr, x.ptr, eps.ptr, x.shape[0], self.grad.ptr,
-                                        self.scalars.ptr, c.stream)
+        c.lib.vms_elbo_forward_backward(self.handle, self.theta.ptr, x.ptr, eps.ptr, x.shape[0],
+                                        self.grad.ptr if grad_ptr is None else grad_ptr, self.scalars.ptr, c.stream)
         return self.scalars
 
     def adam_step(self, opt, grad_scale=1.0):

@@ -103,3 +103,72 @@ class Group(object):
     def close(self):
         if self.world > 1 and self.dist.is_initialized():
             self.dist.destroy_process_group()
+
+
+class PeerExchange(object):
+    """The fused gradient-allreduce + Adam step over NVLink peer memory (`csrc/peer.cu`, `vms_peer_allreduce_adam`).
+
+    Every rank allocates one buffer (two gradient slots + flags), the CUDA IPC handles travel through
+    `torch.distributed.all_gather_object` (plumbing), and from then on a training step's exchange is a single kernel per
+    rank with no host involvement.  Construction raises if peer mapping is unavailable; callers fall back to
+    `Group.allreduce_sum_` (NCCL) + `vms_adam_step`."""
+
+    def __init__(self, group, n_params):
+        import ctypes as C
+        from . import _abi
+        self.C, self.group, self.n = C, group, int(n_params)
+        self.ctx = _abi.ctx()
+        lib = self.ctx.lib
+        self.world, self.rank = group.world, group.rank
+        if self.world > 8:
+            raise NotImplementedError('PeerExchange: at most 8 ranks (one NVSwitch node)')
+        nbytes = int(lib.vms_peer_buffer_bytes(self.n))
+        self.buf = _abi.Tensor((nbytes // 4, ))
+        lib.vms_memset(self.buf.ptr, 0, nbytes, self.ctx.stream)
+        self.ctx.synchronize()
+        handle = (C.c_ubyte * 64)()
+        lib.vms_ipc_get_handle(self.buf.ptr, handle)
+        handles = [None] * self.world
+        if self.world > 1:
+            group.dist.all_gather_object(handles, bytes(handle))
+        self.opened = []
+        bases = (C.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                bases[r] = self.buf.ptr
+            else:
+                p = C.c_void_p()
+                lib.vms_ipc_open_handle((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p))
+                self.opened.append(p.value)
+                bases[r] = p.value
+        self.bases = bases
+        self.step = 0
+        group.barrier()  # every buffer is zeroed and mapped before anyone signals
+
+    def next_slot(self):
+        """Device pointer the NEXT step's local gradient must be written to."""
+        return self.buf.ptr + 4 * self.n * ((self.step + 1) & 1)
+
+    def allreduce_adam(self, fused, opt, grad_out=None):
+        """Sum the ranks' gradients of this step (slot `next_slot()` of every buffer), scale by 1 / world, Adam-update
+        `fused.theta / m / v` in place.  All ranks must call it once per step."""
+        self.step += 1
+        fused.t += 1
+        self.ctx.lib.vms_peer_allreduce_adam(self.world, self.rank, self.bases, self.n, self.step, 1.0 / self.world,
+                                             fused.theta.ptr, fused.m.ptr, fused.v.ptr, fused.t, opt.learning_rate,
+                                             opt.beta_1, opt.beta_2, opt.epsilon, None if grad_out is None else grad_out.ptr,
+                                             self.ctx.stream)
+
+    def timed_out(self):
+        """True if any exchange on this rank gave up waiting for a peer (the kernel's 2 s bound): results are invalid."""
+        import numpy as np
+        self.ctx.synchronize()
+        flags = self.buf.numpy().view(np.uint64)[self.n:self.n + 64]   # the flags follow the 2 n gradient floats
+        return bool(flags[32 + self.rank] != 0)
+
+    def close(self):
+        self.ctx.synchronize()
+        self.group.barrier()
+        for p in self.opened:
+            self.ctx.lib.vms_ipc_close_handle(p)
+        self.opened = []
