@@ -491,6 +491,12 @@ def test_fused_mc_multi_step_equals_single_steps_and_op_by_op_path(vms):
     x2a, _ = c2.run_fused(x0[:600], n_steps=5, log_u_dev=v.Tensor.from_numpy(np.ascontiguousarray(lo[:, :600])))
     assert np.array_equal(x1[:600], x2a)
     assert 0.0 < c1.acceptance_rate <= 1.0
+    # long runs through the public API are pipelined in chunks of 10 steps (host PCG64 || device): same result as one launch
+    c3, c4 = v.mcmc.MCMC(model, energy, random_seed=3), v.mcmc.MCMC(model, energy, random_seed=3)
+    x3, e3 = c3.run(x0, n_steps=25)
+    lo25 = np.log(np.random.default_rng(3).random(size=(25, B)))
+    x4, e4 = c4.run_fused(x0, n_steps=25, log_u_dev=v.Tensor.from_numpy(lo25))
+    assert np.array_equal(x3, x4) and np.array_equal(e3, e4) and c3._num_acc == c4._num_acc
     # op-by-op path on the same first step: same six log-probabilities
     z1, lq1 = model.encoder(v.as_tensor(x0)).sample_with_noise(v.as_tensor(noise[0, :, :2]))
     assert_close(lq1.numpy() + model.prior(z1).log_prob(v.as_tensor(noise[0, :, 2:4])).numpy() +

@@ -102,18 +102,34 @@ class MCMC(object):
             e, valid = Tensor((B, ), np.float64), 0
         else:
             e, valid = as_tensor(np.asarray(energies, np.float64), dtype=np.float64), 1
-        if log_u_dev is None:
-            log_u_dev = Tensor.from_numpy(np.log(self._rng.random(size=(n_steps, B))))  # mcmc.py:119, step by step
         nz = None if noise is None else Tensor.from_numpy(np.ascontiguousarray(noise, np.float32))
-        tr = {}
-        if trace:
-            tr = dict(acc=Tensor((n_steps, B), np.uint8), fwd=Tensor((n_steps, B)), rev=Tensor((n_steps, B)),
-                      e_new=Tensor((n_steps, B), np.float64), log_u=log_u_dev)
         P_ = lambda t: None if t is None else t.ptr
         before = int(fp['n_acc'].numpy()[0]) if configs_dev is None else None
-        c.lib.vms_mc_run(fp['handle'], f.theta.ptr, x.ptr, e.ptr, valid, P_(nz), self._noise_seed, self._step0,
-                         log_u_dev.ptr, fp['means'].ptr, B, n_steps, fp['n_acc'].ptr, P_(tr.get('acc')), P_(tr.get('fwd')),
-                         P_(tr.get('rev')), P_(tr.get('e_new')), c.stream)
+        tr = {}
+        chunk = 10
+        if log_u_dev is None and nz is None and not trace and n_steps > chunk:
+            # pipeline: the host draws / logs the uniforms of the next `chunk` steps (mcmc.py:119; ONE sequential PCG64
+            # stream, so it cannot be parallelised) while the device runs the previous chunk's launch
+            keep = []
+            for s0 in range(0, n_steps, chunk):
+                ns = min(chunk, n_steps - s0)
+                lu = Tensor.from_numpy(np.log(self._rng.random(size=(ns, B))))
+                keep.append(lu)  # stays alive until the stream has consumed it
+                c.lib.vms_mc_run(fp['handle'], f.theta.ptr, x.ptr, e.ptr, valid, None, self._noise_seed,
+                                 self._step0 + s0, lu.ptr, fp['means'].ptr, B, ns, fp['n_acc'].ptr, None, None, None, None,
+                                 c.stream)
+                valid = 1
+            c.synchronize()
+            del keep
+        else:
+            if log_u_dev is None:
+                log_u_dev = Tensor.from_numpy(np.log(self._rng.random(size=(n_steps, B))))  # mcmc.py:119, step by step
+            if trace:
+                tr = dict(acc=Tensor((n_steps, B), np.uint8), fwd=Tensor((n_steps, B)), rev=Tensor((n_steps, B)),
+                          e_new=Tensor((n_steps, B), np.float64), log_u=log_u_dev)
+            c.lib.vms_mc_run(fp['handle'], f.theta.ptr, x.ptr, e.ptr, valid, P_(nz), self._noise_seed, self._step0,
+                             log_u_dev.ptr, fp['means'].ptr, B, n_steps, fp['n_acc'].ptr, P_(tr.get('acc')),
+                             P_(tr.get('fwd')), P_(tr.get('rev')), P_(tr.get('e_new')), c.stream)
         self._step0 += n_steps
         self._num_trials += B * n_steps
         if configs_dev is not None:
