@@ -446,7 +446,7 @@ def run_b200(args, w):
             peer.allreduce_adam(f, opt)
             return
         f.forward_backward(xs[i % n_sets], es[i % n_sets])
-        grp.allreduce_sum_(gt, ext)  # the single data-path collective (NCCL over NVLink), in place
+        grp.allreduce_sum_(gt, host_sync=c.synchronize)  # fallback: NCCL allreduce, host-synchronised
         f.adam_step(opt, grad_scale=1.0 / world)
 
     sampler = ClockSampler(c.device)
@@ -491,7 +491,7 @@ def run_b200(args, w):
             peer.allreduce_adam(f, opt)
         else:
             f.forward_backward(xd, ed)
-            grp.allreduce_sum_(gt, ext)
+            grp.allreduce_sum_(gt, host_sync=c.synchronize)
             f.adam_step(opt, grad_scale=1.0 / world)
         return f.scalars.numpy()  # D2H of {loss, nll, kl}: synchronises the step
 

@@ -83,14 +83,18 @@ class Group(object):
         ext = torch.cuda.ExternalStream(int(stream), device='cuda:%d' % self.local_rank)
         return t, ext
 
-    def allreduce_sum_(self, tensor, ext_stream=None):
+    def allreduce_sum_(self, tensor, ext_stream=None, host_sync=None):
+        """NCCL sum-allreduce of a wrapped device buffer.  This is the FALLBACK exchange (the product path is
+        `PeerExchange`); it brackets the collective with host synchronisation of both streams: enqueueing NCCL on the
+        library's own non-blocking stream worked at 2 ranks but never returned at 4 on the test box, and a
+        fallback must above all terminate."""
         if self.world == 1:
             return
-        if ext_stream is not None:
-            with self.torch.cuda.stream(ext_stream):
-                self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM)
-        else:
-            self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM)
+        if host_sync is not None:
+            host_sync()                                   # the library stream has produced the gradient
+        self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM)
+        if self.backend == 'nccl':
+            self.torch.cuda.current_stream().synchronize()    # ... and NCCL has reduced it before the library reads it
 
     def allreduce_sum_numpy_(self, array):
         """Host (gloo) variant used by the CPU tests of the sharding logic."""
