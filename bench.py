@@ -391,6 +391,30 @@ def mc_bench(v, grp, reps=3):
 
 
 
+def large_batch_leg(v, w, opt, batch=262144, steps=5):
+    """C5's single-GPU shard (BASELINE.json configs[4]: global batch 262,144): the same training step at a batch that keeps
+    every CTA of the persistent kernel busy for 55+ tiles.  Device-resident inputs, CUDA events."""
+    c = v._abi.ctx()
+    model = build_model(v, w, batch)
+    f = model.fused(batch)
+    rng = np.random.default_rng(77)
+    x = v.Tensor.from_numpy(rng.standard_normal((batch, w['dx']), dtype=np.float32))
+    e = v.Tensor.from_numpy(rng.standard_normal((batch, w['dz']), dtype=np.float32))
+    for _ in range(2):
+        f.train_step(x, e, opt)
+    ev = Events(c, 1)
+    c.synchronize()
+    ev.record(0)
+    for _ in range(steps):
+        f.train_step(x, e, opt)
+    ev.record(1)
+    c.synchronize()
+    ms = ev.elapsed_ms(0, 1) / steps
+    return {'workload': 'C5 shard: same model, batch %d on one GPU' % batch, 'ms_per_step': ms,
+            'configs_per_s': batch / (ms * 1e-3),
+            'tflops_fp32': batch * (259200 if w['prior'] != 'normal' else 28800) / (ms * 1e-3) / 1e12}
+
+
 def run_b200(args, w):
     import vaemolsim_b200 as v
     from vaemolsim_b200 import parallel
@@ -579,6 +603,7 @@ def run_b200(args, w):
             'normal_log_prob@stream': micro['normal_log_prob@stream']['frac'],
             'dist_select@C3': micro['dist_select@C3']['frac']}
         line['kernels'] = micro
+        line['large_batch'] = large_batch_leg(v, w, opt)
         line['mc'] = mc_line
         line['mc']['cpu_baseline'] = mc_cpu_baseline()
         rows = batch

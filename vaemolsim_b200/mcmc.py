@@ -110,17 +110,21 @@ class MCMC(object):
         if log_u_dev is None and nz is None and not trace and n_steps > chunk:
             # pipeline: the host draws / logs the uniforms of the next `chunk` steps (mcmc.py:119; ONE sequential PCG64
             # stream, so it cannot be parallelised) while the device runs the previous chunk's launch
-            keep = []
-            for s0 in range(0, n_steps, chunk):
-                ns = min(chunk, n_steps - s0)
-                lu = Tensor.from_numpy(np.log(self._rng.random(size=(ns, B))))
-                keep.append(lu)  # stays alive until the stream has consumed it
+            host, dev, evs = self._uniform_buffers(chunk, B)
+            for k, s0 in enumerate(range(0, n_steps, chunk)):
+                ns, i = min(chunk, n_steps - s0), k & 1
+                if k >= 2:
+                    c.lib.vms_event_synchronize(evs[i])  # the upload that last used this pinned buffer has finished
+                h = host[i][:ns]
+                self._rng.random(out=h)
+                np.log(h, out=h)
+                c.lib.vms_memcpy_h2d(dev[i].ptr, h.ctypes.data, ns * B * 8, c.stream)  # pinned => truly asynchronous
+                c.lib.vms_event_record(evs[i], c.stream)
                 c.lib.vms_mc_run(fp['handle'], f.theta.ptr, x.ptr, e.ptr, valid, None, self._noise_seed,
-                                 self._step0 + s0, lu.ptr, fp['means'].ptr, B, ns, fp['n_acc'].ptr, None, None, None, None,
-                                 c.stream)
+                                 self._step0 + s0, dev[i].ptr, fp['means'].ptr, B, ns, fp['n_acc'].ptr, None, None, None,
+                                 None, c.stream)
                 valid = 1
             c.synchronize()
-            del keep
         else:
             if log_u_dev is None:
                 log_u_dev = Tensor.from_numpy(np.log(self._rng.random(size=(n_steps, B))))  # mcmc.py:119, step by step
@@ -137,6 +141,23 @@ class MCMC(object):
         self._num_acc += float(int(fp['n_acc'].numpy()[0]) - before)
         self._last_trace = {k: t.numpy() for k, t in tr.items()}
         return x.numpy().reshape(configs.shape), e.numpy()
+
+    def _uniform_buffers(self, chunk, B):
+        """Two pinned host buffers + two device buffers + two events for the pipelined uniform stream of `run`."""
+        if getattr(self, '_ub_key', None) != (chunk, B):
+            lib = ctx().lib
+            host, dev, evs = [], [], []
+            for _ in range(2):
+                p = C.c_void_p()
+                lib.vms_malloc_host(C.byref(p), chunk * B * 8)
+                buf = (C.c_byte * (chunk * B * 8)).from_address(p.value)
+                host.append(np.frombuffer(buf, dtype=np.float64).reshape(chunk, B))
+                dev.append(Tensor((chunk, B), np.float64))
+                ev = C.c_void_p()
+                lib.vms_event_create(C.byref(ev))
+                evs.append(ev.value)
+            self._ub_key, self._ub = (chunk, B), (host, dev, evs)
+        return self._ub
 
     def sync_counters(self):
         """Fold the device acceptance counter into `_num_acc` after device-resident `run_fused` calls."""
