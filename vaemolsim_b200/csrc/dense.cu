@@ -247,6 +247,10 @@ vms_status vms_dense_forward(const float* x, int64_t ld_x, const float* W, const
               "dense_forward: conditional_input missing");
   VMS_REQUIRE(x != nullptr || K == 1, VMS_ERR_INVALID_ARG, "dense_forward: NULL x is only valid for the ones input (K=1)");
   if (B == 0) return VMS_OK;
+  if (C == 0 && x != nullptr) {  // large batches: tcgen05 3xTF32 GEMM (gemm_tc.cu); returns false when it does not apply
+    vms_status s = VMS_OK;
+    if (dense_forward_tc_try(x, ld_x, W, b, B, K, N, act, out, ld_out, as_stream(stream), &s)) return s;
+  }
   RowTileParams p = {};
   p.M = (int)B; p.N = N; p.K = K;
   p.A = x; p.lda = ld_x; p.a_ones = (x == nullptr);
