@@ -196,6 +196,37 @@ def test_dense_forward_backward(vms, B, K, N, act):
     assert_close(gb.numpy(), gpre.sum(0), rtol=1e-5, atol=2e-6 * sc, what='dense g_b')
 
 
+@pytest.mark.parametrize('B,K,N,act,pad', [(16384, 100, 95, 0, 0), (10001, 100, 95, 2, 0), (20000, 36, 48, 1, 5),
+                                           (9000, 64, 128, 0, 0)])
+def test_dense_forward_tensor_core_path(vms, B, K, N, act, pad):
+    """Large batches route to the tcgen05 3 x TF32 GEMM (csrc/gemm_tc.cu): float32-grade parity with the float64
+    product (the TF32 split keeps 22 mantissa bits; the TMEM accumulation adds ~5e-6 of the dot product's scale), a
+    ragged last tile, padded K / N, a strided output, and agreement with the FFMA kernel on a small-batch slice."""
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(B + K + N)
+    x = rng.normal(size=(B, K)).astype(np.float32)
+    W = (rng.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    dx, dW, db = T(v, x), T(v, W), T(v, b)
+    ldo = N + pad
+    out = v.Tensor.zeros((B, ldo))
+    before = v._abi.launch_count()
+    c.lib.vms_dense_forward(dx.ptr, K, dW.ptr, db.ptr, B, K, N, act, None, 0, None, 0, out.ptr, ldo, c.stream)
+    assert v._abi.launch_count() - before == 1
+    got = out.numpy()
+    pre = x.astype(np.float64) @ W.astype(np.float64) + b
+    want = [pre, np.maximum(pre, 0), np.tanh(pre)][act]
+    scale = np.sqrt((x.astype(np.float64)**2) @ (W.astype(np.float64)**2))   # magnitude of the terms of each dot product
+    assert np.all(np.abs(got[:, :N] - want) <= 1e-5 * np.abs(want) + 8e-6 * scale + 1e-6), np.abs(got[:, :N] - want).max()
+    if pad:
+        assert np.all(got[:, N:] == 0)   # the strided form must not touch the padding columns
+    # the FFMA kernel (small-batch path) on the first rows gives the same numbers to float32 accuracy
+    small = v.Tensor((1000, N))
+    c.lib.vms_dense_forward(dx.ptr, K, dW.ptr, db.ptr, 1000, K, N, act, None, 0, None, 0, small.ptr, N, c.stream)
+    assert_close(got[:1000, :N], small.numpy(), rtol=2e-5, atol=2e-5, what='tcgen05 vs FFMA dense forward')
+
+
 def test_dense_ones_input_and_conditional(vms):
     v = vms
     c = v._abi.ctx()

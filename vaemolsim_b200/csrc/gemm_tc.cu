@@ -12,13 +12,13 @@
 // representable) and the product is accumulated as a_lo b_hi + a_hi b_lo + a_hi b_hi in the float32 TMEM
 // accumulator: the dropped a_lo b_lo term is 2^-22 relative.  Three MMAs per k-step, ~1e-6 relative error.
 //
-// Structure (one CTA per SM, 128 threads, persistent over 128-row tiles):
+// Structure (one CTA per SM, 256 threads, persistent over 128-row tiles):
 //   * W is split once per CTA into shared memory (B operand, N x K "K-major", no swizzle: core matrices of 8 rows x 16
 //     bytes, 128 bytes apart along N, (Np/8) * 128 bytes apart along K);
-//   * per tile, each thread loads its row of x with 16-byte loads, splits it and writes hi / lo in the same canonical
+//   * per tile, two threads per row load x with 16-byte loads (all loads first, registers), split it and writes hi / lo in the same canonical
 //     layout (A operand, 128 x K); fence.proxy.async hands the tile to the tensor core;
 //   * ONE thread issues the 3 * K/8 tcgen05.mma (M = 128, N = Np, K = 8) and commits them to an mbarrier;
-//   * the four warps read their 32 TMEM lanes (= rows) with tcgen05.ld 32x32b, add bias / apply the activation, stage
+//   * the eight warps read their TMEM lane quarter (= 32 rows, alternate 16-column chunks) with tcgen05.ld 32x32b, add bias / apply the activation, stage
 //     the tile in shared memory and write it out as ONE contiguous, fully coalesced block (the tile is contiguous in a
 //     row-major [B, N] output).
 // This first version is not pipelined (load -> MMA -> epilogue per tile are serial inside a CTA); the 148 CTAs overlap
@@ -32,7 +32,8 @@ namespace vms {
 namespace {
 
 constexpr int TM = 128;     // rows per tile = UMMA M
-constexpr int kMaxKc = 32;  // 16-byte chunks of one x row held in registers (K <= 128)
+constexpr int TT = 256;     // threads per CTA: two threads per row for the loads, two warps per TMEM lane quarter
+constexpr int kMaxKc = 16;  // 16-byte chunks of one x row held in registers PER THREAD (two threads share a row: K <= 128)
 
 struct TcParams {
   const float* x; int64_t ld_x;
@@ -75,20 +76,17 @@ __device__ __forceinline__ void mma_tf32(unsigned tmem_d, unsigned long long da,
       : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
-  unsigned r[32];
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+  unsigned r[16];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 __device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned phase) {
@@ -108,7 +106,7 @@ __device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned phase) {
 // element (row, k) of an operand with `rows` rows in the canonical K-major no-swizzle layout (float index)
 __device__ __forceinline__ int canon(int row, int k, int rows) { return ((k >> 2) * rows + row) * 4 + (k & 3); }
 
-__global__ void __launch_bounds__(TM, 1) dense_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(TT, 1) dense_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) float sm[];
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ unsigned tmem_base_s;
@@ -131,7 +129,7 @@ __global__ void __launch_bounds__(TM, 1) dense_tc_kernel(const TcParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   // B operand: W[k][n] -> (n, k) K-major, split, zero padding up to (Np, Kp)
-  for (int e = tid; e < Np * Kp; e += TM) {
+  for (int e = tid; e < Np * Kp; e += TT) {
     const int k = e / Np, n = e - k * Np;
     const float w = (k < K && n < N) ? __ldg(p.W + (size_t)k * N + n) : 0.f;
     const float hi = tf32_rna(w);
@@ -157,31 +155,34 @@ __global__ void __launch_bounds__(TM, 1) dense_tc_kernel(const TcParams p) {
     {
       // all loads first (up to kMaxKc 16-byte loads in flight per thread: the first version loaded, converted and stored
       // one chunk at a time and spent 20 of its 25 us per tile waiting on HBM latency), then convert + store
-      const int r = tid;
+      const int r = tid & (TM - 1), half = tid >> 7;
       const float* xr = p.x + (row0 + r) * p.ld_x;
       const bool ok = r < nr;
-      const int nkc = Kp / 4;
+      const int nkc_all = Kp / 4, per = (nkc_all + 1) / 2;
+      const int kc0 = half * per, nkc = min(per, nkc_all - kc0);  // this thread's chunks: [kc0, kc0 + nkc)
       float4 v[kMaxKc];
 #pragma unroll
-      for (int kc = 0; kc < kMaxKc; ++kc) {
-        v[kc] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kc < nkc && ok) {
+      for (int i = 0; i < kMaxKc; ++i) {
+        const int kc = kc0 + i;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nkc && ok) {
           if (4 * kc + 3 < K) {
-            v[kc] = __ldg(reinterpret_cast<const float4*>(xr + 4 * kc));
+            v[i] = __ldg(reinterpret_cast<const float4*>(xr + 4 * kc));
           } else {
-            if (4 * kc < K) v[kc].x = __ldg(xr + 4 * kc);
-            if (4 * kc + 1 < K) v[kc].y = __ldg(xr + 4 * kc + 1);
-            if (4 * kc + 2 < K) v[kc].z = __ldg(xr + 4 * kc + 2);
+            if (4 * kc < K) v[i].x = __ldg(xr + 4 * kc);
+            if (4 * kc + 1 < K) v[i].y = __ldg(xr + 4 * kc + 1);
+            if (4 * kc + 2 < K) v[i].z = __ldg(xr + 4 * kc + 2);
           }
         }
       }
 #pragma unroll
-      for (int kc = 0; kc < kMaxKc; ++kc) {
-        if (kc < nkc) {
+      for (int i = 0; i < kMaxKc; ++i) {
+        if (i < nkc) {
+          const int kc = kc0 + i;
           float4 h, l;
-          h.x = tf32_rna(v[kc].x); h.y = tf32_rna(v[kc].y); h.z = tf32_rna(v[kc].z); h.w = tf32_rna(v[kc].w);
-          l.x = tf32_rna(v[kc].x - h.x); l.y = tf32_rna(v[kc].y - h.y);
-          l.z = tf32_rna(v[kc].z - h.z); l.w = tf32_rna(v[kc].w - h.w);
+          h.x = tf32_rna(v[i].x); h.y = tf32_rna(v[i].y); h.z = tf32_rna(v[i].z); h.w = tf32_rna(v[i].w);
+          l.x = tf32_rna(v[i].x - h.x); l.y = tf32_rna(v[i].y - h.y);
+          l.z = tf32_rna(v[i].z - h.z); l.w = tf32_rna(v[i].w - h.w);
           *reinterpret_cast<float4*>(a_hi + (kc * TM + r) * 4) = h;
           *reinterpret_cast<float4*>(a_lo + (kc * TM + r) * 4) = l;
         }
@@ -210,12 +211,13 @@ __global__ void __launch_bounds__(TM, 1) dense_tc_kernel(const TcParams p) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     // ---- epilogue: warp w owns TMEM lanes 32 w .. 32 w + 31 = tile rows; 32 columns per tcgen05.ld
     {
-      const int r = 32 * warp + lane;
-      for (int c0 = 0; c0 < Np; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_d + ((unsigned)(32 * warp) << 16) + (unsigned)c0, v);
+      // warps w and w + 4 share TMEM lane quarter w & 3 (rows 32 (w & 3) ..) and take alternate 16-column chunks
+      const int q = warp & 3, r = 32 * q + lane;
+      for (int c0 = 16 * (warp >> 2); c0 < Np; c0 += 32) {
+        float v[16];
+        tmem_ld16(tmem_d + ((unsigned)(32 * q) << 16) + (unsigned)c0, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
           const int n = c0 + i;
           if (n < N) {
             float y = v[i] + (p.bias ? __ldg(p.bias + n) : 0.f);
@@ -234,14 +236,14 @@ __global__ void __launch_bounds__(TM, 1) dense_tc_kernel(const TcParams p) {
       const int total = nr * N;
       if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
         const int t4 = total / 4;
-        for (int i = tid; i < t4; i += TM)
+        for (int i = tid; i < t4; i += TT)
           reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_out)[i];
-        for (int i = 4 * t4 + tid; i < total; i += TM) dst[i] = s_out[i];
+        for (int i = 4 * t4 + tid; i < total; i += TT) dst[i] = s_out[i];
       } else {
-        for (int i = tid; i < total; i += TM) dst[i] = s_out[i];
+        for (int i = tid; i < total; i += TT) dst[i] = s_out[i];
       }
     } else {
-      for (int i = tid; i < nr * N; i += TM) {
+      for (int i = tid; i < nr * N; i += TT) {
         const int r = i / N, n = i - r * N;
         p.out[(row0 + r) * p.ld_out + n] = s_out[i];
       }
@@ -266,7 +268,7 @@ bool dense_forward_tc_try(const float* x, int64_t ld_x, const float* W, const fl
   }
   if (disabled) return false;
   if (B < 8192 || K < 16 || N < 16 || x == nullptr) return false;  // below ~64 tiles the FFMA kernel is faster
-  if (K > 4 * kMaxKc) return false;
+  if (K > 8 * kMaxKc) return false;
   if (K % 4 != 0 || ld_x % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15u) != 0) return false;
   const int Kp = (K + 7) & ~7, Np = (N + 15) & ~15;
   if (Np > 256) return false;
@@ -284,7 +286,7 @@ bool dense_forward_tc_try(const float* x, int64_t ld_x, const float* W, const fl
   }
   const int64_t n_tiles = (B + TM - 1) / TM;
   const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-  dense_tc_kernel<<<grid, TM, smem, st>>>(p);
+  dense_tc_kernel<<<grid, TT, smem, st>>>(p);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     set_error("launch of dense_tc_kernel failed: %s", cudaGetErrorString(le));
