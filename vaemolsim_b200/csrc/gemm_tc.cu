@@ -46,10 +46,10 @@ struct TcParams {
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// round-to-nearest (ties away) to TF32's 10 mantissa bits -- what cvt.rna.tf32.f32 does for finite values -- with two
+// integer instructions: ncu showed cvt.rna.tf32 throttling on its (slow) conversion pipe, 14 % of the kernel's samples
 __device__ __forceinline__ float tf32_rna(float x) {
-  unsigned r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE ("interleave"), version 1 (Blackwell)
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(TT, 1) dense_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) float sm[];
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ unsigned tmem_base_s;
+  __shared__ float s_bias[256];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Kp = p.Kp, Np = p.Np, K = p.K, N = p.N;
   float* a_hi = sm;                      // [Kp/4][128][4]
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(TT, 1) dense_tc_kernel(const TcParams p) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  for (int n = tid; n < Np; n += TT) s_bias[n] = (p.bias && n < N) ? __ldg(p.bias + n) : 0.f;
   // B operand: W[k][n] -> (n, k) K-major, split, zero padding up to (Np, Kp)
   for (int e = tid; e < Np * Kp; e += TT) {
     const int k = e / Np, n = e - k * Np;
@@ -147,45 +149,48 @@ __global__ void __launch_bounds__(TT, 1) dense_tc_kernel(const TcParams p) {
   unsigned phase = 0;
 
   const int64_t n_tiles = (p.B + TM - 1) / TM;
+  // A-tile loads: two threads per row, each holds its half of the row in registers (all loads issued before any use).
+  // The loads of tile i + 1 are issued right after tile i's MMAs, so HBM latency hides behind the tensor core and the
+  // epilogue (software pipelining through registers: shared memory has no room for a second A stage).
+  const int lr = tid & (TM - 1), half = tid >> 7;
+  const int nkc_all = Kp / 4, per = (nkc_all + 1) / 2;
+  const int kc0 = half * per, nkc = min(per, nkc_all - kc0);  // this thread's chunks: [kc0, kc0 + nkc)
+  float4 v[kMaxKc];
+  auto load_rows = [&](int64_t t) {
+    const int64_t r0 = t * TM;
+    const bool ok = t < n_tiles && r0 + lr < p.B;
+    const float* xr = p.x + (r0 + lr) * p.ld_x;
+#pragma unroll
+    for (int i = 0; i < kMaxKc; ++i) {
+      const int kc = kc0 + i;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < nkc && ok) {
+        if (4 * kc + 3 < K) {
+          v[i] = __ldg(reinterpret_cast<const float4*>(xr + 4 * kc));
+        } else {
+          if (4 * kc < K) v[i].x = __ldg(xr + 4 * kc);
+          if (4 * kc + 1 < K) v[i].y = __ldg(xr + 4 * kc + 1);
+          if (4 * kc + 2 < K) v[i].z = __ldg(xr + 4 * kc + 2);
+        }
+      }
+    }
+  };
+  load_rows(blockIdx.x);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * TM;
     const int nr = (int)min((int64_t)TM, p.B - row0);
-    // ---- A tile: thread r loads row r (16-byte loads), splits, stores hi / lo (conflict-free: consecutive rows are
-    // consecutive 16-byte slots of a k-chunk)
-    {
-      // all loads first (up to kMaxKc 16-byte loads in flight per thread: the first version loaded, converted and stored
-      // one chunk at a time and spent 20 of its 25 us per tile waiting on HBM latency), then convert + store
-      const int r = tid & (TM - 1), half = tid >> 7;
-      const float* xr = p.x + (row0 + r) * p.ld_x;
-      const bool ok = r < nr;
-      const int nkc_all = Kp / 4, per = (nkc_all + 1) / 2;
-      const int kc0 = half * per, nkc = min(per, nkc_all - kc0);  // this thread's chunks: [kc0, kc0 + nkc)
-      float4 v[kMaxKc];
+    // ---- A tile: split the prefetched row halves, store hi / lo (conflict-free: consecutive rows are consecutive
+    // 16-byte slots of a k-chunk)
 #pragma unroll
-      for (int i = 0; i < kMaxKc; ++i) {
+    for (int i = 0; i < kMaxKc; ++i) {
+      if (i < nkc) {
         const int kc = kc0 + i;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < nkc && ok) {
-          if (4 * kc + 3 < K) {
-            v[i] = __ldg(reinterpret_cast<const float4*>(xr + 4 * kc));
-          } else {
-            if (4 * kc < K) v[i].x = __ldg(xr + 4 * kc);
-            if (4 * kc + 1 < K) v[i].y = __ldg(xr + 4 * kc + 1);
-            if (4 * kc + 2 < K) v[i].z = __ldg(xr + 4 * kc + 2);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < kMaxKc; ++i) {
-        if (i < nkc) {
-          const int kc = kc0 + i;
-          float4 h, l;
-          h.x = tf32_rna(v[i].x); h.y = tf32_rna(v[i].y); h.z = tf32_rna(v[i].z); h.w = tf32_rna(v[i].w);
-          l.x = tf32_rna(v[i].x - h.x); l.y = tf32_rna(v[i].y - h.y);
-          l.z = tf32_rna(v[i].z - h.z); l.w = tf32_rna(v[i].w - h.w);
-          *reinterpret_cast<float4*>(a_hi + (kc * TM + r) * 4) = h;
-          *reinterpret_cast<float4*>(a_lo + (kc * TM + r) * 4) = l;
-        }
+        float4 h, l;
+        h.x = tf32_rna(v[i].x); h.y = tf32_rna(v[i].y); h.z = tf32_rna(v[i].z); h.w = tf32_rna(v[i].w);
+        l.x = tf32_rna(v[i].x - h.x); l.y = tf32_rna(v[i].y - h.y);
+        l.z = tf32_rna(v[i].z - h.z); l.w = tf32_rna(v[i].w - h.w);
+        *reinterpret_cast<float4*>(a_hi + (kc * TM + lr) * 4) = h;
+        *reinterpret_cast<float4*>(a_lo + (kc * TM + lr) * 4) = l;
       }
     }
     // generic-proxy writes -> visible to the tensor core (async proxy), then one thread issues the MMAs
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(TT, 1) dense_tc_kernel(const TcParams p) {
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mbar))
                    : "memory");
     }
+    load_rows(tile + gridDim.x);  // next tile's rows: in flight while the tensor core and the epilogue work
     mbar_wait_parity(smem_u32(&mbar), phase);
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(TT, 1) dense_tc_kernel(const TcParams p) {
         for (int i = 0; i < 16; ++i) {
           const int n = c0 + i;
           if (n < N) {
-            float y = v[i] + (p.bias ? __ldg(p.bias + n) : 0.f);
+            float y = v[i] + s_bias[n];
             if (p.act == VMS_ACT_RELU) y = fmaxf(y, 0.f);
             else if (p.act == VMS_ACT_TANH) y = tanhf(y);
             s_out[r * N + n] = y;
