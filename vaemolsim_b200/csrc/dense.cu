@@ -239,6 +239,18 @@ extern "C" {
 vms_status vms_dense_forward(const float* x, int64_t ld_x, const float* W, const float* b, int64_t B, int K, int N,
                              int act, const float* cond, int64_t ld_c, const float* Wc, int C, float* out,
                              int64_t ld_out, vms_stream stream) {
+  return vms::dense_forward_impl(x, ld_x, W, b, B, K, N, act, cond, ld_c, Wc, C, out, ld_out, as_stream(stream), true);
+}
+
+}  // extern "C"
+
+namespace vms {
+// allow_tc = false keeps the FP32 FFMA kernel at every batch size: the unfused ELBO plan uses it so that it stays the
+// float32 cross-check of the fused kernel (the 3 x TF32 tensor-core path carries ~5e-6 of the dot product's scale,
+// which ill-conditioned splines amplify past the 1e-5 budget of that comparison).
+vms_status dense_forward_impl(const float* x, int64_t ld_x, const float* W, const float* b, int64_t B, int K, int N,
+                              int act, const float* cond, int64_t ld_c, const float* Wc, int C, float* out,
+                              int64_t ld_out, cudaStream_t stream, bool allow_tc) {
   VMS_REQUIRE(B >= 0 && K >= 1 && N >= 1, VMS_ERR_SHAPE, "dense_forward: bad shape B=%lld K=%d N=%d", (long long)B, K, N);
   VMS_REQUIRE(B < (1LL << 31), VMS_ERR_SHAPE, "dense_forward: batch too large");
   VMS_REQUIRE(W && out, VMS_ERR_INVALID_ARG, "dense_forward: NULL W / out");
@@ -247,9 +259,9 @@ vms_status vms_dense_forward(const float* x, int64_t ld_x, const float* W, const
               "dense_forward: conditional_input missing");
   VMS_REQUIRE(x != nullptr || K == 1, VMS_ERR_INVALID_ARG, "dense_forward: NULL x is only valid for the ones input (K=1)");
   if (B == 0) return VMS_OK;
-  if (C == 0 && x != nullptr) {  // large batches: tcgen05 3xTF32 GEMM (gemm_tc.cu); returns false when it does not apply
+  if (allow_tc && C == 0 && x != nullptr) {  // large batches: tcgen05 3xTF32 GEMM (gemm_tc.cu); returns false when it does not apply
     vms_status s = VMS_OK;
-    if (dense_forward_tc_try(x, ld_x, W, b, B, K, N, act, out, ld_out, as_stream(stream), &s)) return s;
+    if (dense_forward_tc_try(x, ld_x, W, b, B, K, N, act, out, ld_out, stream, &s)) return s;
   }
   RowTileParams p = {};
   p.M = (int)B; p.N = N; p.K = K;
@@ -257,8 +269,11 @@ vms_status vms_dense_forward(const float* x, int64_t ld_x, const float* W, const
   p.Bm = W; p.ldb = N;
   if (C > 0) { p.A2 = cond; p.lda2 = ld_c; p.B2 = Wc; p.ldb2 = N; p.K2 = C; }
   p.bias = b; p.act = act; p.C = out; p.ldc = ld_out;
-  return gemm_rowtile(p, as_stream(stream));
+  return gemm_rowtile(p, stream);
 }
+}  // namespace vms
+
+extern "C" {
 
 size_t vms_dense_backward_workspace(int64_t B, int K, int N, int C) {
   size_t rows = (size_t)(K + 1) + (size_t)(C > 0 ? C + 1 : 0);

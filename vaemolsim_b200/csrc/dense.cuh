@@ -36,6 +36,10 @@ vms_status sum_partials_launch(const float* part, int n_partials, int64_t stride
                                float* out1, float scale, int accumulate, cudaStream_t st);
 int dense_splits(int64_t B);
 
+vms_status dense_forward_impl(const float* x, int64_t ld_x, const float* W, const float* b, int64_t B, int K, int N,
+                              int act, const float* cond, int64_t ld_c, const float* Wc, int C, float* out,
+                              int64_t ld_out, cudaStream_t stream, bool allow_tc);
+
 // gemm_tc.cu: tcgen05 (3 x TF32) Dense forward for large batches
 bool dense_forward_tc_try(const float* x, int64_t ld_x, const float* W, const float* b, int64_t B, int K, int N, int act,
                           float* out, int64_t ld_out, cudaStream_t st, vms_status* status);

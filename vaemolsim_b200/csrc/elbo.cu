@@ -114,7 +114,7 @@ vms_status alloc(vms_elbo_plan_s* pl, float** p, size_t n_floats) {
 
 vms_status dense_fwd(const float* x, int64_t ldx, const float* W, const float* b, int64_t B, int K, int N, int act,
                      float* out, int64_t ldo, cudaStream_t st) {
-  return vms_dense_forward(x, ldx, W, b, B, K, N, act, nullptr, 0, nullptr, 0, out, ldo, (vms_stream)st);
+  return dense_forward_impl(x, ldx, W, b, B, K, N, act, nullptr, 0, nullptr, 0, out, ldo, st, false);
 }
 
 // weight + bias gradient partials of one Dense layer written straight into the flat partial-gradient stack:
