@@ -10,7 +10,8 @@
 // float32 parity.  kind::tf32 reads float32 containers and uses 10 mantissa bits: 1e-3 relative, outside the 1e-5
 // budget.  So every operand is split a = a_hi + a_lo (a_hi = cvt.rna.tf32(a), a_lo = cvt.rna.tf32(a - a_hi), both exactly
 // representable) and the product is accumulated as a_lo b_hi + a_hi b_lo + a_hi b_hi in the float32 TMEM
-// accumulator: the dropped a_lo b_lo term is 2^-22 relative.  Three MMAs per k-step, ~1e-6 relative error.
+// accumulators (leading products and corrections separately, added in the epilogue): the dropped a_lo b_lo term is
+// 2^-22 relative.  Three MMAs per k-step.
 //
 // Structure (one CTA per SM, 256 threads, persistent over 128-row tiles):
 //   * W is split once per CTA into shared memory (B operand, N x K "K-major", no swizzle: core matrices of 8 rows x 16
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(TT, 1) dense_tc_kernel(const TcParams p) {
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const unsigned tmem_d = tmem_base_s;
+  const unsigned tmem_d = tmem_base_s, tmem_d2 = tmem_base_s + p.tmem_cols / 2;
   // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major, N >> 3, M >> 4
   const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(Np >> 3) << 17) | ((unsigned)(TM >> 4) << 24);
   const unsigned a_lbo = (TM / 8) * 128, b_lbo = (unsigned)(Np / 8) * 128, sbo = 128;
@@ -202,10 +203,13 @@ __global__ void __launch_bounds__(TT, 1) dense_tc_kernel(const TcParams p) {
       const unsigned ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
       for (int k8 = 0; k8 < Kp / 8; ++k8) {
         const unsigned ao = (unsigned)k8 * 2u * a_lbo, bo = (unsigned)k8 * 2u * b_lbo;
-        // small terms first, then the leading product
-        mma_tf32(tmem_d, make_desc(al + ao, a_lbo, sbo), make_desc(bh + bo, b_lbo, sbo), idesc, k8 > 0 ? 1u : 0u);
-        mma_tf32(tmem_d, make_desc(ah + ao, a_lbo, sbo), make_desc(bl + bo, b_lbo, sbo), idesc, 1u);
-        mma_tf32(tmem_d, make_desc(ah + ao, a_lbo, sbo), make_desc(bh + bo, b_lbo, sbo), idesc, 1u);
+        // the leading products a_hi b_hi go to accumulator 1, the two correction products (2^-11 smaller) to accumulator
+        // 2: the tensor core's float32 accumulation is not round-to-nearest, and its error grows with the number of
+        // accumulation steps at FULL magnitude -- 13 instead of 39 this way (measured: 5.1e-6 of the dot product's scale
+        // with one accumulator, 2.3e-6 with two; the FFMA kernel has 2.1e-6).  The epilogue adds the two.
+        mma_tf32(tmem_d2, make_desc(al + ao, a_lbo, sbo), make_desc(bh + bo, b_lbo, sbo), idesc, k8 > 0 ? 1u : 0u);
+        mma_tf32(tmem_d2, make_desc(ah + ao, a_lbo, sbo), make_desc(bl + bo, b_lbo, sbo), idesc, 1u);
+        mma_tf32(tmem_d, make_desc(ah + ao, a_lbo, sbo), make_desc(bh + bo, b_lbo, sbo), idesc, k8 > 0 ? 1u : 0u);
       }
       // completion of everything issued so far -> mbarrier (implies tcgen05.fence::before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mbar))
@@ -220,13 +224,14 @@ __global__ void __launch_bounds__(TT, 1) dense_tc_kernel(const TcParams p) {
       // warps w and w + 4 share TMEM lane quarter w & 3 (rows 32 (w & 3) ..) and take alternate 16-column chunks
       const int q = warp & 3, r = 32 * q + lane;
       for (int c0 = 16 * (warp >> 2); c0 < Np; c0 += 32) {
-        float v[16];
+        float v[16], v2[16];
         tmem_ld16(tmem_d + ((unsigned)(32 * q) << 16) + (unsigned)c0, v);
+        tmem_ld16(tmem_d2 + ((unsigned)(32 * q) << 16) + (unsigned)c0, v2);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int n = c0 + i;
           if (n < N) {
-            float y = v[i] + s_bias[n];
+            float y = (v[i] + v2[i]) + s_bias[n];
             if (p.act == VMS_ACT_RELU) y = fmaxf(y, 0.f);
             else if (p.act == VMS_ACT_TANH) y = tanhf(y);
             s_out[r * N + n] = y;
@@ -284,7 +289,7 @@ bool dense_forward_tc_try(const float* x, int64_t ld_x, const float* W, const fl
   TcParams p = {};
   p.x = x; p.ld_x = ld_x; p.W = W; p.bias = b; p.out = out; p.ld_out = ld_out; p.B = B;
   p.K = K; p.N = N; p.Kp = Kp; p.Np = Np; p.act = act;
-  p.tmem_cols = Np <= 32 ? 32u : Np <= 64 ? 64u : Np <= 128 ? 128u : 256u;
+  p.tmem_cols = Np <= 16 ? 32u : Np <= 32 ? 64u : Np <= 64 ? 128u : Np <= 128 ? 256u : 512u;  // two accumulators
   cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     cudaGetLastError();
