@@ -474,10 +474,20 @@ def run_b200(args, w):
         f.adam_step(opt, grad_scale=1.0 / world)
 
     sampler = ClockSampler(c.device)
-    sampler.start()
+    if rank == 0:  # one nvidia-smi loop per job (rank 0's GPU), not one per rank
+        sampler.start()
     for i in range(max(W, 3)):
         step(i)
     c.synchronize()
+    peer_note = None
+    if peer is not None and grp.sum(1.0 if peer.timed_out() else 0.0) > 0.0:
+        # a rank gave up waiting for a peer's flag during warm-up (the kernel's bound): do not spend the timed region on
+        # 2 s time-outs -- finish on the NCCL exchange and say so
+        peer_note = 'peer exchange timed out during warm-up; NCCL fallback used'
+        sys.stderr.write('bench: %s\n' % peer_note)
+        peer.close()
+        peer = None
+        gt, ext = grp.wrap_device_buffer(f.grad.ptr, f.n_params, c.stream)
 
     # ---- timed region 1: inputs resident in HBM, per-step CUDA events, L2 flushed (untimed) between steps
     ev = Events(c, K)
@@ -530,8 +540,10 @@ def run_b200(args, w):
     e2e_s = grp.max(time.perf_counter() - t0)
     e2e_value = world * batch * K / e2e_s
     # keep the same load going until the clock sampler has a few samples inside a loaded window
+    # (the decision is rank 0's, shared with every rank: step() contains the gradient exchange when N > 1, so all ranks
+    # must run the same number of steps)
     t_load = time.perf_counter()
-    while sampler.count() < 8 and time.perf_counter() - t_load < 3.0:
+    while grp.max(1.0 if rank == 0 and sampler.count() < 8 and time.perf_counter() - t_load < 3.0 else 0.0) > 0.0:
         for i in range(50):
             step(i)
         c.synchronize()
@@ -571,6 +583,8 @@ def run_b200(args, w):
     }
     if replicas_ok is not None:
         line['config']['replicas_bit_identical'] = bool(replicas_ok)
+    if peer_note:
+        line['config']['note'] = peer_note
     if not args.no_extras:
         micro, peak, peak_kind = kernel_microbench(v, w, batch)
         peaks = {}
@@ -623,6 +637,9 @@ def main():
     sys.stdout = os.fdopen(real_out, 'w')
     args = parse()
     w = WORKLOADS[args.workload]
+    if os.environ.get('VMS_BENCH_FAULT_AFTER'):  # development aid: dump every thread's Python stack and exit if stuck
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['VMS_BENCH_FAULT_AFTER']), exit=True)
     if args.impl == 'reference':
         run_reference(args, w)
     else:

@@ -137,17 +137,28 @@ class PeerExchange(object):
             group.dist.all_gather_object(handles, bytes(handle))
         self.opened = []
         bases = (C.c_void_p * self.world)()
-        for r in range(self.world):
-            if r == self.rank:
-                bases[r] = self.buf.ptr
-            else:
-                p = C.c_void_p()
-                lib.vms_ipc_open_handle((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p))
-                self.opened.append(p.value)
-                bases[r] = p.value
+        error = None
+        try:
+            for r in range(self.world):
+                if r == self.rank:
+                    bases[r] = self.buf.ptr
+                else:
+                    p = C.c_void_p()
+                    lib.vms_ipc_open_handle((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p))
+                    self.opened.append(p.value)
+                    bases[r] = p.value
+        except Exception as e:  # no peer mapping from this rank: every rank must learn it (no one-sided exit)
+            error = e
         self.bases = bases
         self.step = 0
-        group.barrier()  # every buffer is zeroed and mapped before anyone signals
+        # collective agreement doubles as the barrier: every buffer is zeroed and mapped before anyone signals
+        n_ok = group.sum(0.0 if error is not None else 1.0)
+        if n_ok != self.world:
+            for p in self.opened:
+                lib.vms_ipc_close_handle(p)
+            self.opened = []
+            raise RuntimeError('PeerExchange: peer mapping failed on %d of %d ranks%s' %
+                               (self.world - int(n_ok), self.world, '' if error is None else ' (this rank: %s)' % error))
 
     def next_slot(self):
         """Device pointer the NEXT step's local gradient must be written to."""
