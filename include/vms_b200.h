@@ -268,9 +268,18 @@ int64_t vms_elbo_param_count(const vms_elbo_desc* desc);
 /* Two implementations sit behind the plan: a FUSED one (a single persistent kernel, 32-row tiles resident in shared
  * memory; chosen automatically when the shape fits: dx, dz <= 8, num_bins <= 32 and a multiple of 4, shared memory
  * <= 227 KB) and an UNFUSED one (per-layer kernels replayed as a CUDA graph; any shape).  mode 0 = auto, 1 = force
- * the unfused path (used by the tests to cross-check the two on the device).                                      */
+ * the unfused float32-FFMA path (used by the tests to cross-check the paths on the device), 2 = the unfused plan with
+ * every RealNVP coupling block (flows.py:184-207 conditioner + spline, forward and reverse mode) as ONE tcgen05
+ * kernel per block (flow_tc.cu: 3 x TF32, accumulators in TMEM, hidden layer and raw spline parameters never leave
+ * the SM) -- the large-batch configuration; VMS_ERR_UNSUPPORTED when a block's shape does not fit (one transformed
+ * dimension, <= 4 conditioner columns, hidden <= 103, num_bins <= 32 and a multiple of 4).
+ * vms_elbo_plan_tc_status: synchronises the device and reports whether any tensor-core completion wait ran into its
+ * bound since the last call (err = 1: results of that interval are invalid); clears the flag.                      */
 vms_status vms_elbo_plan_set_mode(vms_elbo_plan plan, int mode);
 int vms_elbo_plan_is_fused(vms_elbo_plan plan);
+vms_status vms_elbo_plan_tc_status(vms_elbo_plan plan, int* err);
+/* Batch from which mode 0 prefers the mode-2 plan over the single fused kernel (default: see DESIGN.md). */
+vms_status vms_elbo_plan_set_tc_auto_batch(vms_elbo_plan plan, int64_t batch);
 /* Measurement aid (bench.py's roofline leg): with max_launches > 0 the fused path brackets its main kernel with CUDA
  * events on the launching stream for the next max_launches calls; vms_elbo_plan_kernel_ms synchronises, returns the
  * summed device time of that kernel and the number of launches measured, and resets the counter. */

@@ -12,6 +12,7 @@
 // sized once for max_batch -- and replays the whole step as ONE CUDA graph per (batch, pointer set): the step is
 // ~60 small kernels whose launch overhead would otherwise dominate at the named batch of 4096.
 #include "elbo_plan.cuh"
+#include "flow_tc.cuh"
 #include <math.h>
 
 namespace vms {
@@ -147,6 +148,23 @@ vms_status dense_xgrad(const float* W, int64_t B, int K, int N, int act, const f
 
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// mode 2 (or auto at large batches): the flow blocks run as fused tensor-core kernels
+bool plan_uses_tc(const vms_elbo_plan_s* pl, int64_t B) {
+  if (!pl->tc_ok || B < 64) return false;
+  return pl->mode == 2 || (pl->mode == 0 && B >= pl->tc_auto_batch);
+}
+
+FlowTcArgs flow_tc_args(const vms_elbo_plan_s* pl, const float* theta, int i, int64_t B) {
+  const vms_elbo_desc& d = pl->d;
+  const FlowBlock& fb = pl->blocks[i];
+  FlowTcArgs ta = {};
+  ta.B = B; ta.dz = d.dz; ta.cs0 = fb.cs0; ta.nc = fb.cs1 - fb.cs0; ta.ts0 = fb.ts0;
+  ta.H = d.flow_hidden; ta.K = d.num_bins; ta.bin_min = d.bin_min; ta.bin_max = d.bin_max;
+  ta.d1W = theta + fb.off_d1W; ta.d1b = theta + fb.off_d1b; ta.hW = theta + fb.off_hW; ta.hb = theta + fb.off_hb;
+  ta.err = pl->tc_err;
+  return ta;
+}
+
 vms_status forward_body(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B,
                         float* scalars, cudaStream_t st) {
   const vms_elbo_desc& d = pl->d;
@@ -164,6 +182,13 @@ vms_status forward_body(vms_elbo_plan_s* pl, const float* theta, const float* x,
     const FlowBlock& fb = pl->blocks[i];
     const float* uin = pl->u[i + 1];
     float* uout = pl->u[i];
+    if (plan_uses_tc(pl, B)) {
+      // conditioner + spline of the block in ONE tensor-core kernel (flow_tc.cu): hid / raw never reach HBM
+      FlowTcArgs ta = flow_tc_args(pl, theta, i, B);
+      ta.uin = uin; ta.uout = uout; ta.logpz = pl->logpz; ta.accumulate = (i != nb - 1);
+      VMS_TRY(flow_tc_forward(ta, st));
+      continue;
+    }
     const float* cond = fb.cs1 > fb.cs0 ? uin + fb.cs0 : nullptr;  // NULL => ones((B,1)) (flows.py:184-185)
     VMS_TRY(dense_fwd(cond, d.dz, theta + fb.off_d1W, theta + fb.off_d1b, B, fb.cin, d.flow_hidden, VMS_ACT_TANH,
                       pl->hid[i], d.flow_hidden, st));
@@ -237,6 +262,17 @@ vms_status backward_body(vms_elbo_plan_s* pl, const float* theta, const float* x
       const FlowBlock& fb = pl->blocks[i];
       const float* uin = pl->u[i + 1];
       const int nc = fb.cs1 - fb.cs0;
+      if (plan_uses_tc(pl, B)) {
+        const int64_t flow0 = pl->blocks[0].off_d1W;
+        FlowTcArgs ta = flow_tc_args(pl, theta, i, B);
+        ta.uin = uin;
+        ta.g_cur = g_cur; ta.g_nxt = g_nxt; ta.g_ldj = g_logpz;
+        ta.part = pl->tc_part; ta.part_stride = pl->off.total - flow0;
+        ta.o_d1W = fb.off_d1W - flow0; ta.o_d1b = fb.off_d1b - flow0; ta.o_hW = fb.off_hW - flow0; ta.o_hb = fb.off_hb - flow0;
+        VMS_TRY(flow_tc_backward(ta, st));
+        float* t = g_cur; g_cur = g_nxt; g_nxt = t;
+        continue;
+      }
       if (nc > 0)
         VMS_CUDA(cudaMemcpy2DAsync(g_nxt + fb.cs0, d.dz * sizeof(float), g_cur + fb.cs0, d.dz * sizeof(float),
                                    nc * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
@@ -282,6 +318,14 @@ vms_status backward_body(vms_elbo_plan_s* pl, const float* theta, const float* x
   VMS_TRY(dense_wgrad(pl, x, d.dx, B, d.dx, d.hidden, VMS_ACT_RELU, pl->he, d.hidden, pl->g_he, d.hidden, o.enc0W,
                       splits, st));
   // flat gradient = fixed-order sum of the split partials
+  if (nb > 0 && plan_uses_tc(pl, B)) {
+    // MLP layers: the split partials; flow blocks: one partial per CTA of the tensor-core kernels
+    const int64_t flow0 = pl->blocks[0].off_d1W;
+    VMS_TRY(sum_partials_launch(pl->gpart, splits, o.total, flow0, grad, 0, nullptr, 1.f, 0, st));
+    VMS_TRY(sum_partials_launch(pl->tc_part, flow_tc_grid(B), o.total - flow0, o.total - flow0, grad + flow0, 0, nullptr,
+                                1.f, 0, st));
+    return VMS_OK;
+  }
   VMS_TRY(sum_partials_launch(pl->gpart, splits, o.total, o.total, grad, 0, nullptr, 1.f, 0, st));
   return VMS_OK;
 }
@@ -358,6 +402,15 @@ vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan) 
   A_(pl->g_he, B * d.hidden); A_(pl->g_ua, B * d.dz); A_(pl->g_ub, B * d.dz);
   A_(pl->g_raw, B * max_ldr); A_(pl->g_hid, B * (d.num_blocks ? d.flow_hidden : 1)); A_(pl->g_ldj, B);
   A_(pl->gpart, (size_t)pl->splits_max * pl->off.total);
+  pl->tc_ok = d.num_blocks > 0;
+  for (auto& b : pl->blocks) pl->tc_ok = pl->tc_ok && flow_tc_supported(d.dz, b.cin, b.dt, d.flow_hidden, d.num_bins);
+  if (pl->tc_ok) {
+    A_(pl->tc_part, (size_t)sm_count() * (pl->off.total - pl->blocks[0].off_d1W));
+    float* e = nullptr;
+    A_(e, 4);
+    pl->tc_err = reinterpret_cast<int*>(e);
+    if (!s && cudaMemset(pl->tc_err, 0, 16) != cudaSuccess) s = VMS_ERR_CUDA;
+  }
 #undef A_
   if (!s) s = fused_create(pl);
   if (s) { vms_elbo_plan_destroy(pl); return s; }
@@ -384,8 +437,26 @@ static vms_status check_call(vms_elbo_plan pl, const float* theta, const float* 
 
 vms_status vms_elbo_plan_set_mode(vms_elbo_plan pl, int mode) {
   VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "elbo_plan_set_mode: NULL plan");
-  VMS_REQUIRE(mode == 0 || mode == 1, VMS_ERR_INVALID_ARG, "elbo_plan_set_mode: mode must be 0 (auto) or 1 (unfused)");
+  VMS_REQUIRE(mode >= 0 && mode <= 2, VMS_ERR_INVALID_ARG,
+              "elbo_plan_set_mode: mode must be 0 (auto), 1 (unfused, FFMA) or 2 (unfused, tensor-core flow blocks)");
+  VMS_REQUIRE(mode != 2 || pl->tc_ok, VMS_ERR_UNSUPPORTED, "elbo_plan_set_mode: the tensor-core flow kernels do not support this shape");
   pl->mode = mode;
+  return VMS_OK;
+}
+
+vms_status vms_elbo_plan_tc_status(vms_elbo_plan pl, int* err) {
+  VMS_REQUIRE(pl && err, VMS_ERR_INVALID_ARG, "elbo_plan_tc_status: NULL argument");
+  *err = 0;
+  if (!pl->tc_err) return VMS_OK;
+  VMS_CUDA(cudaDeviceSynchronize());
+  VMS_CUDA(cudaMemcpy(err, pl->tc_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (*err) VMS_CUDA(cudaMemset(pl->tc_err, 0, sizeof(int)));
+  return VMS_OK;
+}
+
+vms_status vms_elbo_plan_set_tc_auto_batch(vms_elbo_plan pl, int64_t batch) {
+  VMS_REQUIRE(pl && batch >= 64, VMS_ERR_INVALID_ARG, "elbo_plan_set_tc_auto_batch: NULL plan or batch < 64");
+  pl->tc_auto_batch = batch;
   return VMS_OK;
 }
 
@@ -399,6 +470,12 @@ vms_status vms_elbo_plan_kernel_ms(vms_elbo_plan pl, double* total_ms, int* laun
   return fused_kernel_ms(pl, total_ms, launches);
 }
 
+// the single fused kernel runs the step unless a mode forces the per-layer plan or the batch is large enough for the
+// tensor-core flow kernels (auto)
+static bool use_fused(const vms_elbo_plan_s* pl, int64_t B) {
+  return pl->fused && pl->mode == 0 && !(pl->tc_ok && B >= pl->tc_auto_batch);
+}
+
 int vms_elbo_plan_is_fused(vms_elbo_plan pl) { return pl && pl->fused && pl->mode == 0 ? 1 : 0; }
 
 vms_status vms_elbo_forward(vms_elbo_plan pl, const float* theta, const float* x, const float* eps, int64_t B, float* z,
@@ -406,9 +483,9 @@ vms_status vms_elbo_forward(vms_elbo_plan pl, const float* theta, const float* x
   vms_status s = check_call(pl, theta, x, eps, B);
   if (s) return s;
   cudaStream_t st = as_stream(stream);
-  if (pl->fused && pl->mode == 0)
+  if (use_fused(pl, B))
     return fused_run(pl, theta, x, eps, B, false, z, logq, logpz, logpx, nullptr, scalars, st);
-  std::array<uintptr_t, 10> key = {0, (uintptr_t)B, (uintptr_t)theta, (uintptr_t)x, (uintptr_t)eps, (uintptr_t)z,
+  std::array<uintptr_t, 10> key = {(uintptr_t)(0 | (pl->mode << 8)), (uintptr_t)B, (uintptr_t)theta, (uintptr_t)x, (uintptr_t)eps, (uintptr_t)z,
                                    (uintptr_t)logq, (uintptr_t)logpz, (uintptr_t)logpx, (uintptr_t)scalars};
   const vms_elbo_desc& d = pl->d;
   return run_graphed(pl, key, st, [&]() -> vms_status {
@@ -427,9 +504,9 @@ vms_status vms_elbo_forward_backward(vms_elbo_plan pl, const float* theta, const
   if (s) return s;
   VMS_REQUIRE(grad, VMS_ERR_INVALID_ARG, "elbo_forward_backward: NULL grad");
   cudaStream_t st = as_stream(stream);
-  if (pl->fused && pl->mode == 0)
+  if (use_fused(pl, B))
     return fused_run(pl, theta, x, eps, B, true, nullptr, nullptr, nullptr, nullptr, grad, scalars, st);
-  std::array<uintptr_t, 10> key = {1, (uintptr_t)B, (uintptr_t)theta, (uintptr_t)x, (uintptr_t)eps, (uintptr_t)grad,
+  std::array<uintptr_t, 10> key = {(uintptr_t)(1 | (pl->mode << 8)), (uintptr_t)B, (uintptr_t)theta, (uintptr_t)x, (uintptr_t)eps, (uintptr_t)grad,
                                    (uintptr_t)scalars, 0, 0, 0};
   return run_graphed(pl, key, st, [&]() -> vms_status {
     VMS_TRY(forward_body(pl, theta, x, eps, B, scalars, st));
@@ -446,7 +523,7 @@ vms_status vms_elbo_train_step(vms_elbo_plan pl, float* theta, const float* x, c
   vms_status s = check_call(pl, theta, x, eps, B);
   if (s) return s;
   VMS_REQUIRE(grad && m && v && t >= 1, VMS_ERR_INVALID_ARG, "elbo_train_step: NULL grad / m / v or t < 1");
-  if (pl->fused && pl->mode == 0) {
+  if (use_fused(pl, B)) {
     FusedAdam ad;
     ad.theta = theta; ad.m = m; ad.v = v;
     ad.lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));

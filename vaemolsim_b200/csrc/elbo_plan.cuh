@@ -77,6 +77,12 @@ struct vms_elbo_plan_s {
   // fused path (elbo_fused.cu): NULL when the shape does not fit; mode 0 = auto (fused when available), 1 = unfused
   vms::FusedCfg* fused = nullptr;
   int mode = 0;
+  // tensor-core flow blocks (flow_tc.cu): per-CTA weight-gradient partials [sm_count][flow parameters], error flag,
+  // and the batch from which auto mode prefers them over the single fused kernel
+  bool tc_ok = false;
+  float* tc_part = nullptr;
+  int* tc_err = nullptr;
+  int64_t tc_auto_batch = INT64_MAX;
 };
 
 namespace vms {

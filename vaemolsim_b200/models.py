@@ -252,8 +252,15 @@ class FusedELBO(object):
         raise NotImplementedError('fused ELBO: prior must be a static N(0, I) DistributionLambda or a FlowedDistribution')
 
     def set_mode(self, mode):
-        """0 = auto (the single fused kernel when the shape fits), 1 = force the unfused per-layer graph path."""
+        """0 = auto (the single fused kernel when the shape fits), 1 = force the unfused per-layer float32-FFMA graph
+        path, 2 = unfused plan with the coupling blocks as fused tcgen05 kernels (the large-batch configuration)."""
         ctx().lib.vms_elbo_plan_set_mode(self.handle, int(mode))
+
+    def tc_status(self):
+        """True if a tensor-core kernel of the mode-2 plan gave up waiting for an MMA completion (results invalid)."""
+        err = C.c_int(0)
+        ctx().lib.vms_elbo_plan_tc_status(self.handle, C.byref(err))
+        return bool(err.value)
 
     @property
     def is_fused(self):
