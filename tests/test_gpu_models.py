@@ -303,6 +303,58 @@ def test_fused_kernel_agrees_with_unfused_plan(vms, prior, dz, B, bins):
     assert_close(g_f, g_u, rtol=1e-4, atol=5e-6 * max(np.abs(g_u).max(), 1e-3), what='flat gradient fused vs unfused')
 
 
+@pytest.mark.parametrize('dz,B,bins,fh,hidden', [(2, 10007, 32, 100, 200), (2, 5000, 20, 40, 64), (1, 700, 8, 16, 32),
+                                                 (2, 64, 32, 100, 200)])
+def test_tensor_core_plan_matches_oracle_and_ffma_plan(vms, dz, B, bins, fh, hidden):
+    """Plan mode 2 -- every RealNVP-RQS coupling block as one tcgen05 kernel (flow_tc.cu: 3 x BF16 split, K-major and
+    MN-major reads of the same shared-memory tiles, spline in the epilogue) -- against the float64 oracle (loss scalars,
+    flat gradient) and against the float32 FFMA per-layer plan (per-row outputs); ragged last tile, dz = 1 (ones
+    conditioner input, flows.py:184-185), both raw-parameter widths (K <= 20: 64 columns, else 96)."""
+    v = vms
+    P = ovae.init_vae(31 + dz, dx=6, dz=dz, hidden=hidden, prior='realnvp', num_blocks=4, num_bins=bins, flow_hidden=fh)
+    rng = np.random.default_rng(B)
+    for blk in P['flow']:
+        for k in ('w', 'h', 's'):
+            blk[k] = ((blk[k][0] * 4).astype(np.float32), rng.normal(0, 0.5, blk[k][1].shape).astype(np.float32))
+    x = rng.normal(size=(B, 6)).astype(np.float32)
+    eps = rng.normal(size=(B, dz)).astype(np.float32)
+    model = vae_from_oracle(v, P, weight=0.7)
+    f = model.fused(B)
+    xt, et = v.as_tensor(x), v.as_tensor(eps)
+    f.set_mode(1)
+    out_u = {k: t.numpy() for k, t in f.forward(xt, et).items()}
+    f.forward_backward(xt, et)
+    g_u = f.grad.numpy().copy()
+    f.set_mode(2)
+    out_t = {k: t.numpy() for k, t in f.forward(xt, et).items()}
+    scal = f.forward_backward(xt, et).numpy().copy()
+    g_t = f.grad.numpy().copy()
+    f.forward_backward(xt, et)
+    assert np.array_equal(f.grad.numpy(), g_t), 'tensor-core plan is not deterministic'
+    assert not f.tc_status(), 'a tensor-core completion wait timed out'
+    f.set_mode(0)
+    for k in ('z', 'logq', 'logpz', 'logpx'):
+        assert_close(out_t[k], out_u[k], rtol=1e-5, atol=2e-5, what='tensor-core vs FFMA plan %s' % k)
+    rel = np.linalg.norm(g_t - g_u) / np.linalg.norm(g_u)
+    assert rel < 1e-5, rel
+    if B <= 5000:  # float64 oracle (seconds at these sizes)
+        P64 = ovae.cast_params(P, np.float64)
+        out, G = ovae.elbo_backward(P64, x.astype(np.float64), eps.astype(np.float64), weight=0.7)
+        assert_close(scal[:3], [out['loss'], out['nll'], out['kl']], rtol=1e-5, atol=1e-5, what='loss / nll / kl')
+        want = flat_grad_from_oracle(P64, G)
+        assert_close(g_t, want, rtol=1e-4, atol=5e-6 * max(np.abs(want).max(), 1e-3), what='flat gradient (tensor-core plan)')
+        rel = np.linalg.norm(g_t - want) / np.linalg.norm(want)
+        assert rel < 1e-5, rel
+
+
+def test_tensor_core_plan_refuses_unsupported_shapes(vms):
+    v = vms
+    P = ovae.init_vae(3, dx=6, dz=4, hidden=32, prior='realnvp', num_blocks=2, num_bins=8, flow_hidden=16)  # dt = 2
+    f = vae_from_oracle(v, P).fused(128)
+    with pytest.raises(Exception):
+        f.set_mode(2)
+
+
 def test_generic_model_path_agrees_with_fused(vms):
     """VAE.call (op-by-op, the reference's code path) and the fused plan evaluate the same ELBO."""
     v = vms

@@ -13,6 +13,7 @@
 // ~60 small kernels whose launch overhead would otherwise dominate at the named batch of 4096.
 #include "elbo_plan.cuh"
 #include "flow_tc.cuh"
+#include "mlp_stream.cuh"
 #include <math.h>
 
 namespace vms {
@@ -165,15 +166,37 @@ FlowTcArgs flow_tc_args(const vms_elbo_plan_s* pl, const float* theta, int i, in
   return ta;
 }
 
+MlpArgs mlp_args(const vms_elbo_plan_s* pl, const float* theta, bool encoder, int64_t B) {
+  const vms_elbo_desc& d = pl->d;
+  const Offsets& o = pl->off;
+  MlpArgs ma = {};
+  ma.B = B; ma.H = d.hidden;
+  ma.Din = encoder ? d.dx : d.dz;
+  ma.Dout = encoder ? 2 * d.dz : 2 * d.dx;
+  ma.o_W0 = encoder ? o.enc0W : o.dec0W; ma.o_b0 = encoder ? o.enc0b : o.dec0b;
+  ma.o_W1 = encoder ? o.enc1W : o.dec1W; ma.o_b1 = encoder ? o.enc1b : o.dec1b;
+  ma.W0 = theta + ma.o_W0; ma.b0 = theta + ma.o_b0; ma.W1 = theta + ma.o_W1; ma.b1 = theta + ma.o_b1;
+  ma.part = pl->tc_part; ma.part_stride = pl->off.total;
+  return ma;
+}
+
 vms_status forward_body(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B,
                         float* scalars, cudaStream_t st) {
   const vms_elbo_desc& d = pl->d;
   const Offsets& o = pl->off;
   const int nb = d.num_blocks;
   // encoder: FCDeepNN dx -> H (relu) -> 2 dz ; IndependentNormal: loc | softplus(raw)
-  VMS_TRY(dense_fwd(x, d.dx, theta + o.enc0W, theta + o.enc0b, B, d.dx, d.hidden, VMS_ACT_RELU, pl->he, d.hidden, st));
-  VMS_TRY(dense_fwd(pl->he, d.hidden, theta + o.enc1W, theta + o.enc1b, B, d.hidden, 2 * d.dz, VMS_ACT_NONE, pl->pe,
-                    2 * d.dz, st));
+  const bool tc = plan_uses_tc(pl, B);
+  if (tc) {
+    // large-batch plan: both Dense layers in one kernel, the hidden layer never reaches HBM (mlp_stream.cu)
+    MlpArgs ma = mlp_args(pl, theta, true, B);
+    ma.in = x; ma.ld_in = d.dx; ma.out = pl->pe; ma.ld_out = 2 * d.dz;
+    VMS_TRY(mlp_stream_forward(ma, 2 * sm_count(), st));
+  } else {
+    VMS_TRY(dense_fwd(x, d.dx, theta + o.enc0W, theta + o.enc0b, B, d.dx, d.hidden, VMS_ACT_RELU, pl->he, d.hidden, st));
+    VMS_TRY(dense_fwd(pl->he, d.hidden, theta + o.enc1W, theta + o.enc1b, B, d.hidden, 2 * d.dz, VMS_ACT_NONE, pl->pe,
+                      2 * d.dz, st));
+  }
   float* zbuf = pl->u[nb];
   VMS_TRY(vms_normal_sample_log_prob(pl->pe, 2 * d.dz, 0, d.dz, VMS_SCALE_SOFTPLUS, eps, B, d.dz, zbuf, d.dz, pl->logq,
                                      (vms_stream)st));
@@ -209,9 +232,15 @@ vms_status forward_body(vms_elbo_plan_s* pl, const float* theta, const float* x,
   }
   VMS_TRY(vms_std_normal_log_prob(pl->u[0], d.dz, B, d.dz, pl->logpz, nb > 0, (vms_stream)st));
   // decoder
-  VMS_TRY(dense_fwd(zbuf, d.dz, theta + o.dec0W, theta + o.dec0b, B, d.dz, d.hidden, VMS_ACT_RELU, pl->hd, d.hidden, st));
-  VMS_TRY(dense_fwd(pl->hd, d.hidden, theta + o.dec1W, theta + o.dec1b, B, d.hidden, 2 * d.dx, VMS_ACT_NONE, pl->pd,
-                    2 * d.dx, st));
+  if (tc) {
+    MlpArgs ma = mlp_args(pl, theta, false, B);
+    ma.in = zbuf; ma.ld_in = d.dz; ma.out = pl->pd; ma.ld_out = 2 * d.dx;
+    VMS_TRY(mlp_stream_forward(ma, 2 * sm_count(), st));
+  } else {
+    VMS_TRY(dense_fwd(zbuf, d.dz, theta + o.dec0W, theta + o.dec0b, B, d.dz, d.hidden, VMS_ACT_RELU, pl->hd, d.hidden, st));
+    VMS_TRY(dense_fwd(pl->hd, d.hidden, theta + o.dec1W, theta + o.dec1b, B, d.hidden, 2 * d.dx, VMS_ACT_NONE, pl->pd,
+                      2 * d.dx, st));
+  }
   {
     int32_t kind[64], loc[64], sc[64];
     for (int j = 0; j < d.dx; ++j) { kind[j] = VMS_DIST_NORMAL; loc[j] = j; sc[j] = d.dx + j; }
@@ -238,6 +267,12 @@ vms_status backward_body(vms_elbo_plan_s* pl, const float* theta, const float* x
   // decoder head and MLP
   decoder_head_bwd_kernel<<<nblk(B * d.dx, 256), 256, 0, st>>>(x, pl->pd, B, d.dx, g_logpx, pl->g_pd);
   VMS_LAUNCH_CHECK("decoder_head_bwd_kernel");
+  const bool tc = plan_uses_tc(pl, B);
+  if (tc) {
+    MlpArgs ma = mlp_args(pl, theta, false, B);
+    ma.in = z; ma.ld_in = d.dz; ma.g_out = pl->g_pd; ma.ld_g = 2 * d.dx; ma.g_in = pl->g_z; ma.ld_gin = d.dz;
+    VMS_TRY(mlp_stream_backward(ma, flow_tc_grid(B), st));
+  } else {
   VMS_TRY(dense_wgrad(pl, pl->hd, d.hidden, B, d.hidden, 2 * d.dx, VMS_ACT_NONE, nullptr, 0, pl->g_pd, 2 * d.dx,
                       o.dec1W, splits, st));
   VMS_TRY(dense_xgrad(theta + o.dec1W, B, d.hidden, 2 * d.dx, VMS_ACT_NONE, nullptr, 0, pl->g_pd, 2 * d.dx, pl->g_hd,
@@ -246,6 +281,7 @@ vms_status backward_body(vms_elbo_plan_s* pl, const float* theta, const float* x
                       splits, st));
   VMS_TRY(dense_xgrad(theta + o.dec0W, B, d.dz, d.hidden, VMS_ACT_RELU, pl->hd, d.hidden, pl->g_hd, d.hidden, pl->g_z,
                       d.dz, 0, st));
+  }
   // prior
   if (nb == 0) {
     // d/dz [ g_logpz * sum(-0.5 z^2) ] = -g_logpz * z
@@ -263,12 +299,11 @@ vms_status backward_body(vms_elbo_plan_s* pl, const float* theta, const float* x
       const float* uin = pl->u[i + 1];
       const int nc = fb.cs1 - fb.cs0;
       if (plan_uses_tc(pl, B)) {
-        const int64_t flow0 = pl->blocks[0].off_d1W;
         FlowTcArgs ta = flow_tc_args(pl, theta, i, B);
         ta.uin = uin;
         ta.g_cur = g_cur; ta.g_nxt = g_nxt; ta.g_ldj = g_logpz;
-        ta.part = pl->tc_part; ta.part_stride = pl->off.total - flow0;
-        ta.o_d1W = fb.off_d1W - flow0; ta.o_d1b = fb.off_d1b - flow0; ta.o_hW = fb.off_hW - flow0; ta.o_hb = fb.off_hb - flow0;
+        ta.part = pl->tc_part; ta.part_stride = pl->off.total;
+        ta.o_d1W = fb.off_d1W; ta.o_d1b = fb.off_d1b; ta.o_hW = fb.off_hW; ta.o_hb = fb.off_hb;
         VMS_TRY(flow_tc_backward(ta, st));
         float* t = g_cur; g_cur = g_nxt; g_nxt = t;
         continue;
@@ -311,6 +346,14 @@ vms_status backward_body(vms_elbo_plan_s* pl, const float* theta, const float* x
   // encoder head + MLP
   encoder_head_bwd_kernel<<<nblk(B * d.dz, 256), 256, 0, st>>>(z, pl->pe, eps, pl->g_z, B, d.dz, g_logq, pl->g_pe);
   VMS_LAUNCH_CHECK("encoder_head_bwd_kernel");
+  if (tc) {
+    MlpArgs ma = mlp_args(pl, theta, true, B);
+    ma.in = x; ma.ld_in = d.dx; ma.g_out = pl->g_pe; ma.ld_g = 2 * d.dz;
+    VMS_TRY(mlp_stream_backward(ma, flow_tc_grid(B), st));
+    // every layer's partials are per CTA of the large-batch kernels: one fixed-order sum over the whole flat gradient
+    VMS_TRY(sum_partials_launch(pl->tc_part, flow_tc_grid(B), o.total, o.total, grad, 0, nullptr, 1.f, 0, st));
+    return VMS_OK;
+  }
   VMS_TRY(dense_wgrad(pl, pl->he, d.hidden, B, d.hidden, 2 * d.dz, VMS_ACT_NONE, nullptr, 0, pl->g_pe, 2 * d.dz,
                       o.enc1W, splits, st));
   VMS_TRY(dense_xgrad(theta + o.enc1W, B, d.hidden, 2 * d.dz, VMS_ACT_NONE, nullptr, 0, pl->g_pe, 2 * d.dz, pl->g_he,
@@ -318,14 +361,6 @@ vms_status backward_body(vms_elbo_plan_s* pl, const float* theta, const float* x
   VMS_TRY(dense_wgrad(pl, x, d.dx, B, d.dx, d.hidden, VMS_ACT_RELU, pl->he, d.hidden, pl->g_he, d.hidden, o.enc0W,
                       splits, st));
   // flat gradient = fixed-order sum of the split partials
-  if (nb > 0 && plan_uses_tc(pl, B)) {
-    // MLP layers: the split partials; flow blocks: one partial per CTA of the tensor-core kernels
-    const int64_t flow0 = pl->blocks[0].off_d1W;
-    VMS_TRY(sum_partials_launch(pl->gpart, splits, o.total, flow0, grad, 0, nullptr, 1.f, 0, st));
-    VMS_TRY(sum_partials_launch(pl->tc_part, flow_tc_grid(B), o.total - flow0, o.total - flow0, grad + flow0, 0, nullptr,
-                                1.f, 0, st));
-    return VMS_OK;
-  }
   VMS_TRY(sum_partials_launch(pl->gpart, splits, o.total, o.total, grad, 0, nullptr, 1.f, 0, st));
   return VMS_OK;
 }
@@ -404,8 +439,9 @@ vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan) 
   A_(pl->gpart, (size_t)pl->splits_max * pl->off.total);
   pl->tc_ok = d.num_blocks > 0;
   for (auto& b : pl->blocks) pl->tc_ok = pl->tc_ok && flow_tc_supported(d.dz, b.cin, b.dt, d.flow_hidden, d.num_bins);
+  pl->tc_ok = pl->tc_ok && mlp_stream_supported(d.dx, d.hidden, 2 * d.dz) && mlp_stream_supported(d.dz, d.hidden, 2 * d.dx);
   if (pl->tc_ok) {
-    A_(pl->tc_part, (size_t)sm_count() * (pl->off.total - pl->blocks[0].off_d1W));
+    A_(pl->tc_part, (size_t)sm_count() * pl->off.total);
     float* e = nullptr;
     A_(e, 4);
     pl->tc_err = reinterpret_cast<int*>(e);
