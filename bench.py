@@ -410,7 +410,7 @@ def large_batch_leg(v, w, opt, batch=262144, steps=5):
     ev.record(1)
     c.synchronize()
     ms = ev.elapsed_ms(0, 1) / steps
-    return {'workload': 'C5 shard: same model, batch %d on one GPU' % batch, 'ms_per_step': ms,
+    return {'workload': 'C5 shard: same model, batch %d on one GPU' % batch, 'ms_per_step': ms, 'plan': f.path(batch),
             'configs_per_s': batch / (ms * 1e-3),
             'tflops_fp32': batch * (259200 if w['prior'] != 'normal' else 28800) / (ms * 1e-3) / 1e12}
 

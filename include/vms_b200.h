@@ -278,6 +278,8 @@ int64_t vms_elbo_param_count(const vms_elbo_desc* desc);
 vms_status vms_elbo_plan_set_mode(vms_elbo_plan plan, int mode);
 int vms_elbo_plan_is_fused(vms_elbo_plan plan);
 vms_status vms_elbo_plan_tc_status(vms_elbo_plan plan, int* err);
+/* Which implementation a call with batch B takes: 0 = single fused kernel, 1 = per-layer FFMA plan, 2 = tensor-core plan. */
+int vms_elbo_plan_path(vms_elbo_plan plan, int64_t B);
 /* Batch from which mode 0 prefers the mode-2 plan over the single fused kernel (default: see DESIGN.md). */
 vms_status vms_elbo_plan_set_tc_auto_batch(vms_elbo_plan plan, int64_t batch);
 /* Measurement aid (bench.py's roofline leg): with max_launches > 0 the fused path brackets its main kernel with CUDA

@@ -15,6 +15,7 @@
 #include "flow_tc.cuh"
 #include "mlp_stream.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace vms {
 
@@ -399,6 +400,12 @@ vms_status run_graphed(vms_elbo_plan_s* pl, const std::array<uintptr_t, 10>& key
 
 }  // namespace
 
+// the single fused kernel runs the step unless a mode forces the per-layer plan or the batch is large enough for the
+// tensor-core flow kernels (auto)
+static bool use_fused(const vms_elbo_plan_s* pl, int64_t B) {
+  return pl->fused && pl->mode == 0 && !(pl->tc_ok && B >= pl->tc_auto_batch);
+}
+
 extern "C" {
 
 int64_t vms_elbo_param_count(const vms_elbo_desc* desc) {
@@ -440,6 +447,10 @@ vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan) 
   pl->tc_ok = d.num_blocks > 0;
   for (auto& b : pl->blocks) pl->tc_ok = pl->tc_ok && flow_tc_supported(d.dz, b.cin, b.dt, d.flow_hidden, d.num_bins);
   pl->tc_ok = pl->tc_ok && mlp_stream_supported(d.dx, d.hidden, 2 * d.dz) && mlp_stream_supported(d.dz, d.hidden, 2 * d.dx);
+  if (const char* e = getenv("VMS_TC_AUTO_BATCH")) {  // auto mode switches to the tensor-core plan from this batch on
+    const long long v = atoll(e);
+    if (v >= 64) pl->tc_auto_batch = v;
+  }
   if (pl->tc_ok) {
     A_(pl->tc_part, (size_t)sm_count() * pl->off.total);
     float* e = nullptr;
@@ -490,6 +501,12 @@ vms_status vms_elbo_plan_tc_status(vms_elbo_plan pl, int* err) {
   return VMS_OK;
 }
 
+int vms_elbo_plan_path(vms_elbo_plan pl, int64_t B) {
+  if (!pl) return -1;
+  if (use_fused(pl, B)) return 0;
+  return plan_uses_tc(pl, B) ? 2 : 1;
+}
+
 vms_status vms_elbo_plan_set_tc_auto_batch(vms_elbo_plan pl, int64_t batch) {
   VMS_REQUIRE(pl && batch >= 64, VMS_ERR_INVALID_ARG, "elbo_plan_set_tc_auto_batch: NULL plan or batch < 64");
   pl->tc_auto_batch = batch;
@@ -504,12 +521,6 @@ vms_status vms_elbo_plan_set_timing(vms_elbo_plan pl, int max_launches) {
 vms_status vms_elbo_plan_kernel_ms(vms_elbo_plan pl, double* total_ms, int* launches) {
   VMS_REQUIRE(pl && total_ms && launches, VMS_ERR_INVALID_ARG, "elbo_plan_kernel_ms: NULL argument");
   return fused_kernel_ms(pl, total_ms, launches);
-}
-
-// the single fused kernel runs the step unless a mode forces the per-layer plan or the batch is large enough for the
-// tensor-core flow kernels (auto)
-static bool use_fused(const vms_elbo_plan_s* pl, int64_t B) {
-  return pl->fused && pl->mode == 0 && !(pl->tc_ok && B >= pl->tc_auto_batch);
 }
 
 int vms_elbo_plan_is_fused(vms_elbo_plan pl) { return pl && pl->fused && pl->mode == 0 ? 1 : 0; }

@@ -82,7 +82,7 @@ struct vms_elbo_plan_s {
   bool tc_ok = false;
   float* tc_part = nullptr;
   int* tc_err = nullptr;
-  int64_t tc_auto_batch = INT64_MAX;
+  int64_t tc_auto_batch = 8192;
 };
 
 namespace vms {

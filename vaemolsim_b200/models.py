@@ -256,6 +256,11 @@ class FusedELBO(object):
         path, 2 = unfused plan with the coupling blocks as fused tcgen05 kernels (the large-batch configuration)."""
         ctx().lib.vms_elbo_plan_set_mode(self.handle, int(mode))
 
+    def path(self, batch):
+        """Implementation a step of `batch` rows takes: 'fused' (one persistent kernel), 'ffma' (per-layer float32
+        plan) or 'tensor-core' (large-batch plan: tcgen05 coupling blocks + streaming MLP kernels)."""
+        return ('fused', 'ffma', 'tensor-core')[ctx().lib.vms_elbo_plan_path(self.handle, int(batch))]
+
     def tc_status(self):
         """True if a tensor-core kernel of the mode-2 plan gave up waiting for an MMA completion (results invalid)."""
         err = C.c_int(0)
