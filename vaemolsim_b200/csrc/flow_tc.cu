@@ -56,7 +56,7 @@ struct KParams {
   int Hp, R, LDS, cin;
   float scale;
   // shared-memory offsets (bytes)
-  int o_hid, o_graw, o_w, o_raw, o_w1, o_b1, o_c, o_v, o_g, o_gin;
+  int o_hid, o_graw, o_w, o_raw, o_w1, o_b1, o_c, o_v, o_g, o_lp, o_gin;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -145,47 +145,64 @@ __device__ __forceinline__ unsigned idesc_bf16(int M, int N, int a_mn, int b_mn)
          ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
 }
 
-// The six products of one k-step: a1 b1 -> acc_a; a1 b2, a2 b1, a1 b3, a2 b2, a3 b1 -> acc_b.
-// a[i] / b[i]: shared-memory addresses of part i at this k-step; (al, as) / (bl, bs): the operands' LBO / SBO.
-__device__ __forceinline__ void mma6(unsigned acc_a, unsigned acc_b, const unsigned (&a)[3], const unsigned (&b)[3],
-                                     unsigned al, unsigned as, unsigned bl, unsigned bs, unsigned idesc, bool first) {
-  unsigned long long da[3], db[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    da[i] = make_desc(a[i], al, as);
-    db[i] = make_desc(b[i], bl, bs);
+// One product C = A B with float32-grade accuracy from 3 x BF16 parts, ONE TMEM accumulator: the correction terms go in
+// first, smallest first (a1 b3, a3 b1, a2 b2 ~ 2^-16; then a1 b2, a2 b1 ~ 2^-8), the leading a1 b1 last.  The tensor
+// core's float32 accumulation is not round-to-nearest and its error grows with the magnitude of the running sum, so
+// only the n_k leading steps accumulate at full magnitude.
+// a0 / b0: shared-memory address of part 1 at k-step 0; a_part / b_part: bytes between parts; a_step / b_step: bytes
+// per k-step; (al, as) / (bl, bs): the operands' LBO / SBO.
+__device__ __forceinline__ void issue_product(unsigned acc, unsigned a0, unsigned a_part, unsigned a_step, unsigned al,
+                                              unsigned as, unsigned b0, unsigned b_part, unsigned b_step, unsigned bl,
+                                              unsigned bs, int n_k, unsigned idesc) {
+  unsigned first = 0u;
+#pragma unroll 1
+  for (int ks = 0; ks < n_k; ++ks) {
+    const unsigned a = a0 + ks * a_step, b = b0 + ks * b_step;
+    mma_bf16(acc, make_desc(a, al, as), make_desc(b + 2 * b_part, bl, bs), idesc, first);
+    first = 1u;
+    mma_bf16(acc, make_desc(a + 2 * a_part, al, as), make_desc(b, bl, bs), idesc, 1u);
+    mma_bf16(acc, make_desc(a + a_part, al, as), make_desc(b + b_part, bl, bs), idesc, 1u);
   }
-  mma_bf16(acc_b, da[0], db[2], idesc, first ? 0u : 1u);
-  mma_bf16(acc_b, da[2], db[0], idesc, 1u);
-  mma_bf16(acc_b, da[1], db[1], idesc, 1u);
-  mma_bf16(acc_b, da[0], db[1], idesc, 1u);
-  mma_bf16(acc_b, da[1], db[0], idesc, 1u);
-  mma_bf16(acc_a, da[0], db[0], idesc, first ? 0u : 1u);
+#pragma unroll 1
+  for (int ks = 0; ks < n_k; ++ks) {
+    const unsigned a = a0 + ks * a_step, b = b0 + ks * b_step;
+    mma_bf16(acc, make_desc(a, al, as), make_desc(b + b_part, bl, bs), idesc, 1u);
+    mma_bf16(acc, make_desc(a + a_part, al, as), make_desc(b, bl, bs), idesc, 1u);
+  }
+#pragma unroll 1
+  for (int ks = 0; ks < n_k; ++ks)
+    mma_bf16(acc, make_desc(a0 + ks * a_step, al, as), make_desc(b0 + ks * b_step, bl, bs), idesc, 1u);
 }
 
+// Software pipeline (per CTA, tiles t0, t1, ... of 64 rows; hid / inputs / the raw accumulator are double-buffered):
+//   forward :  [inputs + hid of tile i+1 | tensor core: raw(i)]  ->  issue raw(i+1)  ->  wait raw(i)  ->  TMEM -> smem,
+//              spline(i)                                          (the tensor core is never waited for in steady state)
+//   backward:  wait raw(i) -> TMEM -> smem, spline reverse mode(i) -> issue d hid(i), d hW(i)
+//              -> [inputs + hid of tile i+1 | tensor core] -> issue raw(i+1) -> wait d hid / d hW(i) -> epilogues(i)
 template <int RP, bool BWD>
 __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smb[];
-  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ __align__(8) unsigned long long mbar[3];  // [0], [1]: raw of buffer 0 / 1;  [2]: d hid + d hW
   __shared__ unsigned tmem_base_s;
   const FlowTcArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int H = a.H, Hp = p.Hp, K = a.K, R = p.R, LDS = p.LDS, nc = a.nc, dz = a.dz;
+  const int H = a.H, Hp = p.Hp, K = a.K, R = p.R, LDS = p.LDS, nc = a.nc, dz = a.dz, cin = p.cin;
   const int nchH = Hp / 8;
   constexpr int nchR = RP / 8;
-  const unsigned hid_sz = (unsigned)nchH * CSB;       // bytes of one part of the hid tile
+  const unsigned hid_sz = (unsigned)nchH * CSB;       // bytes of one part of one hid buffer
   constexpr unsigned graw_sz = (unsigned)nchR * CSB;  // ... of the g_raw tile
   const unsigned w_cs = RP * 16u;                     // chunk-column stride of the heads matrix
   const unsigned w_sz = (unsigned)nchH * w_cs;
-  unsigned char* hid = smb + p.o_hid;    // 3 parts
-  unsigned char* graw = smb + p.o_graw;  // 3 parts (BWD)
-  unsigned char* wsm = smb + p.o_w;      // 3 parts
+  unsigned char* hid = smb + p.o_hid;    // [2 buffers][3 parts]
+  unsigned char* graw = smb + p.o_graw;  // [3 parts] (BWD)
+  unsigned char* wsm = smb + p.o_w;      // [3 parts]
   float* s_raw = reinterpret_cast<float*>(smb + p.o_raw);  // [FM][LDS] raw spline parameters / d pre-activation (BWD)
-  float* s_w1 = reinterpret_cast<float*>(smb + p.o_w1);    // [cin][Hp]
+  float* s_w1 = reinterpret_cast<float*>(smb + p.o_w1);    // [4][Hp], rows >= cin zero
   float* s_b1 = reinterpret_cast<float*>(smb + p.o_b1);    // [Hp]
-  float* s_c = reinterpret_cast<float*>(smb + p.o_c);      // [FM][4] conditioner columns
-  float* s_v = reinterpret_cast<float*>(smb + p.o_v);      // [FM] value to transform
-  float* s_g = reinterpret_cast<float*>(smb + p.o_g);      // [FM] upstream gradient of the transformed column
+  float* s_c = reinterpret_cast<float*>(smb + p.o_c);      // [2][FM][4] conditioner columns (1 in column 0 when nc == 0)
+  float* s_v = reinterpret_cast<float*>(smb + p.o_v);      // [2][FM] value to transform
+  float* s_g = reinterpret_cast<float*>(smb + p.o_g);      // [2][FM] upstream gradient of the transformed column (BWD)
+  float* s_lp = reinterpret_cast<float*>(smb + p.o_lp);    // [2][FM] log-det accumulated so far (FWD, accumulate)
   float* s_gin = reinterpret_cast<float*>(smb + p.o_gin);  // [FM] gradient wrt the spline input
 
   if (warp == 0) {
@@ -195,40 +212,104 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar)) : "memory");
+    for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar[i])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  // heads matrix with the bias as row H (the ones column of hid multiplies it), split, zero padded to [Hp, RP]
-  for (int e = tid; e < Hp * RP; e += FT) {
-    const int j = e / RP, c = e - j * RP;
-    float w = 0.f;
-    if (c < R) {
-      if (j < H) w = __ldg(a.hW + (size_t)j * R + c);
-      else if (j == H) w = __ldg(a.hb + c);
+  // heads matrix with the bias as row H (the ones column of hid multiplies it), split, zero padded to [Hp, RP];
+  // four independent loads in flight per thread
+  for (int e0 = 0; e0 < Hp * RP; e0 += 4 * FT) {
+    float w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * FT + tid;
+      const int j = e / RP, c = e - j * RP;
+      w[u] = 0.f;
+      if (e < Hp * RP && c < R) {
+        if (j < H) w[u] = __ldg(a.hW + (size_t)j * R + c);
+        else if (j == H) w[u] = __ldg(a.hb + c);
+      }
     }
-    unsigned h1, h2, h3;
-    split3(w, h1, h2, h3);
-    const unsigned o = (unsigned)(j >> 3) * w_cs + (unsigned)c * 16u + (unsigned)(j & 7) * 2u;
-    *reinterpret_cast<unsigned short*>(wsm + o) = (unsigned short)(h1 >> 16);
-    *reinterpret_cast<unsigned short*>(wsm + w_sz + o) = (unsigned short)(h2 >> 16);
-    *reinterpret_cast<unsigned short*>(wsm + 2 * w_sz + o) = (unsigned short)(h3 >> 16);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * FT + tid;
+      if (e < Hp * RP) {
+        const int j = e / RP, c = e - j * RP;
+        unsigned h1, h2, h3;
+        split3(w[u], h1, h2, h3);
+        const unsigned o = (unsigned)(j >> 3) * w_cs + (unsigned)c * 16u + (unsigned)(j & 7) * 2u;
+        *reinterpret_cast<unsigned short*>(wsm + o) = (unsigned short)(h1 >> 16);
+        *reinterpret_cast<unsigned short*>(wsm + w_sz + o) = (unsigned short)(h2 >> 16);
+        *reinterpret_cast<unsigned short*>(wsm + 2 * w_sz + o) = (unsigned short)(h3 >> 16);
+      }
+    }
   }
-  for (int e = tid; e < p.cin * Hp; e += FT) {
+  for (int e = tid; e < 4 * Hp; e += FT) {
     const int c = e / Hp, j = e - c * Hp;
-    s_w1[e] = j < H ? __ldg(a.d1W + (size_t)c * H + j) : 0.f;
+    s_w1[e] = (c < cin && j < H) ? __ldg(a.d1W + (size_t)c * H + j) : 0.f;
   }
   for (int j = tid; j < Hp; j += FT) s_b1[j] = j < H ? __ldg(a.d1b + j) : 0.f;
   if (BWD)
     for (unsigned e = tid; e < 3 * graw_sz / 4; e += FT) reinterpret_cast<unsigned*>(graw)[e] = 0u;
+
+  const int64_t n_tiles = (a.B + FM - 1) / FM;
+  // ---- S1: a tile's inputs into buffer b
+  auto stage_inputs = [&](int64_t tile, int b) {
+    if (tid < FM) {
+      const int64_t row = tile * FM + tid;
+      const bool ok = row < a.B;
+      const float* ur = a.uin + row * dz;
+      s_v[b * FM + tid] = ok ? __ldg(ur + a.ts0) : 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        s_c[(b * FM + tid) * 4 + c] = (c < nc && ok) ? __ldg(ur + a.cs0 + c) : ((nc == 0 && c == 0) ? 1.f : 0.f);
+      if (BWD) s_g[b * FM + tid] = ok ? __ldg(a.g_cur + row * dz + a.ts0) : 0.f;
+      if (!BWD) s_lp[b * FM + tid] = (ok && a.accumulate) ? a.logpz[row] : 0.f;
+    }
+  };
+  // ---- S2: hid = tanh(cond @ d1W + d1b), ones column at j = H, split into buffer b (the A operand)
+  auto build_hid = [&](int b) {
+    const int r = tid & (FM - 1);
+    const float4 cn = *reinterpret_cast<const float4*>(s_c + (b * FM + r) * 4);
+    const float cnd[4] = {cn.x, cn.y, cn.z, cn.w};
+    unsigned char* hb_ = hid + (unsigned)b * 3u * hid_sz;
+    for (int jq = tid >> 6; jq < 2 * nchH; jq += FT / FM) {  // jq: group of 4 hidden units = half a chunk
+      const float4 b4 = *reinterpret_cast<const float4*>(s_b1 + 4 * jq);
+      float pre[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < cin) {
+          const float4 w4 = *reinterpret_cast<const float4*>(s_w1 + c * Hp + 4 * jq);
+          pre[0] = fmaf(cnd[c], w4.x, pre[0]); pre[1] = fmaf(cnd[c], w4.y, pre[1]);
+          pre[2] = fmaf(cnd[c], w4.z, pre[2]); pre[3] = fmaf(cnd[c], w4.w, pre[3]);
+        }
+      }
+      unsigned h1[4], h2[4], h3[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = 4 * jq + q;
+        const float h = j < H ? tanhf(pre[q]) : (j == H ? 1.f : 0.f);
+        split3(h, h1[q], h2[q], h3[q]);
+      }
+      const unsigned o = (unsigned)(jq >> 1) * CSB + (unsigned)r * 16u + (unsigned)(jq & 1) * 8u;
+      *reinterpret_cast<uint2*>(hb_ + o) = make_uint2(pack2(h1[0], h1[1]), pack2(h1[2], h1[3]));
+      *reinterpret_cast<uint2*>(hb_ + hid_sz + o) = make_uint2(pack2(h2[0], h2[1]), pack2(h2[2], h2[3]));
+      *reinterpret_cast<uint2*>(hb_ + 2 * hid_sz + o) = make_uint2(pack2(h3[0], h3[1]), pack2(h3[2], h3[3]));
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  };
   tc_sync();
   const unsigned tm = tmem_base_s;
-  const unsigned tD1a = tm, tD1b = tm + RP, tD2a = tm + 2 * RP, tD2b = tm + 2 * RP + 128;
+  const unsigned tD2 = tm + 2 * RP, tD3 = tm + 2 * RP + 128;  // raw of buffer b: tm + b * RP
   const unsigned id1 = idesc_bf16(FM, RP, 0, 0);
   const unsigned id2 = idesc_bf16(FM, Hp, 0, 1);
   const unsigned id3 = idesc_bf16(128, RP, 1, 1);
-  const unsigned bar = smem_u32(&mbar);
   const unsigned hid_a = smem_u32(hid), graw_a = smem_u32(graw), w_a = smem_u32(wsm);
-  unsigned phase = 0;
+  // raw = [hid, 1] @ [hW; hb]   (M = 64, N = RP, K = Hp in steps of 16), buffer b
+  auto issue_raw = [&](int b) {
+    issue_product(tm + (unsigned)b * RP, hid_a + (unsigned)b * 3u * hid_sz, hid_sz, 2u * CSB, CSB, 128, w_a, w_sz, 2u * w_cs,
+                  w_cs, 128, Hp / 16, id1);
+    mma_commit(smem_u32(&mbar[b]));
+  };
   bool failed = false;
 
   // reverse-mode accumulators, CTA lifetime.  d [hW; hb]: thread (TMEM quarter q = warp & 3, lane) owns hidden unit
@@ -242,66 +323,41 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
     for (int c = 0; c < kMaxC; ++c) acc_w1[c] = 0.f;
   }
 
-  const int64_t n_tiles = (a.B + FM - 1) / FM;
+  // pipeline prologue: tile 0 of this CTA
+  stage_inputs(blockIdx.x, 0);
+  __syncthreads();
+  build_hid(0);
+  tc_sync();
+  if (tid == 0) issue_raw(0);
+
+  int it = 0;
 #pragma unroll 1
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
     const int64_t row0 = tile * FM;
     const int nr = (int)min((int64_t)FM, a.B - row0);
-    // ---- S1: the tile's inputs
-    if (tid < FM) {
-      const bool ok = tid < nr;
-      const float* ur = a.uin + (row0 + tid) * dz;
-      s_v[tid] = ok ? __ldg(ur + a.ts0) : 0.f;
-      for (int c = 0; c < nc; ++c) s_c[tid * 4 + c] = ok ? __ldg(ur + a.cs0 + c) : 0.f;
-      if (BWD) s_g[tid] = ok ? __ldg(a.g_cur + (row0 + tid) * dz + a.ts0) : 0.f;
+    const int64_t next = tile + gridDim.x;
+    const bool has_next = next < n_tiles;
+    if (!BWD && has_next) {
+      // next tile's inputs and hid while the tensor core computes this tile's raw parameters
+      stage_inputs(next, b ^ 1);
+      __syncthreads();
+      build_hid(b ^ 1);
+      tc_sync();
+      if (tid == 0) issue_raw(b ^ 1);
     }
-    __syncthreads();
-    // ---- S2: hid = tanh(cond @ d1W + d1b), ones column at j = H, split and stored as the A operand
-    for (int e = tid; e < 2 * nchH * FM; e += FT) {
-      const int r = e & (FM - 1), jq = e >> 6;  // jq: group of 4 hidden units = half a chunk
-      unsigned h1[4], h2[4], h3[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j = 4 * jq + q;
-        float pre = s_b1[j];
-        if (nc == 0) pre += s_w1[j];
-        else
-          for (int c = 0; c < nc; ++c) pre = fmaf(s_c[r * 4 + c], s_w1[c * Hp + j], pre);
-        const float h = j < H ? tanhf(pre) : (j == H ? 1.f : 0.f);
-        split3(h, h1[q], h2[q], h3[q]);
-      }
-      const unsigned o = (unsigned)(jq >> 1) * CSB + (unsigned)r * 16u + (unsigned)(jq & 1) * 8u;
-      *reinterpret_cast<uint2*>(hid + o) = make_uint2(pack2(h1[0], h1[1]), pack2(h1[2], h1[3]));
-      *reinterpret_cast<uint2*>(hid + hid_sz + o) = make_uint2(pack2(h2[0], h2[1]), pack2(h2[2], h2[3]));
-      *reinterpret_cast<uint2*>(hid + 2 * hid_sz + o) = make_uint2(pack2(h3[0], h3[1]), pack2(h3[2], h3[3]));
-    }
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    tc_sync();
-    // ---- S3: raw = [hid, 1] @ [hW; hb]   (M = 64, N = RP, K = Hp in steps of 16)
-    if (tid == 0) {
-      for (int ks = 0; ks < Hp / 16; ++ks) {
-        const unsigned ao = (unsigned)ks * 2u * CSB, bo = (unsigned)ks * 2u * w_cs;
-        const unsigned aa[3] = {hid_a + ao, hid_a + hid_sz + ao, hid_a + 2 * hid_sz + ao};
-        const unsigned bb[3] = {w_a + bo, w_a + w_sz + bo, w_a + 2 * w_sz + bo};
-        mma6(tD1a, tD1b, aa, bb, CSB, 128, w_cs, 128, id1, ks == 0);
-      }
-      mma_commit(bar);
-    }
-    if (!mbar_wait_bounded(bar, phase)) failed = true;
-    phase ^= 1;
+    if (!mbar_wait_bounded(smem_u32(&mbar[b]), (unsigned)(it >> 1) & 1u)) failed = true;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     // ---- S4: TMEM -> shared memory (rows 16 q + lane live in lanes 0-15 of TMEM quarter q)
     {
       const int q = warp & 3, row = 16 * q + lane;
       for (int c0 = 16 * (warp >> 2); c0 < RP; c0 += 64) {
-        float v1[16], v2[16];
-        tmem_ld16(tD1a + ((unsigned)(32 * q) << 16) + (unsigned)c0, v1);
-        tmem_ld16(tD1b + ((unsigned)(32 * q) << 16) + (unsigned)c0, v2);
+        float v1[16];
+        tmem_ld16(tm + (unsigned)b * RP + ((unsigned)(32 * q) << 16) + (unsigned)c0, v1);
         if (lane < 16) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(s_raw + row * LDS + c0 + i) =
-                make_float4(v1[i] + v2[i], v1[i + 1] + v2[i + 1], v1[i + 2] + v2[i + 2], v1[i + 3] + v2[i + 3]);
+            *reinterpret_cast<float4*>(s_raw + row * LDS + c0 + i) = make_float4(v1[i], v1[i + 1], v1[i + 2], v1[i + 3]);
         }
       }
     }
@@ -311,7 +367,7 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
       const int r = tid >> 3, j = tid & 7;
       const bool ok = r < nr;
       const float* rr = s_raw + r * LDS;
-      const float v = s_v[r];
+      const float v = s_v[b * FM + r];
       if (!BWD) {
         float out, ldj, ldj_all;
         bool writer;
@@ -320,16 +376,13 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
         if (ok) {
           float* uo = a.uout + (row0 + r) * dz;
           if (writer) uo[a.ts0] = out;
-          if (j < nc) uo[a.cs0 + j] = s_c[r * 4 + j];
-          if (j == 0) {
-            float* lp = a.logpz + row0 + r;
-            *lp = a.accumulate ? *lp + ldj_all : ldj_all;
-          }
+          if (j < nc) uo[a.cs0 + j] = s_c[(b * FM + r) * 4 + j];
+          if (j == 0) a.logpz[row0 + r] = s_lp[b * FM + r] + ldj_all;
         }
       } else {
         float g_in, gw[4], gh[4], gs[4];
         bool writer;
-        rqsdev::octet_backward<4, true, false>(rr, rr + K, rr + 2 * K, v, s_g[r], ok ? a.g_ldj : 0.f, j, K, true,
+        rqsdev::octet_backward<4, true, false>(rr, rr + K, rr + 2 * K, v, s_g[b * FM + r], ok ? a.g_ldj : 0.f, j, K, true,
                                                a.bin_min, p.scale, g_in, writer, gw, gh, gs);
         if (writer) s_gin[r] = g_in;
         if (4 * j < K) {
@@ -356,47 +409,45 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
       tc_sync();
       // ---- S6: d hid = g_raw @ hW^T (M = 64, N = Hp, K = RP)  and  d [hW; hb] = [hid, 1]^T @ g_raw (M = 128, N = RP, K = 64)
       if (tid == 0) {
-        for (int ks = 0; ks < RP / 16; ++ks) {
-          const unsigned ao = (unsigned)ks * 2u * CSB, bo = (unsigned)ks * 256u;
-          const unsigned aa[3] = {graw_a + ao, graw_a + graw_sz + ao, graw_a + 2 * graw_sz + ao};
-          const unsigned bb[3] = {w_a + bo, w_a + w_sz + bo, w_a + 2 * w_sz + bo};
-          mma6(tD2a, tD2b, aa, bb, CSB, 128, 128, w_cs, id2, ks == 0);
-        }
-        for (int ks = 0; ks < FM / 16; ++ks) {
-          const unsigned o = (unsigned)ks * 256u;
-          const unsigned aa[3] = {hid_a + o, hid_a + hid_sz + o, hid_a + 2 * hid_sz + o};
-          const unsigned bb[3] = {graw_a + o, graw_a + graw_sz + o, graw_a + 2 * graw_sz + o};
-          mma6(tD1a, tD1b, aa, bb, 128, CSB, 128, CSB, id3, ks == 0);
-        }
-        mma_commit(bar);
+        issue_product(tD2, graw_a, graw_sz, 2u * CSB, CSB, 128, w_a, w_sz, 256u, 128, w_cs, RP / 16, id2);
+        issue_product(tD3, hid_a + (unsigned)b * 3u * hid_sz, hid_sz, 256u, 128, CSB, graw_a, graw_sz, 256u, 128, CSB,
+                      FM / 16, id3);
+        mma_commit(smem_u32(&mbar[2]));
       }
-      if (!mbar_wait_bounded(bar, phase)) failed = true;
-      phase ^= 1;
+      if (has_next) {
+        // next tile's inputs, hid and raw product behind this tile's gradient products
+        stage_inputs(next, b ^ 1);
+        __syncthreads();
+        build_hid(b ^ 1);
+        tc_sync();
+        if (tid == 0) issue_raw(b ^ 1);
+      }
+      if (!mbar_wait_bounded(smem_u32(&mbar[2]), (unsigned)it & 1u)) failed = true;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       // ---- S7a: d pre-activation = d hid * (1 - hid^2) -> shared memory (over the raw parameters, no longer needed)
       {
         const int q = warp & 3, row = 16 * q + lane;
+        const unsigned char* hb_ = hid + (unsigned)b * 3u * hid_sz;
         for (int c0 = 16 * (warp >> 2); c0 < Hp; c0 += 64) {
-          float v1[16], v2[16];
-          tmem_ld16(tD2a + ((unsigned)(32 * q) << 16) + (unsigned)c0, v1);
-          tmem_ld16(tD2b + ((unsigned)(32 * q) << 16) + (unsigned)c0, v2);
+          float v1[16];
+          tmem_ld16(tD2 + ((unsigned)(32 * q) << 16) + (unsigned)c0, v1);
           if (lane < 16) {
 #pragma unroll
             for (int i = 0; i < 16; i += 8) {
               const unsigned o = (unsigned)((c0 + i) >> 3) * CSB + (unsigned)row * 16u;
-              const uint4 p1 = *reinterpret_cast<const uint4*>(hid + o);
-              const uint4 p2 = *reinterpret_cast<const uint4*>(hid + hid_sz + o);
-              const uint4 p3 = *reinterpret_cast<const uint4*>(hid + 2 * hid_sz + o);
+              const uint4 p1 = *reinterpret_cast<const uint4*>(hb_ + o);
+              const uint4 p2 = *reinterpret_cast<const uint4*>(hb_ + hid_sz + o);
+              const uint4 p3 = *reinterpret_cast<const uint4*>(hb_ + 2 * hid_sz + o);
               const unsigned w1[4] = {p1.x, p1.y, p1.z, p1.w}, w2[4] = {p2.x, p2.y, p2.z, p2.w},
                              w3[4] = {p3.x, p3.y, p3.z, p3.w};
               float d[8];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const float ha = bf_lo(w1[t]) + bf_lo(w2[t]) + bf_lo(w3[t]);
-                const float hb_ = bf_hi(w1[t]) + bf_hi(w2[t]) + bf_hi(w3[t]);
+                const float hb2 = bf_hi(w1[t]) + bf_hi(w2[t]) + bf_hi(w3[t]);
                 const int j = c0 + i + 2 * t;
-                d[2 * t] = j < H ? (v1[i + 2 * t] + v2[i + 2 * t]) * (1.f - ha * ha) : 0.f;
-                d[2 * t + 1] = j + 1 < H ? (v1[i + 2 * t + 1] + v2[i + 2 * t + 1]) * (1.f - hb_ * hb_) : 0.f;
+                d[2 * t] = j < H ? v1[i + 2 * t] * (1.f - ha * ha) : 0.f;
+                d[2 * t + 1] = j + 1 < H ? v1[i + 2 * t + 1] * (1.f - hb2 * hb2) : 0.f;
               }
               *reinterpret_cast<float4*>(s_raw + row * LDS + c0 + i) = make_float4(d[0], d[1], d[2], d[3]);
               *reinterpret_cast<float4*>(s_raw + row * LDS + c0 + i + 4) = make_float4(d[4], d[5], d[6], d[7]);
@@ -411,11 +462,10 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
         for (int h = 0; h < 2; ++h) {
           const int c0 = 16 * (sub + 4 * h);
           if (c0 < RP) {
-            float v1[16], v2[16];
-            tmem_ld16(tD1a + ((unsigned)(32 * q) << 16) + (unsigned)c0, v1);
-            tmem_ld16(tD1b + ((unsigned)(32 * q) << 16) + (unsigned)c0, v2);
+            float v1[16];
+            tmem_ld16(tD3 + ((unsigned)(32 * q) << 16) + (unsigned)c0, v1);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc_w[h][i] += v1[i] + v2[i];
+            for (int i = 0; i < 16; ++i) acc_w[h][i] += v1[i];
           }
         }
       }
@@ -425,16 +475,14 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
         float s = 0.f, sc[kMaxC] = {0.f, 0.f, 0.f, 0.f};
         for (int r = 0; r < FM; ++r) {
           const float d = s_raw[r * LDS + tid];
+          const float4 cn = *reinterpret_cast<const float4*>(s_c + (b * FM + r) * 4);
           s += d;
-#pragma unroll
-          for (int c = 0; c < kMaxC; ++c)
-            if (c < nc) sc[c] = fmaf(s_c[r * 4 + c], d, sc[c]);
+          sc[0] = fmaf(cn.x, d, sc[0]); sc[1] = fmaf(cn.y, d, sc[1]);
+          sc[2] = fmaf(cn.z, d, sc[2]); sc[3] = fmaf(cn.w, d, sc[3]);
         }
         acc_b1 += s;
-        if (nc == 0) acc_w1[0] += s;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c)
-          if (c < nc) acc_w1[c] += sc[c];
+        for (int c = 0; c < kMaxC; ++c) acc_w1[c] += sc[c];
       } else if (tid >= 128 && tid < 256) {
         const int t2 = tid - 128, r = t2 >> 1, half = t2 & 1;
         float gc[kMaxC] = {0.f, 0.f, 0.f, 0.f};
@@ -457,7 +505,7 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
         }
       }
     }
-    __syncthreads();  // the next tile overwrites s_v / s_c / hid / raw
+    __syncthreads();  // s_raw, s_gin and the input buffers of this tile are free again
   }
 
   if (BWD) {
@@ -466,7 +514,7 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
       part[a.o_d1b + tid] = acc_b1;
 #pragma unroll
       for (int c = 0; c < kMaxC; ++c)
-        if (c < p.cin) part[a.o_d1W + (size_t)c * H + tid] = acc_w1[c];
+        if (c < cin) part[a.o_d1W + (size_t)c * H + tid] = acc_w1[c];
     }
     const int jj = 32 * (warp & 3) + lane, sub = warp >> 2;
 #pragma unroll
@@ -503,19 +551,20 @@ vms_status configure(const FlowTcArgs& a, bool bwd, KParams& p, int& RP, size_t&
   p.scale = (float)((double)a.bin_max - (double)a.bin_min - (double)a.K * 1e-2);
   int o = 0;  // bytes
   // d hW reads 16 chunk columns of the hid parts (M = 128): the over-read stays inside initialised shared memory
-  p.o_hid = o; o += 3 * (p.Hp / 8) * (int)CSB;
+  p.o_hid = o; o += 2 * 3 * (p.Hp / 8) * (int)CSB;
   p.o_graw = o; o += bwd ? 3 * (RP / 8) * (int)CSB : 0;
   p.o_w = o; o += 3 * (p.Hp / 8) * RP * 16;
   o = round_up(o, 16);
   p.o_raw = o; o += FM * p.LDS * 4;
-  p.o_w1 = o; o += p.cin * p.Hp * 4;
+  p.o_w1 = o; o += 4 * p.Hp * 4;
   p.o_b1 = o; o += p.Hp * 4;
-  p.o_c = o; o += FM * 4 * 4;
-  p.o_v = o; o += FM * 4;
-  p.o_g = o; o += FM * 4;
+  p.o_c = o; o += 2 * FM * 4 * 4;
+  p.o_v = o; o += 2 * FM * 4;
+  p.o_g = o; o += 2 * FM * 4;
+  p.o_lp = o; o += 2 * FM * 4;
   p.o_gin = o; o += FM * 4;
   smem = (size_t)o;
-  VMS_REQUIRE(smem + 2048 <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "flow_tc: tile does not fit shared memory");
+  VMS_REQUIRE(smem + 1024 <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "flow_tc: tile does not fit shared memory");
   return VMS_OK;
 }
 
