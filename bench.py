@@ -391,28 +391,66 @@ def mc_bench(v, grp, reps=3):
 
 
 
-def large_batch_leg(v, w, opt, batch=262144, steps=5):
-    """C5's single-GPU shard (BASELINE.json configs[4]: global batch 262,144): the same training step at a batch that keeps
-    every CTA of the persistent kernel busy for 55+ tiles.  Device-resident inputs, CUDA events."""
+def large_batch_leg(v, w, opt, grp, collective='auto', global_batch=262144, steps=5):
+    """C5 (BASELINE.json configs[4]: data-parallel training, GLOBAL batch 262,144): every rank takes 262,144 / N rows; one
+    step = ELBO forward + backward on the shard (auto mode: the tensor-core plan at these sizes) + the gradient exchange
+    (N > 1: the fused peer-memory allreduce + Adam kernel, NCCL fallback) + Adam.  Strong scaling.  Device-resident
+    inputs, CUDA events on the launching stream, max over ranks."""
+    from vaemolsim_b200 import parallel
     c = v._abi.ctx()
+    world, rank = grp.world, grp.rank
+    lo, hi = parallel.shard_rows(global_batch, rank, world)
+    batch = hi - lo
     model = build_model(v, w, batch)
     f = model.fused(batch)
-    rng = np.random.default_rng(77)
+    rng = parallel.global_row_seed(77, lo)
     x = v.Tensor.from_numpy(rng.standard_normal((batch, w['dx']), dtype=np.float32))
     e = v.Tensor.from_numpy(rng.standard_normal((batch, w['dz']), dtype=np.float32))
-    for _ in range(2):
-        f.train_step(x, e, opt)
+    peer = gt = None
+    if world > 1:
+        if collective in ('auto', 'peer'):
+            try:
+                peer = parallel.PeerExchange(grp, f.n_params)
+            except Exception as ex:
+                sys.stderr.write('bench (C5 leg): peer exchange unavailable (%s); using NCCL\n' % ex)
+        if peer is None:
+            gt, _ = grp.wrap_device_buffer(f.grad.ptr, f.n_params, c.stream)
+
+    def step():
+        if world == 1:
+            f.train_step(x, e, opt)
+        elif peer is not None:
+            f.forward_backward(x, e, grad_ptr=peer.next_slot())
+            peer.allreduce_adam(f, opt)
+        else:
+            f.forward_backward(x, e)
+            grp.allreduce_sum_(gt, host_sync=c.synchronize)
+            f.adam_step(opt, grad_scale=1.0 / world)
+
+    for _ in range(3):
+        step()
     ev = Events(c, 1)
     c.synchronize()
+    grp.barrier()
     ev.record(0)
     for _ in range(steps):
-        f.train_step(x, e, opt)
+        step()
     ev.record(1)
     c.synchronize()
-    ms = ev.elapsed_ms(0, 1) / steps
-    return {'workload': 'C5 shard: same model, batch %d on one GPU' % batch, 'ms_per_step': ms, 'plan': f.path(batch),
-            'configs_per_s': batch / (ms * 1e-3),
-            'tflops_fp32': batch * (259200 if w['prior'] != 'normal' else 28800) / (ms * 1e-3) / 1e12}
+    grp.barrier()
+    ms = grp.max(ev.elapsed_ms(0, 1)) / steps
+    timed_out = False
+    if peer is not None:
+        timed_out = grp.sum(1.0 if peer.timed_out() else 0.0) > 0.0
+        peer.close()
+    tc_bad = grp.sum(1.0 if f.tc_status() else 0.0) > 0.0
+    flop = 259200 if w['prior'] != 'normal' else 28800
+    return {'workload': 'C5: same model, GLOBAL batch %d over %d GPU(s) (%d rows per GPU), fwd + bwd + gradient exchange '
+                        '+ Adam' % (global_batch, world, batch),
+            'scaling': 'strong', 'ms_per_step': ms, 'plan': f.path(batch), 'configs_per_s': global_batch / (ms * 1e-3),
+            'collective': 'none' if world == 1 else ('peer kernel' if peer is not None else 'nccl'),
+            'tflops_fp32': global_batch * flop / (ms * 1e-3) / 1e12, 'valid': not (timed_out or tc_bad),
+            'last_loss': float(f.scalars.numpy()[0])}
 
 
 def run_b200(args, w):
@@ -559,6 +597,13 @@ def run_b200(args, w):
             replicas_ok = replicas_ok and grp.sum(1.0 if peer.timed_out() else 0.0) == 0.0
             peer.close()
     mc_line = None if args.no_extras else mc_bench(v, grp)
+    lb_line = None
+    if not args.no_extras:
+        try:
+            lb_line = large_batch_leg(v, w, opt, grp, args.collective)
+        except Exception as ex:  # the headline line must survive a failure of this extra leg
+            lb_line = {'error': '%s: %s' % (type(ex).__name__, ex)}
+            sys.stderr.write('bench (C5 leg) failed: %s\n' % lb_line['error'])
     if rank != 0:
         grp.close()
         return
@@ -617,7 +662,7 @@ def run_b200(args, w):
             'normal_log_prob@stream': micro['normal_log_prob@stream']['frac'],
             'dist_select@C3': micro['dist_select@C3']['frac']}
         line['kernels'] = micro
-        line['large_batch'] = large_batch_leg(v, w, opt)
+        line['large_batch'] = lb_line
         line['mc'] = mc_line
         line['mc']['cpu_baseline'] = mc_cpu_baseline()
         rows = batch
