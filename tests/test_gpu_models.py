@@ -282,7 +282,8 @@ def test_fused_kernel_agrees_with_unfused_plan(vms, prior, dz, B, bins):
     eps = v.as_tensor(rng.normal(size=(B, dz)).astype(np.float32))
     model = vae_from_oracle(v, P, weight=0.3)
     f = model.fused(B)
-    assert f.is_fused
+    f.set_tc_auto_batch(1 << 40)  # keep auto mode on the single fused kernel at every batch of this test
+    assert f.is_fused and f.path(B) == 'fused'
     out_f = {k: t.numpy() for k, t in f.forward(x, eps).items()}
     sc_f = f.forward_backward(x, eps).numpy().copy()
     g_f = f.grad.numpy().copy()
@@ -332,7 +333,9 @@ def test_tensor_core_plan_matches_oracle_and_ffma_plan(vms, dz, B, bins, fh, hid
     f.forward_backward(xt, et)
     assert np.array_equal(f.grad.numpy(), g_t), 'tensor-core plan is not deterministic'
     assert not f.tc_status(), 'a tensor-core completion wait timed out'
+    assert f.path(B) == 'tensor-core'
     f.set_mode(0)
+    assert f.path(B) == ('tensor-core' if B > 32 * 148 else 'fused')  # auto: second wave of the fused kernel's tiles
     for k in ('z', 'logq', 'logpz', 'logpx'):
         assert_close(out_t[k], out_u[k], rtol=1e-5, atol=2e-5, what='tensor-core vs FFMA plan %s' % k)
     rel = np.linalg.norm(g_t - g_u) / np.linalg.norm(g_u)

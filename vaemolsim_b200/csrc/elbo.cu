@@ -447,6 +447,9 @@ vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan) 
   pl->tc_ok = d.num_blocks > 0;
   for (auto& b : pl->blocks) pl->tc_ok = pl->tc_ok && flow_tc_supported(d.dz, b.cin, b.dt, d.flow_hidden, d.num_bins);
   pl->tc_ok = pl->tc_ok && mlp_stream_supported(d.dx, d.hidden, 2 * d.dz) && mlp_stream_supported(d.dz, d.hidden, 2 * d.dx);
+  // measured crossover (B200): the single fused kernel wins while its 32-row tiles fit one wave (B <= 32 x #SMs = 4736:
+  // 0.149 ms at 4096 against 0.238 ms); from the second wave on the tensor-core plan is faster (0.242 vs 0.313 ms at 6144)
+  pl->tc_auto_batch = 32 * (int64_t)sm_count() + 1;
   if (const char* e = getenv("VMS_TC_AUTO_BATCH")) {  // auto mode switches to the tensor-core plan from this batch on
     const long long v = atoll(e);
     if (v >= 64) pl->tc_auto_batch = v;

@@ -256,6 +256,11 @@ class FusedELBO(object):
         path, 2 = unfused plan with the coupling blocks as fused tcgen05 kernels (the large-batch configuration)."""
         ctx().lib.vms_elbo_plan_set_mode(self.handle, int(mode))
 
+    def set_tc_auto_batch(self, batch):
+        """Batch from which auto mode (0) prefers the tensor-core plan over the single fused kernel (default: one wave
+        of 32-row tiles, 32 x #SMs + 1)."""
+        ctx().lib.vms_elbo_plan_set_tc_auto_batch(self.handle, int(batch))
+
     def path(self, batch):
         """Implementation a step of `batch` rows takes: 'fused' (one persistent kernel), 'ffma' (per-layer float32
         plan) or 'tensor-core' (large-batch plan: tcgen05 coupling blocks + streaming MLP kernels)."""
