@@ -167,6 +167,12 @@ FlowTcArgs flow_tc_args(const vms_elbo_plan_s* pl, const float* theta, int i, in
   return ta;
 }
 
+// CTAs (= weight-gradient partials) of the large-batch MLP backward kernels: two per SM, 128-row tiles
+int mlp_grid(int64_t B) {
+  const int64_t tiles = (B + 127) / 128;
+  return (int)(tiles < 2 * sm_count() ? tiles : 2 * sm_count());
+}
+
 MlpArgs mlp_args(const vms_elbo_plan_s* pl, const float* theta, bool encoder, int64_t B) {
   const vms_elbo_desc& d = pl->d;
   const Offsets& o = pl->off;
@@ -272,7 +278,7 @@ vms_status backward_body(vms_elbo_plan_s* pl, const float* theta, const float* x
   if (tc) {
     MlpArgs ma = mlp_args(pl, theta, false, B);
     ma.in = z; ma.ld_in = d.dz; ma.g_out = pl->g_pd; ma.ld_g = 2 * d.dx; ma.g_in = pl->g_z; ma.ld_gin = d.dz;
-    VMS_TRY(mlp_stream_backward(ma, flow_tc_grid(B), st));
+    VMS_TRY(mlp_stream_backward(ma, mlp_grid(B), st));
   } else {
   VMS_TRY(dense_wgrad(pl, pl->hd, d.hidden, B, d.hidden, 2 * d.dx, VMS_ACT_NONE, nullptr, 0, pl->g_pd, 2 * d.dx,
                       o.dec1W, splits, st));
@@ -350,9 +356,14 @@ vms_status backward_body(vms_elbo_plan_s* pl, const float* theta, const float* x
   if (tc) {
     MlpArgs ma = mlp_args(pl, theta, true, B);
     ma.in = x; ma.ld_in = d.dx; ma.g_out = pl->g_pe; ma.ld_g = 2 * d.dz;
-    VMS_TRY(mlp_stream_backward(ma, flow_tc_grid(B), st));
-    // every layer's partials are per CTA of the large-batch kernels: one fixed-order sum over the whole flat gradient
-    VMS_TRY(sum_partials_launch(pl->tc_part, flow_tc_grid(B), o.total, o.total, grad, 0, nullptr, 1.f, 0, st));
+    VMS_TRY(mlp_stream_backward(ma, mlp_grid(B), st));
+    // every layer's partials are per CTA of the large-batch kernels: fixed-order sums over the flat gradient (the MLP
+    // kernels run two CTAs per SM, the coupling-block kernels one)
+    const int64_t flow0 = nb > 0 ? pl->blocks[0].off_d1W : o.total;
+    VMS_TRY(sum_partials_launch(pl->tc_part, mlp_grid(B), o.total, flow0, grad, 0, nullptr, 1.f, 0, st));
+    if (nb > 0)
+      VMS_TRY(sum_partials_launch(pl->tc_part + flow0, flow_tc_grid(B), o.total, o.total - flow0, grad + flow0, 0, nullptr,
+                                  1.f, 0, st));
     return VMS_OK;
   }
   VMS_TRY(dense_wgrad(pl, pl->he, d.hidden, B, d.hidden, 2 * d.dz, VMS_ACT_NONE, nullptr, 0, pl->g_pe, 2 * d.dz,
@@ -455,7 +466,7 @@ vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan) 
     if (v >= 64) pl->tc_auto_batch = v;
   }
   if (pl->tc_ok) {
-    A_(pl->tc_part, (size_t)sm_count() * pl->off.total);
+    A_(pl->tc_part, (size_t)2 * sm_count() * pl->off.total);
     float* e = nullptr;
     A_(e, 4);
     pl->tc_err = reinterpret_cast<int*>(e);

@@ -151,27 +151,33 @@ __device__ __forceinline__ unsigned idesc_bf16(int M, int N, int a_mn, int b_mn)
 // only the n_k leading steps accumulate at full magnitude.
 // a0 / b0: shared-memory address of part 1 at k-step 0; a_part / b_part: bytes between parts; a_step / b_step: bytes
 // per k-step; (al, as) / (bl, bs): the operands' LBO / SBO.
+// ONE thread issues every MMA of the CTA and the other 511 wait for it at the next barrier, so the issue path is kept
+// to an add per operand: the descriptors of the three parts are built once, a k-step / part offset only changes the
+// 14-bit start-address field (shared-memory addresses are < 256 KB: no carry out of the field).
 __device__ __forceinline__ void issue_product(unsigned acc, unsigned a0, unsigned a_part, unsigned a_step, unsigned al,
                                               unsigned as, unsigned b0, unsigned b_part, unsigned b_step, unsigned bl,
                                               unsigned bs, int n_k, unsigned idesc) {
+  const unsigned long long da1 = make_desc(a0, al, as), db1 = make_desc(b0, bl, bs);
+  const unsigned long long pa = a_part >> 4, pb = b_part >> 4, sa = a_step >> 4, sb = b_step >> 4;
+  const unsigned long long da2 = da1 + pa, da3 = da2 + pa, db2 = db1 + pb, db3 = db2 + pb;
   unsigned first = 0u;
+  unsigned long long ka = 0, kb = 0;
 #pragma unroll 1
-  for (int ks = 0; ks < n_k; ++ks) {
-    const unsigned a = a0 + ks * a_step, b = b0 + ks * b_step;
-    mma_bf16(acc, make_desc(a, al, as), make_desc(b + 2 * b_part, bl, bs), idesc, first);
+  for (int ks = 0; ks < n_k; ++ks, ka += sa, kb += sb) {
+    mma_bf16(acc, da1 + ka, db3 + kb, idesc, first);
     first = 1u;
-    mma_bf16(acc, make_desc(a + 2 * a_part, al, as), make_desc(b, bl, bs), idesc, 1u);
-    mma_bf16(acc, make_desc(a + a_part, al, as), make_desc(b + b_part, bl, bs), idesc, 1u);
+    mma_bf16(acc, da3 + ka, db1 + kb, idesc, 1u);
+    mma_bf16(acc, da2 + ka, db2 + kb, idesc, 1u);
   }
+  ka = kb = 0;
 #pragma unroll 1
-  for (int ks = 0; ks < n_k; ++ks) {
-    const unsigned a = a0 + ks * a_step, b = b0 + ks * b_step;
-    mma_bf16(acc, make_desc(a, al, as), make_desc(b + b_part, bl, bs), idesc, 1u);
-    mma_bf16(acc, make_desc(a + a_part, al, as), make_desc(b, bl, bs), idesc, 1u);
+  for (int ks = 0; ks < n_k; ++ks, ka += sa, kb += sb) {
+    mma_bf16(acc, da1 + ka, db2 + kb, idesc, 1u);
+    mma_bf16(acc, da2 + ka, db1 + kb, idesc, 1u);
   }
+  ka = kb = 0;
 #pragma unroll 1
-  for (int ks = 0; ks < n_k; ++ks)
-    mma_bf16(acc, make_desc(a0 + ks * a_step, al, as), make_desc(b0 + ks * b_step, bl, bs), idesc, 1u);
+  for (int ks = 0; ks < n_k; ++ks, ka += sa, kb += sb) mma_bf16(acc, da1 + ka, db1 + kb, idesc, 1u);
 }
 
 // Software pipeline (per CTA, tiles t0, t1, ... of 64 rows; hid / inputs / the raw accumulator are double-buffered):
@@ -252,18 +258,27 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
     for (unsigned e = tid; e < 3 * graw_sz / 4; e += FT) reinterpret_cast<unsigned*>(graw)[e] = 0u;
 
   const int64_t n_tiles = (a.B + FM - 1) / FM;
-  // ---- S1: a tile's inputs into buffer b
-  auto stage_inputs = [&](int64_t tile, int b) {
+  // ---- S1: a tile's inputs.  Threads 0..63 load their row of tile t into registers (pre) one tile ahead of its use and
+  // put them into buffer b an iteration later, so the global-load latency hides behind a whole tile of work.
+  float pre[6];  // v, cond[0..3], g (BWD) or the log-det accumulated so far (FWD)
+  auto load_inputs = [&](int64_t tile) {
     if (tid < FM) {
       const int64_t row = tile * FM + tid;
-      const bool ok = row < a.B;
+      const bool ok = tile < n_tiles && row < a.B;
       const float* ur = a.uin + row * dz;
-      s_v[b * FM + tid] = ok ? __ldg(ur + a.ts0) : 0.f;
+      pre[0] = ok ? __ldg(ur + a.ts0) : 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        s_c[(b * FM + tid) * 4 + c] = (c < nc && ok) ? __ldg(ur + a.cs0 + c) : ((nc == 0 && c == 0) ? 1.f : 0.f);
-      if (BWD) s_g[b * FM + tid] = ok ? __ldg(a.g_cur + row * dz + a.ts0) : 0.f;
-      if (!BWD) s_lp[b * FM + tid] = (ok && a.accumulate) ? a.logpz[row] : 0.f;
+      for (int c = 0; c < 4; ++c) pre[1 + c] = (c < nc && ok) ? __ldg(ur + a.cs0 + c) : ((nc == 0 && c == 0) ? 1.f : 0.f);
+      if (BWD) pre[5] = ok ? __ldg(a.g_cur + row * dz + a.ts0) : 0.f;
+      else pre[5] = (ok && a.accumulate) ? a.logpz[row] : 0.f;
+    }
+  };
+  auto put_inputs = [&](int b) {
+    if (tid < FM) {
+      s_v[b * FM + tid] = pre[0];
+      *reinterpret_cast<float4*>(s_c + (b * FM + tid) * 4) = make_float4(pre[1], pre[2], pre[3], pre[4]);
+      if (BWD) s_g[b * FM + tid] = pre[5];
+      else s_lp[b * FM + tid] = pre[5];
     }
   };
   // ---- S2: hid = tanh(cond @ d1W + d1b), ones column at j = H, split into buffer b (the A operand)
@@ -323,8 +338,10 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
     for (int c = 0; c < kMaxC; ++c) acc_w1[c] = 0.f;
   }
 
-  // pipeline prologue: tile 0 of this CTA
-  stage_inputs(blockIdx.x, 0);
+  // pipeline prologue: tile 0 of this CTA; the loads of tile 1 are in flight from here on
+  load_inputs(blockIdx.x);
+  put_inputs(0);
+  load_inputs((int64_t)blockIdx.x + gridDim.x);
   __syncthreads();
   build_hid(0);
   tc_sync();
@@ -340,7 +357,8 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
     const bool has_next = next < n_tiles;
     if (!BWD && has_next) {
       // next tile's inputs and hid while the tensor core computes this tile's raw parameters
-      stage_inputs(next, b ^ 1);
+      put_inputs(b ^ 1);
+      load_inputs(next + gridDim.x);
       __syncthreads();
       build_hid(b ^ 1);
       tc_sync();
@@ -416,7 +434,8 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
       }
       if (has_next) {
         // next tile's inputs, hid and raw product behind this tile's gradient products
-        stage_inputs(next, b ^ 1);
+        put_inputs(b ^ 1);
+        load_inputs(next + gridDim.x);
         __syncthreads();
         build_hid(b ^ 1);
         tc_sync();
