@@ -272,7 +272,8 @@ int64_t vms_elbo_param_count(const vms_elbo_desc* desc);
  * every RealNVP coupling block (flows.py:184-207 conditioner + spline, forward and reverse mode) as ONE tcgen05
  * kernel per block (flow_tc.cu: 3 x TF32, accumulators in TMEM, hidden layer and raw spline parameters never leave
  * the SM) -- the large-batch configuration; VMS_ERR_UNSUPPORTED when a block's shape does not fit (one transformed
- * dimension, <= 4 conditioner columns, hidden <= 103, num_bins <= 32 and a multiple of 4).
+ * dimension, <= 4 conditioner columns, 8 <= flow hidden <= 111, num_bins <= 32 and a multiple of 4, encoder / decoder
+ * widths dx, dz <= 7, 2 dx, 2 dz <= 16, hidden <= 240).
  * vms_elbo_plan_tc_status: synchronises the device and reports whether any tensor-core completion wait ran into its
  * bound since the last call (err = 1: results of that interval are invalid); clears the flag.                      */
 vms_status vms_elbo_plan_set_mode(vms_elbo_plan plan, int mode);

@@ -33,30 +33,6 @@ def main():
             f.forward_backward(x, e)
         c.synchronize()
         return
-    if os.environ.get('FLOW_TC_VARIANTS'):  # descriptor experiments: gradient segment norms per kernel variant
-        for var in [int(t) for t in os.environ['FLOW_TC_VARIANTS'].split(',')]:
-            os.environ['VMS_FLOW_TC_VARIANT'] = str(var)
-            B = 10007 + var
-            model = bench.build_model(v, w, B)
-            f = model.fused(B)
-            rng = np.random.default_rng(11)
-            x = v.Tensor.from_numpy(rng.standard_normal((B, w['dx']), dtype=np.float32))
-            e = v.Tensor.from_numpy(rng.standard_normal((B, w['dz']), dtype=np.float32))
-            g = {}
-            for mode in (1, 2):
-                f.set_mode(mode)
-                f.forward_backward(x, e)
-                c.synchronize()
-                g[mode] = f.grad.numpy().copy()
-            o = 5216
-            seg = dict(d1W=(o, o + 100), d1b=(o + 100, o + 200), hW=(o + 200, o + 9700), hb=(o + 9700, o + 9795))
-            print('variant %d (time-out %s): ' % (var, f.tc_status()) + '  '.join(
-                '%s |g2| %.3e |g1| %.3e err %.2e' % (k, np.linalg.norm(g[2][a:b]), np.linalg.norm(g[1][a:b]),
-                                                      np.linalg.norm(g[2][a:b] - g[1][a:b]) / np.linalg.norm(g[1][a:b]))
-                for k, (a, b) in seg.items()))
-            print('   hb g2', g[2][o + 9700:o + 9704], 'g1', g[1][o + 9700:o + 9704])
-            print('   d1b g2', g[2][o + 100:o + 104], 'g1', g[1][o + 100:o + 104])
-        return
     for B in batches:
         model = bench.build_model(v, w, B)
         f = model.fused(B)
