@@ -176,6 +176,19 @@ vms_status vms_blockwise_log_prob(const float* x, int64_t ld_x, const float* par
 vms_status vms_blockwise_params(const float* params, int64_t ld_p, int64_t B, int D, const int32_t* kind,
                                 const int32_t* loc_off, const int32_t* loc2_off, const int32_t* scale_off,
                                 int scale_mode, float* loc, float* scale, vms_stream stream);
+/* One sample per (row, dof) -- replaces `tfp.distributions.Blockwise.sample` over the per-dof distributions of
+ * dists.py:210-217 / :326-336 / :602-610 (used by mcmc.py:100-108 and models.py:139, :564).  Normal dofs: eps * scale +
+ * loc with eps [B, D] (ld_eps) given by the caller (parity mode) or, when eps is NULL, Philox4x32-10 + Box-Muller keyed by
+ * (seed, row, dof).  von Mises dofs: tfp's Best-Fisher rejection sampler on the same Philox stream, result wrapped to
+ * [-pi, pi).  TF's RNG streams are not reproducible outside TF: sampling parity is distributional, not bitwise.      */
+vms_status vms_blockwise_sample(const float* params, int64_t ld_p, int64_t B, int D, const int32_t* kind,
+                                const int32_t* loc_off, const int32_t* loc2_off, const int32_t* scale_off, int scale_mode,
+                                const float* eps, int64_t ld_eps, unsigned long long seed, float* out, int64_t ld_out,
+                                vms_stream stream);
+/* `IndependentDeterministic` log_prob (dists.py:688-704, tfp Deterministic): lp[B] = 0 where x == loc in every coordinate,
+ * -inf elsewhere. */
+vms_status vms_deterministic_log_prob(const float* x, int64_t ld_x, const float* loc, int64_t ld_loc, int64_t B, int D,
+                                      float* lp, vms_stream stream);
 /* Standard-normal base density used by every flowed prior in the reference's tests / notebooks
  * (tests/test_models.py:172-175): lp[B] (+)= sum_d -0.5 x^2 - 0.5 log 2pi.                                     */
 vms_status vms_std_normal_log_prob(const float* x, int64_t ld_x, int64_t B, int D, float* lp, int accumulate,

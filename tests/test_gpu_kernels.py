@@ -474,3 +474,61 @@ def test_adam_matches_oracle(vms):
         ovae.adam_step(th_o, g, m_o, v_o, t)
     assert_close(dT.numpy(), th_o, rtol=2e-6, atol=2e-7, what='adam theta')  # FMA contraction vs NumPy mul+add
     assert_close(dM.numpy(), m_o, rtol=2e-6, atol=2e-7, what='adam m')
+
+
+# ------------------------------------------------------------------------------------------------ blockwise sampling
+def test_blockwise_sample_normal_and_von_mises(vms):
+    """vms_blockwise_sample (tfp Blockwise.sample over the per-dof distributions of dists.py:210-217 / :602-610): Normal dofs
+    reproduce eps * scale + loc for a given eps; von Mises dofs (tfp's Best-Fisher rejection sampler on a Philox stream)
+    are checked distributionally against scipy's von Mises CDF (Kolmogorov-Smirnov) and the analytic mean resultant
+    length I1(k) / I0(k); samples are reproducible for a seed and wrapped to [-pi, pi)."""
+    import ctypes as C
+    from scipy import special, stats
+    v = vms
+    c = v._abi.ctx()
+    B, D = 100000, 4
+    rng = np.random.default_rng(8)
+    kappa = np.array([0.01, 1.0, 50.0], np.float32)
+    loc_vm = np.array([0.3, -2.5, 3.0], np.float32)
+    # params: [sin, cos, concentration] x 3 von Mises dofs, then [loc, scale] of one Normal dof; identity scale mode
+    P = np.zeros((B, 11), np.float32)
+    for i in range(3):
+        P[:, 3 * i], P[:, 3 * i + 1], P[:, 3 * i + 2] = 2.0 * np.sin(loc_vm[i]), 2.0 * np.cos(loc_vm[i]), kappa[i]
+    P[:, 9] = rng.normal(size=B).astype(np.float32)
+    P[:, 10] = rng.uniform(0.5, 2.0, B).astype(np.float32)
+    i32 = lambda a: (C.c_int32 * len(a))(*a)
+    kind, loc, loc2, sc = i32([1, 1, 1, 0]), i32([0, 3, 6, 9]), i32([1, 4, 7, -1]), i32([2, 5, 8, 10])
+    eps = rng.standard_normal((B, D), dtype=np.float32)
+    Pt, et = v.Tensor.from_numpy(P), v.Tensor.from_numpy(eps)
+
+    def draw(seed, with_eps):
+        out = v.Tensor((B, D))
+        c.lib.vms_blockwise_sample(Pt.ptr, 11, B, D, kind, loc, loc2, sc, 0, et.ptr if with_eps else None, D, seed, out.ptr,
+                                   D, c.stream)
+        return out.numpy()
+
+    x = draw(1234, True)
+    assert np.array_equal(x, draw(1234, True)) and not np.array_equal(x[:, :3], draw(1235, True)[:, :3])
+    assert_close(x[:, 3], eps[:, 3] * P[:, 10] + P[:, 9], rtol=1e-6, atol=1e-6, what='Normal dof from eps')
+    assert np.all(x[:, :3] >= -np.pi - 1e-6) and np.all(x[:, :3] <= np.pi + 1e-6)
+    for i in range(3):
+        dlt = np.angle(np.exp(1j * (x[:, i].astype(np.float64) - loc_vm[i])))
+        ks = stats.kstest(dlt, stats.vonmises(kappa[i]).cdf).statistic
+        assert ks < 2.2 / np.sqrt(B), ('von Mises KS', i, ks)
+        R = np.abs(np.mean(np.exp(1j * dlt)))
+        want = special.i1e(kappa[i]) / special.i0e(kappa[i])
+        assert abs(R - want) < 5.0 / np.sqrt(B), ('mean resultant length', i, R, want)
+    n = draw(77, False)[:, 3]  # Normal dof from the Philox stream
+    zs = (n - P[:, 9]) / P[:, 10]
+    assert abs(zs.mean()) < 5.0 / np.sqrt(B) and abs(zs.var() - 1.0) < 0.03
+    assert stats.kstest(zs, 'norm').statistic < 2.2 / np.sqrt(B)
+
+
+def test_deterministic_log_prob_on_device(vms):
+    v = vms
+    loc = np.arange(12, dtype=np.float32).reshape(4, 3)
+    d = v._protocols.Deterministic(v.Tensor.from_numpy(loc))
+    x = loc.copy()
+    x[2, 1] += 1.0
+    lp = d.log_prob(v.Tensor.from_numpy(x)).numpy()
+    assert np.array_equal(lp, np.array([0.0, 0.0, -np.inf, 0.0], np.float32))

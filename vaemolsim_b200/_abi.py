@@ -88,6 +88,10 @@ _SIGS = {
     'vms_blockwise_log_prob': (None, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_int, c_vp,
                                       c_int, c_vp]),
+    'vms_deterministic_log_prob': (None, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
+    'vms_blockwise_sample': (None, [c_vp, c_i64, c_i64, c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_int, c_vp, c_i64, C.c_ulonglong, c_vp,
+                                    c_i64, c_vp]),
     'vms_blockwise_params': (None, [c_vp, c_i64, c_i64, c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_int, c_vp, c_vp, c_vp]),
     'vms_std_normal_log_prob': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_vp]),

@@ -612,10 +612,6 @@ class Blockwise(Distribution):
                                    self._loc2, self._scale, self.scale_mode, loc.ptr, scale.ptr, c.stream)
         return loc, scale
 
-    def _host_params(self):
-        loc, scale = self.constrained_params()
-        return loc.numpy(), scale.numpy()
-
     def sample_with_noise(self, eps, want_log_prob=True):
         """Reparameterised Normal sample z = eps * scale + loc (and its log_prob) for planar all-Normal layouts."""
         c = ctx()
@@ -631,16 +627,16 @@ class Blockwise(Distribution):
             if eps is None:
                 eps = Tensor.from_numpy(rng().standard_normal((self._n, self.event_size), dtype=np.float32))
             return self.sample_with_noise(as_tensor(eps), want_log_prob=False)[0]
-        # interleaved layouts / von Mises dofs: host sampler (device von Mises sampler deferred)
-        loc, scale = self._host_params()
-        out = np.empty_like(loc)
-        for d, k in enumerate(self.kinds):
-            if k == DIST_NORMAL:
-                e = rng().standard_normal(self._n, dtype=np.float32) if eps is None else np.asarray(eps)[:, d]
-                out[:, d] = e * scale[:, d] + loc[:, d]
-            else:
-                out[:, d] = rng().vonmises(loc[:, d], scale[:, d])
-        return Tensor.from_numpy(out)
+        # interleaved layouts / von Mises dofs: one device kernel for every dof (vms_blockwise_sample: Normal from eps or
+        # Philox, von Mises by tfp's Best-Fisher rejection sampler); the host only draws the 64-bit stream seed
+        c = ctx()
+        out = Tensor((self._n, self.event_size))
+        e = None if eps is None else as_tensor(eps)
+        seed = int(rng().integers(0, 2**63 - 1))
+        c.lib.vms_blockwise_sample(self.params.ptr, self.params.ld, self._n, self.event_size, self._kind, self._loc,
+                                   self._loc2, self._scale, self.scale_mode, _ptr(e), 0 if e is None else e.ld, seed,
+                                   out.ptr, out.ld, c.stream)
+        return out
 
     def experimental_sample_and_log_prob(self, sample_shape=None, **kw):
         if sample_shape is None and self._planar_normal():
@@ -690,8 +686,12 @@ class Deterministic(Distribution):
         return self.loc.copy()
 
     def _log_prob_rows(self, x, **kw):
-        eq = np.all(x.numpy() == self.loc.numpy(), axis=-1)
-        return Tensor.from_numpy(np.where(eq, 0.0, -np.inf).astype(np.float32))
+        c = ctx()
+        x = as_tensor(x)
+        lp = Tensor((self.batch,))
+        c.lib.vms_deterministic_log_prob(x.ptr, x.ld, self.loc.ptr, self.loc.ld, self.batch, self.event_size, lp.ptr,
+                                         c.stream)
+        return lp
 
 
 class TransformedDistribution(Distribution):

@@ -171,6 +171,81 @@ __global__ void normal_lp_bwd_kernel(const float* __restrict__ x, int64_t ld_x, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ sampling
+// Philox4x32-10 (Salmon et al. 2011), counter = (row, dof, attempt), key = seed: samples do not depend on the launch
+// geometry or the rank count.  (TF's own RNG streams cannot be reproduced outside TF; sampling parity is distributional.)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float u01(unsigned a) { return ((float)a + 0.5f) * 2.3283064365386963e-10f; }  // (0, 1)
+
+// One sample per (row, dof) of a Blockwise distribution (dists.py:210-217, :326-336, :602-610 -> tfp sample):
+//   Normal     z = eps * scale + loc   (tfp Normal._sample_n; eps given, or Philox + Box-Muller)
+//   von Mises  tfp random_von_mises: Best & Fisher (1979) rejection sampler with a wrapped-Cauchy envelope,
+//              s = (1 + rho^2) / (2 rho) for concentration > 2e-2 (float32 cut-off) else 1 / concentration;
+//              sample = sign(u) acos(w) + loc, wrapped to [-pi, pi) by x - 2 pi round(x / 2 pi)   [TFP-recalled]
+__global__ void blockwise_sample_kernel(const float* __restrict__ params, int64_t ld_p, int64_t B, int D,
+                                        const BlockwiseSpec spec, int scale_mode, const float* __restrict__ eps,
+                                        int64_t ld_e, unsigned long long seed, float* __restrict__ out, int64_t ld_o) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int64_t b = i / D;
+  const int d = (int)(i - b * D);
+  const float* pr = params + b * ld_p;
+  const float sc = apply_scale(pr[spec.scale[d]], scale_mode);
+  const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+  if (spec.kind[d] == VMS_DIST_NORMAL) {
+    float e;
+    if (eps) {
+      e = eps[b * ld_e + d];
+    } else {
+      const uint4 r = philox4x32_10(make_uint4((unsigned)b, (unsigned)(b >> 32), (unsigned)d, 0u), key);
+      float sn, cs;
+      sincospif(2.f * u01(r.y), &sn, &cs);
+      e = sqrtf(-2.f * logf(u01(r.x))) * cs;
+    }
+    out[b * ld_o + d] = fmaf(e, sc, pr[spec.loc[d]]);
+    return;
+  }
+  const float loc = spec.loc2[d] >= 0 ? atan2f(pr[spec.loc[d]], pr[spec.loc2[d]]) : pr[spec.loc[d]];
+  const float k = sc;
+  const float r = 1.f + sqrtf(1.f + 4.f * k * k);
+  const float rho = (r - sqrtf(2.f * r)) / (2.f * k);
+  const float s = k > 2e-2f ? (1.f + rho * rho) / (2.f * rho) : 1.f / k;
+  float w = 0.f, u = 0.f;
+  for (unsigned attempt = 1; attempt <= 64; ++attempt) {  // acceptance is >= 0.66 for every concentration: 64 is never reached
+    const uint4 rnd = philox4x32_10(make_uint4((unsigned)b, (unsigned)(b >> 32), (unsigned)d, attempt), key);
+    u = 2.f * u01(rnd.x) - 1.f;
+    const float z = cospif(u);
+    w = (1.f + s * z) / (s + z);
+    const float y = k * (s - w);
+    const float v = u01(rnd.y);
+    if (y * (2.f - y) >= v || logf(y / v) + 1.f >= y) break;
+  }
+  w = fminf(fmaxf(w, -1.f), 1.f);
+  float x = copysignf(acosf(w), u) + loc;
+  x -= 6.283185307179586f * rintf(x * 0.15915494309189535f);
+  out[b * ld_o + d] = x;
+}
+
+// Independent(Deterministic(loc)).log_prob (dists.py:701-704): 0 where every coordinate equals loc, -inf elsewhere
+__global__ void deterministic_lp_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ loc,
+                                        int64_t ld_l, int64_t B, int D, float* __restrict__ lp) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  bool eq = true;
+  for (int d = 0; d < D; ++d) eq = eq && (x[b * ld_x + d] == loc[b * ld_l + d]);
+  lp[b] = eq ? 0.f : -INFINITY;
+}
+
 }  // namespace vms
 
 using namespace vms;
@@ -233,6 +308,31 @@ vms_status vms_blockwise_log_prob(const float* x, int64_t ld_x, const float* par
   blockwise_lp_kernel<<<(unsigned)((B + 127) / 128), 128, 0, as_stream(stream)>>>(x, ld_x, params, ld_p, B, D, spec,
                                                                                  scale_mode, lp, accumulate);
   VMS_LAUNCH_CHECK("blockwise_lp_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_blockwise_sample(const float* params, int64_t ld_p, int64_t B, int D, const int32_t* kind,
+                                const int32_t* loc_off, const int32_t* loc2_off, const int32_t* scale_off, int scale_mode,
+                                const float* eps, int64_t ld_eps, unsigned long long seed, float* out, int64_t ld_out,
+                                vms_stream stream) {
+  BlockwiseSpec spec = {};
+  vms_status s = make_spec(spec, B, D, kind, loc_off, loc2_off, scale_off, scale_mode);
+  if (s) return s;
+  VMS_REQUIRE(params && out, VMS_ERR_INVALID_ARG, "blockwise_sample: NULL pointer");
+  if (B == 0) return VMS_OK;
+  blockwise_sample_kernel<<<(unsigned)((B * D + 255) / 256), 256, 0, as_stream(stream)>>>(params, ld_p, B, D, spec,
+                                                                                         scale_mode, eps, ld_eps, seed,
+                                                                                         out, ld_out);
+  VMS_LAUNCH_CHECK("blockwise_sample_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_deterministic_log_prob(const float* x, int64_t ld_x, const float* loc, int64_t ld_loc, int64_t B, int D,
+                                      float* lp, vms_stream stream) {
+  VMS_REQUIRE(x && loc && lp && B >= 0 && D >= 1, VMS_ERR_INVALID_ARG, "deterministic_log_prob: bad arguments");
+  if (B == 0) return VMS_OK;
+  deterministic_lp_kernel<<<(unsigned)((B + 255) / 256), 256, 0, as_stream(stream)>>>(x, ld_x, loc, ld_loc, B, D, lp);
+  VMS_LAUNCH_CHECK("deterministic_lp_kernel");
   return VMS_OK;
 }
 
