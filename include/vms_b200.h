@@ -223,6 +223,24 @@ vms_status vms_axpby(const float* x, const float* y, float a, float b, int64_t n
 vms_status vms_affine_cols(const float* x, int64_t ld_x, int64_t B, int D, const float* scale, const float* shift,
                            int shift_first, float* out, int64_t ld_out, vms_stream stream);
 
+/* ------------------------------------------------------------------------------- batch normalisation (default off)
+ * Replaces tf.keras.layers.BatchNormalization inside FCDeepNN (mappings.py:113-114) and tfp.bijectors.BatchNormalization
+ * between flow blocks (flows.py:308-309, :623-624); both variants are off by default in the reference.
+ *   vms_batch_moments   mean[D], var[D] = tf.nn.moments(x, axis=0): two passes, biased variance, fixed-order sums;
+ *                       workspace: vms_batch_moments_workspace(B, D) bytes of device memory
+ *   vms_batchnorm_coeffs  per-column scale / shift for vms_affine_cols:
+ *                       denormalize == 0: x * inv + (beta - mean * inv), inv = rsqrt(var + eps) * gamma;
+ *                       denormalize != 0: x * r + (mean - beta * r), r = sqrt(var + eps) / gamma (the bijector's forward);
+ *                       ldj[1] (nullable) = +-(sum_d log gamma_d - 0.5 log(var_d + eps)): the map's log-det per row.
+ *                       gamma / beta may be NULL (1 / 0).
+ *   vms_broadcast_scalar  out[0..n) = *scalar (the per-row log-det vector of a Chain)                                 */
+size_t vms_batch_moments_workspace(int64_t B, int D);
+vms_status vms_batch_moments(const float* x, int64_t ld_x, int64_t B, int D, float* mean, float* var, void* workspace,
+                             vms_stream stream);
+vms_status vms_batchnorm_coeffs(const float* mean, const float* var, const float* gamma, const float* beta, int D, float eps,
+                                int denormalize, float* scale, float* shift, float* ldj, vms_stream stream);
+vms_status vms_broadcast_scalar(const float* scalar, int64_t n, float* out, vms_stream stream);
+
 /* ------------------------------------------------------------------------------- K6: DistanceSelection
  * Replaces `DistanceSelection.call` mappings.py:362-455 (TF sub / div / round / mul / reduce_sum / top_k / gather):
  *   local = coords - ref;  if box: local -= box * rint(local / box);  d2 = (lx^2 + ly^2) + lz^2 (no FMA);

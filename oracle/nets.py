@@ -159,3 +159,24 @@ def maf_block_orders(num_blocks, data_dim, order_seed):
             rng.shuffle(o)
             orders.append(o)
     return orders
+
+
+# ------------------------------------------------------------------------------------------------ batch normalisation
+def batch_norm_moments(x):
+    """tf.nn.moments(x, axes=[0]): mean, then the mean of squared differences (biased variance).  [TF-recalled]"""
+    mean = x.mean(axis=0)
+    return mean, ((x - mean) ** 2).mean(axis=0)
+
+
+def batch_norm_normalize(x, mean, var, gamma, beta, eps=1e-3):
+    """tf.nn.batch_normalization as used by tf.keras.layers.BatchNormalization (mappings.py:113-114) and by the INVERSE
+    of tfp.bijectors.BatchNormalization (flows.py:308-309): x * inv + (beta - mean * inv), inv = rsqrt(var + eps) * gamma;
+    log-det per row = sum(log gamma) - 0.5 sum(log(var + eps)).  [TF/TFP-recalled]"""
+    inv = gamma / np.sqrt(var + eps)
+    return x * inv + (beta - mean * inv), float(np.sum(np.log(gamma)) - 0.5 * np.sum(np.log(var + eps)))
+
+
+def batch_norm_denormalize(y, mean, var, gamma, beta, eps=1e-3):
+    """Forward of tfp.bijectors.BatchNormalization: y * r + (mean - beta * r), r = sqrt(var + eps) / gamma.  [TFP-recalled]"""
+    r = np.sqrt(var + eps) / gamma
+    return y * r + (mean - beta * r), float(-(np.sum(np.log(gamma)) - 0.5 * np.sum(np.log(var + eps))))

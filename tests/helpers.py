@@ -61,9 +61,10 @@ def vae_from_oracle(v, P, max_batch=4096, weight=1.0):
     model = models.VAE(enc, dec, prior, regularizer=losses.KLDivergenceEstimate(weight=weight))
     x0 = np.zeros((2, dx), np.float32)
     model(x0)  # build
-    for lay, (W, b) in zip(enc.mapping.layer_list, P['enc']):
+    dense = lambda m: [l for l in m.layer_list if hasattr(l, 'kernel')]
+    for lay, (W, b) in zip(dense(enc.mapping), P['enc']):
         lay.assign(W, b)
-    for lay, (W, b) in zip(dec.mapping.layer_list, P['dec']):
+    for lay, (W, b) in zip(dense(dec.mapping), P['dec']):
         lay.assign(W, b)
     if P['prior'] != 'normal':
         blocks = [b.bijector_fn for b in prior.flow.chain.bijectors[::-1]]

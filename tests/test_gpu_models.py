@@ -557,3 +557,72 @@ def test_fused_mc_multi_step_equals_single_steps_and_op_by_op_path(vms):
     assert_close(lq1.numpy() + model.prior(z1).log_prob(v.as_tensor(noise[0, :, 2:4])).numpy() +
                  model.decoder(v.as_tensor(noise[0, :, 2:4])).sample_with_noise(v.as_tensor(noise[0, :, 4:]))[1].numpy(),
                  tra['fwd'][0], rtol=1e-5, atol=3e-5, what='forward_log_p vs op-by-op path')
+
+
+# ------------------------------------------------------------------------------------------------ batch normalisation
+def test_batch_norm_layer_and_bijector_match_restatement(vms):
+    """tf.keras.layers.BatchNormalization (mappings.py:113-114) and tfp.bijectors.BatchNormalization (flows.py:308-309)
+    on the device (csrc/batchnorm.cu) against the NumPy restatement: inference and training statistics, moving-average
+    update, both directions of the bijector and its log-dets."""
+    from oracle import nets as onets
+    v = vms
+    PR = v._protocols
+    rng = np.random.default_rng(3)
+    B, D = 3001, 5
+    x = (rng.normal(size=(B, D)) * [1.0, 2.0, 0.5, 3.0, 1.5] + [0.5, -1.0, 2.0, 0.0, 4.0]).astype(np.float32)
+    gamma, beta = rng.uniform(0.5, 2.0, D).astype(np.float32), rng.normal(size=D).astype(np.float32)
+    lay = PR.KerasBatchNormalization()
+    out0 = lay(v.as_tensor(x)).numpy()  # inference with the initial moving statistics (0, 1)
+    assert_close(out0, x / np.sqrt(1.0 + 1e-3), rtol=1e-6, atol=1e-6, what='BN inference, initial statistics')
+    lay.state.gamma, lay.state.beta = v.Tensor.from_numpy(gamma), v.Tensor.from_numpy(beta)
+    mean, var = onets.batch_norm_moments(x.astype(np.float64))
+    out1 = lay(v.as_tensor(x), training=True).numpy()
+    want, _ = onets.batch_norm_normalize(x.astype(np.float64), mean, var, gamma, beta)
+    assert_close(out1, want, rtol=1e-5, atol=1e-5, what='BN training output')
+    assert_close(lay.state.moving_mean.numpy(), 0.01 * mean, rtol=1e-5, atol=1e-6, what='moving mean')
+    assert_close(lay.state.moving_variance.numpy(), 0.99 + 0.01 * var, rtol=1e-5, atol=1e-6, what='moving variance')
+    assert lay.count_params() == 4 * D
+    # bijector: inverse = normalisation (batch statistics when training), forward = de-normalisation (moving statistics)
+    bij = PR.BatchNormalization(training=True)
+    y, ildj = bij._inv(v.as_tensor(x))
+    want, want_ldj = onets.batch_norm_normalize(x.astype(np.float64), mean, var, np.ones(D), np.zeros(D))
+    assert_close(y.numpy(), want, rtol=1e-5, atol=1e-5, what='bijector inverse (training)')
+    assert_close(ildj.numpy(), np.full(B, want_ldj), rtol=1e-5, atol=1e-5, what='bijector ildj')
+    bij.training = False
+    mm, mv = bij.state.moving_mean.numpy().astype(np.float64), bij.state.moving_variance.numpy().astype(np.float64)
+    z, fldj = bij._fwd(v.as_tensor(x))
+    want, want_ldj = onets.batch_norm_denormalize(x.astype(np.float64), mm, mv, np.ones(D), np.zeros(D))
+    assert_close(z.numpy(), want, rtol=1e-5, atol=1e-5, what='bijector forward')
+    assert_close(fldj.numpy(), np.full(B, want_ldj), rtol=1e-5, atol=1e-5, what='bijector fldj')
+    back = bij.inverse(z).numpy()
+    assert_close(back, x, rtol=1e-5, atol=1e-5, what='bijector round trip')
+
+
+def test_batch_norm_variants_of_the_reference_layers(vms):
+    """Structure checks of the reference's own tests (tests/test_mappings.py:24-27, tests/test_flows.py:178-196,
+    tests/test_dists.py:172-189): layer counts, `training` plumbing, shapes."""
+    v = vms
+    PR = v._protocols
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(200, 6)).astype(np.float32)
+    nn = v.mappings.FCDeepNN(3, batch_norm=True)
+    out = nn(x)
+    assert len(nn.layer_list) == len(nn.hidden_dim) * 2 + 2 and out.shape == (200, 3)
+    assert not np.array_equal(nn(x, training=True).numpy(), out.numpy())
+    plain = v.mappings.FCDeepNN(3)
+    plain(x)
+    assert len(plain.layer_list) == len(plain.hidden_dim) + 2
+    for f_class in (v.flows.RQSSplineRealNVP, v.flows.RQSSplineMAF):
+        f = f_class(num_blocks=4, batch_norm=True)
+        y0 = f(x)
+        bn = [b for b in f.chain.bijectors if isinstance(b, PR.BatchNormalization)]
+        assert len(f.chain.bijectors) == 2 * f.num_blocks - 1 and len(bn) == 3 and not any(b.training for b in bn)
+        f(x, training=True)
+        assert all(b.training for b in bn)
+        assert y0.shape == x.shape and not np.array_equal(y0.numpy(), x)
+        f(x, training=False)
+        base = PR.StandardNormal(200, 6)
+        lp = f(base).log_prob(y0).numpy()
+        assert lp.shape == (200,) and np.all(np.isfinite(lp))
+        assert_close(f.chain.inverse(f.chain.forward(v.as_tensor(x))).numpy(), x, rtol=1e-4, atol=1e-4,
+                     what='flow with batch norm: round trip')

@@ -89,6 +89,10 @@ _SIGS = {
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_int, c_vp,
                                       c_int, c_vp]),
     'vms_deterministic_log_prob': (None, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
+    'vms_batch_moments_workspace': (c_size, [c_i64, c_int]),
+    'vms_batch_moments': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'vms_batchnorm_coeffs': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'vms_broadcast_scalar': (None, [c_vp, c_i64, c_vp, c_vp]),
     'vms_blockwise_sample': (None, [c_vp, c_i64, c_i64, c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_int, c_vp, c_i64, C.c_ulonglong, c_vp,
                                     c_i64, c_vp]),

@@ -196,6 +196,84 @@ class Dense(Layer):
         return out
 
 
+class _BatchNormState(object):
+    """gamma / beta / moving statistics of one batch-normalisation layer over D features and the device plumbing both
+    variants share (csrc/batchnorm.cu).  Keras defaults: momentum 0.99, epsilon 1e-3, gamma 1, beta 0, moving mean 0,
+    moving variance 1 (what `tf.keras.layers.BatchNormalization()` at mappings.py:114 and the default layer inside
+    `tfp.bijectors.BatchNormalization` at flows.py:309 / :624 create)."""
+
+    def __init__(self, D, momentum=0.99, epsilon=1e-3):
+        self.D, self.momentum, self.epsilon = int(D), float(momentum), float(epsilon)
+        self.gamma, self.beta = Tensor.from_numpy(np.ones(D, np.float32)), Tensor.zeros((D,))
+        self.moving_mean, self.moving_variance = Tensor.zeros((D,)), Tensor.from_numpy(np.ones(D, np.float32))
+        self._scale, self._shift, self._ldj = Tensor((D,)), Tensor((D,)), Tensor((1,))
+        self._mean, self._var = Tensor((D,)), Tensor((D,))
+
+    def weights(self):
+        return [self.gamma, self.beta, self.moving_mean, self.moving_variance]
+
+    def statistics(self, x, training):
+        """(mean, var) to normalise with: the batch moments (moving statistics updated) when training, else the
+        moving statistics."""
+        if not training:
+            return self.moving_mean, self.moving_variance
+        c = ctx()
+        B = x.shape[0]
+        ws = Tensor(((int(c.lib.vms_batch_moments_workspace(B, self.D)) + 3) // 4,))
+        c.lib.vms_batch_moments(x.ptr, x.ld, B, self.D, self._mean.ptr, self._var.ptr, ws.ptr, c.stream)
+        for mov, cur in ((self.moving_mean, self._mean), (self.moving_variance, self._var)):
+            c.lib.vms_axpby(mov.ptr, cur.ptr, self.momentum, 1.0 - self.momentum, self.D, mov.ptr, c.stream)
+        c.synchronize()  # the workspace is released when this frame returns
+        return self._mean, self._var
+
+    def apply(self, x, mean, var, denormalize, want_ldj=False):
+        c = ctx()
+        B = x.shape[0]
+        c.lib.vms_batchnorm_coeffs(mean.ptr, var.ptr, self.gamma.ptr, self.beta.ptr, self.D, self.epsilon,
+                                   1 if denormalize else 0, self._scale.ptr, self._shift.ptr,
+                                   self._ldj.ptr if want_ldj else None, c.stream)
+        out = Tensor((B, self.D))
+        c.lib.vms_affine_cols(x.ptr, x.ld, B, self.D, self._scale.ptr, self._shift.ptr, 0, out.ptr, out.ld, c.stream)
+        if not want_ldj:
+            return out, None
+        ldj = Tensor((B,))
+        c.lib.vms_broadcast_scalar(self._ldj.ptr, B, ldj.ptr, c.stream)
+        return out, ldj
+
+
+class KerasBatchNormalization(Layer):
+    """tf.keras.layers.BatchNormalization() over the last axis of a [B, D] tensor (mappings.py:113-114): batch moments
+    and a moving-average update when training, moving statistics otherwise.  Forward only: `VAE.fit` has no reverse mode
+    through batch statistics."""
+
+    def __init__(self, name='batch_normalization'):
+        super(KerasBatchNormalization, self).__init__(name=name)
+        self.state = None
+
+    def build(self, input_shape):
+        self.state = _BatchNormState(int(input_shape[-1]))
+        self._weights = self.state.weights()
+
+    def call(self, x, training=False):
+        if self.state is None:
+            self.build(x.shape)
+            self.built = True
+        mean, var = self.state.statistics(x, training)
+        return self.state.apply(x, mean, var, denormalize=False)[0]
+
+
+class Reshape(Layer):
+    """tf.keras.layers.Reshape(target_shape): the last entry of FCDeepNN.layer_list (mappings.py:123)."""
+
+    def __init__(self, target_shape, name='reshape'):
+        super(Reshape, self).__init__(name=name)
+        self.target_shape = tuple(target_shape)
+        self._weights = []
+
+    def call(self, x, training=False):
+        return x.reshape((x.shape[0],) + self.target_shape)
+
+
 # ---------------------------------------------------------------------------------------- MADE (AutoregressiveNetwork)
 def _input_order(event_size, input_order):
     if isinstance(input_order, str):
@@ -502,11 +580,32 @@ class Chain(Bijector):
 
 
 class BatchNormalization(Bijector):
-    """tfp.bijectors.BatchNormalization (flows.py:308-309, :623-624) -- SURVEY 8f rank 3, not built yet."""
+    """tfp.bijectors.BatchNormalization(training=...) as placed between flow blocks (flows.py:308-309, :623-624).
+    [TFP-recalled] The bijector's INVERSE is the normalisation (batch moments when `training`, which also updates the
+    moving statistics; moving statistics otherwise), its forward the de-normalisation with the moving statistics;
+    ildj = sum_d log gamma_d - 0.5 log(var_d + eps) for every row, fldj the negative with the moving variance."""
 
     def __init__(self, training=False, name='batch_normalization'):
-        raise NotImplementedError('BatchNormalization bijectors are not implemented in vaemolsim_b200 '
-                                  '(SURVEY.md 8f: deferred); use batch_norm=False')
+        self.training = training
+        self.name = name
+        self.state = None
+
+    def _state(self, v):
+        if self.state is None:
+            self.state = _BatchNormState(v.shape[1])
+        return self.state
+
+    def _fwd(self, x, **kw):
+        st = self._state(x)
+        return st.apply(x, st.moving_mean, st.moving_variance, denormalize=True, want_ldj=True)
+
+    def _inv(self, y, **kw):
+        st = self._state(y)
+        mean, var = st.statistics(y, self.training)
+        return st.apply(y, mean, var, denormalize=False, want_ldj=True)
+
+    def _layers(self):
+        return []
 
 
 # ================================================================================================ distributions

@@ -1,0 +1,133 @@
+// batchnorm.cu -- batch statistics and the (de)normalisation coefficients of the two batch-normalisation variants the
+// reference can switch on (both default off):
+//   tf.keras.layers.BatchNormalization between the Dense layers of FCDeepNN            (mappings.py:113-114)
+//   tfp.bijectors.BatchNormalization between the coupling blocks of the flows          (flows.py:308-309, :623-624)
+// [TF/TFP-recalled]  training: mean, var = tf.nn.moments(x, axis=0) (two passes, biased variance);
+//   normalise     out = x * inv + (beta - mean * inv),  inv = rsqrt(var + eps) * gamma      (tf.nn.batch_normalization)
+//   de-normalise  out = x * r + (mean - beta * r),      r = sqrt(var + eps) / gamma         (tfp bijector forward)
+//   log-det of the normalising direction (the bijector's INVERSE): sum_d log gamma_d - 0.5 log(var_d + eps)
+//   moving statistics: moving = moving * momentum + batch * (1 - momentum)   (vms_axpby)
+// The elementwise map itself is vms_affine_cols (reduce.cu) with the per-column scale / shift produced here, so a batch
+// norm costs one streaming pass (plus two reduction passes over the batch in training mode).  All sums run in a fixed
+// order (deterministic): per-split partials in double, then one thread per column adds the splits.
+#include "common.cuh"
+#include <math.h>
+
+namespace vms {
+
+namespace {
+
+constexpr int kRowsPerSplit = 1024;
+
+int n_splits(int64_t B) {
+  int64_t s = (B + kRowsPerSplit - 1) / kRowsPerSplit;
+  return (int)(s < 1 ? 1 : (s > 256 ? 256 : s));
+}
+
+// partial[split][d] = sum over the split's rows of (x - shift_d)^p, p = 1 or 2
+__global__ void __launch_bounds__(256) col_partial_kernel(const float* __restrict__ x, int64_t ld_x, int64_t B, int D,
+                                                          const float* __restrict__ shift, int square,
+                                                          double* __restrict__ partial) {
+  __shared__ double sh[8][33];
+  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + lane;
+  const int64_t rows = (B + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * rows, r1 = min(B, r0 + rows);
+  const float sft = (shift && d < D) ? shift[d] : 0.f;
+  double acc = 0.0;
+  if (d < D)
+    for (int64_t r = r0 + slot; r < r1; r += 8) {
+      const float v = x[r * ld_x + d] - sft;
+      acc += square ? (double)(v * v) : (double)v;
+    }
+  sh[slot][lane] = acc;
+  __syncthreads();
+  if (slot == 0 && d < D) {
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += sh[k][lane];
+    partial[(size_t)blockIdx.y * D + d] = s;
+  }
+}
+
+__global__ void col_final_kernel(const double* __restrict__ partial, int n_split, int D, double inv_n, float* __restrict__ out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  double s = 0.0;
+  for (int k = 0; k < n_split; ++k) s += partial[(size_t)k * D + d];
+  out[d] = (float)(s * inv_n);
+}
+
+__global__ void bn_coeffs_kernel(const float* __restrict__ mean, const float* __restrict__ var,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, int D, float eps,
+                                 int denormalize, float* __restrict__ scale, float* __restrict__ shift,
+                                 float* __restrict__ ldj) {
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float g = gamma ? gamma[d] : 1.f, b = beta ? beta[d] : 0.f;
+    if (!denormalize) {
+      const float inv = (1.0f / sqrtf(var[d] + eps)) * g;
+      scale[d] = inv;
+      shift[d] = b - mean[d] * inv;
+    } else {
+      const float r = sqrtf(var[d] + eps) / g;
+      scale[d] = r;
+      shift[d] = mean[d] - b * r;
+    }
+  }
+  if (threadIdx.x == 0 && ldj) {
+    double s = 0.0;
+    for (int d = 0; d < D; ++d) s += (double)logf(gamma ? gamma[d] : 1.f) - 0.5 * (double)logf(var[d] + eps);
+    *ldj = (float)(denormalize ? -s : s);
+  }
+}
+
+__global__ void broadcast_scalar_kernel(const float* __restrict__ s, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = *s;
+}
+
+}  // namespace
+
+}  // namespace vms
+
+using namespace vms;
+
+extern "C" {
+
+size_t vms_batch_moments_workspace(int64_t B, int D) { return (size_t)n_splits(B) * (size_t)(D > 0 ? D : 1) * sizeof(double); }
+
+vms_status vms_batch_moments(const float* x, int64_t ld_x, int64_t B, int D, float* mean, float* var, void* workspace,
+                             vms_stream stream) {
+  VMS_REQUIRE(x && mean && var && workspace, VMS_ERR_INVALID_ARG, "batch_moments: NULL pointer");
+  VMS_REQUIRE(B >= 1 && D >= 1 && ld_x >= D, VMS_ERR_SHAPE, "batch_moments: need B >= 1, D >= 1, ld_x >= D");
+  const int ns = n_splits(B);
+  cudaStream_t st = as_stream(stream);
+  double* part = (double*)workspace;
+  dim3 grid((D + 31) / 32, ns);
+  col_partial_kernel<<<grid, 256, 0, st>>>(x, ld_x, B, D, nullptr, 0, part);
+  VMS_LAUNCH_CHECK("col_partial_kernel");
+  col_final_kernel<<<(D + 127) / 128, 128, 0, st>>>(part, ns, D, 1.0 / (double)B, mean);
+  VMS_LAUNCH_CHECK("col_final_kernel");
+  col_partial_kernel<<<grid, 256, 0, st>>>(x, ld_x, B, D, mean, 1, part);
+  VMS_LAUNCH_CHECK("col_partial_kernel");
+  col_final_kernel<<<(D + 127) / 128, 128, 0, st>>>(part, ns, D, 1.0 / (double)B, var);
+  VMS_LAUNCH_CHECK("col_final_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_batchnorm_coeffs(const float* mean, const float* var, const float* gamma, const float* beta, int D, float eps,
+                                int denormalize, float* scale, float* shift, float* ldj, vms_stream stream) {
+  VMS_REQUIRE(mean && var && scale && shift && D >= 1 && eps >= 0.f, VMS_ERR_INVALID_ARG, "batchnorm_coeffs: bad arguments");
+  bn_coeffs_kernel<<<1, 256, 0, as_stream(stream)>>>(mean, var, gamma, beta, D, eps, denormalize, scale, shift, ldj);
+  VMS_LAUNCH_CHECK("bn_coeffs_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_broadcast_scalar(const float* scalar, int64_t n, float* out, vms_stream stream) {
+  VMS_REQUIRE(scalar && out && n >= 0, VMS_ERR_INVALID_ARG, "broadcast_scalar: bad arguments");
+  if (n == 0) return VMS_OK;
+  broadcast_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(scalar, n, out);
+  VMS_LAUNCH_CHECK("broadcast_scalar_kernel");
+  return VMS_OK;
+}
+
+}  // extern "C"

@@ -52,8 +52,6 @@ class FCDeepNN(P.Layer):
         self.hidden_dim = [hidden_dim] if isinstance(hidden_dim, (int, np.integer)) else hidden_dim
         self.periodic_dofs = periodic_dofs
         self.batch_norm = batch_norm
-        if batch_norm:
-            raise NotImplementedError('FCDeepNN(batch_norm=True) is not implemented in vaemolsim_b200 (SURVEY.md 8f)')
         self.activation = activation
         self.kernel_initializer = kernel_initializer
 
@@ -77,10 +75,16 @@ class FCDeepNN(P.Layer):
             lay.built = True
             self.layer_list.append(lay)
             width = hd
+            if self.batch_norm:  # mappings.py:113-114
+                bn = P.KerasBatchNormalization()
+                bn.build((None, width))
+                bn.built = True
+                self.layer_list.append(bn)
         last = P.Dense(int(np.prod(self.target_shape)), activation=None, kernel_initializer=self.kernel_initializer)
         last.build((None, width))
         last.built = True
         self.layer_list.append(last)
+        self.layer_list.append(P.Reshape(self.target_shape))  # mappings.py:123
 
     def call(self, inputs, training=False):
         x = as_tensor(inputs).contig()
@@ -91,8 +95,8 @@ class FCDeepNN(P.Layer):
             c.lib.vms_periodic_featurise(out.ptr, out.shape[0], out.shape[1], self._periodic_dev.ptr, feat.ptr, c.stream)
             out = feat
         for layer in self.layer_list:
-            out = layer.call(out)
-        return out.reshape((out.shape[0], ) + self.target_shape)
+            out = layer.call(out) if isinstance(layer, P.Dense) else layer.call(out, training=training)
+        return out
 
     def get_config(self):
         config = super(FCDeepNN, self).get_config()

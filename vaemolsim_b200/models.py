@@ -230,9 +230,11 @@ class FusedELBO(object):
         fc = m.mapping
         if not fc.built:
             raise RuntimeError('fused ELBO: call the model once on data before training so its layers are built')
-        if fc.any_periodic or len(fc.layer_list) != 2 or fc.layer_list[0].act != P.ACT['relu']:
-            raise NotImplementedError('fused ELBO: %s FCDeepNN must have one relu hidden layer, no periodic dofs' % what)
-        l0, l1 = fc.layer_list
+        dense = [l for l in fc.layer_list if isinstance(l, P.Dense)]
+        if fc.any_periodic or fc.batch_norm or len(dense) != 2 or dense[0].act != P.ACT['relu']:
+            raise NotImplementedError('fused ELBO: %s FCDeepNN must have one relu hidden layer, no periodic dofs, no '
+                                      'batch normalisation' % what)
+        l0, l1 = dense
         return [l0, l1], l0.kernel.shape[0], l1.units // 2, l0.units
 
     @staticmethod
