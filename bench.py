@@ -445,11 +445,27 @@ def large_batch_leg(v, w, opt, grp, collective='auto', global_batch=262144, step
         peer.close()
     tc_bad = grp.sum(1.0 if f.tc_status() else 0.0) > 0.0
     flop = 259200 if w['prior'] != 'normal' else 28800
+    # bf16 MMA work the coupling-block kernels issue per 64-row tile and block (flow_tc.cu: six MMAs per float32 product):
+    # forward 7 k-steps of 64 x 96 x 16, backward the same recompute + 6 k-steps of 64 x 112 x 16 + 4 of 128 x 96 x 16
+    mma = lambda m, n, k: 2.0 * m * n * k
+    per_tile = 6 * (2 * 7 * mma(64, 96, 16) + 6 * mma(64, 112, 16) + 4 * mma(128, 96, 16))
+    mma_flop = per_tile * ((batch + 63) // 64) * w['num_blocks'] * world if f.path(batch) == 'tensor-core' else 0.0
+    try:
+        bf16_peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('bf16_tflops', 1590.0))
+    except (OSError, ValueError):
+        bf16_peak = 1590.0
+    tensor = {'bound': 'tensor', 'kernel': 'flow_tc_kernel<fwd|bwd> (8 launches per step)', 'unit': 'TFLOP/s',
+              'bf16_mma_flop_per_step': mma_flop, 'achieved_over_whole_step': mma_flop / (ms * 1e-3) / 1e12 / world,
+              'peak': bf16_peak, 'frac_over_whole_step': mma_flop / (ms * 1e-3) / 1e12 / world / bf16_peak,
+              'note': 'MMA FLOPs actually issued (3 x BF16 split: six bf16 MMAs per float32 product) divided by the WHOLE '
+                      'step time per GPU -- a lower bound of the kernels\' own rate (they are ~80 % of the step); ncu: '
+                      'tensor pipe active 15-18 % (profiles/r01_ncu_flow_tc_pipelined.txt)'}
     return {'workload': 'C5: same model, GLOBAL batch %d over %d GPU(s) (%d rows per GPU), fwd + bwd + gradient exchange '
                         '+ Adam' % (global_batch, world, batch),
             'scaling': 'strong', 'ms_per_step': ms, 'plan': f.path(batch), 'configs_per_s': global_batch / (ms * 1e-3),
             'collective': 'none' if world == 1 else ('peer kernel' if peer is not None else 'nccl'),
-            'tflops_fp32': global_batch * flop / (ms * 1e-3) / 1e12, 'valid': not (timed_out or tc_bad),
+            'tflops_fp32': global_batch * flop / (ms * 1e-3) / 1e12, 'roofline': tensor,
+            'valid': not (timed_out or tc_bad),
             'last_loss': float(f.scalars.numpy()[0])}
 
 

@@ -153,7 +153,9 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 // mode 2 (or auto at large batches): the flow blocks run as fused tensor-core kernels
 bool plan_uses_tc(const vms_elbo_plan_s* pl, int64_t B) {
   if (!pl->tc_ok || B < 64) return false;
-  return pl->mode == 2 || (pl->mode == 0 && B >= pl->tc_auto_batch);
+  // auto: above one wave of the fused kernel's tiles; or, when the single fused kernel does not support the shape,
+  // from the batch where the tensor-core plan's ~0.23 ms floor beats the per-layer FFMA plan
+  return pl->mode == 2 || (pl->mode == 0 && (B >= pl->tc_auto_batch || (!pl->fused && B >= 1024)));
 }
 
 FlowTcArgs flow_tc_args(const vms_elbo_plan_s* pl, const float* theta, int i, int64_t B) {

@@ -489,32 +489,44 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
         }
       }
       tc_sync();
-      // ---- S7c: d d1b / d d1W (column sums over the tile's rows), gradient wrt the conditioner columns, g_nxt
-      if (tid < Hp) {
-        float s = 0.f, sc[kMaxC] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = 0; r < FM; ++r) {
-          const float d = s_raw[r * LDS + tid];
-          const float4 cn = *reinterpret_cast<const float4*>(s_c + (b * FM + r) * 4);
-          s += d;
-          sc[0] = fmaf(cn.x, d, sc[0]); sc[1] = fmaf(cn.y, d, sc[1]);
-          sc[2] = fmaf(cn.z, d, sc[2]); sc[3] = fmaf(cn.w, d, sc[3]);
-        }
-        acc_b1 += s;
+      // ---- S7c: d d1b / d d1W (column sums over the tile's rows: thread = (hidden unit, quarter of the rows), each
+      // with its own CTA-lifetime accumulators), then the gradient wrt the conditioner columns (one octet per row) and g_nxt
+      {
+        const int j = tid & 127, part = tid >> 7;
+        if (j < Hp) {
+          float s = 0.f, sc[kMaxC] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+          for (int r = part * (FM / 4); r < (part + 1) * (FM / 4); ++r) {
+            const float d = s_raw[r * LDS + j];
+            const float4 cn = *reinterpret_cast<const float4*>(s_c + (b * FM + r) * 4);
+            s += d;
+            sc[0] = fmaf(cn.x, d, sc[0]); sc[1] = fmaf(cn.y, d, sc[1]);
+            sc[2] = fmaf(cn.z, d, sc[2]); sc[3] = fmaf(cn.w, d, sc[3]);
+          }
+          acc_b1 += s;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) acc_w1[c] += sc[c];
-      } else if (tid >= 128 && tid < 256) {
-        const int t2 = tid - 128, r = t2 >> 1, half = t2 & 1;
+          for (int c = 0; c < kMaxC; ++c) acc_w1[c] += sc[c];
+        }
+      }
+      {
+        const int r = tid >> 3, l = tid & 7;
         float gc[kMaxC] = {0.f, 0.f, 0.f, 0.f};
-        const int j0 = half * (Hp / 2), j1 = j0 + Hp / 2;
-        for (int j = j0; j < j1; ++j) {
-          const float d = s_raw[r * LDS + j];
+        if (nc > 0) {
+          const int j0 = l * (Hp / 8), j1 = j0 + Hp / 8;
+          for (int j = j0; j < j1; ++j) {
+            const float d = s_raw[r * LDS + j];
 #pragma unroll
-          for (int c = 0; c < kMaxC; ++c)
-            if (c < nc) gc[c] = fmaf(d, s_w1[c * Hp + j], gc[c]);
+            for (int c = 0; c < kMaxC; ++c)
+              if (c < nc) gc[c] = fmaf(d, s_w1[c * Hp + j], gc[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < kMaxC; ++c) {
+            gc[c] += __shfl_xor_sync(0xffffffffu, gc[c], 1);
+            gc[c] += __shfl_xor_sync(0xffffffffu, gc[c], 2);
+            gc[c] += __shfl_xor_sync(0xffffffffu, gc[c], 4);
+          }
         }
-#pragma unroll
-        for (int c = 0; c < kMaxC; ++c) gc[c] += __shfl_xor_sync(0xffffffffu, gc[c], 1);
-        if (half == 0 && r < nr) {
+        if (l == 0 && r < nr) {
           float* gn = a.g_nxt + (row0 + r) * dz;
           const float* gcur = a.g_cur + (row0 + r) * dz;
           gn[a.ts0] = s_gin[r];
@@ -529,11 +541,25 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
 
   if (BWD) {
     float* part = a.part + (size_t)blockIdx.x * a.part_stride;
-    if (tid < H) {
-      part[a.o_d1b + tid] = acc_b1;
+    {
+      // the four row-quarter accumulators of every hidden unit meet in shared memory (fixed order)
+      float* red = s_raw;  // [4][Hp][5]
+      const int j = tid & 127, pq = tid >> 7;
+      if (j < Hp) {
+        float* q = red + (pq * Hp + j) * 5;
+        q[0] = acc_b1; q[1] = acc_w1[0]; q[2] = acc_w1[1]; q[3] = acc_w1[2]; q[4] = acc_w1[3];
+      }
+      __syncthreads();
+      if (tid < H) {
+        float t[5];
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c)
-        if (c < cin) part[a.o_d1W + (size_t)c * H + tid] = acc_w1[c];
+        for (int k = 0; k < 5; ++k) t[k] = ((red[(0 * Hp + tid) * 5 + k] + red[(1 * Hp + tid) * 5 + k]) +
+                                            red[(2 * Hp + tid) * 5 + k]) + red[(3 * Hp + tid) * 5 + k];
+        part[a.o_d1b + tid] = t[0];
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c)
+          if (c < cin) part[a.o_d1W + (size_t)c * H + tid] = t[1 + c];
+      }
     }
     const int jj = 32 * (warp & 3) + lane, sub = warp >> 2;
 #pragma unroll
