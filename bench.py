@@ -583,15 +583,33 @@ def run_b200(args, w):
             f.adam_step(opt, grad_scale=1.0 / world)
         return f.scalars.numpy()  # D2H of {loss, nll, kl}: synchronises the step
 
-    for i in range(3):
-        e2e_step(i)
-    grp.barrier()
-    c.synchronize()
-    t0 = time.perf_counter()
-    for i in range(K):
-        last = e2e_step(i)
-    c.synchronize()
-    e2e_s = grp.max(time.perf_counter() - t0)
+    e2e_api = 'FusedELBO.train_step (the call behind VAE.train_step / VAE.fit)'
+    if world == 1:
+        # the public training loop (`VAE.fit` -> FusedELBO.train_loop): every step's x and eps leave PINNED host memory on
+        # a copy stream while the previous step trains, every step's {loss, nll, kl} is read back (ring of 8 steps)
+        e2e_api = 'VAE.fit inner loop (FusedELBO.train_loop): per-step H2D of x / eps, step, loss read-back, pipelined'
+        xh = pinned_array(lib, (n_sets * batch, w['dx']))
+        eh = pinned_array(lib, (n_sets * batch, w['dz']))
+        for k in range(n_sets):
+            xh[k * batch:(k + 1) * batch] = xs_host[k]
+            eh[k * batch:(k + 1) * batch] = es_host[k]
+        f.train_loop(xh, opt, batch, eps_host=eh, n_steps=8)
+        c.synchronize()
+        t0 = time.perf_counter()
+        scal = f.train_loop(xh, opt, batch, eps_host=eh, n_steps=K)
+        c.synchronize()
+        e2e_s = time.perf_counter() - t0
+        last = scal[-1]
+    else:
+        for i in range(3):
+            e2e_step(i)
+        grp.barrier()
+        c.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            last = e2e_step(i)
+        c.synchronize()
+        e2e_s = grp.max(time.perf_counter() - t0)
     e2e_value = world * batch * K / e2e_s
     # keep the same load going until the clock sampler has a few samples inside a loaded window
     # (the decision is rank 0's, shared with every rank: step() contains the gradient exchange when N > 1, so all ranks
@@ -637,7 +655,9 @@ def run_b200(args, w):
                    'wall_s_timed_region_incl_flush': wall1 - wall0},
         'e2e': {'value': e2e_value, 'unit': UNIT,
                 'h2d_bytes_per_step': int(xs_host[0].nbytes + es_host[0].nbytes), 'd2h_bytes_per_step': 16,
-                'ms_per_step': e2e_s / K * 1e3, 'api': 'FusedELBO.train_step (the call behind VAE.train_step / VAE.fit)',
+                'ms_per_step': e2e_s / K * 1e3, 'api': e2e_api,
+                'note': 'back-to-back steps (L2 stays warm across steps), whereas `value` flushes L2 before every timed step: '
+                        'e2e can therefore exceed `value`; every step still pays its own H2D (x, eps) and loss read-back',
                 'last_loss': float(last[0])},
         'gpu_launches': int(launches),
         'clocks': clocks,

@@ -64,6 +64,7 @@ vms_status vms_device_synchronize(void);
 vms_status vms_event_create(vms_event* ev);
 vms_status vms_event_destroy(vms_event ev);
 vms_status vms_event_record(vms_event ev, vms_stream stream);
+vms_status vms_stream_wait_event(vms_stream stream, vms_event ev); /* later work on `stream` waits for `ev` (device side) */
 vms_status vms_event_synchronize(vms_event ev);
 vms_status vms_event_elapsed_ms(vms_event start, vms_event stop, float* ms);
 /* counts kernels launched by this library in this process (bench.py's `gpu_launches`) */
@@ -189,6 +190,10 @@ vms_status vms_blockwise_sample(const float* params, int64_t ld_p, int64_t B, in
  * -inf elsewhere. */
 vms_status vms_deterministic_log_prob(const float* x, int64_t ld_x, const float* loc, int64_t ld_loc, int64_t B, int D,
                                       float* lp, vms_stream stream);
+/* out[0..n) ~ N(0, 1): Philox4x32-10 + Box-Muller, element i drawn from counter (offset + i) / 4 under key `seed`, so a
+ * stream continues across calls by advancing `offset` (the reparameterisation noise of models.py:310 when the caller does
+ * not supply eps; TF's own streams are not reproducible outside TF). */
+vms_status vms_standard_normal(unsigned long long seed, unsigned long long offset, int64_t n, float* out, vms_stream stream);
 /* Standard-normal base density used by every flowed prior in the reference's tests / notebooks
  * (tests/test_models.py:172-175): lp[B] (+)= sum_d -0.5 x^2 - 0.5 log 2pi.                                     */
 vms_status vms_std_normal_log_prob(const float* x, int64_t ld_x, int64_t B, int D, float* lp, int accumulate,

@@ -402,6 +402,52 @@ def test_training_reduces_loss_and_matches_oracle_adam(vms):
     assert model.predict(x[:10]).shape == (10, 6)
 
 
+def test_pipelined_train_loop_equals_step_by_step(vms):
+    """FusedELBO.train_loop (the loop behind VAE.fit: copy stream, double-buffered inputs, scalar ring read back every 8
+    steps) must be the SAME training run as one synchronous train_step per batch: identical per-step scalars and
+    bit-identical parameters; 11 steps (ring wrap-around), ragged last batch, with and without a row permutation."""
+    v = vms
+    rng = np.random.default_rng(4)
+    N, bs = 11 * 96 - 40, 96
+    x = rng.normal(size=(N, 6)).astype(np.float32)
+    eps = rng.normal(size=(N, 2)).astype(np.float32)
+    opt = v.models.Adam(learning_rate=1e-3)
+
+    def fresh():
+        P = ovae.init_vae(12, prior='realnvp', flow_hidden=16, num_bins=8, hidden=32)
+        return vae_from_oracle(v, P).fused(bs)
+
+    f1 = fresh()
+    want = []
+    for s0 in range(0, N, bs):
+        sc = f1.train_step(v.as_tensor(x[s0:s0 + bs]), v.as_tensor(eps[s0:s0 + bs]), opt).numpy()
+        want.append(sc[:3].copy())
+    f2 = fresh()
+    got = f2.train_loop(x, opt, bs, eps_host=eps)
+    assert got.shape == (11, 3)
+    assert np.array_equal(got, np.array(want)), 'per-step scalars differ'
+    assert np.array_equal(f1.theta.numpy(), f2.theta.numpy()), 'parameters differ'
+    assert np.array_equal(f2.scalars.numpy()[:3], want[-1])
+    # shuffled epoch with device-drawn noise: runs, finite, reproducible for a seed
+    order = rng.permutation(N)
+    f3, f4 = fresh(), fresh()
+    a = f3.train_loop(x, opt, bs, order=order, seed=99)
+    b = f4.train_loop(x, opt, bs, order=order, seed=99)
+    assert np.all(np.isfinite(a)) and np.array_equal(a, b) and np.array_equal(f3.theta.numpy(), f4.theta.numpy())
+
+
+def test_standard_normal_stream_continues_across_calls(vms):
+    v = vms
+    c = v._abi.ctx()
+    whole, parts = v.Tensor((1001,)), v.Tensor((1001,))
+    c.lib.vms_standard_normal(7, 0, 1001, whole.ptr, c.stream)
+    c.lib.vms_standard_normal(7, 0, 333, parts.ptr, c.stream)
+    c.lib.vms_standard_normal(7, 333, 668, parts.ptr + 4 * 333, c.stream)
+    w = whole.numpy()
+    assert np.array_equal(w, parts.numpy())
+    assert abs(w.mean()) < 0.15 and abs(w.std() - 1.0) < 0.1
+
+
 # ------------------------------------------------------------------------------------------------ MCMC
 def test_mcmc_counters_and_shapes(vms):
     """tests/test_mcmc.py:34-59."""

@@ -70,6 +70,7 @@ _SIGS = {
     'vms_event_create': (None, [C.POINTER(c_vp)]),
     'vms_event_destroy': (None, [c_vp]),
     'vms_event_record': (None, [c_vp, c_vp]),
+    'vms_stream_wait_event': (None, [c_vp, c_vp]),
     'vms_event_synchronize': (None, [c_vp]),
     'vms_event_elapsed_ms': (None, [c_vp, c_vp, C.POINTER(c_f32)]),
     'vms_rqs_forward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_f32, c_vp, c_vp, c_vp]),
@@ -93,6 +94,7 @@ _SIGS = {
     'vms_batch_moments': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vms_batchnorm_coeffs': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vms_broadcast_scalar': (None, [c_vp, c_i64, c_vp, c_vp]),
+    'vms_standard_normal': (None, [C.c_ulonglong, C.c_ulonglong, c_i64, c_vp, c_vp]),
     'vms_blockwise_sample': (None, [c_vp, c_i64, c_i64, c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_int, c_vp, c_i64, C.c_ulonglong, c_vp,
                                     c_i64, c_vp]),

@@ -236,6 +236,27 @@ __global__ void blockwise_sample_kernel(const float* __restrict__ params, int64_
   out[b * ld_o + d] = x;
 }
 
+// four standard normals per Philox call; element i of the stream comes from counter (offset + i) / 4, lane (offset + i) % 4
+__global__ void std_normal_fill_kernel(unsigned long long seed, unsigned long long offset, int64_t n, float* __restrict__ out) {
+  const unsigned long long first = offset >> 2, last = (offset + (unsigned long long)n + 3ull) >> 2;
+  const unsigned long long q = first + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= last) return;
+  const uint4 r = philox4x32_10(make_uint4((unsigned)q, (unsigned)(q >> 32), 0x4e6f726du, 0u),
+                                make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  float v[4], sn, cs;
+  float rad = sqrtf(-2.f * logf(u01(r.x)));
+  sincospif(2.f * u01(r.y), &sn, &cs);
+  v[0] = rad * cs; v[1] = rad * sn;
+  rad = sqrtf(-2.f * logf(u01(r.z)));
+  sincospif(2.f * u01(r.w), &sn, &cs);
+  v[2] = rad * cs; v[3] = rad * sn;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned long long e = 4ull * q + k;
+    if (e >= offset && e < offset + (unsigned long long)n) out[e - offset] = v[k];
+  }
+}
+
 // Independent(Deterministic(loc)).log_prob (dists.py:701-704): 0 where every coordinate equals loc, -inf elsewhere
 __global__ void deterministic_lp_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ loc,
                                         int64_t ld_l, int64_t B, int D, float* __restrict__ lp) {
@@ -324,6 +345,15 @@ vms_status vms_blockwise_sample(const float* params, int64_t ld_p, int64_t B, in
                                                                                          scale_mode, eps, ld_eps, seed,
                                                                                          out, ld_out);
   VMS_LAUNCH_CHECK("blockwise_sample_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_standard_normal(unsigned long long seed, unsigned long long offset, int64_t n, float* out, vms_stream stream) {
+  VMS_REQUIRE(out && n >= 0, VMS_ERR_INVALID_ARG, "standard_normal: bad arguments");
+  if (n == 0) return VMS_OK;
+  const unsigned long long quads = ((offset + (unsigned long long)n + 3ull) >> 2) - (offset >> 2);
+  std_normal_fill_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, as_stream(stream)>>>(seed, offset, n, out);
+  VMS_LAUNCH_CHECK("std_normal_fill_kernel");
   return VMS_OK;
 }
 

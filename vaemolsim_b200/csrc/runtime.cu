@@ -148,6 +148,10 @@ vms_status vms_event_record(vms_event e, vms_stream s) {
   VMS_CUDA(cudaEventRecord((cudaEvent_t)e, as_stream(s)));
   return VMS_OK;
 }
+vms_status vms_stream_wait_event(vms_stream s, vms_event e) {
+  VMS_CUDA(cudaStreamWaitEvent(as_stream(s), (cudaEvent_t)e, 0));
+  return VMS_OK;
+}
 vms_status vms_event_synchronize(vms_event e) {
   VMS_CUDA(cudaEventSynchronize((cudaEvent_t)e));
   return VMS_OK;

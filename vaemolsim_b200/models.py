@@ -139,16 +139,16 @@ class VAE(Model):
         if getattr(self, 'loss', None) is not None and not isinstance(self.loss, losses.LogProbLoss):
             raise NotImplementedError('VAE.fit: only LogProbLoss has a fused backward (SURVEY.md 8f)')
         x = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
+        x = x.reshape(len(x), -1)
         hist = {'loss': [], 'kl_div': []}
+        f = self.fused(min(int(batch_size), len(x)))
+        opt = getattr(self, 'optimizer', None) or Adam()
         for _ in range(epochs):
-            order = P.rng().permutation(len(x)) if shuffle else np.arange(len(x))
-            tot, klt, n = 0.0, 0.0, 0
-            for i in range(0, len(x), batch_size):
-                xb = x[order[i:i + batch_size]]
-                out = self.train_step(Tensor.from_numpy(xb))
-                tot, klt, n = tot + out['loss'] * len(xb), klt + out['kl'] * len(xb), n + len(xb)
-            hist['loss'].append(tot / n)
-            hist['kl_div'].append(klt / n)
+            order = P.rng().permutation(len(x)) if shuffle else None
+            scal = f.train_loop(x, opt, batch_size, order=order)  # pipelined: copies, noise and read-backs overlap the steps
+            w = np.minimum(batch_size, len(x) - np.arange(0, len(x), min(int(batch_size), len(x)))).astype(np.float64)
+            hist['loss'].append(float(np.sum(scal[:, 0] * w) / w.sum()))
+            hist['kl_div'].append(float(np.sum(scal[:, 2] * w) / w.sum()))
         return hist
 
     def evaluate(self, x, y=None, batch_size=32, verbose=0):
@@ -303,6 +303,108 @@ class FusedELBO(object):
         self.t += 1
         c.lib.vms_adam_step(self.theta.ptr, self.grad.ptr, 1, grad_scale, self.m.ptr, self.v.ptr, self.n_params, self.t,
                             opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon, c.stream)
+
+    def train_loop(self, x_host, opt, batch_size, order=None, eps_host=None, n_steps=None, seed=None):
+        """The inner loop of `VAE.fit` (the Keras training loop of tests/test_models.py:181-182) as a device pipeline:
+        batch i + 1 travels host -> device on a copy stream while batch i trains (double-buffered inputs, events in both
+        directions), the reparameterisation noise is drawn on the device (Philox, `vms_standard_normal`) unless `eps_host`
+        is given, and the per-step scalars {loss, nll, kl} land in a small device ring that is read back every 8 steps,
+        so the host never waits for a step.  x_host [N, dx] float32 (pinned memory avoids a staging copy when `order` is
+        None); order: row permutation (shuffle); n_steps: number of batches (default: one epoch, ragged last batch
+        dropped into its own step).  Returns the [n_steps, 3] scalars."""
+        c = ctx()
+        lib = c.lib
+        N = x_host.shape[0]
+        bs = int(min(batch_size, N))
+        starts = list(range(0, N, bs))
+        if n_steps is not None:
+            starts = [starts[i % len(starts)] for i in range(int(n_steps))]
+        R = 8
+        if getattr(self, '_loop', None) is None or self._loop['bs'] < bs:
+            mk = lambda: C.c_void_p()
+            st = mk()
+            lib.vms_stream_create(C.byref(st))
+            evs = []
+            for _ in range(4):
+                e = mk()
+                lib.vms_event_create(C.byref(e))
+                evs.append(e.value)
+            hp = mk()
+            lib.vms_malloc_host(C.byref(hp), R * 4 * 4 * 2)
+            stage = []
+            for _ in range(2):
+                p = mk()
+                lib.vms_malloc_host(C.byref(p), bs * (self.dx + self.dz) * 4)
+                stage.append(p.value)
+            self._loop = dict(bs=bs, copy_stream=st.value, h2d=evs[:2], free=evs[2:], xd=[Tensor((bs, self.dx)) for _ in range(2)],
+                              ed=[Tensor((bs, self.dz)) for _ in range(2)], ring=Tensor((R, 4)), host_ring=hp.value,
+                              stage=stage, noise_offset=0,
+                              noise_seed=int(P.rng().integers(0, 2**63 - 1)) if seed is None else int(seed))
+        L = self._loop
+        if seed is not None:
+            L['noise_seed'], L['noise_offset'] = int(seed), 0
+        cs = L['copy_stream']
+        x_host = np.ascontiguousarray(x_host, np.float32)
+        if eps_host is not None:
+            eps_host = np.ascontiguousarray(eps_host, np.float32)
+        out = np.empty((len(starts), 4), np.float32)
+        ring_host = np.frombuffer((C.c_byte * (R * 4 * 4 * 2)).from_address(L['host_ring']), np.float32).reshape(2, R, 4)
+        pending = []  # (first step, count, half) of ring read-backs in flight
+        used = [False, False]
+
+        def drain(keep):
+            while len(pending) > keep:
+                first, cnt, half, ev = pending.pop(0)
+                lib.vms_event_synchronize(ev)
+                out[first:first + cnt] = ring_host[half, :cnt]
+
+        ring_ev = []
+        for _ in range(2):
+            e = C.c_void_p()
+            lib.vms_event_create(C.byref(e))
+            ring_ev.append(e.value)
+        for i, s0 in enumerate(starts):
+            b = i & 1
+            n = min(bs, N - s0)
+            # ---- copy stream: inputs of step i into buffer b (once step i - 2 released it)
+            if used[b]:
+                lib.vms_stream_wait_event(cs, L['free'][b])
+            if order is None:
+                src_x = x_host.ctypes.data + s0 * self.dx * 4
+            else:
+                if used[b]:
+                    lib.vms_event_synchronize(L['h2d'][b])  # the staging buffer's previous copy has left the host
+                sx = np.frombuffer((C.c_byte * (n * self.dx * 4)).from_address(L['stage'][b]), np.float32).reshape(n, self.dx)
+                np.take(x_host, order[s0:s0 + n], axis=0, out=sx)
+                src_x = L['stage'][b]
+            lib.vms_memcpy_h2d(L['xd'][b].ptr, src_x, n * self.dx * 4, cs)
+            if eps_host is not None:
+                lib.vms_memcpy_h2d(L['ed'][b].ptr, eps_host.ctypes.data + s0 * self.dz * 4, n * self.dz * 4, cs)
+            lib.vms_event_record(L['h2d'][b], cs)
+            # ---- compute stream: noise, the step, release of the buffer
+            if eps_host is None:
+                lib.vms_standard_normal(L['noise_seed'], L['noise_offset'], n * self.dz, L['ed'][b].ptr, c.stream)
+                L['noise_offset'] += n * self.dz
+            lib.vms_stream_wait_event(c.stream, L['h2d'][b])
+            self.t += 1
+            slot = i % R
+            lib.vms_elbo_train_step(self.handle, self.theta.ptr, L['xd'][b].ptr, L['ed'][b].ptr, n, self.grad.ptr,
+                                    L['ring'].ptr + 16 * slot, self.m.ptr, self.v.ptr, self.t, opt.learning_rate, opt.beta_1,
+                                    opt.beta_2, opt.epsilon, c.stream)
+            lib.vms_event_record(L['free'][b], c.stream)
+            used[b] = True
+            if slot == R - 1 or i == len(starts) - 1:
+                half = (i // R) & 1
+                drain(1)  # at most one read-back outstanding before its host half is reused
+                lib.vms_memcpy_d2h(L['host_ring'] + half * R * 16, L['ring'].ptr, (slot + 1) * 16, c.stream)
+                lib.vms_event_record(ring_ev[half], c.stream)
+                pending.append((i - slot, slot + 1, half, ring_ev[half]))
+        drain(0)
+        lib.vms_stream_synchronize(cs)
+        for e in ring_ev:
+            lib.vms_event_destroy(e)
+        lib.vms_memcpy_d2d(self.scalars.ptr, L['ring'].ptr + 16 * ((len(starts) - 1) % R), 16, c.stream)
+        return out[:, :3]
 
     def train_step(self, x, eps, opt):
         """Forward + backward + Adam in one C call (`vms_elbo_train_step`: 2 kernel launches on the fused path)."""
