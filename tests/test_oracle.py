@@ -345,3 +345,23 @@ def test_mc_oracle_matches_reference_mcmc_py(tag, prior):
                                          g['log_rand_%d' % s]), acc)
         n_acc += acc.sum()
     assert float(g['num_trials']) == 5 * 64 and float(g['num_acc']) == n_acc
+
+
+def test_batch_norm_restatement_identities():
+    """oracle/nets.py batch-norm restatement [TF/TFP-recalled]: normalised columns have zero mean / unit variance (up to
+    eps), the bijector's two directions invert each other and their log-dets cancel, and the initial moving statistics
+    (0, 1) with gamma = 1, beta = 0 give x / sqrt(1 + 1e-3) (Keras BatchNormalization in inference mode)."""
+    from oracle import nets as onets
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(500, 4)) * [1.0, 3.0, 0.2, 5.0] + [1.0, -2.0, 0.0, 7.0]
+    mean, var = onets.batch_norm_moments(x)
+    np.testing.assert_allclose(var, x.var(axis=0), rtol=1e-12)
+    gamma, beta = np.array([0.5, 1.0, 2.0, 1.5]), np.array([0.1, 0.0, -1.0, 2.0])
+    y, ildj = onets.batch_norm_normalize(x, mean, var, gamma, beta)
+    np.testing.assert_allclose(y.mean(axis=0), beta, atol=1e-12)
+    np.testing.assert_allclose(y.std(axis=0), gamma * np.sqrt(var / (var + 1e-3)), rtol=1e-12)
+    back, fldj = onets.batch_norm_denormalize(y, mean, var, gamma, beta)
+    np.testing.assert_allclose(back, x, rtol=1e-12, atol=1e-12)
+    assert abs(ildj + fldj) < 1e-12
+    y0, _ = onets.batch_norm_normalize(x, np.zeros(4), np.ones(4), np.ones(4), np.zeros(4))
+    np.testing.assert_allclose(y0, x / np.sqrt(1.0 + 1e-3), rtol=1e-12)
