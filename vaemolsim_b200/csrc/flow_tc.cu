@@ -21,7 +21,7 @@
 // the CTA once, as a per-CTA partial that the caller reduces in a fixed order (deterministic).
 //
 // float32 parity on 16-bit tensor cores.  a = a1 + a2 + a3 with three bfloat16 parts (8 significant bits each,
-// truncation splits: exact for zero and every normal float32) and a.b ~ a1 b1 + (a1 b2 + a2 b1) + (a1 b3 + a2 b2 + a3 b1): six
+// truncation splits: exact for zero and every |a| > 2^-110) and a.b ~ a1 b1 + (a1 b2 + a2 b1) + (a1 b3 + a2 b2 + a3 b1): six
 // kind::f16 MMAs per 16-deep k-step, the dropped terms are 2^-24 relative.  The leading product has its own TMEM
 // accumulator, the five corrections share a second one (added in the epilogue), as in gemm_tc.cu.
 // Why not 3 x TF32 as in gemm_tc.cu: kind::tf32 reads MN-major (transposed) operands only in the 128B-base-32B swizzled
@@ -61,7 +61,7 @@ struct KParams {
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// a = p1 + p2 + p3 exactly (zero and normal float32; tests/test_split_numerics.py), each part a bfloat16 (upper half of a
+// a = p1 + p2 + p3 exactly (zero and |a| > 2^-110; tests/test_split_numerics.py), each part a bfloat16 (upper half of a
 // float32 pattern)
 __device__ __forceinline__ void split3(float a, unsigned& h1, unsigned& h2, unsigned& h3) {
   h1 = __float_as_uint(a) & 0xffff0000u;
