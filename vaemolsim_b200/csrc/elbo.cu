@@ -476,6 +476,7 @@ vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan) 
   }
 #undef A_
   if (!s) s = fused_create(pl);
+  if (!s) s = tcf_create(pl);
   if (s) { vms_elbo_plan_destroy(pl); return s; }
   *plan = pl;
   return VMS_OK;
@@ -486,6 +487,7 @@ vms_status vms_elbo_plan_destroy(vms_elbo_plan pl) {
   for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.first);
   for (void* p : pl->allocs) cudaFree(p);
   fused_destroy(pl);
+  tcf_destroy(pl);
   delete pl;
   return VMS_OK;
 }
@@ -500,8 +502,10 @@ static vms_status check_call(vms_elbo_plan pl, const float* theta, const float* 
 
 vms_status vms_elbo_plan_set_mode(vms_elbo_plan pl, int mode) {
   VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "elbo_plan_set_mode: NULL plan");
-  VMS_REQUIRE(mode >= 0 && mode <= 2, VMS_ERR_INVALID_ARG,
-              "elbo_plan_set_mode: mode must be 0 (auto), 1 (unfused, FFMA) or 2 (unfused, tensor-core flow blocks)");
+  VMS_REQUIRE(mode >= 0 && mode <= 3, VMS_ERR_INVALID_ARG,
+              "elbo_plan_set_mode: mode must be 0 (auto), 1 (unfused, FFMA), 2 (unfused, tensor-core flow blocks) or 3 "
+              "(experimental whole-step tensor-core kernel)");
+  VMS_REQUIRE(mode != 3 || pl->tcf, VMS_ERR_UNSUPPORTED, "elbo_plan_set_mode: mode 3 does not support this shape");
   VMS_REQUIRE(mode != 2 || pl->tc_ok, VMS_ERR_UNSUPPORTED, "elbo_plan_set_mode: the tensor-core flow kernels do not support this shape");
   pl->mode = mode;
   return VMS_OK;
@@ -519,6 +523,7 @@ vms_status vms_elbo_plan_tc_status(vms_elbo_plan pl, int* err) {
 
 int vms_elbo_plan_path(vms_elbo_plan pl, int64_t B) {
   if (!pl) return -1;
+  if (pl->mode == 3 && tcf_available(pl, B)) return 3;
   if (use_fused(pl, B)) return 0;
   return plan_uses_tc(pl, B) ? 2 : 1;
 }
@@ -567,6 +572,7 @@ vms_status vms_elbo_forward_backward(vms_elbo_plan pl, const float* theta, const
   if (s) return s;
   VMS_REQUIRE(grad, VMS_ERR_INVALID_ARG, "elbo_forward_backward: NULL grad");
   cudaStream_t st = as_stream(stream);
+  if (pl->mode == 3 && tcf_available(pl, B)) return tcf_run(pl, theta, x, eps, B, grad, scalars, st);
   if (use_fused(pl, B))
     return fused_run(pl, theta, x, eps, B, true, nullptr, nullptr, nullptr, nullptr, grad, scalars, st);
   std::array<uintptr_t, 10> key = {(uintptr_t)(1 | (pl->mode << 8)), (uintptr_t)B, (uintptr_t)theta, (uintptr_t)x, (uintptr_t)eps, (uintptr_t)grad,
@@ -586,6 +592,15 @@ vms_status vms_elbo_train_step(vms_elbo_plan pl, float* theta, const float* x, c
   vms_status s = check_call(pl, theta, x, eps, B);
   if (s) return s;
   VMS_REQUIRE(grad && m && v && t >= 1, VMS_ERR_INVALID_ARG, "elbo_train_step: NULL grad / m / v or t < 1");
+  if (pl->mode == 3 && tcf_available(pl, B)) {
+    FusedAdam ad;
+    ad.theta = theta; ad.m = m; ad.v = v;
+    ad.lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
+    ad.one_minus_b1 = (float)(1.0 - beta1);
+    ad.one_minus_b2 = (float)(1.0 - beta2);
+    ad.eps = (float)eps_adam;
+    return tcf_run(pl, theta, x, eps, B, grad, scalars, as_stream(stream), &ad);
+  }
   if (use_fused(pl, B)) {
     FusedAdam ad;
     ad.theta = theta; ad.m = m; ad.v = v;

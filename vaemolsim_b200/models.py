@@ -266,7 +266,8 @@ class FusedELBO(object):
     def path(self, batch):
         """Implementation a step of `batch` rows takes: 'fused' (one persistent kernel), 'ffma' (per-layer float32
         plan) or 'tensor-core' (large-batch plan: tcgen05 coupling blocks + streaming MLP kernels)."""
-        return ('fused', 'ffma', 'tensor-core')[ctx().lib.vms_elbo_plan_path(self.handle, int(batch))]
+        return ('fused', 'ffma', 'tensor-core', 'tensor-core-fused (experimental)')[
+            ctx().lib.vms_elbo_plan_path(self.handle, int(batch))]
 
     def tc_status(self):
         """True if a tensor-core kernel of the mode-2 plan gave up waiting for an MMA completion (results invalid)."""
