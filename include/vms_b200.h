@@ -310,6 +310,9 @@ int64_t vms_elbo_param_count(const vms_elbo_desc* desc);
  * the SM) -- the large-batch configuration; VMS_ERR_UNSUPPORTED when a block's shape does not fit (one transformed
  * dimension, <= 4 conditioner columns, 8 <= flow hidden <= 111, num_bins <= 32 and a multiple of 4, encoder / decoder
  * widths dx, dz <= 7, 2 dx, 2 dz <= 16, hidden <= 240).
+ * mode 3 = EXPERIMENTAL whole-step tensor-core kernel (elbo_tcf.cu: all coupling blocks + encoder / decoder of a 64-row
+ * tile in one persistent kernel; forward+backward / train_step only, B <= 64 x #SMs; correct but not yet faster than
+ * the fused kernel -- never chosen automatically).
  * vms_elbo_plan_tc_status: synchronises the device and reports whether any tensor-core completion wait ran into its
  * bound since the last call (err = 1: results of that interval are invalid); clears the flag.                      */
 vms_status vms_elbo_plan_set_mode(vms_elbo_plan plan, int mode);

@@ -4,8 +4,13 @@
 // MN-major reads of the same tiles, octet spline routines on the raw parameters) for all blocks of the chain back to
 // back, with the encoder / decoder MLPs of mlp_stream.cu as in-tile phases, so that at the named batch (4096 rows = 64
 // tiles) the step is one launch whose heavy products run on the tensor core instead of the FFMA pipe of
-// elbo_fused.cu.  Status: written against the verified kernels of flow_tc.cu / mlp_stream.cu, compiled for sm_100a,
-// cross-checked on the device by scripts/test_elbo_tcf.py (mode 3 against mode 1) -- see DESIGN.md 9a for the result.
+// elbo_fused.cu.  Status (round 1, one measurement, scripts/test_elbo_tcf.py at batch 4096): CORRECT -- loss scalars equal
+// to 7 digits, flat gradient 1.5e-7 (norm) against the FFMA plan, worst layer 1.6e-6 -- but SLOWER than the FFMA fused
+// kernel: 0.187 ms against 0.146 ms forward + backward.  One 64-row tile per CTA keeps only 64 of 148 SMs busy and the
+// RealNVP chain makes a tile's phases strictly sequential (block i needs block i + 1's output), so the tensor core
+// idles while the SIMT phases run.  What it needs to win: 32 valid rows per tile (128 CTAs, SIMT phases
+// halved, MMA cost unchanged), heads matrices staged with cp.async.bulk behind the previous block's epilogue, and two
+// tiles per CTA on alternating warp groups.
 //
 // Reference lines replaced: the same as elbo.cu (models.py:289-322 VAE.call; mappings.py:107-155 FCDeepNN;
 // flows.py:184-207, :281-355 RQSSplineRealNVP; dists.py:414-439; losses.py:58, :253) plus TF autodiff through them.
