@@ -11,6 +11,10 @@
 // idles while the SIMT phases run.  What it needs to win: 32 valid rows per tile (128 CTAs, SIMT phases
 // halved, MMA cost unchanged), heads matrices staged with cp.async.bulk behind the previous block's epilogue, and two
 // tiles per CTA on alternating warp groups.
+// AFTER that measurement (no GPU time left in round 1) the row loops were parametrised by `rows` = valid rows per tile:
+// rows = 64 is the default and is meant to be the measured code path unchanged; VMS_TCF_ROWS=32 selects 32-row tiles
+// (zero-padded M = 64 products, d hW over 2 k-steps) and has NOT run on a device yet.  First thing to do next round:
+// `python scripts/test_elbo_tcf.py 4096` with and without VMS_TCF_ROWS=32.
 //
 // Reference lines replaced: the same as elbo.cu (models.py:289-322 VAE.call; mappings.py:107-155 FCDeepNN;
 // flows.py:184-207, :281-355 RQSSplineRealNVP; dists.py:414-439; losses.py:58, :253) plus TF autodiff through them.
@@ -33,6 +37,7 @@
 #include "rqs_device.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace vms {
 
@@ -51,6 +56,7 @@ struct TBlk {
 struct TParams {
   int64_t B;
   int dx, dz, H, nb, K, fh, Hp, R, RP, LDS, P;
+  int rows;  // valid rows per tile: 64, or 32 (the MMAs stay M = 64; rows beyond are zero operands)
   float bin_min, scale, klw;
   int enc0W, enc0b, enc1W, enc1b, dec0W, dec0b, dec1W, dec1b;
   int DIE, DOE, DID, DOD;  // padded MLP widths: round_up(Din + 1, 4), round_up(Dout, 4)
@@ -219,16 +225,17 @@ __device__ __forceinline__ void load_in8(const float* in, int ldi, int Din, int 
 
 // out [FM][DO] = relu(in W0 + b0) W1 + b1;  scratch: [8][FM][DO] floats
 __device__ void mlp_forward(const float* wm, int H, int DI, int DO, const float* in, int ldi, int Din, float* scratch,
-                            float* out) {
+                            float* out, int rows) {
   const float* w0t = wm;
   const float* w1 = wm + H * DI;
   const float* b1 = w1 + H * DO;
-  const int r = threadIdx.x & (FM - 1), g = threadIdx.x >> 6;
+  const int ng = FT / rows;  // thread = (row, one of ng groups of hidden units)
+  const int r = threadIdx.x & (rows - 1), g = threadIdx.x / rows;
   float x[8], acc[16];
   load_in8(in, ldi, Din, r, x);
 #pragma unroll
   for (int n = 0; n < 16; ++n) acc[n] = 0.f;
-  for (int j = g; j < H; j += FT / FM) {
+  for (int j = g; j < H; j += ng) {
     float pre = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -240,12 +247,12 @@ __device__ void mlp_forward(const float* wm, int H, int DI, int DO, const float*
   }
 #pragma unroll
   for (int n = 0; n < 16; ++n)
-    if (n < DO) scratch[(g * FM + r) * DO + n] = acc[n];
+    if (n < DO) scratch[(g * rows + r) * DO + n] = acc[n];
   __syncthreads();
-  for (int e = threadIdx.x; e < FM * DO; e += FT) {
+  for (int e = threadIdx.x; e < rows * DO; e += FT) {
     const int r2 = e / DO, n = e - r2 * DO;
     float s = b1[n];
-    for (int k = 0; k < FT / FM; ++k) s += scratch[(k * FM + r2) * DO + n];
+    for (int k = 0; k < ng; ++k) s += scratch[(k * rows + r2) * DO + n];
     out[e] = s;
   }
   __syncthreads();
@@ -255,7 +262,7 @@ __device__ void mlp_forward(const float* wm, int H, int DI, int DO, const float*
 // optional input gradient gin [FM][4] (Din <= 4).  scratch: max(H * 24, 8 * FM * 4) floats
 __device__ void mlp_backward(const float* wm, int H, int DI, int DO, const float* in, int ldi, int Din, int Dout,
                              const float* gout, float* __restrict__ part, int oW0, int ob0, int oW1, int ob1, float* scratch,
-                             float* gin) {
+                             float* gin, int rows) {
   const float* w0t = wm;
   const float* w1 = wm + H * DI;
   const int tid = threadIdx.x;
@@ -267,7 +274,7 @@ __device__ void mlp_backward(const float* wm, int H, int DI, int DO, const float
 #pragma unroll
     for (int n = 0; n < 16; ++n) { w1r[n] = (j < H && n < DO) ? w1[j * DO + n] : 0.f; dW1[n] = 0.f; }
     if (j < H) {
-      for (int r = half * (FM / 2); r < (half + 1) * (FM / 2); ++r) {
+      for (int r = half * (rows / 2); r < (half + 1) * (rows / 2); ++r) {
         float x[8];
         load_in8(in, ldi, Din, r, x);
         float pre = 0.f, t = 0.f;
@@ -307,18 +314,19 @@ __device__ void mlp_backward(const float* wm, int H, int DI, int DO, const float
     if (tid >= FT - 16 && tid - (FT - 16) < Dout) {  // output bias: column sums of gout
       const int n = tid - (FT - 16);
       float s = 0.f;
-      for (int r = 0; r < FM; ++r) s += gout[r * DO + n];
+      for (int r = 0; r < rows; ++r) s += gout[r * DO + n];
       part[ob1 + n] = s;
     }
     __syncthreads();
   }
   if (gin) {  // input gradient: thread = (row, 1/8 of the hidden units)
-    const int r = tid & (FM - 1), g8 = tid >> 6;
+    const int ng = FT / rows;
+    const int r = tid & (rows - 1), g8 = tid / rows;
     float x[8], g[16], gi[4] = {0.f, 0.f, 0.f, 0.f};
     load_in8(in, ldi, Din, r, x);
 #pragma unroll
     for (int n = 0; n < 16; ++n) g[n] = n < DO ? gout[r * DO + n] : 0.f;
-    for (int j = g8; j < H; j += FT / FM) {
+    for (int j = g8; j < H; j += ng) {
       float pre = 0.f, t = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -332,11 +340,11 @@ __device__ void mlp_backward(const float* wm, int H, int DI, int DO, const float
         if (i < Din) gi[i] = fmaf(gh, w0t[j * DI + i], gi[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) scratch[(g8 * FM + r) * 4 + i] = gi[i];
+    for (int i = 0; i < 4; ++i) scratch[(g8 * rows + r) * 4 + i] = gi[i];
     __syncthreads();
-    for (int e = tid; e < FM * 4; e += FT) {
+    for (int e = tid; e < rows * 4; e += FT) {
       float s = 0.f;
-      for (int k = 0; k < FT / FM; ++k) s += scratch[k * FM * 4 + e];
+      for (int k = 0; k < ng; ++k) s += scratch[k * rows * 4 + e];
       gin[e] = s;
     }
     __syncthreads();
@@ -377,6 +385,7 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
   float* s_w1 = reinterpret_cast<float*>(smb + p.o_w1);     // [nb][4][Hp]
   float* s_b1 = reinterpret_cast<float*>(smb + p.o_b1);     // [nb][Hp]
   const int DOE = p.DOE, DOD = p.DOD;
+  const int rows = p.rows;  // valid rows of a tile (<= FM)
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)),
@@ -397,6 +406,8 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     const int b = e / Hp, j = e - b * Hp;
     s_b1[e] = j < H ? __ldg(p.theta + p.blk[b].off_d1b + j) : 0.f;
   }
+  if (rows < FM)  // rows beyond the tile must be finite (and zero) operands of the M = 64 products
+    for (unsigned e = tid; e < 3 * hid_sz / 4; e += FT) reinterpret_cast<unsigned*>(hid)[e] = 0u;
   tc_sync();
   const unsigned tm = tmem_base_s;
   const unsigned tD1 = tm, tD2 = tm + RP, tD3 = tm + RP + 128;
@@ -409,8 +420,8 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
   bool failed = false;
 
   const int64_t tile = blockIdx.x;  // one tile per CTA
-  const int64_t row0 = tile * FM;
-  const int nr = (int)min((int64_t)FM, p.B - row0);
+  const int64_t row0 = tile * rows;
+  const int nr = (int)min((int64_t)rows, p.B - row0);
   float* part = p.gpart + (size_t)blockIdx.x * p.P;
   const float invB = 1.0f / (float)p.B;
   const float g_logpx = -invB, g_logq = p.klw * invB, g_logpz = -p.klw * invB;
@@ -425,13 +436,13 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
   // ---- hid of block i from the conditioner columns of chain state `uin` ([FM][4]); ones column at j = H
   auto build_hid = [&](int i, const float* uin) {
     const TBlk& fb = p.blk[i];
-    const int r = tid & (FM - 1);
+    const int r = tid & (rows - 1);
     float cnd[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) cnd[c] = c < fb.nc ? uin[r * 4 + fb.cs0 + c] : ((fb.nc == 0 && c == 0) ? 1.f : 0.f);
     const float* w1 = s_w1 + i * 4 * Hp;
     const float* b1 = s_b1 + i * Hp;
-    for (int jq = tid >> 6; jq < 2 * nchH; jq += FT / FM) {
+    for (int jq = tid / rows; jq < 2 * nchH; jq += FT / rows) {
       const float4 b4 = *reinterpret_cast<const float4*>(b1 + 4 * jq);
       float pre[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
@@ -467,31 +478,32 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const int q = warp & 3, row = 16 * q + lane;
-    for (int c0 = 16 * (warp >> 2); c0 < RP; c0 += 64) {
-      float v1[16];
-      tmem_ld16(tD1 + ((unsigned)(32 * q) << 16) + (unsigned)c0, v1);
-      if (lane < 16) {
+    if (16 * q < rows)
+      for (int c0 = 16 * (warp >> 2); c0 < RP; c0 += 64) {
+        float v1[16];
+        tmem_ld16(tD1 + ((unsigned)(32 * q) << 16) + (unsigned)c0, v1);
+        if (lane < 16) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(s_raw + row * LDS + c0 + i) = make_float4(v1[i], v1[i + 1], v1[i + 2], v1[i + 3]);
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(s_raw + row * LDS + c0 + i) = make_float4(v1[i], v1[i + 1], v1[i + 2], v1[i + 3]);
+        }
       }
-    }
     tc_sync();
   };
 
   // ================================================================ T0: the tile's inputs
-  for (int e = tid; e < FM * 8; e += FT) {
+  for (int e = tid; e < rows * 8; e += FT) {
     const int r = e >> 3, c = e & 7;
     s_x[e] = (r < nr && c < dx) ? __ldg(p.x + (row0 + r) * dx + c) : 0.f;
   }
-  for (int e = tid; e < FM * 4; e += FT) {
+  for (int e = tid; e < rows * 4; e += FT) {
     const int r = e >> 2, c = e & 3;
     s_eps[e] = (r < nr && c < dz) ? __ldg(p.eps + (row0 + r) * dz + c) : 0.f;
   }
   // ================================================================ E1: encoder
   stage_mlp(p.theta, p.enc0W, p.enc0b, p.enc1W, p.enc1b, dx, p.H, 2 * dz, p.DIE, DOE, s_mlp);  // (ends with a barrier)
-  mlp_forward(s_mlp, p.H, p.DIE, DOE, s_x, 8, dx, s_raw, s_pe);
-  if (tid < FM) {
+  mlp_forward(s_mlp, p.H, p.DIE, DOE, s_x, 8, dx, s_raw, s_pe, rows);
+  if (tid < rows) {
     float* z = s_u + (nb * FM + tid) * 4;
     float s = 0.f;
     for (int d = 0; d < 4; ++d) z[d] = 0.f;
@@ -514,7 +526,7 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     stage_heads(i);
     build_hid(i, uin);
     raw_product();
-    {
+    if ((tid >> 3) < rows) {  // whole warps (4 rows each)
       const int r = tid >> 3, j = tid & 7;
       const float* rr = s_raw + r * LDS;
       float out, ldj, ldj_all;
@@ -527,7 +539,7 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     }
     __syncthreads();
   }
-  if (tid < FM) {
+  if (tid < rows) {
     float s = s_lp[FM + tid];
     for (int d = 0; d < dz; ++d) s += normal_lp(s_u[tid * 4 + d], 0.f, 1.f);
     s_lp[FM + tid] = s;
@@ -535,8 +547,10 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
   // ================================================================ D1: decoder, loss terms
   stage_mlp(p.theta, p.dec0W, p.dec0b, p.dec1W, p.dec1b, dz, p.H, 2 * dx, p.DID, DOD, s_mlp);
   const float* zt = s_u + nb * FM * 4;
-  mlp_forward(s_mlp, p.H, p.DID, DOD, zt, 4, dz, s_raw, s_pd);
-  if (tid < FM) {
+  mlp_forward(s_mlp, p.H, p.DID, DOD, zt, 4, dz, s_raw, s_pd, rows);
+  red[0] = red[1] = red[2] = red[3] = 0.f;  // (same value from every thread; warps 0 / 1 overwrite their slots below)
+  __syncthreads();
+  if (tid < rows) {
     float s = 0.f;
     for (int d = 0; d < dx; ++d) s += normal_lp(s_x[tid * 8 + d], s_pd[tid * DOD + d], softplus_tf(s_pd[tid * DOD + dx + d]));
     s_lp[2 * FM + tid] = s;
@@ -562,10 +576,11 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     p.spart[2 * blockIdx.x + 1] = red[1] + red[3];
   }
   // ================================================================ B1: decoder reverse mode (weights still staged)
-  mlp_backward(s_mlp, p.H, p.DID, DOD, zt, 4, dz, 2 * dx, s_gpd, part, p.dec0W, p.dec0b, p.dec1W, p.dec1b, s_raw, s_gz);
+  mlp_backward(s_mlp, p.H, p.DID, DOD, zt, 4, dz, 2 * dx, s_gpd, part, p.dec0W, p.dec0b, p.dec1W, p.dec1b, s_raw, s_gz,
+               rows);
   // ================================================================ F': flow reverse mode, block 0 first
   for (unsigned e = tid; e < 3 * graw_sz / 4; e += FT) reinterpret_cast<unsigned*>(graw)[e] = 0u;  // (held the MLP weights)
-  if (tid < FM)
+  if (tid < rows)
     for (int d = 0; d < 4; ++d) s_gu[tid * 4 + d] = d < dz ? -g_logpz * s_u[tid * 4 + d] : 0.f;
   __syncthreads();
 #pragma unroll 1
@@ -575,7 +590,7 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     stage_heads(i);
     build_hid(i, uin);
     raw_product();
-    {  // spline reverse mode, one octet per row
+    if ((tid >> 3) < rows) {  // spline reverse mode, one octet per row (whole warps)
       const int r = tid >> 3, j = tid & 7;
       const bool ok = r < nr;
       const float* rr = s_raw + r * LDS;
@@ -604,13 +619,13 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     tc_sync();
     if (tid == 0) {
       issue_product(tD2, graw_a, graw_sz, 2u * CSB, CSB, 128, w_a, w_sz, 256u, 128, w_cs, RP / 16, id2);
-      issue_product(tD3, hid_a, hid_sz, 256u, 128, CSB, graw_a, graw_sz, 256u, 128, CSB, FM / 16, id3);
+      issue_product(tD3, hid_a, hid_sz, 256u, 128, CSB, graw_a, graw_sz, 256u, 128, CSB, rows / 16, id3);
       mma_commit(bar);
     }
     if (!mbar_wait_bounded(bar, phase)) failed = true;
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    {  // d pre-activation = d hid * (1 - hid^2) -> s_raw
+    if (16 * (warp & 3) < rows) {  // d pre-activation = d hid * (1 - hid^2) -> s_raw
       const int q = warp & 3, row = 16 * q + lane;
       for (int c0 = 16 * (warp >> 2); c0 < Hp; c0 += 64) {
         float v1[16];
@@ -663,7 +678,7 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     {  // d d1b / d d1W: thread = (hidden unit, quarter of the rows)
       const int j = tid & 127, pq = tid >> 7;
       if (j < Hp) {
-        for (int r = pq * (FM / 4); r < (pq + 1) * (FM / 4); ++r) {
+        for (int r = pq * (rows / 4); r < (pq + 1) * (rows / 4); ++r) {
           const float d = s_raw[r * LDS + j];
           cs_b += d;
 #pragma unroll
@@ -677,7 +692,7 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     {  // gradient wrt the conditioner columns (one octet per row), chain-state gradient update
       const int r = tid >> 3, l = tid & 7;
       float gc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (fb.nc > 0) {
+      if (fb.nc > 0 && r < rows) {  // (r < rows is warp-uniform: 4 rows per warp)
         const float* w1 = s_w1 + i * 4 * Hp;
         const int j0 = l * (Hp / 8), j1 = j0 + Hp / 8;
         for (int j = j0; j < j1; ++j) {
@@ -693,7 +708,7 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
           gc[c] += __shfl_xor_sync(0xffffffffu, gc[c], 4);
         }
       }
-      if (l == 0) {
+      if (l == 0 && r < rows) {
         s_gu[r * 4 + fb.ts0] = s_gin[r];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -724,7 +739,7 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     }
   }
   // ================================================================ E2: encoder head and encoder reverse mode
-  if (tid < FM) {
+  if (tid < rows) {
     const bool ok = tid < nr;
     const float* z = s_u + (nb * FM + tid) * 4;
     for (int d = 0; d < DOE; ++d) s_gpe[tid * DOE + d] = 0.f;
@@ -740,7 +755,8 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
   }
   __syncthreads();
   stage_mlp(p.theta, p.enc0W, p.enc0b, p.enc1W, p.enc1b, dx, p.H, 2 * dz, p.DIE, DOE, s_mlp);
-  mlp_backward(s_mlp, p.H, p.DIE, DOE, s_x, 8, dx, 2 * dz, s_gpe, part, p.enc0W, p.enc0b, p.enc1W, p.enc1b, s_raw, nullptr);
+  mlp_backward(s_mlp, p.H, p.DIE, DOE, s_x, 8, dx, 2 * dz, s_gpe, part, p.enc0W, p.enc0b, p.enc1W, p.enc1b, s_raw, nullptr,
+               rows);
 
   if (failed && tid == 0 && p.err) atomicExch(p.err, 1);
   tc_sync();
@@ -875,8 +891,16 @@ void tcf_destroy(vms_elbo_plan_s* pl) {
   pl->tcf = nullptr;
 }
 
+// valid rows per tile: 64 (the measured configuration), or 32 with VMS_TCF_ROWS=32 (UNTESTED on the device at the end
+// of round 1: twice the CTAs, SIMT phases halved, the M = 64 products padded with zero rows)
+static int tcf_rows() {
+  const char* e = getenv("VMS_TCF_ROWS");
+  return (e && atoi(e) == 32) ? 32 : FM;
+}
+
 bool tcf_available(const vms_elbo_plan_s* pl, int64_t B) {
-  return pl->tcf && (B + FM - 1) / FM <= pl->tcf->max_tiles;
+  const int rows = tcf_rows();
+  return pl->tcf && (B + rows - 1) / rows <= pl->tcf->max_tiles;
 }
 
 // forward + backward (+ Adam when `adam`): 3 launches (prepack, the tile kernel, finish)
@@ -887,7 +911,8 @@ vms_status tcf_run(vms_elbo_plan_s* pl, const float* theta, const float* x, cons
   TParams p = f->p;
   p.B = B; p.theta = theta; p.x = x; p.eps = eps;
   p.wpk = f->wpk; p.gpart = f->gpart; p.spart = f->spart; p.err = pl->tc_err;
-  const int n_tiles = (int)((B + FM - 1) / FM);
+  p.rows = tcf_rows();
+  const int n_tiles = (int)((B + p.rows - 1) / p.rows);
   tcf_prepack_kernel<<<dim3((p.Hp * p.RP + 255) / 256, p.nb), 256, 0, st>>>(p, f->wpk);
   VMS_LAUNCH_CHECK("tcf_prepack_kernel");
   if (p.RP == 64) {
