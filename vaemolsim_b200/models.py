@@ -216,18 +216,8 @@ class FusedELBO(object):
 
     def __del__(self):
         try:
-            lib = _abi.load()
-            L = getattr(self, '_loop', None)
-            if L:  # resources of the pipelined training loop
-                lib.vms_device_synchronize()
-                for e in L['h2d'] + L['free']:
-                    lib.vms_event_destroy(e)
-                lib.vms_stream_destroy(L['copy_stream'])
-                for ptr in L['stage'] + [L['host_ring']]:
-                    lib.vms_free_host(ptr)
-                self._loop = None
             if getattr(self, 'handle', None):
-                lib.vms_elbo_plan_destroy(self.handle)
+                _abi.load().vms_elbo_plan_destroy(self.handle)
         except Exception:
             pass
 
