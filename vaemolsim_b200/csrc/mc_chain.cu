@@ -1,0 +1,272 @@
+// mc_chain.cu -- EXPERIMENTAL alternative to mc_fused_kernel (selected with VMS_MC_KERNEL=chain, default off; NOT yet
+// run on a device: written at the end of round 1 after the GPU budget was spent).
+//
+// Same contract as mc_fused.cu (mcmc.py:68-130 `MCMC.single_step` and the loop of `MCMC.run` :133-159 for the
+// Gaussian-VAE family of tests/test_mcmc.py:14-26): n_steps VAE-proposal MC steps of B chains in one launch, noise from
+// the same Philox4x32-10 stream (or given), accept uniforms from the host's PCG64 stream, float64 acceptance arithmetic
+// in the reference's order.
+//
+// Why a second formulation.  mc_fused_kernel runs a 32-chain tile through tile-GEMM phases separated by CTA barriers
+// (6 per step) and reaches 8 TFLOP/s (ncu: issue-active 55 %, barrier 1.7 stalled warps per issue).  The layers are
+// thin (contractions of 6 and 2, outputs of 4 and 12): mlp_stream.cu's "thread per row, weights as 16-byte shared-memory
+// broadcasts" forward reaches 19-21 TFLOP/s on the same shapes.  Here FOUR lanes own a chain for all its steps: every
+// lane holds the chain state in registers, takes every fourth hidden unit of the two MLP evaluations that run side by
+// side (encoder(x1) with decoder(z2), then decoder(z1) with encoder(x2)), and the 16 partial head outputs meet in a
+// two-step butterfly.  No shared-memory activations, no CTA barrier inside a step; per step a chain reads its log u
+// (8 bytes).  Four lanes per chain for EVERY batch size: the summation order, hence every decision, is independent of
+// the number of chains per GPU.
+#include "common.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+namespace vms {
+
+namespace {
+
+constexpr int CT = 128;   // threads per CTA = 32 chains
+constexpr int TPC = 4;    // lanes per chain
+constexpr int WROW = 28;  // floats per hidden unit in shared memory (7 x 16 bytes), see stage below
+constexpr int kMaxDx = 6, kMaxDz = 2;  // compile-time register arrays (the C4a shape: dx = 6, dz = 2)
+
+struct ChainParams {
+  int dx, dz, hidden;
+  int enc0W, enc0b, enc1W, enc1b, dec0W, dec0b, dec1W, dec1b;
+  int64_t B;
+  int n_steps;
+  const float* theta;
+  float* x;
+  double* E;
+  int energies_valid;
+  const float* noise;
+  unsigned long long seed, step0;
+  const double* log_u;
+  const double* means;
+  unsigned long long* n_acc;
+  uint8_t* acc_trace;
+  float *fwd_trace, *rev_trace;
+  double* e_new_trace;
+};
+
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ void box_muller(unsigned a, unsigned b, float& n0, float& n1) {
+  const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;
+  const float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.f * logf(u1));
+  float s, c;
+  sincospif(2.f * u2, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+// sum over the 4 lanes of a chain; every lane gets the same value: (l0 + l1) + (l2 + l3)
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+// Encoder and decoder evaluated side by side on this lane's hidden units j = sub, sub + 4, ...:
+//   pe [2 dz] += relu(xe W0e + b0e)_j W1e[j, :],   pd [2 dx] += relu(zd W0d + b0d)_j W1d[j, :]
+// shared-memory row of hidden unit j (WROW floats): W0e[0..5][j] | b0e[j] | W1e[j][0..3] | W0d[0..1][j] | b0d[j] |
+// W1d[j][0..11] | pad  (dx = 6, dz = 2)
+__device__ __forceinline__ void mlp_pair(const float* __restrict__ wsm, int H, int sub, const float (&xe)[kMaxDx],
+                                         const float (&zd)[kMaxDz], float (&pe)[2 * kMaxDz], float (&pd)[2 * kMaxDx]) {
+#pragma unroll
+  for (int n = 0; n < 2 * kMaxDz; ++n) pe[n] = 0.f;
+#pragma unroll
+  for (int n = 0; n < 2 * kMaxDx; ++n) pd[n] = 0.f;
+#pragma unroll 2
+  for (int j = sub; j < H; j += TPC) {
+    const float4* row = reinterpret_cast<const float4*>(wsm + j * WROW);
+    const float4 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4], f = row[5], g = row[6];
+    // encoder hidden unit: (sum_i x_i W0[i][j]) + b0[j]
+    float he = 0.f;
+    he = fmaf(xe[0], a.x, he); he = fmaf(xe[1], a.y, he); he = fmaf(xe[2], a.z, he);
+    he = fmaf(xe[3], a.w, he); he = fmaf(xe[4], b.x, he); he = fmaf(xe[5], b.y, he);
+    he = fmaxf(he + b.z, 0.f);
+    pe[0] = fmaf(he, b.w, pe[0]); pe[1] = fmaf(he, c.x, pe[1]); pe[2] = fmaf(he, c.y, pe[2]); pe[3] = fmaf(he, c.z, pe[3]);
+    // decoder hidden unit
+    float hd = 0.f;
+    hd = fmaf(zd[0], c.w, hd); hd = fmaf(zd[1], d.x, hd);
+    hd = fmaxf(hd + d.y, 0.f);
+    pd[0] = fmaf(hd, d.z, pd[0]); pd[1] = fmaf(hd, d.w, pd[1]);
+    pd[2] = fmaf(hd, e.x, pd[2]); pd[3] = fmaf(hd, e.y, pd[3]); pd[4] = fmaf(hd, e.z, pd[4]); pd[5] = fmaf(hd, e.w, pd[5]);
+    pd[6] = fmaf(hd, f.x, pd[6]); pd[7] = fmaf(hd, f.y, pd[7]); pd[8] = fmaf(hd, f.z, pd[8]); pd[9] = fmaf(hd, f.w, pd[9]);
+    pd[10] = fmaf(hd, g.x, pd[10]); pd[11] = fmaf(hd, g.y, pd[11]);
+  }
+#pragma unroll
+  for (int n = 0; n < 2 * kMaxDz; ++n) pe[n] = quad_sum(pe[n]);
+#pragma unroll
+  for (int n = 0; n < 2 * kMaxDx; ++n) pd[n] = quad_sum(pd[n]);
+}
+
+__global__ void __launch_bounds__(CT) mc_chain_kernel(const ChainParams p) {
+  extern __shared__ __align__(16) float wsm[];  // [H][WROW] + enc b1 [4] + dec b1 [12]
+  const int tid = threadIdx.x;
+  const int H = p.hidden;
+  constexpr int dx = kMaxDx, dz = kMaxDz, nn = 2 * kMaxDz + kMaxDx;
+  for (int e = tid; e < H * WROW; e += CT) {
+    const int j = e / WROW, c = e - j * WROW;
+    float v = 0.f;
+    if (c < 6) v = __ldg(p.theta + p.enc0W + c * H + j);
+    else if (c == 6) v = __ldg(p.theta + p.enc0b + j);
+    else if (c < 11) v = __ldg(p.theta + p.enc1W + j * 4 + (c - 7));
+    else if (c < 13) v = __ldg(p.theta + p.dec0W + (c - 11) * H + j);
+    else if (c == 13) v = __ldg(p.theta + p.dec0b + j);
+    else if (c < 26) v = __ldg(p.theta + p.dec1W + j * 12 + (c - 14));
+    wsm[e] = v;
+  }
+  float* b1e = wsm + H * WROW;
+  float* b1d = b1e + 4;
+  if (tid < 4) b1e[tid] = __ldg(p.theta + p.enc1b + tid);
+  if (tid < 12) b1d[tid] = __ldg(p.theta + p.dec1b + tid);
+  __syncthreads();
+
+  const int64_t chain = (int64_t)blockIdx.x * (CT / TPC) + (tid / TPC);
+  const int sub = tid & (TPC - 1);
+  const bool live = chain < p.B;
+  const int64_t cc = live ? chain : p.B - 1;  // idle lanes shadow the last chain (full-warp shuffles), writes predicated off
+  float x1[dx];
+#pragma unroll
+  for (int d = 0; d < dx; ++d) x1[d] = __ldg(p.x + cc * dx + d);
+  double e_old;
+  if (p.energies_valid) {
+    e_old = p.E[cc];
+  } else {
+    e_old = 0.0;
+#pragma unroll
+    for (int d = 0; d < dx; ++d) {
+      const double t = __dsub_rn((double)x1[d], p.means[d]);
+      e_old = __dadd_rn(e_old, __dmul_rn(t, t));
+    }
+  }
+  unsigned n_accept = 0;
+
+#pragma unroll 1
+  for (int step = 0; step < p.n_steps; ++step) {
+    // ---- noise of this step: eps(z1) [dz] | eps(z2) [dz] | eps(x2) [dx]
+    float nz[12];
+    if (p.noise) {
+#pragma unroll
+      for (int k = 0; k < nn; ++k) nz[k] = __ldg(p.noise + ((int64_t)step * p.B + cc) * nn + k);
+    } else {
+      const unsigned long long st = p.step0 + (unsigned long long)step;
+      const uint2 key = make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32) ^ (unsigned)(st >> 32));
+#pragma unroll
+      for (int q = 0; q < (nn + 3) / 4; ++q) {
+        const uint4 rnd = philox4x32(make_uint4((unsigned)cc, (unsigned)((unsigned long long)cc >> 32), (unsigned)st, (unsigned)q), key);
+        box_muller(rnd.x, rnd.y, nz[4 * q], nz[4 * q + 1]);
+        box_muller(rnd.z, rnd.w, nz[4 * q + 2], nz[4 * q + 3]);
+      }
+    }
+    float z2[dz];
+#pragma unroll
+    for (int d = 0; d < dz; ++d) z2[d] = nz[dz + d];
+    // ---- encoder(x1) || decoder(z2)
+    float pe1[2 * dz], pd2[2 * dx];
+    mlp_pair(wsm, H, sub, x1, z2, pe1, pd2);
+    // ---- samples z1, x2 and the forward log-probabilities (per-dof terms summed in dof order)
+    float z1[dz], x2[dx];
+    float lq1 = 0.f, lz1 = 0.f, lz2 = 0.f, lx2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < dz; ++d) {
+      const float loc = pe1[d] + b1e[d], sc = softplus_tf(pe1[dz + d] + b1e[dz + d]);
+      z1[d] = __fadd_rn(__fmul_rn(nz[d], sc), loc);
+      lq1 += normal_lp(z1[d], loc, sc);
+      lz1 += normal_lp(z1[d], 0.f, 1.f);
+      lz2 += normal_lp(z2[d], 0.f, 1.f);
+    }
+    double e_new = 0.0;
+#pragma unroll
+    for (int d = 0; d < dx; ++d) {
+      const float loc = pd2[d] + b1d[d], sc = softplus_tf(pd2[dx + d] + b1d[dx + d]);
+      x2[d] = __fadd_rn(__fmul_rn(nz[2 * dz + d], sc), loc);
+      lx2 += normal_lp(x2[d], loc, sc);
+      const double t = __dsub_rn((double)x2[d], p.means[d]);
+      e_new = __dadd_rn(e_new, __dmul_rn(t, t));
+    }
+    // ---- encoder(x2) || decoder(z1)
+    float pe2[2 * dz], pd1[2 * dx];
+    mlp_pair(wsm, H, sub, x2, z1, pe2, pd1);
+    float lq2 = 0.f, lx1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < dz; ++d) lq2 += normal_lp(z2[d], pe2[d] + b1e[d], softplus_tf(pe2[dz + d] + b1e[dz + d]));
+#pragma unroll
+    for (int d = 0; d < dx; ++d) lx1 += normal_lp(x1[d], pd1[d] + b1d[d], softplus_tf(pd1[dx + d] + b1d[dx + d]));
+    // ---- accept / reject (mcmc.py:103, :109, :116-120): every lane of the chain computes the same decision
+    const float fwd = __fadd_rn(__fadd_rn(lq1, lz2), lx2);
+    const float rev = __fadd_rn(__fadd_rn(lq2, lz1), lx1);
+    const int64_t g = (int64_t)step * p.B + cc;
+    const double la = __dsub_rn(__dsub_rn(__dadd_rn(e_new, (double)rev), e_old), (double)fwd);
+    const bool a = la >= __ldg(p.log_u + g);
+    if (live && sub == 0) {
+      if (p.acc_trace) p.acc_trace[g] = a ? 1 : 0;
+      if (p.fwd_trace) p.fwd_trace[g] = fwd;
+      if (p.rev_trace) p.rev_trace[g] = rev;
+      if (p.e_new_trace) p.e_new_trace[g] = e_new;
+      n_accept += a ? 1u : 0u;
+    }
+    if (a) {
+      e_old = e_new;
+#pragma unroll
+      for (int d = 0; d < dx; ++d) x1[d] = x2[d];
+    }
+  }
+  if (live && sub == 0) {
+#pragma unroll
+    for (int d = 0; d < dx; ++d) p.x[chain * dx + d] = x1[d];
+    p.E[chain] = e_old;
+  }
+  // accepted moves of the CTA -> one atomic per warp
+  unsigned w = n_accept;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+  if ((tid & 31) == 0 && w) atomicAdd(p.n_acc, (unsigned long long)w);
+}
+
+}  // namespace
+
+bool mc_chain_enabled(int dx, int dz) {
+  const char* e = getenv("VMS_MC_KERNEL");
+  return e && e[0] == 'c' && dx == kMaxDx && dz == kMaxDz;  // "chain"; built for the C4a shape only
+}
+
+vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x, double* E, int energies_valid,
+                        const float* noise, unsigned long long seed, unsigned long long step0, const double* log_u,
+                        const double* means, int64_t B, int n_steps, unsigned long long* n_acc, uint8_t* acc_trace,
+                        float* fwd_trace, float* rev_trace, double* e_new_trace, cudaStream_t st) {
+  VMS_REQUIRE(dx == kMaxDx && dz == kMaxDz, VMS_ERR_UNSUPPORTED, "mc_chain: built for dx = 6, dz = 2");
+  ChainParams p = {};
+  p.dx = dx; p.dz = dz; p.hidden = hidden;
+  int o = 0;
+  p.enc0W = o; o += dx * hidden;
+  p.enc0b = o; o += hidden;
+  p.enc1W = o; o += hidden * 2 * dz;
+  p.enc1b = o; o += 2 * dz;
+  p.dec0W = o; o += dz * hidden;
+  p.dec0b = o; o += hidden;
+  p.dec1W = o; o += hidden * 2 * dx;
+  p.dec1b = o;
+  p.B = B; p.n_steps = n_steps; p.theta = theta; p.x = x; p.E = E; p.energies_valid = energies_valid;
+  p.noise = noise; p.seed = seed; p.step0 = step0; p.log_u = log_u; p.means = means; p.n_acc = n_acc;
+  p.acc_trace = acc_trace; p.fwd_trace = fwd_trace; p.rev_trace = rev_trace; p.e_new_trace = e_new_trace;
+  const size_t smem = (size_t)(hidden * WROW + 16) * sizeof(float);
+  VMS_REQUIRE(smem <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "mc_chain: hidden too large for shared memory");
+  VMS_CUDA(cudaFuncSetAttribute(mc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((B + CT / TPC - 1) / (CT / TPC));
+  mc_chain_kernel<<<grid, CT, smem, st>>>(p);
+  VMS_LAUNCH_CHECK("mc_chain_kernel");
+  return VMS_OK;
+}
+
+}  // namespace vms

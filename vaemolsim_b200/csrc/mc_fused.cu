@@ -271,6 +271,15 @@ __global__ void __launch_bounds__(FT, 1) mc_fused_kernel(const __grid_constant__
 
 }  // namespace vms
 
+namespace vms {
+// mc_chain.cu: experimental four-lanes-per-chain formulation, selected with VMS_MC_KERNEL=chain (default off)
+bool mc_chain_enabled(int dx, int dz);
+vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x, double* E, int energies_valid,
+                        const float* noise, unsigned long long seed, unsigned long long step0, const double* log_u,
+                        const double* means, int64_t B, int n_steps, unsigned long long* n_acc, uint8_t* acc_trace,
+                        float* fwd_trace, float* rev_trace, double* e_new_trace, cudaStream_t st);
+}  // namespace vms
+
 using namespace vms;
 
 struct vms_mc_plan_s {
@@ -356,6 +365,9 @@ vms_status vms_mc_run(vms_mc_plan pl, const float* theta, float* x, double* E, i
   VMS_REQUIRE(theta && x && E && log_u && means && n_acc, VMS_ERR_INVALID_ARG, "mc_run: NULL pointer");
   VMS_REQUIRE(B >= 0 && n_steps >= 0, VMS_ERR_SHAPE, "mc_run: negative size");
   if (B == 0 || n_steps == 0) return VMS_OK;
+  if (mc_chain_enabled(pl->d.dx, pl->d.dz))
+    return mc_chain_run(pl->d.dx, pl->d.dz, pl->d.hidden, theta, x, E, energies_valid, noise, seed, step0, log_u, means, B,
+                        n_steps, n_acc, acc_trace, fwd_trace, rev_trace, e_new_trace, as_stream(stream));
   McParams p = pl->p;
   p.B = B;
   p.n_tiles = (int)((B + FR - 1) / FR);
