@@ -368,6 +368,28 @@ vms_status vms_mc_run(vms_mc_plan plan, const float* theta, float* x, double* E,
                       int64_t B, int n_steps, unsigned long long* n_acc, uint8_t* acc_trace, float* fwd_trace,
                       float* rev_trace, double* e_new_trace, vms_stream stream);
 
+/* The accept uniforms drawn ON THE DEVICE from NumPy's PCG64 stream (mcmc.py:119 `self._rng.random(size=B)` followed by
+ * np.log): chain c at step k owns draw k * n_global + chain0 + c of the stream that starts at `state`; the 128-bit LCG is
+ * jumped ahead per chain (exact integer arithmetic), u = (xsl_rr(state) >> 11) * 2^-53 is bit-identical to NumPy's, log u
+ * is CUDA's double log.  Decisions can differ from np.log's only where |log_acc - log u| <= 1e-13 max(1, |log u|): those
+ * chain-steps are counted in n_uncertain (device u64, +=) and the caller re-runs the call on the host stream (vms_mc_run)
+ * when it is non-zero.  The caller advances its generator by n_steps * n_global afterwards.
+ *   state / inc: `np.random.Generator.bit_generator.state['state']` (128-bit each, split hi / lo);
+ *   stride_mul / stride_add: the affine map of n_global LCG steps (state' = stride_mul * state + stride_add mod 2^128).
+ * vms_mc_plan_has_device_rng: 1 when the plan's kernel carries the stream (the C4a shape dx = 6, dz = 2), else 0 and
+ * vms_mc_run_pcg64 returns VMS_ERR_UNSUPPORTED.  Optional trace log_u_trace [n_steps, B] float64 = the log u used.       */
+typedef struct {
+  uint64_t state_hi, state_lo, inc_hi, inc_lo;
+  uint64_t stride_mul_hi, stride_mul_lo, stride_add_hi, stride_add_lo;
+  int64_t chain0;
+} vms_pcg64_stream;
+int vms_mc_plan_has_device_rng(vms_mc_plan plan);
+vms_status vms_mc_run_pcg64(vms_mc_plan plan, const float* theta, float* x, double* E, int energies_valid, const float* noise,
+                            unsigned long long seed, unsigned long long step0, const vms_pcg64_stream* rng,
+                            const double* means, int64_t B, int n_steps, unsigned long long* n_acc,
+                            unsigned long long* n_uncertain, uint8_t* acc_trace, float* fwd_trace, float* rev_trace,
+                            double* e_new_trace, double* log_u_trace, vms_stream stream);
+
 /* ------------------------------------------------------------------------------- data-parallel exchange step
  * The single collective of data-parallel training (north_star: one gradient allreduce per step) fused with the Adam
  * update, as ONE kernel over NVLink peer memory.  Every rank owns a buffer of vms_peer_buffer_bytes(P) bytes

@@ -1,6 +1,6 @@
 """Device cross-check and timing of the EXPERIMENTAL whole-step tensor-core kernel (csrc/elbo_tcf.cu, plan mode 3) against
 the float32 FFMA per-layer plan (mode 1) and the production fused kernel (mode 0) at the named batch.
-    python scripts/test_elbo_tcf.py [batch ...]"""
+    python scripts/check_elbo_tcf.py [batch ...]"""
 import os
 import sys
 

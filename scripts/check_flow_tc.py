@@ -1,6 +1,6 @@
 """Device cross-check of the tensor-core coupling-block kernels (csrc/flow_tc.cu, plan mode 2) against the float32
 FFMA per-layer plan (mode 1) and the single fused kernel (mode 0): forward outputs per row, loss scalars, flat
-gradient; then timings at the C5 shard size.  Run on a B200:  python scripts/test_flow_tc.py [batch ...]"""
+gradient; then timings at the C5 shard size.  Run on a B200:  python scripts/check_flow_tc.py [batch ...]"""
 import os
 import sys
 import time

@@ -529,21 +529,28 @@ def _mc_noise(seed, n_steps, B, dz, dx):
     return out
 
 
-def test_fused_mc_matches_reference_mcmc_py_goldens(vms):
-    """`vms_mc_run` against the decisions of the REFERENCE's own vaemolsim/mcmc.py (tests/golden/make_goldens.py):
-    every step restarted from the golden state, same sampling noise, same PCG64 uniform stream."""
+@pytest.mark.parametrize('device_rng', [False, True])
+def test_fused_mc_matches_reference_mcmc_py_goldens(vms, device_rng):
+    """`vms_mc_run` / `vms_mc_run_pcg64` against the decisions of the REFERENCE's own vaemolsim/mcmc.py
+    (tests/golden/make_goldens.py): every step restarted from the golden state, same sampling noise, same PCG64 uniform
+    stream -- drawn by NumPy on the host (device_rng False) or regenerated on the device by LCG jump-ahead (True)."""
     v = vms
     g = np.load(os.path.join(GOLD, 'mcmc_reference_c4a.npz'))
     P = ovae.init_vae(1003, prior='normal', hidden=32)
     model = vae_from_oracle(v, P)
     noise = _mc_noise(777, 5, 64, 2, 6)
     mc = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=4002)
+    mc.device_rng = device_rng
+    assert mc._fused_plan()['device_rng']  # the C4a shape runs the chain kernel, which carries the device stream
     safe_total = 0
     for s in range(5):
         x_old, e_old = g['x_old_%d' % s], g['e_old_%d' % s]
         x_new, e_new = mc.run_fused(x_old, energies=e_old if s else None, n_steps=1, noise=noise[s:s + 1], trace=True)
         tr = mc._last_trace
-        assert np.array_equal(tr['log_u'][0], g['log_rand_%d' % s])  # same PCG64 stream as the reference driver
+        if device_rng:  # bit-identical uniforms; CUDA's double log against np.log: <= 2 ulp
+            np.testing.assert_array_max_ulp(tr['log_u'][0], g['log_rand_%d' % s], maxulp=2)
+        else:
+            assert np.array_equal(tr['log_u'][0], g['log_rand_%d' % s])  # same PCG64 stream as the reference driver
         assert_close(tr['fwd'][0], g['fwd_%d' % s], rtol=1e-5, atol=2e-5, what='forward_log_p step %d' % s)
         assert_close(tr['rev'][0], g['rev_%d' % s], rtol=1e-5, atol=2e-5, what='reverse_log_p step %d' % s)
         assert_close(tr['e_new'][0], g['e_new_%d' % s], rtol=1e-5, atol=1e-5, what='proposal energy step %d' % s)
@@ -560,6 +567,66 @@ def test_fused_mc_matches_reference_mcmc_py_goldens(vms):
         assert_close(x_new[same], g['configs_%d' % s][same], rtol=1e-5, atol=2e-5, what='configs step %d' % s)
         assert_close(e_new[same], g['energies_%d' % s][same], rtol=1e-5, atol=2e-5, what='energies step %d' % s)
     assert safe_total > 300 and mc._num_trials == 5 * 64
+    assert mc.host_stream_reruns == 0
+    # the host generator sits where the reference's would after 5 x 64 draws
+    want_next = np.random.default_rng(4002)
+    want_next.random(size=5 * 64)
+    assert mc._rng.random() == want_next.random()
+
+
+def test_device_pcg64_stream_equals_host_stream(vms):
+    """The device-drawn accept uniforms (`vms_mc_run_pcg64`) reproduce NumPy's PCG64 stream: same decisions / final state
+    as the host-stream path over many steps, for a whole chain set and for a shard (chain0, n_global) of it; the
+    uncertainty fallback re-runs a call on the host stream."""
+    v = vms
+    P = ovae.init_vae(11, prior='normal', hidden=200)
+    model = vae_from_oracle(v, P)
+    B, n_steps = 3000, 40
+    x0 = np.random.default_rng(5).normal(size=(B, 6)).astype(np.float32)
+    energy = v.mcmc.QuadraticEnergy(6)
+    a, b = v.mcmc.MCMC(model, energy, random_seed=9), v.mcmc.MCMC(model, energy, random_seed=9)
+    b.device_rng = False
+    xa, ea = a.run_fused(x0, n_steps=n_steps, trace=True)
+    tra = a._last_trace
+    xb, eb = b.run_fused(x0, n_steps=n_steps, trace=True)
+    trb = b._last_trace
+    u = np.random.default_rng(9).random(size=(n_steps, B))
+    np.testing.assert_array_max_ulp(tra['log_u'], np.log(u), maxulp=2)
+    assert np.array_equal(trb['log_u'], np.log(u))
+    assert np.array_equal(tra['acc'], trb['acc']) and np.array_equal(xa, xb) and np.array_equal(ea, eb)
+    assert a._num_acc == b._num_acc and a._rng.random() == b._rng.random()
+    # a shard of a global chain set draws ITS columns of the global stream
+    lo, hi = 1000, 2200
+    c1 = v.mcmc.MCMC(model, energy, random_seed=9, stream_layout=(lo, B))
+    xc, ec = c1.run(x0[lo:hi], n_steps=n_steps)
+    assert np.array_equal(xc, xa[lo:hi]) and np.array_equal(ec, ea[lo:hi])
+    c2 = v.mcmc.MCMC(model, energy, random_seed=9, stream_layout=(lo, B))
+    c2.device_rng = False
+    xd, ed = c2.run(x0[lo:hi], n_steps=n_steps)
+    assert np.array_equal(xd, xc) and c2._rng.random() == c1._rng.random()
+    # two calls continue the stream exactly like one
+    d = v.mcmc.MCMC(model, energy, random_seed=9)
+    x1, e1 = d.run(x0, n_steps=15)
+    x2, e2 = d.run(x1, energies=e1, n_steps=n_steps - 15)
+    assert np.array_equal(x2, xa) and np.array_equal(e2, ea) and d._num_acc == a._num_acc
+    # the fallback: pretend the device flagged an uncertain decision -> the call is repeated on the host stream
+    f = v.mcmc.MCMC(model, energy, random_seed=9)
+    fp = f._fused_plan()
+    one = np.array([1], np.uint64)
+
+    class Poisoned(v.Tensor):
+        def fill_zero(self):
+            c = v._abi.ctx()
+            c.lib.vms_memcpy_h2d(self.ptr, one.ctypes.data, 8, c.stream)
+            c.synchronize()
+            return self
+
+    pois = Poisoned((1, ), np.uint64)
+    fp['n_unc'] = pois
+    xf, ef = f.run_fused(x0, n_steps=n_steps)
+    assert f.host_stream_reruns == 1
+    assert np.array_equal(xf, xa) and np.array_equal(ef, ea) and f._num_acc == a._num_acc
+    assert f._rng.random() == np.random.default_rng(9).random(size=n_steps * B + 1)[-1]
 
 
 def test_fused_mc_multi_step_equals_single_steps_and_op_by_op_path(vms):
@@ -594,6 +661,7 @@ def test_fused_mc_multi_step_equals_single_steps_and_op_by_op_path(vms):
     assert 0.0 < c1.acceptance_rate <= 1.0
     # long runs through the public API are pipelined in chunks of 10 steps (host PCG64 || device): same result as one launch
     c3, c4 = v.mcmc.MCMC(model, energy, random_seed=3), v.mcmc.MCMC(model, energy, random_seed=3)
+    c3.device_rng = False
     x3, e3 = c3.run(x0, n_steps=25)
     lo25 = np.log(np.random.default_rng(3).random(size=(25, B)))
     x4, e4 = c4.run_fused(x0, n_steps=25, log_u_dev=v.Tensor.from_numpy(lo25))

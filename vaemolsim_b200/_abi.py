@@ -40,6 +40,12 @@ class McDesc(C.Structure):
     _fields_ = [('dx', C.c_int32), ('dz', C.c_int32), ('hidden', C.c_int32)]
 
 
+class Pcg64Stream(C.Structure):
+    _fields_ = [('state_hi', C.c_uint64), ('state_lo', C.c_uint64), ('inc_hi', C.c_uint64), ('inc_lo', C.c_uint64),
+                ('stride_mul_hi', C.c_uint64), ('stride_mul_lo', C.c_uint64), ('stride_add_hi', C.c_uint64),
+                ('stride_add_lo', C.c_uint64), ('chain0', c_i64)]
+
+
 class ElboDesc(C.Structure):
     _fields_ = [('dx', C.c_int32), ('dz', C.c_int32), ('hidden', C.c_int32), ('num_blocks', C.c_int32),
                 ('num_bins', C.c_int32), ('flow_hidden', C.c_int32), ('bin_min', c_f32), ('bin_max', c_f32),
@@ -138,6 +144,9 @@ _SIGS = {
     'vms_mc_plan_destroy': (None, [c_vp]),
     'vms_mc_run': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, C.c_ulonglong, C.c_ulonglong, c_vp, c_vp, c_i64, c_int, c_vp,
                           c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vms_mc_plan_has_device_rng': (c_int, [c_vp]),
+    'vms_mc_run_pcg64': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, C.c_ulonglong, C.c_ulonglong, C.POINTER(Pcg64Stream),
+                                c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_elbo_forward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_elbo_forward_backward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
 }
@@ -285,6 +294,24 @@ class Tensor(object):
             c.lib.vms_memset(t.ptr, 0, t.nbytes, c.stream)
         return t
 
+    def fill_zero(self):
+        if self.nbytes:
+            c = ctx()
+            c.lib.vms_memset(self.ptr, 0, self.nbytes, c.stream)
+        return self
+
+    # -- DLPack (the zero-copy bridge a TF / JAX / CuPy / torch caller uses: `tf.experimental.dlpack.to_dlpack(t)` ->
+    #    `Tensor.from_dlpack`, `tf.experimental.dlpack.from_dlpack(t.__dlpack__())`); see _dlpack below
+    def __dlpack__(self, stream=None, **kwargs):
+        return _dlpack_export(self, stream)
+
+    def __dlpack_device__(self):
+        return (_kDLCUDA, ctx().device)
+
+    @staticmethod
+    def from_dlpack(obj, stream=None):
+        return _dlpack_import(obj, stream)
+
     @property
     def ndim(self):
         return len(self.shape)
@@ -408,6 +435,141 @@ class Tensor(object):
 
     def __repr__(self):
         return 'Tensor(shape=%s, dtype=%s, device=cuda:%d)' % (self.shape, self.dtype.name, ctx().device)
+
+
+# ------------------------------------------------------------------------------------------------- DLPack
+# north_star: "a ctypes/DLPack-bridged TF custom op".  The capsules are built by hand with ctypes (no torch, no cupy): a
+# `DLManagedTensor` (dlpack.h, v0.x ABI -- what tf.experimental.dlpack / torch.utils.dlpack / cupy exchange) whose deleter
+# drops the reference that keeps the producing Tensor alive.  Import wraps the foreign device pointer without copying and
+# calls the producer's deleter when the wrapping Tensor dies.
+_kDLCUDA = 2
+_DL_CODES = {'i': 0, 'u': 1, 'f': 2}
+_DL_KINDS = {0: 'i', 1: 'u', 2: 'f'}
+
+
+class _DLDevice(C.Structure):
+    _fields_ = [('device_type', C.c_int32), ('device_id', C.c_int32)]
+
+
+class _DLDataType(C.Structure):
+    _fields_ = [('code', C.c_uint8), ('bits', C.c_uint8), ('lanes', C.c_uint16)]
+
+
+class _DLTensor(C.Structure):
+    _fields_ = [('data', C.c_void_p), ('device', _DLDevice), ('ndim', C.c_int32), ('dtype', _DLDataType),
+                ('shape', C.POINTER(C.c_int64)), ('strides', C.POINTER(C.c_int64)), ('byte_offset', C.c_uint64)]
+
+
+class _DLManagedTensor(C.Structure):
+    pass
+
+
+_DLDeleter = C.CFUNCTYPE(None, C.POINTER(_DLManagedTensor))
+_DLManagedTensor._fields_ = [('dl_tensor', _DLTensor), ('manager_ctx', C.c_void_p), ('deleter', _DLDeleter)]
+
+_dl_live = {}  # id -> (managed struct, shape array, strides array, Tensor): kept alive until the consumer's deleter runs
+_pyapi = C.pythonapi
+_pyapi.PyCapsule_New.restype = C.py_object
+_pyapi.PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+_pyapi.PyCapsule_IsValid.restype = C.c_int
+_pyapi.PyCapsule_IsValid.argtypes = [C.py_object, C.c_char_p]
+_pyapi.PyCapsule_GetPointer.restype = C.c_void_p
+_pyapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+_pyapi.PyCapsule_SetName.restype = C.c_int
+_pyapi.PyCapsule_SetName.argtypes = [C.py_object, C.c_char_p]
+
+
+@_DLDeleter
+def _dl_deleter(mt):
+    _dl_live.pop(C.addressof(mt.contents), None)
+
+
+_PyCapsuleDestructor = C.CFUNCTYPE(None, C.c_void_p)
+
+
+@_PyCapsuleDestructor
+def _dl_capsule_destructor(capsule):
+    # a capsule nobody consumed still carries the name "dltensor": run the deleter ourselves (DLPack protocol)
+    cap = C.cast(capsule, C.py_object)
+    if _pyapi.PyCapsule_IsValid(cap, b'dltensor'):
+        ptr = _pyapi.PyCapsule_GetPointer(cap, b'dltensor')
+        _dl_live.pop(ptr, None)
+
+
+def _dlpack_export(t, stream=None):
+    """PyCapsule("dltensor") over `t`'s device memory.  Work queued on the library stream is completed first (the
+    consumer's stream is unknown to a ctypes producer), so the consumer may read immediately."""
+    if t.dtype.kind not in _DL_CODES:
+        raise TypeError('__dlpack__: unsupported dtype %s' % t.dtype)
+    ctx().synchronize()
+    nd = len(t.shape)
+    shape = (C.c_int64 * max(nd, 1))(*t.shape)
+    strides = None
+    if nd == 2 and not t.contiguous:
+        strides = (C.c_int64 * 2)(t.ld, 1)
+    mt = _DLManagedTensor()
+    mt.dl_tensor.data = t.ptr
+    mt.dl_tensor.device = _DLDevice(_kDLCUDA, ctx().device)
+    mt.dl_tensor.ndim = nd
+    mt.dl_tensor.dtype = _DLDataType(_DL_CODES[t.dtype.kind], t.dtype.itemsize * 8, 1)
+    mt.dl_tensor.shape = C.cast(shape, C.POINTER(C.c_int64))
+    mt.dl_tensor.strides = C.cast(strides, C.POINTER(C.c_int64)) if strides is not None else None
+    mt.dl_tensor.byte_offset = 0
+    mt.manager_ctx = None
+    mt.deleter = _dl_deleter
+    _dl_live[C.addressof(mt)] = (mt, shape, strides, t)
+    return _pyapi.PyCapsule_New(C.addressof(mt), b'dltensor', C.cast(_dl_capsule_destructor, C.c_void_p))
+
+
+class _Foreign(object):
+    """Owner of an imported DLManagedTensor: calls the producer's deleter when the last view dies."""
+
+    def __init__(self, mt_ptr):
+        self.mt_ptr = mt_ptr
+
+    def __del__(self):
+        try:
+            mt = C.cast(self.mt_ptr, C.POINTER(_DLManagedTensor))
+            if mt.contents.deleter:
+                mt.contents.deleter(mt)
+        except Exception:
+            pass
+
+
+def _dlpack_import(obj, stream=None):
+    """Zero-copy Tensor over a DLPack producer (an object with `__dlpack__`, or a "dltensor" capsule): CUDA device memory on
+    this context's device, compact row-major (or a 2-D row-strided view)."""
+    cap = obj.__dlpack__() if hasattr(obj, '__dlpack__') else obj
+    if not _pyapi.PyCapsule_IsValid(cap, b'dltensor'):
+        raise ValueError('from_dlpack: not a "dltensor" capsule (already consumed?)')
+    ptr = _pyapi.PyCapsule_GetPointer(cap, b'dltensor')
+    mt = C.cast(ptr, C.POINTER(_DLManagedTensor)).contents
+    dl = mt.dl_tensor
+    if dl.device.device_type != _kDLCUDA:
+        raise ValueError('from_dlpack: only CUDA device memory can be wrapped (device_type %d); there is no host path'
+                         % dl.device.device_type)
+    if dl.device.device_id != ctx().device:
+        raise ValueError('from_dlpack: tensor lives on cuda:%d, this context is cuda:%d' % (dl.device.device_id, ctx().device))
+    if dl.dtype.lanes != 1 or dl.dtype.code not in _DL_KINDS:
+        raise TypeError('from_dlpack: unsupported dtype (code %d, lanes %d)' % (dl.dtype.code, dl.dtype.lanes))
+    dtype = np.dtype('%s%d' % (_DL_KINDS[dl.dtype.code], dl.dtype.bits // 8))
+    shape = tuple(int(dl.shape[i]) for i in range(dl.ndim))
+    ld = None
+    if dl.strides:
+        strides = tuple(int(dl.strides[i]) for i in range(dl.ndim))
+        compact, acc = [], 1
+        for n in reversed(shape):
+            compact.append(acc)
+            acc *= n
+        compact = tuple(reversed(compact))
+        if strides != compact and not all(n <= 1 or a == b for n, a, b in zip(shape, strides, compact)):
+            if dl.ndim == 2 and strides[1] == 1 and strides[0] >= shape[1]:
+                ld = strides[0]
+            else:
+                raise ValueError('from_dlpack: only compact row-major or 2-D row-strided tensors (strides %s)' % (strides, ))
+    _pyapi.PyCapsule_SetName(cap, b'used_dltensor')  # ownership of the managed tensor is ours now
+    owner = _Foreign(ptr)
+    return Tensor(shape, dtype, _ptr=int(dl.data or 0) + int(dl.byte_offset), _base=owner, _ld=ld)
 
 
 def as_tensor(x, dtype=np.float32):

@@ -4,7 +4,7 @@
 // MN-major reads of the same tiles, octet spline routines on the raw parameters) for all blocks of the chain back to
 // back, with the encoder / decoder MLPs of mlp_stream.cu as in-tile phases, so that at the named batch (4096 rows = 64
 // tiles) the step is one launch whose heavy products run on the tensor core instead of the FFMA pipe of
-// elbo_fused.cu.  Status (round 1, one measurement, scripts/test_elbo_tcf.py at batch 4096): CORRECT -- loss scalars equal
+// elbo_fused.cu.  Status (round 1, one measurement, scripts/check_elbo_tcf.py at batch 4096): CORRECT -- loss scalars equal
 // to 7 digits, flat gradient 1.5e-7 (norm) against the FFMA plan, worst layer 1.6e-6 -- but SLOWER than the FFMA fused
 // kernel: 0.187 ms against 0.146 ms forward + backward.  One 64-row tile per CTA keeps only 64 of 148 SMs busy and the
 // RealNVP chain makes a tile's phases strictly sequential (block i needs block i + 1's output), so the tensor core
@@ -14,7 +14,7 @@
 // AFTER that measurement (no GPU time left in round 1) the row loops were parametrised by `rows` = valid rows per tile:
 // rows = 64 is the default and is meant to be the measured code path unchanged; VMS_TCF_ROWS=32 selects 32-row tiles
 // (zero-padded M = 64 products, d hW over 2 k-steps) and has NOT run on a device yet.  First thing to do next round:
-// `python scripts/test_elbo_tcf.py 4096` with and without VMS_TCF_ROWS=32.
+// `python scripts/check_elbo_tcf.py 4096` with and without VMS_TCF_ROWS=32.
 //
 // Reference lines replaced: the same as elbo.cu (models.py:289-322 VAE.call; mappings.py:107-155 FCDeepNN;
 // flows.py:184-207, :281-355 RQSSplineRealNVP; dists.py:414-439; losses.py:58, :253) plus TF autodiff through them.

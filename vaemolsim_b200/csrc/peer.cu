@@ -11,6 +11,10 @@
 //      and applies Adam to its local theta / m / v in the same thread.
 // No host round trip, no second kernel, and the sum is deterministic.
 //
+// Failure handling: the wait is bounded in wall-clock time (VMS_PEER_TIMEOUT_MS, default 2000).  A rank that gives up does
+// NOT apply an update, poisons every replica's buffer so nobody updates afterwards, and `PeerExchange.check()` raises on
+// the host -- a stalled peer can no longer silently desynchronise the replicas.
+//
 // Buffers: each rank owns one device allocation [2][P] floats (gradient slots, double-buffered by step parity) +
 // 64 x uint64 flags, shared with the peers through CUDA IPC (vms_ipc_*; handles travel over torch.distributed, which
 // stays the plumbing).  Double buffering is what makes a single barrier per step enough: a rank overwrites slot s & 1
@@ -19,6 +23,7 @@
 // One process per GPU: the kernel waits on OTHER GPUs' kernels, never on another kernel of the same GPU.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace vms {
@@ -35,14 +40,27 @@ struct PeerArgs {
   float *theta, *m, *v;
   float lr_t, one_minus_b1, one_minus_b2, eps;
   float* grad_out;  // optional: the reduced, scaled gradient [P]
+  unsigned long long timeout_ns;
 };
 
 __device__ __forceinline__ unsigned long long* flags_of(float* base, int64_t P) {
   return reinterpret_cast<unsigned long long*>(base + 2 * P);
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Flag slots of a rank's buffer (uint64 each):  [0, 8) arrival flags written by the ranks;  32 + r: rank r gave up waiting
+// at that step (written by r into its own buffer);  40: this rank's grid-wide decision for the current step (2 step + failed,
+// written by block 0, read by the other blocks);  48: POISON -- some rank of the job timed out (written by that rank into
+// every buffer): from then on no rank updates its parameters, so replicas differ by at most the one step in flight and the
+// host (`PeerExchange.check`) raises instead of training on.
 __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(const PeerArgs a) {
-  __shared__ int ready;
+  __shared__ int failed;
+  volatile unsigned long long* mine = flags_of(a.base[a.rank], a.P);
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) {
       // the gradient of this step was written by the preceding kernel on this stream; make it visible system-wide,
@@ -53,24 +71,36 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(const PeerArgs
         *f = a.step;
       }
       __threadfence_system();
-    }
-    // wait for every rank's flag in MY buffer.  Bounded: a rank that never arrives (crashed peer) must not hang this GPU;
-    // after ~2 s the kernel gives up, records the failure in flag slot 32 + rank of its own buffer and carries on.
-    volatile unsigned long long* mine = flags_of(a.base[a.rank], a.P);
-    const long long t0 = clock64();
-    for (int r = 0; r < a.world; ++r) {
-      while (mine[r] < a.step) {
-        __nanosleep(64);
-        if (clock64() - t0 > 4000000000LL) {
-          mine[32 + a.rank] = a.step;
-          break;
+      // wait for every rank's flag in MY buffer.  Bounded (wall-clock nanoseconds, independent of the SM clock): a rank
+      // that never arrives must not hang this GPU.  ONE block decides for the grid, so all blocks agree.
+      int bad = mine[48] != 0ull ? 1 : 0;
+      const unsigned long long t0 = globaltimer_ns();
+      for (int r = 0; r < a.world && !bad; ++r) {
+        while (mine[r] < a.step) {
+          __nanosleep(64);
+          if (globaltimer_ns() - t0 > a.timeout_ns || mine[48] != 0ull) {
+            bad = 1;
+            break;
+          }
         }
       }
+      if (bad) {
+        mine[32 + a.rank] = a.step;
+        for (int r = 0; r < a.world; ++r) flags_of(a.base[r], a.P)[48] = a.step;  // poison every replica
+      }
+      __threadfence_system();
+      mine[40] = 2ull * a.step + (unsigned long long)bad;
+      failed = bad;
+    } else {
+      // block 0 is always dispatched first and waits on nothing of this grid: no co-residency requirement
+      unsigned long long d;
+      while ((d = mine[40]) < 2ull * a.step) __nanosleep(32);
+      __threadfence();
+      failed = (int)(d & 1ull);
     }
-    __threadfence_system();
-    ready = 1;
   }
   __syncthreads();
+  if (failed) return;  // no update on a failed exchange: theta / m / v keep the last consistent state
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.P) return;
   const int64_t off = (int64_t)(a.step & 1ull) * a.P + i;
@@ -137,6 +167,12 @@ vms_status vms_peer_allreduce_adam(int world, int rank, void* const* peer_bases,
   a.one_minus_b1 = (float)(1.0 - beta1);
   a.one_minus_b2 = (float)(1.0 - beta2);
   a.eps = (float)eps;
+  static unsigned long long timeout_ms = 0;
+  if (!timeout_ms) {
+    const char* e = getenv("VMS_PEER_TIMEOUT_MS");
+    timeout_ms = e && atoll(e) > 0 ? (unsigned long long)atoll(e) : 2000ull;
+  }
+  a.timeout_ns = timeout_ms * 1000000ull;
   peer_allreduce_adam_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, as_stream(stream)>>>(a);
   VMS_LAUNCH_CHECK("peer_allreduce_adam_kernel");
   return VMS_OK;

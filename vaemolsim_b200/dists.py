@@ -97,7 +97,15 @@ class IndependentBlockwise(P.Layer):
         mode = None
         for i, d in enumerate(self.dist_classes):
             vm = d.__name__ == 'VonMises'
-            ident = self.param_transforms[i] is _identity
+            tf = self.param_transforms[i]
+            ident = tf is _identity
+            # the reference calls self.param_transforms[i](params[i]) (dists.py:213); here the transform is fused into the
+            # kernels, so only the two transforms that HAVE a kernel are accepted -- anything else must fail, not be
+            # silently replaced by the default
+            want_kind = P.DIST_VONMISES if vm else P.DIST_NORMAL
+            if not ident and getattr(tf, 'dist_kind', None) != want_kind:
+                raise NotImplementedError('param_transforms[%d]: only the identity and make_param_transform(%s) have device '
+                                          'kernels; got %r' % (i, d.__name__, tf))
             this_mode = P.SCALE_IDENTITY if ident else P.SCALE_SOFTPLUS_EPS
             if mode is not None and this_mode != mode:
                 raise NotImplementedError('mixing identity and default parameter transforms is not supported')

@@ -3,8 +3,11 @@
 Same class, methods and counters as the reference (mcmc.py:12 `MCMC`, :48 `acceptance_rate`, :52 `reset`, :68
 `single_step`, :133 `run`).  The six distribution evaluations of a step (mcmc.py:100-108) are the kernels behind
 `vae.encoder / prior / decoder`; the acceptance arithmetic of mcmc.py:116-128 is `vms_mc_accept` (float64, same
-operation order).  The uniform stream stays NumPy's PCG64 + `np.log` on the host (mcmc.py:119) so decisions are
-bit-identical to the reference under the same seed; 8 bytes per chain per step are uploaded.
+operation order).  The accept uniforms are NumPy's PCG64 stream (mcmc.py:119) under the same seed: the op-by-op path draws
+them on the host (8 bytes per chain per step uploaded); the fused path for the C4a shape regenerates the SAME stream on
+the device (`vms_mc_run_pcg64`: per-chain LCG jump-ahead, bit-identical uniforms, CUDA double log) and falls back to the
+host stream for a call whose decisions could depend on the last ulps of the logarithm, so decisions are those of the
+reference either way.
 """
 import ctypes as C
 
@@ -31,16 +34,18 @@ class QuadraticEnergy(object):
 class MCMC(object):
     """Markov chain Monte Carlo with a VAE proposal: as many independent chains as input configurations."""
 
-    def __init__(self, vae, energy_func, random_seed=None):
+    def __init__(self, vae, energy_func, random_seed=None, stream_layout=None):
+        """`stream_layout = (chain0, n_chains_global)` (extension, default (0, B)): this object's chains are rows
+        [chain0, chain0 + B) of a global set of n_chains_global chains that share ONE uniform stream -- how a multi-GPU job
+        keeps the decisions of the single-process run."""
         self.vae = vae
         self.energy_func = energy_func
-        self._num_trials = 0.0
-        self._num_acc = 0.0
-        self._rng = np.random.default_rng(seed=random_seed)
+        self.stream_layout = stream_layout
         self._fused = None
-        self._noise_seed = int(np.random.SeedSequence(random_seed).generate_state(2, np.uint32).astype(np.uint64) @
-                               np.array([1, 1 << 32], np.uint64))
-        self._step0 = 0
+        self._acc_folded = 0   # value of the device acceptance counter already folded into _num_acc
+        self.device_rng = True  # fused path: draw the accept uniforms on the device when the kernel supports it
+        self.host_stream_reruns = 0
+        self.reset(random_seed)
 
     @property
     def acceptance_rate(self):
@@ -53,6 +58,9 @@ class MCMC(object):
         self._noise_seed = int(np.random.SeedSequence(random_seed).generate_state(2, np.uint32).astype(np.uint64) @
                                np.array([1, 1 << 32], np.uint64))
         self._step0 = 0
+        if self._fused:  # accepts counted on the device before the reset must not leak into the new statistics
+            self._fused['n_acc'].fill_zero()
+        self._acc_folded = 0
 
     # ------------------------------------------------------------------------------------------ fused device path
     def _fused_plan(self):
@@ -77,8 +85,61 @@ class MCMC(object):
         except NotImplementedError:
             return None
         self._fused = dict(handle=h.value, elbo=f, means=Tensor.from_numpy(self.energy_func.means),
-                           n_acc=Tensor.zeros((1, ), np.uint64))
+                           n_acc=Tensor.zeros((1, ), np.uint64), n_unc=Tensor.zeros((1, ), np.uint64),
+                           device_rng=bool(c.lib.vms_mc_plan_has_device_rng(h.value)))
         return self._fused
+
+    def close(self):
+        """Releases the fused MC plan and the pinned uniform buffers."""
+        lib = _abi.load()
+        if self._fused:
+            lib.vms_mc_plan_destroy(self._fused['handle'])
+        self._fused = None
+        ub = getattr(self, '_ub', None)
+        if ub is not None:
+            ctx().synchronize()
+            host, dev, evs, raw = ub
+            for e in evs:
+                lib.vms_event_destroy(e)
+            for p in raw:
+                lib.vms_free_host(p)
+            self._ub, self._ub_key = None, None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the PCG64 stream as the device kernel consumes it
+    _PCG_MULT = 0x2360ED051FC65DA44385DF649FCCF645
+    _M128 = (1 << 128) - 1
+
+    def _pcg_stream(self, chain0, n_global):
+        """`vms_pcg64_stream` describing self._rng's CURRENT position: state / increment and the affine jump over n_global
+        draws (one MC step of the global chain set), computed with Python integers (pcg_advance_lcg_128)."""
+        st = self._rng.bit_generator.state
+        if st.get('bit_generator') != 'PCG64':
+            return None
+        state, inc = int(st['state']['state']), int(st['state']['inc'])
+        key = (inc, int(n_global))
+        if getattr(self, '_jump_key', None) != key:
+            am, ap, cm, cp, d, M = 1, 0, self._PCG_MULT, inc, int(n_global), self._M128
+            while d > 0:
+                if d & 1:
+                    am, ap = (am * cm) & M, (ap * cm + cp) & M
+                cp, cm, d = ((cm + 1) * cp) & M, (cm * cm) & M, d >> 1
+            self._jump_key, self._jump = key, (am, ap)
+        am, ap = self._jump
+        lo64 = (1 << 64) - 1
+        return _abi.Pcg64Stream(state >> 64, state & lo64, inc >> 64, inc & lo64, am >> 64, am & lo64, ap >> 64, ap & lo64,
+                                int(chain0))
+
+    def _fold(self):
+        """Fold the device acceptance counter into `_num_acc` (one bookkeeping for the host- and device-resident paths)."""
+        total = int(self._fused['n_acc'].numpy()[0])
+        self._num_acc += float(total - self._acc_folded)
+        self._acc_folded = total
 
     def run_fused(self, configs, energies=None, n_steps=1, noise=None, trace=False, configs_dev=None, energies_dev=None,
                   log_u_dev=None):
@@ -104,20 +165,54 @@ class MCMC(object):
             e, valid = as_tensor(np.asarray(energies, np.float64), dtype=np.float64), 1
         nz = None if noise is None else Tensor.from_numpy(np.ascontiguousarray(noise, np.float32))
         P_ = lambda t: None if t is None else t.ptr
-        before = int(fp['n_acc'].numpy()[0]) if configs_dev is None else None
         tr = {}
+        chain0, n_global = self.stream_layout if self.stream_layout is not None else (0, B)
+        stream = self._pcg_stream(chain0, n_global) if (self.device_rng and fp['device_rng'] and log_u_dev is None) else None
+        done = False
+        if stream is not None:
+            # the accept uniforms are drawn ON THE DEVICE from this generator's PCG64 stream (bit-identical u, device log):
+            # no host draw, no upload.  The chain state is saved first so the call can be repeated on the host stream in the
+            # (~1e-6 per run) case that a decision sits within ~1e-13 of its threshold.
+            x_save, e_save = Tensor(x.shape), Tensor((B, ), np.float64)
+            c.lib.vms_memcpy_d2d(x_save.ptr, x.ptr, x.nbytes, c.stream)
+            if valid:
+                c.lib.vms_memcpy_d2d(e_save.ptr, e.ptr, e.nbytes, c.stream)
+            acc_before = Tensor((1, ), np.uint64)
+            c.lib.vms_memcpy_d2d(acc_before.ptr, fp['n_acc'].ptr, 8, c.stream)
+            fp['n_unc'].fill_zero()
+            if trace:
+                tr = dict(acc=Tensor((n_steps, B), np.uint8), fwd=Tensor((n_steps, B)), rev=Tensor((n_steps, B)),
+                          e_new=Tensor((n_steps, B), np.float64), log_u=Tensor((n_steps, B), np.float64))
+            c.lib.vms_mc_run_pcg64(fp['handle'], f.theta.ptr, x.ptr, e.ptr, valid, P_(nz), self._noise_seed, self._step0,
+                                   C.byref(stream), fp['means'].ptr, B, n_steps, fp['n_acc'].ptr, fp['n_unc'].ptr,
+                                   P_(tr.get('acc')), P_(tr.get('fwd')), P_(tr.get('rev')), P_(tr.get('e_new')),
+                                   P_(tr.get('log_u')), c.stream)
+            if configs_dev is not None and not self.check_uncertain:
+                done = True  # device-resident loops check `uncertain()` themselves (one read-back per loop, not per call)
+            elif int(fp['n_unc'].numpy()[0]) == 0:
+                done = True
+            else:  # repeat this call on the NumPy stream: restore the chain state and the acceptance counter
+                self.host_stream_reruns += 1
+                c.lib.vms_memcpy_d2d(x.ptr, x_save.ptr, x.nbytes, c.stream)
+                if valid:
+                    c.lib.vms_memcpy_d2d(e.ptr, e_save.ptr, e.nbytes, c.stream)
+                c.lib.vms_memcpy_d2d(fp['n_acc'].ptr, acc_before.ptr, 8, c.stream)
+                tr = {}
+            if done:
+                self._rng.bit_generator.advance(n_steps * n_global)
         chunk = 10
-        if log_u_dev is None and nz is None and not trace and n_steps > chunk:
+        if done:
+            pass
+        elif log_u_dev is None and nz is None and not trace and n_steps > chunk:
             # pipeline: the host draws / logs the uniforms of the next `chunk` steps (mcmc.py:119; ONE sequential PCG64
-            # stream, so it cannot be parallelised) while the device runs the previous chunk's launch
-            host, dev, evs = self._uniform_buffers(chunk, B)
+            # stream) while the device runs the previous chunk's launch
+            host, dev, evs, _ = self._uniform_buffers(chunk, B)
             for k, s0 in enumerate(range(0, n_steps, chunk)):
                 ns, i = min(chunk, n_steps - s0), k & 1
                 if k >= 2:
                     c.lib.vms_event_synchronize(evs[i])  # the upload that last used this pinned buffer has finished
                 h = host[i][:ns]
-                self._rng.random(out=h)
-                np.log(h, out=h)
+                self._host_uniform_logs(h, chain0, n_global)
                 c.lib.vms_memcpy_h2d(dev[i].ptr, h.ctypes.data, ns * B * 8, c.stream)  # pinned => truly asynchronous
                 c.lib.vms_event_record(evs[i], c.stream)
                 c.lib.vms_mc_run(fp['handle'], f.theta.ptr, x.ptr, e.ptr, valid, None, self._noise_seed,
@@ -127,7 +222,9 @@ class MCMC(object):
             c.synchronize()
         else:
             if log_u_dev is None:
-                log_u_dev = Tensor.from_numpy(np.log(self._rng.random(size=(n_steps, B))))  # mcmc.py:119, step by step
+                h = np.empty((n_steps, B))
+                self._host_uniform_logs(h, chain0, n_global)  # mcmc.py:119, step by step
+                log_u_dev = Tensor.from_numpy(h)
             if trace:
                 tr = dict(acc=Tensor((n_steps, B), np.uint8), fwd=Tensor((n_steps, B)), rev=Tensor((n_steps, B)),
                           e_new=Tensor((n_steps, B), np.float64), log_u=log_u_dev)
@@ -138,34 +235,55 @@ class MCMC(object):
         self._num_trials += B * n_steps
         if configs_dev is not None:
             return x, e
-        self._num_acc += float(int(fp['n_acc'].numpy()[0]) - before)
+        self._fold()
         self._last_trace = {k: t.numpy() for k, t in tr.items()}
         return x.numpy().reshape(configs.shape), e.numpy()
+
+    check_uncertain = False  # device-resident calls: read the uncertainty counter back after every call (tests)
+
+    def uncertain(self):
+        """Number of chain-steps of device-resident `run_fused` calls (since the last call of this method) whose decision
+        was within ~1e-13 of its threshold under the device logarithm; non-zero means those calls must be repeated on the
+        host stream (`device_rng = False`).  Host-array calls handle this themselves."""
+        fp = self._fused_plan()
+        if fp is None:
+            return 0
+        n = int(fp['n_unc'].numpy()[0])
+        fp['n_unc'].fill_zero()
+        return n
+
+    def _host_uniform_logs(self, out, chain0, n_global):
+        """out [n_steps, B] <- log of this object's columns [chain0, chain0 + B) of the global [n_steps, n_global] block of
+        uniforms (mcmc.py:119), drawn from self._rng in stream order."""
+        B = out.shape[1]
+        if chain0 == 0 and n_global == B:
+            self._rng.random(out=out)
+        else:
+            out[...] = self._rng.random(size=(out.shape[0], n_global))[:, chain0:chain0 + B]
+        np.log(out, out=out)
 
     def _uniform_buffers(self, chunk, B):
         """Two pinned host buffers + two device buffers + two events for the pipelined uniform stream of `run`."""
         if getattr(self, '_ub_key', None) != (chunk, B):
             lib = ctx().lib
-            host, dev, evs = [], [], []
+            host, dev, evs, raw = [], [], [], []
             for _ in range(2):
                 p = C.c_void_p()
                 lib.vms_malloc_host(C.byref(p), chunk * B * 8)
+                raw.append(p.value)
                 buf = (C.c_byte * (chunk * B * 8)).from_address(p.value)
                 host.append(np.frombuffer(buf, dtype=np.float64).reshape(chunk, B))
                 dev.append(Tensor((chunk, B), np.float64))
                 ev = C.c_void_p()
                 lib.vms_event_create(C.byref(ev))
                 evs.append(ev.value)
-            self._ub_key, self._ub = (chunk, B), (host, dev, evs)
+            self._ub_key, self._ub = (chunk, B), (host, dev, evs, raw)
         return self._ub
 
     def sync_counters(self):
         """Fold the device acceptance counter into `_num_acc` after device-resident `run_fused` calls."""
-        fp = self._fused_plan()
-        if fp is not None:
-            total = float(fp['n_acc'].numpy()[0])
-            self._num_acc += total - getattr(self, '_acc_folded', 0.0)
-            self._acc_folded = total
+        if self._fused_plan() is not None:
+            self._fold()
 
     def _energies(self, configs_host, configs_dev):
         """energy_func is the reference's host callable on NumPy arrays; a callable flagged `on_device` instead maps a
@@ -212,7 +330,12 @@ class MCMC(object):
         self._num_trials += B
         self._num_acc += float(n_acc.numpy()[0])
         self._last_acc = acc
-        return x2.numpy().reshape(configs.shape), e_out.numpy()
+        new_configs = x2.numpy().reshape(configs.shape).astype(configs.dtype, copy=False)
+        rej = acc.numpy() == 0
+        if configs.dtype != np.float32 and rej.any():
+            new_configs = np.array(new_configs)
+            new_configs[rej, ...] = configs[rej, ...]  # mcmc.py:126: rejected rows are the caller's own rows, unrounded
+        return new_configs, e_out.numpy()
 
     def run(self, configs, energies=None, n_steps=1):
         if self._fused_plan() is not None:

@@ -123,7 +123,17 @@ class VAE(Model):
     def fused(self, max_batch=4096):
         """The fused ELBO plan for this model (built on first use; rebuilt if max_batch grows)."""
         if self._fused is None or self._fused.max_batch < max_batch:
+            old = self._fused
             self._fused = FusedELBO(self, max_batch)
+            if old is not None:
+                # re-planning for a larger batch must not reset the optimiser: carry Adam's moments and step count over
+                # (the weights travel through the layers' own tensors, re-bound by the new plan)
+                c = ctx()
+                c.lib.vms_memcpy_d2d(self._fused.m.ptr, old.m.ptr, old.m.nbytes, c.stream)
+                c.lib.vms_memcpy_d2d(self._fused.v.ptr, old.v.ptr, old.v.nbytes, c.stream)
+                c.synchronize()
+                self._fused.t = old.t
+                old.close()
         return self._fused
 
     def train_step(self, x, eps=None):
@@ -149,6 +159,9 @@ class VAE(Model):
             w = np.minimum(batch_size, len(x) - np.arange(0, len(x), min(int(batch_size), len(x)))).astype(np.float64)
             hist['loss'].append(float(np.sum(scal[:, 0] * w) / w.sum()))
             hist['kl_div'].append(float(np.sum(scal[:, 2] * w) / w.sum()))
+            if f.tc_status():  # a tensor-core completion wait ran into its bound: this epoch's gradients are invalid
+                raise RuntimeError('VAE.fit: the tensor-core plan reported an MMA completion time-out; parameters of '
+                                   'this epoch are invalid')
         return hist
 
     def evaluate(self, x, y=None, batch_size=32, verbose=0):
@@ -187,7 +200,7 @@ class FusedELBO(object):
         reg = vae.regularizer
         if type(reg) is not losses.KLDivergenceEstimate or reg.sample_dist != 'dist_a':
             raise NotImplementedError('fused ELBO: only KLDivergenceEstimate (samples from dist_a) is built')
-        blocks, nbins, fh, lo, hi = self._check_prior(vae.prior)
+        blocks, nbins, fh, lo, hi = self._check_prior(vae.prior, self.dz)
         self.desc = _abi.ElboDesc(self.dx, self.dz, hidden, len(blocks), nbins, fh, lo, hi, float(reg.weight),
                                   self.max_batch)
         c = ctx()
@@ -214,12 +227,31 @@ class FusedELBO(object):
         c.lib.vms_elbo_plan_create(C.byref(self.desc), C.byref(h))
         self.handle = h.value
 
-    def __del__(self):
+    def _release_loop(self):
+        """Frees the pipelined loop's copy stream, events and pinned buffers (`train_loop`)."""
+        L, self._loop = getattr(self, '_loop', None), None
+        if L is None:
+            return
+        lib = _abi.load()
+        lib.vms_stream_synchronize(L['copy_stream'])
+        for e in L['h2d'] + L['free']:
+            lib.vms_event_destroy(e)
+        for p in L['stage'] + [L['host_ring']]:
+            lib.vms_free_host(p)
+        lib.vms_stream_destroy(L['copy_stream'])
+
+    def close(self):
+        """Releases the plan and the loop resources; the parameter / moment tensors stay valid (layers view theta)."""
         try:
+            self._release_loop()
             if getattr(self, 'handle', None):
                 _abi.load().vms_elbo_plan_destroy(self.handle)
+                self.handle = None
         except Exception:
             pass
+
+    def __del__(self):
+        self.close()
 
     @staticmethod
     def _check_mlp(m, what):
@@ -238,7 +270,20 @@ class FusedELBO(object):
         return [l0, l1], l0.kernel.shape[0], l1.units // 2, l0.units
 
     @staticmethod
-    def _check_prior(prior):
+    def _is_standard_normal(latent, dz):
+        """True only if `latent` (a DistributionLambda) really produces N(0, I_dz): it is called once on a dummy latent
+        batch, exactly as the reference calls the prior at models.py:306-308 / mcmc.py:101,107.  An IndependentNormal
+        layer (a DistributionLambda subclass) or a lambda returning a non-unit Normal must NOT be taken for N(0, I)."""
+        if type(latent) is not P.DistributionLambda:
+            return False
+        try:
+            d = latent(Tensor.zeros((2, dz)))
+        except Exception:
+            return False
+        return type(d) is P.StandardNormal and d.event_size == dz
+
+    @classmethod
+    def _check_prior(cls, prior, dz):
         if isinstance(prior, dists.FlowedDistribution):
             flow, latent = prior.flow, prior.latent_dist
             if not isinstance(flow, flows.RQSSplineRealNVP) or flow.batch_norm or flow.before_flow_transform is not None \
@@ -246,12 +291,16 @@ class FusedELBO(object):
                 raise NotImplementedError('fused ELBO: prior flow must be a plain RQSSplineRealNVP')
             if not flow.built:
                 raise RuntimeError('fused ELBO: call the model once on data before training so the flow is built')
+            if not cls._is_standard_normal(latent, dz):
+                raise NotImplementedError('fused ELBO: the flow\'s latent distribution must be a static N(0, I) '
+                                          '(DistributionLambda -> StandardNormal of the latent size)')
             blocks = [b.bijector_fn for b in flow.chain.bijectors[::-1]]  # chain list is reversed (flows.py:323)
             b0 = blocks[0]
             return blocks, b0.num_bins, b0.hidden_dim, float(b0.bin_min), float(b0.bin_max)
-        if isinstance(prior, P.DistributionLambda):
+        if cls._is_standard_normal(prior, dz):
             return [], 2, 1, -1.0, 1.0
-        raise NotImplementedError('fused ELBO: prior must be a static N(0, I) DistributionLambda or a FlowedDistribution')
+        raise NotImplementedError('fused ELBO: prior must be a static N(0, I) DistributionLambda (-> StandardNormal of the '
+                                  'latent size) or a FlowedDistribution over one')
 
     def set_mode(self, mode):
         """0 = auto (the single fused kernel when the shape fits), 1 = force the unfused per-layer float32-FFMA graph
@@ -321,7 +370,9 @@ class FusedELBO(object):
         if n_steps is not None:
             starts = [starts[i % len(starts)] for i in range(int(n_steps))]
         R = 8
-        if getattr(self, '_loop', None) is None or self._loop['bs'] < bs:
+        if getattr(self, '_loop', None) is not None and self._loop['bs'] < bs:
+            self._release_loop()
+        if getattr(self, '_loop', None) is None:
             mk = lambda: C.c_void_p()
             st = mk()
             lib.vms_stream_create(C.byref(st))

@@ -169,17 +169,30 @@ class PeerExchange(object):
         `fused.theta / m / v` in place.  All ranks must call it once per step."""
         self.step += 1
         fused.t += 1
+        if self.check_every and self.step % self.check_every == 0:
+            self.check()
         self.ctx.lib.vms_peer_allreduce_adam(self.world, self.rank, self.bases, self.n, self.step, 1.0 / self.world,
                                              fused.theta.ptr, fused.m.ptr, fused.v.ptr, fused.t, opt.learning_rate,
                                              opt.beta_1, opt.beta_2, opt.epsilon, None if grad_out is None else grad_out.ptr,
                                              self.ctx.stream)
 
+    check_every = 256  # steps between host-side failure checks inside allreduce_adam (0: never)
+
     def timed_out(self):
-        """True if any exchange on this rank gave up waiting for a peer (the kernel's 2 s bound): results are invalid."""
+        """True if an exchange of the job gave up waiting for a peer (the kernel's bound, VMS_PEER_TIMEOUT_MS): this rank
+        timed out itself (flag 32 + rank) or a peer poisoned the job (flag 48).  No parameter update was applied from that
+        step on."""
         import numpy as np
         self.ctx.synchronize()
         flags = self.buf.numpy().view(np.uint64)[self.n:self.n + 64]   # the flags follow the 2 n gradient floats
-        return bool(flags[32 + self.rank] != 0)
+        return bool(flags[32 + self.rank] != 0 or flags[48] != 0)
+
+    def check(self):
+        """Raises if the exchange failed (a peer stalled longer than the bound); called every `check_every` steps."""
+        if self.timed_out():
+            raise RuntimeError('PeerExchange: a rank stopped answering within VMS_PEER_TIMEOUT_MS; parameter updates were '
+                               'suspended on every replica from that step on (restart from the last checkpoint or use the '
+                               'NCCL exchange)')
 
     def close(self):
         self.ctx.synchronize()
