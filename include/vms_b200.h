@@ -384,6 +384,9 @@ typedef struct {
   int64_t chain0;
 } vms_pcg64_stream;
 int vms_mc_plan_has_device_rng(vms_mc_plan plan);
+/* Global index of chain 0 of the following vms_mc_run calls (default 0): the device noise stream is keyed by the GLOBAL chain
+ * index, so a job sharded over GPUs draws the noise of the single-GPU run (vms_mc_run_pcg64 takes it from rng->chain0). */
+vms_status vms_mc_plan_set_chain_offset(vms_mc_plan plan, int64_t chain0);
 vms_status vms_mc_run_pcg64(vms_mc_plan plan, const float* theta, float* x, double* E, int energies_valid, const float* noise,
                             unsigned long long seed, unsigned long long step0, const vms_pcg64_stream* rng,
                             const double* means, int64_t B, int n_steps, unsigned long long* n_acc,
@@ -408,6 +411,17 @@ vms_status vms_ipc_close_handle(void* device_ptr);
 vms_status vms_peer_allreduce_adam(int world, int rank, void* const* peer_bases, int64_t n_params, unsigned long long step,
                                    float grad_scale, float* theta, float* m, float* v, int64_t t, double lr, double beta1,
                                    double beta2, double eps, float* grad_out, vms_stream stream);
+
+/* ------------------------------------------------------------------------------- machine-peak probes (measurement aid)
+ * The denominators of this repo's compute-bound roofline fractions, measured on the device they are quoted for
+ * (BASELINE.md section 2 asks for them; `bench.py` runs them live and `scripts/measure_peaks.py` writes profiles/*.json):
+ *   vms_probe_ffma  FP32 FFMA issue peak: 2048 resident threads per SM, 8 independent FMA chains per thread out of
+ *                   registers, `iters` x 128 FMAs per thread; tflops = 2 x FMAs / best-of-`reps` event time.
+ *   vms_probe_mma   tcgen05.mma cta_group::1 issue peak, kind 0 = kind::f16 with bfloat16 inputs (K = 16 per MMA), kind 1 =
+ *                   kind::tf32 (K = 8): one CTA per SM issues n_mma back-to-back M x N x K MMAs on shared-memory-resident
+ *                   operands into two alternating TMEM accumulators; nothing is loaded or stored in the timed region.     */
+vms_status vms_probe_ffma(int iters, int reps, double* tflops, double* ms, vms_stream stream);
+vms_status vms_probe_mma(int kind, int M, int N, int n_mma, int reps, double* tflops, double* ms, vms_stream stream);
 
 #ifdef __cplusplus
 }

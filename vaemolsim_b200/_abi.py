@@ -145,8 +145,11 @@ _SIGS = {
     'vms_mc_run': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, C.c_ulonglong, C.c_ulonglong, c_vp, c_vp, c_i64, c_int, c_vp,
                           c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_mc_plan_has_device_rng': (c_int, [c_vp]),
+    'vms_mc_plan_set_chain_offset': (None, [c_vp, c_i64]),
     'vms_mc_run_pcg64': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, C.c_ulonglong, C.c_ulonglong, C.POINTER(Pcg64Stream),
                                 c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vms_probe_ffma': (None, [c_int, c_int, C.POINTER(c_f64), C.POINTER(c_f64), c_vp]),
+    'vms_probe_mma': (None, [c_int, c_int, c_int, c_int, c_int, C.POINTER(c_f64), C.POINTER(c_f64), c_vp]),
     'vms_elbo_forward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_elbo_forward_backward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
 }

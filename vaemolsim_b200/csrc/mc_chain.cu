@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(CT) mc_chain_kernel(const ChainParams p) {
       const uint2 key = make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32) ^ (unsigned)(st >> 32));
 #pragma unroll
       for (int q = 0; q < (nn + 3) / 4; ++q) {
-        const uint4 rnd = philox4x32(make_uint4((unsigned)cc, (unsigned)((unsigned long long)cc >> 32), (unsigned)st, (unsigned)q), key);
+        const unsigned long long gc = (unsigned long long)(p.chain0 + cc);  // GLOBAL chain index: sharding-invariant noise
+        const uint4 rnd = philox4x32(make_uint4((unsigned)gc, (unsigned)(gc >> 32), (unsigned)st, (unsigned)q), key);
         box_muller(rnd.x, rnd.y, nz[4 * q], nz[4 * q + 1]);
         box_muller(rnd.z, rnd.w, nz[4 * q + 2], nz[4 * q + 3]);
       }
@@ -323,7 +324,7 @@ vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x
                         const float* noise, unsigned long long seed, unsigned long long step0, const double* log_u,
                         const double* means, int64_t B, int n_steps, unsigned long long* n_acc, uint8_t* acc_trace,
                         float* fwd_trace, float* rev_trace, double* e_new_trace, cudaStream_t st,
-                        const vms_pcg64_stream* rng, unsigned long long* n_uncertain, double* log_u_trace) {
+                        const vms_pcg64_stream* rng, unsigned long long* n_uncertain, double* log_u_trace, long long chain0) {
   VMS_REQUIRE(dx == kMaxDx && dz == kMaxDz, VMS_ERR_UNSUPPORTED, "mc_chain: built for dx = 6, dz = 2");
   VMS_REQUIRE((log_u != nullptr) != (rng != nullptr), VMS_ERR_INVALID_ARG, "mc_chain: exactly one of log_u / rng");
   ChainParams p = {};
@@ -331,8 +332,8 @@ vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x
     p.use_pcg = 1;
     p.s0_hi = rng->state_hi; p.s0_lo = rng->state_lo; p.inc_hi = rng->inc_hi; p.inc_lo = rng->inc_lo;
     p.jm_hi = rng->stride_mul_hi; p.jm_lo = rng->stride_mul_lo; p.ja_hi = rng->stride_add_hi; p.ja_lo = rng->stride_add_lo;
-    p.chain0 = rng->chain0;
   }
+  p.chain0 = chain0;
   p.n_uncertain = n_uncertain; p.log_u_trace = log_u_trace;
   p.dx = dx; p.dz = dz; p.hidden = hidden;
   int o = 0;

@@ -27,6 +27,7 @@
 namespace vms {
 
 struct McParams {
+  long long chain0;  // global index of chain 0 (Philox key): results do not depend on how chains are sharded
   int dx, dz, hidden, n_mlp;
   int enc0W, enc0b, enc1W, enc1b, dec0W, dec0b, dec1W, dec1b;
   int64_t B;
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(FT, 1) mc_fused_kernel(const __grid_constant__
         const int quads = (nn + 3) / 4;
         for (int i = tid; i < FR * quads; i += FT) {
           const int r = i / quads, q = i - r * quads;
-          const unsigned long long chain = (unsigned long long)(row0 + r), st = p.step0 + (unsigned long long)step;
+          const unsigned long long chain = (unsigned long long)(p.chain0 + row0 + r), st = p.step0 + (unsigned long long)step;
           const uint4 rnd = philox4x32(make_uint4((unsigned)chain, (unsigned)(chain >> 32), (unsigned)st, (unsigned)q),
                                        make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32) ^ (unsigned)(st >> 32)));
           float n[4];
@@ -278,12 +279,13 @@ vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x
                         const float* noise, unsigned long long seed, unsigned long long step0, const double* log_u,
                         const double* means, int64_t B, int n_steps, unsigned long long* n_acc, uint8_t* acc_trace,
                         float* fwd_trace, float* rev_trace, double* e_new_trace, cudaStream_t st,
-                        const vms_pcg64_stream* rng, unsigned long long* n_uncertain, double* log_u_trace);
+                        const vms_pcg64_stream* rng, unsigned long long* n_uncertain, double* log_u_trace, long long chain0);
 }  // namespace vms
 
 using namespace vms;
 
 struct vms_mc_plan_s {
+  long long chain0 = 0;
   vms_mc_desc d;
   McParams p;
   size_t smem_bytes;
@@ -369,8 +371,9 @@ vms_status vms_mc_run(vms_mc_plan pl, const float* theta, float* x, double* E, i
   if (mc_chain_enabled(pl->d.dx, pl->d.dz))
     return mc_chain_run(pl->d.dx, pl->d.dz, pl->d.hidden, theta, x, E, energies_valid, noise, seed, step0, log_u, means, B,
                         n_steps, n_acc, acc_trace, fwd_trace, rev_trace, e_new_trace, as_stream(stream), nullptr, nullptr,
-                        nullptr);
+                        nullptr, pl->chain0);
   McParams p = pl->p;
+  p.chain0 = pl->chain0;
   p.B = B;
   p.n_tiles = (int)((B + FR - 1) / FR);
   p.n_steps = n_steps;
@@ -380,6 +383,12 @@ vms_status vms_mc_run(vms_mc_plan pl, const float* theta, float* x, double* E, i
   const int grid = p.n_tiles < pl->max_grid ? p.n_tiles : pl->max_grid;
   mc_fused_kernel<<<grid, FT, pl->smem_bytes, as_stream(stream)>>>(p);
   VMS_LAUNCH_CHECK("mc_fused_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_mc_plan_set_chain_offset(vms_mc_plan pl, int64_t chain0) {
+  VMS_REQUIRE(pl && chain0 >= 0, VMS_ERR_INVALID_ARG, "mc_plan_set_chain_offset: bad arguments");
+  pl->chain0 = chain0;
   return VMS_OK;
 }
 
@@ -398,7 +407,7 @@ vms_status vms_mc_run_pcg64(vms_mc_plan pl, const float* theta, float* x, double
   if (B == 0 || n_steps == 0) return VMS_OK;
   return mc_chain_run(pl->d.dx, pl->d.dz, pl->d.hidden, theta, x, E, energies_valid, noise, seed, step0, nullptr, means, B,
                       n_steps, n_acc, acc_trace, fwd_trace, rev_trace, e_new_trace, as_stream(stream), rng, n_uncertain,
-                      log_u_trace);
+                      log_u_trace, rng->chain0);
 }
 
 }  // extern "C"

@@ -167,6 +167,7 @@ class MCMC(object):
         P_ = lambda t: None if t is None else t.ptr
         tr = {}
         chain0, n_global = self.stream_layout if self.stream_layout is not None else (0, B)
+        c.lib.vms_mc_plan_set_chain_offset(fp['handle'], int(chain0))
         stream = self._pcg_stream(chain0, n_global) if (self.device_rng and fp['device_rng'] and log_u_dev is None) else None
         done = False
         if stream is not None:
