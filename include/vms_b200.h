@@ -310,16 +310,22 @@ int64_t vms_elbo_param_count(const vms_elbo_desc* desc);
  * the SM) -- the large-batch configuration; VMS_ERR_UNSUPPORTED when a block's shape does not fit (one transformed
  * dimension, <= 4 conditioner columns, 8 <= flow hidden <= 111, num_bins <= 32 and a multiple of 4, encoder / decoder
  * widths dx, dz <= 7, 2 dx, 2 dz <= 16, hidden <= 240).
- * mode 3 = EXPERIMENTAL whole-step tensor-core kernel (elbo_tcf.cu: all coupling blocks + encoder / decoder of a 64-row
- * tile in one persistent kernel; forward+backward / train_step only, B <= 64 x #SMs; correct but not yet faster than
- * the fused kernel -- never chosen automatically).
+ * mode 3 = whole-step tensor-core kernel (elbo_tcf.cu: all coupling blocks on tcgen05 + encoder / decoder of a 32-row tile
+ * in one persistent kernel; forward+backward / train_step only, B <= 32 x #SMs); AUTO mode takes it for those calls whenever
+ * the shape fits (VMS_TCF_AUTO=0 disables).  Its weight images (pre-split heads matrices, transposed MLP weights) are
+ * written by the Adam update of the previous vms_elbo_train_step; call vms_elbo_plan_invalidate after changing theta by any
+ * other means between two train steps (forward_backward always re-packs).
+ * mode 4 = force the single FFMA fused kernel (elbo_fused.cu) for every call it supports (float32 FFMA cross-check).
  * vms_elbo_plan_tc_status: synchronises the device and reports whether any tensor-core completion wait ran into its
  * bound since the last call (err = 1: results of that interval are invalid); clears the flag.                      */
 vms_status vms_elbo_plan_set_mode(vms_elbo_plan plan, int mode);
 int vms_elbo_plan_is_fused(vms_elbo_plan plan);
 vms_status vms_elbo_plan_tc_status(vms_elbo_plan plan, int* err);
-/* Which implementation a call with batch B takes: 0 = single fused kernel, 1 = per-layer FFMA plan, 2 = tensor-core plan. */
+/* Which implementation a forward + backward call with batch B takes: 0 = single FFMA fused kernel, 1 = per-layer FFMA
+ * plan, 2 = tensor-core plan (one kernel per coupling block), 3 = whole-step tensor-core kernel. */
 int vms_elbo_plan_path(vms_elbo_plan plan, int64_t B);
+/* The plan's packed weight images no longer describe theta (host-side assignment between two train steps). */
+vms_status vms_elbo_plan_invalidate(vms_elbo_plan plan);
 /* Batch from which mode 0 prefers the mode-2 plan over the single fused kernel (default: see DESIGN.md). */
 vms_status vms_elbo_plan_set_tc_auto_batch(vms_elbo_plan plan, int64_t batch);
 /* Measurement aid (bench.py's roofline leg): with max_launches > 0 the fused path brackets its main kernel with CUDA

@@ -24,14 +24,14 @@ def main():
         x = v.Tensor.from_numpy(rng.standard_normal((B, w['dx']), dtype=np.float32))
         e = v.Tensor.from_numpy(rng.standard_normal((B, w['dz']), dtype=np.float32))
         res = {}
-        for mode in (1, 3, 0):
+        for mode in (1, 3, 4):
             f.set_mode(mode)
             f.forward_backward(x, e)
             c.synchronize()
             res[mode] = (f.grad.numpy().copy(), f.scalars.numpy()[:3].copy(), f.path(B))
-        print('B = %d   paths: %s   tensor-core wait time-out: %s' % (B, [res[m][2] for m in (1, 3, 0)], f.tc_status()))
+        print('B = %d   paths: %s   tensor-core wait time-out: %s' % (B, [res[m][2] for m in (1, 3, 4)], f.tc_status()))
         ga, sa = res[3][:2]
-        for other in (1, 0):
+        for other in (1, 4):
             gb, sb = res[other][:2]
             print('  mode 3 vs mode %d: scalars %s vs %s | grad max-rel %.2e  norm-rel %.2e' % (
                 other, sa, sb, float(np.abs(ga - gb).max() / np.abs(gb).max()),
@@ -47,7 +47,7 @@ def main():
             o += n
         print('  per layer (norm-rel vs mode 1): ' + '  '.join(line))
         ev = bench.Events(c, 1)
-        for mode in (3, 0):
+        for mode in (3, 4):
             f.set_mode(mode)
             for _ in range(3):
                 f.forward_backward(x, e)
@@ -57,7 +57,38 @@ def main():
                 f.forward_backward(x, e)
             ev.record(1)
             c.synchronize()
-            print('  mode %d (%s): %.4f ms / step (fwd+bwd)' % (mode, f.path(B), ev.elapsed_ms(0, 1) / 20))
+            print('  mode %d (%s): %.4f ms / call  forward_backward (always re-packs the weight images)' % (
+                mode, f.path(B), ev.elapsed_ms(0, 1) / 20))
+        # training steps: the finish kernel writes the next step's weight images (no pre-pack launch in steady state);
+        # parameters after 5 steps against the FFMA fused kernel's
+        theta0 = f.theta.numpy().copy()
+        thetas = {}
+        for mode in (3, 4):
+            f.set_mode(mode)
+            c.lib.vms_memcpy_h2d(f.theta.ptr, theta0.ctypes.data, theta0.nbytes, c.stream)
+            c.lib.vms_memset(f.m.ptr, 0, f.m.nbytes, c.stream)
+            c.lib.vms_memset(f.v.ptr, 0, f.v.nbytes, c.stream)
+            c.synchronize()
+            f.invalidate()
+            f.t = 0
+            for _ in range(5):
+                f.train_step(x, e, model.optimizer)
+            c.synchronize()
+            thetas[mode] = f.theta.numpy().copy()
+            ev.record(0)
+            l0 = v._abi.launch_count()
+            for _ in range(50):
+                f.train_step(x, e, model.optimizer)
+            ev.record(1)
+            c.synchronize()
+            print('  mode %d (%s): %.4f ms / train_step, %.1f launches per step' % (
+                mode, f.path(B), ev.elapsed_ms(0, 1) / 50, (v._abi.launch_count() - l0) / 50.0))
+        d = thetas[3] - thetas[4]
+        print('  parameters after 5 train steps, mode 3 vs mode 4: max abs diff %.2e (update size %.2e)' % (
+            float(np.abs(d).max()), float(np.abs(thetas[4] - theta0).max())))
+        c.lib.vms_memcpy_h2d(f.theta.ptr, theta0.ctypes.data, theta0.nbytes, c.stream)
+        c.synchronize()
+        f.invalidate()
         del f, model
 
 

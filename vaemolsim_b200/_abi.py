@@ -128,6 +128,7 @@ _SIGS = {
     'vms_elbo_plan_is_fused': (c_int, [c_vp]),
     'vms_elbo_plan_tc_status': (None, [c_vp, C.POINTER(c_int)]),
     'vms_elbo_plan_path': (c_int, [c_vp, c_i64]),
+    'vms_elbo_plan_invalidate': (None, [c_vp]),
     'vms_elbo_plan_set_tc_auto_batch': (None, [c_vp, c_i64]),
     'vms_elbo_plan_set_timing': (None, [c_vp, c_int]),
     'vms_elbo_plan_kernel_ms': (None, [c_vp, C.POINTER(c_f64), C.POINTER(c_int)]),

@@ -176,6 +176,9 @@ class Dense(Layer):
             b = np.ascontiguousarray(bias, np.float32)
             c.lib.vms_memcpy_h2d(self.bias.ptr, b.ctypes.data, b.nbytes, c.stream)
         c.synchronize()
+        hook = getattr(self, '_on_assign', None)
+        if hook is not None:
+            hook()
 
     def rebind(self, kernel, bias):
         """Point the layer at externally owned storage (flat parameter buffer views)."""

@@ -416,7 +416,21 @@ vms_status run_graphed(vms_elbo_plan_s* pl, const std::array<uintptr_t, 10>& key
 // the single fused kernel runs the step unless a mode forces the per-layer plan or the batch is large enough for the
 // tensor-core flow kernels (auto)
 static bool use_fused(const vms_elbo_plan_s* pl, int64_t B) {
+  if (pl->fused && pl->mode == 4) return true;
   return pl->fused && pl->mode == 0 && !(pl->tc_ok && B >= pl->tc_auto_batch);
+}
+
+// forward + backward / training steps: the whole-step tensor-core kernel (elbo_tcf.cu) when forced (mode 3) or, in auto
+// mode, whenever the batch fits one wave of its 32-row tiles (VMS_TCF_AUTO=0 keeps auto mode on the FFMA fused kernel)
+static bool use_tcf(const vms_elbo_plan_s* pl, int64_t B) {
+  if (!tcf_available(pl, B)) return false;
+  if (pl->mode == 3) return true;
+  static int auto_on = -1;
+  if (auto_on < 0) {
+    const char* e = getenv("VMS_TCF_AUTO");
+    auto_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return pl->mode == 0 && auto_on && !(pl->tc_ok && B >= pl->tc_auto_batch);
 }
 
 extern "C" {
@@ -502,9 +516,10 @@ static vms_status check_call(vms_elbo_plan pl, const float* theta, const float* 
 
 vms_status vms_elbo_plan_set_mode(vms_elbo_plan pl, int mode) {
   VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "elbo_plan_set_mode: NULL plan");
-  VMS_REQUIRE(mode >= 0 && mode <= 3, VMS_ERR_INVALID_ARG,
-              "elbo_plan_set_mode: mode must be 0 (auto), 1 (unfused, FFMA), 2 (unfused, tensor-core flow blocks) or 3 "
-              "(experimental whole-step tensor-core kernel)");
+  VMS_REQUIRE(mode >= 0 && mode <= 4, VMS_ERR_INVALID_ARG,
+              "elbo_plan_set_mode: mode must be 0 (auto), 1 (unfused, FFMA), 2 (unfused, tensor-core flow blocks), 3 "
+              "(whole-step tensor-core kernel) or 4 (single FFMA fused kernel)");
+  VMS_REQUIRE(mode != 4 || pl->fused, VMS_ERR_UNSUPPORTED, "elbo_plan_set_mode: the FFMA fused kernel does not support this shape");
   VMS_REQUIRE(mode != 3 || pl->tcf, VMS_ERR_UNSUPPORTED, "elbo_plan_set_mode: mode 3 does not support this shape");
   VMS_REQUIRE(mode != 2 || pl->tc_ok, VMS_ERR_UNSUPPORTED, "elbo_plan_set_mode: the tensor-core flow kernels do not support this shape");
   pl->mode = mode;
@@ -523,7 +538,7 @@ vms_status vms_elbo_plan_tc_status(vms_elbo_plan pl, int* err) {
 
 int vms_elbo_plan_path(vms_elbo_plan pl, int64_t B) {
   if (!pl) return -1;
-  if (pl->mode == 3 && tcf_available(pl, B)) return 3;
+  if (use_tcf(pl, B)) return 3;
   if (use_fused(pl, B)) return 0;
   return plan_uses_tc(pl, B) ? 2 : 1;
 }
@@ -536,15 +551,23 @@ vms_status vms_elbo_plan_set_tc_auto_batch(vms_elbo_plan pl, int64_t batch) {
 
 vms_status vms_elbo_plan_set_timing(vms_elbo_plan pl, int max_launches) {
   VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "elbo_plan_set_timing: NULL plan");
-  return fused_set_timing(pl, max_launches);
+  vms_status s = fused_set_timing(pl, max_launches);
+  return s ? s : tcf_set_timing(pl, max_launches);
 }
 
 vms_status vms_elbo_plan_kernel_ms(vms_elbo_plan pl, double* total_ms, int* launches) {
   VMS_REQUIRE(pl && total_ms && launches, VMS_ERR_INVALID_ARG, "elbo_plan_kernel_ms: NULL argument");
-  return fused_kernel_ms(pl, total_ms, launches);
+  vms_status s = fused_kernel_ms(pl, total_ms, launches);  // (sets both outputs)
+  return s ? s : tcf_kernel_ms(pl, total_ms, launches);     // (adds to them)
 }
 
-int vms_elbo_plan_is_fused(vms_elbo_plan pl) { return pl && pl->fused && pl->mode == 0 ? 1 : 0; }
+vms_status vms_elbo_plan_invalidate(vms_elbo_plan pl) {
+  VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "elbo_plan_invalidate: NULL plan");
+  tcf_invalidate(pl);
+  return VMS_OK;
+}
+
+int vms_elbo_plan_is_fused(vms_elbo_plan pl) { return pl && pl->fused && (pl->mode == 0 || pl->mode == 4) ? 1 : 0; }
 
 vms_status vms_elbo_forward(vms_elbo_plan pl, const float* theta, const float* x, const float* eps, int64_t B, float* z,
                             float* logq, float* logpz, float* logpx, float* scalars, vms_stream stream) {
@@ -572,7 +595,7 @@ vms_status vms_elbo_forward_backward(vms_elbo_plan pl, const float* theta, const
   if (s) return s;
   VMS_REQUIRE(grad, VMS_ERR_INVALID_ARG, "elbo_forward_backward: NULL grad");
   cudaStream_t st = as_stream(stream);
-  if (pl->mode == 3 && tcf_available(pl, B)) return tcf_run(pl, theta, x, eps, B, grad, scalars, st);
+  if (use_tcf(pl, B)) return tcf_run(pl, theta, x, eps, B, grad, scalars, st);
   if (use_fused(pl, B))
     return fused_run(pl, theta, x, eps, B, true, nullptr, nullptr, nullptr, nullptr, grad, scalars, st);
   std::array<uintptr_t, 10> key = {(uintptr_t)(1 | (pl->mode << 8)), (uintptr_t)B, (uintptr_t)theta, (uintptr_t)x, (uintptr_t)eps, (uintptr_t)grad,
@@ -592,7 +615,7 @@ vms_status vms_elbo_train_step(vms_elbo_plan pl, float* theta, const float* x, c
   vms_status s = check_call(pl, theta, x, eps, B);
   if (s) return s;
   VMS_REQUIRE(grad && m && v && t >= 1, VMS_ERR_INVALID_ARG, "elbo_train_step: NULL grad / m / v or t < 1");
-  if (pl->mode == 3 && tcf_available(pl, B)) {
+  if (use_tcf(pl, B)) {
     FusedAdam ad;
     ad.theta = theta; ad.m = m; ad.v = v;
     ad.lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));

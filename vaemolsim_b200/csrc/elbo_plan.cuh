@@ -55,7 +55,7 @@ inline Offsets layout(const vms_elbo_desc& d, std::vector<FlowBlock>* blocks) {
 
 
 struct FusedCfg;  // elbo_fused.cu
-struct TcfCfg;    // elbo_tcf.cu (experimental whole-step tensor-core kernel, plan mode 3)
+struct TcfCfg;    // elbo_tcf.cu (whole-step tensor-core kernel, plan mode 3 / auto)
 
 }  // namespace vms
 
@@ -84,7 +84,7 @@ struct vms_elbo_plan_s {
   float* tc_part = nullptr;
   int* tc_err = nullptr;
   int64_t tc_auto_batch = 8192;
-  vms::TcfCfg* tcf = nullptr;  // experimental (mode 3 only)
+  vms::TcfCfg* tcf = nullptr;  // whole-step tensor-core kernel; NULL when the shape does not fit
 };
 
 namespace vms {
@@ -97,10 +97,13 @@ struct FusedAdam {  // optimiser step folded into the fused path's finishing ker
   float *theta, *m, *v;
   float lr_t, one_minus_b1, one_minus_b2, eps;
 };
-// elbo_tcf.cu (experimental, plan mode 3)
+// elbo_tcf.cu (plan mode 3 / auto for forward + backward up to one wave of 32-row tiles)
 vms_status tcf_create(vms_elbo_plan_s* pl);
 void tcf_destroy(vms_elbo_plan_s* pl);
 bool tcf_available(const vms_elbo_plan_s* pl, int64_t B);
+void tcf_invalidate(vms_elbo_plan_s* pl);  // the packed weight images no longer describe theta
+vms_status tcf_set_timing(vms_elbo_plan_s* pl, int max_launches);
+vms_status tcf_kernel_ms(vms_elbo_plan_s* pl, double* total_ms, int* launches);  // ADDS to both outputs
 vms_status tcf_run(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B, float* grad,
                    float* scalars, cudaStream_t st, const FusedAdam* adam = nullptr);
 vms_status fused_run(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B, bool backward,

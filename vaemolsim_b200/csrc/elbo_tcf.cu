@@ -1,20 +1,22 @@
-// elbo_tcf.cu -- EXPERIMENTAL (plan mode 3; never chosen automatically): the whole ELBO training step of the C2 family
-// as ONE persistent tensor-core kernel, one 64-row tile per CTA.  It is the plan of DESIGN.md 9a item 1: the
-// coupling-block pipeline of flow_tc.cu (3 x BF16 split, kind::f16 MMAs, one TMEM accumulator per product, K-major and
-// MN-major reads of the same tiles, octet spline routines on the raw parameters) for all blocks of the chain back to
-// back, with the encoder / decoder MLPs of mlp_stream.cu as in-tile phases, so that at the named batch (4096 rows = 64
-// tiles) the step is one launch whose heavy products run on the tensor core instead of the FFMA pipe of
-// elbo_fused.cu.  Status (round 1, one measurement, scripts/check_elbo_tcf.py at batch 4096): CORRECT -- loss scalars equal
-// to 7 digits, flat gradient 1.5e-7 (norm) against the FFMA plan, worst layer 1.6e-6 -- but SLOWER than the FFMA fused
-// kernel: 0.187 ms against 0.146 ms forward + backward.  One 64-row tile per CTA keeps only 64 of 148 SMs busy and the
-// RealNVP chain makes a tile's phases strictly sequential (block i needs block i + 1's output), so the tensor core
-// idles while the SIMT phases run.  What it needs to win: 32 valid rows per tile (128 CTAs, SIMT phases
-// halved, MMA cost unchanged), heads matrices staged with cp.async.bulk behind the previous block's epilogue, and two
-// tiles per CTA on alternating warp groups.
-// AFTER that measurement (no GPU time left in round 1) the row loops were parametrised by `rows` = valid rows per tile:
-// rows = 64 is the default and is meant to be the measured code path unchanged; VMS_TCF_ROWS=32 selects 32-row tiles
-// (zero-padded M = 64 products, d hW over 2 k-steps) and has NOT run on a device yet.  First thing to do next round:
-// `python scripts/check_elbo_tcf.py 4096` with and without VMS_TCF_ROWS=32.
+// elbo_tcf.cu -- the whole ELBO training step of the C2 family as ONE persistent tensor-core kernel (plan mode 3; chosen
+// automatically for forward + backward / train steps up to one wave of 32-row tiles).  It is the coupling-block pipeline
+// of flow_tc.cu (3 x BF16 split, kind::f16 MMAs, one TMEM accumulator per product, K-major and MN-major reads of the same
+// tiles, octet spline routines on the raw parameters) for all blocks of the chain back to back, with the encoder / decoder
+// MLPs as in-tile FFMA phases, so that at the named batch (4096 rows = 128 tiles of 32 rows) the step is one launch whose
+// heavy products run on the tensor core instead of the FFMA pipe of elbo_fused.cu.
+//
+// History.  Round 1 (one 64-row tile per CTA, every phase serial, weights staged by generic copies): correct, 0.187 ms
+// against 0.146 ms of the FFMA kernel.  Round 2, ncu source view of the 32-row variant (profiles/r02_tcf_v1_hotspots.txt):
+// 17 % of the samples in the scattered 4-byte stores of the d[hW; hb] partial and the barrier behind them, 11 % waiting
+// for MMA completion, 20 % in MLP phases with run-time widths and per-phase weight staging from global memory, 5 % in the
+// generic copy of the heads matrix.  This version: 32 valid rows per tile (the M = 64 products read whatever follows in
+// shared memory for rows 32-63; every product is row-wise independent there and the d hW contraction covers rows 0-31
+// only), the pre-split heads matrix of the NEXT block arrives by cp.async.bulk behind the current block's SIMT phases,
+// encoder / decoder / conditioner weights are resident images brought in once by bulk copies, MLP phases are compiled
+// for the widths of the shape, d[hW; hb] leaves the CTA as 16-byte stores into a padded partial layout, and the finish
+// kernel that sums the partials and applies Adam also writes the NEXT step's pre-split / transposed weight images, so a
+// training loop launches two kernels per step (the pre-pack kernel runs only when the parameters were changed behind the
+// plan's back: first step, host-side weight assignment, data-parallel exchange).
 //
 // Reference lines replaced: the same as elbo.cu (models.py:289-322 VAE.call; mappings.py:107-155 FCDeepNN;
 // flows.py:184-207, :281-355 RQSSplineRealNVP; dists.py:414-439; losses.py:58, :253) plus TF autodiff through them.
@@ -63,9 +65,14 @@ struct TParams {
   TBlk blk[kMaxNb];
   const float *theta, *x, *eps;
   const unsigned short* wpk;  // pre-split heads matrices [nb][3 parts][Hp / 8][RP][8]
+  const float* fpk;           // float images: encoder MLP | decoder MLP | conditioner first layers (see tcf_maps)
+  int f_enc, f_dec, f_d1, n_enc, n_dec, n_d1;  // offsets / sizes in floats (sizes are multiples of 4)
   float *gpart, *spart;
+  int P2;               // floats per CTA partial: theta layout + per block a padded [fh + 1][RP] matrix for d [hW; hb]
+  int poff_h[kMaxNb];   // offset of that matrix in the partial
   int* err;
-  int o_hid, o_graw, o_w, o_raw, o_u, o_gu, o_x, o_eps, o_pe, o_pd, o_gpd, o_gpe, o_gz, o_lp, o_gin, o_w1, o_b1;
+  int o_hid, o_graw, o_w, o_raw, o_u, o_gu, o_x, o_eps, o_pe, o_pd, o_gpd, o_gpe, o_gz, o_lp, o_gin, o_w1, o_b1, o_mlpe,
+      o_mlpd;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -143,6 +150,16 @@ __device__ __forceinline__ void tc_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 }
 
+// 1-D bulk asynchronous copies global -> shared (the TMA path without a tensor map), completion on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void* gmem_src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 __device__ __forceinline__ unsigned idesc_bf16(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)a_mn << 15) | ((unsigned)b_mn << 16) |
          ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
@@ -175,79 +192,74 @@ __device__ __forceinline__ void issue_product(unsigned acc, unsigned a0, unsigne
   for (int ks = 0; ks < n_k; ++ks, ka += sa, kb += sb) mma_bf16(acc, da1 + ka, db1 + kb, idesc, 1u);
 }
 
-// ------------------------------------------------------------------------------------------------ prepack
-// heads matrix of every block with its bias as row H, split into three bfloat16 parts, in the shared-memory layout of
-// the main kernel ([part][j / 8][RP][8]); one launch per step (theta changes every step)
-__global__ void tcf_prepack_kernel(const TParams p, unsigned short* __restrict__ wpk) {
-  const int blk = blockIdx.y;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const int Hp = p.Hp, RP = p.RP, R = p.R, H = p.fh;
-  if (e >= Hp * RP) return;
-  const int j = e / RP, c = e - j * RP;
-  float w = 0.f;
-  if (c < R) {
-    if (j < H) w = p.theta[p.blk[blk].off_hW + (size_t)j * R + c];
-    else if (j == H) w = p.theta[p.blk[blk].off_hb + c];
+// ------------------------------------------------------------------------------------------------ packed weight images
+// The kernel never reads theta directly: every weight arrives in shared memory by a bulk copy of an image laid out for
+// its consumer.  pack_map[i] (built on the host, tcf_create) says where parameter i lives:
+//   bit 31 clear: float image fpk[m]                 (MLP images: W0^T rows with the bias as column Din, W1 rows, b1;
+//                                                      conditioner first layers [nb][4][Hp] and biases [nb][Hp])
+//   bit 31 set:   heads image, part 1 at wpk[m & 0x7fffffff], parts 2 / 3 one / two `part` strides further
+//                 ([blk][3 parts][j / 8][RP][8] bfloat16, the bias hb as row j = fh: the shared-memory layout of the MMA)
+// Padding entries of the images are zeroed once at plan creation.  tcf_prepack_kernel rebuilds the images from theta; the
+// finish kernel updates them in the same thread that applies Adam, so consecutive training steps never run the pre-pack.
+__device__ __forceinline__ void pack_store(float w, unsigned m, float* __restrict__ fpk, unsigned short* __restrict__ wpk,
+                                           size_t part) {
+  if (m & 0x80000000u) {
+    unsigned h1, h2, h3;
+    split3(w, h1, h2, h3);
+    unsigned short* dst = wpk + (m & 0x7fffffffu);
+    dst[0] = (unsigned short)(h1 >> 16);
+    dst[part] = (unsigned short)(h2 >> 16);
+    dst[2 * part] = (unsigned short)(h3 >> 16);
+  } else {
+    fpk[m] = w;
   }
-  unsigned h1, h2, h3;
-  split3(w, h1, h2, h3);
-  const size_t part = (size_t)(Hp / 8) * RP * 8;
-  unsigned short* dst = wpk + (size_t)blk * 3 * part + (size_t)(j >> 3) * RP * 8 + (size_t)c * 8 + (j & 7);
-  dst[0] = (unsigned short)(h1 >> 16);
-  dst[part] = (unsigned short)(h2 >> 16);
-  dst[2 * part] = (unsigned short)(h3 >> 16);
+}
+
+__global__ void __launch_bounds__(256) tcf_prepack_kernel(const float* __restrict__ theta, const unsigned* __restrict__ pack_map,
+                                                          int P, float* __restrict__ fpk, unsigned short* __restrict__ wpk,
+                                                          size_t part) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) pack_store(__ldg(theta + i), __ldg(pack_map + i), fpk, wpk, part);
 }
 
 // ------------------------------------------------------------------------------------------------ MLP phases
-// Weights of one two-layer MLP staged into `wm`: w0t [H][DI] = W0^T with b0 in column Din, w1 [H][DO] zero padded, b1 [DO]
-__device__ void stage_mlp(const float* __restrict__ theta, int oW0, int ob0, int oW1, int ob1, int Din, int H, int Dout, int DI,
-                          int DO, float* wm) {
-  float* w0t = wm;
-  float* w1 = wm + H * DI;
-  float* b1 = w1 + H * DO;
-  for (int e = threadIdx.x; e < H * DI; e += FT) {
-    const int j = e / DI, i = e - j * DI;
-    w0t[e] = i < Din ? __ldg(theta + oW0 + (size_t)i * H + j) : (i == Din ? __ldg(theta + ob0 + j) : 0.f);
-  }
-  for (int e = threadIdx.x; e < H * DO; e += FT) {
-    const int j = e / DO, n = e - j * DO;
-    w1[e] = n < Dout ? __ldg(theta + oW1 + (size_t)j * Dout + n) : 0.f;
-  }
-  for (int n = threadIdx.x; n < DO; n += FT) b1[n] = n < Dout ? __ldg(theta + ob1 + n) : 0.f;
-  __syncthreads();
-}
+// One two-layer MLP image in shared memory: w0t [H][DI] = W0^T with b0 in column Din (zero padded), w1 [H][DO] (zero
+// padded), b1 [DO].  DI, DO are compile-time (multiples of 4): rows are read as 16-byte broadcasts.
 
-// row r of `in` ([FM][ldi], Din valid columns) extended by the bias input 1 and zero padded to 8
-__device__ __forceinline__ void load_in8(const float* in, int ldi, int Din, int r, float (&x)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = i < Din ? in[r * ldi + i] : (i == Din ? 1.f : 0.f);
-}
-
-// out [FM][DO] = relu(in W0 + b0) W1 + b1;  scratch: [8][FM][DO] floats
-__device__ void mlp_forward(const float* wm, int H, int DI, int DO, const float* in, int ldi, int Din, float* scratch,
-                            float* out, int rows) {
+// out [rows][DO] = relu(in W0 + b0) W1 + b1;  scratch: [FT / rows][rows][DO] floats
+template <int DI, int DO>
+__device__ void mlp_forward(const float* wm, int H, const float* in, int ldi, int Din, float* scratch, float* out, int rows) {
   const float* w0t = wm;
   const float* w1 = wm + H * DI;
   const float* b1 = w1 + H * DO;
-  const int ng = FT / rows;  // thread = (row, one of ng groups of hidden units)
+  const int ng = FT / rows;  // thread = (row, one of ng groups of hidden units); a warp shares its group: broadcasts
   const int r = threadIdx.x & (rows - 1), g = threadIdx.x / rows;
-  float x[8], acc[16];
-  load_in8(in, ldi, Din, r, x);
+  float x[DI], acc[DO];
 #pragma unroll
-  for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+  for (int i = 0; i < DI; ++i) x[i] = i < Din ? in[r * ldi + i] : (i == Din ? 1.f : 0.f);
+#pragma unroll
+  for (int n = 0; n < DO; ++n) acc[n] = 0.f;
+#pragma unroll 2
   for (int j = g; j < H; j += ng) {
     float pre = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < DI) pre = fmaf(x[i], w0t[j * DI + i], pre);
+    for (int q = 0; q < DI / 4; ++q) {
+      const float4 w = *reinterpret_cast<const float4*>(w0t + j * DI + 4 * q);
+      pre = fmaf(x[4 * q], w.x, pre); pre = fmaf(x[4 * q + 1], w.y, pre);
+      pre = fmaf(x[4 * q + 2], w.z, pre); pre = fmaf(x[4 * q + 3], w.w, pre);
+    }
     const float h = fmaxf(pre, 0.f);
 #pragma unroll
-    for (int n = 0; n < 16; ++n)
-      if (n < DO) acc[n] = fmaf(h, w1[j * DO + n], acc[n]);
+    for (int q = 0; q < DO / 4; ++q) {
+      const float4 w = *reinterpret_cast<const float4*>(w1 + j * DO + 4 * q);
+      acc[4 * q] = fmaf(h, w.x, acc[4 * q]); acc[4 * q + 1] = fmaf(h, w.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(h, w.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(h, w.w, acc[4 * q + 3]);
+    }
   }
 #pragma unroll
-  for (int n = 0; n < 16; ++n)
-    if (n < DO) scratch[(g * rows + r) * DO + n] = acc[n];
+  for (int q = 0; q < DO / 4; ++q)
+    *reinterpret_cast<float4*>(scratch + (g * rows + r) * DO + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2],
+                                                                                   acc[4 * q + 3]);
   __syncthreads();
   for (int e = threadIdx.x; e < rows * DO; e += FT) {
     const int r2 = e / DO, n = e - r2 * DO;
@@ -258,57 +270,61 @@ __device__ void mlp_forward(const float* wm, int H, int DI, int DO, const float*
   __syncthreads();
 }
 
-// reverse mode: gout [FM][DO] (zero rows beyond the tile) -> this CTA's weight-gradient partial (global, Keras layout),
-// optional input gradient gin [FM][4] (Din <= 4).  scratch: max(H * 24, 8 * FM * 4) floats
-__device__ void mlp_backward(const float* wm, int H, int DI, int DO, const float* in, int ldi, int Din, int Dout,
-                             const float* gout, float* __restrict__ part, int oW0, int ob0, int oW1, int ob1, float* scratch,
-                             float* gin, int rows) {
+// reverse mode: gout [rows][DO] (zero rows beyond the batch) -> this CTA's weight-gradient partial (global, Keras layout),
+// optional input gradient gin [rows][4] (Din <= 4).  scratch: max(H * 24, (FT / rows) * rows * 4) floats
+template <int DI, int DO>
+__device__ void mlp_backward(const float* wm, int H, const float* in, int ldi, int Din, int Dout, const float* gout,
+                             float* __restrict__ part, int oW0, int ob0, int oW1, int ob1, float* scratch, float* gin,
+                             int rows) {
   const float* w0t = wm;
   const float* w1 = wm + H * DI;
   const int tid = threadIdx.x;
-  {  // weight gradients: thread = (hidden unit j, half of the rows)
+  {  // weight gradients: thread = (hidden unit j, half of the rows); inputs and output gradients are broadcasts
     const int j = tid & 255, half = tid >> 8;
-    float w0[8], w1r[16], dW0[8], dW1[16];
+    float w0[DI], w1r[DO], dW0[DI], dW1[DO];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { w0[i] = (j < H && i < DI) ? w0t[j * DI + i] : 0.f; dW0[i] = 0.f; }
+    for (int i = 0; i < DI; ++i) { w0[i] = j < H ? w0t[j * DI + i] : 0.f; dW0[i] = 0.f; }
 #pragma unroll
-    for (int n = 0; n < 16; ++n) { w1r[n] = (j < H && n < DO) ? w1[j * DO + n] : 0.f; dW1[n] = 0.f; }
+    for (int n = 0; n < DO; ++n) { w1r[n] = j < H ? w1[j * DO + n] : 0.f; dW1[n] = 0.f; }
     if (j < H) {
       for (int r = half * (rows / 2); r < (half + 1) * (rows / 2); ++r) {
-        float x[8];
-        load_in8(in, ldi, Din, r, x);
+        float x[DI], g[DO];
+#pragma unroll
+        for (int i = 0; i < DI; ++i) x[i] = i < Din ? in[r * ldi + i] : (i == Din ? 1.f : 0.f);
+#pragma unroll
+        for (int q = 0; q < DO / 4; ++q) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gout + r * DO + 4 * q);
+          g[4 * q] = g4.x; g[4 * q + 1] = g4.y; g[4 * q + 2] = g4.z; g[4 * q + 3] = g4.w;
+        }
         float pre = 0.f, t = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pre = fmaf(x[i], w0[i], pre);
-        float g[16];
+        for (int i = 0; i < DI; ++i) pre = fmaf(x[i], w0[i], pre);
 #pragma unroll
-        for (int n = 0; n < 16; ++n) g[n] = n < DO ? gout[r * DO + n] : 0.f;
-#pragma unroll
-        for (int n = 0; n < 16; ++n) t = fmaf(g[n], w1r[n], t);
+        for (int n = 0; n < DO; ++n) t = fmaf(g[n], w1r[n], t);
         const float h = fmaxf(pre, 0.f);
         const float gh = pre > 0.f ? t : 0.f;
 #pragma unroll
-        for (int n = 0; n < 16; ++n) dW1[n] = fmaf(h, g[n], dW1[n]);
+        for (int n = 0; n < DO; ++n) dW1[n] = fmaf(h, g[n], dW1[n]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dW0[i] = fmaf(x[i], gh, dW0[i]);
+        for (int i = 0; i < DI; ++i) dW0[i] = fmaf(x[i], gh, dW0[i]);
       }
       if (half == 1) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) scratch[j * 24 + i] = dW0[i];
+        for (int i = 0; i < DI; ++i) scratch[j * 24 + i] = dW0[i];
 #pragma unroll
-        for (int n = 0; n < 16; ++n) scratch[j * 24 + 8 + n] = dW1[n];
+        for (int n = 0; n < DO; ++n) scratch[j * 24 + 8 + n] = dW1[n];
       }
     }
     __syncthreads();
     if (j < H && half == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < DI; ++i) {
         const float v = dW0[i] + scratch[j * 24 + i];
         if (i < Din) part[oW0 + (size_t)i * H + j] = v;
         else if (i == Din) part[ob0 + j] = v;
       }
 #pragma unroll
-      for (int n = 0; n < 16; ++n)
+      for (int n = 0; n < DO; ++n)
         if (n < Dout) part[oW1 + (size_t)j * Dout + n] = dW1[n] + scratch[j * 24 + 8 + n];
     }
     if (tid >= FT - 16 && tid - (FT - 16) < Dout) {  // output bias: column sums of gout
@@ -319,28 +335,35 @@ __device__ void mlp_backward(const float* wm, int H, int DI, int DO, const float
     }
     __syncthreads();
   }
-  if (gin) {  // input gradient: thread = (row, 1/8 of the hidden units)
+  if (gin) {  // input gradient: thread = (row, one of FT / rows groups of hidden units)
     const int ng = FT / rows;
     const int r = tid & (rows - 1), g8 = tid / rows;
-    float x[8], g[16], gi[4] = {0.f, 0.f, 0.f, 0.f};
-    load_in8(in, ldi, Din, r, x);
+    float x[DI], g[DO], gi[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int n = 0; n < 16; ++n) g[n] = n < DO ? gout[r * DO + n] : 0.f;
+    for (int i = 0; i < DI; ++i) x[i] = i < Din ? in[r * ldi + i] : (i == Din ? 1.f : 0.f);
+#pragma unroll
+    for (int n = 0; n < DO; ++n) g[n] = gout[r * DO + n];
     for (int j = g8; j < H; j += ng) {
       float pre = 0.f, t = 0.f;
+      float w0[DI];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < DI) pre = fmaf(x[i], w0t[j * DI + i], pre);
+      for (int q = 0; q < DI / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(w0t + j * DI + 4 * q);
+        w0[4 * q] = w.x; w0[4 * q + 1] = w.y; w0[4 * q + 2] = w.z; w0[4 * q + 3] = w.w;
+      }
 #pragma unroll
-      for (int n = 0; n < 16; ++n)
-        if (n < DO) t = fmaf(g[n], w1[j * DO + n], t);
+      for (int i = 0; i < DI; ++i) pre = fmaf(x[i], w0[i], pre);
+#pragma unroll
+      for (int q = 0; q < DO / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(w1 + j * DO + 4 * q);
+        t = fmaf(g[4 * q], w.x, t); t = fmaf(g[4 * q + 1], w.y, t); t = fmaf(g[4 * q + 2], w.z, t); t = fmaf(g[4 * q + 3], w.w, t);
+      }
       const float gh = pre > 0.f ? t : 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (i < Din) gi[i] = fmaf(gh, w0t[j * DI + i], gi[i]);
+        if (i < Din && i < DI) gi[i] = fmaf(gh, w0[i], gi[i]);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) scratch[(g8 * rows + r) * 4 + i] = gi[i];
+    *reinterpret_cast<float4*>(scratch + (g8 * rows + r) * 4) = make_float4(gi[0], gi[1], gi[2], gi[3]);
     __syncthreads();
     for (int e = tid; e < rows * 4; e += FT) {
       float s = 0.f;
@@ -352,10 +375,12 @@ __device__ void mlp_backward(const float* wm, int H, int DI, int DO, const float
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int RP>
+template <int RP, bool EXACT>
 __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TParams p) {
+  // MLP image widths: the C2 shape (dx = 5..7, dz = 1..2) exactly, else padded to the maxima (zero columns)
+  constexpr int DIE = 8, DOE = EXACT ? 4 : 16, DID = EXACT ? 4 : 8, DOD = EXACT ? 12 : 16;
   extern __shared__ __align__(128) unsigned char smb[];
-  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ __align__(8) unsigned long long mbars[3];  // [0] MMA completion, [1] heads-matrix copies, [2] resident images
   __shared__ unsigned tmem_base_s;
   __shared__ float red[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -370,7 +395,8 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
   unsigned char* graw = smb + p.o_graw;
   unsigned char* wsm = smb + p.o_w;
   float* s_raw = reinterpret_cast<float*>(smb + p.o_raw);   // raw parameters / d pre-activation / MLP scratch
-  float* s_mlp = reinterpret_cast<float*>(smb + p.o_graw);  // MLP weights borrow the g_raw tiles outside the flow's reverse mode
+  const float* s_mlpe = reinterpret_cast<const float*>(smb + p.o_mlpe);  // encoder image (resident)
+  const float* s_mlpd = reinterpret_cast<const float*>(smb + p.o_mlpd);  // decoder image (resident)
   float* s_u = reinterpret_cast<float*>(smb + p.o_u);       // [nb + 1][FM][4] chain states, u[nb] = z
   float* s_gu = reinterpret_cast<float*>(smb + p.o_gu);     // [FM][4] gradient wrt the current chain state
   float* s_x = reinterpret_cast<float*>(smb + p.o_x);       // [FM][8]
@@ -382,9 +408,8 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
   float* s_gz = reinterpret_cast<float*>(smb + p.o_gz);     // [FM][4]
   float* s_lp = reinterpret_cast<float*>(smb + p.o_lp);     // [3][FM]: log q, log p(z), log p(x | z)
   float* s_gin = reinterpret_cast<float*>(smb + p.o_gin);   // [FM]
-  float* s_w1 = reinterpret_cast<float*>(smb + p.o_w1);     // [nb][4][Hp]
-  float* s_b1 = reinterpret_cast<float*>(smb + p.o_b1);     // [nb][Hp]
-  const int DOE = p.DOE, DOD = p.DOD;
+  const float* s_w1 = reinterpret_cast<const float*>(smb + p.o_w1);  // [nb][4][Hp]   (resident image, with s_b1 behind it)
+  const float* s_b1 = reinterpret_cast<const float*>(smb + p.o_b1);  // [nb][Hp]
   const int rows = p.rows;  // valid rows of a tile (<= FM)
 
   if (warp == 0) {
@@ -393,46 +418,46 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
+  const unsigned bar = smem_u32(&mbars[0]), wbar = smem_u32(&mbars[1]), sbar = smem_u32(&mbars[2]);
+  const unsigned hid_a = smem_u32(hid), graw_a = smem_u32(graw), w_a = smem_u32(wsm);
+  const size_t wpk_blk = 3 * (size_t)nchH * RP * 8;  // bfloat16 elements of one block's pre-split heads image
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar)) : "memory");
+    for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbars[i])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  // conditioner first layers of every block
-  for (int e = tid; e < nb * 4 * Hp; e += FT) {
-    const int b = e / (4 * Hp), c = (e / Hp) & 3, j = e % Hp;
-    s_w1[e] = (c < p.blk[b].cin && j < H) ? __ldg(p.theta + p.blk[b].off_d1W + (size_t)c * H + j) : 0.f;
-  }
-  for (int e = tid; e < nb * Hp; e += FT) {
-    const int b = e / Hp, j = e - b * Hp;
-    s_b1[e] = j < H ? __ldg(p.theta + p.blk[b].off_d1b + j) : 0.f;
-  }
-  if (rows < FM)  // rows beyond the tile must be finite (and zero) operands of the M = 64 products
-    for (unsigned e = tid; e < 3 * hid_sz / 4; e += FT) reinterpret_cast<unsigned*>(hid)[e] = 0u;
+  // every element of the A-type tiles the tensor core can read must be finite: rows beyond the tile, the padding column
+  // of g_raw (a NaN there would survive the multiplication by the zero padding row of hW)
+  for (unsigned e = tid; e < 3 * hid_sz / 4; e += FT) reinterpret_cast<unsigned*>(hid)[e] = 0u;
+  for (unsigned e = tid; e < 3 * graw_sz / 4; e += FT) reinterpret_cast<unsigned*>(graw)[e] = 0u;
   tc_sync();
+  // ---- bulk copies: the resident images (MLPs, conditioner first layers) and the heads matrix of the first block
+  auto load_heads = [&](int i) {  // thread 0 only; the previous reader of the buffer (an MMA) has been waited for
+    mbar_expect_tx(wbar, 3u * w_sz);
+    for (int q = 0; q < 3; ++q)
+      bulk_g2s(w_a + q * w_sz, p.wpk + (size_t)i * wpk_blk + (size_t)q * (wpk_blk / 3), w_sz, wbar);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(sbar, 4u * (unsigned)(p.n_enc + p.n_dec + p.n_d1));
+    bulk_g2s(smem_u32(smb + p.o_mlpe), p.fpk + p.f_enc, 4u * (unsigned)p.n_enc, sbar);
+    bulk_g2s(smem_u32(smb + p.o_mlpd), p.fpk + p.f_dec, 4u * (unsigned)p.n_dec, sbar);
+    bulk_g2s(smem_u32(smb + p.o_w1), p.fpk + p.f_d1, 4u * (unsigned)p.n_d1, sbar);
+    load_heads(nb - 1);
+  }
   const unsigned tm = tmem_base_s;
   const unsigned tD1 = tm, tD2 = tm + RP, tD3 = tm + RP + 128;
   const unsigned id1 = idesc_bf16(FM, RP, 0, 0);
   const unsigned id2 = idesc_bf16(FM, Hp, 0, 1);
   const unsigned id3 = idesc_bf16(128, RP, 1, 1);
-  const unsigned bar = smem_u32(&mbar);
-  const unsigned hid_a = smem_u32(hid), graw_a = smem_u32(graw), w_a = smem_u32(wsm);
-  unsigned phase = 0;
+  unsigned phase = 0, wphase = 0;
   bool failed = false;
 
   const int64_t tile = blockIdx.x;  // one tile per CTA
   const int64_t row0 = tile * rows;
   const int nr = (int)min((int64_t)rows, p.B - row0);
-  float* part = p.gpart + (size_t)blockIdx.x * p.P;
+  float* part = p.gpart + (size_t)blockIdx.x * p.P2;
   const float invB = 1.0f / (float)p.B;
   const float g_logpx = -invB, g_logq = p.klw * invB, g_logpz = -p.klw * invB;
 
-  // ---- heads matrix of block i -> shared memory (generic copy of the pre-split tiles, then visible to the tensor core)
-  auto stage_heads = [&](int i) {
-    const uint4* src = reinterpret_cast<const uint4*>(p.wpk + (size_t)i * 3 * (size_t)nchH * RP * 8);
-    uint4* dst = reinterpret_cast<uint4*>(wsm);
-    const int n16 = (int)(3u * w_sz / 16u);
-    for (int e = tid; e < n16; e += FT) dst[e] = __ldg(src + e);
-  };
   // ---- hid of block i from the conditioner columns of chain state `uin` ([FM][4]); ones column at j = H
   auto build_hid = [&](int i, const float* uin) {
     const TBlk& fb = p.blk[i];
@@ -467,8 +492,14 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     }
   };
   // ---- raw = [hid, 1] [hW; hb] on the tensor core, then TMEM -> s_raw
-  auto raw_product = [&]() {
+  // wait_w: the heads matrix of this block arrives by a bulk copy that has to be waited for;  prefetch >= 0: block whose
+  // heads matrix is fetched into the (single) buffer as soon as this product has consumed the current one
+  auto raw_product = [&](bool wait_w, int prefetch) {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if (wait_w) {
+      if (!mbar_wait_bounded(wbar, wphase)) failed = true;
+      wphase ^= 1;
+    }
     tc_sync();
     if (tid == 0) {
       issue_product(tD1, hid_a, hid_sz, 2u * CSB, CSB, 128, w_a, w_sz, 2u * w_cs, w_cs, 128, Hp / 16, id1);
@@ -477,6 +508,7 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     if (!mbar_wait_bounded(bar, phase)) failed = true;
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (tid == 0 && prefetch >= 0) load_heads(prefetch);
     const int q = warp & 3, row = 16 * q + lane;
     if (16 * q < rows)
       for (int c0 = 16 * (warp >> 2); c0 < RP; c0 += 64) {
@@ -501,8 +533,9 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     s_eps[e] = (r < nr && c < dz) ? __ldg(p.eps + (row0 + r) * dz + c) : 0.f;
   }
   // ================================================================ E1: encoder
-  stage_mlp(p.theta, p.enc0W, p.enc0b, p.enc1W, p.enc1b, dx, p.H, 2 * dz, p.DIE, DOE, s_mlp);  // (ends with a barrier)
-  mlp_forward(s_mlp, p.H, p.DIE, DOE, s_x, 8, dx, s_raw, s_pe, rows);
+  if (!mbar_wait_bounded(sbar, 0)) failed = true;  // resident images have landed
+  __syncthreads();
+  mlp_forward<DIE, DOE>(s_mlpe, p.H, s_x, 8, dx, s_raw, s_pe, rows);
   if (tid < rows) {
     float* z = s_u + (nb * FM + tid) * 4;
     float s = 0.f;
@@ -523,9 +556,8 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     const TBlk& fb = p.blk[i];
     const float* uin = s_u + (i + 1) * FM * 4;
     float* uout = s_u + i * FM * 4;
-    stage_heads(i);
     build_hid(i, uin);
-    raw_product();
+    raw_product(true, i > 0 ? i - 1 : -1);  // (block 0's matrix stays: it is the first one the reverse pass needs)
     if ((tid >> 3) < rows) {  // whole warps (4 rows each)
       const int r = tid >> 3, j = tid & 7;
       const float* rr = s_raw + r * LDS;
@@ -545,9 +577,9 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     s_lp[FM + tid] = s;
   }
   // ================================================================ D1: decoder, loss terms
-  stage_mlp(p.theta, p.dec0W, p.dec0b, p.dec1W, p.dec1b, dz, p.H, 2 * dx, p.DID, DOD, s_mlp);
+  __syncthreads();
   const float* zt = s_u + nb * FM * 4;
-  mlp_forward(s_mlp, p.H, p.DID, DOD, zt, 4, dz, s_raw, s_pd, rows);
+  mlp_forward<DID, DOD>(s_mlpd, p.H, zt, 4, dz, s_raw, s_pd, rows);
   red[0] = red[1] = red[2] = red[3] = 0.f;  // (same value from every thread; warps 0 / 1 overwrite their slots below)
   __syncthreads();
   if (tid < rows) {
@@ -576,10 +608,8 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     p.spart[2 * blockIdx.x + 1] = red[1] + red[3];
   }
   // ================================================================ B1: decoder reverse mode (weights still staged)
-  mlp_backward(s_mlp, p.H, p.DID, DOD, zt, 4, dz, 2 * dx, s_gpd, part, p.dec0W, p.dec0b, p.dec1W, p.dec1b, s_raw, s_gz,
-               rows);
+  mlp_backward<DID, DOD>(s_mlpd, p.H, zt, 4, dz, 2 * dx, s_gpd, part, p.dec0W, p.dec0b, p.dec1W, p.dec1b, s_raw, s_gz, rows);
   // ================================================================ F': flow reverse mode, block 0 first
-  for (unsigned e = tid; e < 3 * graw_sz / 4; e += FT) reinterpret_cast<unsigned*>(graw)[e] = 0u;  // (held the MLP weights)
   if (tid < rows)
     for (int d = 0; d < 4; ++d) s_gu[tid * 4 + d] = d < dz ? -g_logpz * s_u[tid * 4 + d] : 0.f;
   __syncthreads();
@@ -587,9 +617,8 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
   for (int i = 0; i < nb; ++i) {
     const TBlk& fb = p.blk[i];
     const float* uin = s_u + (i + 1) * FM * 4;
-    stage_heads(i);
     build_hid(i, uin);
-    raw_product();
+    raw_product(i > 0, -1);
     if ((tid >> 3) < rows) {  // spline reverse mode, one octet per row (whole warps)
       const int r = tid >> 3, j = tid & 7;
       const bool ok = r < nr;
@@ -625,6 +654,7 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
     if (!mbar_wait_bounded(bar, phase)) failed = true;
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (tid == 0 && i + 1 < nb) load_heads(i + 1);  // both products have consumed this block's matrix
     if (16 * (warp & 3) < rows) {  // d pre-activation = d hid * (1 - hid^2) -> s_raw
       const int q = warp & 3, row = 16 * q + lane;
       for (int c0 = 16 * (warp >> 2); c0 < Hp; c0 += 64) {
@@ -654,21 +684,20 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
         }
       }
     }
-    {  // d [hW; hb] of this tile -> the CTA's partial (thread = hidden unit 32 q + lane, 16-column chunks sub, sub + 4)
+    {  // d [hW; hb] of this tile -> the CTA's partial, a padded [fh + 1][RP] matrix (rows 16-byte aligned): thread =
+       // hidden unit 32 q + lane, 16-column chunks sub, sub + 4, four 16-byte stores per chunk
       const int q = warp & 3, sub = warp >> 2, jj = 32 * q + lane;
+      float* dst = part + p.poff_h[i] + (size_t)jj * RP;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c0 = 16 * (sub + 4 * h);
         if (c0 < RP) {
           float v1[16];
           tmem_ld16(tD3 + ((unsigned)(32 * q) << 16) + (unsigned)c0, v1);
+          if (jj <= H) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int n = c0 + k;
-            if (n < R) {
-              if (jj < H) part[fb.off_hW + (size_t)jj * R + n] = v1[k];
-              else if (jj == H) part[fb.off_hb + n] = v1[k];
-            }
+            for (int k = 0; k < 16; k += 4)
+              *reinterpret_cast<float4*>(dst + c0 + k) = make_float4(v1[k], v1[k + 1], v1[k + 2], v1[k + 3]);
           }
         }
       }
@@ -754,42 +783,58 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
       }
   }
   __syncthreads();
-  stage_mlp(p.theta, p.enc0W, p.enc0b, p.enc1W, p.enc1b, dx, p.H, 2 * dz, p.DIE, DOE, s_mlp);
-  mlp_backward(s_mlp, p.H, p.DIE, DOE, s_x, 8, dx, 2 * dz, s_gpe, part, p.enc0W, p.enc0b, p.enc1W, p.enc1b, s_raw, nullptr,
-               rows);
+  mlp_backward<DIE, DOE>(s_mlpe, p.H, s_x, 8, dx, 2 * dz, s_gpe, part, p.enc0W, p.enc0b, p.enc1W, p.enc1b, s_raw, nullptr, rows);
 
   if (failed && tid == 0 && p.err) atomicExch(p.err, 1);
   tc_sync();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512u) : "memory");
 }
 
-// grad[i] = sum over the tiles' partials in a fixed order (+ Keras Adam), and the three loss scalars
+// grad[i] = sum over the tiles' partials in a fixed order (+ Keras Adam + the next step's weight images), and the three
+// loss scalars.  Block = 4 groups x 128 parameters: group g sums its quarter of the partials with eight independent
+// running sums (all loads of a thread in flight at once), the four group sums meet in shared memory in a fixed order.
 struct TcfAdam {
   float *theta, *m, *v;
   float lr_t, one_minus_b1, one_minus_b2, eps;
 };
-__global__ void __launch_bounds__(256) tcf_finish_kernel(const float* __restrict__ gpart, int n_part, int P,
-                                                         float* __restrict__ grad, const float* __restrict__ spart,
-                                                         int64_t B, float klw, float* __restrict__ scalars, const TcfAdam ad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int c = 0;
-    for (; c + 4 <= n_part; c += 4) {
-      s0 += gpart[(size_t)c * P + i];
-      s1 += gpart[(size_t)(c + 1) * P + i];
-      s2 += gpart[(size_t)(c + 2) * P + i];
-      s3 += gpart[(size_t)(c + 3) * P + i];
+constexpr int kFinP = 128, kFinG = 4;
+__global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_kernel(const float* __restrict__ gpart, int n_part, int P, int P2,
+                                                                   const int* __restrict__ part_map, float* __restrict__ grad,
+                                                                   const float* __restrict__ spart, int64_t B, float klw,
+                                                                   float* __restrict__ scalars, const TcfAdam ad,
+                                                                   const unsigned* __restrict__ pack_map, float* __restrict__ fpk,
+                                                                   unsigned short* __restrict__ wpk, size_t part) {
+  __shared__ float sh[kFinG][kFinP];
+  const int tx = threadIdx.x & (kFinP - 1), g = threadIdx.x / kFinP;
+  const int i = blockIdx.x * kFinP + tx;
+  const bool live = i < P;
+  float th = 0.f, mi = 0.f, vi = 0.f;
+  if (live && g == 0 && ad.theta) { th = ad.theta[i]; mi = ad.m[i]; vi = ad.v[i]; }  // in flight beside the partial loads
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    const int per = (n_part + kFinG - 1) / kFinG;
+    const int c0 = g * per, c1 = min(n_part, c0 + per);
+    const float* src = gpart + __ldg(part_map + i);
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += src[(size_t)(c + u) * P2];
     }
-    for (; c < n_part; ++c) s0 += gpart[(size_t)c * P + i];
-    const float t = (s0 + s1) + (s2 + s3);
+    for (; c < c1; ++c) acc[0] += src[(size_t)c * P2];
+  }
+  sh[g][tx] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  __syncthreads();
+  if (g == 0 && live) {
+    const float t = (sh[0][tx] + sh[1][tx]) + (sh[2][tx] + sh[3][tx]);
     grad[i] = t;
-    if (ad.theta) {
-      const float mi = ad.m[i] + (t - ad.m[i]) * ad.one_minus_b1;
-      const float vi = ad.v[i] + (t * t - ad.v[i]) * ad.one_minus_b2;
+    if (ad.theta) {  // Keras Adam on the flat buffer, same arithmetic as adam_kernel (adam.cu)
+      mi = mi + (t - mi) * ad.one_minus_b1;
+      vi = vi + (t * t - vi) * ad.one_minus_b2;
       ad.m[i] = mi;
       ad.v[i] = vi;
-      ad.theta[i] = ad.theta[i] - ad.lr_t * mi / (sqrtf(vi) + ad.eps);
+      th = th - ad.lr_t * mi / (sqrtf(vi) + ad.eps);
+      ad.theta[i] = th;
+      pack_store(th, __ldg(pack_map + i), fpk, wpk, part);  // the next step's images, written by the optimiser itself
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && scalars) {
@@ -810,8 +855,20 @@ struct TcfCfg {
   TParams p;
   size_t smem;
   int max_tiles;
-  float *gpart, *spart;
+  bool exact;       // MLP images in the C2 widths (DI, DO) = (8, 4) / (4, 12); else padded to (8, 16) / (8, 16)
+  float *gpart, *spart, *fpk;
   unsigned short* wpk;
+  unsigned* pack_map;  // [P] device
+  int* part_map;       // [P] device
+  size_t part;         // bfloat16 elements between the three parts of a block's heads image
+  size_t fpk_floats, wpk_elems;
+  // the images are valid for the parameters at `pack_theta` as this plan last left them (a fused Adam step wrote them)
+  bool pack_valid = false;
+  const float* pack_theta = nullptr;
+  // optional per-launch timing of the main kernel (bench.py's roofline leg)
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  size_t ev_used = 0;
 };
 
 // Sets pl->tcf when the shape is supported (same block shapes as flow_tc, MLP widths dx <= 7, dz <= 3, hidden <= 240).
@@ -836,23 +893,60 @@ vms_status tcf_create(vms_elbo_plan_s* pl) {
   p.P = (int)o.total;
   p.enc0W = (int)o.enc0W; p.enc0b = (int)o.enc0b; p.enc1W = (int)o.enc1W; p.enc1b = (int)o.enc1b;
   p.dec0W = (int)o.dec0W; p.dec0b = (int)o.dec0b; p.dec1W = (int)o.dec1W; p.dec1b = (int)o.dec1b;
-  p.DIE = round_up(d.dx + 1, 4); p.DOE = round_up(2 * d.dz, 4);
-  p.DID = round_up(d.dz + 1, 4); p.DOD = round_up(2 * d.dx, 4);
+  f->exact = round_up(d.dx + 1, 4) == 8 && round_up(2 * d.dz, 4) == 4 && round_up(d.dz + 1, 4) == 4 && round_up(2 * d.dx, 4) == 12;
+  p.DIE = 8; p.DOE = f->exact ? 4 : 16;
+  p.DID = f->exact ? 4 : 8; p.DOD = f->exact ? 12 : 16;
   for (int i = 0; i < d.num_blocks; ++i) {
     const FlowBlock& b = pl->blocks[i];
     TBlk& t = p.blk[i];
     t.cs0 = b.cs0; t.nc = b.cs1 - b.cs0; t.ts0 = b.ts0; t.cin = b.cin;
     t.off_d1W = (int)b.off_d1W; t.off_d1b = (int)b.off_d1b; t.off_hW = (int)b.off_hW; t.off_hb = (int)b.off_hb;
   }
-  const int nchH = p.Hp / 8, nchR = p.RP / 8;
+  const int nchH = p.Hp / 8, nchR = p.RP / 8, H = d.hidden, fh = d.flow_hidden, nb = d.num_blocks;
+  // ---- float images and the maps parameter -> image / parameter -> partial
+  p.n_enc = round_up(H * (p.DIE + p.DOE) + p.DOE, 4);
+  p.n_dec = round_up(H * (p.DID + p.DOD) + p.DOD, 4);
+  p.n_d1 = nb * 5 * p.Hp;
+  p.f_enc = 0; p.f_dec = p.n_enc; p.f_d1 = p.n_enc + p.n_dec;
+  f->fpk_floats = (size_t)p.n_enc + p.n_dec + p.n_d1;
+  f->part = (size_t)nchH * p.RP * 8;
+  f->wpk_elems = (size_t)nb * 3 * f->part;
+  std::vector<unsigned> pmap((size_t)p.P, 0u);
+  std::vector<int> qmap((size_t)p.P, 0);
+  for (int i = 0; i < p.P; ++i) qmap[i] = i;
+  auto mlp_map = [&](int base, int oW0, int ob0, int oW1, int ob1, int Din, int Dout, int DI, int DO) {
+    for (int i = 0; i < Din; ++i)
+      for (int j = 0; j < H; ++j) pmap[oW0 + (size_t)i * H + j] = (unsigned)(base + j * DI + i);
+    for (int j = 0; j < H; ++j) pmap[ob0 + j] = (unsigned)(base + j * DI + Din);
+    for (int j = 0; j < H; ++j)
+      for (int n = 0; n < Dout; ++n) pmap[oW1 + (size_t)j * Dout + n] = (unsigned)(base + H * DI + j * DO + n);
+    for (int n = 0; n < Dout; ++n) pmap[ob1 + n] = (unsigned)(base + H * DI + H * DO + n);
+  };
+  mlp_map(p.f_enc, p.enc0W, p.enc0b, p.enc1W, p.enc1b, d.dx, 2 * d.dz, p.DIE, p.DOE);
+  mlp_map(p.f_dec, p.dec0W, p.dec0b, p.dec1W, p.dec1b, d.dz, 2 * d.dx, p.DID, p.DOD);
+  int P2 = round_up(p.P, 4);
+  for (int b = 0; b < nb; ++b) {
+    const TBlk& t = p.blk[b];
+    for (int c = 0; c < t.cin; ++c)
+      for (int j = 0; j < fh; ++j) pmap[t.off_d1W + (size_t)c * fh + j] = (unsigned)(p.f_d1 + (b * 4 + c) * p.Hp + j);
+    for (int j = 0; j < fh; ++j) pmap[t.off_d1b + j] = (unsigned)(p.f_d1 + nb * 4 * p.Hp + b * p.Hp + j);
+    p.poff_h[b] = P2;
+    for (int j = 0; j <= fh; ++j)
+      for (int n = 0; n < p.R; ++n) {
+        const size_t th = j < fh ? (size_t)t.off_hW + (size_t)j * p.R + n : (size_t)t.off_hb + n;
+        pmap[th] = 0x80000000u | (unsigned)((size_t)b * 3 * f->part + (size_t)(j >> 3) * p.RP * 8 + (size_t)n * 8 + (j & 7));
+        qmap[th] = P2 + j * p.RP + n;
+      }
+    P2 += (fh + 1) * p.RP;
+  }
+  p.P2 = P2;
+  // ---- shared-memory carve-up (bytes)
   int off = 0;
   auto take = [&](int bytes) { int o0 = off; off += round_up(bytes, 16); return o0; };
   p.o_hid = take(3 * nchH * (int)CSB);
-  const int mlp_floats = d.hidden * ((p.DIE + p.DOE) > (p.DID + p.DOD) ? (p.DIE + p.DOE) : (p.DID + p.DOD)) + 16;
-  const int graw_bytes = 3 * nchR * (int)CSB;
-  p.o_graw = take(graw_bytes > 4 * mlp_floats ? graw_bytes : 4 * mlp_floats);
+  p.o_graw = take(3 * nchR * (int)CSB);
   p.o_w = take(3 * nchH * p.RP * 16);
-  // s_raw doubles as scratch of the MLP phases: 8 row groups x FM x 16 outputs, or hidden x 24 accumulators
+  // s_raw doubles as scratch of the MLP phases: 16 row groups x 32 rows x 16 outputs, or hidden x 24 accumulators
   int raw_floats = FM * p.LDS;
   if (raw_floats < 8 * FM * 16) raw_floats = 8 * FM * 16;
   if (raw_floats < d.hidden * 24) raw_floats = d.hidden * 24;
@@ -863,39 +957,58 @@ vms_status tcf_create(vms_elbo_plan_s* pl) {
   p.o_pe = take(FM * p.DOE * 4); p.o_pd = take(FM * p.DOD * 4);
   p.o_gpd = take(FM * p.DOD * 4); p.o_gpe = take(FM * p.DOE * 4);
   p.o_gz = take(FM * 4 * 4); p.o_lp = take(3 * FM * 4); p.o_gin = take(FM * 4);
-  p.o_w1 = take(d.num_blocks * 4 * p.Hp * 4); p.o_b1 = take(d.num_blocks * p.Hp * 4);
+  p.o_w1 = take(p.n_d1 * 4);  // [nb][4][Hp] followed by [nb][Hp]: one bulk copy
+  p.o_b1 = p.o_w1 + nb * 4 * p.Hp * 4;
+  p.o_mlpe = take(p.n_enc * 4);
+  p.o_mlpd = take(p.n_dec * 4);
   f->smem = (size_t)off;
   if (f->smem + 1024 > (size_t)max_smem_optin()) { delete f; return VMS_OK; }
   f->max_tiles = sm_count();
-  void *g = nullptr, *s = nullptr, *w = nullptr;
-  const size_t wpk_bytes = (size_t)d.num_blocks * 3 * nchH * p.RP * 8 * sizeof(unsigned short);
-  if (cudaMalloc(&g, (size_t)f->max_tiles * p.P * sizeof(float)) != cudaSuccess ||
-      cudaMalloc(&s, (size_t)f->max_tiles * 2 * sizeof(float)) != cudaSuccess || cudaMalloc(&w, wpk_bytes) != cudaSuccess) {
+  void *g = nullptr, *s = nullptr, *w = nullptr, *fp = nullptr, *pm = nullptr, *qm = nullptr;
+  bool ok = cudaMalloc(&g, (size_t)f->max_tiles * p.P2 * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&s, (size_t)f->max_tiles * 2 * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&w, f->wpk_elems * sizeof(unsigned short)) == cudaSuccess &&
+            cudaMalloc(&fp, f->fpk_floats * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&pm, (size_t)p.P * sizeof(unsigned)) == cudaSuccess &&
+            cudaMalloc(&qm, (size_t)p.P * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMemset(w, 0, f->wpk_elems * sizeof(unsigned short)) == cudaSuccess &&
+       cudaMemset(fp, 0, f->fpk_floats * sizeof(float)) == cudaSuccess &&
+       cudaMemcpy(pm, pmap.data(), (size_t)p.P * sizeof(unsigned), cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(qm, qmap.data(), (size_t)p.P * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+  // the conditioner image's ones-column convention: an empty conditioner (cin = 1, nc = 0) multiplies d1W row 0 by 1
+  if (!ok) {
     cudaGetLastError();
-    if (g) cudaFree(g);
-    if (s) cudaFree(s);
+    for (void* q : {g, s, w, fp, pm, qm})
+      if (q) cudaFree(q);
     delete f;
-    return VMS_OK;  // experimental path: simply unavailable
+    return VMS_OK;  // this path is simply unavailable; the FFMA fused kernel serves the shape
   }
-  f->gpart = (float*)g; f->spart = (float*)s; f->wpk = (unsigned short*)w;
+  f->gpart = (float*)g; f->spart = (float*)s; f->wpk = (unsigned short*)w; f->fpk = (float*)fp;
+  f->pack_map = (unsigned*)pm; f->part_map = (int*)qm;
   pl->tcf = f;
   return VMS_OK;
 }
 
 void tcf_destroy(vms_elbo_plan_s* pl) {
   if (!pl->tcf) return;
+  for (auto& e : pl->tcf->ev) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
   cudaFree(pl->tcf->gpart);
   cudaFree(pl->tcf->spart);
   cudaFree(pl->tcf->wpk);
+  cudaFree(pl->tcf->fpk);
+  cudaFree(pl->tcf->pack_map);
+  cudaFree(pl->tcf->part_map);
   delete pl->tcf;
   pl->tcf = nullptr;
 }
 
-// valid rows per tile: 64 (the measured configuration), or 32 with VMS_TCF_ROWS=32 (UNTESTED on the device at the end
-// of round 1: twice the CTAs, SIMT phases halved, the M = 64 products padded with zero rows)
+// valid rows per tile: 32 (default: 128 CTAs at batch 4096), or 64 with VMS_TCF_ROWS=64 (round 1's configuration)
 static int tcf_rows() {
   const char* e = getenv("VMS_TCF_ROWS");
-  return (e && atoi(e) == 32) ? 32 : FM;
+  return (e && atoi(e) == 64) ? FM : 32;
 }
 
 bool tcf_available(const vms_elbo_plan_s* pl, int64_t B) {
@@ -903,34 +1016,81 @@ bool tcf_available(const vms_elbo_plan_s* pl, int64_t B) {
   return pl->tcf && (B + rows - 1) / rows <= pl->tcf->max_tiles;
 }
 
-// forward + backward (+ Adam when `adam`): 3 launches (prepack, the tile kernel, finish)
+void tcf_invalidate(vms_elbo_plan_s* pl) {
+  if (pl->tcf) pl->tcf->pack_valid = false;
+}
+
+vms_status tcf_set_timing(vms_elbo_plan_s* pl, int max_launches) {
+  TcfCfg* f = pl->tcf;
+  if (!f) return VMS_OK;
+  f->ev_used = 0;
+  f->timing = max_launches > 0;
+  while ((int)f->ev.size() < max_launches) {
+    cudaEvent_t a, b;
+    VMS_CUDA(cudaEventCreate(&a));
+    VMS_CUDA(cudaEventCreate(&b));
+    f->ev.emplace_back(a, b);
+  }
+  return VMS_OK;
+}
+
+vms_status tcf_kernel_ms(vms_elbo_plan_s* pl, double* total_ms, int* launches) {
+  TcfCfg* f = pl->tcf;
+  if (!f) return VMS_OK;
+  for (size_t i = 0; i < f->ev_used; ++i) {
+    float ms = 0.f;
+    VMS_CUDA(cudaEventSynchronize(f->ev[i].second));
+    VMS_CUDA(cudaEventElapsedTime(&ms, f->ev[i].first, f->ev[i].second));
+    *total_ms += ms;
+  }
+  *launches += (int)f->ev_used;
+  f->ev_used = 0;
+  return VMS_OK;
+}
+
+// forward + backward (+ Adam when `adam`): the tile kernel and the finish kernel; the pre-pack kernel only when the
+// images are not known to match theta (first call, parameters changed behind the plan's back)
 vms_status tcf_run(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B, float* grad,
                    float* scalars, cudaStream_t st, const FusedAdam* adam) {
   TcfCfg* f = pl->tcf;
   VMS_REQUIRE(f && tcf_available(pl, B), VMS_ERR_UNSUPPORTED, "elbo (mode 3): shape or batch not supported");
   TParams p = f->p;
   p.B = B; p.theta = theta; p.x = x; p.eps = eps;
-  p.wpk = f->wpk; p.gpart = f->gpart; p.spart = f->spart; p.err = pl->tc_err;
+  p.wpk = f->wpk; p.fpk = f->fpk; p.gpart = f->gpart; p.spart = f->spart; p.err = pl->tc_err;
   p.rows = tcf_rows();
   const int n_tiles = (int)((B + p.rows - 1) / p.rows);
-  tcf_prepack_kernel<<<dim3((p.Hp * p.RP + 255) / 256, p.nb), 256, 0, st>>>(p, f->wpk);
-  VMS_LAUNCH_CHECK("tcf_prepack_kernel");
-  if (p.RP == 64) {
-    VMS_CUDA(cudaFuncSetAttribute(tcf_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
-    tcf_kernel<64><<<n_tiles, FT, f->smem, st>>>(p);
-  } else {
-    VMS_CUDA(cudaFuncSetAttribute(tcf_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
-    tcf_kernel<96><<<n_tiles, FT, f->smem, st>>>(p);
+  if (!(f->pack_valid && f->pack_theta == theta)) {
+    tcf_prepack_kernel<<<(p.P + 255) / 256, 256, 0, st>>>(theta, f->pack_map, p.P, f->fpk, f->wpk, f->part);
+    VMS_LAUNCH_CHECK("tcf_prepack_kernel");
   }
+  const bool timed = f->timing && f->ev_used < f->ev.size();
+  if (timed) VMS_CUDA(cudaEventRecord(f->ev[f->ev_used].first, st));
+#define VMS_TCF_LAUNCH(RPV, EX)                                                                                             \
+  do {                                                                                                                      \
+    VMS_CUDA(cudaFuncSetAttribute(tcf_kernel<RPV, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));         \
+    tcf_kernel<RPV, EX><<<n_tiles, FT, f->smem, st>>>(p);                                                                   \
+  } while (0)
+  if (p.RP == 64) {
+    if (f->exact) VMS_TCF_LAUNCH(64, true); else VMS_TCF_LAUNCH(64, false);
+  } else {
+    if (f->exact) VMS_TCF_LAUNCH(96, true); else VMS_TCF_LAUNCH(96, false);
+  }
+#undef VMS_TCF_LAUNCH
   VMS_LAUNCH_CHECK("tcf_kernel");
+  if (timed) VMS_CUDA(cudaEventRecord(f->ev[f->ev_used++].second, st));
   TcfAdam ad = {};
   if (adam) {
     ad.theta = adam->theta; ad.m = adam->m; ad.v = adam->v;
     ad.lr_t = adam->lr_t; ad.one_minus_b1 = adam->one_minus_b1; ad.one_minus_b2 = adam->one_minus_b2; ad.eps = adam->eps;
   }
-  tcf_finish_kernel<<<(p.P + 255) / 256, 256, 0, st>>>(f->gpart, n_tiles, p.P, grad, f->spart, B, p.klw,
-                                                      scalars ? scalars : pl->scalars, ad);
+  tcf_finish_kernel<<<(p.P + kFinP - 1) / kFinP, kFinP * kFinG, 0, st>>>(f->gpart, n_tiles, p.P, p.P2, f->part_map, grad,
+                                                                          f->spart, B, p.klw, scalars ? scalars : pl->scalars,
+                                                                          ad, f->pack_map, f->fpk, f->wpk, f->part);
   VMS_LAUNCH_CHECK("tcf_finish_kernel");
+  // after a fused Adam step the images describe the updated parameters; without it nothing is known about what the caller
+  // does to theta next (e.g. the data-parallel exchange updates it in its own kernel)
+  f->pack_valid = adam != nullptr && adam->theta == theta;
+  f->pack_theta = theta;
   return VMS_OK;
 }
 

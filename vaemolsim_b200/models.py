@@ -221,6 +221,7 @@ class FusedELBO(object):
             off += b.size
             lay.rebind(kW, kb)
             lay.assign(W, b)
+            lay._on_assign = self.invalidate  # host-side weight assignment: the plan's packed weight images are stale
         if off != self.n_params:
             raise RuntimeError('fused ELBO: parameter layout mismatch (%d != %d)' % (off, self.n_params))
         h = C.c_void_p()
@@ -302,9 +303,16 @@ class FusedELBO(object):
         raise NotImplementedError('fused ELBO: prior must be a static N(0, I) DistributionLambda (-> StandardNormal of the '
                                   'latent size) or a FlowedDistribution over one')
 
+    def invalidate(self):
+        """Tell the plan that theta changed behind its back (its packed weight images must be rebuilt)."""
+        if getattr(self, 'handle', None):
+            ctx().lib.vms_elbo_plan_invalidate(self.handle)
+
     def set_mode(self, mode):
-        """0 = auto (the single fused kernel when the shape fits), 1 = force the unfused per-layer float32-FFMA graph
-        path, 2 = unfused plan with the coupling blocks as fused tcgen05 kernels (the large-batch configuration)."""
+        """0 = auto (whole-step tensor-core kernel for training steps that fit one wave, the FFMA fused kernel for forward
+        evaluation, the tensor-core plan above), 1 = force the unfused per-layer float32-FFMA graph path, 2 = unfused plan
+        with the coupling blocks as fused tcgen05 kernels (the large-batch configuration), 3 = force the whole-step
+        tensor-core kernel, 4 = force the single FFMA fused kernel."""
         ctx().lib.vms_elbo_plan_set_mode(self.handle, int(mode))
 
     def set_tc_auto_batch(self, batch):
@@ -315,7 +323,7 @@ class FusedELBO(object):
     def path(self, batch):
         """Implementation a step of `batch` rows takes: 'fused' (one persistent kernel), 'ffma' (per-layer float32
         plan) or 'tensor-core' (large-batch plan: tcgen05 coupling blocks + streaming MLP kernels)."""
-        return ('fused', 'ffma', 'tensor-core', 'tensor-core-fused (experimental)')[
+        return ('fused', 'ffma', 'tensor-core', 'tensor-core-fused')[
             ctx().lib.vms_elbo_plan_path(self.handle, int(batch))]
 
     def tc_status(self):
@@ -354,14 +362,17 @@ class FusedELBO(object):
         c.lib.vms_adam_step(self.theta.ptr, self.grad.ptr, 1, grad_scale, self.m.ptr, self.v.ptr, self.n_params, self.t,
                             opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon, c.stream)
 
-    def train_loop(self, x_host, opt, batch_size, order=None, eps_host=None, n_steps=None, seed=None):
+    def train_loop(self, x_host, opt, batch_size, order=None, eps_host=None, n_steps=None, seed=None, exchange=None):
         """The inner loop of `VAE.fit` (the Keras training loop of tests/test_models.py:181-182) as a device pipeline:
         batch i + 1 travels host -> device on a copy stream while batch i trains (double-buffered inputs, events in both
         directions), the reparameterisation noise is drawn on the device (Philox, `vms_standard_normal`) unless `eps_host`
         is given, and the per-step scalars {loss, nll, kl} land in a small device ring that is read back every 8 steps,
         so the host never waits for a step.  x_host [N, dx] float32 (pinned memory avoids a staging copy when `order` is
         None); order: row permutation (shuffle); n_steps: number of batches (default: one epoch, ragged last batch
-        dropped into its own step).  Returns the [n_steps, 3] scalars."""
+        dropped into its own step).  exchange: a `parallel.PeerExchange` -- data-parallel training: the step becomes
+        forward + backward into this rank's slot of the exchange buffer followed by the fused NVLink allreduce + Adam kernel
+        (every rank must run the same number of steps); the scalars are this rank's shard means.  Returns the
+        [n_steps, 3] scalars."""
         c = ctx()
         lib = c.lib
         N = x_host.shape[0]
@@ -438,11 +449,16 @@ class FusedELBO(object):
                 lib.vms_standard_normal(L['noise_seed'], L['noise_offset'], n * self.dz, L['ed'][b].ptr, c.stream)
                 L['noise_offset'] += n * self.dz
             lib.vms_stream_wait_event(c.stream, L['h2d'][b])
-            self.t += 1
             slot = i % R
-            lib.vms_elbo_train_step(self.handle, self.theta.ptr, L['xd'][b].ptr, L['ed'][b].ptr, n, self.grad.ptr,
-                                    L['ring'].ptr + 16 * slot, self.m.ptr, self.v.ptr, self.t, opt.learning_rate, opt.beta_1,
-                                    opt.beta_2, opt.epsilon, c.stream)
+            if exchange is None:
+                self.t += 1
+                lib.vms_elbo_train_step(self.handle, self.theta.ptr, L['xd'][b].ptr, L['ed'][b].ptr, n, self.grad.ptr,
+                                        L['ring'].ptr + 16 * slot, self.m.ptr, self.v.ptr, self.t, opt.learning_rate,
+                                        opt.beta_1, opt.beta_2, opt.epsilon, c.stream)
+            else:
+                lib.vms_elbo_forward_backward(self.handle, self.theta.ptr, L['xd'][b].ptr, L['ed'][b].ptr, n,
+                                              exchange.next_slot(), L['ring'].ptr + 16 * slot, c.stream)
+                exchange.allreduce_adam(self, opt)  # advances self.t
             lib.vms_event_record(L['free'][b], c.stream)
             used[b] = True
             if slot == R - 1 or i == len(starts) - 1:
