@@ -13,10 +13,13 @@ Lines printed (one JSON object, rank 0):
   value        inputs resident in HBM; per-step CUDA events on the launching stream; L2 flushed between timed steps
   e2e          same step through the public API (`VAE.train_step`) from PINNED HOST buffers: H2D of x and eps, D2H of
                the loss scalars, wall clock, every step
-  roofline     the dominant kernel of the step (elbo_fused_kernel), its device time measured with CUDA events around
-               every launch INSIDE the timed region (vms_elbo_plan_set_timing); HBM-bound kernels timed alone are under
-               "kernels"
-  mc           the second headline metric: MC proposals/sec (C4a: 65,536 chains over all GPUs, 100 steps, fused kernel)
+  roofline     the dominant kernel of the step (tcf_kernel: the whole-step tcgen05 kernel), its device time measured with
+               CUDA events around every launch INSIDE the timed region (vms_elbo_plan_set_timing), against the measured
+               bf16 peak (MEASURED_PEAKS.json) and against the FFMA / tcgen05 issue peaks measured live by the library's
+               probe kernels (csrc/probe.cu); HBM-bound kernels timed alone are under "kernels"
+  legs         the other BASELINE.json configurations as short legs, each with value / e2e / roofline / cpu_baseline:
+               c1 (Gaussian VAE), c3 (neighbour selection through DistanceSelection.__call__, rows sharded over ranks),
+               c4a_mc (= "mc": MC proposals/sec, 65,536 chains over all GPUs), c5 (= "large_batch": global batch 262,144)
   cpu_baseline the NumPy oracle (CPU restatement; TF/TFP are not installable here) on a bounded sample, rank 0
 `--impl reference` times that CPU restatement as the reference arm (the reference's TF path cannot run in this image).
 """
@@ -232,23 +235,44 @@ def build_model(v, w, batch):
     return model
 
 
-def kernel_microbench(v, w, batch, reps=20):
-    """CUDA-event timings of the HBM-bound kernels, alone: at the workload's shape (cold L2) and at a streaming size."""
-    c = v._abi.ctx()
-    peaks = {}
+def load_json(name):
     try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return json.load(open(os.path.join(ROOT, name)))
     except (OSError, ValueError):
-        pass
-    peak = float(peaks.get('hbm_gbs', 6650.0))
-    peak_kind = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+        return {}
+
+
+def measured_peaks(v):
+    """Roofline denominators: the driver-written MEASURED_PEAKS.json (HBM copy, cuBLAS bf16) and, measured LIVE by the
+    library's probe kernels (csrc/probe.cu), the FP32 FFMA issue peak and the tcgen05 bf16 / tf32 issue peaks
+    (BASELINE.md section 2 asks for them)."""
+    c = v._abi.ctx()
+    drv = load_json('MEASURED_PEAKS.json')
+    out = {'hbm_gbs': float(drv.get('hbm_gbs', 6650.0)), 'bf16_tflops': float(drv.get('bf16_tflops', 1590.0)),
+           'bf16_tflops_sustained': float(drv.get('bf16_tflops_sustained', 1400.0)),
+           'kind': 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in drv else 'fallback (B200_PROFILING.md)'}
+    t, ms = C.c_double(0), C.c_double(0)
+    c.lib.vms_probe_ffma(2048, 3, C.byref(t), C.byref(ms), c.stream)
+    out['fp32_ffma_tflops'] = t.value
+    out['fp32_ffma_nominal_tflops'] = c.sm_count * 128 * 2 * 1.965e9 / 1e12
+    for kind, name in ((0, 'bf16'), (1, 'tf32')):
+        for M, N in ((128, 256), (64, 96)):
+            c.lib.vms_probe_mma(kind, M, N, 8000, 3, C.byref(t), C.byref(ms), c.stream)
+            out['tcgen05_%s_m%d_n%d_tflops' % (name, M, N)] = t.value
+    out['probe'] = 'csrc/probe.cu, best of 3 launches, CUDA events (this run)'
+    return out
+
+
+def kernel_microbench(v, w, batch, peak, reps=20):
+    """CUDA-event timings of the HBM-bound kernels, alone, at streaming sizes (cold L2)."""
+    c = v._abi.ctx()
     K = w['num_bins']
     flush = v.Tensor((64 << 20, ))  # 256 MiB > 126 MB L2
     ev = Events(c, 1)
     rng = np.random.default_rng(5)
     res = {}
 
-    def timed(fn, n_rep, do_flush):
+    def timed(fn, n_rep, do_flush=True):
         ts = []
         for _ in range(n_rep):
             if do_flush:
@@ -260,29 +284,28 @@ def kernel_microbench(v, w, batch, reps=20):
             ts.append(ev.elapsed_ms(0, 1))
         return float(np.mean(ts[2:])) if len(ts) > 4 else float(np.mean(ts))
 
-    for tag, n in (('workload', batch), ('stream', 1 << 21)):
-        rw = v.Tensor.from_numpy(rng.standard_normal((n, K), dtype=np.float32))
-        rh = v.Tensor.from_numpy(rng.standard_normal((n, K), dtype=np.float32))
-        rs = v.Tensor.from_numpy(rng.standard_normal((n, K - 1), dtype=np.float32))
-        x = v.Tensor.from_numpy(rng.uniform(-10, 10, n).astype(np.float32))
-        g = v.Tensor.from_numpy(rng.standard_normal(n, dtype=np.float32))
-        y, l = v.Tensor((n, )), v.Tensor((n, ))
-        gi, gw, gh, gs = v.Tensor((n, )), v.Tensor((n, K)), v.Tensor((n, K)), v.Tensor((n, K - 1))
-        fwd_bytes = n * (4 * (3 * K - 1) + 12)
-        bwd_bytes = n * (2 * 4 * (3 * K - 1) + 4 + 8 + 4)
-        for name, nbytes, fn in (
-            ('rqs_forward', fwd_bytes, lambda: c.lib.vms_rqs_forward(x.ptr, rw.ptr, rh.ptr, rs.ptr, n, K, -10.0, 10.0,
-                                                                     y.ptr, l.ptr, c.stream)),
-            ('rqs_inverse', fwd_bytes, lambda: c.lib.vms_rqs_inverse(x.ptr, rw.ptr, rh.ptr, rs.ptr, n, K, -10.0, 10.0,
-                                                                     y.ptr, l.ptr, c.stream)),
-            ('rqs_backward', bwd_bytes, lambda: c.lib.vms_rqs_backward(x.ptr, rw.ptr, rh.ptr, rs.ptr, n, K, -10.0, 10.0,
-                                                                       1, g.ptr, g.ptr, gi.ptr, gw.ptr, gh.ptr, gs.ptr,
-                                                                       c.stream)),
-        ):
-            ms = timed(fn, reps, True)
-            gbs = nbytes / (ms * 1e-3) / 1e9
-            res['%s@%s' % (name, tag)] = {'n_elem': n, 'ms': ms, 'bytes': nbytes, 'gbs': gbs, 'frac': gbs / peak}
-    # decoder-distribution log_prob (K4) and neighbour selection (K6) at streaming sizes
+    n = 1 << 21
+    rw = v.Tensor.from_numpy(rng.standard_normal((n, K), dtype=np.float32))
+    rh = v.Tensor.from_numpy(rng.standard_normal((n, K), dtype=np.float32))
+    rs = v.Tensor.from_numpy(rng.standard_normal((n, K - 1), dtype=np.float32))
+    x = v.Tensor.from_numpy(rng.uniform(-10, 10, n).astype(np.float32))
+    g = v.Tensor.from_numpy(rng.standard_normal(n, dtype=np.float32))
+    y, l = v.Tensor((n, )), v.Tensor((n, ))
+    gi, gw, gh, gs = v.Tensor((n, )), v.Tensor((n, K)), v.Tensor((n, K)), v.Tensor((n, K - 1))
+    fwd_bytes = n * (4 * (3 * K - 1) + 12)
+    bwd_bytes = n * (2 * 4 * (3 * K - 1) + 4 + 8 + 4)
+    for name, nbytes, fn in (
+        ('rqs_forward', fwd_bytes, lambda: c.lib.vms_rqs_forward(x.ptr, rw.ptr, rh.ptr, rs.ptr, n, K, -10.0, 10.0, y.ptr, l.ptr,
+                                                                 c.stream)),
+        ('rqs_inverse', fwd_bytes, lambda: c.lib.vms_rqs_inverse(x.ptr, rw.ptr, rh.ptr, rs.ptr, n, K, -10.0, 10.0, y.ptr, l.ptr,
+                                                                 c.stream)),
+        ('rqs_backward', bwd_bytes, lambda: c.lib.vms_rqs_backward(x.ptr, rw.ptr, rh.ptr, rs.ptr, n, K, -10.0, 10.0, 1, g.ptr,
+                                                                   g.ptr, gi.ptr, gw.ptr, gh.ptr, gs.ptr, c.stream)),
+    ):
+        ms = timed(fn, reps)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        res['%s@stream' % name] = {'n_elem': n, 'ms': ms, 'bytes': nbytes, 'gbs': gbs, 'frac': gbs / peak}
+    del rw, rh, rs, gw, gh, gs
     n, D = 1 << 22, w['dx']
     xx = v.Tensor.from_numpy(rng.standard_normal((n, D), dtype=np.float32))
     pp = v.Tensor.from_numpy(rng.standard_normal((n, 2 * D), dtype=np.float32))
@@ -290,21 +313,94 @@ def kernel_microbench(v, w, batch, reps=20):
     i32 = lambda a: (C.c_int32 * len(a))(*a)
     kind, loc, loc2, sc = i32([0] * D), i32(list(range(D))), i32([-1] * D), i32(list(range(D, 2 * D)))
     ms = timed(lambda: c.lib.vms_blockwise_log_prob(xx.ptr, D, pp.ptr, 2 * D, n, D, kind, loc, loc2, sc, 1, lp.ptr, 0,
-                                                    c.stream), reps, True)
+                                                    c.stream), reps)
     nbytes = n * (3 * D * 4 + 4)
     res['normal_log_prob@stream'] = {'n_rows': n, 'ms': ms, 'bytes': nbytes, 'gbs': nbytes / ms / 1e6,
                                      'frac': nbytes / ms / 1e6 / peak}
-    Bs, N, k = 4096, 10000, 50  # C3 shape: 4096 reference rows x 10,000 particles (coords replicated per row, as the API requires)
-    coords = v.Tensor.from_numpy(np.broadcast_to(rng.uniform(-23.2, 23.2, (1, N, 3)).astype(np.float32), (Bs, N, 3)))
-    ref = v.Tensor.from_numpy(rng.uniform(-23.2, 23.2, (Bs, 3)).astype(np.float32))
-    box = v.Tensor.from_numpy(np.full(3, 46.416, np.float32))
-    oxyz = v.Tensor((Bs, k, 3))
-    ms = timed(lambda: c.lib.vms_dist_select(coords.ptr, None, Bs, N, ref.ptr, box.ptr, 0, 9.0, k, None, 0, oxyz.ptr,
-                                             None, None, c.stream), reps, True)
-    nbytes = Bs * (12 * N + 12 + k * 12)
-    res['dist_select@C3'] = {'rows': Bs, 'N': N, 'k': k, 'ms': ms, 'bytes': nbytes, 'gbs': nbytes / ms / 1e6,
-                                  'frac': nbytes / ms / 1e6 / peak}
-    return res, peak, peak_kind
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------- C3 leg
+C3 = dict(rows=4096, N=10000, L=46.416, k=50, P=2, cutoff=3.0)
+C3_LABEL = ('C3 backmapping selection: DistanceSelection(cutoff 3.0, max_included 50, box 46.416^3) over one frame of 10,000 '
+            'particles replicated per reference row (the API takes [B, N, 3]), one-hot particle_info P = 2, int32 indices; '
+            '4096 reference rows sharded over the GPUs')
+
+
+def c3_leg(v, grp, peak_hbm, reps=10):
+    """Neighbour selection at the C3 shape: `value` = rows/s with coords / info resident in HBM (CUDA events, L2 flushed),
+    `e2e` = the same call through `DistanceSelection.__call__` from pinned HOST arrays (H2D of coords / ref / info and D2H
+    of the selection inside the timed region), rows sharded over the ranks, no collective."""
+    from vaemolsim_b200 import parallel
+    from oracle import mappings as omap
+    c = v._abi.ctx()
+    lib = c.lib
+    lo, hi = parallel.shard_rows(C3['rows'], grp.rank, grp.world)
+    B, N, k, P = hi - lo, C3['N'], C3['k'], C3['P']
+    L = np.float32(C3['L'])
+    rng = np.random.default_rng(3001)
+    frame = rng.uniform(-L / 2, L / 2, (N, 3)).astype(np.float32)
+    kinds = rng.integers(0, 2, N)
+    ref_all = np.random.default_rng(3002).uniform(-L / 2, L / 2, (C3['rows'], 1, 3)).astype(np.float32)
+    coords_h = pinned_array(lib, (B, N, 3))
+    info_h = pinned_array(lib, (B, N, P))
+    ref_h = pinned_array(lib, (B, 1, 3))
+    coords_h[...] = frame[None]
+    info_h[...] = np.eye(2, dtype=np.float32)[kinds][None]
+    ref_h[...] = ref_all[lo:hi]
+    box = np.array([L, L, L], np.float32)
+    layer = v.mappings.DistanceSelection(C3['cutoff'], max_included=k, box_lengths=box)
+    coords_d, info_d, ref_d = v.Tensor.from_numpy(coords_h), v.Tensor.from_numpy(info_h), v.Tensor.from_numpy(ref_h)
+    flush = v.Tensor((64 << 20, ))
+    ev = Events(c, 1)
+    for _ in range(3):
+        out = layer(coords_d, ref_d, particle_info=info_d, return_indices=True)
+    c.synchronize()
+    grp.barrier()
+    l0 = v._abi.launch_count()
+    dev_ms = 0.0
+    for _ in range(reps):
+        lib.vms_memset(flush.ptr, 0, flush.nbytes, c.stream)
+        ev.record(0)
+        out = layer(coords_d, ref_d, particle_info=info_d, return_indices=True)
+        ev.record(1)
+        c.synchronize()
+        dev_ms += ev.elapsed_ms(0, 1)
+    launches = v._abi.launch_count() - l0  # (vms_memset is a runtime call, not counted)
+    dev_ms = grp.max(dev_ms) / reps
+    # end to end from pinned host arrays through the layer call
+    n_e2e = 3
+    sel = layer(coords_h, ref_h, particle_info=info_h, return_indices=True)
+    [t.numpy() for t in sel]
+    grp.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        sel = layer(coords_h, ref_h, particle_info=info_h, return_indices=True)
+        got = [t.numpy() for t in sel]
+    e2e_s = grp.max(time.perf_counter() - t0) / n_e2e
+    bytes_row = 12 * N + 12 + k * (12 + 4 * P) + 4 * k * P + 4 * k  # SURVEY 8d (+ the int32 indices)
+    gbs = B * bytes_row / (dev_ms * 1e-3) / 1e9
+    res = {'metric': 'reference rows/sec (neighbour selection)', 'value': C3['rows'] / (dev_ms * 1e-3), 'unit': 'rows/s',
+           'workload': C3_LABEL, 'rows_per_gpu': B, 'ms_per_call': dev_ms, 'scaling': 'strong (rows sharded, no collective)',
+           'gpu_launches_per_call': max(1, int(round(launches / reps))) if launches > 0 else 1,
+           'e2e': {'value': C3['rows'] / e2e_s, 'unit': 'rows/s', 'ms_per_call': e2e_s * 1e3,
+                   'h2d_bytes_per_step': int(coords_h.nbytes + info_h.nbytes + ref_h.nbytes),
+                   'd2h_bytes_per_step': int(B * k * (12 + 4 * P + 4)),
+                   'api': 'DistanceSelection.__call__(coords, ref, particle_info=..., return_indices=True) from pinned host arrays',
+                   'note': 'PCIe-bound by construction: the reference API takes the frame replicated per row, 120 KB per row'},
+           'roofline': {'bound': 'hbm', 'kernel': 'dist_select_kernel', 'achieved': gbs, 'peak': peak_hbm, 'unit': 'GB/s',
+                        'frac': gbs / peak_hbm, 'algorithmic_bytes_per_row': bytes_row, 'traffic': None}}
+    if grp.rank == 0:
+        n_cpu = 32
+        t0 = time.perf_counter()
+        want = omap.distance_selection(coords_h[:n_cpu], ref_h[:n_cpu].reshape(n_cpu, 3), C3['cutoff'], k, box_lengths=box,
+                                       particle_info=info_h[:n_cpu], return_indices=True)
+        dt = time.perf_counter() - t0
+        res['cpu_baseline'] = {'value': n_cpu / dt, 'unit': 'rows/s', 'cores': cpu_threads(), 'kind': 'port',
+                               'sample': '%d rows, oracle/mappings.py (restatement of mappings.py:362-455)' % n_cpu}
+        res['parity_vs_oracle'] = bool(np.array_equal(got[0][:n_cpu], want[0]) and np.array_equal(got[1][:n_cpu], want[1])
+                                       and np.array_equal(got[2][:n_cpu], want[2]))
+    return res
 
 
 # ---------------------------------------------------------------------------------------------------- MC leg (C4a)
@@ -332,43 +428,86 @@ def mc_cpu_baseline(chains=4096, steps=3):
                       (steps, chains)}
 
 
-def mc_bench(v, grp, reps=3):
-    """MC proposals/sec: chains sharded over ranks with no collective; the accept uniforms are ONE PCG64
-    stream sliced per rank, so decisions do not depend on the rank count."""
+def mc_flips_vs_oracle(v, model, chains=1024, steps=20):
+    """Decisions of the device path against the oracle restatement of mcmc.py on a small sample of the job (same noise,
+    same PCG64 columns): number of chains whose decision trace differs anywhere (tracked in the bench line)."""
+    from oracle import mcmc as omc
+    from oracle import vae as ovae
+    P = ovae.init_vae(2003, dx=6, dz=2, hidden=200, prior='normal')
+    theta = np.concatenate([a.reshape(-1) for W, b in P['enc'] + P['dec'] for a in (W, b)]).astype(np.float32)
+    f = model.fused()
+    saved = f.theta.numpy().copy()
+    c = v._abi.ctx()
+    c.lib.vms_memcpy_h2d(f.theta.ptr, theta.ctypes.data, theta.nbytes, c.stream)
+    c.synchronize()
+    x0 = np.random.default_rng(4001).standard_normal((MC_CHAINS, 6), dtype=np.float32)[:chains]
+    rng = np.random.default_rng(777)
+    noise = np.empty((steps, chains, 10), np.float32)
+    for s in range(steps):
+        noise[s, :, :2] = rng.standard_normal((chains, 2), dtype=np.float32)
+        noise[s, :, 2:4] = rng.standard_normal((chains, 2), dtype=np.float32)
+        noise[s, :, 4:] = rng.standard_normal((chains, 6), dtype=np.float32)
+    mc = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=4002, stream_layout=(0, MC_CHAINS))
+    mc.run_fused(x0, n_steps=steps, noise=noise, trace=True)
+    acc_d = mc._last_trace['acc'].astype(bool)
+    u = np.random.default_rng(4002).random(size=(steps, MC_CHAINS))[:, :chains]
+
+    class Cols(object):
+        s = 0
+
+        def random(self, size):
+            self.s += 1
+            return u[self.s - 1]
+
+    ovm, cols = omc.OracleVAE(P, noise_seed=777), Cols()
+    xo, eo = x0.copy(), None
+    acc_o = np.empty((steps, chains), bool)
+    for s in range(steps):
+        xo, eo, acc_o[s] = omc.single_step(ovm, omc.quadratic_energy, cols, xo, eo)
+    c.lib.vms_memcpy_h2d(f.theta.ptr, saved.ctypes.data, saved.nbytes, c.stream)
+    c.synchronize()
+    return {'chains': chains, 'steps': steps, 'flipped_chains': int((acc_d != acc_o).any(axis=0).sum()),
+            'accepted_device': int(acc_d.sum()), 'accepted_oracle': int(acc_o.sum()),
+            'host_stream_reruns': int(mc.host_stream_reruns)}
+
+
+def mc_bench(v, grp, ffma_peak, reps=3):
+    """MC proposals/sec: chains sharded over ranks with no collective; the accept uniforms are ONE PCG64 stream
+    whose columns every rank regenerates on the device for its own chains, and the sampling noise is keyed by the global
+    chain index, so decisions do not depend on the rank count."""
     from vaemolsim_b200 import parallel
     c = v._abi.ctx()
     lo, hi = parallel.shard_rows(MC_CHAINS, grp.rank, grp.world)
     B = hi - lo
     model = build_model(v, WORKLOADS['c1'], 4096)
-    mc = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=4002)
+    mc = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=4002, stream_layout=(lo, MC_CHAINS))
     if mc._fused_plan() is None:
         raise RuntimeError('bench: the fused MC plan is unavailable')
     x0 = np.random.default_rng(4001).standard_normal((MC_CHAINS, 6), dtype=np.float32)[lo:hi]
-    t_rng = time.perf_counter()
-    log_u = np.ascontiguousarray(np.log(np.random.default_rng(4002).random(size=(MC_STEPS, MC_CHAINS)))[:, lo:hi])
-    t_rng = time.perf_counter() - t_rng
-    # device-resident leg: chain state and the uniforms live in HBM; one launch = MC_STEPS steps of B chains
-    xd, lud = v.Tensor.from_numpy(np.ascontiguousarray(x0)), v.Tensor.from_numpy(log_u)
-    xd, ed = mc.run_fused(None, n_steps=MC_STEPS, configs_dev=xd, log_u_dev=lud)  # warm-up (also computes E)
+    # device-resident leg: chain state lives in HBM, uniforms and noise are generated in the kernel; one launch = MC_STEPS
+    # steps of B chains
+    xd = v.Tensor.from_numpy(np.ascontiguousarray(x0))
+    xd, ed = mc.run_fused(None, n_steps=MC_STEPS, configs_dev=xd)  # warm-up (also computes E)
     for _ in range(2):
-        mc.run_fused(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed, log_u_dev=lud)
+        mc.run_fused(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed)
     ev = Events(c, reps)
     grp.barrier()
     c.synchronize()
     l0 = v._abi.launch_count()
     for i in range(reps):
         ev.record(2 * i)
-        mc.run_fused(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed, log_u_dev=lud)
+        mc.run_fused(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed)
         ev.record(2 * i + 1)
     c.synchronize()
     grp.barrier()
     launches = v._abi.launch_count() - l0
     dev_ms = grp.max(sum(ev.elapsed_ms(2 * i, 2 * i + 1) for i in range(reps)))
+    uncertain = mc.uncertain()
     mc.sync_counters()
     acc_rate = mc.acceptance_rate
-    # end to end through the public API: MCMC.run(configs, n_steps) from host arrays -- host PCG64 + log for the
-    # uniforms (mcmc.py:119), H2D of x / log u, the launch, D2H of x / E
-    mc2 = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=4002)
+    # end to end through the public API: MCMC.run(configs, n_steps) from host arrays -- H2D of x, the launch(es), D2H of
+    # x / E and of the counters
+    mc2 = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=4002, stream_layout=(lo, MC_CHAINS))
     mc2.run(x0, n_steps=2)
     grp.barrier()
     t0 = time.perf_counter()
@@ -376,22 +515,27 @@ def mc_bench(v, grp, reps=3):
         xe, ee = mc2.run(x0, n_steps=MC_STEPS)
     e2e_s = grp.max(time.perf_counter() - t0)
     tot = MC_CHAINS * MC_STEPS * reps
-    return {'metric': 'MC proposals/sec', 'value': tot / (dev_ms * 1e-3), 'unit': 'proposals/s', 'workload': MC_LABEL,
-            'chains_global': MC_CHAINS, 'chains_per_gpu': B, 'steps_per_launch': MC_STEPS, 'launches_timed': reps,
-            'scaling': 'strong (65,536 chains split over the GPUs, no data-path collective)',
-            'ms_per_mc_step': dev_ms / (reps * MC_STEPS), 'gpu_launches': int(launches), 'acceptance_rate': acc_rate,
-            'e2e': {'value': tot / e2e_s, 'unit': 'proposals/s', 'h2d_bytes_per_step': int(B * 8 + B * 24 / MC_STEPS),
-                    'd2h_bytes_per_step': int(B * 32 / MC_STEPS), 'ms_per_mc_step': e2e_s / (reps * MC_STEPS) * 1e3,
-                    'api': 'MCMC.run(configs, n_steps=%d) from host arrays' % MC_STEPS,
-                    'note': 'includes NumPy PCG64 + log of the accept uniforms on the host (%.1f ms per %d x %d block '
-                            'on this box): the stream is kept on the host so decisions stay bit-identical to the '
-                            'reference under the same seed' % (t_rng * 1e3, MC_STEPS, B)},
-            'algorithmic_flop_per_proposal': 19200,
-            'tflops_fp32': tot * 19200 / (dev_ms * 1e-3) / 1e12}
+    tflops = tot * 19200 / (dev_ms * 1e-3) / 1e12
+    res = {'metric': 'MC proposals/sec', 'value': tot / (dev_ms * 1e-3), 'unit': 'proposals/s', 'workload': MC_LABEL,
+           'chains_global': MC_CHAINS, 'chains_per_gpu': B, 'steps_per_launch': MC_STEPS, 'launches_timed': reps,
+           'scaling': 'strong (65,536 chains split over the GPUs, no data-path collective)',
+           'ms_per_mc_step': dev_ms / (reps * MC_STEPS), 'gpu_launches': int(launches), 'acceptance_rate': acc_rate,
+           'uniform_stream': 'NumPy PCG64 regenerated on the device (per-chain LCG jump-ahead), uncertain decisions: %d, '
+                             'host-stream re-runs: %d' % (uncertain, mc2.host_stream_reruns),
+           'e2e': {'value': tot / e2e_s, 'unit': 'proposals/s', 'h2d_bytes_per_step': int(B * 24 / MC_STEPS),
+                   'd2h_bytes_per_step': int(B * 32 / MC_STEPS), 'ms_per_mc_step': e2e_s / (reps * MC_STEPS) * 1e3,
+                   'api': 'MCMC.run(configs, n_steps=%d) from host arrays' % MC_STEPS},
+           'roofline': {'bound': 'ffma', 'kernel': 'mc_chain_kernel', 'achieved': tflops / grp.world, 'peak': ffma_peak,
+                        'unit': 'TFLOP/s', 'frac': tflops / grp.world / ffma_peak, 'traffic': None,
+                        'algorithmic_flop_per_proposal': 19200,
+                        'peak_kind': 'FP32 FFMA issue peak measured in this run (csrc/probe.cu)'},
+           'tflops_fp32': tflops}
+    if grp.rank == 0:
+        res['flips_vs_oracle'] = mc_flips_vs_oracle(v, model)
+    return res
 
 
-
-def large_batch_leg(v, w, opt, grp, collective='auto', global_batch=262144, steps=5):
+def large_batch_leg(v, w, opt, grp, peaks, collective='auto', global_batch=262144, steps=5):
     """C5 (BASELINE.json configs[4]: data-parallel training, GLOBAL batch 262,144): every rank takes 262,144 / N rows; one
     step = ELBO forward + backward on the shard (auto mode: the tensor-core plan at these sizes) + the gradient exchange
     (N > 1: the fused peer-memory allreduce + Adam kernel, NCCL fallback) + Adam.  Strong scaling.  Device-resident
@@ -406,15 +550,12 @@ def large_batch_leg(v, w, opt, grp, collective='auto', global_batch=262144, step
     rng = parallel.global_row_seed(77, lo)
     x = v.Tensor.from_numpy(rng.standard_normal((batch, w['dx']), dtype=np.float32))
     e = v.Tensor.from_numpy(rng.standard_normal((batch, w['dz']), dtype=np.float32))
-    peer = gt = None
-    if world > 1:
-        if collective in ('auto', 'peer'):
-            try:
-                peer = parallel.PeerExchange(grp, f.n_params)
-            except Exception as ex:
-                sys.stderr.write('bench (C5 leg): peer exchange unavailable (%s); using NCCL\n' % ex)
-        if peer is None:
-            gt, _ = grp.wrap_device_buffer(f.grad.ptr, f.n_params, c.stream)
+    peer = None
+    if world > 1 and collective in ('auto', 'peer'):
+        try:
+            peer = parallel.PeerExchange(grp, f.n_params)
+        except Exception as ex:
+            sys.stderr.write('bench (C5 leg): peer exchange unavailable (%s); using NCCL\n' % ex)
 
     def step():
         if world == 1:
@@ -424,7 +565,7 @@ def large_batch_leg(v, w, opt, grp, collective='auto', global_batch=262144, step
             peer.allreduce_adam(f, opt)
         else:
             f.forward_backward(x, e)
-            grp.allreduce_sum_(gt, host_sync=c.synchronize)
+            grp.allreduce_sum_device_(f.grad.ptr, f.n_params, c.stream)
             f.adam_step(opt, grad_scale=1.0 / world)
 
     for _ in range(3):
@@ -449,108 +590,87 @@ def large_batch_leg(v, w, opt, grp, collective='auto', global_batch=262144, step
     # forward 7 k-steps of 64 x 96 x 16, backward the same recompute + 6 k-steps of 64 x 112 x 16 + 4 of 128 x 96 x 16
     mma = lambda m, n, k: 2.0 * m * n * k
     per_tile = 6 * (2 * 7 * mma(64, 96, 16) + 6 * mma(64, 112, 16) + 4 * mma(128, 96, 16))
-    mma_flop = per_tile * ((batch + 63) // 64) * w['num_blocks'] * world if f.path(batch) == 'tensor-core' else 0.0
-    try:
-        bf16_peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('bf16_tflops', 1590.0))
-    except (OSError, ValueError):
-        bf16_peak = 1590.0
-    tensor = {'bound': 'tensor', 'kernel': 'flow_tc_kernel<fwd|bwd> (8 launches per step)', 'unit': 'TFLOP/s',
-              'bf16_mma_flop_per_step': mma_flop, 'achieved_over_whole_step': mma_flop / (ms * 1e-3) / 1e12 / world,
-              'peak': bf16_peak, 'frac_over_whole_step': mma_flop / (ms * 1e-3) / 1e12 / world / bf16_peak,
-              'note': 'MMA FLOPs actually issued (3 x BF16 split: six bf16 MMAs per float32 product) divided by the WHOLE '
-                      'step time per GPU -- a lower bound of the kernels\' own rate (they are ~80 % of the step); ncu: '
-                      'tensor pipe active 15-18 % (profiles/r01_ncu_flow_tc_pipelined.txt)'}
+    mma_flop = per_tile * ((batch + 63) // 64) * w['num_blocks'] if f.path(batch) == 'tensor-core' else 0.0
+    tfl = batch * flop / (ms * 1e-3) / 1e12  # per GPU, algorithmic (float32-equivalent)
+    bf16_peak = peaks['bf16_tflops_sustained']
+    roof = {'bound': 'tensor', 'kernel': 'flow_tc_kernel<fwd|bwd> (8 launches per step, ~80 % of it)', 'unit': 'TFLOP/s',
+            'achieved': tfl, 'peak': bf16_peak, 'frac': tfl / bf16_peak, 'traffic': None,
+            'peak_kind': 'measured cuBLAS bf16, sustained (MEASURED_PEAKS.json): the kernels run inside a long step',
+            'issued_bf16_mma_tflops_over_whole_step': mma_flop / (ms * 1e-3) / 1e12,
+            'issued_frac_of_peak_over_whole_step': mma_flop / (ms * 1e-3) / 1e12 / bf16_peak,
+            'note': 'achieved = algorithmic float32 FLOPs (259,200 per configuration) per GPU over the WHOLE step; issued = the '
+                    'bf16 MMAs actually launched (3 x BF16 split: six per float32 product, padded tiles)'}
     return {'workload': 'C5: same model, GLOBAL batch %d over %d GPU(s) (%d rows per GPU), fwd + bwd + gradient exchange '
                         '+ Adam' % (global_batch, world, batch),
-            'scaling': 'strong', 'ms_per_step': ms, 'plan': f.path(batch), 'configs_per_s': global_batch / (ms * 1e-3),
+            'scaling': 'strong', 'ms_per_step': ms, 'plan': f.path(batch), 'value': global_batch / (ms * 1e-3),
+            'unit': UNIT, 'configs_per_s': global_batch / (ms * 1e-3),
             'collective': 'none' if world == 1 else ('peer kernel' if peer is not None else 'nccl'),
-            'tflops_fp32': global_batch * flop / (ms * 1e-3) / 1e12, 'roofline': tensor,
-            'valid': not (timed_out or tc_bad),
-            'last_loss': float(f.scalars.numpy()[0])}
+            'tflops_fp32': global_batch * flop / (ms * 1e-3) / 1e12, 'roofline': roof,
+            'valid': not (timed_out or tc_bad), 'last_loss': float(f.scalars.numpy()[0])}
 
 
-def run_b200(args, w):
-    import vaemolsim_b200 as v
+# ---------------------------------------------------------------------------------------------------- ELBO legs (C2, C1)
+def elbo_leg(v, w, grp, batch, K, W, collective, sampler=None):
+    """One ELBO training workload: `value` (inputs resident in HBM, per-step CUDA events, L2 flushed between steps) and
+    `e2e` (the public training loop from pinned host memory, per-step H2D of x / eps and read-back of the loss)."""
     from vaemolsim_b200 import parallel
-    grp = parallel.Group()
-    rank, world = grp.rank, grp.world
     c = v._abi.ctx()
     lib = c.lib
-    if args.mc_only:
-        line = mc_bench(v, grp)
-        if rank == 0:
-            print(json.dumps(line), flush=True)
-        grp.close()
-        return
-    batch = args.batch or w['batch']
-    K, W = args.steps, args.warmup
+    rank, world = grp.rank, grp.world
     model = build_model(v, w, batch)
     f = model.fused(batch)
     opt = model.optimizer
     # synthetic inputs keyed by the GLOBAL row index of this rank's shard (results independent of the rank count)
-    row0 = rank * batch
-    rng = parallel.global_row_seed(1001, row0)
+    rng = parallel.global_row_seed(1001, rank * batch)
     n_sets = 4  # rotate a few input sets so consecutive steps do not see identical data
-    xs_host = [pinned_array(lib, (batch, w['dx'])) for _ in range(n_sets)]
-    es_host = [pinned_array(lib, (batch, w['dz'])) for _ in range(n_sets)]
-    for a in xs_host + es_host:
-        a[...] = rng.standard_normal(a.shape, dtype=np.float32)
-    xs = [v.Tensor.from_numpy(a) for a in xs_host]
-    es = [v.Tensor.from_numpy(a) for a in es_host]
+    xh = pinned_array(lib, (n_sets * batch, w['dx']))
+    eh = pinned_array(lib, (n_sets * batch, w['dz']))
+    xh[...] = rng.standard_normal(xh.shape, dtype=np.float32)
+    eh[...] = rng.standard_normal(eh.shape, dtype=np.float32)
+    xs = [v.Tensor.from_numpy(xh[k * batch:(k + 1) * batch]) for k in range(n_sets)]
+    es = [v.Tensor.from_numpy(eh[k * batch:(k + 1) * batch]) for k in range(n_sets)]
     flush = v.Tensor((64 << 20, ))  # 256 MiB float32 > 126 MB L2
-    gt = ext = peer = None
+    peer = None
+    note = None
     if world > 1:
-        if args.collective in ('auto', 'peer'):
+        if collective in ('auto', 'peer'):
             try:
                 peer = parallel.PeerExchange(grp, f.n_params)
             except Exception as e:  # no P2P mapping between the ranks' GPUs: NCCL path
-                if args.collective == 'peer':
+                if collective == 'peer':
                     raise
                 sys.stderr.write('bench: peer exchange unavailable (%s); using NCCL\n' % e)
-        # all ranks must agree on the path
-        if grp.sum(1.0 if peer is not None else 0.0) != world:
+        if grp.sum(1.0 if peer is not None else 0.0) != world:  # all ranks must agree on the path
             peer = None
-        if peer is None:
-            gt, ext = grp.wrap_device_buffer(f.grad.ptr, f.n_params, c.stream)
 
     def step(i):
         if world == 1:
             f.train_step(xs[i % n_sets], es[i % n_sets], opt)  # forward + backward + Adam: 2 launches
-            return
-        if peer is not None:
+        elif peer is not None:
             # gradient straight into this step's slot of the exchange buffer, then ONE kernel: flags + peer reads over
             # NVLink + rank-ordered sum + Adam
             f.forward_backward(xs[i % n_sets], es[i % n_sets], grad_ptr=peer.next_slot())
             peer.allreduce_adam(f, opt)
-            return
-        f.forward_backward(xs[i % n_sets], es[i % n_sets])
-        grp.allreduce_sum_(gt, host_sync=c.synchronize)  # fallback: NCCL allreduce, host-synchronised
-        f.adam_step(opt, grad_scale=1.0 / world)
+        else:
+            f.forward_backward(xs[i % n_sets], es[i % n_sets])
+            grp.allreduce_sum_device_(f.grad.ptr, f.n_params, c.stream)  # fallback: NCCL allreduce on the library's stream
+            f.adam_step(opt, grad_scale=1.0 / world)
 
-    sampler = ClockSampler(c.device)
-    if rank == 0:  # one nvidia-smi loop per job (rank 0's GPU), not one per rank
-        sampler.start()
     for i in range(max(W, 3)):
         step(i)
     c.synchronize()
-    peer_note = None
     if peer is not None and grp.sum(1.0 if peer.timed_out() else 0.0) > 0.0:
-        # a rank gave up waiting for a peer's flag during warm-up (the kernel's bound): do not spend the timed region on
-        # 2 s time-outs -- finish on the NCCL exchange and say so
-        peer_note = 'peer exchange timed out during warm-up; NCCL fallback used'
-        sys.stderr.write('bench: %s\n' % peer_note)
+        note = 'peer exchange timed out during warm-up; NCCL fallback used'
+        sys.stderr.write('bench: %s\n' % note)
         peer.close()
         peer = None
-        gt, ext = grp.wrap_device_buffer(f.grad.ptr, f.n_params, c.stream)
-
-    # ---- timed region 1: inputs resident in HBM, per-step CUDA events, L2 flushed (untimed) between steps
+    # ---- timed region 1
     ev = Events(c, K)
     lib.vms_elbo_plan_set_timing(f.handle, K)
     grp.barrier()
     c.synchronize()
     launches0 = v._abi.launch_count()
     t_clock0 = time.perf_counter()
-    wall0 = time.perf_counter()
     for i in range(K):
         lib.vms_memset(flush.ptr, 0, flush.nbytes, c.stream)
         ev.record(2 * i)
@@ -558,70 +678,51 @@ def run_b200(args, w):
         ev.record(2 * i + 1)
     c.synchronize()
     grp.barrier()
-    wall1 = time.perf_counter()
+    wall = time.perf_counter() - t_clock0
     launches = v._abi.launch_count() - launches0
-    dev_ms = sum(ev.elapsed_ms(2 * i, 2 * i + 1) for i in range(K))
-    dev_ms = grp.max(dev_ms)
+    dev_ms = grp.max(sum(ev.elapsed_ms(2 * i, 2 * i + 1) for i in range(K)))
     k_ms, k_n = C.c_double(0), C.c_int(0)
     lib.vms_elbo_plan_kernel_ms(f.handle, C.byref(k_ms), C.byref(k_n))
     lib.vms_elbo_plan_set_timing(f.handle, 0)
-    ms_per_step = dev_ms / K
-    value = world * batch * K / (dev_ms * 1e-3)
-
-    # ---- timed region 2: end to end through the public API from pinned host memory
-    def e2e_step(i):
-        xd = v.Tensor.from_numpy(xs_host[i % n_sets])  # H2D (pinned)
-        ed = v.Tensor.from_numpy(es_host[i % n_sets])
-        if world == 1:
-            f.train_step(xd, ed, opt)
-        elif peer is not None:
-            f.forward_backward(xd, ed, grad_ptr=peer.next_slot())
-            peer.allreduce_adam(f, opt)
-        else:
+    # ---- timed region 2: end to end through the public training loop (`VAE.fit` -> FusedELBO.train_loop): every step's x
+    # and eps leave PINNED host memory on a copy stream while the previous step trains, every step's {loss, nll, kl} is
+    # read back (ring of 8 steps); N > 1: the same loop with the peer exchange inside
+    exchange = peer
+    if world > 1 and peer is None:
+        e2e_api = 'FusedELBO.forward_backward + NCCL allreduce + Adam per step (synchronous), H2D / D2H per step'
+        def e2e_step(i):
+            xd, ed = v.Tensor.from_numpy(xh[(i % n_sets) * batch:(i % n_sets + 1) * batch]), \
+                v.Tensor.from_numpy(eh[(i % n_sets) * batch:(i % n_sets + 1) * batch])
             f.forward_backward(xd, ed)
-            grp.allreduce_sum_(gt, host_sync=c.synchronize)
+            grp.allreduce_sum_device_(f.grad.ptr, f.n_params, c.stream)
             f.adam_step(opt, grad_scale=1.0 / world)
-        return f.scalars.numpy()  # D2H of {loss, nll, kl}: synchronises the step
-
-    e2e_api = 'FusedELBO.train_step (the call behind VAE.train_step / VAE.fit)'
-    if world == 1:
-        # the public training loop (`VAE.fit` -> FusedELBO.train_loop): every step's x and eps leave PINNED host memory on
-        # a copy stream while the previous step trains, every step's {loss, nll, kl} is read back (ring of 8 steps)
-        e2e_api = 'VAE.fit inner loop (FusedELBO.train_loop): per-step H2D of x / eps, step, loss read-back, pipelined'
-        xh = pinned_array(lib, (n_sets * batch, w['dx']))
-        eh = pinned_array(lib, (n_sets * batch, w['dz']))
-        for k in range(n_sets):
-            xh[k * batch:(k + 1) * batch] = xs_host[k]
-            eh[k * batch:(k + 1) * batch] = es_host[k]
-        f.train_loop(xh, opt, batch, eps_host=eh, n_steps=8)
-        c.synchronize()
-        t0 = time.perf_counter()
-        scal = f.train_loop(xh, opt, batch, eps_host=eh, n_steps=K)
-        c.synchronize()
-        e2e_s = time.perf_counter() - t0
-        last = scal[-1]
-    else:
+            return f.scalars.numpy()
         for i in range(3):
             e2e_step(i)
         grp.barrier()
-        c.synchronize()
         t0 = time.perf_counter()
         for i in range(K):
             last = e2e_step(i)
+        e2e_s = grp.max(time.perf_counter() - t0)
+    else:
+        e2e_api = ('VAE.fit inner loop (FusedELBO.train_loop): per-step H2D of x / eps, step%s, loss read-back, pipelined' %
+                   ('' if world == 1 else ' + peer-memory gradient exchange'))
+        f.train_loop(xh, opt, batch, eps_host=eh, n_steps=8, exchange=exchange)
+        c.synchronize()
+        grp.barrier()
+        t0 = time.perf_counter()
+        scal = f.train_loop(xh, opt, batch, eps_host=eh, n_steps=K, exchange=exchange)
         c.synchronize()
         e2e_s = grp.max(time.perf_counter() - t0)
-    e2e_value = world * batch * K / e2e_s
-    # keep the same load going until the clock sampler has a few samples inside a loaded window
-    # (the decision is rank 0's, shared with every rank: step() contains the gradient exchange when N > 1, so all ranks
-    # must run the same number of steps)
-    t_load = time.perf_counter()
-    while grp.max(1.0 if rank == 0 and sampler.count() < 8 and time.perf_counter() - t_load < 3.0 else 0.0) > 0.0:
-        for i in range(50):
-            step(i)
-        c.synchronize()
-    t_clock1 = time.perf_counter()
-    clocks = sampler.stop(t_clock0, t_clock1)
-
+        last = scal[-1]
+    if sampler is not None:
+        # keep the same load going until the clock sampler has a few samples inside a loaded window (rank 0 decides for
+        # all ranks: step() contains the gradient exchange when N > 1, so every rank must run the same number of steps)
+        t_load = time.perf_counter()
+        while grp.max(1.0 if rank == 0 and sampler.count() < 8 and time.perf_counter() - t_load < 3.0 else 0.0) > 0.0:
+            for i in range(50):
+                step(i)
+            c.synchronize()
     replicas_ok = None
     if world > 1:
         # replicas must hold bit-identical parameters after the run (same reduced gradient on every rank)
@@ -630,81 +731,156 @@ def run_b200(args, w):
         if peer is not None:
             replicas_ok = replicas_ok and grp.sum(1.0 if peer.timed_out() else 0.0) == 0.0
             peer.close()
-    mc_line = None if args.no_extras else mc_bench(v, grp)
-    lb_line = None
+    return dict(model=model, f=f, opt=opt, ms_per_step=dev_ms / K, value=world * batch * K / (dev_ms * 1e-3),
+                e2e_value=world * batch * K / e2e_s, e2e_ms=e2e_s / K * 1e3, e2e_api=e2e_api, last_loss=float(last[0]),
+                launches=int(launches), kernel_ms=k_ms.value, kernel_launches=k_n.value, wall=wall, t0=t_clock0,
+                t1=time.perf_counter(), path=f.path(batch), h2d=int(batch * (w['dx'] + w['dz']) * 4),
+                collective=('none' if world == 1 else
+                            'one fused kernel per step: NVLink peer-memory gradient allreduce + Adam (csrc/peer.cu)'
+                            if exchange is not None else 'one NCCL allreduce(sum) of the flat gradient per step'),
+                replicas_ok=replicas_ok, note=note, tc_bad=bool(f.tc_status()))
+
+
+def tcf_issued_mma_flop(w, batch, rows=32):
+    """bf16 MMA FLOPs the whole-step tensor-core kernel issues per launch (elbo_tcf.cu: six MMAs per float32 product; per
+    32-row tile and block: forward 7 k-steps of 64 x 96 x 16, backward the same recompute + 6 k-steps of 64 x 112 x 16 +
+    rows / 16 k-steps of 128 x 96 x 16)."""
+    mma = lambda m, n, k: 2.0 * m * n * k
+    per_tile = 6 * (2 * 7 * mma(64, 96, 16) + 6 * mma(64, 112, 16) + (rows // 16) * mma(128, 96, 16))
+    return per_tile * ((batch + rows - 1) // rows) * w['num_blocks']
+
+
+def run_b200(args, w):
+    import vaemolsim_b200 as v
+    from vaemolsim_b200 import parallel
+    grp = parallel.Group()
+    rank, world = grp.rank, grp.world
+    c = v._abi.ctx()
+    if args.mc_only:
+        line = mc_bench(v, grp, measured_peaks(v)['fp32_ffma_tflops'])
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        grp.close()
+        return
+    batch = args.batch or w['batch']
+    K, W = args.steps, args.warmup
+    sampler = ClockSampler(c.device)
+    if rank == 0:  # one nvidia-smi loop per job (rank 0's GPU), not one per rank
+        sampler.start()
+    r = elbo_leg(v, w, grp, batch, K, W, args.collective, sampler)
+    clocks = sampler.stop(r['t0'], r['t1'])
+    f = r['f']
+    legs, micro, peaks = {}, None, None
     if not args.no_extras:
+        peaks = measured_peaks(v)
         try:
-            lb_line = large_batch_leg(v, w, opt, grp, args.collective)
-        except Exception as ex:  # the headline line must survive a failure of this extra leg
-            lb_line = {'error': '%s: %s' % (type(ex).__name__, ex)}
-            sys.stderr.write('bench (C5 leg) failed: %s\n' % lb_line['error'])
+            legs['c4a_mc'] = mc_bench(v, grp, peaks['fp32_ffma_tflops'])
+        except Exception as ex:  # the headline line must survive a failure of an extra leg
+            legs['c4a_mc'] = {'error': '%s: %s' % (type(ex).__name__, ex)}
+        try:
+            legs['c5'] = large_batch_leg(v, w, r['opt'], grp, peaks, args.collective)
+        except Exception as ex:
+            legs['c5'] = {'error': '%s: %s' % (type(ex).__name__, ex)}
+        try:
+            legs['c3'] = c3_leg(v, grp, peaks['hbm_gbs'])
+        except Exception as ex:
+            legs['c3'] = {'error': '%s: %s' % (type(ex).__name__, ex)}
+        try:
+            if args.workload != 'c1':
+                r1 = elbo_leg(v, WORKLOADS['c1'], grp, WORKLOADS['c1']['batch'], min(K, 100), 5, args.collective)
+                k1 = r1['kernel_ms'] / max(r1['kernel_launches'], 1)
+                tfl1 = 28800 * WORKLOADS['c1']['batch'] / (k1 * 1e-3) / 1e12 if k1 else None
+                legs['c1'] = {'metric': METRIC, 'value': r1['value'], 'unit': UNIT, 'workload': WORKLOADS['c1']['label'],
+                              'ms_per_step': r1['ms_per_step'], 'scaling': 'weak', 'plan': r1['path'],
+                              'e2e': {'value': r1['e2e_value'], 'unit': UNIT, 'ms_per_step': r1['e2e_ms'],
+                                      'h2d_bytes_per_step': r1['h2d'], 'd2h_bytes_per_step': 16, 'api': r1['e2e_api']},
+                              'roofline': {'bound': 'ffma', 'kernel': 'elbo_fused_kernel<bwd>', 'achieved': tfl1,
+                                           'peak': peaks['fp32_ffma_tflops'], 'unit': 'TFLOP/s',
+                                           'frac': tfl1 / peaks['fp32_ffma_tflops'] if tfl1 else None, 'traffic': None,
+                                           'launch_ms': k1, 'algorithmic_flop_per_launch': 28800 * WORKLOADS['c1']['batch']}}
+                if rank == 0:
+                    cv, cs = time_cpu(WORKLOADS['c1'], WORKLOADS['c1']['batch'], 10, 2)
+                    legs['c1']['cpu_baseline'] = {'value': cv, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
+                                                  'sample': '10 steps of 4096 configs, NumPy oracle', 'ms_per_step': cs * 1e3}
+        except Exception as ex:
+            legs['c1'] = {'error': '%s: %s' % (type(ex).__name__, ex)}
     if rank != 0:
         grp.close()
         return
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
-        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
+        'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': w['label'], 'global_batch': world * batch, 'params': f.n_params,
-                   'parallelism': 'dp%d' % world if world > 1 else 'single',
-                   'collective': ('none' if world == 1 else
-                                  'one fused kernel per step: NVLink peer-memory gradient allreduce + Adam (csrc/peer.cu)'
-                                  if peer is not None else 'one NCCL allreduce(sum) of the flat gradient per step'),
+        'config': {'workload': w['label'], 'global_batch': world * batch, 'params': f.n_params, 'plan': r['path'],
+                   'parallelism': 'dp%d' % world if world > 1 else 'single', 'collective': r['collective'],
                    'l2': 'flushed between timed steps (256 MiB memset, outside the per-step events)',
                    'timing': 'sum of per-step CUDA-event intervals on the launching stream, max over ranks',
-                   'wall_s_timed_region_incl_flush': wall1 - wall0},
-        'e2e': {'value': e2e_value, 'unit': UNIT,
-                'h2d_bytes_per_step': int(xs_host[0].nbytes + es_host[0].nbytes), 'd2h_bytes_per_step': 16,
-                'ms_per_step': e2e_s / K * 1e3, 'api': e2e_api,
+                   'wall_s_timed_region_incl_flush': r['wall']},
+        'e2e': {'value': r['e2e_value'], 'unit': UNIT, 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': 16,
+                'ms_per_step': r['e2e_ms'], 'api': r['e2e_api'],
                 'note': 'back-to-back steps (L2 stays warm across steps), whereas `value` flushes L2 before every timed step: '
                         'e2e can therefore exceed `value`; every step still pays its own H2D (x, eps) and loss read-back',
-                'last_loss': float(last[0])},
-        'gpu_launches': int(launches),
+                'last_loss': r['last_loss']},
+        'gpu_launches': r['launches'],
         'clocks': clocks,
     }
-    if replicas_ok is not None:
-        line['config']['replicas_bit_identical'] = bool(replicas_ok)
-    if peer_note:
-        line['config']['note'] = peer_note
+    if r['replicas_ok'] is not None:
+        line['config']['replicas_bit_identical'] = bool(r['replicas_ok'])
+    if r['note']:
+        line['config']['note'] = r['note']
+    if r['tc_bad']:
+        line['config']['tensor_core_wait_timeout'] = True
     if not args.no_extras:
-        micro, peak, peak_kind = kernel_microbench(v, w, batch)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except (OSError, ValueError):
-            pass
         flop_per_config = 259200 if w['prior'] != 'normal' else 28800  # SURVEY 8d: GEMM FLOPs fwd + bwd per configuration
-        if k_n.value:
-            launch_ms = k_ms.value / k_n.value
+        traffic = load_json(os.path.join('profiles', 'r02_traffic.json'))
+        if r['kernel_launches']:
+            launch_ms = r['kernel_ms'] / r['kernel_launches']
             tflops = flop_per_config * batch / (launch_ms * 1e-3) / 1e12
-            tens_peak = float(peaks.get('bf16_tflops', 1590.0))
-            line['roofline'] = {
-                'bound': 'tensor', 'kernel': 'elbo_fused_kernel<bwd>', 'achieved': tflops, 'peak': tens_peak,
-                'unit': 'TFLOP/s', 'frac': tflops / tens_peak, 'traffic': None,
-                'peak_kind': ('measured bf16 dense, burst (MEASURED_PEAKS.json)' if 'bf16_tflops' in peaks else
-                              'fallback (B200_PROFILING.md)'),
-                'algorithmic_flop_per_launch': flop_per_config * batch, 'launch_ms': launch_ms, 'launches_timed': k_n.value,
-                'share_of_step': launch_ms / ms_per_step,
-                'fp32_ffma_peak_nominal_tflops': 74.4, 'frac_of_fp32_ffma': tflops / 74.4,
-                'note': 'the step is one FP32-FFMA kernel (float32 parity forbids plain TF32 tensor-core inputs, DESIGN.md 6); '
-                        'it is bounded by per-phase latency at 32 rows per SM, not by a pipe: the math-pipe roofline is '
-                        'reported against the measured bf16 peak as the contract asks and against the nominal FP32 FFMA '
-                        'peak; HBM-bound kernels and their fractions of the measured copy peak are under "kernels"'}
+            tc = r['path'] == 'tensor-core-fused'
+            kname = 'tcf_kernel<96, true> (whole-step tcgen05 kernel, elbo_tcf.cu)' if tc else 'elbo_fused_kernel<bwd>'
+            peak = peaks['bf16_tflops'] if tc else peaks['fp32_ffma_tflops']
+            roof = {'bound': 'tensor' if tc else 'ffma', 'kernel': kname, 'achieved': tflops, 'peak': peak, 'unit': 'TFLOP/s',
+                    'frac': tflops / peak,
+                    'traffic': (traffic.get('tcf_kernel' if tc else 'elbo_fused_kernel') or {}).get('dram_bytes_per_launch'),
+                    'traffic_note': (traffic.get('tcf_kernel' if tc else 'elbo_fused_kernel') or {}).get('note'),
+                    'peak_kind': ('measured cuBLAS bf16 dense, burst (MEASURED_PEAKS.json)' if tc else
+                                  'FP32 FFMA issue peak measured in this run (csrc/probe.cu)'),
+                    'algorithmic_flop_per_launch': flop_per_config * batch, 'launch_ms': launch_ms,
+                    'launches_timed': r['kernel_launches'], 'share_of_step': launch_ms / r['ms_per_step'],
+                    'fp32_ffma_peak_measured_tflops': peaks['fp32_ffma_tflops'],
+                    'frac_of_fp32_ffma_measured': tflops / peaks['fp32_ffma_tflops']}
+            if tc:
+                issued = tcf_issued_mma_flop(w, batch) / (launch_ms * 1e-3) / 1e12
+                roof.update({'issued_bf16_mma_tflops': issued,
+                             'issued_frac_of_bf16_peak': issued / peaks['bf16_tflops'],
+                             'issued_frac_of_tcgen05_m64_n96_issue_peak': issued / peaks['tcgen05_bf16_m64_n96_tflops'],
+                             'note': 'achieved = ALGORITHMIC float32 FLOPs (259,200 per configuration) over the kernel time; the '
+                                     'kernel issues six bf16 MMAs per float32 product on 64-row tiles of which 32 rows are valid '
+                                     '(issued_*); batch 4096 = 128 tiles of a strictly sequential chain, so the kernel is bounded '
+                                     'by phase latency, not by the tensor pipe (ncu: profiles/r02_*)'})
+            line['roofline'] = roof
+        micro = kernel_microbench(v, w, batch, peaks['hbm_gbs'])
+        line['peaks'] = peaks
         line['roofline_hbm_kernels'] = {
-            'peak': peak, 'unit': 'GB/s', 'peak_kind': peak_kind,
+            'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'peak_kind': peaks['kind'],
             'rqs_forward@stream': micro['rqs_forward@stream']['frac'],
             'rqs_inverse@stream': micro['rqs_inverse@stream']['frac'],
             'rqs_backward@stream': micro['rqs_backward@stream']['frac'],
             'normal_log_prob@stream': micro['normal_log_prob@stream']['frac'],
-            'dist_select@C3': micro['dist_select@C3']['frac']}
+            'dist_select@C3': (legs.get('c3', {}).get('roofline') or {}).get('frac')}
         line['kernels'] = micro
-        line['large_batch'] = lb_line
-        line['mc'] = mc_line
-        line['mc']['cpu_baseline'] = mc_cpu_baseline()
-        rows = batch
-        cpu_val, cpu_sec = time_cpu(w, rows, 10, 2)
+        if 'error' not in legs.get('c4a_mc', {'error': 1}):
+            legs['c4a_mc']['cpu_baseline'] = mc_cpu_baseline()
+        line['legs'] = legs
+        # short per-leg summary (kept flat so that per-N records retain every leg's number)
+        line['leg_values'] = {k: {'value': d.get('value'), 'unit': d.get('unit'), 'e2e': (d.get('e2e') or {}).get('value'),
+                                  'roofline_frac': (d.get('roofline') or {}).get('frac')}
+                              for k, d in legs.items() if 'error' not in d}
+        line['mc'] = legs.get('c4a_mc')
+        line['large_batch'] = legs.get('c5')
+        cpu_val, cpu_sec = time_cpu(w, batch, 10, 2)
         line['cpu_baseline'] = {'value': cpu_val, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
-                                'sample': '10 steps of %d configs, NumPy oracle (ELBO fwd + analytic bwd + Adam)' % rows,
+                                'sample': '10 steps of %d configs, NumPy oracle (ELBO fwd + analytic bwd + Adam)' % batch,
                                 'ms_per_step': cpu_sec * 1e3}
     print(json.dumps(line), flush=True)
     grp.close()

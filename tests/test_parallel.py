@@ -39,7 +39,7 @@ sys.path.insert(0, %(root)r)
 from vaemolsim_b200 import parallel
 from oracle import vae as ovae
 
-grp = parallel.Group(backend='gloo')
+grp = parallel.Group(backend=%(backend)r)
 rank, world = grp.rank, grp.world
 assert world == 2
 # global batch of 64 configurations, sharded by rows; every rank builds the same model
@@ -51,6 +51,8 @@ P = ovae.cast_params(ovae.init_vae(3, prior='realnvp', hidden=16, flow_hidden=8,
 lo, hi = parallel.shard_rows(B, rank, world)
 out, G = ovae.elbo_backward(P, x[lo:hi], eps[lo:hi])
 g = ovae.flatten(ovae.grad_list(P, G)).astype(np.float32)
+parts = grp.all_gather_bytes(('rank%%d' %% rank).encode())
+assert parts == [b'rank0', b'rank1'], parts
 grp.allreduce_sum_numpy_(g)          # the one collective of the training step
 g = g / world                          # loss is a batch MEAN over equal shards (losses.py:253)
 full, Gf = ovae.elbo_backward(P, x, eps)
@@ -73,9 +75,11 @@ def _free_port():
 
 
 @pytest.mark.timeout(300)
-def test_gradient_allreduce_world2_gloo(tmp_path):
+@pytest.mark.parametrize('backend', ['socket', 'gloo'])
+def test_gradient_allreduce_world2(tmp_path, backend):
+    """world_size 2 on the CPU: the product's own socket rendezvous (no torch) and the torch.distributed gloo backend."""
     script = tmp_path / 'worker.py'
-    script.write_text(WORKER % {'root': ROOT})
+    script.write_text(WORKER % {'root': ROOT, 'backend': backend})
     port = _free_port()
     procs = []
     for rank in range(2):
