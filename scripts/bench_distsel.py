@@ -38,7 +38,7 @@ def main():
             ms = float(np.mean(ts[2:]))
             nbytes = B * (12 * N + 12 + k * 12 + (k * (4 * 2 + 4 * 2 + 4) if kw else 0))
             print('VMS_DISTSEL_STREAM=%s k=%d %-18s %.4f ms  %.0f GB/s  %.3f of 6544.7' % (
-                os.environ.get('VMS_DISTSEL_STREAM', '1'), k, tag, ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / 6544.7))
+                os.environ.get('VMS_DISTSEL_STREAM', '0'), k, tag, ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / 6544.7))
 
 
 if __name__ == '__main__':
