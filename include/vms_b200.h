@@ -418,6 +418,39 @@ vms_status vms_peer_allreduce_adam(int world, int rank, void* const* peer_bases,
                                    float grad_scale, float* theta, float* m, float* v, int64_t t, double lr, double beta1,
                                    double beta2, double eps, float* grad_out, vms_stream stream);
 
+/* ------------------------------------------------------------------------------- reverse mode of the op-by-op path
+ * What TF autodiff does for compositions outside the fused ELBO family (tests/test_models.py:189-262: von Mises encoder,
+ * periodic FCDeepNN, blockwise / autoregressive / MAF-flowed decoders; models.py:85-139 FlowModel).  The host keeps a tape of
+ * the kernels it launched (vaemolsim_b200/_autodiff.py) and replays it backwards through these entry points, the existing
+ * vms_dense_backward / vms_rqs_apply_backward / vms_normal_log_prob_backward, and vms_adam_step.  Every output ACCUMULATES.
+ *   vms_blockwise_log_prob_backward   d/dx and d/dparams of vms_blockwise_log_prob (Normal and von Mises dofs, atan2 /
+ *                                     softplus parameter transforms of dists.py:56-78 included); g_x / g_params nullable
+ *   vms_std_normal_log_prob_backward  g_x += -x g_lp
+ *   vms_blockwise_sample_backward     d z / d params of a reparameterised sample z (vms_blockwise_sample): Normal = pathwise;
+ *                                     von Mises = loc pathwise + tfp's IMPLICIT reparameterisation in the concentration,
+ *                                     -dF/dk / p(z) with F = von_mises_cdf (Hill's 20-term series below k = 10.5, corrected
+ *                                     Normal approximation above), as tfp von_mises.py `_von_mises_sample_bwd`
+ *   vms_periodic_featurise_backward   mappings.py:144-149: g_x += g_out[~periodic part], -sin x g_cos + cos x g_sin
+ *   vms_add_cols / vms_add_scalar / vms_mul_inplace / vms_sum_all   strided +=, dst += alpha * scalar[0] (scalar NULL: alpha),
+ *                                     dst *= src (MADE masks on kernel gradients), out[0] += alpha * sum(src) (fixed order)   */
+vms_status vms_blockwise_log_prob_backward(const float* x, int64_t ld_x, const float* params, int64_t ld_p, int64_t B, int D,
+                                           const int32_t* kind, const int32_t* loc_off, const int32_t* loc2_off,
+                                           const int32_t* scale_off, int scale_mode, const float* g_lp, float* g_x,
+                                           int64_t ld_gx, float* g_params, int64_t ld_gp, vms_stream stream);
+vms_status vms_std_normal_log_prob_backward(const float* x, int64_t ld_x, int64_t B, int D, const float* g_lp, float* g_x,
+                                            int64_t ld_gx, vms_stream stream);
+vms_status vms_blockwise_sample_backward(const float* params, int64_t ld_p, int64_t B, int D, const int32_t* kind,
+                                         const int32_t* loc_off, const int32_t* loc2_off, const int32_t* scale_off,
+                                         int scale_mode, const float* z, int64_t ld_z, const float* g_z, int64_t ld_gz,
+                                         float* g_params, int64_t ld_gp, vms_stream stream);
+vms_status vms_periodic_featurise_backward(const float* x, int64_t B, int D, const uint8_t* periodic, int n_periodic,
+                                           const float* g_out, float* g_x, vms_stream stream);
+vms_status vms_add_cols(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t B, int D, float alpha,
+                        vms_stream stream);
+vms_status vms_add_scalar(float* dst, int64_t n, const float* scalar, float alpha, vms_stream stream);
+vms_status vms_mul_inplace(float* dst, const float* src, int64_t n, vms_stream stream);
+vms_status vms_sum_all(const float* src, int64_t n, float alpha, float* out, vms_stream stream);
+
 /* ------------------------------------------------------------------------------- machine-peak probes (measurement aid)
  * The denominators of this repo's compute-bound roofline fractions, measured on the device they are quoted for
  * (BASELINE.md section 2 asks for them; `bench.py` runs them live and `scripts/measure_peaks.py` writes profiles/*.json):

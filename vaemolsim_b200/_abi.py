@@ -149,6 +149,16 @@ _SIGS = {
     'vms_mc_plan_set_chain_offset': (None, [c_vp, c_i64]),
     'vms_mc_run_pcg64': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, C.c_ulonglong, C.c_ulonglong, C.POINTER(Pcg64Stream),
                                 c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vms_blockwise_log_prob_backward': (None, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_int, c_vp, c_vp, c_i64,
+                                               c_vp, c_i64, c_vp]),
+    'vms_std_normal_log_prob_backward': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_vp]),
+    'vms_blockwise_sample_backward': (None, [c_vp, c_i64, c_i64, c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_int, c_vp, c_i64, c_vp, c_i64, c_vp,
+                                             c_i64, c_vp]),
+    'vms_periodic_featurise_backward': (None, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
+    'vms_add_cols': (None, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_f32, c_vp]),
+    'vms_add_scalar': (None, [c_vp, c_i64, c_vp, c_f32, c_vp]),
+    'vms_mul_inplace': (None, [c_vp, c_vp, c_i64, c_vp]),
+    'vms_sum_all': (None, [c_vp, c_i64, c_f32, c_vp, c_vp]),
     'vms_probe_ffma': (None, [c_int, c_int, C.POINTER(c_f64), C.POINTER(c_f64), c_vp]),
     'vms_probe_mma': (None, [c_int, c_int, c_int, c_int, c_int, C.POINTER(c_f64), C.POINTER(c_f64), c_vp]),
     'vms_elbo_forward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -344,6 +354,7 @@ class Tensor(object):
         it = self.dtype.itemsize
         c.lib.vms_memcpy2d_d2d(t.ptr, self.shape[1] * it, self.ptr, self.ld * it, self.shape[1] * it, self.shape[0],
                                c.stream)
+        _record_copy(self, t)
         return t
 
     def assign_cols(self, start, src):
@@ -388,6 +399,7 @@ class Tensor(object):
         if self.nbytes:
             c = ctx()
             c.lib.vms_memcpy_d2d(t.ptr, self.ptr, self.nbytes, c.stream)
+        _record_copy(self, t)
         return t
 
     # -- arithmetic (float32 only; anything else goes through NumPy on the host)
@@ -402,6 +414,7 @@ class Tensor(object):
                 return Tensor.from_numpy(a * self.numpy() + b * other.numpy())
             out = Tensor(self.shape)
             c.lib.vms_axpby(self.ptr, other.ptr, a, b, self.size, out.ptr, c.stream)
+            _record_axpby(self, other, a, b, out)
             return out
         return Tensor.from_numpy((a * self.numpy() + b * np.asarray(other)).astype(self.dtype))
 
@@ -427,6 +440,7 @@ class Tensor(object):
         c = ctx()
         out = Tensor(self.shape)
         c.lib.vms_axpby(self.ptr, None, float(k), 0.0, self.size, out.ptr, c.stream)
+        _record_axpby(self, None, float(k), 0.0, out)
         return out
 
     __rmul__ = __mul__
@@ -574,6 +588,44 @@ def _dlpack_import(obj, stream=None):
     _pyapi.PyCapsule_SetName(cap, b'used_dltensor')  # ownership of the managed tensor is ours now
     owner = _Foreign(ptr)
     return Tensor(shape, dtype, _ptr=int(dl.data or 0) + int(dl.byte_offset), _base=owner, _ld=ld)
+
+
+# ------------------------------------------------------------------------------------------------- tape hooks
+def _tape():
+    from . import _autodiff
+    return _autodiff.Tape.active(), _autodiff
+
+
+def _record_copy(src, dst):
+    """dst is a copy of src (contig / copy): g_src += g_dst."""
+    if src.dtype != np.float32:
+        return
+    tp, ad = _tape()
+    if tp is None:
+        return
+
+    def bw():
+        if tp.has(dst):
+            ad.add_into(tp.grad(src), tp.grad(dst), 1.0)
+
+    tp.record(bw)
+
+
+def _record_axpby(x, y, a, b, out):
+    """out = a x + b y (y may be None): g_x += a g_out, g_y += b g_out."""
+    tp, ad = _tape()
+    if tp is None:
+        return
+
+    def bw():
+        if not tp.has(out):
+            return
+        g = tp.grad(out)
+        ad.add_into(tp.grad(x), g, a)
+        if y is not None:
+            ad.add_into(tp.grad(y), g, b)
+
+    tp.record(bw)
 
 
 def as_tensor(x, dtype=np.float32):

@@ -1,0 +1,142 @@
+"""Reverse mode for the op-by-op path: a tape of the kernels the host launched, replayed backwards.
+
+The reference trains every composition through TF autodiff (`tf.GradientTape` inside Keras `fit`, tests/test_models.py:
+189-262, models.py:85-139).  The fused plans (`csrc/elbo*.cu`) cover the headline family; everything else -- von Mises
+encoders, periodic FCDeepNN, blockwise / autoregressive / MAF-flowed decoders, FlowModel NLL training -- runs here: while a
+`Tape` is active every device op of `_protocols.py` / `_abi.py` / `mappings.py` / `losses.py` records a closure that
+launches its reverse-mode kernel (`vms_dense_backward`, `vms_rqs_apply_backward`, `vms_blockwise_log_prob_backward`,
+`vms_blockwise_sample_backward`, `vms_periodic_featurise_backward`, ...).  Gradients live in device tensors shaped like the
+ROOT allocation of each tensor; a view's gradient is the same view of its root's gradient, so column slices and reshapes
+need no ops of their own and every backward kernel ACCUMULATES.
+
+`Trainer` is the Keras `fit` / `train_step` replacement for this path: forward under a tape, backward, MADE masks on the
+masked kernels' gradients, Keras Adam per parameter tensor (`vms_adam_step`).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._abi import Tensor, ctx
+
+
+class Tape(object):
+    """Records backward closures in forward order; `backward(loss)` seeds d loss = 1 and replays them in reverse."""
+    current = None
+
+    def __init__(self):
+        self.ops = []
+        self.grads = {}   # id(root tensor) -> (root, gradient of the root allocation)
+        self._paused = 0
+
+    def __enter__(self):
+        self._prev, Tape.current = Tape.current, self
+        return self
+
+    def __exit__(self, *exc):
+        Tape.current = self._prev
+        return False
+
+    # -- recording
+    @staticmethod
+    def active():
+        t = Tape.current
+        return t if (t is not None and not t._paused) else None
+
+    def record(self, fn):
+        self.ops.append(fn)
+
+    class _Pause(object):
+        def __init__(self, tape):
+            self.tape = tape
+
+        def __enter__(self):
+            self.tape._paused += 1
+
+        def __exit__(self, *exc):
+            self.tape._paused -= 1
+            return False
+
+    def paused(self):
+        return Tape._Pause(self)
+
+    # -- gradients
+    @staticmethod
+    def _root(t):
+        r = t
+        while isinstance(r._base, Tensor):
+            r = r._base
+        return r
+
+    def has(self, t):
+        return id(self._root(t)) in self.grads
+
+    def grad(self, t):
+        """Gradient tensor shaped (and strided) like `t`: a view into the gradient of t's root allocation."""
+        r = self._root(t)
+        ent = self.grads.get(id(r))
+        if ent is None:
+            g = Tensor.zeros(r.shape if r.nbytes else (1, ), np.float32)
+            self.grads[id(r)] = ent = (r, g)
+        g = ent[1]
+        if t is r:
+            return g
+        return Tensor(t.shape, np.float32, _ptr=g.ptr + (t.ptr - r.ptr), _base=g, _ld=t.ld)
+
+    def backward(self, loss):
+        c = ctx()
+        g = self.grad(loss)
+        one = np.ones(max(loss.size, 1), np.float32)
+        c.lib.vms_memcpy_h2d(g.ptr, one.ctypes.data, one.nbytes, c.stream)
+        c.synchronize()
+        for fn in reversed(self.ops):
+            fn()
+
+
+def add_into(dst, src, alpha=1.0):
+    """dst += alpha * src for same-shaped (possibly column-strided) float32 tensors."""
+    c = ctx()
+    if dst.ndim == 2:
+        c.lib.vms_add_cols(dst.ptr, dst.ld, src.ptr, src.ld, dst.shape[0], dst.shape[1], float(alpha), c.stream)
+    else:
+        n = dst.size
+        c.lib.vms_add_cols(dst.ptr, n, src.ptr, n, 1, n, float(alpha), c.stream)
+
+
+class Trainer(object):
+    """Keras-style training of an arbitrary model of this package: `step(fn)` runs fn() under a tape (fn returns the scalar
+    loss Tensor), back-propagates and applies Adam to every weight of `model.weights` that received a gradient."""
+
+    def __init__(self, model, optimizer):
+        self.model, self.opt = model, optimizer
+        self.state = {}  # id(weight) -> (weight, m, v)
+        self.t = 0
+
+    def step(self, fn):
+        c = ctx()
+        with Tape() as tape:
+            loss = fn()
+            tape.backward(loss)
+        self.t += 1
+        seen = set()
+        for w in self.model.weights:
+            if id(w) in seen or not tape.has(w):
+                continue
+            seen.add(id(w))
+            g = tape.grad(w)
+            mask = getattr(w, '_grad_mask', None)
+            if mask is not None:  # tfp AutoregressiveNetwork: masked kernel entries stay zero
+                c.lib.vms_mul_inplace(g.ptr, mask.ptr, g.size, c.stream)
+            st = self.state.get(id(w))
+            if st is None:
+                st = self.state[id(w)] = (w, Tensor.zeros(w.shape), Tensor.zeros(w.shape))
+            o = self.opt
+            if w.contiguous and g.contiguous:
+                c.lib.vms_adam_step(w.ptr, g.ptr, 1, 1.0, st[1].ptr, st[2].ptr, w.size, self.t, o.learning_rate, o.beta_1, o.beta_2,
+                                    o.epsilon, c.stream)
+            else:  # a weight that is a strided view of a flat buffer: update a contiguous copy and write it back
+                wc, gc = w.contig(), g.contig()
+                c.lib.vms_adam_step(wc.ptr, gc.ptr, 1, 1.0, st[1].ptr, st[2].ptr, w.size, self.t, o.learning_rate, o.beta_1,
+                                    o.beta_2, o.epsilon, c.stream)
+                it = 4
+                c.lib.vms_memcpy2d_d2d(w.ptr, w.ld * it, wc.ptr, wc.ld * it, w.shape[-1] * it, w.shape[0], c.stream)
+        return loss

@@ -47,6 +47,16 @@ def _act_code(activation):
     return ACT[activation]
 
 
+def _tape():
+    from . import _autodiff
+    return _autodiff.Tape.active()
+
+
+def _ad():
+    from . import _autodiff
+    return _autodiff
+
+
 def _ptr(t):
     return None if t is None else t.ptr
 
@@ -196,6 +206,26 @@ class Dense(Layer):
         Cn = 0 if cond is None else cond.shape[1]
         c.lib.vms_dense_forward(xp, ldx, self.kernel.ptr, _ptr(self.bias), B, K, self.units, self.act, _ptr(cond),
                                 0 if cond is None else cond.ld, _ptr(cond_kernel), Cn, out.ptr, out.ld, c.stream)
+        tp = _tape()
+        if tp is not None:
+            W, bias, act, N = self.kernel, self.bias, self.act, self.units
+
+            def bw():  # TF autodiff through Dense: input, kernel, bias and conditional-input / conditional-kernel gradients
+                if not tp.has(out):
+                    return
+                g_out = tp.grad(out)
+                ws = Tensor((max(int(c.lib.vms_dense_backward_workspace(B, K, N, Cn)) // 4, 1), ))
+                g_x = None if ones_input else tp.grad(x)
+                g_c = Tensor((B, Cn)) if cond is not None else None  # (the kernel overwrites g_cond: accumulate below)
+                c.lib.vms_dense_backward(xp, ldx, W.ptr, B, K, N, act, out.ptr, out.ld, g_out.ptr, g_out.ld, _ptr(cond),
+                                         0 if cond is None else cond.ld, _ptr(cond_kernel), Cn, _ptr(g_x),
+                                         0 if g_x is None else g_x.ld, 1, tp.grad(W).ptr,
+                                         None if bias is None else tp.grad(bias).ptr, _ptr(g_c), Cn,
+                                         None if cond_kernel is None else tp.grad(cond_kernel).ptr, 1, ws.ptr, c.stream)
+                if g_c is not None:
+                    _ad().add_into(tp.grad(cond), g_c, 1.0)
+
+            tp.record(bw)
         return out
 
 
@@ -344,6 +374,7 @@ class AutoregressiveNetwork(Layer):
             lay = Dense(b, activation=None, name='%s_dense_%d' % (self.name, k))
             W = _init_kernel(self.kernel_initializer, a, b) * self.masks[k].astype(np.float32)
             lay.set_weights([W, np.zeros(b, np.float32)])
+            lay.kernel._grad_mask = Tensor.from_numpy(self.masks[k].astype(np.float32))  # applied to the kernel's gradient
             lay.act = self.act if k + 1 < len(sizes) - 1 else 0
             self.layers.append(lay)
             self._weights += lay._weights
@@ -362,6 +393,7 @@ class AutoregressiveNetwork(Layer):
         for k, lay in enumerate(self.layers):
             W = np.asarray(next(it), np.float32) * self.masks[k].astype(np.float32)
             lay.set_weights([W, np.asarray(next(it), np.float32)])
+            lay.kernel._grad_mask = Tensor.from_numpy(self.masks[k].astype(np.float32))
             self._weights += lay._weights
             if self.conditional:
                 self.cond_kernels[k] = Tensor.from_numpy(np.asarray(next(it), np.float32))
@@ -427,6 +459,28 @@ class RationalQuadraticSpline(Bijector):
                          self.raw_w.ld, self.raw_h.ptr, self.raw_h.ld, self.raw_s.ptr, self.raw_s.ld, out.ptr, out.ld,
                          _ptr(ldj), _ptr(ldj_sum), 1 if accumulate else 0, 1 if inverse else 0)
         c.lib.vms_rqs_apply(C.byref(a), c.stream)
+        tp = _tape()
+        if tp is not None:
+            rw, rh, rs, nd, K = self.raw_w, self.raw_h, self.raw_s, self.n_dims, self.num_bins
+
+            def bw():  # reverse mode of the spline (vms_rqs_apply_backward overwrites its outputs: temporaries + accumulate)
+                has_out, has_l = tp.has(out), (ldj_sum is not None and tp.has(ldj_sum))
+                if ldj is not None and tp.has(ldj):
+                    raise NotImplementedError('reverse mode through per-dimension log-dets (event_ndims=0) is not built')
+                if not (has_out or has_l):
+                    return
+                g_out = tp.grad(out) if has_out else Tensor.zeros((B, nd))
+                g_in, g_w, g_h, g_s = Tensor((B, nd)), Tensor((B, nd * K)), Tensor((B, nd * K)), Tensor((B, nd * (K - 1)))
+                ba = _abi.RqsBwdArgs(a, g_out.ptr, g_out.ld, tp.grad(ldj_sum).ptr if has_l else None, g_in.ptr, g_in.ld,
+                                     g_w.ptr, g_w.ld, g_h.ptr, g_h.ld, g_s.ptr, g_s.ld)
+                c.lib.vms_rqs_apply_backward(C.byref(ba), c.stream)
+                ad = _ad()
+                ad.add_into(tp.grad(v), g_in, 1.0)
+                ad.add_into(tp.grad(rw), g_w, 1.0)
+                ad.add_into(tp.grad(rh), g_h, 1.0)
+                ad.add_into(tp.grad(rs), g_s, 1.0)
+
+            tp.record(bw)
 
     def _apply(self, v, inverse):
         out = Tensor(v.shape)
@@ -469,7 +523,20 @@ class RealNVP(Bijector):
         (c0, c1), (t0, t1) = self._split(D)
         cond = v.cols(c0, c1)
         bij = self.bijector_fn(cond, t1 - t0, **kw)
-        out = v.contig().copy() if c1 > c0 else Tensor(v.shape)
+        tp = _tape()
+        if tp is None:
+            out = v.contig().copy() if c1 > c0 else Tensor(v.shape)
+        else:
+            vc = v.contig()
+            with tp.paused():  # the pass-through copy is differentiated here: only the conditioner columns flow straight back
+                out = vc.copy() if c1 > c0 else Tensor(v.shape)
+            if c1 > c0:
+                def bw():
+                    if tp.has(out):
+                        _ad().add_into(tp.grad(vc).cols(c0, c1), tp.grad(out).cols(c0, c1), 1.0)
+
+                tp.record(bw)
+            v = vc
         ldj = Tensor((v.shape[0],))
         bij.apply_into(v.cols(t0, t1), out.cols(t0, t1), ldj, False, inverse)
         return out, ldj
@@ -671,6 +738,17 @@ class StandardNormal(Distribution):
         c = ctx()
         lp = Tensor((x.shape[0],))
         c.lib.vms_std_normal_log_prob(x.ptr, x.ld, x.shape[0], self.event_size, lp.ptr, 0, c.stream)
+        tp = _tape()
+        if tp is not None:
+            D = self.event_size
+
+            def bw():
+                if tp.has(lp):
+                    g_x = tp.grad(x)
+                    c.lib.vms_std_normal_log_prob_backward(x.ptr, x.ld, x.shape[0], D, tp.grad(lp).ptr, g_x.ptr, g_x.ld,
+                                                           c.stream)
+
+            tp.record(bw)
         return lp
 
     def _log_prob_rows(self, x, **kw):
@@ -694,12 +772,34 @@ class Blockwise(Distribution):
         self.loc_off, self.loc2_off, self.scale_off = list(loc_off), list(loc2_off), list(scale_off)
         self.scale_mode = int(scale_mode)
 
-    def _log_prob_rows(self, x, **kw):
+    def _lp_call(self, x, n, ld_p):
+        """log_prob of n rows; ld_p = 0 broadcasts the single parameter row of an unbatched distribution to every row."""
         c = ctx()
-        lp = Tensor((self._n,))
-        c.lib.vms_blockwise_log_prob(x.ptr, x.ld, self.params.ptr, self.params.ld, self._n, self.event_size,
-                                     self._kind, self._loc, self._loc2, self._scale, self.scale_mode, lp.ptr, 0, c.stream)
+        lp = Tensor((n,))
+        params, D = self.params, self.event_size
+        c.lib.vms_blockwise_log_prob(x.ptr, x.ld, params.ptr, ld_p, n, D, self._kind, self._loc, self._loc2, self._scale,
+                                     self.scale_mode, lp.ptr, 0, c.stream)
+        tp = _tape()
+        if tp is not None:
+            def bw():  # TF autodiff through Normal / VonMises log_prob and the parameter transforms (dists.py:56-78)
+                if not tp.has(lp):
+                    return
+                g_p = tp.grad(params) if ld_p else None  # (a broadcast parameter row is a constant of the model)
+                g_x = tp.grad(x)
+                c.lib.vms_blockwise_log_prob_backward(x.ptr, x.ld, params.ptr, ld_p, n, D, self._kind, self._loc, self._loc2,
+                                                      self._scale, self.scale_mode, tp.grad(lp).ptr, g_x.ptr, g_x.ld, _ptr(g_p),
+                                                      0 if g_p is None else g_p.ld, c.stream)
+
+            tp.record(bw)
         return lp
+
+    def _log_prob_rows(self, x, **kw):
+        return self._lp_call(x, self._n, self.params.ld)
+
+    def _broadcast_log_prob(self, x, **kw):
+        if self._n != 1:
+            return Distribution._broadcast_log_prob(self, x, **kw)
+        return self._lp_call(x, x.shape[0], 0)
 
     def _planar_normal(self):
         D = self.event_size
@@ -722,7 +822,30 @@ class Blockwise(Distribution):
         c.lib.vms_normal_sample_log_prob(self.params.ptr, self.params.ld, self.loc_off[0], self.scale_off[0],
                                          self.scale_mode, eps.ptr, self._n, self.event_size, z.ptr, z.ld, _ptr(lp),
                                          c.stream)
+        self._record_sample(z)
+        if lp is not None and _tape() is not None:
+            raise NotImplementedError('reverse mode through the fused sample + log_prob call is not built: use sample() and '
+                                      'log_prob() separately under a tape')
         return z, lp
+
+    def _record_sample(self, z):
+        """Reparameterised sample z: pathwise gradient for Normal dofs and for the von Mises location, tfp's implicit
+        reparameterisation for the von Mises concentration (vms_blockwise_sample_backward)."""
+        tp = _tape()
+        if tp is None:
+            return
+        c = ctx()
+        params = self.params
+
+        def bw():
+            if not tp.has(z):
+                return
+            g_z, g_p = tp.grad(z), tp.grad(params)
+            c.lib.vms_blockwise_sample_backward(params.ptr, params.ld, self._n, self.event_size, self._kind, self._loc,
+                                                self._loc2, self._scale, self.scale_mode, z.ptr, z.ld, g_z.ptr, g_z.ld,
+                                                g_p.ptr, g_p.ld, c.stream)
+
+        tp.record(bw)
 
     def _sample_rows(self, eps=None, **kw):
         if self._planar_normal():
@@ -738,6 +861,7 @@ class Blockwise(Distribution):
         c.lib.vms_blockwise_sample(self.params.ptr, self.params.ld, self._n, self.event_size, self._kind, self._loc,
                                    self._loc2, self._scale, self.scale_mode, _ptr(e), 0 if e is None else e.ld, seed,
                                    out.ptr, out.ld, c.stream)
+        self._record_sample(out)
         return out
 
     def experimental_sample_and_log_prob(self, sample_shape=None, **kw):

@@ -15,10 +15,26 @@ def _mean_diff(a, b, sign=1.0):
     c = ctx()
     a = a.contig()
     out = Tensor(())
+    if b is not None:
+        b = b.contig()
     if b is None:
         c.lib.vms_scaled_mean(a.ptr, a.size, sign, out.ptr, c.stream)
     else:
-        c.lib.vms_kl_mean(a.ptr, b.contig().ptr, a.size, sign, out.ptr, c.stream)
+        c.lib.vms_kl_mean(a.ptr, b.ptr, a.size, sign, out.ptr, c.stream)
+    from . import _autodiff
+    tp = _autodiff.Tape.active()
+    if tp is not None:
+        n = a.size
+
+        def bw():  # d mean / d a_i = sign / n (Keras mean reduction, losses.py:58, :253)
+            if not tp.has(out):
+                return
+            g = tp.grad(out)
+            c.lib.vms_add_scalar(tp.grad(a).ptr, n, g.ptr, float(sign) / n, c.stream)
+            if b is not None:
+                c.lib.vms_add_scalar(tp.grad(b).ptr, n, g.ptr, -float(sign) / n, c.stream)
+
+        tp.record(bw)
     return out
 
 

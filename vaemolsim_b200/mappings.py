@@ -93,6 +93,17 @@ class FCDeepNN(P.Layer):
             c = ctx()
             feat = Tensor((out.shape[0], out.shape[1] + int(np.sum(self.periodic_dofs))))
             c.lib.vms_periodic_featurise(out.ptr, out.shape[0], out.shape[1], self._periodic_dev.ptr, feat.ptr, c.stream)
+            from . import _autodiff
+            tp = _autodiff.Tape.active()
+            if tp is not None:
+                src, n_per, per = out, int(np.sum(self.periodic_dofs)), self._periodic_dev
+
+                def bw():
+                    if tp.has(feat):
+                        c.lib.vms_periodic_featurise_backward(src.ptr, src.shape[0], src.shape[1], per.ptr, n_per,
+                                                              tp.grad(feat).ptr, tp.grad(src).ptr, c.stream)
+
+                tp.record(bw)
             out = feat
         for layer in self.layer_list:
             out = layer.call(out) if isinstance(layer, P.Dense) else layer.call(out, training=training)

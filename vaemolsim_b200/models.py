@@ -34,6 +34,78 @@ class Model(P.Layer):
     def predict_step(self, inputs):
         return self(inputs, training=False).sample()
 
+    # ------------------------------------------------------------------ generic training (tape-based reverse mode)
+    # Keras `fit` / `evaluate` for ANY composition of this package's layers (tests/test_models.py:189-228, models.py:85-139):
+    # forward op by op under a tape (_autodiff.py), reverse-mode kernels, Adam per weight tensor.  The fused plans of
+    # `VAE` take over for the model family they support.
+    def _loss_tensor(self, xb, yb, training):
+        out = self(xb, training=training)
+        loss_fn = getattr(self, 'loss', None) or losses.LogProbLoss()
+        total = loss_fn(yb, out)
+        for extra in getattr(self, 'losses', []) or []:
+            if isinstance(extra, Tensor):
+                total = total + extra
+            elif extra:
+                total = total + float(extra)
+        return total
+
+    def _check_trainable(self):
+        stack, seen = [self], set()
+        while stack:
+            lay = stack.pop()
+            if id(lay) in seen:
+                continue
+            seen.add(id(lay))
+            if isinstance(lay, P.KerasBatchNormalization) or getattr(lay, 'batch_norm', False):
+                raise NotImplementedError('training through batch normalisation is not built (SURVEY.md 8f rank 3): reverse '
+                                          'mode of the batch statistics is missing')
+            stack += lay._sublayers()
+
+    def _trainer(self):
+        from . import _autodiff
+        opt = getattr(self, 'optimizer', None) or Adam()
+        tr = getattr(self, '_generic_trainer', None)
+        if tr is None or tr.opt is not opt:
+            tr = self._generic_trainer = _autodiff.Trainer(self, opt)
+        return tr
+
+    def _prep_xy(self, x, y):
+        x = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
+        y = x if y is None else np.asarray(y.numpy() if isinstance(y, Tensor) else y, np.float32)
+        return x, y
+
+    def fit(self, x, y=None, epochs=1, batch_size=32, verbose=0, shuffle=True):
+        x, y = self._prep_xy(x, y)
+        self(Tensor.from_numpy(x[:min(2, len(x))]))  # build
+        self._check_trainable()
+        tr = self._trainer()
+        hist = {'loss': []}
+        for _ in range(epochs):
+            order = P.rng().permutation(len(x)) if shuffle else np.arange(len(x))
+            tot, n = 0.0, 0
+            for i in range(0, len(x), batch_size):
+                idx = order[i:i + batch_size]
+                xb, yb = Tensor.from_numpy(x[idx]), Tensor.from_numpy(y[idx])
+                loss = tr.step(lambda: self._loss_tensor(xb, yb, True))
+                tot, n = tot + float(loss.numpy()) * len(idx), n + len(idx)
+            hist['loss'].append(tot / max(n, 1))
+        return hist
+
+    def train_on_batch(self, x, y=None):
+        """One optimiser step on one batch; returns the loss (the inner call of `fit`)."""
+        x, y = self._prep_xy(x, y)
+        xb, yb = Tensor.from_numpy(x), Tensor.from_numpy(y)
+        self._check_trainable()
+        return float(self._trainer().step(lambda: self._loss_tensor(xb, yb, True)).numpy())
+
+    def evaluate(self, x, y=None, batch_size=32, verbose=0):
+        x, y = self._prep_xy(x, y)
+        tot, n = 0.0, 0
+        for i in range(0, len(x), batch_size):
+            xb, yb = Tensor.from_numpy(x[i:i + batch_size]), Tensor.from_numpy(y[i:i + batch_size])
+            tot, n = tot + float(self._loss_tensor(xb, yb, False).numpy()) * xb.shape[0], n + xb.shape[0]
+        return tot / max(n, 1)
+
     def predict(self, x, batch_size=32, verbose=0):
         x = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
         outs = [self.predict_step(Tensor.from_numpy(x[i:i + batch_size])).numpy() for i in range(0, len(x), batch_size)]
@@ -145,13 +217,25 @@ class VAE(Model):
         scal = f.train_step(x, as_tensor(eps), getattr(self, 'optimizer', None) or Adam())
         return dict(zip(('loss', 'nll', 'kl'), scal.numpy()[:3].tolist()))
 
-    def fit(self, x, y=None, epochs=1, batch_size=32, verbose=0, shuffle=True):
+    def _fused_or_none(self, max_batch):
+        """The fused plan when this composition belongs to its family (and the loss is LogProbLoss), else None: the
+        tape-based generic path of `Model` trains everything else."""
         if getattr(self, 'loss', None) is not None and not isinstance(self.loss, losses.LogProbLoss):
-            raise NotImplementedError('VAE.fit: only LogProbLoss has a fused backward (SURVEY.md 8f)')
-        x = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
-        x = x.reshape(len(x), -1)
+            return None
+        try:
+            return self.fused(max_batch)
+        except NotImplementedError:
+            return None
+
+    def fit(self, x, y=None, epochs=1, batch_size=32, verbose=0, shuffle=True):
+        xa = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
+        if not self.built:
+            self(Tensor.from_numpy(xa[:min(2, len(xa))]))
+        f = self._fused_or_none(min(int(batch_size), len(xa)))
+        if f is None:
+            return Model.fit(self, x, y, epochs=epochs, batch_size=batch_size, verbose=verbose, shuffle=shuffle)
+        x = xa.reshape(len(xa), -1)
         hist = {'loss': [], 'kl_div': []}
-        f = self.fused(min(int(batch_size), len(x)))
         opt = getattr(self, 'optimizer', None) or Adam()
         for _ in range(epochs):
             order = P.rng().permutation(len(x)) if shuffle else None
@@ -166,7 +250,9 @@ class VAE(Model):
 
     def evaluate(self, x, y=None, batch_size=32, verbose=0):
         x = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
-        f = self.fused(min(batch_size, len(x)))
+        f = self._fused_or_none(min(batch_size, len(x)))
+        if f is None:
+            return Model.evaluate(self, x, y, batch_size=batch_size, verbose=verbose)
         tot, n = 0.0, 0
         for i in range(0, len(x), batch_size):
             xb = Tensor.from_numpy(x[i:i + batch_size])
