@@ -176,23 +176,28 @@ def _directional_check(v, model, xb, yb, rtol, seed=0, h=2e-3, n_dirs=3):
 
 
 def _decoder(v, which):
+    """Decoders of tests/test_models.py:189-228 at small widths.  The mapping networks use tanh here: a relu network is not
+    differentiable along a random direction (units cross zero inside the finite-difference step), and the relu reverse
+    mode of vms_dense_backward has its own oracle test (tests/test_gpu_kernels.py)."""
     d = v.dists
     kinds = [d.Normal] * 2 + [d.VonMises] * 2
+    fc = lambda target, **kw: v.mappings.FCDeepNN(target, hidden_dim=24, activation='tanh', **kw)
     if which == 'blockwise':
         dist = d.IndependentBlockwise(4, kinds)
-        mapping = v.mappings.FCDeepNN(dist.params_size(), hidden_dim=24, periodic_dofs=[False, True, True])
-        return v.models.MappingToDistribution(dist, mapping=mapping, name='decoder')
-    if which == 'autoregressive':
-        return v.models.MappingToDistribution(d.AutoregressiveBlockwise(4, kinds, auto_net_params={'hidden_units': [16, 16]}),
+        return v.models.MappingToDistribution(dist, mapping=fc(dist.params_size(), periodic_dofs=[False, True, True]),
                                               name='decoder')
+    if which == 'autoregressive':
+        dist = d.AutoregressiveBlockwise(4, kinds, auto_net_params={'hidden_units': [16, 16]})
+        return v.models.MappingToDistribution(dist, mapping=fc(dist.params_size()), name='decoder')
     if which == 'autoregressive-conditional':
-        return v.models.MappingToDistribution(
-            d.AutoregressiveBlockwise(4, kinds, conditional=True, conditional_event_shape=3,
-                                      auto_net_params={'hidden_units': [16], 'activation': 'tanh'}), name='decoder')
+        dist = d.AutoregressiveBlockwise(4, kinds, conditional=True, conditional_event_shape=3,
+                                         auto_net_params={'hidden_units': [16], 'activation': 'tanh'})
+        return v.models.MappingToDistribution(dist, mapping=fc(dist.params_size()), name='decoder')
     if which == 'maf-flowed':
         flow = v.flows.RQSSplineMAF(num_blocks=2, order_seed=3, rqs_params=dict(num_bins=8, hidden_dim=12, bin_range=[-6.0, 6.0]))
         flow(np.ones((1, 4), np.float32))
-        return v.models.MappingToDistribution(d.FlowedDistribution(flow, d.IndependentBlockwise(4, kinds)), name='decoder')
+        dist = d.FlowedDistribution(flow, d.IndependentBlockwise(4, kinds))
+        return v.models.MappingToDistribution(dist, mapping=fc(dist.params_size()), name='decoder')
     raise ValueError(which)
 
 
