@@ -245,6 +245,17 @@ vms_status vms_batch_moments(const float* x, int64_t ld_x, int64_t B, int D, flo
 vms_status vms_batchnorm_coeffs(const float* mean, const float* var, const float* gamma, const float* beta, int D, float eps,
                                 int denormalize, float* scale, float* shift, float* ldj, vms_stream stream);
 vms_status vms_broadcast_scalar(const float* scalar, int64_t n, float* out, vms_stream stream);
+/* Reverse mode of the NORMALISING direction y = (x - mean) rsqrt(var + eps) gamma + beta (TF autodiff through
+ * tf.nn.batch_normalization + tf.nn.moments; mappings.py:113-114 in training, flows.py:308-309 / :623-624 inverse):
+ *   batch_stats != 0: mean / var are the batch moments of x (gradients flow through them);  == 0: constants (moving statistics)
+ *   g_ldj_total (nullable, device scalar): sum over the rows of the upstream gradient of the bijector's per-row log-det
+ *   sum_d log gamma_d - 0.5 log(var_d + eps).   g_x += ..., g_gamma += ..., g_beta += ... (g_gamma / g_beta nullable).
+ * workspace: vms_batchnorm_backward_workspace(D) bytes of device memory.  Fixed-order column sums (deterministic). */
+size_t vms_batchnorm_backward_workspace(int D);
+vms_status vms_batchnorm_backward(const float* x, int64_t ld_x, int64_t B, int D, const float* mean, const float* var,
+                                  const float* gamma, float eps, int batch_stats, const float* g_out, int64_t ld_g,
+                                  const float* g_ldj_total, float* g_x, int64_t ld_gx, float* g_gamma, float* g_beta,
+                                  void* workspace, vms_stream stream);
 
 /* ------------------------------------------------------------------------------- K6: DistanceSelection
  * Replaces `DistanceSelection.call` mappings.py:362-455 (TF sub / div / round / mul / reduce_sum / top_k / gather):

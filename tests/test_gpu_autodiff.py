@@ -134,6 +134,7 @@ def _tape_gradients(v, model, xb, yb):
         if not any(w is u for u in ws):
             ws.append(w)
     grads = []
+    ws = [w for w in ws if tp.has(w)]  # (moving statistics of batch-norm layers are weights without a gradient)
     for w in ws:
         g = tp.grad(w).numpy().astype(np.float64) if tp.has(w) else np.zeros(w.shape)
         m = getattr(w, '_grad_mask', None)
@@ -141,7 +142,7 @@ def _tape_gradients(v, model, xb, yb):
     return float(loss.numpy()), ws, grads
 
 
-def _directional_check(v, model, xb, yb, rtol, seed=0, h=2e-3, n_dirs=3):
+def _directional_check(v, model, xb, yb, rtol, seed=0, h=2e-3, n_dirs=3, training=False):
     """Tape gradient . direction against a central difference of the DEVICE forward along that direction (float32 forward:
     the difference carries ~1e-4 relative noise, enough to catch a missing term, a wrong sign or a wrong transpose)."""
     c = v._abi.ctx()
@@ -166,7 +167,7 @@ def _directional_check(v, model, xb, yb, rtol, seed=0, h=2e-3, n_dirs=3):
                 else:
                     w.assign_cols(0, v.Tensor.from_numpy(a))
             c.synchronize()
-            vals.append(float(model._loss_tensor(v.as_tensor(xb), v.as_tensor(yb), False).numpy()))
+            vals.append(float(model._loss_tensor(v.as_tensor(xb), v.as_tensor(yb), training).numpy()))
         got = (vals[0] - vals[1]) / (2 * h)
         assert abs(got - want) <= rtol * max(abs(want), 1e-2) + 5e-4, 'directional derivative %g (finite difference) vs %g (tape)' % (got, want)
     for w, b0 in zip(ws, base):
@@ -318,3 +319,92 @@ def test_vae_with_von_mises_encoder_and_flow_prior_trains(vms, which):
     assert hist is not None and np.isfinite(hist['loss']).all()
     l1 = np.mean([vae.evaluate(x, batch_size=64) for _ in range(4)])
     assert l1 < l0 - 0.1, (l0, l1, hist['loss'][-3:])
+
+
+# ------------------------------------------------------------------------------------------------ batch normalisation
+def test_batchnorm_backward_matches_float64_finite_differences(vms):
+    """vms_batchnorm_backward (TF autodiff through tf.nn.batch_normalization + tf.nn.moments and the tfp bijector's
+    log-det): L = sum(G_out * y) + sum_b g_l[b] * ldj, gradients wrt x, gamma, beta, with batch statistics and with constant
+    (moving) statistics, against central differences of the float64 oracle."""
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(21)
+    B, D, eps = 200, 5, 1e-3
+    x = rng.normal(1.0, 2.0, (B, D))
+    gamma, beta = rng.uniform(0.5, 1.5, D), rng.normal(size=D)
+    G_out, g_l = rng.normal(size=(B, D)), rng.normal(size=B)
+    mov_m, mov_v = rng.normal(size=D), rng.uniform(0.5, 2.0, D)
+
+    def L(x_, ga, be, batch):
+        m, va = (x_.mean(0), x_.var(0)) if batch else (mov_m, mov_v)
+        y = onets.batch_norm_normalize(x_, m, va, ga, be, eps)
+        ldj = np.sum(np.log(ga) - 0.5 * np.log(va + eps))
+        return float(np.sum(G_out * y) + np.sum(g_l) * ldj)
+
+    f32 = lambda a: v.Tensor.from_numpy(np.ascontiguousarray(a, np.float32))
+    for batch in (True, False):
+        m, va = (x.mean(0), x.var(0)) if batch else (mov_m, mov_v)
+        gx, gg, gb = v.Tensor.zeros((B, D)), v.Tensor.zeros((D, )), v.Tensor.zeros((D, ))
+        Gt = f32(np.array([g_l.astype(np.float32).sum()]))
+        ws = v.Tensor((int(c.lib.vms_batchnorm_backward_workspace(D)) // 4 + 1, ))
+        xd, md, vd, gad, god = f32(x), f32(m), f32(va), f32(gamma), f32(G_out)
+        c.lib.vms_batchnorm_backward(xd.ptr, D, B, D, md.ptr, vd.ptr, gad.ptr, eps, 1 if batch else 0, god.ptr, D, Gt.ptr, gx.ptr,
+                                     D, gg.ptr, gb.ptr, ws.ptr, c.stream)
+        h = 1e-6
+        want_x = np.zeros((B, D))
+        for b in range(0, B, 17):
+            for d in range(D):
+                e = np.zeros((B, D)); e[b, d] = h
+                want_x[b, d] = (L(x + e, gamma, beta, batch) - L(x - e, gamma, beta, batch)) / (2 * h)
+        rows = np.arange(0, B, 17)
+        assert_close(gx.numpy()[rows], want_x[rows], rtol=1e-4, atol=1e-4, what='batch norm d/dx (batch stats %s)' % batch)
+        wg = np.array([(L(x, gamma + h * np.eye(D)[d], beta, batch) - L(x, gamma - h * np.eye(D)[d], beta, batch)) / (2 * h)
+                       for d in range(D)])
+        wb = np.array([(L(x, gamma, beta + h * np.eye(D)[d], batch) - L(x, gamma, beta - h * np.eye(D)[d], batch)) / (2 * h)
+                       for d in range(D)])
+        assert_close(gg.numpy(), wg, rtol=1e-4, atol=2e-3, what='batch norm d/dgamma')
+        assert_close(gb.numpy(), wb, rtol=1e-4, atol=2e-3, what='batch norm d/dbeta')
+
+
+def test_batch_norm_models_train(vms):
+    """Port of tests/test_models.py:230-262 (`test_batch_norm`): batch normalisation inside both FCDeepNNs, between the
+    blocks of a conditional MAF decoder flow and of the RealNVP prior flow; call / sample / log_prob / compile / fit /
+    evaluate.  Plus a finite-difference check of the tape through a batch-normalised decoder in training mode."""
+    v = vms
+    import vaemolsim_b200._protocols as PR
+    d = v.dists
+    v.set_seed(13)
+    rng = np.random.default_rng(6)
+    zdim = 2
+    x = np.concatenate([rng.normal(size=(64, 3)), rng.uniform(-3, 3, (64, 3))], axis=1).astype(np.float32)
+    kinds = [d.Normal] * 3 + [d.VonMises] * 3
+    enc_dist = PR.IndependentNormal(zdim)
+    enc_map = v.mappings.FCDeepNN(enc_dist.params_size(zdim), hidden_dim=32, batch_norm=True, periodic_dofs=[False] * 3 + [True] * 3)
+    encoder = v.models.MappingToDistribution(enc_dist, mapping=enc_map, name='encoder')
+    dec_dist = d.FlowedDistribution(
+        v.flows.RQSSplineMAF(rqs_params={'conditional': True, 'conditional_event_shape': zdim, 'hidden_dim': 24, 'num_bins': 8},
+                             batch_norm=True), d.IndependentBlockwise(6, kinds))
+    dec_dist.flow(np.ones((1, 6), np.float32), conditional_input=np.ones((1, zdim), np.float32))
+    dec_map = v.mappings.FCDeepNN(dec_dist.params_size(), hidden_dim=32, batch_norm=True)
+    decoder = v.models.MappingToDistribution(dec_dist, mapping=dec_map, name='decoder')
+    prior = d.FlowedDistribution(v.flows.RQSSplineRealNVP(batch_norm=True, rqs_params={'hidden_dim': 24, 'num_bins': 8}),
+                                 PR.DistributionLambda(lambda t: PR.StandardNormal(t.shape[0], zdim)), name='prior')
+    prior.flow(np.ones((1, zdim), np.float32))
+    vae = v.models.VAE(encoder, decoder, prior)
+    out = vae(x)
+    assert out.sample().shape == (64, 6) and out.log_prob(x).shape == (64, )
+    vae.compile(optimizer=v.models.Adam(learning_rate=2e-3), loss=v.losses.LogProbLoss())
+    hist = vae.fit(x, x, epochs=15, batch_size=32)
+    assert hist is not None and np.isfinite(hist['loss']).all() and hist['loss'][-1] < hist['loss'][0]
+    assert np.isfinite(vae.evaluate(x, batch_size=64))
+    n_bn = sum(1 for w in vae.weights if w.shape == (32, ) or w.shape == (6, ) or w.shape == (zdim, ))
+    assert n_bn >= 8  # gamma / beta / moving statistics of the batch-norm layers are model variables
+    # tape vs finite differences through a batch-normalised mapping in TRAINING mode (batch statistics)
+    dist = d.IndependentBlockwise(4, [d.Normal] * 2 + [d.VonMises] * 2)
+    dec = v.models.MappingToDistribution(
+        dist, mapping=v.mappings.FCDeepNN(dist.params_size(), hidden_dim=16, activation='tanh', batch_norm=True), name='dec')
+    dec.compile(optimizer=v.models.Adam(1e-3), loss=v.losses.LogProbLoss())
+    z = rng.normal(size=(96, 3)).astype(np.float32)
+    y = np.concatenate([rng.normal(size=(96, 2)), rng.uniform(-3, 3, (96, 2))], axis=1).astype(np.float32)
+    dec(z)
+    _directional_check(v, dec, z, y, rtol=2e-2, training=True)

@@ -100,6 +100,9 @@ _SIGS = {
     'vms_batch_moments': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vms_batchnorm_coeffs': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vms_broadcast_scalar': (None, [c_vp, c_i64, c_vp, c_vp]),
+    'vms_batchnorm_backward_workspace': (c_size, [c_int]),
+    'vms_batchnorm_backward': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_f32, c_int, c_vp, c_i64, c_vp, c_vp, c_i64,
+                                      c_vp, c_vp, c_vp, c_vp]),
     'vms_standard_normal': (None, [C.c_ulonglong, C.c_ulonglong, c_i64, c_vp, c_vp]),
     'vms_blockwise_sample': (None, [c_vp, c_i64, c_i64, c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_int, c_vp, c_i64, C.c_ulonglong, c_vp,

@@ -267,17 +267,42 @@ class _BatchNormState(object):
                                    self._ldj.ptr if want_ldj else None, c.stream)
         out = Tensor((B, self.D))
         c.lib.vms_affine_cols(x.ptr, x.ld, B, self.D, self._scale.ptr, self._shift.ptr, 0, out.ptr, out.ld, c.stream)
-        if not want_ldj:
-            return out, None
-        ldj = Tensor((B,))
-        c.lib.vms_broadcast_scalar(self._ldj.ptr, B, ldj.ptr, c.stream)
+        ldj = None
+        if want_ldj:
+            ldj = Tensor((B,))
+            c.lib.vms_broadcast_scalar(self._ldj.ptr, B, ldj.ptr, c.stream)
+        tp = _tape()
+        if tp is not None:
+            if denormalize:
+                raise NotImplementedError('reverse mode through the de-normalising direction of the batch-norm bijector '
+                                          '(sampling direction) is not built')
+            batch_stats = mean is self._mean  # statistics() handed out the batch moments: gradients flow through them
+            m_, v_ = (mean.copy(), var.copy()) if batch_stats else (mean, var)  # the layer's buffers are reused per call
+            D, eps, gamma, beta = self.D, self.epsilon, self.gamma, self.beta
+
+            def bw():  # TF autodiff through tf.nn.batch_normalization + tf.nn.moments (and the bijector's log-det)
+                has_o, has_l = tp.has(out), (ldj is not None and tp.has(ldj))
+                if not (has_o or has_l):
+                    return
+                g_out = tp.grad(out) if has_o else Tensor.zeros((B, D))
+                G = None
+                if has_l:
+                    G = Tensor.zeros((1, ))
+                    c.lib.vms_sum_all(tp.grad(ldj).ptr, B, 1.0, G.ptr, c.stream)
+                ws = Tensor((int(c.lib.vms_batchnorm_backward_workspace(D)) // 4 + 1, ))
+                g_x = tp.grad(x)
+                c.lib.vms_batchnorm_backward(x.ptr, x.ld, B, D, m_.ptr, v_.ptr, gamma.ptr, eps, 1 if batch_stats else 0,
+                                             g_out.ptr, g_out.ld, _ptr(G), g_x.ptr, g_x.ld, tp.grad(gamma).ptr,
+                                             tp.grad(beta).ptr, ws.ptr, c.stream)
+
+            tp.record(bw)
         return out, ldj
 
 
 class KerasBatchNormalization(Layer):
     """tf.keras.layers.BatchNormalization() over the last axis of a [B, D] tensor (mappings.py:113-114): batch moments
-    and a moving-average update when training, moving statistics otherwise.  Forward only: `VAE.fit` has no reverse mode
-    through batch statistics."""
+    and a moving-average update when training, moving statistics otherwise; reverse mode through the batch statistics by
+    `vms_batchnorm_backward` when a tape is active."""
 
     def __init__(self, name='batch_normalization'):
         super(KerasBatchNormalization, self).__init__(name=name)
@@ -659,6 +684,7 @@ class BatchNormalization(Bijector):
         self.training = training
         self.name = name
         self.state = None
+        self._holder = _BatchNormWeights(self)
 
     def _state(self, v):
         if self.state is None:
@@ -675,7 +701,25 @@ class BatchNormalization(Bijector):
         return st.apply(y, mean, var, denormalize=False, want_ldj=True)
 
     def _layers(self):
+        return [self._holder]  # gamma / beta are trainable variables of the model, as in tfp
+
+
+class _BatchNormWeights(Layer):
+    """Exposes the variables of a batch-norm bijector (created lazily at its first call) to `Model.weights`."""
+
+    def __init__(self, owner):
+        super(_BatchNormWeights, self).__init__(name=owner.name + '_variables')
+        self.owner_ref = [owner]  # (a list: keep the bijector out of Layer._sublayers' attribute scan)
+
+    def _sublayers(self):
         return []
+
+    @property
+    def weights(self):
+        st = self.owner_ref[0].state
+        return st.weights() if st is not None else []
+
+    trainable_weights = weights
 
 
 # ================================================================================================ distributions

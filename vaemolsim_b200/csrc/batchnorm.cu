@@ -80,6 +80,63 @@ __global__ void bn_coeffs_kernel(const float* __restrict__ mean, const float* __
   }
 }
 
+// ---- reverse mode of the NORMALISING direction  y = (x - mean) rsqrt(var + eps) gamma + beta  (Keras layer in training /
+// inference mode; the tfp bijector's inverse, whose log-det sum_d log gamma_d - 0.5 log(var_d + eps) is added to every row).
+// Column sums in a fixed order (one block per 32 columns, 8 row slots, doubles):
+//   s1_d = sum_b g[b, d],   s2_d = sum_b g[b, d] xhat[b, d]      with xhat = (x - mean) rsqrt(var + eps)
+__global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ g,
+                                                          int64_t ld_g, int64_t B, int D, const float* __restrict__ mean,
+                                                          const float* __restrict__ var, float eps, double* __restrict__ s1,
+                                                          double* __restrict__ s2) {
+  __shared__ double sh1[8][33], sh2[8][33];
+  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + lane;
+  double a1 = 0.0, a2 = 0.0;
+  if (d < D) {
+    const float m = mean[d], r = 1.0f / sqrtf(var[d] + eps);
+    for (int64_t b = slot; b < B; b += 8) {
+      const float gv = g[b * ld_g + d];
+      a1 += (double)gv;
+      a2 += (double)(gv * ((x[b * ld_x + d] - m) * r));
+    }
+  }
+  sh1[slot][lane] = a1;
+  sh2[slot][lane] = a2;
+  __syncthreads();
+  if (slot == 0 && d < D) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int k = 0; k < 8; ++k) { t1 += sh1[k][lane]; t2 += sh2[k][lane]; }
+    s1[d] = t1;
+    s2[d] = t2;
+  }
+}
+
+// g_x += gamma r (g - [batch_stats] (s1 + xhat s2) / B) - [batch_stats] G (x - mean) r^2 / B;   one thread per element.
+// Block (0, 0) row 0 also adds the parameter gradients: g_beta += s1, g_gamma += s2 + G / gamma.
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ g, int64_t ld_g, int64_t B,
+                                    int D, const float* __restrict__ mean, const float* __restrict__ var,
+                                    const float* __restrict__ gamma, float eps, int batch_stats, const double* __restrict__ s1,
+                                    const double* __restrict__ s2, const float* __restrict__ G_ptr, float* __restrict__ g_x,
+                                    int64_t ld_gx, float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int64_t b = i / D;
+  const int d = (int)(i - b * D);
+  const float gm = gamma ? gamma[d] : 1.f;
+  const float r = 1.0f / sqrtf(var[d] + eps);
+  const float xc = x[b * ld_x + d] - mean[d];
+  const float G = G_ptr ? *G_ptr : 0.f;
+  float dx = g[b * ld_g + d];
+  if (batch_stats) dx -= (float)((s1[d] + (double)(xc * r) * s2[d]) / (double)B);
+  dx *= gm * r;
+  if (batch_stats) dx -= G * xc * r * r / (float)B;
+  g_x[b * ld_gx + d] += dx;
+  if (b == 0) {
+    if (g_beta) g_beta[d] += (float)s1[d];
+    if (g_gamma) g_gamma[d] += (float)s2[d] + G / gm;
+  }
+}
+
 __global__ void broadcast_scalar_kernel(const float* __restrict__ s, int64_t n, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = *s;
@@ -119,6 +176,26 @@ vms_status vms_batchnorm_coeffs(const float* mean, const float* var, const float
   VMS_REQUIRE(mean && var && scale && shift && D >= 1 && eps >= 0.f, VMS_ERR_INVALID_ARG, "batchnorm_coeffs: bad arguments");
   bn_coeffs_kernel<<<1, 256, 0, as_stream(stream)>>>(mean, var, gamma, beta, D, eps, denormalize, scale, shift, ldj);
   VMS_LAUNCH_CHECK("bn_coeffs_kernel");
+  return VMS_OK;
+}
+
+size_t vms_batchnorm_backward_workspace(int D) { return (size_t)2 * (size_t)(D > 0 ? D : 1) * sizeof(double); }
+
+vms_status vms_batchnorm_backward(const float* x, int64_t ld_x, int64_t B, int D, const float* mean, const float* var,
+                                  const float* gamma, float eps, int batch_stats, const float* g_out, int64_t ld_g,
+                                  const float* g_ldj_total, float* g_x, int64_t ld_gx, float* g_gamma, float* g_beta,
+                                  void* workspace, vms_stream stream) {
+  VMS_REQUIRE(x && mean && var && g_out && g_x && workspace, VMS_ERR_INVALID_ARG, "batchnorm_backward: NULL pointer");
+  VMS_REQUIRE(B >= 1 && D >= 1, VMS_ERR_SHAPE, "batchnorm_backward: need B >= 1, D >= 1");
+  cudaStream_t st = as_stream(stream);
+  double* s1 = (double*)workspace;
+  double* s2 = s1 + D;
+  bn_bwd_sums_kernel<<<(D + 31) / 32, 256, 0, st>>>(x, ld_x, g_out, ld_g, B, D, mean, var, eps, s1, s2);
+  VMS_LAUNCH_CHECK("bn_bwd_sums_kernel");
+  bn_bwd_apply_kernel<<<(unsigned)((B * D + 255) / 256), 256, 0, st>>>(x, ld_x, g_out, ld_g, B, D, mean, var, gamma, eps,
+                                                                       batch_stats, s1, s2, g_ldj_total, g_x, ld_gx, g_gamma,
+                                                                       g_beta);
+  VMS_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return VMS_OK;
 }
 

@@ -50,16 +50,7 @@ class Model(P.Layer):
         return total
 
     def _check_trainable(self):
-        stack, seen = [self], set()
-        while stack:
-            lay = stack.pop()
-            if id(lay) in seen:
-                continue
-            seen.add(id(lay))
-            if isinstance(lay, P.KerasBatchNormalization) or getattr(lay, 'batch_norm', False):
-                raise NotImplementedError('training through batch normalisation is not built (SURVEY.md 8f rank 3): reverse '
-                                          'mode of the batch statistics is missing')
-            stack += lay._sublayers()
+        pass  # every layer of this package has a reverse mode now (batch normalisation included)
 
     def _trainer(self):
         from . import _autodiff
