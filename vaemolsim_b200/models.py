@@ -97,6 +97,57 @@ class Model(P.Layer):
             tot, n = tot + float(self._loss_tensor(xb, yb, False).numpy()) * xb.shape[0], n + xb.shape[0]
         return tot / max(n, 1)
 
+    # ------------------------------------------------------------------ weights in / out (Keras `get_weights` protocol)
+    # The reference's users move trained weights with Keras (`model.save_weights`, `model.get_weights()`, models.py:470-572;
+    # the `order_seed` of RQSSplineMAF exists so that a re-built flow matches saved weights, flows.py:572-575).  TF / h5py
+    # are not available here, so the exchange format is the Keras VARIABLE ORDER itself: `get_weights()` / `set_weights()`
+    # list every variable in the order Keras tracks them for the same composition (layer creation order; per Dense kernel
+    # then bias; per MADE layer kernel, bias[, conditional kernel]; batch norm gamma, beta, moving mean, moving variance),
+    # and `save_weights` / `load_weights` store that list as an .npz -- on the TF side
+    # `np.savez(path, *keras_model.get_weights())` produces a file `load_weights` reads, and
+    # `keras_model.set_weights([f[k] for k in f.files])` consumes one written here.  MADE kernels are re-masked on import.
+    def _unique_weights(self):
+        out = []
+        for w in self.weights:
+            if not any(w is u for u in out):
+                out.append(w)
+        return out
+
+    def get_weights(self):
+        return [w.numpy() for w in self._unique_weights()]
+
+    def set_weights(self, arrays):
+        ws = self._unique_weights()
+        arrays = list(arrays)
+        if len(arrays) != len(ws):
+            raise ValueError('set_weights: the model has %d variables, got %d arrays (build the model by calling it once on '
+                             'data first)' % (len(ws), len(arrays)))
+        c = ctx()
+        for w, a in zip(ws, arrays):
+            a = np.ascontiguousarray(a, np.float32)
+            if tuple(a.shape) != tuple(w.shape):
+                raise ValueError('set_weights: shape %s does not match variable of shape %s' % (a.shape, w.shape))
+            mask = getattr(w, '_grad_mask', None)
+            if mask is not None:
+                a = np.ascontiguousarray(a * mask.numpy())
+            if w.contiguous:
+                c.lib.vms_memcpy_h2d(w.ptr, a.ctypes.data, a.nbytes, c.stream)
+                c.synchronize()
+            else:
+                w.assign_cols(0, Tensor.from_numpy(a))
+        f = getattr(self, '_fused', None)
+        if f is not None:
+            f.invalidate()
+
+    def save_weights(self, path):
+        arrs = self.get_weights()
+        np.savez(path, **{'arr_%d' % i: a for i, a in enumerate(arrs)})
+
+    def load_weights(self, path):
+        with np.load(path) as f:
+            keys = sorted(f.files, key=lambda k: int(k.split('_')[-1]) if k.split('_')[-1].isdigit() else 0)
+            self.set_weights([f[k] for k in keys])
+
     def predict(self, x, batch_size=32, verbose=0):
         x = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
         outs = [self.predict_step(Tensor.from_numpy(x[i:i + batch_size])).numpy() for i in range(0, len(x), batch_size)]
