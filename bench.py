@@ -61,6 +61,7 @@ def parse():
     ap.add_argument('--no-extras', action='store_true', help='skip roofline microbenchmarks and the CPU baseline')
     ap.add_argument('--collective', default='auto', choices=['auto', 'peer', 'nccl'],
                     help='N > 1: fused NVLink peer-memory allreduce+Adam kernel (peer), NCCL allreduce + Adam (nccl)')
+    ap.add_argument('--c4b-only', action='store_true', help='development aid: run only the C4b MC leg and print it')
     ap.add_argument('--mc-only', action='store_true', help='development aid: run only the MC leg and print it')
     return ap.parse_args()
 
@@ -471,6 +472,159 @@ def mc_flips_vs_oracle(v, model, chains=1024, steps=20):
             'host_stream_reruns': int(mc.host_stream_reruns)}
 
 
+# ---------------------------------------------------------------------------------------------- C4b: the MC notebook's model
+C4B_FLOP = 64352  # 2 encoder, 2 MAF prior, 2 decoder-mapping evaluations, 4 MADE passes per proposal
+C4B_LABEL = ('C4b: MC notebook model (enc 2-200-2 Normal(1); prior RQSSplineMAF 4 blocks K=20 H=40 over N(0,1); dec FCDeepNN '
+             '1-200-(2,2) + AutoregressiveBlockwise(2 Normal, cond 1, hidden [10,100,10])), Gaussian-mixture energy, '
+             '%d chains x %d steps' % (MC_CHAINS, MC_STEPS))
+
+
+def build_c4b_model(v, seed=2003):
+    """examples/MC_Moves_with_VAEs.ipynb cells 11-20 through the host API, randomly initialised; the (untrained) decoder's
+    output layer is aimed at the mixture's main component so that the chains see both accepts and rejects."""
+    import vaemolsim_b200._protocols as PR
+    d = v.dists
+    v.set_seed(seed)
+    enc = v.models.MappingToDistribution(PR.IndependentNormal(1), name='encoder')
+    dec_dist = d.AutoregressiveBlockwise(2, [d.Normal] * 2, conditional=True, conditional_event_shape=(1, ),
+                                         auto_net_params={'hidden_units': [10, 100, 10]})
+    dec = v.models.MappingToDistribution(dec_dist, name='decoder')
+    flow = v.flows.RQSSplineMAF(num_blocks=4, rqs_params={'bin_range': [-10.0, 10.0], 'num_bins': 20, 'hidden_dim': 40})
+    flow(np.zeros((2, 1), np.float32))
+    prior = d.FlowedDistribution(flow, PR.DistributionLambda(lambda t: PR.StandardNormal(t.shape[0], 1)), name='prior')
+    model = v.models.VAE(enc, dec, prior)
+    model(np.zeros((2, 2), np.float32))
+    rng = np.random.default_rng(seed)
+    last = [l for l in dec.mapping.layer_list if hasattr(l, 'kernel')][-1]
+    inv_softplus = lambda y: float(np.log(np.expm1(y)))
+    last.assign(last.kernel.numpy() * np.float32(0.2),
+                np.array([-0.5, inv_softplus(0.1), 0.0, inv_softplus(0.5)], np.float32))
+    net = dec_dist.auto_net
+    arrs = []
+    for k, lay in enumerate(net.layers):
+        sc = np.float32(0.2 if k == len(net.layers) - 1 else 1.0)
+        arrs += [lay.kernel.numpy() * sc, rng.normal(0, 0.3, lay.units).astype(np.float32) * sc, net.cond_kernels[k].numpy() * sc]
+    net.set_weights(arrs)
+    for bij in flow.chain.bijectors:
+        msb = bij.bijector_fn
+        for sub in (msb.bin_widths, msb.bin_heights, msb.knot_slopes):
+            sub.set_weights([a for lay in sub.layers for a in (lay.kernel.numpy(), rng.normal(0, 0.3, lay.units).astype(np.float32))])
+    return model
+
+
+def c4b_oracle_params(model):
+    """The product model's weights in the layout of oracle.mcmc.init_vae_b (checker side only)."""
+    dense = lambda m: [(l.kernel.numpy(), l.bias.numpy()) for l in m.layer_list if hasattr(l, 'kernel')]
+    net = model.decoder.distribution.auto_net
+    made = [dict(W=lay.kernel.numpy(), b=lay.bias.numpy(), Wc=net.cond_kernels[k].numpy(), mask=None)
+            for k, lay in enumerate(net.layers)]
+    maf = []
+    for bij in model.prior.flow.chain.bijectors[::-1]:
+        msb = bij.bijector_fn
+        maf.append({key: [dict(W=lay.kernel.numpy(), b=lay.bias.numpy(), Wc=None, mask=None) for lay in sub.layers]
+                    for key, sub in (('w', msb.bin_widths), ('h', msb.bin_heights), ('s', msb.knot_slopes))})
+    return dict(enc=dense(model.encoder.mapping), dec=dense(model.decoder.mapping), made=made, maf=maf, num_bins=20,
+                bin_range=(-10.0, 10.0), hidden=200)
+
+
+def gmm_start(n, seed=5001):
+    """Chains start in the notebook's data distribution (cell 5, 41: `mc_sim.run(data_sample, ...)`)."""
+    rng = np.random.default_rng(seed)
+    probs = np.array([0.7, 0.2, 0.1])
+    locs = np.array([[-0.5, 0.0], [1.0, 2.0], [-1.5, 0.0]], np.float32)
+    scales = np.array([[0.05, 0.5], [1.0, 0.5], [0.5, 0.2]], np.float32)
+    k = rng.choice(3, size=n, p=probs)
+    return (locs[k] + scales[k] * rng.standard_normal((n, 2))).astype(np.float32)
+
+
+def c4b_check_and_cpu(v, model, chains=2048, steps=3):
+    """Checker + CPU baseline of the C4b leg (rank 0): the oracle restatement of mcmc.py over the NumPy notebook model with
+    the product's weights, timed on the host cores; its decisions against the device path's under the same noise and
+    uniforms (chains whose trace differs anywhere)."""
+    import vaemolsim_b200._protocols as PR
+    from oracle import mcmc as omc
+    P = c4b_oracle_params(model)
+    x0 = gmm_start(MC_CHAINS)[:chains]
+    twin, rng = omc.OracleVAEb(P, noise_seed=888), np.random.default_rng(5002)
+    xo, eo = x0, None
+    acc_o = np.empty((steps, chains), bool)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        xo, eo, acc_o[s] = omc.single_step(twin, omc.gmm_energy, rng, xo, eo)
+    dt = time.perf_counter() - t0
+    mc = v.mcmc.MCMC(model, v.mcmc.GaussianMixtureEnergy(), random_seed=5002)
+    v.set_seed(888)
+    xd, ed = x0, None
+    acc_d = np.empty((steps, chains), bool)
+    for s in range(steps):
+        xd, ed = mc.single_step(xd, energies=ed)
+        acc_d[s] = mc._last_acc.numpy().astype(bool)
+    return ({'value': chains * steps / dt, 'unit': 'proposals/s', 'cores': cpu_threads(), 'kind': 'port',
+             'sample': '%d steps of %d chains, oracle/mcmc.py (restatement of mcmc.py:68-130) over the NumPy notebook model '
+                       '(oracle.mcmc.OracleVAEb)' % (steps, chains)},
+            {'chains': chains, 'steps': steps, 'flipped_chains': int((acc_d != acc_o).any(axis=0).sum()),
+             'accepted_device': int(acc_d.sum()), 'accepted_oracle': int(acc_o.sum())})
+
+
+def c4b_bench(v, grp, ffma_peak, reps=2):
+    """MC proposals/sec for the notebook's model family: chains sharded over the ranks, no collective.  This family runs
+    op-by-op (MAF forward / inverse, MADE passes, autoregressive sampling, mixture energy, accept kernel) with the chain
+    state resident on the device; sampling noise and uniforms are host PCG64 draws uploaded per step, as in the reference."""
+    from vaemolsim_b200 import parallel
+    c = v._abi.ctx()
+    lo, hi = parallel.shard_rows(MC_CHAINS, grp.rank, grp.world)
+    B = hi - lo
+    model = build_c4b_model(v)
+    energy = v.mcmc.GaussianMixtureEnergy()
+    mc = v.mcmc.MCMC(model, energy, random_seed=5002)
+    x0 = gmm_start(MC_CHAINS)[lo:hi]
+    v.set_seed(888 + grp.rank)
+    xd = v.Tensor.from_numpy(np.ascontiguousarray(x0))
+    xd, ed = mc.run_device(None, n_steps=3, configs_dev=xd)
+    ev = Events(c, reps)
+    grp.barrier()
+    c.synchronize()
+    l0 = v._abi.launch_count()
+    t0 = time.perf_counter()
+    for i in range(reps):
+        ev.record(2 * i)
+        xd, ed = mc.run_device(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed)
+        ev.record(2 * i + 1)
+    c.synchronize()
+    wall = time.perf_counter() - t0
+    grp.barrier()
+    launches = v._abi.launch_count() - l0
+    dev_ms = grp.max(sum(ev.elapsed_ms(2 * i, 2 * i + 1) for i in range(reps)))
+    acc_rate = mc.acceptance_rate
+    mc2 = v.mcmc.MCMC(model, energy, random_seed=5002)
+    mc2.run(x0, n_steps=2)
+    grp.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        xe, ee = mc2.run(x0, n_steps=MC_STEPS)
+    e2e_s = grp.max(time.perf_counter() - t0)
+    tot = MC_CHAINS * MC_STEPS * reps
+    tflops = tot * C4B_FLOP / (dev_ms * 1e-3) / 1e12
+    res = {'metric': 'MC proposals/sec', 'value': tot / (dev_ms * 1e-3), 'unit': 'proposals/s', 'workload': C4B_LABEL,
+           'chains_global': MC_CHAINS, 'chains_per_gpu': B, 'steps': MC_STEPS, 'runs_timed': reps,
+           'scaling': 'strong (65,536 chains split over the GPUs, no data-path collective)',
+           'ms_per_mc_step': dev_ms / (reps * MC_STEPS), 'host_wall_ms_per_mc_step': wall / (reps * MC_STEPS) * 1e3,
+           'gpu_launches': int(launches), 'launches_per_mc_step': launches / (reps * MC_STEPS), 'acceptance_rate': acc_rate,
+           'path': 'op-by-op kernels, chain state device-resident (MCMC.run_device)',
+           'e2e': {'value': tot / e2e_s, 'unit': 'proposals/s', 'h2d_bytes_per_step': int(B * (8 + 16 + 8)),
+                   'd2h_bytes_per_step': int(B * 12 / MC_STEPS), 'ms_per_mc_step': e2e_s / (reps * MC_STEPS) * 1e3,
+                   'api': 'MCMC.run(configs, n_steps=%d) from host arrays (per step: noise + uniforms uploaded)' % MC_STEPS},
+           'roofline': {'bound': 'ffma', 'kernel': 'whole MC step (op-by-op)', 'achieved': tflops / grp.world,
+                        'peak': ffma_peak, 'unit': 'TFLOP/s', 'frac': tflops / grp.world / ffma_peak, 'traffic': None,
+                        'algorithmic_flop_per_proposal': C4B_FLOP,
+                        'peak_kind': 'FP32 FFMA issue peak measured in this run (csrc/probe.cu)',
+                        'note': 'launch- and latency-bound: ~%d small kernels per MC step, no fused kernel for this family'
+                                % round(launches / (reps * MC_STEPS))}}
+    if grp.rank == 0:
+        res['cpu_baseline'], res['flips_vs_oracle'] = c4b_check_and_cpu(v, model)
+    return res
+
+
 def mc_bench(v, grp, ffma_peak, reps=3):
     """MC proposals/sec: chains sharded over ranks with no collective; the accept uniforms are ONE PCG64 stream
     whose columns every rank regenerates on the device for its own chains, and the sampling noise is keyed by the global
@@ -756,8 +910,8 @@ def run_b200(args, w):
     grp = parallel.Group()
     rank, world = grp.rank, grp.world
     c = v._abi.ctx()
-    if args.mc_only:
-        line = mc_bench(v, grp, measured_peaks(v)['fp32_ffma_tflops'])
+    if args.mc_only or args.c4b_only:
+        line = (c4b_bench if args.c4b_only else mc_bench)(v, grp, measured_peaks(v)['fp32_ffma_tflops'])
         if rank == 0:
             print(json.dumps(line), flush=True)
         grp.close()
@@ -777,6 +931,10 @@ def run_b200(args, w):
             legs['c4a_mc'] = mc_bench(v, grp, peaks['fp32_ffma_tflops'])
         except Exception as ex:  # the headline line must survive a failure of an extra leg
             legs['c4a_mc'] = {'error': '%s: %s' % (type(ex).__name__, ex)}
+        try:
+            legs['c4b_mc'] = c4b_bench(v, grp, peaks['fp32_ffma_tflops'])
+        except Exception as ex:
+            legs['c4b_mc'] = {'error': '%s: %s' % (type(ex).__name__, ex)}
         try:
             legs['c5'] = large_batch_leg(v, w, r['opt'], grp, peaks, args.collective)
         except Exception as ex:

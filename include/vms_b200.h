@@ -277,9 +277,20 @@ vms_status vms_dist_select(const float* coords, const int64_t* row_splits, int64
 vms_status vms_mc_accept(const double* E_new, const double* E_old, const float* fwd, const float* rev,
                          const double* log_u, int64_t B, int D, const float* x_old, float* x_new_inout,
                          double* E_out, uint8_t* acc, unsigned long long* n_acc, vms_stream stream);
+/* The same rule for an energy callback that returns float32 (a tfp log_prob, MC_Moves_with_VAEs.ipynb cell 38): NumPy then
+ * evaluates mcmc.py:116 in float32, ((E_new + rev) - E_old) - fwd, and only the comparison with log_u is in float64.     */
+vms_status vms_mc_accept_f32(const float* E_new, const float* E_old, const float* fwd, const float* rev,
+                             const double* log_u, int64_t B, int D, const float* x_old, float* x_new_inout, float* E_out,
+                             uint8_t* acc, unsigned long long* n_acc, vms_stream stream);
 /* Device-resident energies so the MC loop is not PCIe-bound (SURVEY 7 "hard parts"):
  *   kind 0: tests/test_mcmc.py:28-32  E = sum_d (x_d - means_d)^2, evaluated in float64 like the NumPy callback. */
 vms_status vms_energy_quadratic(const float* x, int64_t B, int D, const double* means, double* E, vms_stream stream);
+/*   Gaussian-mixture log-density, the "energy" of examples/MC_Moves_with_VAEs.ipynb cell 5 / 38 (tfp Mixture of Independent
+ *   Normals, `data_dist.log_prob(configs)`): log_w [n_comp] = log cat probabilities, loc / scale [n_comp, D]; float32
+ *   arithmetic as tfp (per-component sums, max-shifted logsumexp), float32 out like `log_prob(...).numpy()`; pair it
+ *   with vms_mc_accept_f32.  n_comp <= 16.                                                                            */
+vms_status vms_energy_gmm(const float* x, int64_t B, int D, int n_comp, const float* log_w, const float* loc,
+                          const float* scale, float* E, vms_stream stream);
 
 /* ------------------------------------------------------------------------------- K8: optimiser
  * Keras Adam (tests/test_models.py:181: lr 1e-3, beta 0.9 / 0.999, eps 1e-7), on a flat parameter buffer:

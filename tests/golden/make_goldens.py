@@ -5,6 +5,8 @@
 * mcmc_reference.npz -- produced by the REFERENCE's own `vaemolsim/mcmc.py` (loaded by file path from /root/reference;
   it imports only NumPy) driving `oracle.mcmc.OracleVAE`: per-step accept decisions, configurations, energies, counters
   and the log-probability traces fed to the acceptance rule.  Pins `oracle.mcmc.single_step` and `vms_mc_accept`.
+* mcmc_reference_c4b.npz -- the same driver on `oracle.mcmc.OracleVAEb` (the MC notebook's model family: MAF prior,
+  conditional autoregressive decoder) with the notebook's Gaussian-mixture log-density as energy callback.
 * maf_orders.json    -- MAF block input orders computed with the reference's recipe (flows.py:606-621) for the seeds
   named in SURVEY 8c item 10.
 * elbo_c1.npz / elbo_c2.npz -- oracle ELBO forward / backward outputs on seeded inputs (regression fixtures for the
@@ -66,6 +68,41 @@ def make_mcmc(prior, tag, n_chains=64, n_steps=5):
     print(tag, 'acceptance', mc.acceptance_rate)
 
 
+def gmm_sample(rng, n):
+    """Draws from the notebook's data distribution (cell 5): the chains start in the mixture."""
+    k = rng.choice(3, size=n, p=omc.GMM_PROBS.astype(np.float64) / omc.GMM_PROBS.astype(np.float64).sum())
+    return (omc.GMM_LOCS[k] + omc.GMM_SCALES[k] * rng.standard_normal((n, 2))).astype(np.float32)
+
+
+def make_mcmc_c4b(n_chains=256, n_steps=5, hidden=64):
+    """C4b (MC_Moves_with_VAEs.ipynb cell 39-41): the reference's mcmc.py driving the notebook's model family -- MAF prior,
+    conditional AutoregressiveBlockwise decoder, Gaussian-mixture log-density as the energy callback."""
+    ref = load_reference_mcmc()
+    P = omc.init_vae_b(2003, hidden=hidden)
+    x0 = gmm_sample(np.random.default_rng(5001), n_chains)
+    mc = ref.MCMC(omc.OracleVAEb(P, noise_seed=888), omc.gmm_energy, random_seed=5002)
+    twin = omc.OracleVAEb(P, noise_seed=888)
+    twin_rng = np.random.default_rng(5002)
+    configs, energies = x0, None
+    tconfigs, tenergies = x0, None
+    out = {}
+    for s in range(n_steps):
+        configs, energies = mc.single_step(configs, energies=energies)
+        trace = {}
+        tconfigs, tenergies, acc = omc.single_step(twin, omc.gmm_energy, twin_rng, tconfigs, tenergies, trace)
+        assert np.array_equal(configs, tconfigs) and np.array_equal(energies, tenergies), 'oracle != reference mcmc.py'
+        out['configs_%d' % s] = configs.copy()
+        out['energies_%d' % s] = energies.copy()
+        out['acc_%d' % s] = acc
+        for k, v in trace.items():
+            out['%s_%d' % (k, s)] = v
+    out['num_trials'] = np.float64(mc._num_trials)
+    out['num_acc'] = np.float64(mc._num_acc)
+    out['x0'] = x0
+    np.savez_compressed(os.path.join(HERE, 'mcmc_reference_c4b.npz'), **out)
+    print('c4b acceptance', mc.acceptance_rate)
+
+
 def make_orders():
     res = {}
     for nb, D, seed in ((3, 3, 42), (4, 6, 42), (4, 2, 7)):
@@ -87,6 +124,7 @@ def make_elbo(prior, tag, B=64):
 if __name__ == '__main__':
     make_mcmc('normal', 'c4a')
     make_mcmc('realnvp', 'flow')
+    make_mcmc_c4b()
     make_orders()
     make_elbo('normal', 'c1')
     make_elbo('realnvp', 'c2')

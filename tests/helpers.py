@@ -73,3 +73,38 @@ def vae_from_oracle(v, P, max_batch=4096, weight=1.0):
             sb.heads.assign(np.concatenate([blk[k][0] for k in ('w', 'h', 's')], axis=1),
                             np.concatenate([blk[k][1] for k in ('w', 'h', 's')]))
     return model
+
+
+def vae_b_from_oracle(v, P):
+    """The MC notebook's model family (examples/MC_Moves_with_VAEs.ipynb cells 11-20) through the product's host API, with
+    the weights of `oracle.mcmc.init_vae_b`."""
+    from vaemolsim_b200 import dists, flows, models
+    import vaemolsim_b200._protocols as PR
+    enc = models.MappingToDistribution(PR.IndependentNormal(1), name='encoder')
+    dec_dist = dists.AutoregressiveBlockwise(2, [dists.Normal] * 2, conditional=True, conditional_event_shape=(1, ),
+                                             auto_net_params={'hidden_units': [L['W'].shape[1] for L in P['made'][:-1]]})
+    dec = models.MappingToDistribution(dec_dist, name='decoder')
+    enc.mapping.hidden_dim = [P['hidden']]
+    dec.mapping.hidden_dim = [P['hidden']]
+    nb = len(P['maf'])
+    H = P['maf'][0]['w'][0]['W'].shape[1]
+    flow = flows.RQSSplineMAF(num_blocks=nb, rqs_params=dict(bin_range=list(P['bin_range']), num_bins=P['num_bins'],
+                                                             hidden_dim=H))
+    flow(np.zeros((2, 1), np.float32))
+    prior = dists.FlowedDistribution(flow, PR.DistributionLambda(lambda t: PR.StandardNormal(t.shape[0], 1)), name='prior')
+    model = models.VAE(enc, dec, prior)
+    model(np.zeros((2, 2), np.float32))  # build
+    dense = lambda m: [l for l in m.layer_list if hasattr(l, 'kernel')]
+    for lay, (W, b) in zip(dense(enc.mapping), P['enc']):
+        lay.assign(W, b)
+    for lay, (W, b) in zip(dense(dec.mapping), P['dec']):
+        lay.assign(W, b)
+    arrs = []
+    for L in P['made']:
+        arrs += [L['W'], L['b'], L['Wc']]
+    dec_dist.auto_net.set_weights(arrs)
+    for bij, blk in zip(flow.chain.bijectors[::-1], P['maf']):
+        msb = bij.bijector_fn
+        for key, net in (('w', msb.bin_widths), ('h', msb.bin_heights), ('s', msb.knot_slopes)):
+            net.set_weights([a for L in blk[key] for a in (L['W'], L['b'])])
+    return model

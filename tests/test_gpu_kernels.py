@@ -432,6 +432,32 @@ def test_mc_accept_bit_exact_vs_reference_mcmc(vms, tag):
     assert float(n_acc.numpy()[0]) == float(g['num_acc'])
 
 
+def test_mc_accept_f32_bit_exact_vs_reference_mcmc_c4b(vms):
+    """A float32 energy callback (tfp log_prob, MC notebook cell 38) makes NumPy evaluate mcmc.py:116 in float32:
+    vms_mc_accept_f32 reproduces the reference driver's decisions from the same inputs; vms_energy_gmm against the oracle."""
+    v = vms
+    c = v._abi.ctx()
+    g = np.load(os.path.join(GOLD, 'mcmc_reference_c4b.npz'))
+    n_acc = v.Tensor.zeros((1, ), np.uint64)
+    lw, loc, sc = T(v, np.log(omc.GMM_PROBS)), T(v, omc.GMM_LOCS), T(v, omc.GMM_SCALES)
+    for s in range(5):
+        B, D = g['x_old_%d' % s].shape
+        assert g['e_new_%d' % s].dtype == np.float32
+        d = dict(e_new=T(v, g['e_new_%d' % s]), e_old=T(v, g['e_old_%d' % s]), fwd=T(v, g['fwd_%d' % s]),
+                 rev=T(v, g['rev_%d' % s]), lr=T(v, g['log_rand_%d' % s], np.float64), x_old=T(v, g['x_old_%d' % s]),
+                 x_new=T(v, g['x_new_%d' % s]))
+        e_dev = v.Tensor((B, ), np.float32)
+        c.lib.vms_energy_gmm(d['x_new'].ptr, B, D, 3, lw.ptr, loc.ptr, sc.ptr, e_dev.ptr, c.stream)
+        np.testing.assert_allclose(e_dev.numpy(), g['e_new_%d' % s], rtol=2e-6, atol=2e-6)
+        e_out, acc = v.Tensor((B, ), np.float32), v.Tensor((B, ), np.uint8)
+        c.lib.vms_mc_accept_f32(d['e_new'].ptr, d['e_old'].ptr, d['fwd'].ptr, d['rev'].ptr, d['lr'].ptr, B, D,
+                                d['x_old'].ptr, d['x_new'].ptr, e_out.ptr, acc.ptr, n_acc.ptr, c.stream)
+        assert np.array_equal(acc.numpy().astype(bool), g['acc_%d' % s])
+        assert np.array_equal(d['x_new'].numpy(), g['configs_%d' % s])
+        assert np.array_equal(e_out.numpy(), g['energies_%d' % s])
+    assert float(n_acc.numpy()[0]) == float(g['num_acc'])
+
+
 def test_mc_accept_random_and_energy(vms):
     v = vms
     c = v._abi.ctx()

@@ -577,6 +577,56 @@ def test_fused_mc_matches_reference_mcmc_py_goldens(vms, device_rng):
     assert mc._rng.random() == want_next.random()
 
 
+def test_mc_c4b_notebook_model_matches_reference_mcmc_py_goldens(vms):
+    """C4b (MC_Moves_with_VAEs.ipynb cell 39-41): MAF prior + conditional autoregressive decoder + Gaussian-mixture energy,
+    op-by-op kernels with the chain state on the device, against the decisions of the REFERENCE's own mcmc.py
+    (tests/golden/make_goldens.py): every step restarted from the golden state, same sampling noise (host generator, same
+    seed and draw order as the oracle twin), same PCG64 uniforms."""
+    v = vms
+    import vaemolsim_b200._protocols as PR
+    from helpers import vae_b_from_oracle
+    g = np.load(os.path.join(GOLD, 'mcmc_reference_c4b.npz'))
+    P = omc.init_vae_b(2003, hidden=64)
+    model = vae_b_from_oracle(v, P)
+    energy = v.mcmc.GaussianMixtureEnergy()
+    mc = v.mcmc.MCMC(model, energy, random_seed=5002)
+    assert mc._fused_plan() is None
+    v.set_seed(888)
+    safe_total = flips = 0
+    for s in range(5):
+        x_old, e_old = g['x_old_%d' % s], g['e_old_%d' % s]
+        x1 = v.as_tensor(x_old)
+        x2, e_out, acc, n_acc = mc._device_step(x1, v.Tensor.from_numpy(e_old))
+        assert e_out.dtype == np.float32  # the callback's type, like the reference's returned energies
+        acc = acc.numpy().astype(bool)
+        margin = np.abs(g['e_new_%d' % s] + g['rev_%d' % s] - g['e_old_%d' % s] - g['fwd_%d' % s] - g['log_rand_%d' % s])
+        safe = margin > 2e-3
+        safe_total += int(safe.sum())
+        flips += int((acc != g['acc_%d' % s]).sum())
+        assert np.array_equal(acc[safe], g['acc_%d' % s][safe])
+        same = acc == g['acc_%d' % s]
+        assert_close(x2.numpy()[same], g['configs_%d' % s][same], rtol=1e-5, atol=5e-5, what='configs step %d' % s)
+        assert_close(e_out.numpy()[same], g['energies_%d' % s][same], rtol=1e-5, atol=2e-4, what='energies step %d' % s)
+        assert int(n_acc.numpy()[0]) == int(acc.sum())
+    assert safe_total > 1200 and flips <= 2
+    # whole-loop entry points: `run` keeps the state on the device and equals n single_steps under the same seeds
+    x0 = g['x0']
+    a, b = v.mcmc.MCMC(model, energy, random_seed=3), v.mcmc.MCMC(model, energy, random_seed=3)
+    v.set_seed(21)
+    xa, ea = a.run(x0, n_steps=4)
+    v.set_seed(21)
+    xb, eb = x0, None
+    for _ in range(4):
+        xb, eb = b.single_step(xb, energies=eb)
+    assert np.array_equal(xa, xb) and np.array_equal(ea, eb) and a._num_acc == b._num_acc and a._num_trials == 4 * 256
+    assert ea.dtype == np.float32 and 0.0 < a.acceptance_rate < 1.0
+    # a host callback (the reference's protocol) gives the same chain as the device energy, up to float32 log/exp rounding
+    c = v.mcmc.MCMC(model, omc.gmm_energy, random_seed=3)
+    v.set_seed(21)
+    xc, ec = c.run(x0, n_steps=4)
+    assert np.mean(np.all(xc == xa, axis=1)) > 0.99
+
+
 def test_device_pcg64_stream_equals_host_stream(vms):
     """The device-drawn accept uniforms (`vms_mc_run_pcg64`) reproduce NumPy's PCG64 stream: same decisions / final state
     as the host-stream path over many steps, for a whole chain set and for a shard (chain0, n_global) of it; the

@@ -347,6 +347,40 @@ def test_mc_oracle_matches_reference_mcmc_py(tag, prior):
     assert float(g['num_trials']) == 5 * 64 and float(g['num_acc']) == n_acc
 
 
+def test_mc_oracle_c4b_matches_reference_mcmc_py():
+    """C4b: the reference's mcmc.py drove the MC notebook's model family (MAF prior, conditional autoregressive decoder,
+    Gaussian-mixture log-density as energy): the restatement reproduces its decisions, configurations and energies bit for
+    bit, in the float32 arithmetic NumPy uses for a float32 energy callback (mcmc.py:116)."""
+    g = np.load(os.path.join(GOLD, 'mcmc_reference_c4b.npz'))
+    P = omc.init_vae_b(2003, hidden=64)
+    model = omc.OracleVAEb(P, noise_seed=888)
+    rng = np.random.default_rng(5002)
+    configs, energies, n_acc = g['x0'], None, 0
+    for s in range(5):
+        configs, energies, acc = omc.single_step(model, omc.gmm_energy, rng, configs, energies)
+        assert energies.dtype == np.float32
+        assert np.array_equal(acc, g['acc_%d' % s])
+        assert np.array_equal(configs, g['configs_%d' % s]) and np.array_equal(energies, g['energies_%d' % s])
+        n_acc += acc.sum()
+    assert float(g['num_trials']) == 5 * 256 and float(g['num_acc']) == n_acc and 100 < n_acc < 400
+
+
+def test_gmm_energy_is_the_mixture_log_density():
+    """oracle.mcmc.gmm_energy (MC notebook cell 5 / 38) against scipy's float64 mixture density; the product's host-side
+    callback (`GaussianMixtureEnergy` on NumPy input) is the same arithmetic."""
+    from scipy.stats import norm
+    from vaemolsim_b200.mcmc import GaussianMixtureEnergy
+    x = np.random.default_rng(3).normal(size=(4000, 2)).astype(np.float32) * 1.5
+    want = np.log(sum(p * norm.pdf(x[:, 0], m[0], s[0]) * norm.pdf(x[:, 1], m[1], s[1])
+                      for p, m, s in zip(omc.GMM_PROBS.astype(np.float64), omc.GMM_LOCS.astype(np.float64),
+                                         omc.GMM_SCALES.astype(np.float64))))
+    got = omc.gmm_energy(x)
+    ok = np.isfinite(want)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=2e-5, atol=2e-5)
+    host = GaussianMixtureEnergy()(x)
+    assert host.dtype == np.float32 and np.array_equal(host, got)
+
+
 def test_batch_norm_restatement_identities():
     """oracle/nets.py batch-norm restatement [TF/TFP-recalled]: normalised columns have zero mean / unit variance (up to
     eps), the bijector's two directions invert each other and their log-dets cancel, and the initial moving statistics

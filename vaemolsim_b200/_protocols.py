@@ -901,7 +901,9 @@ class Blockwise(Distribution):
         c = ctx()
         out = Tensor((self._n, self.event_size))
         e = None if eps is None else as_tensor(eps)
-        seed = int(rng().integers(0, 2**63 - 1))
+        # (all-Normal dofs with given noise use no device stream: the host generator is left where the caller's noise ended)
+        needs_stream = e is None or any(k != DIST_NORMAL for k in self.kinds)
+        seed = int(rng().integers(0, 2**63 - 1)) if needs_stream else 0
         c.lib.vms_blockwise_sample(self.params.ptr, self.params.ld, self._n, self.event_size, self._kind, self._loc,
                                    self._loc2, self._scale, self.scale_mode, _ptr(e), 0 if e is None else e.ld, seed,
                                    out.ptr, out.ld, c.stream)
@@ -1019,12 +1021,17 @@ class Autoregressive(Distribution):
     def _log_prob_rows(self, x, **kw):
         return self.distribution_fn(x).log_prob(x)
 
-    def _sample_rows(self, **kw):
+    def _sample_rows(self, eps=None, **kw):
+        # tfp re-uses ONE seed for every pass, i.e. the same noise per dof at every step: the Normal noise is drawn once on
+        # the host generator ([B, D] float32, reproducible by the oracle) and handed to every pass; the generator state is
+        # restored before each pass so that von Mises dofs (device Philox stream, seeded from it) repeat their noise too
+        if eps is None:
+            eps = Tensor.from_numpy(rng().standard_normal((self.batch, self.event_size), dtype=np.float32))
         state = rng().bit_generator.state
         s = self.sample0
         for _ in range(self.num_steps + 1):
-            rng().bit_generator.state = state  # same seed at every step, as tfp does
-            s = self.distribution_fn(s)._sample_rows()
+            rng().bit_generator.state = state
+            s = self.distribution_fn(s)._sample_rows(eps=eps)
         return s
 
 

@@ -31,6 +31,42 @@ class QuadraticEnergy(object):
         return np.sum((np.asarray(configs) - self.means[np.newaxis, :])**2, axis=-1)
 
 
+class GaussianMixtureEnergy(object):
+    """The "energy" of examples/MC_Moves_with_VAEs.ipynb (cell 5, 38): the log-density of a mixture of independent Normals,
+    `tfp.distributions.Mixture(Categorical(probs), [Independent(Normal(loc_k, scale_k))...]).log_prob(configs)`.  Callable on
+    NumPy arrays like the reference's callback (float32 result, tfp's arithmetic), and flagged `on_device`: an `MCMC` calls
+    it with device tensors and gets device float32 energies back (`vms_energy_gmm`, the dtype of `log_prob(...).numpy()`), so an MC loop has no PCIe round trip.
+    Defaults: the notebook's three components."""
+    on_device = True
+
+    def __init__(self, probs=(0.7, 0.2, 0.1), locs=((-0.5, 0.0), (1.0, 2.0), (-1.5, 0.0)),
+                 scales=((0.05, 0.5), (1.0, 0.5), (0.5, 0.2))):
+        self.probs = np.asarray(probs, np.float32)
+        self.locs = np.asarray(locs, np.float32).reshape(len(self.probs), -1)
+        self.scales = np.asarray(scales, np.float32).reshape(len(self.probs), -1)
+        self._dev = None
+
+    def _host(self, configs):
+        x = np.asarray(configs, np.float32)
+        lp = np.stack([np.sum(-0.5 * (x / s - m / s)**2 - (np.float32(0.9189385332046727) + np.log(s)), axis=-1,
+                              dtype=np.float32) + np.log(p)
+                       for p, m, s in zip(self.probs, self.locs, self.scales)], axis=-1).astype(np.float32)
+        mx = lp.max(axis=-1, keepdims=True)
+        return (mx[..., 0] + np.log(np.sum(np.exp(lp - mx), axis=-1, dtype=np.float32))).astype(np.float32)
+
+    def __call__(self, configs):
+        if not isinstance(configs, Tensor):
+            return self._host(configs)
+        c = ctx()
+        if self._dev is None:
+            self._dev = (Tensor.from_numpy(np.log(self.probs)), Tensor.from_numpy(self.locs), Tensor.from_numpy(self.scales))
+        x = configs.contig()
+        E = Tensor((x.shape[0], ), np.float32)
+        c.lib.vms_energy_gmm(x.ptr, x.shape[0], x.shape[1], len(self.probs), self._dev[0].ptr, self._dev[1].ptr,
+                             self._dev[2].ptr, E.ptr, c.stream)
+        return E
+
+
 class MCMC(object):
     """Markov chain Monte Carlo with a VAE proposal: as many independent chains as input configurations."""
 
@@ -286,26 +322,30 @@ class MCMC(object):
         if self._fused_plan() is not None:
             self._fold()
 
+    @staticmethod
+    def _energy_tensor(e):
+        """Energies keep the callback's floating type: mcmc.py:116 is evaluated by NumPy in float64 for a float64 callback
+        (tests/test_mcmc.py:28-32) and in float32 for a float32 one (a tfp log_prob, MC notebook cell 38)."""
+        if isinstance(e, Tensor):
+            return e if e.dtype in (np.float32, np.float64) else as_tensor(e.numpy(), dtype=np.float64)
+        e = np.asarray(e)
+        return Tensor.from_numpy(e, dtype=np.float32 if e.dtype == np.float32 else np.float64)
+
     def _energies(self, configs_host, configs_dev):
         """energy_func is the reference's host callable on NumPy arrays; a callable flagged `on_device` instead maps a
-        device Tensor [B, D] float32 to a device Tensor [B] float64 (no PCIe round trip)."""
+        device Tensor [B, D] float32 to a device Tensor [B] (float32 or float64) with no PCIe round trip."""
         if getattr(self.energy_func, 'on_device', False):
-            return self.energy_func(configs_dev)
+            return self._energy_tensor(self.energy_func(configs_dev))
         if configs_host is None:
             configs_host = configs_dev.numpy()
-        return Tensor.from_numpy(np.asarray(self.energy_func(configs_host), dtype=np.float64))
+        return self._energy_tensor(self.energy_func(configs_host))
 
-    def single_step(self, configs, energies=None):
+    def _device_step(self, x1, e_old, n_acc=None):
+        """One MC step with the chain state on the device: x1 [B, D] float32, e_old [B] float64 -> (x2, e_out, acc, n_acc).
+        The six distribution evaluations of mcmc.py:100-108 are op-by-op kernels, the accept rule is `vms_mc_accept`; the
+        uniforms are this step's draw of the host PCG64 stream (mcmc.py:119)."""
         c = ctx()
-        configs = np.array(configs.numpy() if isinstance(configs, Tensor) else configs)
-        x1 = Tensor.from_numpy(configs, dtype=np.float32)
         B = x1.shape[0]
-        x1 = x1.reshape(B, -1)
-        if energies is None:
-            e_old = self._energies(configs, x1)
-        else:
-            e_old = as_tensor(energies, dtype=np.float64)
-
         # forward proposal: encode, move in latent space, decode (mcmc.py:100-103)
         z1, log_z1_given_x1 = self.vae.encoder(x1).experimental_sample_and_log_prob()
         z2, log_z2 = self.vae.prior(z1).experimental_sample_and_log_prob()
@@ -318,16 +358,29 @@ class MCMC(object):
         log_x1_given_z1 = self.vae.decoder(z1).log_prob(x1)
         reverse_log_p = log_z2_given_x2 + log_z1 + log_x1_given_z1
 
+        x2 = x2.contig()
         e_new = self._energies(None, x2)
 
         # accept / reject on the device with the host's uniform stream (mcmc.py:116-128)
         log_rand = Tensor.from_numpy(np.log(self._rng.random(size=B)))
-        x2 = x2.contig() if x2.contiguous else x2.contig()
-        e_out = Tensor((B, ), np.float64)
+        if e_new.dtype != e_old.dtype:  # NumPy would promote the mixed pair
+            e_new, e_old = (e if e.dtype == np.float64 else Tensor.from_numpy(e.numpy(), dtype=np.float64) for e in (e_new, e_old))
+        e_out = Tensor((B, ), e_new.dtype)
         acc = Tensor((B, ), np.uint8)
-        n_acc = Tensor.zeros((1, ), np.uint64)
-        c.lib.vms_mc_accept(e_new.ptr, e_old.ptr, forward_log_p.ptr, reverse_log_p.ptr, log_rand.ptr, B, x2.shape[1],
+        if n_acc is None:
+            n_acc = Tensor.zeros((1, ), np.uint64)
+        accept = c.lib.vms_mc_accept if e_new.dtype == np.float64 else c.lib.vms_mc_accept_f32
+        accept(e_new.ptr, e_old.ptr, forward_log_p.ptr, reverse_log_p.ptr, log_rand.ptr, B, x2.shape[1],
                             x1.ptr, x2.ptr, e_out.ptr, acc.ptr, n_acc.ptr, c.stream)
+        return x2, e_out, acc, n_acc
+
+    def single_step(self, configs, energies=None):
+        configs = np.array(configs.numpy() if isinstance(configs, Tensor) else configs)
+        x1 = Tensor.from_numpy(configs, dtype=np.float32)
+        B = x1.shape[0]
+        x1 = x1.reshape(B, -1)
+        e_old = self._energies(configs, x1) if energies is None else self._energy_tensor(energies)
+        x2, e_out, acc, n_acc = self._device_step(x1, e_old)
         self._num_trials += B
         self._num_acc += float(n_acc.numpy()[0])
         self._last_acc = acc
@@ -338,9 +391,38 @@ class MCMC(object):
             new_configs[rej, ...] = configs[rej, ...]  # mcmc.py:126: rejected rows are the caller's own rows, unrounded
         return new_configs, e_out.numpy()
 
+    def run_device(self, configs, energies=None, n_steps=1, configs_dev=None, energies_dev=None):
+        """`run` for models outside the fused kernel's family with the chain state kept on the device for the whole loop:
+        per step the only host traffic is the upload of that step's sampling noise and B uniforms (and the energy
+        callback's round trip when `energy_func` is a host function); the accept counters are read once at the end.  Same
+        decisions as n_steps calls of `single_step` under the same seeds.  With `configs_dev` ([B, D] float32 device
+        tensor) the state is taken from and returned on the device."""
+        on_dev = configs_dev is not None
+        if on_dev:
+            x = configs_dev
+            shape, B = x.shape, x.shape[0]
+        else:
+            configs = np.array(configs.numpy() if isinstance(configs, Tensor) else configs)
+            shape, B = configs.shape, configs.shape[0]
+            x = Tensor.from_numpy(configs, dtype=np.float32).reshape(B, -1)
+        if energies_dev is not None:
+            e = energies_dev
+        elif energies is not None:
+            e = self._energy_tensor(energies)
+        else:
+            e = self._energies(None if on_dev else configs, x)
+        total = Tensor.zeros((1, ), np.uint64)
+        acc = None
+        for _ in range(n_steps):
+            x, e, acc, _n = self._device_step(x, e, n_acc=total)
+        self._num_trials += B * n_steps
+        self._num_acc += float(total.numpy()[0])
+        self._last_acc = acc
+        if on_dev:
+            return x, e
+        return x.numpy().reshape(shape), e.numpy()
+
     def run(self, configs, energies=None, n_steps=1):
         if self._fused_plan() is not None:
             return self.run_fused(configs, energies=energies, n_steps=n_steps)
-        for n in range(n_steps):
-            configs, energies = self.single_step(configs, energies=energies)
-        return configs, energies
+        return self.run_device(configs, energies=energies, n_steps=n_steps)
