@@ -473,7 +473,10 @@ def mc_flips_vs_oracle(v, model, chains=1024, steps=20):
 
 
 # ---------------------------------------------------------------------------------------------- C4b: the MC notebook's model
-C4B_FLOP = 64352  # 2 encoder, 2 MAF prior, 2 decoder-mapping evaluations, 4 MADE passes per proposal
+# FLOP the fused kernel executes per proposal: 2 encoder + 2 decoder-mapping evaluations (1-hidden-layer FCDeepNN, H = 200) and
+# 5 MADE passes ([3 -> 10 -> 100 -> 10 -> 4]; 3 sampling + 2 log_prob).  SURVEY 8d quotes 64,352 for the op-by-op form, which
+# also evaluates the prior's 12 conditioner networks per chain; the kernel replaces those by per-call knot tables.
+C4B_FLOP = 2 * (2 * 200 + 200 * 2) * 2 + 2 * (200 + 200 * 4) * 2 + 2 * (3 * 10 + 10 * 100 + 100 * 10 + 10 * 4) * 5
 C4B_LABEL = ('C4b: MC notebook model (enc 2-200-2 Normal(1); prior RQSSplineMAF 4 blocks K=20 H=40 over N(0,1); dec FCDeepNN '
              '1-200-(2,2) + AutoregressiveBlockwise(2 Normal, cond 1, hidden [10,100,10])), Gaussian-mixture energy, '
              '%d chains x %d steps' % (MC_CHAINS, MC_STEPS))
@@ -567,59 +570,74 @@ def c4b_check_and_cpu(v, model, chains=2048, steps=3):
 
 
 def c4b_bench(v, grp, ffma_peak, reps=2):
-    """MC proposals/sec for the notebook's model family: chains sharded over the ranks, no collective.  This family runs
-    op-by-op (MAF forward / inverse, MADE passes, autoregressive sampling, mixture energy, accept kernel) with the chain
-    state resident on the device; sampling noise and uniforms are host PCG64 draws uploaded per step, as in the reference."""
+    """MC proposals/sec for the notebook's model family: chains sharded over the ranks, no collective; whole MC steps in the
+    fused kernel (`vms_mc_nb_run`), accept uniforms regenerated on the device from the one PCG64 stream, sampling noise
+    keyed by the global chain index.  The op-by-op path of the same model is timed beside it."""
     from vaemolsim_b200 import parallel
     c = v._abi.ctx()
     lo, hi = parallel.shard_rows(MC_CHAINS, grp.rank, grp.world)
     B = hi - lo
     model = build_c4b_model(v)
     energy = v.mcmc.GaussianMixtureEnergy()
-    mc = v.mcmc.MCMC(model, energy, random_seed=5002)
+    mc = v.mcmc.MCMC(model, energy, random_seed=5002, stream_layout=(lo, MC_CHAINS))
+    if mc._nb_plan() is None:
+        raise RuntimeError('bench: the fused notebook-family MC plan is unavailable')
     x0 = gmm_start(MC_CHAINS)[lo:hi]
-    v.set_seed(888 + grp.rank)
+    # device-resident leg: chain state in HBM, noise and uniforms generated in the kernel; one launch = MC_STEPS steps
     xd = v.Tensor.from_numpy(np.ascontiguousarray(x0))
-    xd, ed = mc.run_device(None, n_steps=3, configs_dev=xd)
+    xd, ed = mc.run_nb(None, n_steps=MC_STEPS, configs_dev=xd)
+    for _ in range(2):
+        mc.run_nb(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed)
     ev = Events(c, reps)
     grp.barrier()
     c.synchronize()
     l0 = v._abi.launch_count()
-    t0 = time.perf_counter()
     for i in range(reps):
         ev.record(2 * i)
-        xd, ed = mc.run_device(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed)
+        mc.run_nb(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed)
         ev.record(2 * i + 1)
     c.synchronize()
-    wall = time.perf_counter() - t0
     grp.barrier()
     launches = v._abi.launch_count() - l0
     dev_ms = grp.max(sum(ev.elapsed_ms(2 * i, 2 * i + 1) for i in range(reps)))
+    uncertain = mc.uncertain()
+    mc.sync_counters()
     acc_rate = mc.acceptance_rate
-    mc2 = v.mcmc.MCMC(model, energy, random_seed=5002)
+    # end to end through the public API: MCMC.run(configs, n_steps) from host arrays
+    mc2 = v.mcmc.MCMC(model, energy, random_seed=5002, stream_layout=(lo, MC_CHAINS))
     mc2.run(x0, n_steps=2)
     grp.barrier()
     t0 = time.perf_counter()
     for _ in range(reps):
         xe, ee = mc2.run(x0, n_steps=MC_STEPS)
     e2e_s = grp.max(time.perf_counter() - t0)
+    # the op-by-op path of the same model (what every other model family runs), a few steps
+    mc3 = v.mcmc.MCMC(model, energy, random_seed=5002)
+    mc3.fuse_notebook = False
+    v.set_seed(888 + grp.rank)
+    xo, eo = mc3.run_device(None, n_steps=2, configs_dev=v.Tensor.from_numpy(np.ascontiguousarray(x0)))
+    c.synchronize()
+    t0 = time.perf_counter()
+    mc3.run_device(None, n_steps=10, configs_dev=xo, energies_dev=eo)
+    c.synchronize()
+    op_ms = (time.perf_counter() - t0) / 10 * 1e3
     tot = MC_CHAINS * MC_STEPS * reps
     tflops = tot * C4B_FLOP / (dev_ms * 1e-3) / 1e12
     res = {'metric': 'MC proposals/sec', 'value': tot / (dev_ms * 1e-3), 'unit': 'proposals/s', 'workload': C4B_LABEL,
-           'chains_global': MC_CHAINS, 'chains_per_gpu': B, 'steps': MC_STEPS, 'runs_timed': reps,
+           'chains_global': MC_CHAINS, 'chains_per_gpu': B, 'steps_per_launch': MC_STEPS, 'launches_timed': reps,
            'scaling': 'strong (65,536 chains split over the GPUs, no data-path collective)',
-           'ms_per_mc_step': dev_ms / (reps * MC_STEPS), 'host_wall_ms_per_mc_step': wall / (reps * MC_STEPS) * 1e3,
-           'gpu_launches': int(launches), 'launches_per_mc_step': launches / (reps * MC_STEPS), 'acceptance_rate': acc_rate,
-           'path': 'op-by-op kernels, chain state device-resident (MCMC.run_device)',
-           'e2e': {'value': tot / e2e_s, 'unit': 'proposals/s', 'h2d_bytes_per_step': int(B * (8 + 16 + 8)),
+           'ms_per_mc_step': dev_ms / (reps * MC_STEPS), 'gpu_launches': int(launches), 'acceptance_rate': acc_rate,
+           'path': 'mc_nb_kernel (fused, 4 lanes per chain); per call: 24 conditioner launches + 4 knot tables + 1 MC launch',
+           'uniform_stream': 'NumPy PCG64 regenerated on the device, uncertain decisions: %d, host-stream re-runs: %d'
+                             % (uncertain, mc2.host_stream_reruns),
+           'op_by_op_ms_per_mc_step': op_ms,
+           'e2e': {'value': tot / e2e_s, 'unit': 'proposals/s', 'h2d_bytes_per_step': int(B * 8 / MC_STEPS),
                    'd2h_bytes_per_step': int(B * 12 / MC_STEPS), 'ms_per_mc_step': e2e_s / (reps * MC_STEPS) * 1e3,
-                   'api': 'MCMC.run(configs, n_steps=%d) from host arrays (per step: noise + uniforms uploaded)' % MC_STEPS},
-           'roofline': {'bound': 'ffma', 'kernel': 'whole MC step (op-by-op)', 'achieved': tflops / grp.world,
-                        'peak': ffma_peak, 'unit': 'TFLOP/s', 'frac': tflops / grp.world / ffma_peak, 'traffic': None,
+                   'api': 'MCMC.run(configs, n_steps=%d) from host arrays' % MC_STEPS},
+           'roofline': {'bound': 'ffma', 'kernel': 'mc_nb_kernel', 'achieved': tflops / grp.world, 'peak': ffma_peak,
+                        'unit': 'TFLOP/s', 'frac': tflops / grp.world / ffma_peak, 'traffic': None,
                         'algorithmic_flop_per_proposal': C4B_FLOP,
-                        'peak_kind': 'FP32 FFMA issue peak measured in this run (csrc/probe.cu)',
-                        'note': 'launch- and latency-bound: ~%d small kernels per MC step, no fused kernel for this family'
-                                % round(launches / (reps * MC_STEPS))}}
+                        'peak_kind': 'FP32 FFMA issue peak measured in this run (csrc/probe.cu)'}}
     if grp.rank == 0:
         res['cpu_baseline'], res['flips_vs_oracle'] = c4b_check_and_cpu(v, model)
     return res

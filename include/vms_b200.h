@@ -421,6 +421,57 @@ vms_status vms_mc_run_pcg64(vms_mc_plan plan, const float* theta, float* x, doub
                             unsigned long long* n_uncertain, uint8_t* acc_trace, float* fwd_trace, float* rev_trace,
                             double* e_new_trace, double* log_u_trace, vms_stream stream);
 
+/* ------------------------------------------------------------------------------- K9: fused MC, MC-notebook family (C4b)
+ * Whole MC steps (mcmc.py:68-130, the loop of MCMC.run :133-159) for the model of examples/MC_Moves_with_VAEs.ipynb in ONE
+ * launch, chain state in registers:
+ *   encoder  FCDeepNN(2 -> enc_hidden -> 2, relu) into tfp.layers.IndependentNormal(1)                  (cell 11)
+ *   prior    FlowedDistribution(RQSSplineMAF over a 1-D latent, Independent N(0, 1))                     (cell 14)
+ *   decoder  FCDeepNN(1 -> dec_hidden -> (2, 2), relu) into AutoregressiveBlockwise(2, [Normal] * 2, conditional = z,
+ *            MADE hidden_units made_hidden[0..2], activation made_act)  (cell 17; dists.py:246-340)
+ *   energy   mixture-of-independent-Normals log-density (cell 5 / 38), float32 -- see vms_energy_gmm.
+ * All pointers are device pointers to the host mirror's live weight tensors (row-major [in, out] kernels, as Keras stores
+ * them; MADE kernels pre-masked; made_Wc = the bias-free conditional kernels [1, out] of every MADE layer).
+ * `tables`: n_blocks knot tables in the chain's SAMPLING order (block 0 is applied first to the base noise), each
+ * vms_rqs_knot_table_doubles(n_bins) doubles, built by vms_rqs_knot_table from the raw conditioner outputs.  A masked
+ * autoregressive flow over ONE dimension has input-independent parameters (flows.py:450-515 with event size 1: the MADE
+ * mask is empty), so the host evaluates the three conditioner networks of a block once per call, on one row.             */
+typedef struct {
+  int dx, dz;                     /* must be 2 and 1 */
+  int enc_hidden, dec_hidden;
+  const float *enc_W0, *enc_b0, *enc_W1, *enc_b1;
+  const float *dec_W0, *dec_b0, *dec_W1, *dec_b1;
+  int made_hidden[3];             /* [<= 16, <= 512, <= 16] */
+  int made_act;                   /* VMS_ACT_*: tfp AutoregressiveNetwork `activation` (default none) */
+  const float* made_W[4];
+  const float* made_b[4];
+  const float* made_Wc[4];
+  int n_blocks, n_bins;
+  float range_min, range_max;
+  const double* tables;
+  int n_comp;                     /* <= 16 */
+  const float *gmm_log_w, *gmm_loc, *gmm_scale;   /* [n_comp], [n_comp, 2], [n_comp, 2] */
+} vms_mc_nb_model;
+/* Knot table of n_splines splines from raw parameters raw_w / raw_h [n_splines, n_bins], raw_s [n_splines, n_bins - 1]:
+ * flows.py:86-101 "activations" (softmax * (range - n_bins 1e-2) + 1e-2; softplus + 1e-2) and the cumulative knot positions
+ * of tfp RationalQuadraticSpline, in the arithmetic of the RQS kernels (float64 knots, float32 derivatives).
+ * Layout per spline: double kx[n_bins + 1], double ky[n_bins + 1], float d[n_bins + 1] (+ pad to 8 bytes).               */
+int64_t vms_rqs_knot_table_doubles(int n_bins);
+vms_status vms_rqs_knot_table(const float* raw_w, const float* raw_h, const float* raw_s, int n_splines, int n_bins,
+                              float range_min, float range_max, double* tables, vms_stream stream);
+/* 1 when the shape is inside the kernel's family (the host mirror falls back to the op-by-op path otherwise). */
+int vms_mc_nb_supported(const vms_mc_nb_model* model);
+/* n_steps MC steps of B chains.  x [B, 2] and E [B] float32 are updated in place (E is computed first when
+ * energies_valid = 0).  noise: NULL (device Philox stream keyed by (seed, chain0 + chain, step0 + step)) or
+ * [n_steps, B, 4] = eps(z1) | eps(z2) | eps(x2) [2] per chain, the order mcmc.py:100-102 draws it.  Accept uniforms: exactly
+ * one of log_u [n_steps, B] (float64 logs of the host stream, mcmc.py:119) and rng (the stream regenerated on the device,
+ * see vms_pcg64_stream; uncertain decisions counted in n_uncertain).  Acceptance: NumPy's float32 evaluation of mcmc.py:116
+ * (vms_mc_accept_f32).  n_acc += accepted moves.  Optional traces [n_steps, B]: acc u8, fwd / rev / e_new f32, log_u f64. */
+vms_status vms_mc_nb_run(const vms_mc_nb_model* model, float* x, float* E, int energies_valid, const float* noise,
+                         unsigned long long seed, unsigned long long step0, const double* log_u, const vms_pcg64_stream* rng,
+                         int64_t chain0, int64_t B, int n_steps, unsigned long long* n_acc, unsigned long long* n_uncertain,
+                         uint8_t* acc_trace, float* fwd_trace, float* rev_trace, float* e_new_trace, double* log_u_trace,
+                         vms_stream stream);
+
 /* ------------------------------------------------------------------------------- data-parallel exchange step
  * The single collective of data-parallel training (north_star: one gradient allreduce per step) fused with the Adam
  * update, as ONE kernel over NVLink peer memory.  Every rank owns a buffer of vms_peer_buffer_bytes(P) bytes

@@ -75,14 +75,15 @@ def vae_from_oracle(v, P, max_batch=4096, weight=1.0):
     return model
 
 
-def vae_b_from_oracle(v, P):
+def vae_b_from_oracle(v, P, made_activation=None):
     """The MC notebook's model family (examples/MC_Moves_with_VAEs.ipynb cells 11-20) through the product's host API, with
     the weights of `oracle.mcmc.init_vae_b`."""
     from vaemolsim_b200 import dists, flows, models
     import vaemolsim_b200._protocols as PR
     enc = models.MappingToDistribution(PR.IndependentNormal(1), name='encoder')
     dec_dist = dists.AutoregressiveBlockwise(2, [dists.Normal] * 2, conditional=True, conditional_event_shape=(1, ),
-                                             auto_net_params={'hidden_units': [L['W'].shape[1] for L in P['made'][:-1]]})
+                                             auto_net_params={'hidden_units': [L['W'].shape[1] for L in P['made'][:-1]],
+                                                              'activation': made_activation})
     dec = models.MappingToDistribution(dec_dist, name='decoder')
     enc.mapping.hidden_dim = [P['hidden']]
     dec.mapping.hidden_dim = [P['hidden']]

@@ -609,9 +609,10 @@ def test_mc_c4b_notebook_model_matches_reference_mcmc_py_goldens(vms):
         assert_close(e_out.numpy()[same], g['energies_%d' % s][same], rtol=1e-5, atol=2e-4, what='energies step %d' % s)
         assert int(n_acc.numpy()[0]) == int(acc.sum())
     assert safe_total > 1200 and flips <= 2
-    # whole-loop entry points: `run` keeps the state on the device and equals n single_steps under the same seeds
+    # whole-loop entry point of the op-by-op path: the state stays on the device and equals n single_steps under the same seeds
     x0 = g['x0']
     a, b = v.mcmc.MCMC(model, energy, random_seed=3), v.mcmc.MCMC(model, energy, random_seed=3)
+    a.fuse_notebook = False
     v.set_seed(21)
     xa, ea = a.run(x0, n_steps=4)
     v.set_seed(21)
@@ -625,6 +626,115 @@ def test_mc_c4b_notebook_model_matches_reference_mcmc_py_goldens(vms):
     v.set_seed(21)
     xc, ec = c.run(x0, n_steps=4)
     assert np.mean(np.all(xc == xa, axis=1)) > 0.99
+
+
+def _nb_noise(seed, n_steps, B):
+    """Sampling noise of the notebook family in the reference's draw order (mcmc.py:100-102): z1 [1], z2 [1], x2 [2]."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((n_steps, B, 4), np.float32)
+    for s in range(n_steps):
+        out[s, :, 0:1] = rng.standard_normal((B, 1), dtype=np.float32)
+        out[s, :, 1:2] = rng.standard_normal((B, 1), dtype=np.float32)
+        out[s, :, 2:4] = rng.standard_normal((B, 2), dtype=np.float32)
+    return out
+
+
+@pytest.mark.parametrize('device_rng', [False, True])
+def test_fused_mc_notebook_kernel_matches_reference_mcmc_py_goldens(vms, device_rng):
+    """`vms_mc_nb_run` (the fused kernel of the MC notebook's model family, C4b) against the decisions of the REFERENCE's own
+    mcmc.py: every step restarted from the golden state, injected sampling noise, PCG64 uniforms from the host or
+    regenerated on the device."""
+    v = vms
+    from helpers import vae_b_from_oracle
+    g = np.load(os.path.join(GOLD, 'mcmc_reference_c4b.npz'))
+    P = omc.init_vae_b(2003, hidden=64)
+    model = vae_b_from_oracle(v, P)
+    mc = v.mcmc.MCMC(model, v.mcmc.GaussianMixtureEnergy(), random_seed=5002)
+    mc.device_rng = device_rng
+    assert mc._fused_plan() is None and mc._nb_plan() is not None
+    noise = _nb_noise(888, 5, 256)
+    safe_total = flips = 0
+    for s in range(5):
+        x_old, e_old = g['x_old_%d' % s], g['e_old_%d' % s]
+        x_new, e_new = mc.run_nb(x_old, energies=e_old if s else None, n_steps=1, noise=noise[s:s + 1], trace=True)
+        tr = mc._last_trace
+        if device_rng:
+            np.testing.assert_array_max_ulp(tr['log_u'][0], g['log_rand_%d' % s], maxulp=2)
+        else:
+            assert np.array_equal(tr['log_u'][0], g['log_rand_%d' % s])
+        assert_close(tr['fwd'][0], g['fwd_%d' % s], rtol=1e-5, atol=5e-5, what='forward_log_p step %d' % s)
+        assert_close(tr['rev'][0], g['rev_%d' % s], rtol=1e-5, atol=2e-4, what='reverse_log_p step %d' % s)
+        assert_close(tr['e_new'][0], g['e_new_%d' % s], rtol=1e-5, atol=2e-4, what='proposal energy step %d' % s)
+        # the kernel's acceptance arithmetic is NumPy's float32 evaluation given ITS log-probabilities (mcmc.py:116-120)
+        la = (tr['e_new'][0] + tr['rev'][0] - e_old - tr['fwd'][0])
+        assert la.dtype == np.float32 and np.array_equal(tr['acc'][0].astype(bool), la >= tr['log_u'][0])
+        margin = np.abs(g['e_new_%d' % s] + g['rev_%d' % s] - g['e_old_%d' % s] - g['fwd_%d' % s] - g['log_rand_%d' % s])
+        safe = margin > 2e-3
+        safe_total += int(safe.sum())
+        acc = tr['acc'][0].astype(bool)
+        flips += int((acc != g['acc_%d' % s]).sum())
+        assert np.array_equal(acc[safe], g['acc_%d' % s][safe])
+        same = acc == g['acc_%d' % s]
+        assert_close(x_new[same], g['configs_%d' % s][same], rtol=1e-5, atol=5e-5, what='configs step %d' % s)
+        assert_close(e_new[same], g['energies_%d' % s][same], rtol=1e-5, atol=2e-4, what='energies step %d' % s)
+    assert safe_total > 1200 and flips <= 2 and mc._num_trials == 5 * 256 and mc.host_stream_reruns == 0
+    assert mc._num_acc == sum(int(g['acc_%d' % s].sum()) for s in range(5)) or flips > 0
+    want_next = np.random.default_rng(5002)
+    want_next.random(size=5 * 256)
+    assert mc._rng.random() == want_next.random()
+
+
+def test_fused_mc_notebook_kernel_equals_op_by_op_path_over_many_steps(vms):
+    """The fused notebook-family kernel against the op-by-op path on 3000 chains x 12 steps with the same sampling noise and
+    uniforms (a tanh MADE this time): same decision trace except where a decision sits within float32 rounding of its
+    threshold, multi-step launches equal repeated single-step launches bit for bit, shards equal the whole."""
+    v = vms
+    import vaemolsim_b200._protocols as PR
+    from helpers import vae_b_from_oracle
+    P = omc.init_vae_b(77, hidden=200)
+    model = vae_b_from_oracle(v, P, made_activation='tanh')
+    energy = v.mcmc.GaussianMixtureEnergy()
+    B, n_steps = 3000, 12
+    rng = np.random.default_rng(5)
+    k = rng.choice(3, size=B, p=[0.7, 0.2, 0.1])
+    x0 = (omc.GMM_LOCS[k] + omc.GMM_SCALES[k] * rng.standard_normal((B, 2))).astype(np.float32)
+    noise = _nb_noise(31, n_steps, B)
+    a = v.mcmc.MCMC(model, energy, random_seed=9)
+    xa, ea = a.run_nb(x0, n_steps=n_steps, noise=noise, trace=True)
+    tra = a._last_trace
+    # op-by-op: host generator replays the same noise
+    b = v.mcmc.MCMC(model, energy, random_seed=9)
+    b.fuse_notebook = False
+    v.set_seed(31)
+    xb, eb = x0, None
+    acc_b = np.empty((n_steps, B), bool)
+    for s in range(n_steps):
+        xb, eb = b.single_step(xb, energies=eb)
+        acc_b[s] = b._last_acc.numpy().astype(bool)
+    diff_chains = (tra['acc'].astype(bool) != acc_b).any(axis=0)
+    assert diff_chains.sum() <= 3, diff_chains.sum()
+    ok = ~diff_chains
+    assert_close(xa[ok], xb[ok], rtol=1e-5, atol=5e-5, what='final configs')
+    assert_close(ea[ok], eb[ok], rtol=1e-5, atol=2e-4, what='final energies')
+    assert 0.02 < a.acceptance_rate < 0.9
+    # one launch of 12 steps == 12 launches of one step (device rng: the stream position carries over)
+    c = v.mcmc.MCMC(model, energy, random_seed=9)
+    xc, ec = x0, None
+    for s in range(n_steps):
+        xc, ec = c.run_nb(xc, energies=ec, n_steps=1, noise=noise[s:s + 1])
+    assert np.array_equal(xc, xa) and np.array_equal(ec, ea) and c._num_acc == a._num_acc
+    # host-stream uniforms give the same chain as the device stream
+    d = v.mcmc.MCMC(model, energy, random_seed=9)
+    d.device_rng = False
+    xd, ed_ = d.run_nb(x0, n_steps=n_steps, noise=noise)
+    assert np.array_equal(xd, xa) and np.array_equal(ed_, ea) and d._rng.random() == a._rng.random()
+    # a shard (chain0, n_global) of the chain set reproduces its rows of the whole run, with the device noise stream too
+    w = v.mcmc.MCMC(model, energy, random_seed=9)
+    xw, ew = w.run(x0, n_steps=n_steps)
+    lo, hi = 1000, 2200
+    sh = v.mcmc.MCMC(model, energy, random_seed=9, stream_layout=(lo, B))
+    xs, es = sh.run(x0[lo:hi], n_steps=n_steps)
+    assert np.array_equal(xs, xw[lo:hi]) and np.array_equal(es, ew[lo:hi])
 
 
 def test_device_pcg64_stream_equals_host_stream(vms):

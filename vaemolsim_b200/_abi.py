@@ -46,6 +46,17 @@ class Pcg64Stream(C.Structure):
                 ('stride_add_lo', C.c_uint64), ('chain0', c_i64)]
 
 
+class McNbModel(C.Structure):
+    """vms_mc_nb_model (include/vms_b200.h): device pointers to the live weights of the MC notebook's model family."""
+    _fields_ = [('dx', C.c_int), ('dz', C.c_int), ('enc_hidden', C.c_int), ('dec_hidden', C.c_int),
+                ('enc_W0', c_vp), ('enc_b0', c_vp), ('enc_W1', c_vp), ('enc_b1', c_vp),
+                ('dec_W0', c_vp), ('dec_b0', c_vp), ('dec_W1', c_vp), ('dec_b1', c_vp),
+                ('made_hidden', C.c_int * 3), ('made_act', C.c_int),
+                ('made_W', c_vp * 4), ('made_b', c_vp * 4), ('made_Wc', c_vp * 4),
+                ('n_blocks', C.c_int), ('n_bins', C.c_int), ('range_min', c_f32), ('range_max', c_f32),
+                ('tables', c_vp), ('n_comp', C.c_int), ('gmm_log_w', c_vp), ('gmm_loc', c_vp), ('gmm_scale', c_vp)]
+
+
 class ElboDesc(C.Structure):
     _fields_ = [('dx', C.c_int32), ('dz', C.c_int32), ('hidden', C.c_int32), ('num_blocks', C.c_int32),
                 ('num_bins', C.c_int32), ('flow_hidden', C.c_int32), ('bin_min', c_f32), ('bin_max', c_f32),
@@ -154,6 +165,11 @@ _SIGS = {
     'vms_mc_plan_set_chain_offset': (None, [c_vp, c_i64]),
     'vms_mc_run_pcg64': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, C.c_ulonglong, C.c_ulonglong, C.POINTER(Pcg64Stream),
                                 c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vms_rqs_knot_table_doubles': (c_i64, [c_int]),
+    'vms_rqs_knot_table': (None, [c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_f32, c_vp, c_vp]),
+    'vms_mc_nb_supported': (c_int, [C.POINTER(McNbModel)]),
+    'vms_mc_nb_run': (None, [C.POINTER(McNbModel), c_vp, c_vp, c_int, c_vp, C.c_ulonglong, C.c_ulonglong, c_vp,
+                             C.POINTER(Pcg64Stream), c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_blockwise_log_prob_backward': (None, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_int, c_vp, c_vp, c_i64,
                                                c_vp, c_i64, c_vp]),
     'vms_std_normal_log_prob_backward': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_vp]),

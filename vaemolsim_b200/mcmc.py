@@ -78,6 +78,7 @@ class MCMC(object):
         self.energy_func = energy_func
         self.stream_layout = stream_layout
         self._fused = None
+        self._nb = None
         self._acc_folded = 0   # value of the device acceptance counter already folded into _num_acc
         self.device_rng = True  # fused path: draw the accept uniforms on the device when the kernel supports it
         self.host_stream_reruns = 0
@@ -96,6 +97,10 @@ class MCMC(object):
         self._step0 = 0
         if self._fused:  # accepts counted on the device before the reset must not leak into the new statistics
             self._fused['n_acc'].fill_zero()
+        if getattr(self, '_nb', None):
+            self._nb['n_acc'].fill_zero()
+            self._nb['n_unc'].fill_zero()
+            self._nb['folded'] = 0
         self._acc_folded = 0
 
     # ------------------------------------------------------------------------------------------ fused device path
@@ -282,7 +287,7 @@ class MCMC(object):
         """Number of chain-steps of device-resident `run_fused` calls (since the last call of this method) whose decision
         was within ~1e-13 of its threshold under the device logarithm; non-zero means those calls must be repeated on the
         host stream (`device_rng = False`).  Host-array calls handle this themselves."""
-        fp = self._fused_plan()
+        fp = self._fused_plan() or (self._nb or None)
         if fp is None:
             return 0
         n = int(fp['n_unc'].numpy()[0])
@@ -321,6 +326,11 @@ class MCMC(object):
         """Fold the device acceptance counter into `_num_acc` after device-resident `run_fused` calls."""
         if self._fused_plan() is not None:
             self._fold()
+        nb = self._nb or None
+        if nb:
+            total = int(nb['n_acc'].numpy()[0])
+            self._num_acc += float(total - nb['folded'])
+            nb['folded'] = total
 
     @staticmethod
     def _energy_tensor(e):
@@ -422,7 +432,202 @@ class MCMC(object):
             return x, e
         return x.numpy().reshape(shape), e.numpy()
 
+    # ------------------------------------------------------------------------------ fused path, MC-notebook family (C4b)
+    fuse_notebook = True  # set False to force the op-by-op path for this family (cross-checks)
+
+    def _nb_plan(self):
+        """State of the fused kernel for the model family of examples/MC_Moves_with_VAEs.ipynb (`vms_mc_nb_run`), or None
+        when (vae, energy) is anything else: FCDeepNN(2 -> H -> 2) + IndependentNormal(1) encoder, RQSSplineMAF prior over a
+        one-dimensional N(0, 1), FCDeepNN(1 -> H -> (2, 2)) + conditional AutoregressiveBlockwise(2 Normal) decoder with a
+        three-hidden-layer MADE, GaussianMixtureEnergy.  Only the STRUCTURE is cached: weight pointers and the prior's knot
+        tables are gathered at every call, so training / set_weights between calls is seen."""
+        if self._nb is not None:
+            return self._nb or None
+        self._nb = False
+        if not self.fuse_notebook:
+            self._nb = None
+            return None
+        from . import dists, flows, mappings
+        from . import _protocols as PR
+        E, vae = self.energy_func, self.vae
+        if not isinstance(E, GaussianMixtureEnergy) or E.locs.shape[1] != 2 or not 1 <= len(E.probs) <= 16:
+            return None
+        enc, dec, prior = (getattr(vae, k, None) for k in ('encoder', 'decoder', 'prior'))
+
+        def two_dense(mtd, n_in, n_out):
+            m = getattr(mtd, 'mapping', None)
+            if not isinstance(m, mappings.FCDeepNN) or not getattr(m, 'layer_list', None):
+                return None
+            if m.batch_norm or m.any_periodic:
+                return None
+            d = [l for l in m.layer_list if isinstance(l, PR.Dense)]
+            if len(d) != 2 or d[0].act != PR._act_code('relu') or d[1].act != 0 or not (d[0].use_bias and d[1].use_bias):
+                return None
+            if d[0].kernel.shape[0] != n_in or d[1].units != n_out:
+                return None
+            return d
+
+        ed = getattr(enc, 'distribution', None)
+        if not isinstance(ed, PR.IndependentNormal) or ed.event_size != 1:
+            return None
+        dd = getattr(dec, 'distribution', None)
+        if not isinstance(dd, dists.AutoregressiveBlockwise) or dd.num_dofs != 2 or not dd.conditional:
+            return None
+        if any(d is not dists.Normal for d in dd.dist_classes) or list(dd.param_nums) != [2, 2]:
+            return None
+        if any(getattr(t, 'dist_kind', None) != PR.DIST_NORMAL for t in dd.param_transforms):
+            return None
+        net = getattr(dd, 'auto_net', None)
+        if net is None or len(net.layers) != 4 or net.cond_size != 1 or net.params != 2:
+            return None
+        e_l, d_l = two_dense(enc, 2, 2), two_dense(dec, 1, 4)
+        if e_l is None or d_l is None:
+            return None
+        flow = getattr(prior, 'flow', None)
+        if not isinstance(prior, dists.FlowedDistribution) or not isinstance(flow, flows.RQSSplineMAF):
+            return None
+        if flow.conditional or flow.batch_norm or flow.before_flow_transform is not None or \
+                flow.after_flow_transform is not None or getattr(flow, 'data_dim', None) != 1:
+            return None
+        try:
+            base = prior.latent_dist(Tensor.zeros((2, 1)))
+        except Exception:
+            return None
+        if not isinstance(base, PR.StandardNormal) or base.event_size != 1:
+            return None
+        blocks = [b.bijector_fn for b in flow.chain.bijectors[::-1]]  # sampling order: block 0 first
+        msb = blocks[0]
+        if any((b.num_bins, b.bin_min, b.bin_max) != (msb.num_bins, msb.bin_min, msb.bin_max) for b in blocks):
+            return None
+        m = _abi.McNbModel()
+        m.dx, m.dz, m.enc_hidden, m.dec_hidden = 2, 1, e_l[0].units, d_l[0].units
+        for k in range(3):
+            m.made_hidden[k] = net.layers[k].units
+        m.made_act = net.act
+        m.n_blocks, m.n_bins, m.range_min, m.range_max = len(blocks), msb.num_bins, msb.bin_min, msb.bin_max
+        m.n_comp = len(E.probs)
+        if not _abi.load().vms_mc_nb_supported(C.byref(m)):
+            return None
+        self._nb = dict(model=m, enc=e_l, dec=d_l, net=net, blocks=blocks,
+                        gmm=(Tensor.from_numpy(np.log(E.probs)), Tensor.from_numpy(E.locs), Tensor.from_numpy(E.scales)),
+                        n_acc=Tensor.zeros((1, ), np.uint64), n_unc=Tensor.zeros((1, ), np.uint64), folded=0)
+        return self._nb
+
+    def _nb_model(self, nb):
+        """Fills the kernel's model record from the live weights and rebuilds the prior's knot tables (one row through each
+        block's three conditioner networks + vms_rqs_knot_table)."""
+        c = ctx()
+        m = nb['model']
+        keep = []
+
+        def ptr(t):
+            t = t if t.contiguous else t.contig()
+            keep.append(t)
+            return t.ptr
+
+        (m.enc_W0, m.enc_b0), (m.enc_W1, m.enc_b1) = ((ptr(l.kernel), ptr(l.bias)) for l in nb['enc'])
+        (m.dec_W0, m.dec_b0), (m.dec_W1, m.dec_b1) = ((ptr(l.kernel), ptr(l.bias)) for l in nb['dec'])
+        net = nb['net']
+        for k, lay in enumerate(net.layers):
+            m.made_W[k], m.made_b[k], m.made_Wc[k] = ptr(lay.kernel), ptr(lay.bias), ptr(net.cond_kernels[k])
+        K, nbk = m.n_bins, m.n_blocks
+        ts = int(c.lib.vms_rqs_knot_table_doubles(K))
+        tables = Tensor((nbk, ts), np.float64)
+        zero = Tensor.zeros((1, 1))
+        for b, msb in enumerate(nb['blocks']):
+            rw, rh, rs_ = (n(zero).contig() for n in (msb.bin_widths, msb.bin_heights, msb.knot_slopes))
+            keep += [rw, rh, rs_]
+            c.lib.vms_rqs_knot_table(rw.ptr, rh.ptr, rs_.ptr, 1, K, m.range_min, m.range_max, tables.ptr + b * ts * 8, c.stream)
+        m.tables = tables.ptr
+        m.gmm_log_w, m.gmm_loc, m.gmm_scale = (t.ptr for t in nb['gmm'])
+        keep.append(tables)
+        return m, keep
+
+    def run_nb(self, configs, energies=None, n_steps=1, noise=None, trace=False, configs_dev=None, energies_dev=None):
+        """n_steps MC steps of the notebook family in one `vms_mc_nb_run` launch.  `noise` [n_steps, B, 4] injects the
+        sampling noise (eps(z1) | eps(z2) | eps(x2), the order mcmc.py:100-102 draws it; parity tests); otherwise the device
+        Philox stream keyed by (seed, global chain, step).  Accept uniforms: this object's PCG64 stream, regenerated on the
+        device (`device_rng`) with the host-stream re-run for uncertain decisions, or drawn on the host and uploaded."""
+        nb = self._nb_plan()
+        if nb is None:
+            raise NotImplementedError('run_nb: needs the MC notebook model family and a GaussianMixtureEnergy')
+        c = ctx()
+        if configs_dev is None:
+            configs = np.array(configs.numpy() if isinstance(configs, Tensor) else configs)
+            x = Tensor.from_numpy(configs.reshape(configs.shape[0], -1), dtype=np.float32)
+        else:
+            x = configs_dev
+        B = x.shape[0]
+        if energies_dev is not None:
+            e, valid = energies_dev, 1
+        elif energies is None:
+            e, valid = Tensor((B, ), np.float32), 0
+        else:
+            e, valid = Tensor.from_numpy(np.asarray(energies, np.float32)), 1
+        if e.dtype != np.float32:
+            raise TypeError('run_nb: energies are float32 (the dtype of the mixture log_prob)')
+        m, keep = self._nb_model(nb)
+        nz = None if noise is None else Tensor.from_numpy(np.ascontiguousarray(noise, np.float32))
+        P_ = lambda t: None if t is None else t.ptr
+        chain0, n_global = self.stream_layout if self.stream_layout is not None else (0, B)
+
+        def traces(log_u=None):
+            if not trace:
+                return {}
+            return dict(acc=Tensor((n_steps, B), np.uint8), fwd=Tensor((n_steps, B)), rev=Tensor((n_steps, B)),
+                        e_new=Tensor((n_steps, B)), log_u=log_u if log_u is not None else Tensor((n_steps, B), np.float64))
+
+        def launch(log_u, stream, tr):
+            c.lib.vms_mc_nb_run(C.byref(m), x.ptr, e.ptr, valid, P_(nz), self._noise_seed, self._step0, P_(log_u),
+                                None if stream is None else C.byref(stream), int(chain0), B, n_steps, nb['n_acc'].ptr,
+                                nb['n_unc'].ptr, P_(tr.get('acc')), P_(tr.get('fwd')), P_(tr.get('rev')), P_(tr.get('e_new')),
+                                P_(tr.get('log_u')), c.stream)
+
+        stream = self._pcg_stream(chain0, n_global) if self.device_rng else None
+        done, tr = False, {}
+        if stream is not None:
+            x_save, e_save = Tensor(x.shape), Tensor((B, ))
+            c.lib.vms_memcpy_d2d(x_save.ptr, x.ptr, x.nbytes, c.stream)
+            if valid:
+                c.lib.vms_memcpy_d2d(e_save.ptr, e.ptr, e.nbytes, c.stream)
+            acc_before = Tensor((1, ), np.uint64)
+            c.lib.vms_memcpy_d2d(acc_before.ptr, nb['n_acc'].ptr, 8, c.stream)
+            if not (configs_dev is not None and not self.check_uncertain):
+                nb['n_unc'].fill_zero()
+            tr = traces()
+            launch(None, stream, tr)
+            if configs_dev is not None and not self.check_uncertain:
+                done = True  # device-resident loops read `uncertain()` themselves, once per loop
+            elif int(nb['n_unc'].numpy()[0]) == 0:
+                done = True
+            else:  # repeat the call on the NumPy stream from the saved state
+                self.host_stream_reruns += 1
+                c.lib.vms_memcpy_d2d(x.ptr, x_save.ptr, x.nbytes, c.stream)
+                if valid:
+                    c.lib.vms_memcpy_d2d(e.ptr, e_save.ptr, e.nbytes, c.stream)
+                c.lib.vms_memcpy_d2d(nb['n_acc'].ptr, acc_before.ptr, 8, c.stream)
+            if done:
+                self._rng.bit_generator.advance(n_steps * n_global)
+        if not done:
+            h = np.empty((n_steps, B))
+            self._host_uniform_logs(h, chain0, n_global)  # mcmc.py:119, step by step
+            log_u = Tensor.from_numpy(h)
+            tr = traces(log_u)
+            launch(log_u, None, tr)
+        self._step0 += n_steps
+        self._num_trials += B * n_steps
+        if configs_dev is not None:
+            self._nb_keep = keep  # the launch may still be running: its inputs stay alive until the next call
+            return x, e
+        total = int(nb['n_acc'].numpy()[0])
+        self._num_acc += float(total - nb['folded'])
+        nb['folded'] = total
+        self._last_trace = {k: t.numpy() for k, t in tr.items()}
+        return x.numpy().reshape(configs.shape), e.numpy()
+
     def run(self, configs, energies=None, n_steps=1):
         if self._fused_plan() is not None:
             return self.run_fused(configs, energies=energies, n_steps=n_steps)
+        if self._nb_plan() is not None:
+            return self.run_nb(configs, energies=energies, n_steps=n_steps)
         return self.run_device(configs, energies=energies, n_steps=n_steps)
