@@ -442,6 +442,10 @@ typedef struct {
   const float *dec_W0, *dec_b0, *dec_W1, *dec_b1;
   int made_hidden[3];             /* [<= 16, <= 512, <= 16] */
   int made_act;                   /* VMS_ACT_*: tfp AutoregressiveNetwork `activation` (default none) */
+  int made_first_dof;             /* 0 / 1: the MADE masks put this dof first (input_order left-to-right / right-to-left): its
+                                     parameters depend on the conditional input only and the other dof is hidden from every
+                                     unit, so tfp's D + 1 sampling passes + the log_prob pass give bit-identical values to ONE
+                                     pass; -1: no such structure, run every pass */
   const float* made_W[4];
   const float* made_b[4];
   const float* made_Wc[4];

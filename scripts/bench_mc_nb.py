@@ -1,0 +1,29 @@
+"""Development aid: device-resident timing of the fused notebook-family MC kernel (vms_mc_nb_run), 65,536 chains x 100 steps,
+for the register-budget variants selected by VMS_NB_OCC."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+import vaemolsim_b200 as v  # noqa: E402
+
+c = v._abi.ctx()
+model = bench.build_c4b_model(v)
+x0 = bench.gmm_start(65536)
+for occ in sys.argv[1:] or ['2']:
+    os.environ['VMS_NB_OCC'] = occ
+    mc = v.mcmc.MCMC(model, v.mcmc.GaussianMixtureEnergy(), random_seed=5002)
+    xd = v.Tensor.from_numpy(x0)
+    xd, ed = mc.run_nb(None, n_steps=100, configs_dev=xd)
+    c.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        mc.run_nb(None, n_steps=100, configs_dev=xd, energies_dev=ed)
+    c.synchronize()
+    dt = (time.perf_counter() - t0) / 3
+    mc.sync_counters()
+    print('occ %s: %.3f ms / MC step, %.1f M proposals/s, acceptance %.4f' % (occ, dt * 10, 65536 * 100 / dt / 1e6, mc.acceptance_rate),
+          flush=True)

@@ -51,7 +51,7 @@ class McNbModel(C.Structure):
     _fields_ = [('dx', C.c_int), ('dz', C.c_int), ('enc_hidden', C.c_int), ('dec_hidden', C.c_int),
                 ('enc_W0', c_vp), ('enc_b0', c_vp), ('enc_W1', c_vp), ('enc_b1', c_vp),
                 ('dec_W0', c_vp), ('dec_b0', c_vp), ('dec_W1', c_vp), ('dec_b1', c_vp),
-                ('made_hidden', C.c_int * 3), ('made_act', C.c_int),
+                ('made_hidden', C.c_int * 3), ('made_act', C.c_int), ('made_first_dof', C.c_int),
                 ('made_W', c_vp * 4), ('made_b', c_vp * 4), ('made_Wc', c_vp * 4),
                 ('n_blocks', C.c_int), ('n_bins', C.c_int), ('range_min', c_f32), ('range_max', c_f32),
                 ('tables', c_vp), ('n_comp', C.c_int), ('gmm_log_w', c_vp), ('gmm_loc', c_vp), ('gmm_scale', c_vp)]

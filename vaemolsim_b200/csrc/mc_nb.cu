@@ -28,6 +28,7 @@
 #include "mc_rng.cuh"
 #include "rqs_device.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace vms {
 
@@ -196,18 +197,34 @@ __device__ __forceinline__ void made_pass(const float* __restrict__ sm, const La
 }
 
 // Mixture log-density as tfp evaluates it in float32 (mcmc.cu energy_gmm_kernel)
-__device__ __forceinline__ float gmm_energy(const float* __restrict__ g, int n, float x0, float x1) {
-  const float* lw = g;
+__device__ __forceinline__ float gmm_component(const float* __restrict__ g, int n, int k, float x0, float x1) {
   const float* loc = g + n;
   const float* sc = g + 3 * n;
+  float s = 0.f;
+  s += normal_lp(x0, loc[2 * k], sc[2 * k]);
+  s += normal_lp(x1, loc[2 * k + 1], sc[2 * k + 1]);
+  return s + g[k];
+}
+__device__ __forceinline__ float gmm_energy(const float* __restrict__ g, int n, float x0, float x1) {
+  if (n <= 4) {  // the notebook's three components: everything in registers
+    float lp[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      lp[k] = k < n ? gmm_component(g, n, k, x0, x1) : -INFINITY;
+      mx = fmaxf(mx, lp[k]);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < n) acc += expf(lp[k] - mx);
+    return mx + logf(acc);
+  }
   float lp[16];
   float mx = -INFINITY;
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
-    float s = 0.f;
-    s += normal_lp(x0, loc[2 * k], sc[2 * k]);
-    s += normal_lp(x1, loc[2 * k + 1], sc[2 * k + 1]);
-    lp[k] = s + lw[k];
+    lp[k] = gmm_component(g, n, k, x0, x1);
     mx = fmaxf(mx, lp[k]);
   }
   float acc = 0.f;
@@ -216,8 +233,8 @@ __device__ __forceinline__ float gmm_energy(const float* __restrict__ g, int n, 
   return mx + logf(acc);
 }
 
-template <int P>
-__global__ void __launch_bounds__(CT) mc_nb_kernel(const NbParams p) {
+template <int P, int MINB>
+__global__ void __launch_bounds__(CT, MINB) mc_nb_kernel(const NbParams p) {
   extern __shared__ __align__(16) float sm[];
   const vms_mc_nb_model& m = p.m;
   const Layout L = make_layout(m, P);
@@ -335,16 +352,33 @@ __global__ void __launch_bounds__(CT) mc_nb_kernel(const NbParams p) {
 #pragma unroll
     for (int n = 0; n < 4; ++n) in2[n] = pd[n] + db1[n];
     float s0 = 1.f, s1 = 1.f, mo[4];
-#pragma unroll 1
-    for (int pass = 0; pass < DX + 1; ++pass) {
+    if (m.made_first_dof >= 0) {
+      // The masks make the first dof's parameters a function of the conditional input alone (its output columns of the last
+      // kernel are zero: fmaf(v, 0, o) == o) and hide the second dof from every hidden unit (its input row is zero), so
+      // passes 2, 3 and the log_prob pass of tfp's procedure see bit-identical hidden activations: one pass gives them all.
+      const bool f = m.made_first_dof != 0;
+      const float4 bb = reinterpret_cast<const float4*>(sm + L.tail + 6 * P)[0], wc = reinterpret_cast<const float4*>(sm + L.tail + 6 * P)[1];
+      const float lf = (f ? in2[2] : in2[0]) + fmaf(z2, f ? wc.z : wc.x, f ? bb.z : bb.x);
+      const float cf = softplus_tf((f ? in2[3] : in2[1]) + fmaf(z2, f ? wc.w : wc.y, f ? bb.w : bb.y)) + VMS_EPS32;
+      const float sf = __fadd_rn(__fmul_rn(f ? nz[3] : nz[2], cf), lf);
+      if (f) s1 = sf; else s0 = sf;
       made_pass<P>(sm, L, h1, act, sub, s0, s1, z2, mo);
-      const float l0 = in2[0] + mo[0], c0 = softplus_tf(in2[1] + mo[1]) + VMS_EPS32;
-      const float l1 = in2[2] + mo[2], c1 = softplus_tf(in2[3] + mo[3]) + VMS_EPS32;
-      s0 = __fadd_rn(__fmul_rn(nz[2], c0), l0);
-      s1 = __fadd_rn(__fmul_rn(nz[3], c1), l1);
+      const float lo_ = f ? in2[0] + mo[0] : in2[2] + mo[2];
+      const float co = softplus_tf(f ? in2[1] + mo[1] : in2[3] + mo[3]) + VMS_EPS32;
+      const float so = __fadd_rn(__fmul_rn(f ? nz[2] : nz[3], co), lo_);
+      if (f) s0 = so; else s1 = so;
+    } else {
+#pragma unroll 1
+      for (int pass = 0; pass < DX + 1; ++pass) {
+        made_pass<P>(sm, L, h1, act, sub, s0, s1, z2, mo);
+        const float l0 = in2[0] + mo[0], c0 = softplus_tf(in2[1] + mo[1]) + VMS_EPS32;
+        const float l1 = in2[2] + mo[2], c1 = softplus_tf(in2[3] + mo[3]) + VMS_EPS32;
+        s0 = __fadd_rn(__fmul_rn(nz[2], c0), l0);
+        s1 = __fadd_rn(__fmul_rn(nz[3], c1), l1);
+      }
+      made_pass<P>(sm, L, h1, act, sub, s0, s1, z2, mo);
     }
     const float x2[DX] = {s0, s1};
-    made_pass<P>(sm, L, h1, act, sub, x2[0], x2[1], z2, mo);
     float lx2 = 0.f;
     lx2 += normal_lp(x2[0], in2[0] + mo[0], softplus_tf(in2[1] + mo[1]) + VMS_EPS32);
     lx2 += normal_lp(x2[1], in2[2] + mo[2], softplus_tf(in2[3] + mo[3]) + VMS_EPS32);
@@ -479,6 +513,7 @@ int vms_mc_nb_supported(const vms_mc_nb_model* m) {
   if (m->made_act != VMS_ACT_NONE && m->made_act != VMS_ACT_RELU && m->made_act != VMS_ACT_TANH) return 0;
   if (m->n_blocks < 1 || m->n_blocks > 16 || m->n_bins < 2 || m->n_bins > 256) return 0;
   if (m->n_comp < 1 || m->n_comp > 16) return 0;
+  if (m->made_first_dof < -1 || m->made_first_dof > 1) return 0;
   return 1;
 }
 
@@ -520,13 +555,22 @@ vms_status vms_mc_nb_run(const vms_mc_nb_model* model, float* x, float* E, int e
   VMS_REQUIRE(smem <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "mc_nb_run: model too large for shared memory");
   cudaStream_t st = as_stream(stream);
   const unsigned grid = (unsigned)((B + CT / TPC - 1) / (CT / TPC));
+  int occ = 2;
+  if (const char* e = getenv("VMS_NB_OCC")) occ = atoi(e);  // development aid: resident CTAs per SM the register budget targets
+#define VMS_NB_LAUNCH(PP, OO)                                                                                        \
+  do {                                                                                                               \
+    VMS_CUDA(cudaFuncSetAttribute(mc_nb_kernel<PP, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    mc_nb_kernel<PP, OO><<<grid, CT, smem, st>>>(p);                                                                 \
+  } while (0)
   if (p.P == 12) {
-    VMS_CUDA(cudaFuncSetAttribute(mc_nb_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mc_nb_kernel<12><<<grid, CT, smem, st>>>(p);
+    if (occ <= 1) VMS_NB_LAUNCH(12, 1);
+    else if (occ == 2) VMS_NB_LAUNCH(12, 2);
+    else if (occ == 3) VMS_NB_LAUNCH(12, 3);
+    else VMS_NB_LAUNCH(12, 4);
   } else {
-    VMS_CUDA(cudaFuncSetAttribute(mc_nb_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mc_nb_kernel<16><<<grid, CT, smem, st>>>(p);
+    VMS_NB_LAUNCH(16, 2);
   }
+#undef VMS_NB_LAUNCH
   VMS_LAUNCH_CHECK("mc_nb_kernel");
   return VMS_OK;
 }

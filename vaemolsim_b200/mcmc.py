@@ -504,6 +504,13 @@ class MCMC(object):
         for k in range(3):
             m.made_hidden[k] = net.layers[k].units
         m.made_act = net.act
+        # which dof the masks put first: the other dof's input row and the first dof's output columns are masked out
+        # (set_weights and the gradient masks keep them exactly zero)
+        mk = net.masks
+        m.made_first_dof = -1
+        for f in (0, 1):
+            if not mk[0][1 - f, :].any() and not mk[-1][:, 2 * f:2 * f + 2].any():
+                m.made_first_dof = f
         m.n_blocks, m.n_bins, m.range_min, m.range_max = len(blocks), msb.num_bins, msb.bin_min, msb.bin_max
         m.n_comp = len(E.probs)
         if not _abi.load().vms_mc_nb_supported(C.byref(m)):
