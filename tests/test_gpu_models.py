@@ -737,6 +737,32 @@ def test_fused_mc_notebook_kernel_equals_op_by_op_path_over_many_steps(vms):
     assert np.array_equal(xs, xw[lo:hi]) and np.array_equal(es, ew[lo:hi])
 
 
+def test_fused_mc_notebook_kernel_lane_counts_are_bitwise_equal(vms, monkeypatch):
+    """The launcher picks 1 or 4 lanes per chain by the number of chains; all lane counts walk the same four unit streams,
+    so states, energies and decision traces are bit-identical (a shard of a multi-GPU job equals its rows of the whole)."""
+    v = vms
+    from helpers import vae_b_from_oracle
+    P = omc.init_vae_b(78, hidden=50)   # 50 hidden units: not a multiple of 4 (zero-row padding)
+    model = vae_b_from_oracle(v, P, made_activation='relu')
+    energy = v.mcmc.GaussianMixtureEnergy()
+    B, n_steps = 1500, 10
+    rng = np.random.default_rng(6)
+    k = rng.choice(3, size=B, p=[0.7, 0.2, 0.1])
+    x0 = (omc.GMM_LOCS[k] + omc.GMM_SCALES[k] * rng.standard_normal((B, 2))).astype(np.float32)
+    res = {}
+    for tpc in ('1', '2', '4'):
+        monkeypatch.setenv('VMS_NB_TPC', tpc)
+        mc = v.mcmc.MCMC(model, energy, random_seed=12)
+        x, e = mc.run_nb(x0, n_steps=n_steps, trace=True)
+        res[tpc] = (x, e, mc._last_trace, mc._num_acc)
+    for tpc in ('2', '4'):
+        assert np.array_equal(res[tpc][0], res['1'][0]) and np.array_equal(res[tpc][1], res['1'][1])
+        for key in ('acc', 'fwd', 'rev', 'e_new', 'log_u'):
+            assert np.array_equal(res[tpc][2][key], res['1'][2][key]), (tpc, key)
+        assert res[tpc][3] == res['1'][3]
+    assert 0 < res['1'][3] < B * n_steps
+
+
 def test_device_pcg64_stream_equals_host_stream(vms):
     """The device-drawn accept uniforms (`vms_mc_run_pcg64`) reproduce NumPy's PCG64 stream: same decisions / final state
     as the host-stream path over many steps, for a whole chain set and for a shard (chain0, n_global) of it; the

@@ -36,14 +36,12 @@ using namespace mcdev;
 
 namespace {
 
-constexpr int CT = 128;   // threads per CTA = 32 chains
-constexpr int TPC = 4;    // lanes per chain
+constexpr int CT = 128;   // threads per CTA
 constexpr int MROW = 12;  // floats per FCDeepNN hidden unit: enc W0[0..1][j] b0[j] W1[j][0..1] | dec W0[0][j] b0[j] W1[j][0..3] | pad
 constexpr int DX = 2, DZ = 1, NN = 2 * DZ + DX;
 
 struct NbParams {
   vms_mc_nb_model m;
-  int P;  // padded width of the outer MADE hidden layers (multiple of 4)
   int64_t B;
   int n_steps;
   float* x;
@@ -62,47 +60,45 @@ struct NbParams {
 };
 
 __host__ __device__ inline int table_stride(int K) { return 2 * (K + 1) + (K + 2) / 2; }  // in doubles
+__host__ __device__ inline int r4(int v) { return (v + 3) & ~3; }
 
-// shared-memory image (offsets in floats; the knot tables come first for their 8-byte alignment)
+// shared-memory image (offsets in floats; every region starts on a 16-byte boundary, the knot tables come first for their
+// 8-byte alignment).  Hidden-unit rows are padded with zero rows to a multiple of 4 units: every lane count walks the
+// same four interleaved unit streams (below), a zero row adds +0 to its stream.
 struct Layout {
   int tables, mlp, eb1, db1, l0, mid, tail, gmm, total;
-  int H, RS;
+  int Hp, H1p, RS;
 };
-__host__ __device__ inline Layout make_layout(const vms_mc_nb_model& m, int P) {
+__host__ __device__ inline Layout make_layout(const vms_mc_nb_model& m, int H0P, int H2P) {
   Layout L;
-  L.H = m.enc_hidden > m.dec_hidden ? m.enc_hidden : m.dec_hidden;
-  L.RS = 2 * P + 4;
+  L.Hp = r4(m.enc_hidden > m.dec_hidden ? m.enc_hidden : m.dec_hidden);
+  L.H1p = r4(m.made_hidden[1]);
+  L.RS = r4(H0P + H2P + 2);                // row of middle unit j: W1[:, j] [H0P] | W2[j, :] [H2P] | b1[j] | Wc1[j] | pad
   int o = 0;
-  L.tables = o; o = (o + 2 * m.n_blocks * table_stride(m.n_bins) + 3) & ~3;  // every region starts on a 16-byte boundary
-  L.mlp = o;    o += L.H * MROW;
+  L.tables = o; o = r4(o + 2 * m.n_blocks * table_stride(m.n_bins));
+  L.mlp = o;    o += L.Hp * MROW;
   L.eb1 = o;    o += 4;
   L.db1 = o;    o += 4;
-  L.l0 = o;     o += 4 * P;                 // per unit i: W0[0][i], W0[1][i], Wc0[i], b0[i]
-  L.mid = o;    o += m.made_hidden[1] * L.RS;
-  L.tail = o;   o += 2 * P + 4 * P + 8;     // b2 [P] | Wc2 [P] | W3 [P][4] | b3 [4] | Wc3 [4]
-  L.gmm = o;    o += 5 * m.n_comp;          // log_w [n] | loc [n][2] | scale [n][2]
-  L.total = (o + 3) & ~3;
+  L.l0 = o;     o += 4 * H0P;              // per unit i: W0[0][i], W0[1][i], Wc0[i], b0[i]
+  L.mid = o;    o += L.H1p * L.RS;
+  L.tail = o;   o += 6 * H2P + 8;          // b2 [H2P] | Wc2 [H2P] | W3 [H2P][4] | b3 [4] | Wc3 [4]
+  L.gmm = o;    o += r4(7 * m.n_comp);     // log_w [n] | per (component, dim): scale, loc / scale, 0.5 log 2pi + log scale
+  L.total = r4(o);
   return L;
 }
 
-__device__ __forceinline__ float act_fn(float v, int act) {
-  if (act == VMS_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == VMS_ACT_TANH) return tanhf(v);
-  return v;
-}
+// tfp Normal._log_prob for N(0, 1): normal_lp(x, 0, 1) with its exact simplifications (x / 1 - 0 / 1 = x, log 1 = 0)
+__device__ __forceinline__ float std_normal_lp(float x) { return -0.5f * x * x - VMS_HALF_LOG_2PI; }
 
 // One block of the MAF prior from its knot table (the formulas of rqs_device.cuh `octet_apply`).
-__device__ __forceinline__ void spline_apply(const double* __restrict__ tb, int K, float bin_min, float v, bool inv, float& out,
-                                             float& ldj) {
+__device__ __noinline__ float2 spline_apply(const double* __restrict__ tb, int K, float bin_min, float v, bool inv) {
   const double* kx = tb;
   const double* ky = tb + (K + 1);
   const float* dks = reinterpret_cast<const float*>(tb + 2 * (K + 1));
   const double* ks = inv ? ky : kx;
   const double vd = (double)v;
-  out = v;
-  ldj = 0.f;
   // bin k covers [knot k, knot k+1); the range edges themselves are outside (TFP: identity)
-  if (!(vd > (double)bin_min && vd < ks[K])) return;
+  if (!(vd > (double)bin_min && vd < ks[K])) return make_float2(v, 0.f);
   int lo = 0, hi = K;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -117,6 +113,7 @@ __device__ __forceinline__ void spline_apply(const double* __restrict__ tb, int 
   const float rr = rqsdev::rel_pos(b, vd, sk, dk, dk1, inv);
   const float omr = 1.f - rr, u = rr * omr;
   const float den = sk + (dk1 + dk - 2.f * sk) * u;
+  float out;
   if (!inv) {
     const float num = b.hk * (sk * rr * rr + dk * u);
     out = (float)(b.lo_y + (double)(num / den));
@@ -124,85 +121,142 @@ __device__ __forceinline__ void spline_apply(const double* __restrict__ tb, int 
     out = (float)(b.lo_x + (double)(rr * b.wk));
   }
   const float Pq = dk1 * rr * rr + 2.f * sk * u + dk * omr * omr;
-  ldj = logf((sk * sk) * Pq / (den * den));
-  if (inv) ldj = -ldj;
+  const float ldj = logf((sk * sk) * Pq / (den * den));
+  return make_float2(out, inv ? -ldj : ldj);
 }
 
-// encoder(xe) and decoder-mapping(zd) side by side on this lane's hidden units j = sub, sub + 4, ...
-__device__ __forceinline__ void mlp_pair(const float* __restrict__ rows, int H, int sub, float x0, float x1, float zd,
-                                         float (&pe)[2], float (&pd)[4]) {
-  pe[0] = pe[1] = 0.f;
-  pd[0] = pd[1] = pd[2] = pd[3] = 0.f;
-#pragma unroll 2
-  for (int j = sub; j < H; j += TPC) {
-    const float4* row = reinterpret_cast<const float4*>(rows + j * MROW);
-    const float4 a = row[0], b = row[1], c = row[2];
-    float he = fmaf(x1, a.y, x0 * a.x);
-    he = fmaxf(he + a.z, 0.f);
-    pe[0] = fmaf(he, a.w, pe[0]);
-    pe[1] = fmaf(he, b.x, pe[1]);
-    const float hd = fmaxf(fmaf(zd, b.y, b.z), 0.f);
-    pd[0] = fmaf(hd, b.w, pd[0]);
-    pd[1] = fmaf(hd, c.x, pd[1]);
-    pd[2] = fmaf(hd, c.y, pd[2]);
-    pd[3] = fmaf(hd, c.z, pd[3]);
+// The hidden units of every wide layer are walked as FOUR interleaved streams (units j = s, s + 4, ... for s = 0..3), each
+// summed in ascending j, and the four partial sums meet as (s0 + s1) + (s2 + s3).  A chain is owned by TPC lanes (4, 2 or 1),
+// each taking 4 / TPC streams: the summation order, hence every bit of every result and every decision, is the same for
+// every TPC, so the launcher may pick the lane count by the number of chains (one lane per chain when there are enough chains
+// to fill the GPU: no replicated scalar work, a quarter of the shared-memory traffic; four lanes when chains are scarce,
+// e.g. a shard of a multi-GPU job).
+template <int TPC>
+__device__ __forceinline__ float combine(const float (&a)[4 / TPC]) {
+  if constexpr (TPC == 4) {
+    return quad_sum(a[0]);
+  } else if constexpr (TPC == 2) {
+    const float t0 = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+    const float t1 = a[1] + __shfl_xor_sync(0xffffffffu, a[1], 1);
+    return t0 + t1;
+  } else {
+    return (a[0] + a[1]) + (a[2] + a[3]);
   }
-  pe[0] = quad_sum(pe[0]); pe[1] = quad_sum(pe[1]);
+}
+
+// encoder(x0, x1) and decoder-mapping(zd) side by side
+template <int TPC>
+__device__ __forceinline__ void mlp_pair(const float* __restrict__ rows, int Hp, int sub, float x0, float x1, float zd,
+                                         float (&pe)[2], float (&pd)[4]) {
+  constexpr int NS = 4 / TPC;
+  float ae[2][NS], ad[4][NS];
 #pragma unroll
-  for (int n = 0; n < 4; ++n) pd[n] = quad_sum(pd[n]);
+  for (int q = 0; q < NS; ++q) {
+    ae[0][q] = ae[1][q] = 0.f;
+    ad[0][q] = ad[1][q] = ad[2][q] = ad[3][q] = 0.f;
+  }
+#pragma unroll 2
+  for (int j0 = 0; j0 < Hp; j0 += 4) {
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const float4* row = reinterpret_cast<const float4*>(rows + (j0 + sub + TPC * q) * MROW);
+      const float4 a = row[0], b = row[1], c = row[2];
+      float he = fmaf(x1, a.y, x0 * a.x);
+      he = fmaxf(he + a.z, 0.f);
+      ae[0][q] = fmaf(he, a.w, ae[0][q]);
+      ae[1][q] = fmaf(he, b.x, ae[1][q]);
+      const float hd = fmaxf(fmaf(zd, b.y, b.z), 0.f);
+      ad[0][q] = fmaf(hd, b.w, ad[0][q]);
+      ad[1][q] = fmaf(hd, c.x, ad[1][q]);
+      ad[2][q] = fmaf(hd, c.y, ad[2][q]);
+      ad[3][q] = fmaf(hd, c.z, ad[3][q]);
+    }
+  }
+  pe[0] = combine<TPC>(ae[0]); pe[1] = combine<TPC>(ae[1]);
+#pragma unroll
+  for (int n = 0; n < 4; ++n) pd[n] = combine<TPC>(ad[n]);
+}
+
+// activation of tfp's AutoregressiveNetwork hidden layers: none / relu as one max (lo = -inf / 0), tanh on a uniform flag
+__device__ __forceinline__ float act_fn(float v, float lo, bool is_tanh) {
+  v = fmaxf(v, lo);
+  return is_tanh ? tanhf(v) : v;
 }
 
 // AutoregressiveNetwork(params = 2, event 2, conditional 1, hidden [h0, h1, h2]) on (s0, s1 | cond) -> out [dof][param]
-template <int P>
-__device__ __forceinline__ void made_pass(const float* __restrict__ sm, const Layout& L, int h1, int act, int sub, float s0,
-                                          float s1, float cond, float (&out)[4]) {
-  float a0[P], a2[P];
+template <int TPC, int H0P, int H2P>
+__device__ __forceinline__ float4 made_pass(const float* __restrict__ sm, const Layout& L, float act_lo, bool is_tanh, int sub,
+                                            float s0, float s1, float cond) {
+  constexpr int NS = 4 / TPC;
+  constexpr int RS = (H0P + H2P + 2 + 3) & ~3;
+  float a0[H0P];
   const float4* l0 = reinterpret_cast<const float4*>(sm + L.l0);
 #pragma unroll
-  for (int i = 0; i < P; ++i) {
+  for (int i = 0; i < H0P; ++i) {
     const float4 w = l0[i];
-    a0[i] = act_fn(fmaf(cond, w.z, fmaf(s1, w.y, s0 * w.x)) + w.w, act);  // (padding units: act(0) = 0 for every supported act)
-    a2[i] = 0.f;
+    a0[i] = act_fn(fmaf(cond, w.z, fmaf(s1, w.y, s0 * w.x)) + w.w, act_lo, is_tanh);  // (padding units: act(0) = 0)
   }
+  float a2[H2P][NS];
+#pragma unroll
+  for (int k = 0; k < H2P; ++k)
+#pragma unroll
+    for (int q = 0; q < NS; ++q) a2[k][q] = 0.f;
 #pragma unroll 1
-  for (int j = sub; j < h1; j += TPC) {
-    const float4* row = reinterpret_cast<const float4*>(sm + L.mid + j * L.RS);
-    const float4 t = row[2 * (P / 4)];  // b1[j], Wc1[j]
-    float h = cond * t.y;
+  for (int j0 = 0; j0 < L.H1p; j0 += 4) {
 #pragma unroll
-    for (int q = 0; q < P / 4; ++q) {
-      const float4 w = row[q];
-      h = fmaf(a0[4 * q], w.x, h); h = fmaf(a0[4 * q + 1], w.y, h); h = fmaf(a0[4 * q + 2], w.z, h); h = fmaf(a0[4 * q + 3], w.w, h);
-    }
-    h = act_fn(h + t.x, act);
+    for (int q = 0; q < NS; ++q) {
+      const float4* row = reinterpret_cast<const float4*>(sm + L.mid + (j0 + sub + TPC * q) * RS);
+      float w[RS];
 #pragma unroll
-    for (int q = 0; q < P / 4; ++q) {
-      const float4 w = row[P / 4 + q];
-      a2[4 * q] = fmaf(h, w.x, a2[4 * q]); a2[4 * q + 1] = fmaf(h, w.y, a2[4 * q + 1]);
-      a2[4 * q + 2] = fmaf(h, w.z, a2[4 * q + 2]); a2[4 * q + 3] = fmaf(h, w.w, a2[4 * q + 3]);
+      for (int t = 0; t < RS / 4; ++t) {
+        const float4 r = row[t];
+        w[4 * t] = r.x; w[4 * t + 1] = r.y; w[4 * t + 2] = r.z; w[4 * t + 3] = r.w;
+      }
+      float h = cond * w[H0P + H2P + 1];
+#pragma unroll
+      for (int i = 0; i < H0P; ++i) h = fmaf(a0[i], w[i], h);
+      h = act_fn(h + w[H0P + H2P], act_lo, is_tanh);
+#pragma unroll
+      for (int k = 0; k < H2P; ++k) a2[k][q] = fmaf(h, w[H0P + k], a2[k][q]);
     }
   }
   const float* tl = sm + L.tail;
-  const float4* b3 = reinterpret_cast<const float4*>(tl + 6 * P);
-  const float4 bb = b3[0], wc = b3[1];
+  const float4 bb = reinterpret_cast<const float4*>(tl + 6 * H2P)[0], wc = reinterpret_cast<const float4*>(tl + 6 * H2P)[1];
   float o0 = fmaf(cond, wc.x, bb.x), o1 = fmaf(cond, wc.y, bb.y), o2 = fmaf(cond, wc.z, bb.z), o3 = fmaf(cond, wc.w, bb.w);
-  const float4* W3 = reinterpret_cast<const float4*>(tl + 2 * P);
+  const float4* W3 = reinterpret_cast<const float4*>(tl + 2 * H2P);
 #pragma unroll
-  for (int k = 0; k < P; ++k) {
-    const float v = act_fn(fmaf(cond, tl[P + k], quad_sum(a2[k])) + tl[k], act);
+  for (int k = 0; k < H2P; ++k) {
+    const float v = act_fn(fmaf(cond, tl[H2P + k], combine<TPC>(a2[k])) + tl[k], act_lo, is_tanh);
     const float4 w = W3[k];
     o0 = fmaf(v, w.x, o0); o1 = fmaf(v, w.y, o1); o2 = fmaf(v, w.z, o2); o3 = fmaf(v, w.w, o3);
   }
-  out[0] = o0; out[1] = o1; out[2] = o2; out[3] = o3;
+  return make_float4(o0, o1, o2, o3);
 }
 
-// Mixture log-density as tfp evaluates it in float32 (mcmc.cu energy_gmm_kernel)
+// tfp Autoregressive sampling without mask knowledge (cold path): sample0 = ones, D + 1 passes with the same noise
+template <int TPC, int H0P, int H2P>
+__device__ __noinline__ float2 ar_sample_generic(const float* __restrict__ sm, const Layout L, float act_lo, bool is_tanh,
+                                                 int sub, float4 in, float e0, float e1, float cond) {
+  float s0 = 1.f, s1 = 1.f;
+#pragma unroll 1
+  for (int pass = 0; pass < DX + 1; ++pass) {
+    const float4 mo = made_pass<TPC, H0P, H2P>(sm, L, act_lo, is_tanh, sub, s0, s1, cond);
+    const float l0 = in.x + mo.x, c0 = softplus_tf(in.y + mo.y) + VMS_EPS32;
+    const float l1 = in.z + mo.z, c1 = softplus_tf(in.w + mo.w) + VMS_EPS32;
+    s0 = __fadd_rn(__fmul_rn(e0, c0), l0);
+    s1 = __fadd_rn(__fmul_rn(e1, c1), l1);
+  }
+  return make_float2(s0, s1);
+}
+
+// Mixture log-density as tfp evaluates it in float32 (mcmc.cu energy_gmm_kernel): per component sum_d Normal log_prob
+// (x / s - m / s form; m / s and 0.5 log 2pi + log s staged) + log cat prob, max-shifted logsumexp over the components.
 __device__ __forceinline__ float gmm_component(const float* __restrict__ g, int n, int k, float x0, float x1) {
-  const float* loc = g + n;
-  const float* sc = g + 3 * n;
+  const float* c = g + n + 6 * k;
+  const float z0 = x0 / c[0] - c[1], z1 = x1 / c[3] - c[4];
   float s = 0.f;
-  s += normal_lp(x0, loc[2 * k], sc[2 * k]);
-  s += normal_lp(x1, loc[2 * k + 1], sc[2 * k + 1]);
+  s += -0.5f * z0 * z0 - c[2];
+  s += -0.5f * z1 * z1 - c[5];
   return s + g[k];
 }
 __device__ __forceinline__ float gmm_energy(const float* __restrict__ g, int n, float x0, float x1) {
@@ -232,12 +286,15 @@ __device__ __forceinline__ float gmm_energy(const float* __restrict__ g, int n, 
   for (int k = 0; k < n; ++k) acc += expf(lp[k] - mx);
   return mx + logf(acc);
 }
+__device__ __noinline__ float gmm_energy_cold(const float* __restrict__ g, int n, float x0, float x1) {
+  return gmm_energy(g, n, x0, x1);
+}
 
-template <int P, int MINB>
-__global__ void __launch_bounds__(CT, MINB) mc_nb_kernel(const NbParams p) {
+template <int TPC, int H0P, int H2P>
+__global__ void __launch_bounds__(CT) mc_nb_kernel(const NbParams p) {
   extern __shared__ __align__(16) float sm[];
   const vms_mc_nb_model& m = p.m;
-  const Layout L = make_layout(m, P);
+  const Layout L = make_layout(m, H0P, H2P);
   const int tid = threadIdx.x;
   const int K = m.n_bins, nb = m.n_blocks, TS = table_stride(K);
   const int h0 = m.made_hidden[0], h1 = m.made_hidden[1], h2 = m.made_hidden[2];
@@ -245,7 +302,7 @@ __global__ void __launch_bounds__(CT, MINB) mc_nb_kernel(const NbParams p) {
   {
     const float* src = reinterpret_cast<const float*>(m.tables);
     for (int e = tid; e < 2 * nb * TS; e += CT) sm[L.tables + e] = __ldg(src + e);
-    for (int e = tid; e < L.H * MROW; e += CT) {
+    for (int e = tid; e < L.Hp * MROW; e += CT) {
       const int j = e / MROW, c = e - j * MROW;
       float v = 0.f;
       if (j < m.enc_hidden) {
@@ -262,33 +319,41 @@ __global__ void __launch_bounds__(CT, MINB) mc_nb_kernel(const NbParams p) {
     }
     if (tid < 2) sm[L.eb1 + tid] = __ldg(m.enc_b1 + tid);
     if (tid < 4) sm[L.db1 + tid] = __ldg(m.dec_b1 + tid);
-    for (int e = tid; e < 4 * P; e += CT) {
+    for (int e = tid; e < 4 * H0P; e += CT) {
       const int i = e >> 2, c = e & 3;
       float v = 0.f;
       if (i < h0) v = c < 2 ? __ldg(m.made_W[0] + c * h0 + i) : (c == 2 ? __ldg(m.made_Wc[0] + i) : __ldg(m.made_b[0] + i));
       sm[L.l0 + e] = v;
     }
-    for (int e = tid; e < h1 * L.RS; e += CT) {
+    for (int e = tid; e < L.H1p * L.RS; e += CT) {
       const int j = e / L.RS, c = e - j * L.RS;
       float v = 0.f;
-      if (c < P) { if (c < h0) v = __ldg(m.made_W[1] + c * h1 + j); }
-      else if (c < 2 * P) { if (c - P < h2) v = __ldg(m.made_W[2] + j * h2 + (c - P)); }
-      else if (c == 2 * P) v = __ldg(m.made_b[1] + j);
-      else if (c == 2 * P + 1) v = __ldg(m.made_Wc[1] + j);
+      if (j < h1) {
+        if (c < H0P) { if (c < h0) v = __ldg(m.made_W[1] + c * h1 + j); }
+        else if (c < H0P + H2P) { if (c - H0P < h2) v = __ldg(m.made_W[2] + j * h2 + (c - H0P)); }
+        else if (c == H0P + H2P) v = __ldg(m.made_b[1] + j);
+        else if (c == H0P + H2P + 1) v = __ldg(m.made_Wc[1] + j);
+      }
       sm[L.mid + e] = v;
     }
-    for (int e = tid; e < 6 * P + 8; e += CT) {
+    for (int e = tid; e < 6 * H2P + 8; e += CT) {
       float v = 0.f;
-      if (e < P) { if (e < h2) v = __ldg(m.made_b[2] + e); }
-      else if (e < 2 * P) { if (e - P < h2) v = __ldg(m.made_Wc[2] + (e - P)); }
-      else if (e < 6 * P) { const int k = (e - 2 * P) >> 2, n = (e - 2 * P) & 3; if (k < h2) v = __ldg(m.made_W[3] + k * 4 + n); }
-      else if (e < 6 * P + 4) v = __ldg(m.made_b[3] + (e - 6 * P));
-      else v = __ldg(m.made_Wc[3] + (e - 6 * P - 4));
+      if (e < H2P) { if (e < h2) v = __ldg(m.made_b[2] + e); }
+      else if (e < 2 * H2P) { if (e - H2P < h2) v = __ldg(m.made_Wc[2] + (e - H2P)); }
+      else if (e < 6 * H2P) { const int k = (e - 2 * H2P) >> 2, n = (e - 2 * H2P) & 3; if (k < h2) v = __ldg(m.made_W[3] + k * 4 + n); }
+      else if (e < 6 * H2P + 4) v = __ldg(m.made_b[3] + (e - 6 * H2P));
+      else v = __ldg(m.made_Wc[3] + (e - 6 * H2P - 4));
       sm[L.tail + e] = v;
     }
     const int n = m.n_comp;
-    for (int e = tid; e < 5 * n; e += CT)
-      sm[L.gmm + e] = e < n ? __ldg(m.gmm_log_w + e) : (e < 3 * n ? __ldg(m.gmm_loc + (e - n)) : __ldg(m.gmm_scale + (e - 3 * n)));
+    if (tid < n) sm[L.gmm + tid] = __ldg(m.gmm_log_w + tid);
+    for (int e = tid; e < 2 * n; e += CT) {  // (component, dim) pairs
+      const float sc = __ldg(m.gmm_scale + e), lc = __ldg(m.gmm_loc + e);
+      float* c = sm + L.gmm + n + 3 * e;
+      c[0] = sc;
+      c[1] = lc / sc;
+      c[2] = VMS_HALF_LOG_2PI + logf(sc);
+    }
   }
   __syncthreads();
   const double* tables = reinterpret_cast<const double*>(sm + L.tables);
@@ -296,16 +361,18 @@ __global__ void __launch_bounds__(CT, MINB) mc_nb_kernel(const NbParams p) {
   const float* eb1 = sm + L.eb1;
   const float* db1 = sm + L.db1;
   const float* gmm = sm + L.gmm;
-  const int act = m.made_act;
+  const bool is_tanh = m.made_act == VMS_ACT_TANH;
+  const float act_lo = m.made_act == VMS_ACT_RELU ? 0.f : -INFINITY;
+  const int first = m.made_first_dof;
 
-  const int64_t chain = (int64_t)blockIdx.x * (CT / TPC) + (tid / TPC);
+  const int64_t chain = ((int64_t)blockIdx.x * CT + tid) / TPC;
   const int sub = tid & (TPC - 1);
   const bool live = chain < p.B;
   const int64_t cc = live ? chain : p.B - 1;  // idle lanes shadow the last chain (full-warp shuffles), writes predicated off
   float x1[DX];
   x1[0] = __ldg(p.x + cc * DX);
   x1[1] = __ldg(p.x + cc * DX + 1);
-  float e_old = p.energies_valid ? p.E[cc] : gmm_energy(gmm, m.n_comp, x1[0], x1[1]);
+  float e_old = p.energies_valid ? p.E[cc] : gmm_energy_cold(gmm, m.n_comp, x1[0], x1[1]);
   unsigned n_accept = 0, n_unc = 0;
   U128 rs = {0ull, 0ull};
   const U128 jm = {p.jm_hi, p.jm_lo}, ja = {p.ja_hi, p.ja_lo};
@@ -327,88 +394,72 @@ __global__ void __launch_bounds__(CT, MINB) mc_nb_kernel(const NbParams p) {
       box_muller(rnd.x, rnd.y, nz[0], nz[1]);
       box_muller(rnd.z, rnd.w, nz[2], nz[3]);
     }
-    // ---- z2 ~ prior: base noise through the chain's blocks in sampling direction; log p(z2) = log N(eps) - sum fldj
-    float z2 = nz[1];
-    float lz2 = normal_lp(nz[1], 0.f, 1.f);
-    {
-      float fl = 0.f;
+    // Forward move (dir 0): z2 ~ prior, z1 ~ encoder(x1), x2 ~ decoder(z2) with their log-probabilities (mcmc.py:100-103);
+    // reverse move (dir 1): encoder(x2).log_prob(z2), prior.log_prob(z1), decoder(z1).log_prob(x1) (mcmc.py:106-109).
+    // Both halves are: the prior's spline chain, encoder || decoder-mapping, one MADE pass, a blockwise Normal log_prob.
+    float z1 = 0.f, z2 = 0.f, x2[DX] = {0.f, 0.f}, e_new = 0.f;
+    float lq0 = 0.f, lq1 = 0.f, lz0 = 0.f, lz1 = 0.f, lx0 = 0.f, lx1 = 0.f;
+#pragma unroll 1
+    for (int dir = 0; dir < 2; ++dir) {
+      // ---- prior: base noise through the blocks in sampling direction (log p = log N(eps) - sum fldj), or z1 back through
+      // them (log p = log N(base) + sum ildj)
+      float v = dir ? z1 : nz[1], ld = 0.f;
 #pragma unroll 1
       for (int b = 0; b < nb; ++b) {
-        float y, l;
-        spline_apply(tables + b * TS, K, m.range_min, z2, false, y, l);
-        z2 = y;
-        fl += l;
+        const float2 r = spline_apply(tables + (dir ? nb - 1 - b : b) * TS, K, m.range_min, v, dir != 0);
+        v = r.x;
+        ld += r.y;
       }
-      lz2 -= fl;
-    }
-    // ---- encoder(x1) || decoder-mapping(z2)
-    float pe[2], pd[4];
-    mlp_pair(rows, L.H, sub, x1[0], x1[1], z2, pe, pd);
-    const float loc1 = pe[0] + eb1[0], sc1 = softplus_tf(pe[1] + eb1[1]);
-    const float z1 = __fadd_rn(__fmul_rn(nz[0], sc1), loc1);
-    const float lq1 = normal_lp(z1, loc1, sc1);
-    // ---- x2 ~ decoder(z2): tfp Autoregressive sampling, sample0 = ones, D + 1 passes with the same noise, then log_prob
-    float in2[4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) in2[n] = pd[n] + db1[n];
-    float s0 = 1.f, s1 = 1.f, mo[4];
-    if (m.made_first_dof >= 0) {
-      // The masks make the first dof's parameters a function of the conditional input alone (its output columns of the last
-      // kernel are zero: fmaf(v, 0, o) == o) and hide the second dof from every hidden unit (its input row is zero), so
-      // passes 2, 3 and the log_prob pass of tfp's procedure see bit-identical hidden activations: one pass gives them all.
-      const bool f = m.made_first_dof != 0;
-      const float4 bb = reinterpret_cast<const float4*>(sm + L.tail + 6 * P)[0], wc = reinterpret_cast<const float4*>(sm + L.tail + 6 * P)[1];
-      const float lf = (f ? in2[2] : in2[0]) + fmaf(z2, f ? wc.z : wc.x, f ? bb.z : bb.x);
-      const float cf = softplus_tf((f ? in2[3] : in2[1]) + fmaf(z2, f ? wc.w : wc.y, f ? bb.w : bb.y)) + VMS_EPS32;
-      const float sf = __fadd_rn(__fmul_rn(f ? nz[3] : nz[2], cf), lf);
-      if (f) s1 = sf; else s0 = sf;
-      made_pass<P>(sm, L, h1, act, sub, s0, s1, z2, mo);
-      const float lo_ = f ? in2[0] + mo[0] : in2[2] + mo[2];
-      const float co = softplus_tf(f ? in2[1] + mo[1] : in2[3] + mo[3]) + VMS_EPS32;
-      const float so = __fadd_rn(__fmul_rn(f ? nz[2] : nz[3], co), lo_);
-      if (f) s0 = so; else s1 = so;
-    } else {
-#pragma unroll 1
-      for (int pass = 0; pass < DX + 1; ++pass) {
-        made_pass<P>(sm, L, h1, act, sub, s0, s1, z2, mo);
-        const float l0 = in2[0] + mo[0], c0 = softplus_tf(in2[1] + mo[1]) + VMS_EPS32;
-        const float l1 = in2[2] + mo[2], c1 = softplus_tf(in2[3] + mo[3]) + VMS_EPS32;
-        s0 = __fadd_rn(__fmul_rn(nz[2], c0), l0);
-        s1 = __fadd_rn(__fmul_rn(nz[3], c1), l1);
+      if (!dir) { z2 = v; lz0 = std_normal_lp(nz[1]) - ld; } else { lz1 = std_normal_lp(v) + ld; }
+      // ---- encoder(x) || decoder-mapping(z)
+      const float zd = dir ? z1 : z2;
+      float pe[2], pd[4];
+      mlp_pair<TPC>(rows, L.Hp, sub, dir ? x2[0] : x1[0], dir ? x2[1] : x1[1], zd, pe, pd);
+      const float loc = pe[0] + eb1[0], sc = softplus_tf(pe[1] + eb1[1]);
+      if (!dir) z1 = __fadd_rn(__fmul_rn(nz[0], sc), loc);
+      { const float t = normal_lp(dir ? z2 : z1, loc, sc); if (dir) lq1 = t; else lq0 = t; }
+      const float4 in = make_float4(pd[0] + db1[0], pd[1] + db1[1], pd[2] + db1[2], pd[3] + db1[3]);
+      // ---- decoder: tfp Autoregressive over a Blockwise Normal whose raw parameters are in + MADE(samples | z)
+      float s0 = x1[0], s1 = x1[1];
+      if (!dir) {
+        s0 = s1 = 1.f;  // sample0 = ones (dists.py:338)
+        if (first >= 0) {
+          // The masks make the first dof's parameters a function of the conditional input alone (its output columns of the
+          // last kernel are zero: fmaf(v, 0, o) == o) and hide the other dof from every hidden unit (its input row is zero),
+          // so tfp's passes 2, 3 and the log_prob pass see bit-identical hidden activations: ONE pass below gives them all.
+          const bool f = first != 0;
+          const float4 bb = reinterpret_cast<const float4*>(sm + L.tail + 6 * H2P)[0];
+          const float4 wc = reinterpret_cast<const float4*>(sm + L.tail + 6 * H2P)[1];
+          const float lf = (f ? in.z : in.x) + fmaf(zd, f ? wc.z : wc.x, f ? bb.z : bb.x);
+          const float cf = softplus_tf((f ? in.w : in.y) + fmaf(zd, f ? wc.w : wc.y, f ? bb.w : bb.y)) + VMS_EPS32;
+          const float sf = __fadd_rn(__fmul_rn(f ? nz[3] : nz[2], cf), lf);
+          if (f) s1 = sf; else s0 = sf;
+        } else {
+          const float2 s = ar_sample_generic<TPC, H0P, H2P>(sm, L, act_lo, is_tanh, sub, in, nz[2], nz[3], zd);
+          s0 = s.x;
+          s1 = s.y;
+        }
       }
-      made_pass<P>(sm, L, h1, act, sub, s0, s1, z2, mo);
-    }
-    const float x2[DX] = {s0, s1};
-    float lx2 = 0.f;
-    lx2 += normal_lp(x2[0], in2[0] + mo[0], softplus_tf(in2[1] + mo[1]) + VMS_EPS32);
-    lx2 += normal_lp(x2[1], in2[2] + mo[2], softplus_tf(in2[3] + mo[3]) + VMS_EPS32);
-    const float e_new = gmm_energy(gmm, m.n_comp, x2[0], x2[1]);
-    // ---- reverse move: encoder(x2) || decoder-mapping(z1); prior.log_prob(z1); decoder(z1).log_prob(x1)
-    float pe2[2], pd1[4];
-    mlp_pair(rows, L.H, sub, x2[0], x2[1], z1, pe2, pd1);
-    const float lq2 = normal_lp(z2, pe2[0] + eb1[0], softplus_tf(pe2[1] + eb1[1]));
-    float lz1;
-    {
-      float v = z1, il = 0.f;
-#pragma unroll 1
-      for (int b = nb - 1; b >= 0; --b) {
-        float y, l;
-        spline_apply(tables + b * TS, K, m.range_min, v, true, y, l);
-        v = y;
-        il += l;
+      const float4 mo = made_pass<TPC, H0P, H2P>(sm, L, act_lo, is_tanh, sub, s0, s1, zd);
+      const float l0 = in.x + mo.x, c0 = softplus_tf(in.y + mo.y) + VMS_EPS32;
+      const float l1 = in.z + mo.z, c1 = softplus_tf(in.w + mo.w) + VMS_EPS32;
+      if (!dir && first >= 0) {  // the second dof's sample from the same pass
+        if (first != 0) s0 = __fadd_rn(__fmul_rn(nz[2], c0), l0);
+        else s1 = __fadd_rn(__fmul_rn(nz[3], c1), l1);
       }
-      lz1 = normal_lp(v, 0.f, 1.f) + il;
+      float lp = 0.f;
+      lp += normal_lp(s0, l0, c0);
+      lp += normal_lp(s1, l1, c1);
+      if (dir) lx1 = lp; else lx0 = lp;
+      if (!dir) {
+        x2[0] = s0;
+        x2[1] = s1;
+        e_new = gmm_energy(gmm, m.n_comp, s0, s1);
+      }
     }
-    float in1[4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) in1[n] = pd1[n] + db1[n];
-    made_pass<P>(sm, L, h1, act, sub, x1[0], x1[1], z1, mo);
-    float lx1 = 0.f;
-    lx1 += normal_lp(x1[0], in1[0] + mo[0], softplus_tf(in1[1] + mo[1]) + VMS_EPS32);
-    lx1 += normal_lp(x1[1], in1[2] + mo[2], softplus_tf(in1[3] + mo[3]) + VMS_EPS32);
     // ---- accept / reject (mcmc.py:103, :109, :116-120), NumPy's float32 evaluation for a float32 energy
-    const float fwd = __fadd_rn(__fadd_rn(lq1, lz2), lx2);
-    const float rev = __fadd_rn(__fadd_rn(lq2, lz1), lx1);
+    const float fwd = __fadd_rn(__fadd_rn(lq0, lz0), lx0);
+    const float rev = __fadd_rn(__fadd_rn(lq1, lz1), lx1);
     const int64_t g = (int64_t)step * p.B + cc;
     const double la = (double)__fsub_rn(__fsub_rn(__fadd_rn(e_new, rev), e_old), fwd);
     double lu;
@@ -537,8 +588,6 @@ vms_status vms_mc_nb_run(const vms_mc_nb_model* model, float* x, float* E, int e
   if (B == 0 || n_steps == 0) return VMS_OK;
   NbParams p = {};
   p.m = m;
-  const int wide = m.made_hidden[0] > m.made_hidden[2] ? m.made_hidden[0] : m.made_hidden[2];
-  p.P = wide <= 12 ? 12 : 16;
   if (rng) {
     p.use_pcg = 1;
     p.s0_hi = rng->state_hi; p.s0_lo = rng->state_lo; p.inc_hi = rng->inc_hi; p.inc_lo = rng->inc_lo;
@@ -550,26 +599,37 @@ vms_status vms_mc_nb_run(const vms_mc_nb_model* model, float* x, float* E, int e
   p.n_acc = n_acc; p.n_uncertain = n_uncertain;
   p.acc_trace = acc_trace; p.fwd_trace = fwd_trace; p.rev_trace = rev_trace; p.e_new_trace = e_new_trace;
   p.log_u_trace = log_u_trace;
-  const Layout L = make_layout(m, p.P);
+  // outer MADE widths as staged: the notebook's [10, ., 10] exactly, anything else zero-padded to 12 or 16
+  const int wide = m.made_hidden[0] > m.made_hidden[2] ? m.made_hidden[0] : m.made_hidden[2];
+  const int HP = (m.made_hidden[0] == 10 && m.made_hidden[2] == 10) ? 10 : (wide <= 12 ? 12 : 16);
+  const Layout L = make_layout(m, HP, HP);
   const size_t smem = (size_t)L.total * sizeof(float);
   VMS_REQUIRE(smem <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "mc_nb_run: model too large for shared memory");
   cudaStream_t st = as_stream(stream);
-  const unsigned grid = (unsigned)((B + CT / TPC - 1) / (CT / TPC));
-  int occ = 2;
-  if (const char* e = getenv("VMS_NB_OCC")) occ = atoi(e);  // development aid: resident CTAs per SM the register budget targets
-#define VMS_NB_LAUNCH(PP, OO)                                                                                        \
-  do {                                                                                                               \
-    VMS_CUDA(cudaFuncSetAttribute(mc_nb_kernel<PP, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    mc_nb_kernel<PP, OO><<<grid, CT, smem, st>>>(p);                                                                 \
-  } while (0)
-  if (p.P == 12) {
-    if (occ <= 1) VMS_NB_LAUNCH(12, 1);
-    else if (occ == 2) VMS_NB_LAUNCH(12, 2);
-    else if (occ == 3) VMS_NB_LAUNCH(12, 3);
-    else VMS_NB_LAUNCH(12, 4);
-  } else {
-    VMS_NB_LAUNCH(16, 2);
+  // lanes per chain: one when the chains alone fill the GPU, four otherwise (identical results, see `combine`)
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  int tpc = B >= (int64_t)sms * 256 ? 1 : 4;
+  if (const char* e = getenv("VMS_NB_TPC")) {  // cross-checks: force a lane count
+    const int t = atoi(e);
+    if (t == 1 || t == 2 || t == 4) tpc = t;
   }
+  const unsigned grid = (unsigned)((B * tpc + CT - 1) / CT);
+#define VMS_NB_LAUNCH(T, H)                                                                                        \
+  do {                                                                                                             \
+    VMS_CUDA(cudaFuncSetAttribute(mc_nb_kernel<T, H, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mc_nb_kernel<T, H, H><<<grid, CT, smem, st>>>(p);                                                              \
+  } while (0)
+#define VMS_NB_SHAPE(T)                 \
+  do {                                  \
+    if (HP == 10) VMS_NB_LAUNCH(T, 10); \
+    else if (HP == 12) VMS_NB_LAUNCH(T, 12); \
+    else VMS_NB_LAUNCH(T, 16);          \
+  } while (0)
+  if (tpc == 1) VMS_NB_SHAPE(1);
+  else if (tpc == 2) VMS_NB_SHAPE(2);
+  else VMS_NB_SHAPE(4);
+#undef VMS_NB_SHAPE
 #undef VMS_NB_LAUNCH
   VMS_LAUNCH_CHECK("mc_nb_kernel");
   return VMS_OK;
