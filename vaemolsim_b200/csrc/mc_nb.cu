@@ -606,10 +606,11 @@ vms_status vms_mc_nb_run(const vms_mc_nb_model* model, float* x, float* E, int e
   const size_t smem = (size_t)L.total * sizeof(float);
   VMS_REQUIRE(smem <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "mc_nb_run: model too large for shared memory");
   cudaStream_t st = as_stream(stream);
-  // lanes per chain: one when the chains alone fill the GPU, four otherwise (identical results, see `combine`)
+  // lanes per chain: one when the chains alone fill the GPU, two / four when they are scarce (identical results, see `combine`)
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  int tpc = B >= (int64_t)sms * 256 ? 1 : 4;
+  // (B200, 148 SMs, measured: 1 lane wins from 16,384 chains up, 2 lanes around 8,192, 4 lanes below ~6,000)
+  int tpc = B >= (int64_t)sms * 110 ? 1 : (B >= (int64_t)sms * 40 ? 2 : 4);
   if (const char* e = getenv("VMS_NB_TPC")) {  // cross-checks: force a lane count
     const int t = atoi(e);
     if (t == 1 || t == 2 || t == 4) tpc = t;
