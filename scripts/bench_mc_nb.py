@@ -15,12 +15,14 @@ model = bench.build_c4b_model(v)
 x0 = bench.gmm_start(65536)
 for arg in sys.argv[1:] or ['auto']:
     tpc, _, nch = arg.partition(':')
+    nch, _, occ_ = nch.partition(':')
     nch = int(nch or 65536)
+    os.environ['VMS_NB_OCC'] = occ_ or '2'
     if tpc == 'auto':
         os.environ.pop('VMS_NB_TPC', None)
     else:
         os.environ['VMS_NB_TPC'] = tpc
-    occ = 'tpc %s, %d chains' % (tpc, nch)
+    occ = 'tpc %s, %d chains, occ %s' % (tpc, nch, occ_ or '2')
     mc = v.mcmc.MCMC(model, v.mcmc.GaussianMixtureEnergy(), random_seed=5002)
     xd = v.Tensor.from_numpy(np.ascontiguousarray(x0[:nch]))
     xd, ed = mc.run_nb(None, n_steps=100, configs_dev=xd)

@@ -737,6 +737,28 @@ def test_fused_mc_notebook_kernel_equals_op_by_op_path_over_many_steps(vms):
     assert np.array_equal(xs, xw[lo:hi]) and np.array_equal(es, ew[lo:hi])
 
 
+def test_fused_mc_chain_kernel_lane_counts_are_bitwise_equal(vms, monkeypatch):
+    """C4a kernel (mc_chain.cu): 1, 2 or 4 lanes per chain walk the same four hidden-unit streams -- identical states,
+    energies, log-probability and decision traces (hidden = 50: zero-row padding to a multiple of 4)."""
+    v = vms
+    P = ovae.init_vae(13, prior='normal', hidden=50)
+    model = vae_from_oracle(v, P)
+    B, n_steps = 1500, 10
+    x0 = np.random.default_rng(6).normal(size=(B, 6)).astype(np.float32)
+    res = {}
+    for tpc in ('1', '2', '4'):
+        monkeypatch.setenv('VMS_MC_TPC', tpc)
+        mc = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=12)
+        x, e = mc.run_fused(x0, n_steps=n_steps, trace=True)
+        res[tpc] = (x, e, mc._last_trace, mc._num_acc)
+    for tpc in ('2', '4'):
+        assert np.array_equal(res[tpc][0], res['1'][0]) and np.array_equal(res[tpc][1], res['1'][1])
+        for key in ('acc', 'fwd', 'rev', 'e_new', 'log_u'):
+            assert np.array_equal(res[tpc][2][key], res['1'][2][key]), (tpc, key)
+        assert res[tpc][3] == res['1'][3]
+    assert 0 < res['1'][3] < B * n_steps
+
+
 def test_fused_mc_notebook_kernel_lane_counts_are_bitwise_equal(vms, monkeypatch):
     """The launcher picks 1 or 4 lanes per chain by the number of chains; all lane counts walk the same four unit streams,
     so states, energies and decision traces are bit-identical (a shard of a multi-GPU job equals its rows of the whole)."""

@@ -29,8 +29,7 @@ using namespace mcdev;
 
 namespace {
 
-constexpr int CT = 128;   // threads per CTA = 32 chains
-constexpr int TPC = 4;    // lanes per chain
+constexpr int CT = 128;   // threads per CTA
 constexpr int WROW = 28;  // floats per hidden unit in shared memory (7 x 16 bytes), see stage below
 constexpr int kMaxDx = 6, kMaxDz = 2;  // compile-time register arrays (the C4a shape: dx = 6, dz = 2)
 
@@ -63,46 +62,78 @@ struct ChainParams {
 //   pe [2 dz] += relu(xe W0e + b0e)_j W1e[j, :],   pd [2 dx] += relu(zd W0d + b0d)_j W1d[j, :]
 // shared-memory row of hidden unit j (WROW floats): W0e[0..5][j] | b0e[j] | W1e[j][0..3] | W0d[0..1][j] | b0d[j] |
 // W1d[j][0..11] | pad  (dx = 6, dz = 2)
-__device__ __forceinline__ void mlp_pair(const float* __restrict__ wsm, int H, int sub, const float (&xe)[kMaxDx],
-                                         const float (&zd)[kMaxDz], float (&pe)[2 * kMaxDz], float (&pd)[2 * kMaxDx]) {
-#pragma unroll
-  for (int n = 0; n < 2 * kMaxDz; ++n) pe[n] = 0.f;
-#pragma unroll
-  for (int n = 0; n < 2 * kMaxDx; ++n) pd[n] = 0.f;
-#pragma unroll 2
-  for (int j = sub; j < H; j += TPC) {
-    const float4* row = reinterpret_cast<const float4*>(wsm + j * WROW);
-    const float4 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4], f = row[5], g = row[6];
-    // encoder hidden unit: (sum_i x_i W0[i][j]) + b0[j]
-    float he = 0.f;
-    he = fmaf(xe[0], a.x, he); he = fmaf(xe[1], a.y, he); he = fmaf(xe[2], a.z, he);
-    he = fmaf(xe[3], a.w, he); he = fmaf(xe[4], b.x, he); he = fmaf(xe[5], b.y, he);
-    he = fmaxf(he + b.z, 0.f);
-    pe[0] = fmaf(he, b.w, pe[0]); pe[1] = fmaf(he, c.x, pe[1]); pe[2] = fmaf(he, c.y, pe[2]); pe[3] = fmaf(he, c.z, pe[3]);
-    // decoder hidden unit
-    float hd = 0.f;
-    hd = fmaf(zd[0], c.w, hd); hd = fmaf(zd[1], d.x, hd);
-    hd = fmaxf(hd + d.y, 0.f);
-    pd[0] = fmaf(hd, d.z, pd[0]); pd[1] = fmaf(hd, d.w, pd[1]);
-    pd[2] = fmaf(hd, e.x, pd[2]); pd[3] = fmaf(hd, e.y, pd[3]); pd[4] = fmaf(hd, e.z, pd[4]); pd[5] = fmaf(hd, e.w, pd[5]);
-    pd[6] = fmaf(hd, f.x, pd[6]); pd[7] = fmaf(hd, f.y, pd[7]); pd[8] = fmaf(hd, f.z, pd[8]); pd[9] = fmaf(hd, f.w, pd[9]);
-    pd[10] = fmaf(hd, g.x, pd[10]); pd[11] = fmaf(hd, g.y, pd[11]);
+// The hidden units are walked as FOUR interleaved streams (units j = s, s + 4, ...), each summed in ascending j, and the
+// four partial sums meet as (s0 + s1) + (s2 + s3).  A chain is owned by TPC lanes (4, 2 or 1), each taking 4 / TPC streams:
+// the summation order, hence every bit of every result and every decision, is the same for every TPC, so the launcher picks
+// the lane count by the number of chains (one lane per chain when the chains alone fill the GPU: no replicated scalar work
+// and a quarter of the shared-memory traffic; four lanes when chains are scarce, e.g. one shard of an 8-GPU job).
+template <int TPC>
+__device__ __forceinline__ float combine(const float (&a)[4 / TPC]) {
+  if constexpr (TPC == 4) {
+    return quad_sum(a[0]);
+  } else if constexpr (TPC == 2) {
+    const float t0 = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+    const float t1 = a[1] + __shfl_xor_sync(0xffffffffu, a[1], 1);
+    return t0 + t1;
+  } else {
+    return (a[0] + a[1]) + (a[2] + a[3]);
   }
-#pragma unroll
-  for (int n = 0; n < 2 * kMaxDz; ++n) pe[n] = quad_sum(pe[n]);
-#pragma unroll
-  for (int n = 0; n < 2 * kMaxDx; ++n) pd[n] = quad_sum(pd[n]);
 }
 
+template <int TPC>
+__device__ __forceinline__ void mlp_pair(const float* __restrict__ wsm, int Hp, int sub, const float (&xe)[kMaxDx],
+                                         const float (&zd)[kMaxDz], float (&pe)[2 * kMaxDz], float (&pd)[2 * kMaxDx]) {
+  constexpr int NS = 4 / TPC;
+  float ae[2 * kMaxDz][NS], ad[2 * kMaxDx][NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+#pragma unroll
+    for (int n = 0; n < 2 * kMaxDz; ++n) ae[n][q] = 0.f;
+#pragma unroll
+    for (int n = 0; n < 2 * kMaxDx; ++n) ad[n][q] = 0.f;
+  }
+#pragma unroll 2
+  for (int j0 = 0; j0 < Hp; j0 += 4) {  // Hp: hidden units padded with zero rows to a multiple of 4 (a zero row adds +0)
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const float4* row = reinterpret_cast<const float4*>(wsm + (j0 + sub + TPC * q) * WROW);
+      const float4 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4], f = row[5], g = row[6];
+      // encoder hidden unit: (sum_i x_i W0[i][j]) + b0[j]
+      float he = 0.f;
+      he = fmaf(xe[0], a.x, he); he = fmaf(xe[1], a.y, he); he = fmaf(xe[2], a.z, he);
+      he = fmaf(xe[3], a.w, he); he = fmaf(xe[4], b.x, he); he = fmaf(xe[5], b.y, he);
+      he = fmaxf(he + b.z, 0.f);
+      ae[0][q] = fmaf(he, b.w, ae[0][q]); ae[1][q] = fmaf(he, c.x, ae[1][q]);
+      ae[2][q] = fmaf(he, c.y, ae[2][q]); ae[3][q] = fmaf(he, c.z, ae[3][q]);
+      // decoder hidden unit
+      float hd = 0.f;
+      hd = fmaf(zd[0], c.w, hd); hd = fmaf(zd[1], d.x, hd);
+      hd = fmaxf(hd + d.y, 0.f);
+      ad[0][q] = fmaf(hd, d.z, ad[0][q]); ad[1][q] = fmaf(hd, d.w, ad[1][q]);
+      ad[2][q] = fmaf(hd, e.x, ad[2][q]); ad[3][q] = fmaf(hd, e.y, ad[3][q]);
+      ad[4][q] = fmaf(hd, e.z, ad[4][q]); ad[5][q] = fmaf(hd, e.w, ad[5][q]);
+      ad[6][q] = fmaf(hd, f.x, ad[6][q]); ad[7][q] = fmaf(hd, f.y, ad[7][q]);
+      ad[8][q] = fmaf(hd, f.z, ad[8][q]); ad[9][q] = fmaf(hd, f.w, ad[9][q]);
+      ad[10][q] = fmaf(hd, g.x, ad[10][q]); ad[11][q] = fmaf(hd, g.y, ad[11][q]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 2 * kMaxDz; ++n) pe[n] = combine<TPC>(ae[n]);
+#pragma unroll
+  for (int n = 0; n < 2 * kMaxDx; ++n) pd[n] = combine<TPC>(ad[n]);
+}
+
+template <int TPC>
 __global__ void __launch_bounds__(CT) mc_chain_kernel(const ChainParams p) {
-  extern __shared__ __align__(16) float wsm[];  // [H][WROW] + enc b1 [4] + dec b1 [12]
+  extern __shared__ __align__(16) float wsm[];  // [Hp][WROW] + enc b1 [4] + dec b1 [12]
   const int tid = threadIdx.x;
-  const int H = p.hidden;
+  const int H = p.hidden, Hp = (H + 3) & ~3;
   constexpr int dx = kMaxDx, dz = kMaxDz, nn = 2 * kMaxDz + kMaxDx;
-  for (int e = tid; e < H * WROW; e += CT) {
+  for (int e = tid; e < Hp * WROW; e += CT) {
     const int j = e / WROW, c = e - j * WROW;
     float v = 0.f;
-    if (c < 6) v = __ldg(p.theta + p.enc0W + c * H + j);
+    if (j >= H) v = 0.f;
+    else if (c < 6) v = __ldg(p.theta + p.enc0W + c * H + j);
     else if (c == 6) v = __ldg(p.theta + p.enc0b + j);
     else if (c < 11) v = __ldg(p.theta + p.enc1W + j * 4 + (c - 7));
     else if (c < 13) v = __ldg(p.theta + p.dec0W + (c - 11) * H + j);
@@ -110,13 +141,13 @@ __global__ void __launch_bounds__(CT) mc_chain_kernel(const ChainParams p) {
     else if (c < 26) v = __ldg(p.theta + p.dec1W + j * 12 + (c - 14));
     wsm[e] = v;
   }
-  float* b1e = wsm + H * WROW;
+  float* b1e = wsm + Hp * WROW;
   float* b1d = b1e + 4;
   if (tid < 4) b1e[tid] = __ldg(p.theta + p.enc1b + tid);
   if (tid < 12) b1d[tid] = __ldg(p.theta + p.dec1b + tid);
   __syncthreads();
 
-  const int64_t chain = (int64_t)blockIdx.x * (CT / TPC) + (tid / TPC);
+  const int64_t chain = ((int64_t)blockIdx.x * CT + tid) / TPC;
   const int sub = tid & (TPC - 1);
   const bool live = chain < p.B;
   const int64_t cc = live ? chain : p.B - 1;  // idle lanes shadow the last chain (full-warp shuffles), writes predicated off
@@ -163,7 +194,7 @@ __global__ void __launch_bounds__(CT) mc_chain_kernel(const ChainParams p) {
     for (int d = 0; d < dz; ++d) z2[d] = nz[dz + d];
     // ---- encoder(x1) || decoder(z2)
     float pe1[2 * dz], pd2[2 * dx];
-    mlp_pair(wsm, H, sub, x1, z2, pe1, pd2);
+    mlp_pair<TPC>(wsm, Hp, sub, x1, z2, pe1, pd2);
     // ---- samples z1, x2 and the forward log-probabilities (per-dof terms summed in dof order)
     float z1[dz], x2[dx];
     float lq1 = 0.f, lz1 = 0.f, lz2 = 0.f, lx2 = 0.f;
@@ -186,7 +217,7 @@ __global__ void __launch_bounds__(CT) mc_chain_kernel(const ChainParams p) {
     }
     // ---- encoder(x2) || decoder(z1)
     float pe2[2 * dz], pd1[2 * dx];
-    mlp_pair(wsm, H, sub, x2, z1, pe2, pd1);
+    mlp_pair<TPC>(wsm, Hp, sub, x2, z1, pe2, pd1);
     float lq2 = 0.f, lx1 = 0.f;
 #pragma unroll
     for (int d = 0; d < dz; ++d) lq2 += normal_lp(z2[d], pe2[d] + b1e[d], softplus_tf(pe2[dz + d] + b1e[dz + d]));
@@ -274,11 +305,26 @@ vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x
   p.B = B; p.n_steps = n_steps; p.theta = theta; p.x = x; p.E = E; p.energies_valid = energies_valid;
   p.noise = noise; p.seed = seed; p.step0 = step0; p.log_u = log_u; p.means = means; p.n_acc = n_acc;
   p.acc_trace = acc_trace; p.fwd_trace = fwd_trace; p.rev_trace = rev_trace; p.e_new_trace = e_new_trace;
-  const size_t smem = (size_t)(hidden * WROW + 16) * sizeof(float);
+  const size_t smem = (size_t)(((hidden + 3) & ~3) * WROW + 16) * sizeof(float);
   VMS_REQUIRE(smem <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "mc_chain: hidden too large for shared memory");
-  VMS_CUDA(cudaFuncSetAttribute(mc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)((B + CT / TPC - 1) / (CT / TPC));
-  mc_chain_kernel<<<grid, CT, smem, st>>>(p);
+  // lanes per chain by the number of chains (identical results for every choice, see `combine`)
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  int tpc = B >= (int64_t)sms * 110 ? 1 : (B >= (int64_t)sms * 40 ? 2 : 4);
+  if (const char* e = getenv("VMS_MC_TPC")) {  // cross-checks: force a lane count
+    const int t = atoi(e);
+    if (t == 1 || t == 2 || t == 4) tpc = t;
+  }
+  const unsigned grid = (unsigned)((B * tpc + CT - 1) / CT);
+#define VMS_CHAIN_LAUNCH(T)                                                                                      \
+  do {                                                                                                           \
+    VMS_CUDA(cudaFuncSetAttribute(mc_chain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mc_chain_kernel<T><<<grid, CT, smem, st>>>(p);                                                              \
+  } while (0)
+  if (tpc == 1) VMS_CHAIN_LAUNCH(1);
+  else if (tpc == 2) VMS_CHAIN_LAUNCH(2);
+  else VMS_CHAIN_LAUNCH(4);
+#undef VMS_CHAIN_LAUNCH
   VMS_LAUNCH_CHECK("mc_chain_kernel");
   return VMS_OK;
 }

@@ -290,8 +290,8 @@ __device__ __noinline__ float gmm_energy_cold(const float* __restrict__ g, int n
   return gmm_energy(g, n, x0, x1);
 }
 
-template <int TPC, int H0P, int H2P>
-__global__ void __launch_bounds__(CT) mc_nb_kernel(const NbParams p) {
+template <int TPC, int H0P, int H2P, int MINB>
+__global__ void __launch_bounds__(CT, MINB) mc_nb_kernel(const NbParams p) {
   extern __shared__ __align__(16) float sm[];
   const vms_mc_nb_model& m = p.m;
   const Layout L = make_layout(m, H0P, H2P);
@@ -616,20 +616,28 @@ vms_status vms_mc_nb_run(const vms_mc_nb_model* model, float* x, float* E, int e
     if (t == 1 || t == 2 || t == 4) tpc = t;
   }
   const unsigned grid = (unsigned)((B * tpc + CT - 1) / CT);
-#define VMS_NB_LAUNCH(T, H)                                                                                        \
-  do {                                                                                                             \
-    VMS_CUDA(cudaFuncSetAttribute(mc_nb_kernel<T, H, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    mc_nb_kernel<T, H, H><<<grid, CT, smem, st>>>(p);                                                              \
+  int minb = 2;
+  if (const char* e = getenv("VMS_NB_OCC")) minb = atoi(e);  // development aid: register budget of the one-lane kernel
+#define VMS_NB_LAUNCH(T, H, M)                                                                                        \
+  do {                                                                                                                \
+    VMS_CUDA(cudaFuncSetAttribute(mc_nb_kernel<T, H, H, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mc_nb_kernel<T, H, H, M><<<grid, CT, smem, st>>>(p);                                                              \
   } while (0)
-#define VMS_NB_SHAPE(T)                 \
-  do {                                  \
-    if (HP == 10) VMS_NB_LAUNCH(T, 10); \
-    else if (HP == 12) VMS_NB_LAUNCH(T, 12); \
-    else VMS_NB_LAUNCH(T, 16);          \
+#define VMS_NB_SHAPE(T, M)                     \
+  do {                                         \
+    if (HP == 10) VMS_NB_LAUNCH(T, 10, M);     \
+    else if (HP == 12) VMS_NB_LAUNCH(T, 12, M); \
+    else VMS_NB_LAUNCH(T, 16, M);              \
   } while (0)
-  if (tpc == 1) VMS_NB_SHAPE(1);
-  else if (tpc == 2) VMS_NB_SHAPE(2);
-  else VMS_NB_SHAPE(4);
+  if (tpc == 1) {
+    if (minb == 3) VMS_NB_SHAPE(1, 3);
+    else if (minb == 4) VMS_NB_SHAPE(1, 4);
+    else VMS_NB_SHAPE(1, 2);
+  } else if (tpc == 2) {
+    VMS_NB_SHAPE(2, 1);
+  } else {
+    VMS_NB_SHAPE(4, 1);
+  }
 #undef VMS_NB_SHAPE
 #undef VMS_NB_LAUNCH
   VMS_LAUNCH_CHECK("mc_nb_kernel");
