@@ -1,8 +1,8 @@
-// mc_chain.cu -- the production fused MC kernel for the C4a shape (dx = 6, dz = 2): four lanes per chain, chain state in
+// mc_chain.cu -- the production fused MC kernel for the C4a shape (dx = 6, dz = 2): a few lanes per chain, chain state in
 // registers.  mc_fused_kernel (mc_fused.cu: 32-chain tiles, tile GEMMs) serves every other dx, dz <= 8 and stays
 // selectable with VMS_MC_KERNEL=tile as an on-device cross-check.  Measured on a B200 (65,536 chains x 100 steps):
-// 810 M proposals/s = 15.6 TFLOP/s against 417 M of the tile kernel; bit-exact against the goldens of the reference's own
-// mcmc.py (tests/test_gpu_models.py).
+// 1,270 M proposals/s = 24.4 TFLOP/s with two lanes per chain (799 M with four, 417 M for the tile kernel); bit-exact
+// against the goldens of the reference's own mcmc.py (tests/test_gpu_models.py).
 //
 // Same contract as mc_fused.cu (mcmc.py:68-130 `MCMC.single_step` and the loop of `MCMC.run` :133-159 for the
 // Gaussian-VAE family of tests/test_mcmc.py:14-26): n_steps VAE-proposal MC steps of B chains in one launch, noise from
@@ -12,12 +12,13 @@
 // Why a second formulation.  mc_fused_kernel runs a 32-chain tile through tile-GEMM phases separated by CTA barriers
 // (6 per step) and reaches 8 TFLOP/s (ncu: issue-active 55 %, barrier 1.7 stalled warps per issue).  The layers are
 // thin (contractions of 6 and 2, outputs of 4 and 12): mlp_stream.cu's "thread per row, weights as 16-byte shared-memory
-// broadcasts" forward reaches 19-21 TFLOP/s on the same shapes.  Here FOUR lanes own a chain for all its steps: every
-// lane holds the chain state in registers, takes every fourth hidden unit of the two MLP evaluations that run side by
-// side (encoder(x1) with decoder(z2), then decoder(z1) with encoder(x2)), and the 16 partial head outputs meet in a
-// two-step butterfly.  No shared-memory activations, no CTA barrier inside a step; per step a chain reads its log u
-// (8 bytes).  Four lanes per chain for EVERY batch size: the summation order, hence every decision, is independent of
-// the number of chains per GPU.
+// broadcasts" forward reaches 19-21 TFLOP/s on the same shapes.  Here the lanes that own a chain keep its state in
+// registers for all its steps and split the hidden units of the two MLP evaluations that run side by side (encoder(x1)
+// with decoder(z2), then decoder(z1) with encoder(x2)) as FOUR interleaved unit streams whose partial head outputs meet as
+// (s0 + s1) + (s2 + s3) -- in registers or through a butterfly, depending on the lane count (see `combine`).  No
+// shared-memory activations, no CTA barrier inside a step; per step a chain reads its log u (8 bytes).  The four streams
+// are the same for EVERY lane count and batch size: the summation order, hence every decision, is independent of the
+// number of chains per GPU and of how many lanes the launcher gives a chain.
 #include "common.cuh"
 #include "mc_rng.cuh"
 #include <math.h>
@@ -123,8 +124,8 @@ __device__ __forceinline__ void mlp_pair(const float* __restrict__ wsm, int Hp, 
   for (int n = 0; n < 2 * kMaxDx; ++n) pd[n] = combine<TPC>(ad[n]);
 }
 
-template <int TPC>
-__global__ void __launch_bounds__(CT) mc_chain_kernel(const ChainParams p) {
+template <int TPC, int MINB>
+__global__ void __launch_bounds__(CT, MINB) mc_chain_kernel(const ChainParams p) {
   extern __shared__ __align__(16) float wsm[];  // [Hp][WROW] + enc b1 [4] + dec b1 [12]
   const int tid = threadIdx.x;
   const int H = p.hidden, Hp = (H + 3) & ~3;
@@ -310,16 +311,17 @@ vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x
   // lanes per chain by the number of chains (identical results for every choice, see `combine`)
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  int tpc = B >= (int64_t)sms * 110 ? 1 : (B >= (int64_t)sms * 40 ? 2 : 4);
+  // (B200, 65,536 chains x 100 steps: 4 lanes 799 M proposals/s, 2 lanes 1,270 M, 1 lane 1,241 M at 128 registers)
+  int tpc = B >= (int64_t)sms * 40 ? 2 : 4;
   if (const char* e = getenv("VMS_MC_TPC")) {  // cross-checks: force a lane count
     const int t = atoi(e);
     if (t == 1 || t == 2 || t == 4) tpc = t;
   }
   const unsigned grid = (unsigned)((B * tpc + CT - 1) / CT);
-#define VMS_CHAIN_LAUNCH(T)                                                                                      \
-  do {                                                                                                           \
-    VMS_CUDA(cudaFuncSetAttribute(mc_chain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    mc_chain_kernel<T><<<grid, CT, smem, st>>>(p);                                                              \
+#define VMS_CHAIN_LAUNCH(T)                                                                                         \
+  do {                                                                                                              \
+    VMS_CUDA(cudaFuncSetAttribute(mc_chain_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mc_chain_kernel<T, 4><<<grid, CT, smem, st>>>(p);                                                              \
   } while (0)
   if (tpc == 1) VMS_CHAIN_LAUNCH(1);
   else if (tpc == 2) VMS_CHAIN_LAUNCH(2);
