@@ -50,6 +50,24 @@ int max_smem_optin();
 
 namespace vms {
 
+// NVTX ranges around the C-ABI entry points of the hot path (timeline annotation for Nsight Systems / Compute, SURVEY 5
+// "tracing"): active when VMS_NVTX=1 is set in the environment, otherwise one predictable branch.
+bool nvtx_enabled();
+void nvtx_push(const char* name);
+void nvtx_pop();
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) : on(nvtx_enabled()) {
+    if (on) nvtx_push(name);
+  }
+  ~NvtxRange() {
+    if (on) nvtx_pop();
+  }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define VMS_RANGE(name) vms::NvtxRange _vms_range(name)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -618,6 +618,7 @@ extern "C" vms_status vms_dist_select(const float* coords, const int64_t* row_sp
                                       const float* ref, const float* box, int box_per_row, float cutoff_sq, int k,
                                       const float* info, int P, float* out_xyz, float* out_info, int32_t* out_idx,
                                       vms_stream stream) {
+  VMS_RANGE("vms_dist_select");
   VMS_REQUIRE(B >= 0 && N >= 0, VMS_ERR_SHAPE, "dist_select: bad shape");
   VMS_REQUIRE(k >= 1 && k <= kCap, VMS_ERR_INVALID_ARG, "dist_select: max_included must be in [1, %d], got %d", kCap, k);
   VMS_REQUIRE(N < (1LL << 31) && B < (1LL << 31), VMS_ERR_SHAPE, "dist_select: too many particles / rows");

@@ -571,6 +571,7 @@ int vms_elbo_plan_is_fused(vms_elbo_plan pl) { return pl && pl->fused && (pl->mo
 
 vms_status vms_elbo_forward(vms_elbo_plan pl, const float* theta, const float* x, const float* eps, int64_t B, float* z,
                             float* logq, float* logpz, float* logpx, float* scalars, vms_stream stream) {
+  VMS_RANGE("vms_elbo_forward");
   vms_status s = check_call(pl, theta, x, eps, B);
   if (s) return s;
   cudaStream_t st = as_stream(stream);
@@ -591,6 +592,7 @@ vms_status vms_elbo_forward(vms_elbo_plan pl, const float* theta, const float* x
 
 vms_status vms_elbo_forward_backward(vms_elbo_plan pl, const float* theta, const float* x, const float* eps, int64_t B,
                                      float* grad, float* scalars, vms_stream stream) {
+  VMS_RANGE("vms_elbo_forward_backward");
   vms_status s = check_call(pl, theta, x, eps, B);
   if (s) return s;
   VMS_REQUIRE(grad, VMS_ERR_INVALID_ARG, "elbo_forward_backward: NULL grad");
@@ -612,6 +614,7 @@ vms_status vms_elbo_forward_backward(vms_elbo_plan pl, const float* theta, const
 vms_status vms_elbo_train_step(vms_elbo_plan pl, float* theta, const float* x, const float* eps, int64_t B, float* grad,
                                float* scalars, float* m, float* v, int64_t t, double lr, double beta1, double beta2,
                                double eps_adam, vms_stream stream) {
+  VMS_RANGE("vms_elbo_train_step");
   vms_status s = check_call(pl, theta, x, eps, B);
   if (s) return s;
   VMS_REQUIRE(grad && m && v && t >= 1, VMS_ERR_INVALID_ARG, "elbo_train_step: NULL grad / m / v or t < 1");

@@ -364,6 +364,7 @@ vms_status vms_mc_run(vms_mc_plan pl, const float* theta, float* x, double* E, i
                       unsigned long long seed, unsigned long long step0, const double* log_u, const double* means,
                       int64_t B, int n_steps, unsigned long long* n_acc, uint8_t* acc_trace, float* fwd_trace,
                       float* rev_trace, double* e_new_trace, vms_stream stream) {
+  VMS_RANGE("vms_mc_run");
   VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "mc_run: NULL plan");
   VMS_REQUIRE(theta && x && E && log_u && means && n_acc, VMS_ERR_INVALID_ARG, "mc_run: NULL pointer");
   VMS_REQUIRE(B >= 0 && n_steps >= 0, VMS_ERR_SHAPE, "mc_run: negative size");
@@ -399,6 +400,7 @@ vms_status vms_mc_run_pcg64(vms_mc_plan pl, const float* theta, float* x, double
                             const double* means, int64_t B, int n_steps, unsigned long long* n_acc,
                             unsigned long long* n_uncertain, uint8_t* acc_trace, float* fwd_trace, float* rev_trace,
                             double* e_new_trace, double* log_u_trace, vms_stream stream) {
+  VMS_RANGE("vms_mc_run_pcg64");
   VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "mc_run_pcg64: NULL plan");
   VMS_REQUIRE(theta && x && E && rng && means && n_acc && n_uncertain, VMS_ERR_INVALID_ARG, "mc_run_pcg64: NULL pointer");
   VMS_REQUIRE(B >= 0 && n_steps >= 0 && rng->chain0 >= 0, VMS_ERR_SHAPE, "mc_run_pcg64: negative size");

@@ -573,6 +573,7 @@ vms_status vms_mc_nb_run(const vms_mc_nb_model* model, float* x, float* E, int e
                          int64_t chain0, int64_t B, int n_steps, unsigned long long* n_acc, unsigned long long* n_uncertain,
                          uint8_t* acc_trace, float* fwd_trace, float* rev_trace, float* e_new_trace, double* log_u_trace,
                          vms_stream stream) {
+  VMS_RANGE("vms_mc_nb_run");
   VMS_REQUIRE(model != nullptr, VMS_ERR_INVALID_ARG, "mc_nb_run: NULL model");
   VMS_REQUIRE(vms_mc_nb_supported(model), VMS_ERR_UNSUPPORTED,
               "mc_nb_run: built for the MC notebook's family (dx = 2, dz = 1, MADE hidden [<=16, <=512, <=16])");

@@ -152,6 +152,7 @@ vms_status vms_ipc_close_handle(void* device_ptr) {
 vms_status vms_peer_allreduce_adam(int world, int rank, void* const* peer_bases, int64_t n_params, unsigned long long step,
                                    float grad_scale, float* theta, float* m, float* v, int64_t t, double lr, double beta1,
                                    double beta2, double eps, float* grad_out, vms_stream stream) {
+  VMS_RANGE("vms_peer_allreduce_adam");
   VMS_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, VMS_ERR_INVALID_ARG,
               "peer_allreduce_adam: world must be in [1, %d] and 0 <= rank < world", kMaxPeers);
   VMS_REQUIRE(peer_bases && theta && m && v && n_params >= 1 && step >= 1 && t >= 1, VMS_ERR_INVALID_ARG,

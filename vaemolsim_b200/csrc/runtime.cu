@@ -2,7 +2,9 @@
 // (ctypes + NumPy) needs no other CUDA binding.  No reference counterpart: TensorFlow's runtime did this.
 #include "common.cuh"
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
+#include <nvtx3/nvToolsExt.h>
 
 namespace vms {
 static thread_local char g_err[512] = "";
@@ -15,6 +17,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+bool nvtx_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VMS_NVTX");
+    return e && e[0] && e[0] != '0';
+  }();
+  return on;
+}
+void nvtx_push(const char* name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
 
 static int g_sm[64];
 static int g_smem[64];
