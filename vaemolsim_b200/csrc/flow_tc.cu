@@ -47,7 +47,8 @@ namespace vms {
 namespace {
 
 constexpr int FM = 64;               // rows per tile (UMMA M of the row-major products)
-constexpr int FT = 512;              // threads per CTA: one octet per row in the spline phase
+constexpr int FT = 512;              // worker threads per CTA: one octet per row in the spline phase
+constexpr int FTA = FT + 32;         // + the warp that issues the tensor-core instructions
 constexpr unsigned CSB = (FM + 1) * 16;  // bytes per chunk column of an A-type tile (64 rows + one pad slot)
 constexpr int kMaxC = 4;             // conditioner columns supported
 
@@ -140,6 +141,24 @@ __device__ __forceinline__ void tc_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 }
 
+// The 16 worker warps synchronise among themselves on named barrier 1; the MMA warp never takes part, so a worker never
+// waits for the issue of tensor-core instructions, only (at an mbarrier) for their completion.
+__device__ __forceinline__ void worker_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  asm volatile("bar.sync 1, %0;\n" ::"n"(FT) : "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+// workers -> MMA warp: "the operands of the next product are in shared memory / its TMEM target is free"
+__device__ __forceinline__ void operands_ready(int id) {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "n"(FTA) : "memory");
+}
+__device__ __forceinline__ void wait_operands(int id) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "n"(FTA) : "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+
 // instruction descriptor: D = F32, A = B = BF16, optional MN-major operands, N >> 3, M >> 4
 __device__ __forceinline__ unsigned idesc_bf16(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)a_mn << 15) | ((unsigned)b_mn << 16) |
@@ -181,13 +200,18 @@ __device__ __forceinline__ void issue_product(unsigned acc, unsigned a0, unsigne
   for (int ks = 0; ks < n_k; ++ks, ka += sa, kb += sb) mma_bf16(acc, da1 + ka, db1 + kb, idesc, 1u);
 }
 
-// Software pipeline (per CTA, tiles t0, t1, ... of 64 rows; hid / inputs / the raw accumulator are double-buffered):
-//   forward :  [inputs + hid of tile i+1 | tensor core: raw(i)]  ->  issue raw(i+1)  ->  wait raw(i)  ->  TMEM -> smem,
-//              spline(i)                                          (the tensor core is never waited for in steady state)
-//   backward:  wait raw(i) -> TMEM -> smem, spline reverse mode(i) -> issue d hid(i), d hW(i)
-//              -> [inputs + hid of tile i+1 | tensor core] -> issue raw(i+1) -> wait d hid / d hW(i) -> epilogues(i)
+// Software pipeline (per CTA, tiles t0, t1, ... of 64 rows; hid / inputs / the raw accumulator are double-buffered).
+// 16 worker warps + ONE MMA warp: the workers signal "operands ready" on a named barrier they only ARRIVE at, the MMA warp
+// waits there, issues the products and commits them to an mbarrier the workers wait on when they need the result
+// (round 1 had worker thread 0 issue: 42-102 MMAs per tile queue up behind the tensor pipe, and the other 511 threads
+// waited for that thread at the next CTA barrier -- ncu: 22 % of all stall samples at that barrier).
+//   forward  workers:  inputs + hid of tile i+1 -> ready(hid) | wait raw(i) -> TMEM -> smem -> spline(i)
+//            MMA warp: wait ready(hid) -> raw(i+1)
+//   backward workers:  wait raw(i) -> TMEM -> smem, spline reverse mode(i) -> ready(g_raw) -> inputs + hid of tile i+1
+//                      -> ready(hid) -> wait d hid / d hW(i) -> epilogues(i)
+//            MMA warp: wait ready(g_raw) -> d hid(i), d hW(i);  wait ready(hid) -> raw(i+1)
 template <int RP, bool BWD>
-__global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(FTA, 1) flow_tc_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smb[];
   __shared__ __align__(8) unsigned long long mbar[3];  // [0], [1]: raw of buffer 0 / 1;  [2]: d hid + d hW
   __shared__ unsigned tmem_base_s;
@@ -222,9 +246,10 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
     for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar[i])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  const bool worker = tid < FT;  // warp 16 issues the tensor-core instructions and does nothing else
   // heads matrix with the bias as row H (the ones column of hid multiplies it), split, zero padded to [Hp, RP];
   // four independent loads in flight per thread
-  for (int e0 = 0; e0 < Hp * RP; e0 += 4 * FT) {
+  for (int e0 = 0; worker && e0 < Hp * RP; e0 += 4 * FT) {
     float w[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -250,13 +275,13 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
       }
     }
   }
-  for (int e = tid; e < 4 * Hp; e += FT) {
+  for (int e = tid; worker && e < 4 * Hp; e += FT) {
     const int c = e / Hp, j = e - c * Hp;
     s_w1[e] = (c < cin && j < H) ? __ldg(a.d1W + (size_t)c * H + j) : 0.f;
   }
-  for (int j = tid; j < Hp; j += FT) s_b1[j] = j < H ? __ldg(a.d1b + j) : 0.f;
+  for (int j = tid; worker && j < Hp; j += FT) s_b1[j] = j < H ? __ldg(a.d1b + j) : 0.f;
   if (BWD)
-    for (unsigned e = tid; e < 3 * graw_sz / 4; e += FT) reinterpret_cast<unsigned*>(graw)[e] = 0u;
+    for (unsigned e = tid; worker && e < 3 * graw_sz / 4; e += FT) reinterpret_cast<unsigned*>(graw)[e] = 0u;
 
   const int64_t n_tiles = (a.B + FM - 1) / FM;
   // ---- S1: a tile's inputs.  Threads 0..63 load their row of tile t into registers (pre) one tile ahead of its use and
@@ -339,14 +364,43 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
     for (int c = 0; c < kMaxC; ++c) acc_w1[c] = 0.f;
   }
 
+  // named barriers: 1 = the workers among themselves; 2, 3 = "hid of tile it is built" (alternating: a worker may be one
+  // tile ahead of the MMA warp in the forward kernel); 4 = "g_raw of this tile is written" (backward)
+  if (!worker) {
+    // ---- the MMA warp: same tile loop, only the products
+    int it = 0;
+    wait_operands(2);
+    if (lane == 0) issue_raw(0);
+#pragma unroll 1
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const bool has_next = tile + gridDim.x < n_tiles;
+      if (BWD) {
+        // d hid = g_raw @ hW^T (M = 64, N = Hp, K = RP)  and  d [hW; hb] = [hid, 1]^T @ g_raw (M = 128, N = RP, K = 64)
+        wait_operands(4);
+        if (lane == 0) {
+          issue_product(tD2, graw_a, graw_sz, 2u * CSB, CSB, 128, w_a, w_sz, 256u, 128, w_cs, RP / 16, id2);
+          issue_product(tD3, hid_a + (unsigned)b * 3u * hid_sz, hid_sz, 256u, 128, CSB, graw_a, graw_sz, 256u, 128, CSB,
+                        FM / 16, id3);
+          mma_commit(smem_u32(&mbar[2]));
+        }
+        __syncwarp();
+      }
+      if (has_next) {
+        wait_operands(2 + ((it + 1) & 1));
+        if (lane == 0) issue_raw(b ^ 1);
+        __syncwarp();
+      }
+    }
+  } else {
+  // ---- the workers
   // pipeline prologue: tile 0 of this CTA; the loads of tile 1 are in flight from here on
   load_inputs(blockIdx.x);
   put_inputs(0);
   load_inputs((int64_t)blockIdx.x + gridDim.x);
-  __syncthreads();
+  worker_sync();
   build_hid(0);
-  tc_sync();
-  if (tid == 0) issue_raw(0);
+  operands_ready(2);
 
   int it = 0;
 #pragma unroll 1
@@ -360,10 +414,9 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
       // next tile's inputs and hid while the tensor core computes this tile's raw parameters
       put_inputs(b ^ 1);
       load_inputs(next + gridDim.x);
-      __syncthreads();
+      worker_sync();
       build_hid(b ^ 1);
-      tc_sync();
-      if (tid == 0) issue_raw(b ^ 1);
+      operands_ready(2 + ((it + 1) & 1));
     }
     if (!mbar_wait_bounded(smem_u32(&mbar[b]), (unsigned)(it >> 1) & 1u)) failed = true;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -380,7 +433,7 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
         }
       }
     }
-    tc_sync();
+    worker_sync();
     // ---- S5: the spline, one octet per row
     {
       const int r = tid >> 3, j = tid & 7;
@@ -424,23 +477,17 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
       }
     }
     if (BWD) {
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      tc_sync();
-      // ---- S6: d hid = g_raw @ hW^T (M = 64, N = Hp, K = RP)  and  d [hW; hb] = [hid, 1]^T @ g_raw (M = 128, N = RP, K = 64)
-      if (tid == 0) {
-        issue_product(tD2, graw_a, graw_sz, 2u * CSB, CSB, 128, w_a, w_sz, 256u, 128, w_cs, RP / 16, id2);
-        issue_product(tD3, hid_a + (unsigned)b * 3u * hid_sz, hid_sz, 256u, 128, CSB, graw_a, graw_sz, 256u, 128, CSB,
-                      FM / 16, id3);
-        mma_commit(smem_u32(&mbar[2]));
-      }
+      // ---- S6 (MMA warp): d hid and d [hW; hb] from the g_raw tile just written
+      operands_ready(4);
       if (has_next) {
-        // next tile's inputs, hid and raw product behind this tile's gradient products
+        // next tile's inputs and hid behind this tile's gradient products; the MMA warp queues raw(i+1) after them
         put_inputs(b ^ 1);
         load_inputs(next + gridDim.x);
-        __syncthreads();
+        worker_sync();
         build_hid(b ^ 1);
-        tc_sync();
-        if (tid == 0) issue_raw(b ^ 1);
+        operands_ready(2 + ((it + 1) & 1));
+      } else {
+        worker_sync();  // every octet has read its raw parameters before S7a overwrites them
       }
       if (!mbar_wait_bounded(smem_u32(&mbar[2]), (unsigned)it & 1u)) failed = true;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -489,7 +536,7 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
           }
         }
       }
-      tc_sync();
+      worker_sync();
       // ---- S7c: d d1b / d d1W (column sums over the tile's rows: thread = (hidden unit, quarter of the rows), each
       // with its own CTA-lifetime accumulators), then the gradient wrt the conditioner columns (one octet per row) and g_nxt
       {
@@ -537,7 +584,7 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
         }
       }
     }
-    __syncthreads();  // s_raw, s_gin and the input buffers of this tile are free again
+    worker_sync();  // s_raw, s_gin and the input buffers of this tile are free again
   }
 
   if (BWD) {
@@ -550,7 +597,7 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
         float* q = red + (pq * Hp + j) * 5;
         q[0] = acc_b1; q[1] = acc_w1[0]; q[2] = acc_w1[1]; q[3] = acc_w1[2]; q[4] = acc_w1[3];
       }
-      __syncthreads();
+      worker_sync();
       if (tid < H) {
         float t[5];
 #pragma unroll
@@ -576,6 +623,7 @@ __global__ void __launch_bounds__(FT, 1) flow_tc_kernel(const __grid_constant__ 
     }
   }
   if (failed && tid == 0 && a.err) atomicExch(a.err, 1);
+  }  // workers
   tc_sync();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512u) : "memory");
 }
@@ -617,7 +665,7 @@ vms_status configure(const FlowTcArgs& a, bool bwd, KParams& p, int& RP, size_t&
 template <int RP, bool BWD>
 vms_status launch(const KParams& p, size_t smem, cudaStream_t st) {
   VMS_CUDA(cudaFuncSetAttribute(flow_tc_kernel<RP, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  flow_tc_kernel<RP, BWD><<<flow_tc_grid(p.a.B), FT, smem, st>>>(p);
+  flow_tc_kernel<RP, BWD><<<flow_tc_grid(p.a.B), FTA, smem, st>>>(p);
   VMS_LAUNCH_CHECK("flow_tc_kernel");
   return VMS_OK;
 }
