@@ -213,7 +213,7 @@ __device__ __forceinline__ void issue_product(unsigned acc, unsigned a0, unsigne
 template <int RP, bool BWD>
 __global__ void __launch_bounds__(FTA, 1) flow_tc_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smb[];
-  __shared__ __align__(8) unsigned long long mbar[3];  // [0], [1]: raw of buffer 0 / 1;  [2]: d hid + d hW
+  __shared__ __align__(8) unsigned long long mbar[4];  // [0], [1]: raw of buffer 0 / 1;  [2]: d hid;  [3]: d hW
   __shared__ unsigned tmem_base_s;
   const FlowTcArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(FTA, 1) flow_tc_kernel(const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar[i])) : "memory");
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar[i])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   const bool worker = tid < FT;  // warp 16 issues the tensor-core instructions and does nothing else
@@ -380,9 +380,10 @@ __global__ void __launch_bounds__(FTA, 1) flow_tc_kernel(const __grid_constant__
         wait_operands(4);
         if (lane == 0) {
           issue_product(tD2, graw_a, graw_sz, 2u * CSB, CSB, 128, w_a, w_sz, 256u, 128, w_cs, RP / 16, id2);
+          mma_commit(smem_u32(&mbar[2]));  // S7a starts on d hid while d hW is still in the pipe
           issue_product(tD3, hid_a + (unsigned)b * 3u * hid_sz, hid_sz, 256u, 128, CSB, graw_a, graw_sz, 256u, 128, CSB,
                         FM / 16, id3);
-          mma_commit(smem_u32(&mbar[2]));
+          mma_commit(smem_u32(&mbar[3]));
         }
         __syncwarp();
       }
@@ -523,6 +524,8 @@ __global__ void __launch_bounds__(FTA, 1) flow_tc_kernel(const __grid_constant__
         }
       }
       // ---- S7b: this tile's d [hW; hb] joins the register accumulators
+      if (!mbar_wait_bounded(smem_u32(&mbar[3]), (unsigned)it & 1u)) failed = true;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       {
         const int q = warp & 3, sub = warp >> 2;
 #pragma unroll

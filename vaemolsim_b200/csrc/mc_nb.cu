@@ -517,7 +517,7 @@ __global__ void rqs_knot_table_kernel(const float* __restrict__ raw_w, const flo
   for (int k = 0; k < K; ++k) mx = fmaxf(mx, raw[k]);
   double tot = 0.0;
   for (int k = 0; k < K; ++k) tot += (double)expf(raw[k] - mx);
-  const double c = (double)scale / tot, bm = (double)bin_min;
+  const double c = (double)scale * rqsdev::recip_pos(tot), bm = (double)bin_min;
   double E = 0.0;
   for (int k = 0; k <= K; ++k) {
     kn[k] = bm + fma(c, E, 1e-2 * (double)k);

@@ -90,6 +90,16 @@ struct Bin {
   bool found;
 };
 
+// 1 / x for a positive, normal double (a softmax denominator, 1 <= x <= bins): float32 reciprocal refined by two Newton
+// steps in float64 (relative error ~1e-16 after the second; the IEEE division it replaces costs ~30 dependent FP64
+// instructions per lane and was the top stall of the tensor-core coupling kernel, where nothing hides it).
+__device__ __forceinline__ double recip_pos(double x) {
+  double r = (double)__frcp_rn((float)x);
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
 // Softmax statistics, octet scan, knot walk over this lane's bins.  On return ew / eh hold exp(logit - max),
 // inv_tot_* = 1 / sum(exp), c* = scale / sum(exp).
 template <int BPL>
@@ -112,8 +122,8 @@ __device__ __forceinline__ Bin find_bin(float (&ew)[BPL], float (&eh)[BPL], int 
   const double iw = oct_scan(sw, j), ih = oct_scan(sh, j);
   totw = __shfl_sync(0xffffffffu, iw, kOct - 1, kOct);
   toth = __shfl_sync(0xffffffffu, ih, kOct - 1, kOct);
-  cwd = (double)scale / totw;
-  chd = (double)scale / toth;
+  cwd = (double)scale * recip_pos(totw);
+  chd = (double)scale * recip_pos(toth);
   // knots: k-th lower knot = bin_min + (scale * E_k / total + 1e-2 k), E_k = sum of exps of bins < k
   Bin b;
   b.found = false;
