@@ -90,3 +90,80 @@ def test_peer_allreduce_adam_two_gpus(tmp_path):
     res = [[ln for ln in o.splitlines() if ln.startswith('RESULT')][0].split() for o in outs]
     assert all(float(r[2]) < 2e-6 for r in res), res     # Adam on the summed gradient (float32 rounding only)
     assert res[0][3] == res[1][3], 'replicas diverged'    # bit-identical parameters on both ranks
+
+
+DP_WORKER = r'''
+import os, sys, hashlib
+import numpy as np
+sys.path.insert(0, %(root)r)
+import vaemolsim_b200 as v
+from vaemolsim_b200 import parallel
+import vaemolsim_b200._protocols as PR
+
+grp = parallel.Group()
+rank, world = grp.rank, grp.world
+d = v.dists
+
+
+def make():
+    v.set_seed(3)
+    kinds = [d.Normal] * 2 + [d.VonMises] * 2
+    dist = d.AutoregressiveBlockwise(4, kinds, conditional=True, conditional_event_shape=3,
+                                     auto_net_params={'hidden_units': [16], 'activation': 'tanh'})
+    m = v.models.MappingToDistribution(dist, mapping=v.mappings.FCDeepNN(dist.params_size(), hidden_dim=24, activation='tanh'),
+                                       name='decoder')
+    m.compile(optimizer=v.models.Adam(2e-3), loss=v.losses.LogProbLoss())
+    return m
+
+
+rng = np.random.default_rng(3)
+B = 128
+z = rng.normal(size=(B, 3)).astype(np.float32)
+x = np.concatenate([rng.normal(size=(B, 2)), rng.uniform(-3, 3, (B, 2))], axis=1).astype(np.float32)
+lo, hi = parallel.shard_rows(B, rank, world)
+model = make()
+model(z[:2])
+model.distribute(grp)
+for step in range(6):
+    model.train_on_batch(z[lo:hi], x[lo:hi])
+got = np.concatenate([w.numpy().ravel() for w in model.weights])
+# the same six steps on the whole batch in one process
+ref = make()
+ref(z[:2])
+for step in range(6):
+    ref.train_on_batch(z, x)
+want = np.concatenate([w.numpy().ravel() for w in ref.weights])
+moved = float(np.abs(want - np.concatenate([w.numpy().ravel() for w in (lambda m: (m(z[:2]), m)[1])(make()).weights])).max())
+err = float(np.abs(got - want).max())
+print('RESULT %%d %%.3e %%.3e %%s' %% (rank, err, moved, hashlib.sha1(got.tobytes()).hexdigest()), flush=True)
+grp.close()
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_data_parallel_training_of_a_tape_model_two_gpus(tmp_path):
+    """`Model.distribute(group)`: the generic (tape) training path sharded over two GPUs -- one NCCL allreduce of the flat
+    gradient per step -- against the same steps on the whole batch in one process; replicas bit-identical."""
+    import ctypes
+    from vaemolsim_b200 import _abi
+    n = ctypes.c_int(0)
+    _abi.load().vms_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip('needs 2 GPUs')
+    script = tmp_path / 'dp_worker.py'
+    script.write_text(DP_WORKER % {'root': ROOT})
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1',
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=280)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    res = [[ln for ln in o.splitlines() if ln.startswith('RESULT')][0].split() for o in outs]
+    assert all(float(r[3]) > 1e-3 for r in res), res          # the six steps moved the weights
+    assert all(float(r[2]) < 2e-5 for r in res), res          # sharded == whole batch up to float32 summation order
+    assert res[0][4] == res[1][4], 'replicas diverged'

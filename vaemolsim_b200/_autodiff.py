@@ -106,10 +106,15 @@ class Trainer(object):
     """Keras-style training of an arbitrary model of this package: `step(fn)` runs fn() under a tape (fn returns the scalar
     loss Tensor), back-propagates and applies Adam to every weight of `model.weights` that received a gradient."""
 
-    def __init__(self, model, optimizer):
+    def __init__(self, model, optimizer, group=None):
         self.model, self.opt = model, optimizer
         self.state = {}  # id(weight) -> (weight, m, v)
         self.t = 0
+        # data-parallel training of ANY model (north_star: one gradient allreduce per step): every rank runs the step on its
+        # shard of the batch, the gradients of all weights travel as ONE flat float32 buffer through an NCCL sum-allreduce
+        # on the library's stream, Adam then applies sum / world -- identical on every rank, so replicas stay in step
+        self.group = group if (group is not None and group.world > 1) else None
+        self._flat = None
 
     def step(self, fn):
         c = ctx()
@@ -118,24 +123,41 @@ class Trainer(object):
             tape.backward(loss)
         self.t += 1
         seen = set()
+        todo = []
         for w in self.model.weights:
-            if id(w) in seen or not tape.has(w):
+            if id(w) in seen or not (tape.has(w) or self.group is not None):
                 continue
             seen.add(id(w))
-            g = tape.grad(w)
+            g = tape.grad(w)  # (data-parallel: every rank exchanges every weight, a zero gradient if it received none)
             mask = getattr(w, '_grad_mask', None)
             if mask is not None:  # tfp AutoregressiveNetwork: masked kernel entries stay zero
                 c.lib.vms_mul_inplace(g.ptr, mask.ptr, g.size, c.stream)
+            todo.append((w, g))
+        scale = 1.0
+        if self.group is not None:
+            total = sum(w.size for w, _ in todo)
+            if self._flat is None or self._flat.size != total:
+                self._flat = Tensor((total, ))
+            off, flat = 0, []
+            for w, g in todo:
+                gc = g if g.contiguous else g.contig()
+                dst = Tensor(w.shape, np.float32, _ptr=self._flat.ptr + 4 * off, _base=self._flat)
+                c.lib.vms_memcpy_d2d(dst.ptr, gc.ptr, 4 * w.size, c.stream)
+                flat.append((w, dst))
+                off += w.size
+            self.group.allreduce_sum_device_(self._flat.ptr, total, c.stream)
+            todo, scale = flat, 1.0 / self.group.world
+        for w, g in todo:
             st = self.state.get(id(w))
             if st is None:
                 st = self.state[id(w)] = (w, Tensor.zeros(w.shape), Tensor.zeros(w.shape))
             o = self.opt
             if w.contiguous and g.contiguous:
-                c.lib.vms_adam_step(w.ptr, g.ptr, 1, 1.0, st[1].ptr, st[2].ptr, w.size, self.t, o.learning_rate, o.beta_1, o.beta_2,
+                c.lib.vms_adam_step(w.ptr, g.ptr, 1, scale, st[1].ptr, st[2].ptr, w.size, self.t, o.learning_rate, o.beta_1, o.beta_2,
                                     o.epsilon, c.stream)
             else:  # a weight that is a strided view of a flat buffer: update a contiguous copy and write it back
                 wc, gc = w.contig(), g.contig()
-                c.lib.vms_adam_step(wc.ptr, gc.ptr, 1, 1.0, st[1].ptr, st[2].ptr, w.size, self.t, o.learning_rate, o.beta_1,
+                c.lib.vms_adam_step(wc.ptr, gc.ptr, 1, scale, st[1].ptr, st[2].ptr, w.size, self.t, o.learning_rate, o.beta_1,
                                     o.beta_2, o.epsilon, c.stream)
                 it = 4
                 c.lib.vms_memcpy2d_d2d(w.ptr, w.ld * it, wc.ptr, wc.ld * it, w.shape[-1] * it, w.shape[0], c.stream)

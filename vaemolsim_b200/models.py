@@ -56,9 +56,18 @@ class Model(P.Layer):
         from . import _autodiff
         opt = getattr(self, 'optimizer', None) or Adam()
         tr = getattr(self, '_generic_trainer', None)
-        if tr is None or tr.opt is not opt:
-            tr = self._generic_trainer = _autodiff.Trainer(self, opt)
+        grp = getattr(self, '_dp_group', None)
+        if tr is None or tr.opt is not opt or tr.group is not (grp if (grp is not None and grp.world > 1) else None):
+            tr = self._generic_trainer = _autodiff.Trainer(self, opt, group=grp)
         return tr
+
+    def distribute(self, group):
+        """Data-parallel training over `group` (`parallel.Group`, one process per GPU): `fit` / `train_on_batch` run on this
+        rank's shard of the data and every step sums the gradients of all weights over the ranks (one NCCL allreduce) before
+        Adam, so the replicas stay identical.  Batch-normalisation layers keep per-replica batch statistics, as Keras'
+        BatchNormalization does under a mirrored strategy.  Pass None to go back to single-process training."""
+        self._dp_group = group
+        return self
 
     def _prep_xy(self, x, y):
         x = np.asarray(x.numpy() if isinstance(x, Tensor) else x, np.float32)
