@@ -252,7 +252,8 @@ class NcclComm(object):
         uid = UniqueId()
         if group.rank == 0:
             self._check(self.lib.ncclGetUniqueId(C.byref(uid)))
-        raw = group.all_gather_bytes(bytes(uid.internal) if group.rank == 0 else b'')[0]
+        # (string_at, not the c_char array's value: that one stops at the first NUL byte of the 128-byte id)
+        raw = group.all_gather_bytes(C.string_at(C.byref(uid), 128) if group.rank == 0 else b'')[0]
         uid = UniqueId()
         C.memmove(C.byref(uid), raw.ljust(128, b'\0'), 128)
         self.comm = C.c_void_p()
