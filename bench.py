@@ -644,9 +644,38 @@ def c4b_bench(v, grp, ffma_peak, reps=2):
                                 'D + 1 = 3 sampling passes + 2 log_prob passes); the kernel proves 3 of them bit-identical '
                                 'from the MADE masks and executes 2 (executed_*)',
                         'peak_kind': 'FP32 FFMA issue peak measured in this run (csrc/probe.cu)'}}
+    if grp.world > 1:
+        res['weak'] = mc_weak_record(
+            v, grp, lambda layout: v.mcmc.MCMC(model, energy, random_seed=5002, stream_layout=layout),
+            lambda m, xd, ed: m.run_nb(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed),
+            lambda a, b: gmm_start(MC_CHAINS * grp.world)[a:b], 2)
     if grp.rank == 0:
         res['cpu_baseline'], res['flips_vs_oracle'] = c4b_check_and_cpu(v, model)
     return res
+
+
+def mc_weak_record(v, grp, make_mc, run, x_all_fn, dx, reps=3):
+    """The same kernel with 65,536 chains on EVERY rank (weak scaling: 65,536 x N chains, one global PCG64 stream / noise
+    stream sharded by chain index) -- reported beside the named strong-scaling configuration when N > 1."""
+    c = v._abi.ctx()
+    n_global = MC_CHAINS * grp.world
+    lo = MC_CHAINS * grp.rank
+    mc = make_mc((lo, n_global))
+    xd = v.Tensor.from_numpy(np.ascontiguousarray(x_all_fn(lo, lo + MC_CHAINS)))
+    xd, ed = run(mc, xd, None)
+    run(mc, xd, ed)
+    ev = Events(c, reps)
+    grp.barrier()
+    c.synchronize()
+    for i in range(reps):
+        ev.record(2 * i)
+        run(mc, xd, ed)
+        ev.record(2 * i + 1)
+    c.synchronize()
+    grp.barrier()
+    ms = grp.max(sum(ev.elapsed_ms(2 * i, 2 * i + 1) for i in range(reps)))
+    return {'value': n_global * MC_STEPS * reps / (ms * 1e-3), 'unit': 'proposals/s', 'chains_global': n_global,
+            'chains_per_gpu': MC_CHAINS, 'scaling': 'weak', 'ms_per_mc_step': ms / (reps * MC_STEPS)}
 
 
 def mc_bench(v, grp, ffma_peak, reps=3):
@@ -708,6 +737,11 @@ def mc_bench(v, grp, ffma_peak, reps=3):
                         'algorithmic_flop_per_proposal': 19200,
                         'peak_kind': 'FP32 FFMA issue peak measured in this run (csrc/probe.cu)'},
            'tflops_fp32': tflops}
+    if grp.world > 1:
+        x_all = lambda a, b: np.random.default_rng(4001).standard_normal((MC_CHAINS * grp.world, 6), dtype=np.float32)[a:b]
+        res['weak'] = mc_weak_record(
+            v, grp, lambda layout: v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=4002, stream_layout=layout),
+            lambda m, xd, ed: m.run_fused(None, n_steps=MC_STEPS, configs_dev=xd, energies_dev=ed), x_all, 6)
     if grp.rank == 0:
         res['flips_vs_oracle'] = mc_flips_vs_oracle(v, model)
     return res
@@ -1056,7 +1090,8 @@ def run_b200(args, w):
         line['legs'] = legs
         # short per-leg summary (kept flat so that per-N records retain every leg's number)
         line['leg_values'] = {k: {'value': d.get('value'), 'unit': d.get('unit'), 'e2e': (d.get('e2e') or {}).get('value'),
-                                  'roofline_frac': (d.get('roofline') or {}).get('frac')}
+                                  'roofline_frac': (d.get('roofline') or {}).get('frac'),
+                                  'weak_value': (d.get('weak') or {}).get('value')}
                               for k, d in legs.items() if 'error' not in d}
         line['mc'] = legs.get('c4a_mc')
         line['large_batch'] = legs.get('c5')
