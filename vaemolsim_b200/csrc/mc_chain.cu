@@ -1,7 +1,8 @@
 // mc_chain.cu -- the production fused MC kernel for the C4a shape (dx = 6, dz = 2): a few lanes per chain, chain state in
 // registers.  mc_fused_kernel (mc_fused.cu: 32-chain tiles, tile GEMMs) serves every other dx, dz <= 8 and stays
 // selectable with VMS_MC_KERNEL=tile as an on-device cross-check.  Measured on a B200 (65,536 chains x 100 steps):
-// 1,270 M proposals/s = 24.4 TFLOP/s with two lanes per chain (799 M with four, 417 M for the tile kernel); bit-exact
+// 1,469 M proposals/s = 28.2 TFLOP/s with one lane per chain and two chains per lane (1,270 M with two lanes per chain,
+// 799 M with four, 417 M for the tile kernel); bit-exact
 // against the goldens of the reference's own mcmc.py (tests/test_gpu_models.py).
 //
 // Same contract as mc_fused.cu (mcmc.py:68-130 `MCMC.single_step` and the loop of `MCMC.run` :133-159 for the
@@ -81,50 +82,61 @@ __device__ __forceinline__ float combine(const float (&a)[4 / TPC]) {
   }
 }
 
-template <int TPC>
-__device__ __forceinline__ void mlp_pair(const float* __restrict__ wsm, int Hp, int sub, const float (&xe)[kMaxDx],
-                                         const float (&zd)[kMaxDz], float (&pe)[2 * kMaxDz], float (&pd)[2 * kMaxDx]) {
+// CPL chains per lane group share every weight load (the kernel is bound by shared-memory wavefronts -- a 16-byte
+// broadcast costs up to four -- not by FFMA issue: two chains per load halve the wavefronts per FFMA).
+template <int TPC, int CPL>
+__device__ __forceinline__ void mlp_pair(const float* __restrict__ wsm, int Hp, int sub, const float (&xe)[CPL][kMaxDx],
+                                         const float (&zd)[CPL][kMaxDz], float (&pe)[CPL][2 * kMaxDz],
+                                         float (&pd)[CPL][2 * kMaxDx]) {
   constexpr int NS = 4 / TPC;
-  float ae[2 * kMaxDz][NS], ad[2 * kMaxDx][NS];
+  float ae[CPL][2 * kMaxDz][NS], ad[CPL][2 * kMaxDx][NS];
 #pragma unroll
-  for (int q = 0; q < NS; ++q) {
+  for (int k = 0; k < CPL; ++k)
 #pragma unroll
-    for (int n = 0; n < 2 * kMaxDz; ++n) ae[n][q] = 0.f;
+    for (int q = 0; q < NS; ++q) {
 #pragma unroll
-    for (int n = 0; n < 2 * kMaxDx; ++n) ad[n][q] = 0.f;
-  }
+      for (int n = 0; n < 2 * kMaxDz; ++n) ae[k][n][q] = 0.f;
+#pragma unroll
+      for (int n = 0; n < 2 * kMaxDx; ++n) ad[k][n][q] = 0.f;
+    }
 #pragma unroll 2
   for (int j0 = 0; j0 < Hp; j0 += 4) {  // Hp: hidden units padded with zero rows to a multiple of 4 (a zero row adds +0)
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
       const float4* row = reinterpret_cast<const float4*>(wsm + (j0 + sub + TPC * q) * WROW);
       const float4 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4], f = row[5], g = row[6];
-      // encoder hidden unit: (sum_i x_i W0[i][j]) + b0[j]
-      float he = 0.f;
-      he = fmaf(xe[0], a.x, he); he = fmaf(xe[1], a.y, he); he = fmaf(xe[2], a.z, he);
-      he = fmaf(xe[3], a.w, he); he = fmaf(xe[4], b.x, he); he = fmaf(xe[5], b.y, he);
-      he = fmaxf(he + b.z, 0.f);
-      ae[0][q] = fmaf(he, b.w, ae[0][q]); ae[1][q] = fmaf(he, c.x, ae[1][q]);
-      ae[2][q] = fmaf(he, c.y, ae[2][q]); ae[3][q] = fmaf(he, c.z, ae[3][q]);
-      // decoder hidden unit
-      float hd = 0.f;
-      hd = fmaf(zd[0], c.w, hd); hd = fmaf(zd[1], d.x, hd);
-      hd = fmaxf(hd + d.y, 0.f);
-      ad[0][q] = fmaf(hd, d.z, ad[0][q]); ad[1][q] = fmaf(hd, d.w, ad[1][q]);
-      ad[2][q] = fmaf(hd, e.x, ad[2][q]); ad[3][q] = fmaf(hd, e.y, ad[3][q]);
-      ad[4][q] = fmaf(hd, e.z, ad[4][q]); ad[5][q] = fmaf(hd, e.w, ad[5][q]);
-      ad[6][q] = fmaf(hd, f.x, ad[6][q]); ad[7][q] = fmaf(hd, f.y, ad[7][q]);
-      ad[8][q] = fmaf(hd, f.z, ad[8][q]); ad[9][q] = fmaf(hd, f.w, ad[9][q]);
-      ad[10][q] = fmaf(hd, g.x, ad[10][q]); ad[11][q] = fmaf(hd, g.y, ad[11][q]);
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        // encoder hidden unit: (sum_i x_i W0[i][j]) + b0[j]
+        float he = 0.f;
+        he = fmaf(xe[k][0], a.x, he); he = fmaf(xe[k][1], a.y, he); he = fmaf(xe[k][2], a.z, he);
+        he = fmaf(xe[k][3], a.w, he); he = fmaf(xe[k][4], b.x, he); he = fmaf(xe[k][5], b.y, he);
+        he = fmaxf(he + b.z, 0.f);
+        ae[k][0][q] = fmaf(he, b.w, ae[k][0][q]); ae[k][1][q] = fmaf(he, c.x, ae[k][1][q]);
+        ae[k][2][q] = fmaf(he, c.y, ae[k][2][q]); ae[k][3][q] = fmaf(he, c.z, ae[k][3][q]);
+        // decoder hidden unit
+        float hd = 0.f;
+        hd = fmaf(zd[k][0], c.w, hd); hd = fmaf(zd[k][1], d.x, hd);
+        hd = fmaxf(hd + d.y, 0.f);
+        ad[k][0][q] = fmaf(hd, d.z, ad[k][0][q]); ad[k][1][q] = fmaf(hd, d.w, ad[k][1][q]);
+        ad[k][2][q] = fmaf(hd, e.x, ad[k][2][q]); ad[k][3][q] = fmaf(hd, e.y, ad[k][3][q]);
+        ad[k][4][q] = fmaf(hd, e.z, ad[k][4][q]); ad[k][5][q] = fmaf(hd, e.w, ad[k][5][q]);
+        ad[k][6][q] = fmaf(hd, f.x, ad[k][6][q]); ad[k][7][q] = fmaf(hd, f.y, ad[k][7][q]);
+        ad[k][8][q] = fmaf(hd, f.z, ad[k][8][q]); ad[k][9][q] = fmaf(hd, f.w, ad[k][9][q]);
+        ad[k][10][q] = fmaf(hd, g.x, ad[k][10][q]); ad[k][11][q] = fmaf(hd, g.y, ad[k][11][q]);
+      }
     }
   }
 #pragma unroll
-  for (int n = 0; n < 2 * kMaxDz; ++n) pe[n] = combine<TPC>(ae[n]);
+  for (int k = 0; k < CPL; ++k) {
 #pragma unroll
-  for (int n = 0; n < 2 * kMaxDx; ++n) pd[n] = combine<TPC>(ad[n]);
+    for (int n = 0; n < 2 * kMaxDz; ++n) pe[k][n] = combine<TPC>(ae[k][n]);
+#pragma unroll
+    for (int n = 0; n < 2 * kMaxDx; ++n) pd[k][n] = combine<TPC>(ad[k][n]);
+  }
 }
 
-template <int TPC, int MINB>
+template <int TPC, int CPL, int MINB>
 __global__ void __launch_bounds__(CT, MINB) mc_chain_kernel(const ChainParams p) {
   extern __shared__ __align__(16) float wsm[];  // [Hp][WROW] + enc b1 [4] + dec b1 [12]
   const int tid = threadIdx.x;
@@ -148,114 +160,140 @@ __global__ void __launch_bounds__(CT, MINB) mc_chain_kernel(const ChainParams p)
   if (tid < 12) b1d[tid] = __ldg(p.theta + p.dec1b + tid);
   __syncthreads();
 
-  const int64_t chain = ((int64_t)blockIdx.x * CT + tid) / TPC;
+  // lane group g owns chains g * CPL + k
+  const int64_t group = ((int64_t)blockIdx.x * CT + tid) / TPC;
   const int sub = tid & (TPC - 1);
-  const bool live = chain < p.B;
-  const int64_t cc = live ? chain : p.B - 1;  // idle lanes shadow the last chain (full-warp shuffles), writes predicated off
-  float x1[dx];
+  bool live[CPL];
+  int64_t cc[CPL];  // idle slots shadow the last chain (full-warp shuffles), writes predicated off
+  float x1[CPL][dx];
+  double e_old[CPL];
+  U128 rs[CPL];
+  const U128 jm = {p.jm_hi, p.jm_lo}, ja = {p.ja_hi, p.ja_lo};
 #pragma unroll
-  for (int d = 0; d < dx; ++d) x1[d] = __ldg(p.x + cc * dx + d);
-  double e_old;
-  if (p.energies_valid) {
-    e_old = p.E[cc];
-  } else {
-    e_old = 0.0;
+  for (int k = 0; k < CPL; ++k) {
+    const int64_t chain = group * CPL + k;
+    live[k] = chain < p.B;
+    cc[k] = live[k] ? chain : p.B - 1;
 #pragma unroll
-    for (int d = 0; d < dx; ++d) {
-      const double t = __dsub_rn((double)x1[d], p.means[d]);
-      e_old = __dadd_rn(e_old, __dmul_rn(t, t));
+    for (int d = 0; d < dx; ++d) x1[k][d] = __ldg(p.x + cc[k] * dx + d);
+    if (p.energies_valid) {
+      e_old[k] = p.E[cc[k]];
+    } else {
+      e_old[k] = 0.0;
+#pragma unroll
+      for (int d = 0; d < dx; ++d) {
+        const double t = __dsub_rn((double)x1[k][d], p.means[d]);
+        e_old[k] = __dadd_rn(e_old[k], __dmul_rn(t, t));
+      }
     }
+    rs[k] = U128{0ull, 0ull};
+    if (p.use_pcg)
+      rs[k] = pcg_advance(U128{p.s0_hi, p.s0_lo}, U128{p.inc_hi, p.inc_lo}, (unsigned long long)(p.chain0 + cc[k]) + 1ull);
   }
   unsigned n_accept = 0, n_unc = 0;
-  U128 rs = {0ull, 0ull};
-  const U128 jm = {p.jm_hi, p.jm_lo}, ja = {p.ja_hi, p.ja_lo};
-  if (p.use_pcg)
-    rs = pcg_advance(U128{p.s0_hi, p.s0_lo}, U128{p.inc_hi, p.inc_lo}, (unsigned long long)(p.chain0 + cc) + 1ull);
 
 #pragma unroll 1
   for (int step = 0; step < p.n_steps; ++step) {
     // ---- noise of this step: eps(z1) [dz] | eps(z2) [dz] | eps(x2) [dx]
-    float nz[12];
-    if (p.noise) {
+    float nz[CPL][12];
+    float z2[CPL][dz];
 #pragma unroll
-      for (int k = 0; k < nn; ++k) nz[k] = __ldg(p.noise + ((int64_t)step * p.B + cc) * nn + k);
-    } else {
-      const unsigned long long st = p.step0 + (unsigned long long)step;
-      const uint2 key = make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32) ^ (unsigned)(st >> 32));
+    for (int k = 0; k < CPL; ++k) {
+      if (p.noise) {
 #pragma unroll
-      for (int q = 0; q < (nn + 3) / 4; ++q) {
-        const unsigned long long gc = (unsigned long long)(p.chain0 + cc);  // GLOBAL chain index: sharding-invariant noise
-        const uint4 rnd = philox4x32(make_uint4((unsigned)gc, (unsigned)(gc >> 32), (unsigned)st, (unsigned)q), key);
-        box_muller(rnd.x, rnd.y, nz[4 * q], nz[4 * q + 1]);
-        box_muller(rnd.z, rnd.w, nz[4 * q + 2], nz[4 * q + 3]);
+        for (int i = 0; i < nn; ++i) nz[k][i] = __ldg(p.noise + ((int64_t)step * p.B + cc[k]) * nn + i);
+      } else {
+        const unsigned long long st = p.step0 + (unsigned long long)step;
+        const uint2 key = make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32) ^ (unsigned)(st >> 32));
+#pragma unroll
+        for (int q = 0; q < (nn + 3) / 4; ++q) {
+          const unsigned long long gc = (unsigned long long)(p.chain0 + cc[k]);  // GLOBAL chain index: sharding-invariant noise
+          const uint4 rnd = philox4x32(make_uint4((unsigned)gc, (unsigned)(gc >> 32), (unsigned)st, (unsigned)q), key);
+          box_muller(rnd.x, rnd.y, nz[k][4 * q], nz[k][4 * q + 1]);
+          box_muller(rnd.z, rnd.w, nz[k][4 * q + 2], nz[k][4 * q + 3]);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < dz; ++d) z2[k][d] = nz[k][dz + d];
+    }
+    // ---- encoder(x1) || decoder(z2)
+    float pe1[CPL][2 * dz], pd2[CPL][2 * dx];
+    mlp_pair<TPC, CPL>(wsm, Hp, sub, x1, z2, pe1, pd2);
+    // ---- samples z1, x2 and the forward log-probabilities (per-dof terms summed in dof order)
+    float z1[CPL][dz], x2[CPL][dx];
+    float lq1[CPL], lz1[CPL], lz2[CPL], lx2[CPL];
+    double e_new[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      lq1[k] = lz1[k] = lz2[k] = lx2[k] = 0.f;
+#pragma unroll
+      for (int d = 0; d < dz; ++d) {
+        const float loc = pe1[k][d] + b1e[d], sc = softplus_tf(pe1[k][dz + d] + b1e[dz + d]);
+        z1[k][d] = __fadd_rn(__fmul_rn(nz[k][d], sc), loc);
+        lq1[k] += normal_lp(z1[k][d], loc, sc);
+        lz1[k] += normal_lp(z1[k][d], 0.f, 1.f);
+        lz2[k] += normal_lp(z2[k][d], 0.f, 1.f);
+      }
+      e_new[k] = 0.0;
+#pragma unroll
+      for (int d = 0; d < dx; ++d) {
+        const float loc = pd2[k][d] + b1d[d], sc = softplus_tf(pd2[k][dx + d] + b1d[dx + d]);
+        x2[k][d] = __fadd_rn(__fmul_rn(nz[k][2 * dz + d], sc), loc);
+        lx2[k] += normal_lp(x2[k][d], loc, sc);
+        const double t = __dsub_rn((double)x2[k][d], p.means[d]);
+        e_new[k] = __dadd_rn(e_new[k], __dmul_rn(t, t));
       }
     }
-    float z2[dz];
-#pragma unroll
-    for (int d = 0; d < dz; ++d) z2[d] = nz[dz + d];
-    // ---- encoder(x1) || decoder(z2)
-    float pe1[2 * dz], pd2[2 * dx];
-    mlp_pair<TPC>(wsm, Hp, sub, x1, z2, pe1, pd2);
-    // ---- samples z1, x2 and the forward log-probabilities (per-dof terms summed in dof order)
-    float z1[dz], x2[dx];
-    float lq1 = 0.f, lz1 = 0.f, lz2 = 0.f, lx2 = 0.f;
-#pragma unroll
-    for (int d = 0; d < dz; ++d) {
-      const float loc = pe1[d] + b1e[d], sc = softplus_tf(pe1[dz + d] + b1e[dz + d]);
-      z1[d] = __fadd_rn(__fmul_rn(nz[d], sc), loc);
-      lq1 += normal_lp(z1[d], loc, sc);
-      lz1 += normal_lp(z1[d], 0.f, 1.f);
-      lz2 += normal_lp(z2[d], 0.f, 1.f);
-    }
-    double e_new = 0.0;
-#pragma unroll
-    for (int d = 0; d < dx; ++d) {
-      const float loc = pd2[d] + b1d[d], sc = softplus_tf(pd2[dx + d] + b1d[dx + d]);
-      x2[d] = __fadd_rn(__fmul_rn(nz[2 * dz + d], sc), loc);
-      lx2 += normal_lp(x2[d], loc, sc);
-      const double t = __dsub_rn((double)x2[d], p.means[d]);
-      e_new = __dadd_rn(e_new, __dmul_rn(t, t));
-    }
     // ---- encoder(x2) || decoder(z1)
-    float pe2[2 * dz], pd1[2 * dx];
-    mlp_pair<TPC>(wsm, Hp, sub, x2, z1, pe2, pd1);
-    float lq2 = 0.f, lx1 = 0.f;
+    float pe2[CPL][2 * dz], pd1[CPL][2 * dx];
+    mlp_pair<TPC, CPL>(wsm, Hp, sub, x2, z1, pe2, pd1);
 #pragma unroll
-    for (int d = 0; d < dz; ++d) lq2 += normal_lp(z2[d], pe2[d] + b1e[d], softplus_tf(pe2[dz + d] + b1e[dz + d]));
+    for (int k = 0; k < CPL; ++k) {
+      float lq2 = 0.f, lx1 = 0.f;
 #pragma unroll
-    for (int d = 0; d < dx; ++d) lx1 += normal_lp(x1[d], pd1[d] + b1d[d], softplus_tf(pd1[dx + d] + b1d[dx + d]));
-    // ---- accept / reject (mcmc.py:103, :109, :116-120): every lane of the chain computes the same decision
-    const float fwd = __fadd_rn(__fadd_rn(lq1, lz2), lx2);
-    const float rev = __fadd_rn(__fadd_rn(lq2, lz1), lx1);
-    const int64_t g = (int64_t)step * p.B + cc;
-    const double la = __dsub_rn(__dsub_rn(__dadd_rn(e_new, (double)rev), e_old), (double)fwd);
-    double lu;
-    if (p.use_pcg) {
-      lu = log(pcg_uniform(rs));
-      rs = add128(mul128(jm, rs), ja);  // this chain's draw of the next MC step: B_global draws further down the stream
-      if (fabs(la - lu) <= 1e-13 * fmax(1.0, fabs(lu))) n_unc += (live && sub == 0) ? 1u : 0u;
-    } else {
-      lu = __ldg(p.log_u + g);
-    }
-    const bool a = la >= lu;
-    if (live && sub == 0) {
-      if (p.log_u_trace) p.log_u_trace[g] = lu;
-      if (p.acc_trace) p.acc_trace[g] = a ? 1 : 0;
-      if (p.fwd_trace) p.fwd_trace[g] = fwd;
-      if (p.rev_trace) p.rev_trace[g] = rev;
-      if (p.e_new_trace) p.e_new_trace[g] = e_new;
-      n_accept += a ? 1u : 0u;
-    }
-    if (a) {
-      e_old = e_new;
+      for (int d = 0; d < dz; ++d)
+        lq2 += normal_lp(z2[k][d], pe2[k][d] + b1e[d], softplus_tf(pe2[k][dz + d] + b1e[dz + d]));
 #pragma unroll
-      for (int d = 0; d < dx; ++d) x1[d] = x2[d];
+      for (int d = 0; d < dx; ++d)
+        lx1 += normal_lp(x1[k][d], pd1[k][d] + b1d[d], softplus_tf(pd1[k][dx + d] + b1d[dx + d]));
+      // ---- accept / reject (mcmc.py:103, :109, :116-120): every lane of the chain computes the same decision
+      const float fwd = __fadd_rn(__fadd_rn(lq1[k], lz2[k]), lx2[k]);
+      const float rev = __fadd_rn(__fadd_rn(lq2, lz1[k]), lx1);
+      const int64_t g = (int64_t)step * p.B + cc[k];
+      const double la = __dsub_rn(__dsub_rn(__dadd_rn(e_new[k], (double)rev), e_old[k]), (double)fwd);
+      const bool mine = live[k] && sub == 0;
+      double lu;
+      if (p.use_pcg) {
+        lu = log(pcg_uniform(rs[k]));
+        rs[k] = add128(mul128(jm, rs[k]), ja);  // this chain's draw of the next MC step: B_global draws further down the stream
+        if (fabs(la - lu) <= 1e-13 * fmax(1.0, fabs(lu))) n_unc += mine ? 1u : 0u;
+      } else {
+        lu = __ldg(p.log_u + g);
+      }
+      const bool a = la >= lu;
+      if (mine) {
+        if (p.log_u_trace) p.log_u_trace[g] = lu;
+        if (p.acc_trace) p.acc_trace[g] = a ? 1 : 0;
+        if (p.fwd_trace) p.fwd_trace[g] = fwd;
+        if (p.rev_trace) p.rev_trace[g] = rev;
+        if (p.e_new_trace) p.e_new_trace[g] = e_new[k];
+        n_accept += a ? 1u : 0u;
+      }
+      if (a) {
+        e_old[k] = e_new[k];
+#pragma unroll
+        for (int d = 0; d < dx; ++d) x1[k][d] = x2[k][d];
+      }
     }
   }
-  if (live && sub == 0) {
 #pragma unroll
-    for (int d = 0; d < dx; ++d) p.x[chain * dx + d] = x1[d];
-    p.E[chain] = e_old;
+  for (int k = 0; k < CPL; ++k) {
+    if (live[k] && sub == 0) {
+      const int64_t chain = group * CPL + k;
+#pragma unroll
+      for (int d = 0; d < dx; ++d) p.x[chain * dx + d] = x1[k][d];
+      p.E[chain] = e_old[k];
+    }
   }
   // accepted moves of the CTA -> one atomic per warp
   unsigned w = n_accept;
@@ -311,21 +349,35 @@ vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x
   // lanes per chain by the number of chains (identical results for every choice, see `combine`)
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  // (B200, 65,536 chains x 100 steps: 4 lanes 799 M proposals/s, 2 lanes 1,270 M, 1 lane 1,241 M at 128 registers)
-  int tpc = B >= (int64_t)sms * 40 ? 2 : 4;
+  // (B200, 65,536 chains x 100 steps: 4 lanes 799 M proposals/s, 2 lanes 1,270 M, 1 lane 1,241 M at 128 registers, 1 lane
+  //  with two chains per lane 1,469 M; 32,768 chains: 2 lanes 1,106 M; 8,192: 2 lanes 678 M, 4 lanes 510 M)
+  const bool full = B >= (int64_t)sms * 256;  // enough chains for one lane per chain and two chains per lane
+  int tpc = full ? 1 : (B >= (int64_t)sms * 40 ? 2 : 4);
   if (const char* e = getenv("VMS_MC_TPC")) {  // cross-checks: force a lane count
     const int t = atoi(e);
     if (t == 1 || t == 2 || t == 4) tpc = t;
   }
-  const unsigned grid = (unsigned)((B * tpc + CT - 1) / CT);
-#define VMS_CHAIN_LAUNCH(T)                                                                                         \
-  do {                                                                                                              \
-    VMS_CUDA(cudaFuncSetAttribute(mc_chain_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    mc_chain_kernel<T, 4><<<grid, CT, smem, st>>>(p);                                                              \
+  int cpl = full ? 2 : 1;
+  if (const char* e = getenv("VMS_MC_CPL")) {  // cross-checks: chains per lane group
+    const int t = atoi(e);
+    if (t == 1 || t == 2) cpl = t;
+  }
+  const int64_t groups = (B + cpl - 1) / cpl;
+  const unsigned grid = (unsigned)((groups * tpc + CT - 1) / CT);
+#define VMS_CHAIN_LAUNCH(T, C, M)                                                                                      \
+  do {                                                                                                                 \
+    VMS_CUDA(cudaFuncSetAttribute(mc_chain_kernel<T, C, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mc_chain_kernel<T, C, M><<<grid, CT, smem, st>>>(p);                                                              \
   } while (0)
-  if (tpc == 1) VMS_CHAIN_LAUNCH(1);
-  else if (tpc == 2) VMS_CHAIN_LAUNCH(2);
-  else VMS_CHAIN_LAUNCH(4);
+  if (cpl == 1) {
+    if (tpc == 1) VMS_CHAIN_LAUNCH(1, 1, 4);
+    else if (tpc == 2) VMS_CHAIN_LAUNCH(2, 1, 4);
+    else VMS_CHAIN_LAUNCH(4, 1, 4);
+  } else {
+    if (tpc == 1) VMS_CHAIN_LAUNCH(1, 2, 2);
+    else if (tpc == 2) VMS_CHAIN_LAUNCH(2, 2, 2);
+    else VMS_CHAIN_LAUNCH(4, 2, 3);
+  }
 #undef VMS_CHAIN_LAUNCH
   VMS_LAUNCH_CHECK("mc_chain_kernel");
   return VMS_OK;
