@@ -391,6 +391,40 @@ def c3_leg(v, grp, peak_hbm, reps=10):
                    'note': 'PCIe-bound by construction: the reference API takes the frame replicated per row, 120 KB per row'},
            'roofline': {'bound': 'hbm', 'kernel': 'dist_select_kernel', 'achieved': gbs, 'peak': peak_hbm, 'unit': 'GB/s',
                         'frac': gbs / peak_hbm, 'algorithmic_bytes_per_row': bytes_row, 'traffic': None}}
+    # the same selection through the shared-frame entry (`DistanceSelection.select_from_frame`, vms_dist_select_frame): the C3
+    # workload IS one box of 10,000 particles with 4,096 sites -- the reference API makes the caller tile the box per site
+    frame_d, kinds_d = v.Tensor.from_numpy(frame), v.Tensor.from_numpy(np.eye(2, dtype=np.float32)[kinds])
+    for _ in range(3):
+        fsel = layer.select_from_frame(frame_d, ref_d, particle_info=kinds_d, return_indices=True)
+    c.synchronize()
+    grp.barrier()
+    f_ms = 0.0
+    for _ in range(reps):
+        lib.vms_memset(flush.ptr, 0, flush.nbytes, c.stream)
+        ev.record(0)
+        fsel = layer.select_from_frame(frame_d, ref_d, particle_info=kinds_d, return_indices=True)
+        ev.record(1)
+        c.synchronize()
+        f_ms += ev.elapsed_ms(0, 1)
+    f_ms = grp.max(f_ms) / reps
+    frame_h, kinds_h = pinned_array(lib, (N, 3)), pinned_array(lib, (N, P))
+    frame_h[...] = frame
+    kinds_h[...] = np.eye(2, dtype=np.float32)[kinds]
+    fgot = [t.numpy() for t in layer.select_from_frame(frame_h, ref_h, particle_info=kinds_h, return_indices=True)]
+    grp.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        fgot = [t.numpy() for t in layer.select_from_frame(frame_h, ref_h, particle_info=kinds_h, return_indices=True)]
+    f_e2e = grp.max(time.perf_counter() - t0) / n_e2e
+    res['shared_frame'] = {
+        'value': C3['rows'] / (f_ms * 1e-3), 'unit': 'rows/s', 'ms_per_call': f_ms,
+        'e2e': {'value': C3['rows'] / f_e2e, 'unit': 'rows/s', 'ms_per_call': f_e2e * 1e3,
+                'h2d_bytes_per_step': int(frame_h.nbytes + kinds_h.nbytes + ref_h.nbytes),
+                'd2h_bytes_per_step': int(B * k * (12 + 4 * P + 4)),
+                'api': 'DistanceSelection.select_from_frame(frame [N, 3], ref [B, 3], particle_info=[N, P], return_indices=True)'},
+        'equals_tiled_call': bool(all(np.array_equal(a, b) for a, b in zip(fgot, got))),
+        'note': 'extension without a reference counterpart: one frame shared by all sites, read from HBM once and then from '
+                'L2; the roofline above is for the reference-shaped (tiled) call'}
     if grp.rank == 0:
         n_cpu = 32
         t0 = time.perf_counter()

@@ -269,6 +269,12 @@ vms_status vms_batchnorm_backward(const float* x, int64_t ld_x, int64_t B, int D
 vms_status vms_dist_select(const float* coords, const int64_t* row_splits, int64_t B, int64_t N, const float* ref,
                            const float* box, int box_per_row, float cutoff_sq, int k, const float* info, int P,
                            float* out_xyz, float* out_info, int32_t* out_idx, vms_stream stream);
+/* The same selection for B sites around ONE frame: coords [N, 3] and info [N, P] are shared by every row, i.e. the result
+ * of vms_dist_select on the frame tiled B times (what mappings.py:362-455 makes a caller materialise for a simulation box:
+ * `batch_size = tf.shape(coords)[0]`, :399) with the frame uploaded and read from HBM once.  No reference counterpart.   */
+vms_status vms_dist_select_frame(const float* coords, int64_t N, const float* ref, int64_t B, const float* box,
+                                 int box_per_row, float cutoff_sq, int k, const float* info, int P, float* out_xyz,
+                                 float* out_info, int32_t* out_idx, vms_stream stream);
 
 /* ------------------------------------------------------------------------------- K7: MC acceptance
  * Replaces mcmc.py:116-128:  log_acc = E_new + rev - E_old - fwd (float64; log-probs float32 promoted);

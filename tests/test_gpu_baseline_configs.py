@@ -317,3 +317,28 @@ def test_flow_model_static_and_mapped_latent_match_oracle(vms):
     assert_close(d2.log_prob(y).numpy(), want2, rtol=1e-5, atol=3e-5, what='FlowModel (mapped latent) log_prob')
     # a tfp.layers-style latent (IndependentNormal IS a DistributionLambda) gets no mapping, exactly as in the reference
     assert v.models.FlowModel(flow2, PR.IndependentNormal(D)).mapping is None
+
+
+def test_dist_select_shared_frame_equals_tiled_call(vms):
+    """`DistanceSelection.select_from_frame` (vms_dist_select_frame): B sites around ONE frame give exactly the tiled
+    reference-shaped call -- coordinates, particle info and top_k indices -- with a stored box, a per-site box and no box;
+    and the oracle on the first rows."""
+    v = vms
+    rng = np.random.default_rng(8)
+    N, B, k, L = 3001, 97, 24, np.float32(21.5)
+    frame = rng.uniform(-L / 2, L / 2, (N, 3)).astype(np.float32)
+    info = np.eye(3, dtype=np.float32)[rng.integers(0, 3, N)]
+    ref = rng.uniform(-L / 2, L / 2, (B, 3)).astype(np.float32)
+    tiled, tinfo = np.ascontiguousarray(np.broadcast_to(frame, (B, N, 3))), np.ascontiguousarray(np.broadcast_to(info, (B, N, 3)))
+    for box, per_site in ((np.array([L, L, L], np.float32), None), (None, rng.uniform(18, 25, (B, 3)).astype(np.float32)),
+                          (None, None)):
+        layer = v.mappings.DistanceSelection(5.0, max_included=k, box_lengths=box)
+        a = [t.numpy() for t in layer.select_from_frame(frame, ref, box_lengths=per_site, particle_info=info, return_indices=True)]
+        b = [t.numpy() for t in layer(tiled, ref, box_lengths=per_site, particle_info=tinfo, return_indices=True)]
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        want = omap.distance_selection(tiled[:8], ref[:8], 5.0, k, box_lengths=box if per_site is None else per_site[:8],
+                                       particle_info=tinfo[:8], return_indices=True)
+        assert np.array_equal(a[0][:8], want[0]) and np.array_equal(a[1][:8], want[1]) and np.array_equal(a[2][:8], want[2])
+    only = v.mappings.DistanceSelection(5.0, max_included=k).select_from_frame(frame, ref)
+    assert only.shape == (B, k, 3)
+

@@ -131,6 +131,7 @@ _SIGS = {
     'vms_affine_cols': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
     'vms_dist_select': (None, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_f32, c_int, c_vp, c_int, c_vp, c_vp,
                                c_vp, c_vp]),
+    'vms_dist_select_frame': (None, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_f32, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vms_mc_accept': (None, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_mc_accept_f32': (None, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_energy_quadratic': (None, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),

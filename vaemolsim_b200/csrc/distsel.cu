@@ -33,6 +33,7 @@ struct DistSelParams {
   const float* info; int P;
   float* out_xyz; float* out_info; int32_t* out_idx;
   int dbg;  // development aid (VMS_DS_DBG): 1 = the stream kernel consumes the ring without arithmetic
+  int shared_frame;  // every row selects from the SAME N particles (coords [N, 3], info [N, P]): vms_dist_select_frame
 };
 
 struct Local { float x, y, z, d2; };
@@ -375,8 +376,8 @@ __global__ void __launch_bounds__(DT, 5) dist_select_kernel(const DistSelParams 
   unsigned& s_count = sm.s_count;
 
   const int64_t b = blockIdx.x;
-  const int64_t start = p.row_splits ? p.row_splits[b] : b * p.N;
-  const int64_t n64 = p.row_splits ? p.row_splits[b + 1] - start : p.N;
+  const int64_t start = p.shared_frame ? 0 : (p.row_splits ? p.row_splits[b] : b * p.N);
+  const int64_t n64 = (p.row_splits && !p.shared_frame) ? p.row_splits[b + 1] - start : p.N;
   const int n = (int)n64;
   const float* crow = p.coords + start * 3;
   const float rx = p.ref[b * 3], ry = p.ref[b * 3 + 1], rz = p.ref[b * 3 + 2];
@@ -614,10 +615,9 @@ __global__ void __launch_bounds__(DT, 3) dist_select_stream_kernel(const DistSel
 
 using namespace vms;
 
-extern "C" vms_status vms_dist_select(const float* coords, const int64_t* row_splits, int64_t B, int64_t N,
-                                      const float* ref, const float* box, int box_per_row, float cutoff_sq, int k,
-                                      const float* info, int P, float* out_xyz, float* out_info, int32_t* out_idx,
-                                      vms_stream stream) {
+static vms_status dist_select_impl(const float* coords, const int64_t* row_splits, int64_t B, int64_t N, const float* ref,
+                                   const float* box, int box_per_row, float cutoff_sq, int k, const float* info, int P,
+                                   float* out_xyz, float* out_info, int32_t* out_idx, int shared_frame, vms_stream stream) {
   VMS_RANGE("vms_dist_select");
   VMS_REQUIRE(B >= 0 && N >= 0, VMS_ERR_SHAPE, "dist_select: bad shape");
   VMS_REQUIRE(k >= 1 && k <= kCap, VMS_ERR_INVALID_ARG, "dist_select: max_included must be in [1, %d], got %d", kCap, k);
@@ -627,7 +627,8 @@ extern "C" vms_status vms_dist_select(const float* coords, const int64_t* row_sp
   VMS_REQUIRE((out_info == nullptr) || (info != nullptr && P >= 1), VMS_ERR_INVALID_ARG,
               "dist_select: particle_info required for out_info");
   if (B == 0) return VMS_OK;
-  DistSelParams p = {coords, row_splits, B, N, ref, box, box_per_row, cutoff_sq, k, info, P, out_xyz, out_info, out_idx, 0};
+  DistSelParams p = {coords, row_splits, B, N, ref, box, box_per_row, cutoff_sq, k, info, P, out_xyz, out_info, out_idx, 0,
+                     shared_frame};
   if (const char* e = getenv("VMS_DS_DBG")) p.dbg = atoi(e);
   // VMS_DISTSEL_STREAM=1: dense rows whose stride is a multiple of 16 bytes stream through the TMA ring (persistent CTAs);
   // default: one CTA per row with direct 16-byte loads, which measured faster
@@ -636,7 +637,7 @@ extern "C" vms_status vms_dist_select(const float* coords, const int64_t* row_sp
     const char* e = getenv("VMS_DISTSEL_STREAM");
     stream_on = (e && e[0] == '1') ? 1 : 0;
   }
-  const bool aligned = !row_splits && N % 4 == 0 && N >= kChunk && k <= 512 && (reinterpret_cast<uintptr_t>(coords) & 15u) == 0;
+  const bool aligned = !shared_frame && !row_splits && N % 4 == 0 && N >= kChunk && k <= 512 && (reinterpret_cast<uintptr_t>(coords) & 15u) == 0;
   if (stream_on && aligned) {
     const size_t smem = (size_t)kStages * kChunk * 12 + sizeof(RowSmem) + 128;
     static bool attr_set = false;
@@ -661,4 +662,19 @@ extern "C" vms_status vms_dist_select(const float* coords, const int64_t* row_sp
   dist_select_kernel<<<(unsigned)B, DT, 0, as_stream(stream)>>>(p);
   VMS_LAUNCH_CHECK("dist_select_kernel");
   return VMS_OK;
+}
+
+extern "C" vms_status vms_dist_select(const float* coords, const int64_t* row_splits, int64_t B, int64_t N,
+                                      const float* ref, const float* box, int box_per_row, float cutoff_sq, int k,
+                                      const float* info, int P, float* out_xyz, float* out_info, int32_t* out_idx,
+                                      vms_stream stream) {
+  return dist_select_impl(coords, row_splits, B, N, ref, box, box_per_row, cutoff_sq, k, info, P, out_xyz, out_info, out_idx, 0,
+                          stream);
+}
+
+extern "C" vms_status vms_dist_select_frame(const float* coords, int64_t N, const float* ref, int64_t B, const float* box,
+                                            int box_per_row, float cutoff_sq, int k, const float* info, int P, float* out_xyz,
+                                            float* out_info, int32_t* out_idx, vms_stream stream) {
+  return dist_select_impl(coords, nullptr, B, N, ref, box, box_per_row, cutoff_sq, k, info, P, out_xyz, out_info, out_idx, 1,
+                          stream);
 }

@@ -139,6 +139,52 @@ class DistanceSelection(P.Layer):
             return RaggedTensor.from_rows(x, inner)
         return None
 
+    def select_from_frame(self, frame, ref, box_lengths=None, particle_info=None, return_indices=False):
+        """Extension (no reference counterpart): B reference sites selecting from ONE frame.  `frame` [N, 3] (and
+        `particle_info` [N, P]) are the particles of a single configuration, `ref` [B, 3] the sites; the result is exactly
+        `call(tile(frame, B), ref, ...)` -- what the reference API requires a caller to materialise -- without the B copies:
+        the frame is uploaded and read from HBM once (it stays in L2 across rows) instead of B times.  This is the shape of
+        backmapping a simulation box: thousands of coarse-grained sites, one box of particles."""
+        c = ctx()
+        frame = as_tensor(frame).contig()
+        if frame.ndim == 3 and frame.shape[0] == 1:
+            frame = frame.reshape(frame.shape[1], 3)
+        if frame.ndim != 2 or frame.shape[1] != 3:
+            raise ValueError('frame must have shape (N_particles, 3); got %s' % (frame.shape, ))
+        N = frame.shape[0]
+        ref = as_tensor(ref).contig()
+        if ref.size % 3 != 0:
+            raise ValueError('ref must have shape (N_sites, 3); got %s' % (ref.shape, ))
+        B = ref.size // 3
+        box_ptr, per_row = None, 0
+        if box_lengths is not None:
+            box = as_tensor(box_lengths).contig()
+            if box.size == 3:
+                box_ptr = box.ptr
+            elif box.size == B * 3:
+                box_ptr, per_row = box.ptr, 1
+            else:
+                raise ValueError('box_lengths must have shape (3,) or (N_sites, 3); got %s' % (box.shape, ))
+        elif self.box_lengths is not None:
+            box_ptr = self._box_dev.ptr
+        k = int(self.max_included)
+        info_ptr, P_, out_info = None, 0, None
+        if particle_info is not None:
+            info = as_tensor(particle_info).contig()
+            if info.ndim == 3 and info.shape[0] == 1:
+                info = info.reshape(info.shape[1], info.shape[2])
+            if info.ndim != 2 or info.shape[0] != N:
+                raise ValueError('particle_info must have shape (N_particles, P) like frame')
+            P_, info_ptr = info.shape[1], info.ptr
+            out_info = Tensor((B, k, P_))
+        out_xyz = Tensor((B, k, 3))
+        out_idx = Tensor((B, k), np.int32) if return_indices else None
+        c.lib.vms_dist_select_frame(frame.ptr, N, ref.ptr, B, box_ptr, per_row, float(np.float32(self.sq_cut)), k, info_ptr, P_,
+                                    out_xyz.ptr, None if out_info is None else out_info.ptr,
+                                    None if out_idx is None else out_idx.ptr, c.stream)
+        outs = [out_xyz] + ([out_info] if out_info is not None else []) + ([out_idx] if return_indices else [])
+        return outs[0] if len(outs) == 1 else tuple(outs)
+
     def call(self, coords, ref, box_lengths=None, particle_info=None, return_indices=False):
         c = ctx()
         rag = self._ragged(coords, 3)
