@@ -438,6 +438,43 @@ def c3_leg(v, grp, peak_hbm, reps=10):
     return res
 
 
+# ------------------------------------------------------------------------------ FlowModel NLL training (generic tape path)
+def flow_model_leg(v, grp):
+    """`FlowModel` of examples/Using_Normalizing_Flows.ipynb (cells 18-24: 1-D RQSSplineRealNVP, 4 blocks, K = 32, H = 100
+    over N(0, 1), NLL `fit`) through the generic path -- op-by-op kernels recorded on a tape, reverse mode, Adam per weight
+    (no fused plan exists for this family): training steps per second at the notebook's batch size 32 (BASELINE.md quotes the
+    notebook's Keras progress bar: 2 ms/step on an M1/M2 Mac) and at batch 4096, host-driven, wall clock."""
+    import vaemolsim_b200._protocols as PR
+    c = v._abi.ctx()
+    v.set_seed(7)
+    flow = v.flows.RQSSplineRealNVP(num_blocks=4, rqs_params=dict(bin_range=[-10.0, 10.0], num_bins=32, hidden_dim=100))
+    fm = v.models.FlowModel(flow, PR.DistributionLambda(lambda t: PR.StandardNormal(t.shape[0], 1)))
+    fm.compile(optimizer=v.models.Adam(1e-3), loss=v.losses.LogProbLoss())
+    rng = np.random.default_rng(21)
+    out = {}
+    losses = []
+    for B, n in ((32, 60), (4096, 30)):
+        x = (rng.normal(size=(B, 1)) * 1.5 + 0.5).astype(np.float32)
+        for _ in range(5):
+            fm.train_on_batch(x, x)
+        c.synchronize()
+        l0 = v._abi.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            losses.append(fm.train_on_batch(x, x))
+        c.synchronize()
+        dt = (time.perf_counter() - t0) / n
+        out['batch_%d' % B] = {'ms_per_step': dt * 1e3, 'configs_per_s': B / dt,
+                               'gpu_launches_per_step': (v._abi.launch_count() - l0) / n}
+    return {'metric': 'FlowModel NLL training steps (tape path)', 'value': out['batch_4096']['configs_per_s'], 'unit': 'configs/s',
+            'workload': 'Using_Normalizing_Flows.ipynb FlowModel: 1-D RQSSplineRealNVP 4 blocks K=32 H=100 over N(0,1), NLL + Adam',
+            'scaling': 'replicas (every rank runs the same steps)', **out, 'loss_finite': bool(np.isfinite(losses).all()),
+            'reference_notebook': 'Keras progress bar of the notebook (BASELINE.md 2): 2 ms/step at batch 32 on an Apple M1/M2 '
+                                  '= 16-20 k configs/s; other hardware, quoted for orientation only',
+            'e2e': {'value': out['batch_4096']['configs_per_s'], 'unit': 'configs/s', 'h2d_bytes_per_step': 4096 * 4 * 2,
+                    'd2h_bytes_per_step': 4, 'api': 'FlowModel.train_on_batch(x, x) from host arrays'}}
+
+
 # ---------------------------------------------------------------------------------------------------- MC leg (C4a)
 MC_CHAINS, MC_STEPS = 65536, 100
 MC_LABEL = ('C4a VAE-proposal MC: Gaussian VAE (enc 6-200-4, dec 2-200-12, N(0,I) prior), quadratic energy on device, '
@@ -1027,6 +1064,10 @@ def run_b200(args, w):
             legs['c4b_mc'] = c4b_bench(v, grp, peaks['fp32_ffma_tflops'])
         except Exception as ex:
             legs['c4b_mc'] = {'error': '%s: %s' % (type(ex).__name__, ex)}
+        try:
+            legs['flow_model'] = flow_model_leg(v, grp)
+        except Exception as ex:
+            legs['flow_model'] = {'error': '%s: %s' % (type(ex).__name__, ex)}
         try:
             legs['c5'] = large_batch_leg(v, w, r['opt'], grp, peaks, args.collective)
         except Exception as ex:
