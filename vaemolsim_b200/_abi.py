@@ -275,6 +275,20 @@ class _Context(object):
         self.lib.vms_stream_synchronize(self.stream)
 
 
+# Bumped by every host call that changes model parameters on the device (Dense.set_weights / assign / rebind, MADE
+# set_weights, Model.set_weights, a Trainer step, the fused plans' training steps): consumers that cache something DERIVED
+# from the weights (the MC notebook kernel's knot tables) compare it with the value they cached at.
+_param_epoch = [0]
+
+
+def bump_param_epoch():
+    _param_epoch[0] += 1
+
+
+def param_epoch():
+    return _param_epoch[0]
+
+
 def ctx():
     global _ctx
     if _ctx is None:

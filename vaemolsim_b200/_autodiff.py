@@ -16,6 +16,7 @@ import ctypes as C
 
 import numpy as np
 
+from . import _abi
 from ._abi import Tensor, ctx
 
 
@@ -168,5 +169,6 @@ class Trainer(object):
                                     o.beta_2, o.epsilon, c.stream)
                 it = 4
                 c.lib.vms_memcpy2d_d2d(w.ptr, w.ld * it, wc.ptr, wc.ld * it, w.shape[-1] * it, w.shape[0], c.stream)
+        _abi.bump_param_epoch()
         tape.release()
         return loss

@@ -171,6 +171,7 @@ class Dense(Layer):
             self.bias = Tensor.from_numpy(np.asarray(arrays[1], np.float32))
         self._weights = [self.kernel] + ([self.bias] if self.use_bias else [])
         self.built = True
+        _abi.bump_param_epoch()
 
     def get_weights(self):
         return [w.numpy() for w in self._weights]
@@ -186,6 +187,7 @@ class Dense(Layer):
             b = np.ascontiguousarray(bias, np.float32)
             c.lib.vms_memcpy_h2d(self.bias.ptr, b.ctypes.data, b.nbytes, c.stream)
         c.synchronize()
+        _abi.bump_param_epoch()
         hook = getattr(self, '_on_assign', None)
         if hook is not None:
             hook()
@@ -193,6 +195,7 @@ class Dense(Layer):
     def rebind(self, kernel, bias):
         """Point the layer at externally owned storage (flat parameter buffer views)."""
         self.kernel, self.bias = kernel, bias
+        _abi.bump_param_epoch()
         self._weights = [self.kernel] + ([self.bias] if self.use_bias else [])
 
     def call(self, x, ones_input=False, cond=None, cond_kernel=None):
@@ -423,6 +426,7 @@ class AutoregressiveNetwork(Layer):
             if self.conditional:
                 self.cond_kernels[k] = Tensor.from_numpy(np.asarray(next(it), np.float32))
                 self._weights.append(self.cond_kernels[k])
+        _abi.bump_param_epoch()
 
     def call(self, x, conditional_input=None):
         if self.conditional and conditional_input is None:

@@ -439,8 +439,10 @@ class MCMC(object):
         """State of the fused kernel for the model family of examples/MC_Moves_with_VAEs.ipynb (`vms_mc_nb_run`), or None
         when (vae, energy) is anything else: FCDeepNN(2 -> H -> 2) + IndependentNormal(1) encoder, RQSSplineMAF prior over a
         one-dimensional N(0, 1), FCDeepNN(1 -> H -> (2, 2)) + conditional AutoregressiveBlockwise(2 Normal) decoder with a
-        three-hidden-layer MADE, GaussianMixtureEnergy.  Only the STRUCTURE is cached: weight pointers and the prior's knot
-        tables are gathered at every call, so training / set_weights between calls is seen."""
+        three-hidden-layer MADE, GaussianMixtureEnergy.  The structure is cached here; weight pointers and the prior's knot
+        tables are re-derived whenever the package's parameter epoch moved (`_abi.param_epoch()`: bumped by set_weights /
+        assign / training steps), so training between calls is seen.  Code that overwrites weights through raw device
+        pointers must call `_abi.bump_param_epoch()` itself."""
         if self._nb is not None:
             return self._nb or None
         self._nb = False
@@ -525,6 +527,9 @@ class MCMC(object):
         block's three conditioner networks + vms_rqs_knot_table)."""
         c = ctx()
         m = nb['model']
+        cached = nb.get('cache')
+        if cached is not None and cached[0] == _abi.param_epoch():
+            return m, cached[1]  # no parameter changed since the tables were built (same pointers, same values)
         keep = []
 
         def ptr(t):
@@ -548,6 +553,7 @@ class MCMC(object):
         m.tables = tables.ptr
         m.gmm_log_w, m.gmm_loc, m.gmm_scale = (t.ptr for t in nb['gmm'])
         keep.append(tables)
+        nb['cache'] = (_abi.param_epoch(), keep)
         return m, keep
 
     def run_nb(self, configs, energies=None, n_steps=1, noise=None, trace=False, configs_dev=None, energies_dev=None):

@@ -144,6 +144,7 @@ class Model(P.Layer):
                 c.synchronize()
             else:
                 w.assign_cols(0, Tensor.from_numpy(a))
+        _abi.bump_param_epoch()
         f = getattr(self, '_fused', None)
         if f is not None:
             f.invalidate()
@@ -494,6 +495,7 @@ class FusedELBO(object):
         return self.scalars
 
     def adam_step(self, opt, grad_scale=1.0):
+        _abi.bump_param_epoch()
         c = ctx()
         self.t += 1
         c.lib.vms_adam_step(self.theta.ptr, self.grad.ptr, 1, grad_scale, self.m.ptr, self.v.ptr, self.n_params, self.t,
@@ -510,6 +512,7 @@ class FusedELBO(object):
         forward + backward into this rank's slot of the exchange buffer followed by the fused NVLink allreduce + Adam kernel
         (every rank must run the same number of steps); the scalars are this rank's shard means.  Returns the
         [n_steps, 3] scalars."""
+        _abi.bump_param_epoch()
         c = ctx()
         lib = c.lib
         N = x_host.shape[0]
@@ -613,6 +616,7 @@ class FusedELBO(object):
 
     def train_step(self, x, eps, opt):
         """Forward + backward + Adam in one C call (`vms_elbo_train_step`: 2 kernel launches on the fused path)."""
+        _abi.bump_param_epoch()
         c = ctx()
         self.t += 1
         c.lib.vms_elbo_train_step(self.handle, self.theta.ptr, x.ptr, eps.ptr, x.shape[0], self.grad.ptr, self.scalars.ptr,

@@ -330,6 +330,8 @@ class PeerExchange(object):
         `fused.theta / m / v` in place.  All ranks must call it once per step."""
         self.step += 1
         fused.t += 1
+        from . import _abi
+        _abi.bump_param_epoch()
         if self.check_every and self.step % self.check_every == 0:
             self.check()
         self.ctx.lib.vms_peer_allreduce_adam(self.world, self.rank, self.bases, self.n, self.step, 1.0 / self.world,
