@@ -989,6 +989,76 @@ def test_keras_style_weight_export_import_round_trip(vms, tmp_path):
         b.set_weights(ws[:-1])
 
 
+@pytest.mark.parametrize('made_hidden,order,act,bins,blocks,hidden', [
+    ([10, 100, 10], 'left-to-right', None, 20, 4, 200),
+    ([10, 100, 10], 'right-to-left', 'tanh', 20, 2, 64),
+    ([7, 33, 12], 'left-to-right', 'relu', 8, 1, 37),
+    ([16, 64, 16], 'right-to-left', None, 12, 3, 50),
+    ([3, 5, 2], 'left-to-right', 'tanh', 4, 2, 8),
+])
+def test_fused_mc_notebook_kernel_shapes_orders_activations(vms, monkeypatch, made_hidden, order, act, bins, blocks, hidden):
+    """The fused notebook-family kernel over the shapes it accepts -- padded MADE widths (12 / 16), both input orders (which
+    dof the masks put first), the three activations, 1-4 flow blocks, hidden sizes that are no multiple of 4 -- against the
+    op-by-op kernels on the same noise and uniforms; and the generic D + 1-pass sampling path (no mask knowledge) against
+    the one-pass path, bit for bit."""
+    v = vms
+    import vaemolsim_b200._protocols as PR
+    d = v.dists
+    v.set_seed(17)
+    enc = v.models.MappingToDistribution(PR.IndependentNormal(1), name='encoder')
+    dec_dist = d.AutoregressiveBlockwise(2, [d.Normal] * 2, conditional=True, conditional_event_shape=(1, ),
+                                         auto_net_params={'hidden_units': made_hidden, 'activation': act, 'input_order': order})
+    dec = v.models.MappingToDistribution(dec_dist, name='decoder')
+    enc.mapping.hidden_dim = [hidden]
+    dec.mapping.hidden_dim = [hidden + 3]
+    flow = v.flows.RQSSplineMAF(num_blocks=blocks, rqs_params={'bin_range': [-6.0, 6.0], 'num_bins': bins, 'hidden_dim': 9})
+    flow(np.zeros((2, 1), np.float32))
+    prior = d.FlowedDistribution(flow, PR.DistributionLambda(lambda t: PR.StandardNormal(t.shape[0], 1)), name='prior')
+    model = v.models.VAE(enc, dec, prior)
+    model(np.zeros((2, 2), np.float32))
+    rng = np.random.default_rng(2)
+    # biases away from zero (a zero-bias 1-D MAF is the identity), the MADE's shift kept moderate
+    net = dec_dist.auto_net
+    arrs = []
+    for k, lay in enumerate(net.layers):
+        sc = np.float32(0.3 if k == len(net.layers) - 1 else 1.0)
+        arrs += [lay.kernel.numpy() * sc, rng.normal(0, 0.3, lay.units).astype(np.float32) * sc, net.cond_kernels[k].numpy() * sc]
+    net.set_weights(arrs)
+    for bij in flow.chain.bijectors:
+        msb = bij.bijector_fn
+        for sub in (msb.bin_widths, msb.bin_heights, msb.knot_slopes):
+            sub.set_weights([a for lay in sub.layers for a in (lay.kernel.numpy(), rng.normal(0, 0.5, lay.units).astype(np.float32))])
+    energy = v.mcmc.GaussianMixtureEnergy(probs=(0.5, 0.5), locs=((0.0, 0.0), (1.0, -1.0)), scales=((1.0, 1.0), (0.7, 1.3)))
+    B, n_steps = 777, 6
+    x0 = rng.normal(size=(B, 2)).astype(np.float32)
+    noise = _nb_noise(5, n_steps, B)
+    a = v.mcmc.MCMC(model, energy, random_seed=4)
+    assert a._nb_plan() is not None and a._nb_plan()['model'].made_first_dof == (0 if order == 'left-to-right' else 1)
+    xa, ea = a.run_nb(x0, n_steps=n_steps, noise=noise, trace=True)
+    tra = a._last_trace
+    b = v.mcmc.MCMC(model, energy, random_seed=4)
+    b.fuse_notebook = False
+    v.set_seed(5)
+    xb, eb = x0, None
+    acc_b = np.empty((n_steps, B), bool)
+    for s in range(n_steps):
+        xb, eb = b.single_step(xb, energies=eb)
+        acc_b[s] = b._last_acc.numpy().astype(bool)
+    diff = (tra['acc'].astype(bool) != acc_b).any(axis=0)
+    assert diff.sum() <= 2, diff.sum()
+    assert_close(xa[~diff], xb[~diff], rtol=1e-5, atol=1e-4, what='final configs')
+    assert_close(ea[~diff], eb[~diff], rtol=1e-5, atol=3e-4, what='final energies')
+    assert 0.01 < a.acceptance_rate < 0.99
+    # tfp's full procedure (D + 1 sampling passes + log_prob pass) gives the same bits as the one-pass path
+    monkeypatch.setenv('VMS_NB_GENERIC', '1')
+    g = v.mcmc.MCMC(model, energy, random_seed=4)
+    assert g._nb_plan()['model'].made_first_dof == -1
+    xg, eg = g.run_nb(x0, n_steps=n_steps, noise=noise, trace=True)
+    assert np.array_equal(xg, xa) and np.array_equal(eg, ea)
+    for key in ('acc', 'fwd', 'rev', 'e_new'):
+        assert np.array_equal(g._last_trace[key], tra[key]), key
+
+
 def test_mc_notebook_workflow_train_then_sample(vms):
     """The workflow of examples/MC_Moves_with_VAEs.ipynb end to end on the device: build the notebook's VAE (cells 11-20),
     train it on samples of the Gaussian mixture (cell 22-25; the generic tape path: MAF prior, autoregressive decoder,

@@ -10,6 +10,7 @@ host stream for a call whose decisions could depend on the last ulps of the loga
 reference either way.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -513,6 +514,8 @@ class MCMC(object):
         for f in (0, 1):
             if not mk[0][1 - f, :].any() and not mk[-1][:, 2 * f:2 * f + 2].any():
                 m.made_first_dof = f
+        if os.environ.get('VMS_NB_GENERIC') == '1':  # cross-checks: tfp's D + 1 sampling passes + log_prob pass, no mask knowledge
+            m.made_first_dof = -1
         m.n_blocks, m.n_bins, m.range_min, m.range_max = len(blocks), msb.num_bins, msb.bin_min, msb.bin_max
         m.n_comp = len(E.probs)
         if not _abi.load().vms_mc_nb_supported(C.byref(m)):
