@@ -319,6 +319,57 @@ def test_flow_model_static_and_mapped_latent_match_oracle(vms):
     assert v.models.FlowModel(flow2, PR.IndependentNormal(D)).mapping is None
 
 
+def test_mc_c4b_1024_of_65536_chains_100_steps_vs_oracle(vms):
+    """BASELINE configs[3] / C4b (the MC notebook's model at its full widths: hidden 200, 4 MAF blocks, K = 20, H = 40, MADE
+    [10, 100, 10]): chains [20480, 21504) of the 65,536-chain job, 100 MC steps in ONE launch of the fused kernel with the
+    uniform stream drawn on the device, against the oracle restatement of mcmc.py:68-130 on `OracleVAEb` with the same
+    sampling noise and the same PCG64 columns.  Chains are compared decision by decision; the flip count is bounded."""
+    v = vms
+    from helpers import vae_b_from_oracle
+    n_global, lo, B, n_steps = 65536, 20480, 1024, 100
+    P = omc.init_vae_b(2003, hidden=200)
+    model = vae_b_from_oracle(v, P)
+    rng0 = np.random.default_rng(5001)
+    k = rng0.choice(3, size=n_global, p=[0.7, 0.2, 0.1])
+    x0 = (omc.GMM_LOCS[k] + omc.GMM_SCALES[k] * rng0.standard_normal((n_global, 2))).astype(np.float32)[lo:lo + B]
+    rng = np.random.default_rng(888)
+    noise = np.empty((n_steps, B, 4), np.float32)
+    for s in range(n_steps):  # the order the reference's step draws in (mcmc.py:100-102): encoder, prior, decoder
+        noise[s, :, 0:1] = rng.standard_normal((B, 1), dtype=np.float32)
+        noise[s, :, 1:2] = rng.standard_normal((B, 1), dtype=np.float32)
+        noise[s, :, 2:4] = rng.standard_normal((B, 2), dtype=np.float32)
+    mc = v.mcmc.MCMC(model, v.mcmc.GaussianMixtureEnergy(), random_seed=5002, stream_layout=(lo, n_global))
+    assert mc._nb_plan() is not None
+    x_dev, e_dev = mc.run_nb(x0, n_steps=n_steps, noise=noise, trace=True)
+    tr = mc._last_trace
+    assert mc.host_stream_reruns == 0
+    u = np.random.default_rng(5002).random(size=(n_steps, n_global))[:, lo:lo + B]
+    np.testing.assert_array_max_ulp(tr['log_u'], np.log(u), maxulp=2)
+
+    class _Cols(object):  # hands the oracle step the shard's columns of the global stream
+        s = 0
+
+        def random(self, size):
+            self.s += 1
+            return u[self.s - 1]
+
+    ovm, cols = omc.OracleVAEb(P, noise_seed=888), _Cols()
+    xo, eo = x0.copy(), None
+    acc_o = np.empty((n_steps, B), bool)
+    for s in range(n_steps):
+        xo, eo, acc_o[s] = omc.single_step(ovm, omc.gmm_energy, cols, xo, eo)
+    acc_d = tr['acc'].astype(bool)
+    differs = (acc_d != acc_o).any(axis=0)
+    flips = int(differs.sum())
+    print('C4b parity: %d of %d chains flipped a decision in %d steps (accepted: device %d, oracle %d)' %
+          (flips, B, n_steps, acc_d.sum(), acc_o.sum()))
+    assert flips <= 4, flips
+    same = ~differs
+    assert_close(x_dev[same], xo[same], rtol=1e-5, atol=1e-4, what='C4b final configurations')
+    assert_close(e_dev[same], eo[same], rtol=1e-5, atol=3e-4, what='C4b final energies')
+    assert mc._num_trials == B * n_steps and mc._num_acc == float(acc_d.sum()) and acc_d.sum() > 1000
+
+
 def test_dist_select_shared_frame_equals_tiled_call(vms):
     """`DistanceSelection.select_from_frame` (vms_dist_select_frame): B sites around ONE frame give exactly the tiled
     reference-shaped call -- coordinates, particle info and top_k indices -- with a stored box, a per-site box and no box;
