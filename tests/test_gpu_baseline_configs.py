@@ -327,7 +327,7 @@ def test_mc_c4b_1024_of_65536_chains_100_steps_vs_oracle(vms):
     v = vms
     from helpers import vae_b_from_oracle
     n_global, lo, B, n_steps = 65536, 20480, 1024, 100
-    P = omc.init_vae_b(2003, hidden=200)
+    P = omc.init_vae_b(7, hidden=200)  # (a seed whose untrained proposal is accepted ~20 % of the time)
     model = vae_b_from_oracle(v, P)
     rng0 = np.random.default_rng(5001)
     k = rng0.choice(3, size=n_global, p=[0.7, 0.2, 0.1])
