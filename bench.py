@@ -863,6 +863,24 @@ def large_batch_leg(v, w, opt, grp, peaks, collective='auto', global_batch=26214
     c.synchronize()
     grp.barrier()
     ms = grp.max(ev.elapsed_ms(0, 1)) / steps
+    # end to end: the same steps through the public pipelined loop (`FusedELBO.train_loop`, what `VAE.fit` runs), every step's
+    # shard of x / eps leaving PINNED host memory on the copy stream while the previous step trains, every step's scalars
+    # read back; the peer exchange runs inside the loop when N > 1
+    e2e = None
+    if world == 1 or peer is not None:
+        n_e2e = steps
+        xh, eh = pinned_array(c.lib, (2 * batch, w['dx'])), pinned_array(c.lib, (2 * batch, w['dz']))
+        xh[...] = rng.standard_normal((2 * batch, w['dx']), dtype=np.float32)
+        eh[...] = rng.standard_normal((2 * batch, w['dz']), dtype=np.float32)
+        f.train_loop(xh, opt, batch, eps_host=eh, n_steps=2, exchange=peer)
+        grp.barrier()
+        t0 = time.perf_counter()
+        f.train_loop(xh, opt, batch, eps_host=eh, n_steps=n_e2e, exchange=peer)
+        e2e_s = grp.max(time.perf_counter() - t0) / n_e2e
+        e2e = {'value': global_batch / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
+               'h2d_bytes_per_step': int(batch * (w['dx'] + w['dz']) * 4), 'd2h_bytes_per_step': 16,
+               'api': 'FusedELBO.train_loop (VAE.fit inner loop): per-step H2D of the shard from pinned memory, step, '
+                      'scalars read-back, pipelined'}
     timed_out = False
     if peer is not None:
         timed_out = grp.sum(1.0 if peer.timed_out() else 0.0) > 0.0
@@ -888,7 +906,7 @@ def large_batch_leg(v, w, opt, grp, peaks, collective='auto', global_batch=26214
             'scaling': 'strong', 'ms_per_step': ms, 'plan': f.path(batch), 'value': global_batch / (ms * 1e-3),
             'unit': UNIT, 'configs_per_s': global_batch / (ms * 1e-3),
             'collective': 'none' if world == 1 else ('peer kernel' if peer is not None else 'nccl'),
-            'tflops_fp32': global_batch * flop / (ms * 1e-3) / 1e12, 'roofline': roof,
+            'tflops_fp32': global_batch * flop / (ms * 1e-3) / 1e12, 'roofline': roof, 'e2e': e2e,
             'valid': not (timed_out or tc_bad), 'last_loss': float(f.scalars.numpy()[0])}
 
 
