@@ -306,6 +306,20 @@ vms_status vms_energy_gmm(const float* x, int64_t B, int D, int n_comp, const fl
 vms_status vms_adam_step(float* theta, const float* g, int n_partials, float grad_scale, float* m, float* v,
                          int64_t n, int64_t t, double lr, double beta1, double beta2, double eps, vms_stream stream);
 vms_status vms_sum_partials(const float* g, int n_partials, int64_t n, float scale, float* out, vms_stream stream);
+/* The same update for every weight tensor of a model in one launch per VMS_ADAM_MULTI_MAX tensors (Keras applies Adam per
+ * variable, models.py:85-139 `fit`; the op-by-op training path is bound by its launch count).  mask (nullable): 0 / 1
+ * multiplier of the gradient, the constraint of tfp's AutoregressiveNetwork kernels (flows.py:450-487).                */
+#define VMS_ADAM_MULTI_MAX 64
+typedef struct {
+  float* theta;
+  const float* grad;
+  const float* mask;
+  float* m;
+  float* v;
+  int64_t n;
+} vms_adam_tensor;
+vms_status vms_adam_step_multi(const vms_adam_tensor* tensors, int n_tensors, float grad_scale, int64_t t, double lr,
+                               double beta1, double beta2, double eps, vms_stream stream);
 
 /* ------------------------------------------------------------------------------- fused ELBO step (C1 / C2)
  * One handle = one VAE of the family used by the reference's tests (tests/test_models.py:161-228):

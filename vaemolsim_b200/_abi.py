@@ -58,6 +58,11 @@ class McNbModel(C.Structure):
                 ('tables', c_vp), ('n_comp', C.c_int), ('gmm_log_w', c_vp), ('gmm_loc', c_vp), ('gmm_scale', c_vp)]
 
 
+class AdamTensor(C.Structure):
+    """vms_adam_tensor (include/vms_b200.h)."""
+    _fields_ = [('theta', c_vp), ('grad', c_vp), ('mask', c_vp), ('m', c_vp), ('v', c_vp), ('n', c_i64)]
+
+
 class ElboDesc(C.Structure):
     _fields_ = [('dx', C.c_int32), ('dz', C.c_int32), ('hidden', C.c_int32), ('num_blocks', C.c_int32),
                 ('num_bins', C.c_int32), ('flow_hidden', C.c_int32), ('bin_min', c_f32), ('bin_max', c_f32),
@@ -137,6 +142,7 @@ _SIGS = {
     'vms_mc_accept_f32': (None, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_energy_quadratic': (None, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     'vms_energy_gmm': (None, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vms_adam_step_multi': (None, [C.POINTER(AdamTensor), c_int, c_f32, c_i64, c_f64, c_f64, c_f64, c_f64, c_vp]),
     'vms_adam_step': (None, [c_vp, c_vp, c_int, c_f32, c_vp, c_vp, c_i64, c_i64, c_f64, c_f64, c_f64, c_f64, c_vp]),
     'vms_sum_partials': (None, [c_vp, c_int, c_i64, c_f32, c_vp, c_vp]),
     'vms_elbo_plan_create': (None, [C.POINTER(ElboDesc), C.POINTER(c_vp)]),

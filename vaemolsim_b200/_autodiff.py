@@ -131,44 +131,50 @@ class Trainer(object):
             tape.backward(loss)
         self.t += 1
         seen = set()
-        todo = []
+        todo = []  # (weight, gradient, mask or None)
         for w in self.model.weights:
             if id(w) in seen or not (tape.has(w) or self.group is not None):
                 continue
             seen.add(id(w))
             g = tape.grad(w)  # (data-parallel: every rank exchanges every weight, a zero gradient if it received none)
-            mask = getattr(w, '_grad_mask', None)
-            if mask is not None:  # tfp AutoregressiveNetwork: masked kernel entries stay zero
-                c.lib.vms_mul_inplace(g.ptr, mask.ptr, g.size, c.stream)
-            todo.append((w, g))
+            todo.append((w, g, getattr(w, '_grad_mask', None)))  # mask: tfp AutoregressiveNetwork, masked entries stay zero
         scale = 1.0
         if self.group is not None:
-            total = sum(w.size for w, _ in todo)
+            total = sum(w.size for w, _, _ in todo)
             if self._flat is None or self._flat.size != total:
                 self._flat = Tensor((total, ))
             off, flat = 0, []
-            for w, g in todo:
+            for w, g, mask in todo:
+                if mask is not None:  # masked before the exchange, so that every rank sends the constrained gradient
+                    c.lib.vms_mul_inplace(g.ptr, mask.ptr, g.size, c.stream)
                 gc = g if g.contiguous else g.contig()
                 dst = Tensor(w.shape, np.float32, _ptr=self._flat.ptr + 4 * off, _base=self._flat)
                 c.lib.vms_memcpy_d2d(dst.ptr, gc.ptr, 4 * w.size, c.stream)
-                flat.append((w, dst))
+                flat.append((w, dst, None))
                 off += w.size
             self.group.allreduce_sum_device_(self._flat.ptr, total, c.stream)
             todo, scale = flat, 1.0 / self.group.world
-        for w, g in todo:
+        o = self.opt
+        table, keep = [], []
+        for w, g, mask in todo:
             st = self.state.get(id(w))
             if st is None:
                 st = self.state[id(w)] = (w, Tensor.zeros(w.shape), Tensor.zeros(w.shape))
-            o = self.opt
             if w.contiguous and g.contiguous:
-                c.lib.vms_adam_step(w.ptr, g.ptr, 1, scale, st[1].ptr, st[2].ptr, w.size, self.t, o.learning_rate, o.beta_1, o.beta_2,
-                                    o.epsilon, c.stream)
+                # every contiguous weight tensor of the model in ONE launch (vms_adam_step_multi: the path is launch-bound)
+                table.append(_abi.AdamTensor(w.ptr, g.ptr, None if mask is None else mask.ptr, st[1].ptr, st[2].ptr, w.size))
+                keep.append(g)
             else:  # a weight that is a strided view of a flat buffer: update a contiguous copy and write it back
+                if mask is not None:
+                    c.lib.vms_mul_inplace(g.ptr, mask.ptr, g.size, c.stream)
                 wc, gc = w.contig(), g.contig()
                 c.lib.vms_adam_step(wc.ptr, gc.ptr, 1, scale, st[1].ptr, st[2].ptr, w.size, self.t, o.learning_rate, o.beta_1,
                                     o.beta_2, o.epsilon, c.stream)
                 it = 4
                 c.lib.vms_memcpy2d_d2d(w.ptr, w.ld * it, wc.ptr, wc.ld * it, w.shape[-1] * it, w.shape[0], c.stream)
+        if table:
+            arr = (_abi.AdamTensor * len(table))(*table)
+            c.lib.vms_adam_step_multi(arr, len(table), scale, self.t, o.learning_rate, o.beta_1, o.beta_2, o.epsilon, c.stream)
         _abi.bump_param_epoch()
         tape.release()
         return loss

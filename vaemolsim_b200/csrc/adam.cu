@@ -23,6 +23,27 @@ __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__
   theta[i] = theta[i] - lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// Every weight tensor of a model in ONE launch (the op-by-op training path is bound by its launch count: a Keras model has
+// a kernel and a bias per layer).  blockIdx.y = tensor; an optional 0 / 1 mask multiplies the gradient first (the MADE
+// constraint of tfp's AutoregressiveNetwork: masked kernel entries stay zero).
+struct AdamMulti {
+  vms_adam_tensor t[VMS_ADAM_MULTI_MAX];
+};
+__global__ void adam_multi_kernel(const AdamMulti a, float grad_scale, float lr_t, float one_minus_b1, float one_minus_b2,
+                                  float eps) {
+  const vms_adam_tensor& t = a.t[blockIdx.y];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = t.grad[i];
+    if (t.mask) gi *= t.mask[i];
+    gi *= grad_scale;
+    const float mi = t.m[i] + (gi - t.m[i]) * one_minus_b1;
+    const float vi = t.v[i] + (gi * gi - t.v[i]) * one_minus_b2;
+    t.m[i] = mi;
+    t.v[i] = vi;
+    t.theta[i] = t.theta[i] - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
 }  // namespace vms
 
 using namespace vms;
@@ -39,6 +60,32 @@ vms_status vms_adam_step(float* theta, const float* g, int n_partials, float gra
       theta, g, n_partials, n, grad_scale, m, v, n, (float)lr_t, (float)(1.0 - beta1),
       (float)(1.0 - beta2), (float)eps);
   VMS_LAUNCH_CHECK("adam_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_adam_step_multi(const vms_adam_tensor* tensors, int n_tensors, float grad_scale, int64_t t, double lr,
+                               double beta1, double beta2, double eps, vms_stream stream) {
+  VMS_REQUIRE(n_tensors >= 0 && t >= 1, VMS_ERR_INVALID_ARG, "adam_step_multi: bad arguments");
+  VMS_REQUIRE(n_tensors == 0 || tensors, VMS_ERR_INVALID_ARG, "adam_step_multi: NULL tensor table");
+  const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t));
+  for (int base = 0; base < n_tensors; base += VMS_ADAM_MULTI_MAX) {
+    const int cnt = n_tensors - base < VMS_ADAM_MULTI_MAX ? n_tensors - base : VMS_ADAM_MULTI_MAX;
+    AdamMulti a = {};
+    int64_t n_max = 0;
+    for (int k = 0; k < cnt; ++k) {
+      const vms_adam_tensor& e = tensors[base + k];
+      VMS_REQUIRE(e.n >= 0 && (e.n == 0 || (e.theta && e.grad && e.m && e.v)), VMS_ERR_INVALID_ARG,
+                  "adam_step_multi: NULL pointer in tensor %d", base + k);
+      a.t[k] = e;
+      if (e.n > n_max) n_max = e.n;
+    }
+    if (n_max == 0) continue;
+    int64_t bx = (n_max + 255) / 256;
+    if (bx > 1024) bx = 1024;  // grid-stride beyond
+    adam_multi_kernel<<<dim3((unsigned)bx, (unsigned)cnt), 256, 0, as_stream(stream)>>>(
+        a, grad_scale, (float)lr_t, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps);
+    VMS_LAUNCH_CHECK("adam_multi_kernel");
+  }
   return VMS_OK;
 }
 
