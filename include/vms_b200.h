@@ -348,13 +348,13 @@ int64_t vms_elbo_param_count(const vms_elbo_desc* desc);
  * <= 227 KB) and an UNFUSED one (per-layer kernels replayed as a CUDA graph; any shape).  mode 0 = auto, 1 = force
  * the unfused float32-FFMA path (used by the tests to cross-check the paths on the device), 2 = the unfused plan with
  * every RealNVP coupling block (flows.py:184-207 conditioner + spline, forward and reverse mode) as ONE tcgen05
- * kernel per block (flow_tc.cu: 3 x TF32, accumulators in TMEM, hidden layer and raw spline parameters never leave
+ * kernel per block (flow_tc.cu: 3 x BF16 split, accumulators in TMEM, hidden layer and raw spline parameters never leave
  * the SM) -- the large-batch configuration; VMS_ERR_UNSUPPORTED when a block's shape does not fit (one transformed
  * dimension, <= 4 conditioner columns, 8 <= flow hidden <= 111, num_bins <= 32 and a multiple of 4, encoder / decoder
  * widths dx, dz <= 7, 2 dx, 2 dz <= 16, hidden <= 240).
  * mode 3 = whole-step tensor-core kernel (elbo_tcf.cu: all coupling blocks on tcgen05 + encoder / decoder of a 32-row tile
- * in one persistent kernel; forward+backward / train_step only, B <= 32 x #SMs); AUTO mode takes it for those calls whenever
- * the shape fits (VMS_TCF_AUTO=0 disables).  Its weight images (pre-split heads matrices, transposed MLP weights) are
+ * in one kernel; forward+backward / train_step only, B <= 3 x 32 x #SMs: up to three waves of one-tile CTAs); AUTO mode takes
+ * it for those calls whenever the shape fits (VMS_TCF_AUTO=0 disables; an explicit tc_auto_batch threshold wins).  Its weight images (pre-split heads matrices, transposed MLP weights) are
  * written by the Adam update of the previous vms_elbo_train_step; call vms_elbo_plan_invalidate after changing theta by any
  * other means between two train steps (forward_backward always re-packs).
  * mode 4 = force the single FFMA fused kernel (elbo_fused.cu) for every call it supports (float32 FFMA cross-check).
@@ -368,7 +368,8 @@ vms_status vms_elbo_plan_tc_status(vms_elbo_plan plan, int* err);
 int vms_elbo_plan_path(vms_elbo_plan plan, int64_t B);
 /* The plan's packed weight images no longer describe theta (host-side assignment between two train steps). */
 vms_status vms_elbo_plan_invalidate(vms_elbo_plan plan);
-/* Batch from which mode 0 prefers the mode-2 plan over the single fused kernel (default: see DESIGN.md). */
+/* Batch from which mode 0 prefers the mode-2 plan over the fused kernels (default: above one wave of 32-row tiles for the
+ * FFMA kernel, above three waves for the whole-step tensor-core kernel; an explicit value applies to both). */
 vms_status vms_elbo_plan_set_tc_auto_batch(vms_elbo_plan plan, int64_t batch);
 /* Measurement aid (bench.py's roofline leg): with max_launches > 0 the fused path brackets its main kernel with CUDA
  * events on the launching stream for the next max_launches calls; vms_elbo_plan_kernel_ms synchronises, returns the

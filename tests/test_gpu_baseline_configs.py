@@ -72,18 +72,21 @@ def test_c2_exact_shape_every_plan_vs_float64_oracle(vms, mode, name):
             assert_close(fw[k].numpy(), out[k], rtol=1e-5, atol=3e-5, what='C2 %s %s' % (name, k))
 
 
-def test_c5_shard_tensor_core_plan_10007_rows_vs_float64_oracle(vms):
-    """The large-batch (auto-selected tensor-core) plan at the C2 widths with a ragged last tile: B = 10,007, float64
-    oracle on all rows."""
+@pytest.mark.parametrize('B,mode,name', [(10007, 2, 'tensor-core'), (10007, 0, 'tensor-core-fused'),
+                                         (14239, 0, 'tensor-core')])
+def test_c5_shard_large_batch_plans_vs_float64_oracle(vms, B, mode, name):
+    """The plans that serve batches beyond one wave of tiles, at the C2 widths with a ragged last tile, float64 oracle on
+    all rows: the per-block tensor-core plan (forced at B = 10,007, auto-selected above three waves of 32-row tiles) and
+    the whole-step tensor-core kernel running three tiles per SM (auto at B = 10,007 = 313 tiles on 148 SMs)."""
     v = vms
     P = _c2_params(seed=2011)
-    B = 10007
     rng = np.random.default_rng(B)
     x = rng.standard_normal((B, 6), dtype=np.float32)
     eps = rng.standard_normal((B, 2), dtype=np.float32)
     f = vae_from_oracle(v, P, max_batch=B, weight=0.7).fused(B)
-    assert f.path(B) == 'tensor-core'  # auto mode
-    _check_against_float64_oracle(f, v, P, x, eps, 0.7, 'C5-shard B=10007 (auto: tensor-core plan)')
+    f.set_mode(mode)
+    assert f.path(B) == name
+    _check_against_float64_oracle(f, v, P, x, eps, 0.7, 'C5-shard B=%d (%s)' % (B, name))
     assert not f.tc_status()
 
 

@@ -430,7 +430,9 @@ static bool use_tcf(const vms_elbo_plan_s* pl, int64_t B) {
     const char* e = getenv("VMS_TCF_AUTO");
     auto_on = (e && e[0] == '0') ? 0 : 1;
   }
-  return pl->mode == 0 && auto_on && !(pl->tc_ok && B >= pl->tc_auto_batch);
+  // the kernel stays ahead of the per-block tensor-core plan for up to three waves of its one-tile CTAs (tcf_create sizes
+  // max_tiles accordingly); an explicit VMS_TC_AUTO_BATCH / vms_elbo_plan_set_tc_auto_batch still wins
+  return pl->mode == 0 && auto_on && !(pl->tc_ok && pl->tc_auto_user && B >= pl->tc_auto_batch);
 }
 
 extern "C" {
@@ -479,7 +481,7 @@ vms_status vms_elbo_plan_create(const vms_elbo_desc* desc, vms_elbo_plan* plan) 
   pl->tc_auto_batch = 32 * (int64_t)sm_count() + 1;
   if (const char* e = getenv("VMS_TC_AUTO_BATCH")) {  // auto mode switches to the tensor-core plan from this batch on
     const long long v = atoll(e);
-    if (v >= 64) pl->tc_auto_batch = v;
+    if (v >= 64) { pl->tc_auto_batch = v; pl->tc_auto_user = true; }
   }
   if (pl->tc_ok) {
     A_(pl->tc_part, (size_t)2 * sm_count() * pl->off.total);
@@ -546,6 +548,7 @@ int vms_elbo_plan_path(vms_elbo_plan pl, int64_t B) {
 vms_status vms_elbo_plan_set_tc_auto_batch(vms_elbo_plan pl, int64_t batch) {
   VMS_REQUIRE(pl && batch >= 64, VMS_ERR_INVALID_ARG, "elbo_plan_set_tc_auto_batch: NULL plan or batch < 64");
   pl->tc_auto_batch = batch;
+  pl->tc_auto_user = true;
   return VMS_OK;
 }
 

@@ -84,6 +84,7 @@ struct vms_elbo_plan_s {
   float* tc_part = nullptr;
   int* tc_err = nullptr;
   int64_t tc_auto_batch = 8192;
+  bool tc_auto_user = false;  // threshold set by the caller / environment (overrides the whole-step kernel's multi-wave range)
   vms::TcfCfg* tcf = nullptr;  // whole-step tensor-core kernel; NULL when the shape does not fit
 };
 

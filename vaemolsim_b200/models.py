@@ -447,15 +447,15 @@ class FusedELBO(object):
             ctx().lib.vms_elbo_plan_invalidate(self.handle)
 
     def set_mode(self, mode):
-        """0 = auto (whole-step tensor-core kernel for training steps that fit one wave, the FFMA fused kernel for forward
+        """0 = auto (whole-step tensor-core kernel for training steps up to three waves of tiles, the FFMA fused kernel for forward
         evaluation, the tensor-core plan above), 1 = force the unfused per-layer float32-FFMA graph path, 2 = unfused plan
         with the coupling blocks as fused tcgen05 kernels (the large-batch configuration), 3 = force the whole-step
         tensor-core kernel, 4 = force the single FFMA fused kernel."""
         ctx().lib.vms_elbo_plan_set_mode(self.handle, int(mode))
 
     def set_tc_auto_batch(self, batch):
-        """Batch from which auto mode (0) prefers the tensor-core plan over the single fused kernel (default: one wave
-        of 32-row tiles, 32 x #SMs + 1)."""
+        """Batch from which auto mode (0) prefers the tensor-core plan over the fused kernels (default: above one wave of
+        32-row tiles for the FFMA kernel, above three waves for the whole-step tensor-core kernel)."""
         ctx().lib.vms_elbo_plan_set_tc_auto_batch(self.handle, int(batch))
 
     def path(self, batch):
