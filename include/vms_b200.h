@@ -549,6 +549,56 @@ vms_status vms_add_scalar(float* dst, int64_t n, const float* scalar, float alph
 vms_status vms_mul_inplace(float* dst, const float* src, int64_t n, vms_stream stream);
 vms_status vms_sum_all(const float* src, int64_t n, float alpha, float* out, vms_stream stream);
 
+/* ------------------------------------------------------------ geometric-algebra attention over a selected point cloud
+ * mappings.py:480-561 (AttentionBlock), :564-688 (ParticleEmbedding): the arithmetic of
+ * geometric_algebra_attention.keras.VectorAttention(score_net, value_net, reduce, merge_fun='concat', join_fun='concat',
+ * rank=2) (mappings.py:518-525, :633-647; third-party, unpinned, restated in oracle/gaa.py) and of
+ * tf.keras.layers.LayerNormalization / Masking.  Pair tensors are [B, n(i), n(j), .]: entry (i, j) belongs to the geometric
+ * product r_j * r_i; reduce = 0 sums over j for every i ([B, n, D]), reduce = 1 over all pairs of a cloud ([B, D]).
+ *   vms_gaa_zero_mask         Masking(mask_value=0).compute_mask: mask[p] = any(coords[p, :] != 0)
+ *   vms_gaa_pair_invariants   out[b, i, j, :] = (r_j . r_i, |r_j ^ r_i|)     (vecvec + vecvec_invariants, TF op order)
+ *   vms_layernorm_forward     y = act(LayerNormalization(x)) over the last axis of [R, H] (biased variance, epsilon inside the
+ *                             square root); stats [R, 2] = (mean, 1 / sqrt(var + eps)) for the reverse mode (nullable)
+ *   vms_layernorm_backward    g_x += ..., g_gamma += ..., g_beta += ... (column sums over per-CTA partials, fixed order; H <= 128)
+ *   vms_gaa_pair_merge        out[b, i, j, :] = u[b, j, :] + w[b, i, :]  (u = v merge_kernel_0, w = v merge_kernel_1)
+ *   vms_gaa_pair_merge_backward   g_u[b, p, :] += sum_i g[b, i, p, :],  g_w[b, p, :] += sum_j g[b, p, j, :]
+ *   vms_gaa_attend            scores [B, n, n] (pairs with a masked member: -1e9) -> softmax (per row / per cloud) ->
+ *                             out = sum attention x values [B, n, n, D]; attention [B, n, n] is kept for the reverse mode
+ *   vms_gaa_attend_backward   g_scores += att (g_out . values - sum att g_out . values) (0 at masked pairs), g_values += att g_out
+ *   vms_gaa_attention_forward ONE kernel for a whole VectorAttention layer (inference / sampling path): a thread owns a pair
+ *                             from its invariants to its score, weights are shared-memory broadcasts, online softmax; no pair
+ *                             tensor reaches HBM.  D <= 32, H <= 64 (vms_gaa_attention_forward_supported), else
+ *                             VMS_ERR_UNSUPPORTED and the caller composes the kernels above with vms_dense_forward.      */
+typedef struct vms_gaa_weights {
+  const float* merge0; const float* merge1;           /* merge_kernel_0 / _1 [D, D] */
+  const float* join1; const float* join2;             /* join_kernel_1 (invariant values) / _2 (merged values) [D, D] */
+  const float* score_w1; const float* score_b1;       /* score_net: Dense(H, act) [D, H], [H] */
+  const float* score_w2; const float* score_b2;       /*            Dense(1)      [H, 1], [1] */
+  const float* value_w1; const float* value_b1;       /* value_net: Dense(H) [2, H], [H] */
+  const float* value_gamma; const float* value_beta;  /*            LayerNormalization [H], [H]; then Activation */
+  const float* value_w2; const float* value_b2;       /*            Dense(D) [H, D], [D] */
+} vms_gaa_weights;
+vms_status vms_gaa_zero_mask(const float* coords, int64_t n_particles, uint8_t* mask, vms_stream stream);
+vms_status vms_gaa_pair_invariants(const float* coords, int64_t B, int n, float* out, vms_stream stream);
+vms_status vms_layernorm_forward(const float* x, int64_t ld_x, int64_t R, int H, const float* gamma, const float* beta,
+                                 float eps, int act, float* y, int64_t ld_y, float* stats, vms_stream stream);
+size_t vms_layernorm_backward_workspace(int64_t R, int H);
+vms_status vms_layernorm_backward(const float* x, int64_t ld_x, int64_t R, int H, const float* gamma, const float* stats,
+                                  int act, const float* y, int64_t ld_y, const float* g_y, int64_t ld_gy, float* g_x,
+                                  int64_t ld_gx, float* g_gamma, float* g_beta, void* workspace, vms_stream stream);
+vms_status vms_gaa_pair_merge(const float* u, int64_t ld_u, const float* w, int64_t ld_w, int64_t B, int n, int D, float* out,
+                              vms_stream stream);
+vms_status vms_gaa_pair_merge_backward(const float* g, int64_t B, int n, int D, float* g_u, int64_t ld_gu, float* g_w,
+                                       int64_t ld_gw, vms_stream stream);
+vms_status vms_gaa_attend(const float* scores, const float* values, const uint8_t* mask, int64_t B, int n, int D, int reduce,
+                          float* out, float* attention, vms_stream stream);
+vms_status vms_gaa_attend_backward(const float* attention, const float* values, const uint8_t* mask, int64_t B, int n, int D,
+                                   int reduce, const float* g_out, float* g_scores, float* g_values, vms_stream stream);
+int vms_gaa_attention_forward_supported(int n, int D, int H);
+vms_status vms_gaa_attention_forward(const float* coords, const float* values, int64_t ld_v, const uint8_t* mask, int64_t B,
+                                     int n, int D, int H, const vms_gaa_weights* w, int reduce, int act, float ln_eps,
+                                     float* out, vms_stream stream);
+
 /* ------------------------------------------------------------------------------- machine-peak probes (measurement aid)
  * The denominators of this repo's compute-bound roofline fractions, measured on the device they are quoted for
  * (BASELINE.md section 2 asks for them; `bench.py` runs them live and `scripts/measure_peaks.py` writes profiles/*.json):

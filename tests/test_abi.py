@@ -34,12 +34,13 @@ def test_struct_layouts_match_header():
     """ctypes mirrors of the by-pointer structs have the sizes a C compiler gives the header's definitions."""
     import ctypes
     from vaemolsim_b200 import _abi
-    code = '#include <stdio.h>\n#include "vms_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(vms_rqs_args), ' \
-           'sizeof(vms_rqs_bwd_args), sizeof(vms_elbo_desc));return 0;}'
+    code = '#include <stdio.h>\n#include "vms_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(vms_rqs_args), ' \
+           'sizeof(vms_rqs_bwd_args), sizeof(vms_elbo_desc), sizeof(vms_gaa_weights));return 0;}'
     exe = '/tmp/vms_sizes'
     subprocess.run(['gcc', '-x', 'c', '-', '-I', os.path.join(ROOT, 'include'), '-o', exe], input=code, text=True, check=True)
     sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
-    assert sizes == [ctypes.sizeof(_abi.RqsArgs), ctypes.sizeof(_abi.RqsBwdArgs), ctypes.sizeof(_abi.ElboDesc)]
+    assert sizes == [ctypes.sizeof(_abi.RqsArgs), ctypes.sizeof(_abi.RqsBwdArgs), ctypes.sizeof(_abi.ElboDesc),
+                     ctypes.sizeof(_abi.GaaWeights)]
 
 
 def test_no_cpu_fallback_without_device():

@@ -63,6 +63,12 @@ class AdamTensor(C.Structure):
     _fields_ = [('theta', c_vp), ('grad', c_vp), ('mask', c_vp), ('m', c_vp), ('v', c_vp), ('n', c_i64)]
 
 
+class GaaWeights(C.Structure):
+    """vms_gaa_weights (include/vms_b200.h): device pointers of one VectorAttention layer."""
+    _fields_ = [(k, c_vp) for k in ('merge0', 'merge1', 'join1', 'join2', 'score_w1', 'score_b1', 'score_w2', 'score_b2',
+                                    'value_w1', 'value_b1', 'value_gamma', 'value_beta', 'value_w2', 'value_b2')]
+
+
 class ElboDesc(C.Structure):
     _fields_ = [('dx', C.c_int32), ('dz', C.c_int32), ('hidden', C.c_int32), ('num_blocks', C.c_int32),
                 ('num_bins', C.c_int32), ('flow_hidden', C.c_int32), ('bin_min', c_f32), ('bin_max', c_f32),
@@ -188,6 +194,19 @@ _SIGS = {
     'vms_add_scalar': (None, [c_vp, c_i64, c_vp, c_f32, c_vp]),
     'vms_mul_inplace': (None, [c_vp, c_vp, c_i64, c_vp]),
     'vms_sum_all': (None, [c_vp, c_i64, c_f32, c_vp, c_vp]),
+    'vms_gaa_zero_mask': (None, [c_vp, c_i64, c_vp, c_vp]),
+    'vms_gaa_pair_invariants': (None, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    'vms_layernorm_forward': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_f32, c_int, c_vp, c_i64, c_vp, c_vp]),
+    'vms_layernorm_backward_workspace': (c_size, [c_i64, c_int]),
+    'vms_layernorm_backward': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp,
+                                      c_vp, c_vp, c_vp]),
+    'vms_gaa_pair_merge': (None, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
+    'vms_gaa_pair_merge_backward': (None, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    'vms_gaa_attend': (None, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    'vms_gaa_attend_backward': (None, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'vms_gaa_attention_forward_supported': (c_int, [c_int, c_int, c_int]),
+    'vms_gaa_attention_forward': (None, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, C.POINTER(GaaWeights), c_int,
+                                         c_int, c_f32, c_vp, c_vp]),
     'vms_probe_ffma': (None, [c_int, c_int, C.POINTER(c_f64), C.POINTER(c_f64), c_vp]),
     'vms_probe_mma': (None, [c_int, c_int, c_int, c_int, c_int, C.POINTER(c_f64), C.POINTER(c_f64), c_vp]),
     'vms_elbo_forward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -199,36 +199,123 @@ class Dense(Layer):
         self._weights = [self.kernel] + ([self.bias] if self.use_bias else [])
 
     def call(self, x, ones_input=False, cond=None, cond_kernel=None):
+        if not ones_input and x.shape[1] != self.kernel.shape[0]:
+            raise ValueError('Dense %s expects last dimension %d, got %d' % (self.name, self.kernel.shape[0], x.shape[1]))
+        return dense_op(x, self.kernel, self.bias, self.act, ones_input=ones_input, cond=cond, cond_kernel=cond_kernel)
+
+
+def dense_op(x, W, bias=None, act=0, ones_input=False, cond=None, cond_kernel=None):
+    """act(x @ W + bias + cond @ cond_kernel) on the device (vms_dense_forward), recorded on the active tape
+    (vms_dense_backward: input, kernel, bias and conditional-input / conditional-kernel gradients, as TF autodiff)."""
+    c = ctx()
+    B = x.shape[0]
+    K, N = W.shape[0], W.shape[1]
+    out = Tensor((B, N))
+    xp, ldx = (None, 1) if ones_input else (x.ptr, x.ld)
+    Cn = 0 if cond is None else cond.shape[1]
+    c.lib.vms_dense_forward(xp, ldx, W.ptr, _ptr(bias), B, K, N, act, _ptr(cond), 0 if cond is None else cond.ld,
+                            _ptr(cond_kernel), Cn, out.ptr, out.ld, c.stream)
+    tp = _tape()
+    if tp is not None:
+
+        def bw():
+            if not tp.has(out):
+                return
+            g_out = tp.grad(out)
+            ws = Tensor((max(int(c.lib.vms_dense_backward_workspace(B, K, N, Cn)) // 4, 1), ))
+            g_x = None if ones_input else tp.grad(x)
+            g_c = Tensor((B, Cn)) if cond is not None else None  # (the kernel overwrites g_cond: accumulate below)
+            c.lib.vms_dense_backward(xp, ldx, W.ptr, B, K, N, act, out.ptr, out.ld, g_out.ptr, g_out.ld, _ptr(cond),
+                                     0 if cond is None else cond.ld, _ptr(cond_kernel), Cn, _ptr(g_x),
+                                     0 if g_x is None else g_x.ld, 1, tp.grad(W).ptr,
+                                     None if bias is None else tp.grad(bias).ptr, _ptr(g_c), Cn,
+                                     None if cond_kernel is None else tp.grad(cond_kernel).ptr, 1, ws.ptr, c.stream)
+            if g_c is not None:
+                _ad().add_into(tp.grad(cond), g_c, 1.0)
+
+        tp.record(bw)
+    return out
+
+
+class LayerNormalization(Layer):
+    """tf.keras.layers.LayerNormalization() over the last axis (Keras defaults: epsilon 1e-3, gamma 1, beta 0), optionally
+    with the `tf.keras.layers.Activation` that follows it in the reference's networks (mappings.py:511-512) folded into the
+    same kernel (vms_layernorm_forward / _backward)."""
+
+    def __init__(self, epsilon=1e-3, name='layer_normalization'):
+        super(LayerNormalization, self).__init__(name=name)
+        self.epsilon = float(epsilon)
+        self.gamma = self.beta = None
+
+    def build(self, input_shape):
+        H = int(input_shape[-1])
+        self.gamma, self.beta = Tensor.from_numpy(np.ones(H, np.float32)), Tensor.zeros((H,))
+        self._weights = [self.gamma, self.beta]
+
+    def call(self, x, activation=0):
         c = ctx()
-        B = x.shape[0]
-        K = self.kernel.shape[0]
-        out = Tensor((B, self.units))
-        xp, ldx = (None, 1) if ones_input else (x.ptr, x.ld)
-        if not ones_input and x.shape[1] != K:
-            raise ValueError('Dense %s expects last dimension %d, got %d' % (self.name, K, x.shape[1]))
-        Cn = 0 if cond is None else cond.shape[1]
-        c.lib.vms_dense_forward(xp, ldx, self.kernel.ptr, _ptr(self.bias), B, K, self.units, self.act, _ptr(cond),
-                                0 if cond is None else cond.ld, _ptr(cond_kernel), Cn, out.ptr, out.ld, c.stream)
+        R, H = x.shape
+        y, stats = Tensor((R, H)), Tensor((R, 2))
+        c.lib.vms_layernorm_forward(x.ptr, x.ld, R, H, self.gamma.ptr, self.beta.ptr, self.epsilon, activation, y.ptr, y.ld,
+                                    stats.ptr, c.stream)
         tp = _tape()
         if tp is not None:
-            W, bias, act, N = self.kernel, self.bias, self.act, self.units
+            gamma, beta = self.gamma, self.beta
 
-            def bw():  # TF autodiff through Dense: input, kernel, bias and conditional-input / conditional-kernel gradients
-                if not tp.has(out):
+            def bw():
+                if not tp.has(y):
                     return
-                g_out = tp.grad(out)
-                ws = Tensor((max(int(c.lib.vms_dense_backward_workspace(B, K, N, Cn)) // 4, 1), ))
-                g_x = None if ones_input else tp.grad(x)
-                g_c = Tensor((B, Cn)) if cond is not None else None  # (the kernel overwrites g_cond: accumulate below)
-                c.lib.vms_dense_backward(xp, ldx, W.ptr, B, K, N, act, out.ptr, out.ld, g_out.ptr, g_out.ld, _ptr(cond),
-                                         0 if cond is None else cond.ld, _ptr(cond_kernel), Cn, _ptr(g_x),
-                                         0 if g_x is None else g_x.ld, 1, tp.grad(W).ptr,
-                                         None if bias is None else tp.grad(bias).ptr, _ptr(g_c), Cn,
-                                         None if cond_kernel is None else tp.grad(cond_kernel).ptr, 1, ws.ptr, c.stream)
-                if g_c is not None:
-                    _ad().add_into(tp.grad(cond), g_c, 1.0)
+                ws = Tensor((max(int(c.lib.vms_layernorm_backward_workspace(R, H)) // 4, 1), ))
+                g_y, g_x = tp.grad(y), tp.grad(x)
+                c.lib.vms_layernorm_backward(x.ptr, x.ld, R, H, gamma.ptr, stats.ptr, activation, y.ptr, y.ld, g_y.ptr, g_y.ld,
+                                             g_x.ptr, g_x.ld, tp.grad(gamma).ptr, tp.grad(beta).ptr, ws.ptr, c.stream)
 
             tp.record(bw)
+        return y
+
+
+class Activation(Layer):
+    """tf.keras.layers.Activation(fn); inside a `Sequential` it is folded into the LayerNormalization before it."""
+
+    def __init__(self, activation, name='activation'):
+        super(Activation, self).__init__(name=name)
+        self.act = _act_code(activation)
+        self._weights = []
+
+    def call(self, x):
+        if self.act == 0:
+            return x
+        raise NotImplementedError('a stand-alone Activation layer is only supported directly after LayerNormalization')
+
+
+class Sequential(Layer):
+    """tf.keras.models.Sequential over Dense / LayerNormalization / Activation layers acting on the last axis of a 2-D
+    tensor (the score / value / nonlinearity networks of mappings.py:505-532)."""
+
+    def __init__(self, layers, name='sequential'):
+        super(Sequential, self).__init__(name=name)
+        self.layers = list(layers)
+
+    def build(self, input_shape):
+        shape = tuple(input_shape)
+        for lay in self.layers:
+            if not lay.built:
+                lay.build(shape)
+                lay.built = True
+            if isinstance(lay, Dense):
+                shape = shape[:-1] + (lay.units,)
+
+    def call(self, x):
+        out, skip = x, False
+        for i, lay in enumerate(self.layers):
+            if skip:
+                skip = False
+                continue
+            nxt = self.layers[i + 1] if i + 1 < len(self.layers) else None
+            if isinstance(lay, LayerNormalization) and isinstance(nxt, Activation):
+                out, skip = lay.call(out, activation=nxt.act), True
+            else:
+                out = lay.call(out)
         return out
 
 

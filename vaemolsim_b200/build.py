@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvms_b200.so')
-SOURCES = ['runtime.cu', 'rqs.cu', 'rqs_stream.cu', 'dense.cu', 'gemm_tc.cu', 'flow_tc.cu', 'mlp_stream.cu', 'logprob.cu', 'reduce.cu', 'batchnorm.cu', 'distsel.cu', 'mcmc.cu', 'adam.cu', 'elbo.cu', 'elbo_fused.cu', 'elbo_tcf.cu', 'mc_fused.cu', 'mc_chain.cu', 'mc_nb.cu', 'peer.cu', 'probe.cu', 'autodiff.cu']
+SOURCES = ['runtime.cu', 'rqs.cu', 'rqs_stream.cu', 'dense.cu', 'gemm_tc.cu', 'flow_tc.cu', 'mlp_stream.cu', 'logprob.cu', 'reduce.cu', 'batchnorm.cu', 'distsel.cu', 'mcmc.cu', 'adam.cu', 'elbo.cu', 'elbo_fused.cu', 'elbo_tcf.cu', 'mc_fused.cu', 'mc_chain.cu', 'mc_nb.cu', 'peer.cu', 'probe.cu', 'autodiff.cu', 'gaa.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',

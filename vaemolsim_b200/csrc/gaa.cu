@@ -1,0 +1,792 @@
+// gaa.cu -- rank-2 geometric-algebra vector attention over a selected point cloud (mappings.py:480-688: AttentionBlock /
+// ParticleEmbedding; arithmetic of geometric_algebra_attention.VectorAttention(rank=2, merge_fun='concat',
+// join_fun='concat') and Keras LayerNormalization, restated in oracle/gaa.py -- parity unpinned, the package is not vendored).
+//
+// Pair tensors are laid out [B, n(i), n(j), .]: entry (i, j) belongs to the geometric product r_j * r_i, output row i sums
+// over j (reduce = 0) or the cloud sums over all (i, j) (reduce = 1).
+//
+// Two implementations:
+//   * op-by-op kernels the host tape composes with vms_dense_forward / _backward (training, any width):
+//       vms_gaa_pair_invariants, vms_layernorm_forward / _backward, vms_gaa_pair_merge / _backward,
+//       vms_gaa_attend / _backward -- pair tensors live in HBM, every reduction in a fixed order;
+//   * vms_gaa_attention_forward: ONE kernel per attention layer (inference / sampling): a thread owns a pair from its two
+//     invariants to its score, weights are shared-memory broadcasts, the softmax is accumulated online (running max / sum /
+//     weighted value per thread, merged per output row in a fixed order) -- no pair tensor ever reaches HBM.
+#include "common.cuh"
+#include "dense.cuh"
+
+namespace vms {
+namespace {
+
+constexpr float kMaskedScore = -1e9f;  // geometric_algebra_attention: masked logits
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  return act == VMS_ACT_RELU ? fmaxf(x, 0.f) : (act == VMS_ACT_TANH ? tanhf(x) : x);
+}
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+  return act == VMS_ACT_RELU ? (y > 0.f ? 1.f : 0.f) : (act == VMS_ACT_TANH ? 1.f - y * y : 1.f);
+}
+
+// (r_j . r_i, |r_j ^ r_i|) with TF's op order: nine separate products, then sums (no contraction)
+__device__ __forceinline__ void pair_invariants(const float* a, const float* b, float& dot, float& nrm) {
+  dot = __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
+  const float xy = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
+  const float xz = __fsub_rn(__fmul_rn(a[0], b[2]), __fmul_rn(a[2], b[0]));
+  const float yz = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
+  nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(xy, xy), __fmul_rn(xz, xz)), __fmul_rn(yz, yz)));
+}
+
+__global__ void gaa_pair_inv_kernel(const float* __restrict__ coords, int64_t total, int n, float* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int j = (int)(p % n);
+  const int64_t bi = p / n;
+  const int i = (int)(bi % n);
+  const int64_t b = bi / n;
+  float dot, nrm;
+  pair_invariants(coords + (b * n + j) * 3, coords + (b * n + i) * 3, dot, nrm);
+  reinterpret_cast<float2*>(out)[p] = make_float2(dot, nrm);
+}
+
+// ------------------------------------------------------------------------------------------------- layer normalisation
+// eight lanes per row: lane l owns columns l, l + 8, ...; row sums = ascending per lane, then xor 4, 2, 1
+constexpr int LNG = 8;
+
+__device__ __forceinline__ float group_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int H,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float eps, int act, float* __restrict__ y, int64_t ldy,
+                                                            float* __restrict__ stats) {
+  const int64_t row_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LNG;
+  const bool ok = row_raw < R;
+  const int64_t row = ok ? row_raw : R - 1;
+  const int l = threadIdx.x & (LNG - 1);
+  const float* xr = x + row * ldx;
+  float s = 0.f;
+  for (int k = l; k < H; k += LNG) s += xr[k];
+  const float mean = group_sum(s) / (float)H;
+  float q = 0.f;
+  for (int k = l; k < H; k += LNG) {
+    const float d = xr[k] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(group_sum(q) / (float)H + eps);
+  if (!ok) return;
+  float* yr = y + row * ldy;
+  for (int k = l; k < H; k += LNG) yr[k] = act_apply((xr[k] - mean) * rstd * gamma[k] + beta[k], act);
+  if (l == 0 && stats) reinterpret_cast<float2*>(stats)[row] = make_float2(mean, rstd);
+}
+
+// reverse mode: g_x += rstd (dxh - mean(dxh) - xhat mean(dxh xhat)), dxh = g_y act'(y) gamma; per-CTA column partials of
+// d gamma = sum g_pre xhat and d beta = sum g_pre (E = columns per lane, registers)
+template <int E>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int H,
+                                                            const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                            int act, const float* __restrict__ y, int64_t ldy,
+                                                            const float* __restrict__ gy, int64_t ldgy,
+                                                            float* __restrict__ gx, int64_t ldgx, float* __restrict__ part) {
+  extern __shared__ float sm[];  // [32 groups][2 H]
+  const int l = threadIdx.x & (LNG - 1);
+  const int grp = threadIdx.x / LNG;
+  const int groups = blockDim.x / LNG;
+  float ag[E], ab[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) ag[e] = ab[e] = 0.f;
+  const int64_t n_iter = (R + (int64_t)gridDim.x * groups - 1) / ((int64_t)gridDim.x * groups);
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t row_raw = (it * gridDim.x + blockIdx.x) * groups + grp;
+    const bool ok = row_raw < R;
+    const int64_t row = ok ? row_raw : R - 1;
+    const float2 st = reinterpret_cast<const float2*>(stats)[row];
+    const float* xr = x + row * ldx;
+    const float* yr = y + row * ldy;
+    const float* gr = gy + row * ldgy;
+    float dxh[E], xh[E];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = l + e * LNG;
+      dxh[e] = xh[e] = 0.f;
+      if (k < H) {
+        xh[e] = (xr[k] - st.x) * st.y;
+        const float gp = ok ? gr[k] * act_grad_from_out(yr[k], act) : 0.f;
+        ab[e] += gp;
+        ag[e] += gp * xh[e];
+        dxh[e] = gp * gamma[k];
+        s1 += dxh[e];
+        s2 += dxh[e] * xh[e];
+      }
+    }
+    s1 = group_sum(s1) / (float)H;
+    s2 = group_sum(s2) / (float)H;
+    if (ok && gx) {
+      float* gxr = gx + row * ldgx;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int k = l + e * LNG;
+        if (k < H) gxr[k] += st.y * (dxh[e] - s1 - xh[e] * s2);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int k = l + e * LNG;
+    if (k < H) {
+      sm[grp * 2 * H + k] = ag[e];
+      sm[grp * 2 * H + H + k] = ab[e];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < groups; ++g) s += sm[g * 2 * H + c];
+    part[(int64_t)blockIdx.x * 2 * H + c] = s;
+  }
+}
+
+int ln_bwd_grid(int64_t R) {
+  const int64_t want = (R + 31) / 32;
+  const int64_t cap = 2 * (int64_t)sm_count();
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------- merged values of a pair
+// out[b, i, j, :] = u[b, j, :] + w[b, i, :]
+__global__ void gaa_pair_merge_kernel(const float* __restrict__ u, int64_t ldu, const float* __restrict__ w, int64_t ldw,
+                                      int64_t total, int n, int D, float* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int d = (int)(e % D);
+  const int64_t p = e / D;
+  const int j = (int)(p % n);
+  const int64_t bi = p / n;  // b * n + i
+  const int64_t b = bi / n;
+  out[e] = u[(b * n + j) * ldu + d] + w[bi * ldw + d];
+}
+
+// g_u[b, p, :] += sum_i g[b, i, p, :],  g_w[b, p, :] += sum_j g[b, p, j, :]   (ascending order)
+__global__ void gaa_pair_merge_bwd_kernel(const float* __restrict__ g, int64_t total, int n, int D, float* __restrict__ gu,
+                                          int64_t ldgu, float* __restrict__ gw, int64_t ldgw) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [B, n, D]
+  if (e >= total) return;
+  const int d = (int)(e % D);
+  const int64_t bp = e / D;
+  const int p = (int)(bp % n);
+  const int64_t b = bp / n;
+  const float* gb = g + b * n * n * D;
+  float su = 0.f, sw = 0.f;
+  for (int q = 0; q < n; ++q) {
+    su += gb[((int64_t)q * n + p) * D + d];
+    sw += gb[((int64_t)p * n + q) * D + d];
+  }
+  gu[bp * ldgu + d] += su;
+  gw[bp * ldgw + d] += sw;
+}
+
+// ------------------------------------------------------------------------------------------------------- attention
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float masked_score(const float* scores, const uint8_t* mask, int64_t b, int n, int i, int j,
+                                              int64_t idx) {
+  if (mask && !(mask[b * n + i] && mask[b * n + j])) return kMaskedScore;
+  return scores[idx];
+}
+
+// reduce = 0: one warp per output row (b, i): softmax over j, out[b, i, :] = sum_j att_ij val_ij
+__global__ void __launch_bounds__(256) gaa_attend_rows_kernel(const float* __restrict__ scores, const float* __restrict__ val,
+                                                              const uint8_t* __restrict__ mask, int64_t rows, int n, int D,
+                                                              float* __restrict__ out, float* __restrict__ att) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = w / n;
+  const int i = (int)(w % n);
+  float m = -INFINITY;
+  for (int j = lane; j < n; j += 32) m = fmaxf(m, masked_score(scores, mask, b, n, i, j, w * n + j));
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) {
+    const float e = expf(masked_score(scores, mask, b, n, i, j, w * n + j) - m);
+    att[w * n + j] = e;
+    s += e;
+  }
+  s = warp_sum(s);
+  for (int j = lane; j < n; j += 32) att[w * n + j] = att[w * n + j] / s;
+  __syncwarp();
+  for (int d = lane; d < D; d += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) acc += att[w * n + j] * val[(w * n + j) * D + d];
+    out[w * D + d] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) gaa_attend_rows_bwd_kernel(const float* __restrict__ att, const float* __restrict__ val,
+                                                                  const uint8_t* __restrict__ mask, int64_t rows, int n, int D,
+                                                                  const float* __restrict__ g_out, float* __restrict__ g_scores,
+                                                                  float* __restrict__ g_val) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = w / n;
+  const int i = (int)(w % n);
+  const float* go = g_out + w * D;
+  float S = 0.f;
+  for (int j = lane; j < n; j += 32) {
+    float dot = 0.f;
+    for (int d = 0; d < D; ++d) dot += go[d] * val[(w * n + j) * D + d];
+    S += att[w * n + j] * dot;
+  }
+  S = warp_sum(S);
+  for (int j = lane; j < n; j += 32) {
+    const float a = att[w * n + j];
+    float dot = 0.f;
+    for (int d = 0; d < D; ++d) dot += go[d] * val[(w * n + j) * D + d];
+    const bool masked = mask && !(mask[b * n + i] && mask[b * n + j]);
+    if (g_scores && !masked) g_scores[w * n + j] += a * (dot - S);
+    if (g_val)
+      for (int d = 0; d < D; ++d) g_val[(w * n + j) * D + d] += a * go[d];
+  }
+}
+
+// reduce = 1: one CTA per cloud: ONE softmax over all n^2 pairs, out[b, :] = sum_ij att_ij val_ij
+constexpr int AT = 256;
+__device__ float block_reduce(float v, float* red, bool is_max) {
+  const int t = threadIdx.x;
+  red[t] = v;
+  __syncthreads();
+  for (int o = AT / 2; o; o >>= 1) {
+    if (t < o) red[t] = is_max ? fmaxf(red[t], red[t + o]) : red[t] + red[t + o];
+    __syncthreads();
+  }
+  const float r = red[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(AT) gaa_attend_all_kernel(const float* __restrict__ scores, const float* __restrict__ val,
+                                                            const uint8_t* __restrict__ mask, int n, int D,
+                                                            float* __restrict__ out, float* __restrict__ att) {
+  __shared__ float red[AT];
+  __shared__ float part[AT / 32][33];
+  const int64_t b = blockIdx.x;
+  const int t = threadIdx.x;
+  const int N2 = n * n;
+  const int64_t base = b * N2;
+  float m = -INFINITY;
+  for (int p = t; p < N2; p += AT) m = fmaxf(m, masked_score(scores, mask, b, n, p / n, p % n, base + p));
+  m = block_reduce(m, red, true);
+  float s = 0.f;
+  for (int p = t; p < N2; p += AT) {
+    const float e = expf(masked_score(scores, mask, b, n, p / n, p % n, base + p) - m);
+    att[base + p] = e;
+    s += e;
+  }
+  s = block_reduce(s, red, false);
+  for (int p = t; p < N2; p += AT) att[base + p] = att[base + p] / s;
+  __syncthreads();
+  const int c = t >> 5, lane = t & 31;
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    const int d = d0 + lane;
+    float acc = 0.f;
+    if (d < D)
+      for (int p = c; p < N2; p += AT / 32) acc += att[base + p] * val[(base + p) * D + d];
+    part[c][lane] = acc;
+    __syncthreads();
+    if (c == 0 && d < D) {
+      float o = 0.f;
+      for (int k = 0; k < AT / 32; ++k) o += part[k][lane];
+      out[b * D + d] = o;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(AT) gaa_attend_all_bwd_kernel(const float* __restrict__ att, const float* __restrict__ val,
+                                                                const uint8_t* __restrict__ mask, int n, int D,
+                                                                const float* __restrict__ g_out, float* __restrict__ g_scores,
+                                                                float* __restrict__ g_val) {
+  __shared__ float red[AT];
+  const int64_t b = blockIdx.x;
+  const int t = threadIdx.x;
+  const int N2 = n * n;
+  const int64_t base = b * N2;
+  const float* go = g_out + b * D;
+  float S = 0.f;
+  for (int p = t; p < N2; p += AT) {
+    float dot = 0.f;
+    for (int d = 0; d < D; ++d) dot += go[d] * val[(base + p) * D + d];
+    S += att[base + p] * dot;
+  }
+  S = block_reduce(S, red, false);
+  for (int p = t; p < N2; p += AT) {
+    const float a = att[base + p];
+    float dot = 0.f;
+    for (int d = 0; d < D; ++d) dot += go[d] * val[(base + p) * D + d];
+    const bool masked = mask && !(mask[b * n + p / n] && mask[b * n + p % n]);
+    if (g_scores && !masked) g_scores[base + p] += a * (dot - S);
+    if (g_val)
+      for (int d = 0; d < D; ++d) g_val[(base + p) * D + d] += a * go[d];
+  }
+}
+
+__global__ void gaa_zero_mask_kernel(const float* __restrict__ coords, int64_t total, uint8_t* __restrict__ mask) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const float* r = coords + p * 3;
+  mask[p] = (r[0] != 0.f || r[1] != 0.f || r[2] != 0.f) ? 1 : 0;
+}
+
+// ===================================================================================== fused forward (one attention layer)
+// One CTA per cloud (grid-stride).  Shared memory: the layer's weights (zero padded to HP / DP columns, rows 16-byte
+// aligned), coordinates, mask, the per-particle halves of the merged values u = v M0, w = v M1, and the per-thread online
+// softmax states when they are merged.  Thread t owns output row i = t / TPR and walks j = t % TPR, + TPR, ...:
+//   inv(2) -> h = inv Wv1 + bv1 -> LayerNorm -> act -> iv = . Wv2 + bv2 -> joined = iv J1 + (u_j + w_i) J2
+//   -> score = act(joined Ws1 + bs1) Ws2 + bs2  -> running (max, sum, sum of exp x joined).
+template <int HP, int DP>
+struct GaaSmem {
+  // weights (floats)
+  static constexpr int oWv1 = 0;                  // [2][HP]
+  static constexpr int obv1 = oWv1 + 2 * HP;      // [HP]
+  static constexpr int oLg = obv1 + HP;           // [HP]
+  static constexpr int oLb = oLg + HP;            // [HP]
+  static constexpr int oWv2 = oLb + HP;           // [HP][DP]
+  static constexpr int obv2 = oWv2 + HP * DP;     // [DP]
+  static constexpr int oJ1 = obv2 + DP;           // [DP][DP]
+  static constexpr int oJ2 = oJ1 + DP * DP;       // [DP][DP]
+  static constexpr int oWs1 = oJ2 + DP * DP;      // [DP][HP]
+  static constexpr int obs1 = oWs1 + DP * HP;     // [HP]
+  static constexpr int oWs2 = obs1 + HP;          // [HP]
+  static constexpr int oM0 = oWs2 + HP;           // [DP][DP]
+  static constexpr int oM1 = oM0 + DP * DP;       // [DP][DP]
+  static constexpr int nW = oM1 + DP * DP;
+};
+
+struct GaaFwdParams {
+  const float* coords; const float* v; int64_t ldv; const uint8_t* mask;
+  int64_t B; int n, D, H, reduce, act, tpr;
+  const float *M0, *M1, *J1, *J2, *Ws1, *bs1, *Ws2, *bs2, *Wv1, *bv1, *lg, *lb, *Wv2, *bv2;
+  float ln_eps;
+  float* out;
+};
+
+template <int HP, int DP>
+__global__ void __launch_bounds__(256) gaa_attention_fwd_kernel(GaaFwdParams p) {
+  using L = GaaSmem<HP, DP>;
+  extern __shared__ __align__(16) float smem[];
+  float* W = smem;
+  const int n = p.n, D = p.D, H = p.H;
+  float* s_r = W + L::nW;               // [n][3] (+ pad to a multiple of 4)
+  float* s_u = s_r + ((3 * n + 3) & ~3);  // [n][DP]
+  float* s_w = s_u + n * DP;            // [n][DP]
+  float* s_v = s_w + n * DP;            // [n][DP]
+  float* s_st = s_v + n * DP;           // [blockDim][DP + 2] online-softmax states
+  uint8_t* s_m = reinterpret_cast<uint8_t*>(s_st + blockDim.x * (DP + 2));  // [n]
+  const int t = threadIdx.x;
+
+  // weights -> shared memory, zero padded
+  for (int k = t; k < L::nW; k += blockDim.x) W[k] = 0.f;
+  __syncthreads();
+  for (int k = t; k < 2 * H; k += blockDim.x) W[L::oWv1 + (k / H) * HP + k % H] = p.Wv1[k];
+  for (int k = t; k < H; k += blockDim.x) {
+    W[L::obv1 + k] = p.bv1[k];
+    W[L::oLg + k] = p.lg[k];
+    W[L::oLb + k] = p.lb[k];
+    W[L::obs1 + k] = p.bs1[k];
+    W[L::oWs2 + k] = p.Ws2[k];
+  }
+  for (int k = t; k < H * D; k += blockDim.x) W[L::oWv2 + (k / D) * DP + k % D] = p.Wv2[k];
+  for (int k = t; k < D * H; k += blockDim.x) W[L::oWs1 + (k / H) * HP + k % H] = p.Ws1[k];
+  for (int k = t; k < D; k += blockDim.x) W[L::obv2 + k] = p.bv2[k];
+  for (int k = t; k < D * D; k += blockDim.x) {
+    const int o = (k / D) * DP + k % D;
+    W[L::oJ1 + o] = p.J1[k];
+    W[L::oJ2 + o] = p.J2[k];
+    W[L::oM0 + o] = p.M0[k];
+    W[L::oM1 + o] = p.M1[k];
+  }
+  const float bs2 = p.bs2[0];
+  const float inv_H = 1.f / (float)H;
+  const int tpr = p.tpr;
+  const int rows_per_pass = blockDim.x / tpr;
+
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    __syncthreads();
+    for (int k = t; k < 3 * n; k += blockDim.x) s_r[k] = p.coords[b * n * 3 + k];
+    for (int k = t; k < n; k += blockDim.x) s_m[k] = p.mask ? p.mask[b * n + k] : 1;
+    for (int k = t; k < n * DP; k += blockDim.x) {
+      const int q = k / DP, d = k % DP;
+      s_v[k] = d < D ? p.v[(b * n + q) * p.ldv + d] : 0.f;
+    }
+    __syncthreads();
+    for (int k = t; k < n * DP; k += blockDim.x) {  // u = v M0, w = v M1 (contraction ascending, as the Dense kernels)
+      const int q = k / DP, d = k % DP;
+      float su = 0.f, sw = 0.f;
+      for (int c = 0; c < D; ++c) {
+        const float vv = s_v[q * DP + c];
+        su = fmaf(vv, W[L::oM0 + c * DP + d], su);
+        sw = fmaf(vv, W[L::oM1 + c * DP + d], sw);
+      }
+      s_u[k] = su;
+      s_w[k] = sw;
+    }
+    __syncthreads();
+
+    float red_m = -INFINITY, red_l = 0.f;  // reduce = 1: thread 0 accumulates the cloud's state over the passes
+    float red_o = 0.f;                     // (threads 0 .. DP-1 each keep m / l and column t of the weighted sum)
+
+    for (int i0 = 0; i0 < n; i0 += rows_per_pass) {
+      const int i = i0 + t / tpr;
+      const int sub = t % tpr;
+      const bool active = (t / tpr) < rows_per_pass && i < n;
+      float m = -INFINITY, l = 0.f;
+      float acc[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) acc[d] = 0.f;
+      if (active) {
+        const float* ri = s_r + 3 * i;
+        const bool mi = s_m[i];
+        for (int j = sub; j < n; j += tpr) {
+          // the weights are loop-invariant shared-memory loads: without this fence the compiler hoists all ~3,000 of them
+          // out of the pair loop and spills them to local memory (12 KB of stack per thread)
+          asm volatile("" ::: "memory");
+          float dot, nrm;
+          pair_invariants(s_r + 3 * j, ri, dot, nrm);
+          // value net, first layer + layer normalisation (two-pass moments over the H true columns)
+          float h[HP];
+          float mean = 0.f;
+#pragma unroll
+          for (int k = 0; k < HP; k += 4) {
+            const float4 w0 = *reinterpret_cast<const float4*>(W + L::oWv1 + k);
+            const float4 w1 = *reinterpret_cast<const float4*>(W + L::oWv1 + HP + k);
+            const float4 bb = *reinterpret_cast<const float4*>(W + L::obv1 + k);
+            h[k] = fmaf(nrm, w1.x, fmaf(dot, w0.x, bb.x));
+            h[k + 1] = fmaf(nrm, w1.y, fmaf(dot, w0.y, bb.y));
+            h[k + 2] = fmaf(nrm, w1.z, fmaf(dot, w0.z, bb.z));
+            h[k + 3] = fmaf(nrm, w1.w, fmaf(dot, w0.w, bb.w));
+          }
+#pragma unroll
+          for (int k = 0; k < HP; ++k) mean += (k < H) ? h[k] : 0.f;
+          mean *= inv_H;
+          float var = 0.f;
+#pragma unroll
+          for (int k = 0; k < HP; ++k) {
+            const float dlt = h[k] - mean;
+            var += (k < H) ? dlt * dlt : 0.f;
+          }
+          const float rstd = rsqrtf(var * inv_H + p.ln_eps);
+          float iv[DP];
+#pragma unroll
+          for (int d = 0; d < DP; d += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(W + L::obv2 + d);
+            iv[d] = bb.x; iv[d + 1] = bb.y; iv[d + 2] = bb.z; iv[d + 3] = bb.w;
+          }
+#pragma unroll
+          for (int k = 0; k < HP; ++k) {
+            const float a = act_apply((h[k] - mean) * rstd * W[L::oLg + k] + W[L::oLb + k], p.act);  // padded columns: gamma = beta = 0
+#pragma unroll
+            for (int d = 0; d < DP; d += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(W + L::oWv2 + k * DP + d);
+              iv[d] = fmaf(a, w4.x, iv[d]); iv[d + 1] = fmaf(a, w4.y, iv[d + 1]);
+              iv[d + 2] = fmaf(a, w4.z, iv[d + 2]); iv[d + 3] = fmaf(a, w4.w, iv[d + 3]);
+            }
+          }
+          // joined = iv J1 + (u_j + w_i) J2
+          float jn[DP];
+#pragma unroll
+          for (int d = 0; d < DP; ++d) jn[d] = 0.f;
+#pragma unroll
+          for (int c = 0; c < DP; ++c) {
+            const float a = iv[c];
+#pragma unroll
+            for (int d = 0; d < DP; d += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(W + L::oJ1 + c * DP + d);
+              jn[d] = fmaf(a, w4.x, jn[d]); jn[d + 1] = fmaf(a, w4.y, jn[d + 1]);
+              jn[d + 2] = fmaf(a, w4.z, jn[d + 2]); jn[d + 3] = fmaf(a, w4.w, jn[d + 3]);
+            }
+          }
+          {
+            float j2[DP];
+#pragma unroll
+            for (int d = 0; d < DP; ++d) j2[d] = 0.f;
+#pragma unroll
+            for (int c = 0; c < DP; ++c) {
+              const float a = s_u[j * DP + c] + s_w[i * DP + c];
+#pragma unroll
+              for (int d = 0; d < DP; d += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(W + L::oJ2 + c * DP + d);
+                j2[d] = fmaf(a, w4.x, j2[d]); j2[d + 1] = fmaf(a, w4.y, j2[d + 1]);
+                j2[d + 2] = fmaf(a, w4.z, j2[d + 2]); j2[d + 3] = fmaf(a, w4.w, j2[d + 3]);
+              }
+            }
+#pragma unroll
+            for (int d = 0; d < DP; ++d) jn[d] += j2[d];
+          }
+          // score net
+          float sc = bs2;
+#pragma unroll
+          for (int k0 = 0; k0 < HP; k0 += 4) {
+            float4 hh = *reinterpret_cast<const float4*>(W + L::obs1 + k0);
+#pragma unroll
+            for (int c = 0; c < DP; ++c) {
+              const float4 w4 = *reinterpret_cast<const float4*>(W + L::oWs1 + c * HP + k0);
+              hh.x = fmaf(jn[c], w4.x, hh.x); hh.y = fmaf(jn[c], w4.y, hh.y);
+              hh.z = fmaf(jn[c], w4.z, hh.z); hh.w = fmaf(jn[c], w4.w, hh.w);
+            }
+            const float4 w2 = *reinterpret_cast<const float4*>(W + L::oWs2 + k0);
+            sc = fmaf(act_apply(hh.x, p.act), w2.x, sc);
+            sc = fmaf(act_apply(hh.y, p.act), w2.y, sc);
+            sc = fmaf(act_apply(hh.z, p.act), w2.z, sc);
+            sc = fmaf(act_apply(hh.w, p.act), w2.w, sc);
+          }
+          if (!(mi && s_m[j])) sc = kMaskedScore;
+          // online softmax
+          const float mn = fmaxf(m, sc);
+          const float scale = expf(m - mn);  // first pair: exp(-inf) = 0
+          const float e = expf(sc - mn);
+          l = l * scale + e;
+#pragma unroll
+          for (int d = 0; d < DP; ++d) acc[d] = acc[d] * scale + e * jn[d];
+          m = mn;
+        }
+      }
+      // merge the states of the threads of a row (reduce = 0) or of the pass (reduce = 1) in ascending thread order
+      float* st = s_st + t * (DP + 2);
+      st[0] = m; st[1] = l;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) st[2 + d] = acc[d];
+      __syncthreads();
+      if (!p.reduce) {
+        // thread (row, d): d = sub index over DP when tpr >= DP is not guaranteed -> loop
+        if (active) {
+          const int first = (t / tpr) * tpr;
+          float M = -INFINITY;
+          for (int q = 0; q < tpr; ++q) M = fmaxf(M, s_st[(first + q) * (DP + 2)]);
+          float Ls = 0.f;
+          for (int q = 0; q < tpr; ++q) {
+            const float* sq = s_st + (first + q) * (DP + 2);
+            if (sq[1] > 0.f) Ls += sq[1] * expf(sq[0] - M);
+          }
+          for (int d = sub; d < D; d += tpr) {
+            float o = 0.f;
+            for (int q = 0; q < tpr; ++q) {
+              const float* sq = s_st + (first + q) * (DP + 2);
+              if (sq[1] > 0.f) o += sq[2 + d] * expf(sq[0] - M);
+            }
+            p.out[(b * n + i) * D + d] = o / Ls;
+          }
+        }
+      } else if (t < DP) {
+        // threads 0 .. DP-1 fold this pass into the cloud state (each keeps m / l redundantly, column t of acc)
+        const int nact = min(rows_per_pass, n - i0) * tpr;
+        float M = red_m;
+        for (int q = 0; q < nact; ++q) M = fmaxf(M, s_st[q * (DP + 2)]);
+        const float sc0 = red_l > 0.f ? expf(red_m - M) : 0.f;
+        float Ls = red_l * sc0, o = red_o * sc0;
+        for (int q = 0; q < nact; ++q) {
+          const float* sq = s_st + q * (DP + 2);
+          if (sq[1] > 0.f) {
+            const float f = expf(sq[0] - M);
+            Ls += sq[1] * f;
+            o += sq[2 + t] * f;
+          }
+        }
+        red_m = M; red_l = Ls; red_o = o;
+      }
+      __syncthreads();
+    }
+    if (p.reduce && t < D) p.out[b * D + t] = red_o / red_l;
+  }
+}
+
+template <int HP, int DP>
+vms_status gaa_fused_launch(const GaaFwdParams& p, cudaStream_t st) {
+  using L = GaaSmem<HP, DP>;
+  int threads = ((p.n * p.tpr + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (threads < DP) threads = ((DP + 31) / 32) * 32;
+  const size_t fl = (size_t)L::nW + ((3 * p.n + 3) & ~3) + (size_t)3 * p.n * DP + (size_t)threads * (DP + 2);
+  const size_t smem = fl * sizeof(float) + (size_t)((p.n + 15) & ~15);
+  VMS_REQUIRE(smem <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "gaa_attention_forward: cloud of %d particles does not fit",
+              p.n);
+  VMS_CUDA(cudaFuncSetAttribute(gaa_attention_fwd_kernel<HP, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t cap = 4 * (int64_t)sm_count();
+  const int grid = (int)(p.B < cap ? p.B : cap);
+  gaa_attention_fwd_kernel<HP, DP><<<grid, threads, smem, st>>>(p);
+  VMS_LAUNCH_CHECK("gaa_attention_fwd_kernel");
+  return VMS_OK;
+}
+
+}  // namespace
+}  // namespace vms
+
+using namespace vms;
+
+extern "C" {
+
+vms_status vms_gaa_pair_invariants(const float* coords, int64_t B, int n, float* out, vms_stream stream) {
+  VMS_REQUIRE(B >= 0 && n >= 1 && (B == 0 || (coords && out)), VMS_ERR_INVALID_ARG, "gaa_pair_invariants: bad arguments");
+  const int64_t total = B * n * n;
+  if (total == 0) return VMS_OK;
+  gaa_pair_inv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(coords, total, n, out);
+  VMS_LAUNCH_CHECK("gaa_pair_inv_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_gaa_zero_mask(const float* coords, int64_t n_particles, uint8_t* mask, vms_stream stream) {
+  VMS_REQUIRE(n_particles >= 0 && (n_particles == 0 || (coords && mask)), VMS_ERR_INVALID_ARG, "gaa_zero_mask: bad arguments");
+  if (n_particles == 0) return VMS_OK;
+  gaa_zero_mask_kernel<<<(unsigned)((n_particles + 255) / 256), 256, 0, as_stream(stream)>>>(coords, n_particles, mask);
+  VMS_LAUNCH_CHECK("gaa_zero_mask_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_layernorm_forward(const float* x, int64_t ld_x, int64_t R, int H, const float* gamma, const float* beta,
+                                 float eps, int act, float* y, int64_t ld_y, float* stats, vms_stream stream) {
+  VMS_REQUIRE(R >= 0 && H >= 1 && (R == 0 || (x && y && gamma && beta)), VMS_ERR_INVALID_ARG, "layernorm_forward: bad arguments");
+  VMS_REQUIRE(act >= 0 && act <= 2 && eps >= 0.f, VMS_ERR_INVALID_ARG, "layernorm_forward: bad activation / epsilon");
+  if (R == 0) return VMS_OK;
+  layernorm_fwd_kernel<<<(unsigned)((R * LNG + 255) / 256), 256, 0, as_stream(stream)>>>(x, ld_x, R, H, gamma, beta, eps, act, y,
+                                                                                         ld_y, stats);
+  VMS_LAUNCH_CHECK("layernorm_fwd_kernel");
+  return VMS_OK;
+}
+
+size_t vms_layernorm_backward_workspace(int64_t R, int H) {
+  return (size_t)ln_bwd_grid(R) * 2 * (size_t)(H > 0 ? H : 1) * sizeof(float);
+}
+
+vms_status vms_layernorm_backward(const float* x, int64_t ld_x, int64_t R, int H, const float* gamma, const float* stats,
+                                  int act, const float* y, int64_t ld_y, const float* g_y, int64_t ld_gy, float* g_x,
+                                  int64_t ld_gx, float* g_gamma, float* g_beta, void* workspace, vms_stream stream) {
+  VMS_REQUIRE(R >= 0 && H >= 1 && (R == 0 || (x && y && gamma && stats && g_y && workspace)), VMS_ERR_INVALID_ARG,
+              "layernorm_backward: bad arguments");
+  VMS_REQUIRE(H <= 128, VMS_ERR_UNSUPPORTED, "layernorm_backward: H = %d > 128", H);
+  if (R == 0) return VMS_OK;
+  cudaStream_t st = as_stream(stream);
+  const int grid = ln_bwd_grid(R);
+  const size_t smem = (size_t)32 * 2 * H * sizeof(float);
+  float* part = (float*)workspace;
+  const int E = (H + LNG - 1) / LNG;
+#define VMS_LN_BWD(EE)                                                                                                    \
+  layernorm_bwd_kernel<EE><<<grid, 256, smem, st>>>(x, ld_x, R, H, gamma, stats, act, y, ld_y, g_y, ld_gy, g_x, ld_gx, part)
+  if (E <= 2) VMS_LN_BWD(2);
+  else if (E <= 4) VMS_LN_BWD(4);
+  else if (E <= 5) VMS_LN_BWD(5);
+  else if (E <= 8) VMS_LN_BWD(8);
+  else VMS_LN_BWD(16);
+#undef VMS_LN_BWD
+  VMS_LAUNCH_CHECK("layernorm_bwd_kernel");
+  return sum_partials_launch(part, grid, 2 * (int64_t)H, H, g_gamma, H, g_beta, 1.f, 1, st);
+}
+
+vms_status vms_gaa_pair_merge(const float* u, int64_t ld_u, const float* w, int64_t ld_w, int64_t B, int n, int D, float* out,
+                              vms_stream stream) {
+  VMS_REQUIRE(B >= 0 && n >= 1 && D >= 1 && (B == 0 || (u && w && out)), VMS_ERR_INVALID_ARG, "gaa_pair_merge: bad arguments");
+  const int64_t total = B * n * n * D;
+  if (total == 0) return VMS_OK;
+  gaa_pair_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(u, ld_u, w, ld_w, total, n, D, out);
+  VMS_LAUNCH_CHECK("gaa_pair_merge_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_gaa_pair_merge_backward(const float* g, int64_t B, int n, int D, float* g_u, int64_t ld_gu, float* g_w,
+                                       int64_t ld_gw, vms_stream stream) {
+  VMS_REQUIRE(B >= 0 && n >= 1 && D >= 1 && (B == 0 || (g && g_u && g_w)), VMS_ERR_INVALID_ARG,
+              "gaa_pair_merge_backward: bad arguments");
+  const int64_t total = B * n * D;
+  if (total == 0) return VMS_OK;
+  gaa_pair_merge_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(g, total, n, D, g_u, ld_gu, g_w,
+                                                                                            ld_gw);
+  VMS_LAUNCH_CHECK("gaa_pair_merge_bwd_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_gaa_attend(const float* scores, const float* values, const uint8_t* mask, int64_t B, int n, int D, int reduce,
+                          float* out, float* attention, vms_stream stream) {
+  VMS_REQUIRE(B >= 0 && n >= 1 && D >= 1 && (B == 0 || (scores && values && out && attention)), VMS_ERR_INVALID_ARG,
+              "gaa_attend: bad arguments");
+  if (B == 0) return VMS_OK;
+  cudaStream_t st = as_stream(stream);
+  if (reduce) {
+    VMS_REQUIRE(B < (1LL << 31), VMS_ERR_SHAPE, "gaa_attend: too many clouds");
+    gaa_attend_all_kernel<<<(unsigned)B, AT, 0, st>>>(scores, values, mask, n, D, out, attention);
+    VMS_LAUNCH_CHECK("gaa_attend_all_kernel");
+  } else {
+    const int64_t rows = B * n;
+    gaa_attend_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(scores, values, mask, rows, n, D, out, attention);
+    VMS_LAUNCH_CHECK("gaa_attend_rows_kernel");
+  }
+  return VMS_OK;
+}
+
+vms_status vms_gaa_attend_backward(const float* attention, const float* values, const uint8_t* mask, int64_t B, int n, int D,
+                                   int reduce, const float* g_out, float* g_scores, float* g_values, vms_stream stream) {
+  VMS_REQUIRE(B >= 0 && n >= 1 && D >= 1 && (B == 0 || (attention && values && g_out)), VMS_ERR_INVALID_ARG,
+              "gaa_attend_backward: bad arguments");
+  if (B == 0) return VMS_OK;
+  cudaStream_t st = as_stream(stream);
+  if (reduce) {
+    gaa_attend_all_bwd_kernel<<<(unsigned)B, AT, 0, st>>>(attention, values, mask, n, D, g_out, g_scores, g_values);
+    VMS_LAUNCH_CHECK("gaa_attend_all_bwd_kernel");
+  } else {
+    const int64_t rows = B * n;
+    gaa_attend_rows_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(attention, values, mask, rows, n, D, g_out, g_scores,
+                                                                           g_values);
+    VMS_LAUNCH_CHECK("gaa_attend_rows_bwd_kernel");
+  }
+  return VMS_OK;
+}
+
+int vms_gaa_attention_forward_supported(int n, int D, int H) {
+  return (n >= 1 && D >= 1 && D <= 32 && H >= 1 && H <= 64) ? 1 : 0;
+}
+
+vms_status vms_gaa_attention_forward(const float* coords, const float* values, int64_t ld_v, const uint8_t* mask, int64_t B,
+                                     int n, int D, int H, const vms_gaa_weights* w, int reduce, int act, float ln_eps,
+                                     float* out, vms_stream stream) {
+  VMS_RANGE("vms_gaa_attention_forward");
+  VMS_REQUIRE(coords && values && w && out && B >= 0, VMS_ERR_INVALID_ARG, "gaa_attention_forward: NULL pointer");
+  VMS_REQUIRE(vms_gaa_attention_forward_supported(n, D, H), VMS_ERR_UNSUPPORTED,
+              "gaa_attention_forward: needs D <= 32 and H <= 64 (got D = %d, H = %d)", D, H);
+  VMS_REQUIRE(w->merge0 && w->merge1 && w->join1 && w->join2 && w->score_w1 && w->score_b1 && w->score_w2 && w->score_b2 &&
+                  w->value_w1 && w->value_b1 && w->value_gamma && w->value_beta && w->value_w2 && w->value_b2,
+              VMS_ERR_INVALID_ARG, "gaa_attention_forward: NULL weight");
+  VMS_REQUIRE(act >= 0 && act <= 2, VMS_ERR_INVALID_ARG, "gaa_attention_forward: unknown activation");
+  if (B == 0) return VMS_OK;
+  GaaFwdParams p;
+  p.coords = coords; p.v = values; p.ldv = ld_v; p.mask = mask; p.B = B; p.n = n; p.D = D; p.H = H; p.reduce = reduce; p.act = act;
+  p.M0 = w->merge0; p.M1 = w->merge1; p.J1 = w->join1; p.J2 = w->join2;
+  p.Ws1 = w->score_w1; p.bs1 = w->score_b1; p.Ws2 = w->score_w2; p.bs2 = w->score_b2;
+  p.Wv1 = w->value_w1; p.bv1 = w->value_b1; p.lg = w->value_gamma; p.lb = w->value_beta; p.Wv2 = w->value_w2; p.bv2 = w->value_b2;
+  p.ln_eps = ln_eps; p.out = out;
+  int tpr = 256 / n;
+  if (tpr < 1) tpr = 1;
+  if (tpr > n) tpr = n;
+  p.tpr = tpr;
+  cudaStream_t st = as_stream(stream);
+  const int HP = H <= 24 ? 24 : (H <= 40 ? 40 : 64);
+  const int DP = D <= 12 ? 12 : (D <= 20 ? 20 : 32);
+#define VMS_GAA(HH, DD) if (HP == HH && DP == DD) return gaa_fused_launch<HH, DD>(p, st)
+  VMS_GAA(24, 12); VMS_GAA(24, 20); VMS_GAA(24, 32);
+  VMS_GAA(40, 12); VMS_GAA(40, 20); VMS_GAA(40, 32);
+  VMS_GAA(64, 12); VMS_GAA(64, 20); VMS_GAA(64, 32);
+#undef VMS_GAA
+  return VMS_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

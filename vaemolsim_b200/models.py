@@ -5,8 +5,8 @@ model builds distribution objects exactly as the reference does (op-by-op kernel
 GradientTape / Adam in the reference, tests/test_models.py:181-182) goes through the fused ELBO plan of `csrc/elbo.cu`
 for the model family of the reference's tests (IndependentNormal encoder / decoder over one-hidden-layer FCDeepNNs,
 N(0, I) or RealNVP-RQS-flowed prior, KLDivergenceEstimate + LogProbLoss) and raises NotImplementedError for
-compositions whose backward kernels are not built yet.  `VAEDualELBO` (models.py:335, cannot be
-constructed in the reference) and `BackmappingOnly` (needs the out-of-scope GAA embedding) are not mirrored.
+compositions whose backward kernels are not built yet.  `BackmappingOnly` (models.py:470-572) runs and trains
+on the tape path.  `VAEDualELBO` (models.py:335, cannot be constructed in the reference) is not mirrored.
 """
 import ctypes as C
 
@@ -217,6 +217,82 @@ class MappingToDistribution(Model):
     def get_config(self):
         config = super(MappingToDistribution, self).get_config()
         config.update({"distribution": self.distribution, "mapping": self.mapping})
+        return config
+
+
+class BackmappingOnly(Model):
+    """models.py:470-572: [CG sites to decode (B, 1, 3), all other coordinates (B, (N), 3) -- dense or ragged --, particle
+    properties (B, (N), P)] -> local descriptors (`mask_and_embed`, e.g. `LocalParticleDescriptors`) -> decoding
+    distribution (`decode_dist`, e.g. `MappingToDistribution`).  `fit` / `evaluate` / `predict` take that list as `x`
+    (tests/test_models.py:265-308) and train on the tape path."""
+
+    def __init__(self, mask_and_embed, decode_dist, name='backmapping', **kwargs):
+        super(BackmappingOnly, self).__init__(name=name, **kwargs)
+        self.mask_and_embed = mask_and_embed
+        self.decode_dist = decode_dist
+
+    def call(self, inputs, training=False):
+        cg_to_decode, other_coords, other_particle_props = inputs[0], inputs[1], inputs[2]
+        local_descriptors = self.mask_and_embed(other_coords, cg_to_decode, other_particle_props)
+        return self.decode_dist(local_descriptors, training=training)
+
+    # -- Keras fit / evaluate / predict over a LIST of inputs whose second and third entries may be ragged
+    @staticmethod
+    def _n_rows(inputs):
+        return int(np.asarray(inputs[0].numpy() if isinstance(inputs[0], Tensor) else inputs[0]).shape[0])
+
+    @staticmethod
+    def _take(a, idx):
+        if isinstance(a, mappings.RaggedTensor):
+            return mappings.RaggedTensor.from_rows([a.values[a.row_splits[i]:a.row_splits[i + 1]] for i in idx],
+                                                   inner=a.values.shape[-1])
+        if isinstance(a, (list, tuple)):
+            return [a[i] for i in idx]
+        a = a.numpy() if isinstance(a, Tensor) else np.asarray(a, np.float32)
+        return np.ascontiguousarray(a[idx])
+
+    def _batch(self, inputs, idx):
+        return [self._take(a, idx) for a in inputs]
+
+    def fit(self, x, y=None, epochs=1, batch_size=32, verbose=0, shuffle=True):
+        n = self._n_rows(x)
+        y = np.asarray(y.numpy() if isinstance(y, Tensor) else y, np.float32)
+        self(self._batch(x, np.arange(min(2, n))))  # build
+        tr = self._trainer()
+        hist = {'loss': []}
+        for _ in range(epochs):
+            order = P.rng().permutation(n) if shuffle else np.arange(n)
+            tot, cnt = 0.0, 0
+            for i in range(0, n, batch_size):
+                idx = order[i:i + batch_size]
+                xb, yb = self._batch(x, idx), Tensor.from_numpy(y[idx])
+                loss = tr.step(lambda: self._loss_tensor(xb, yb, True))
+                tot, cnt = tot + float(loss.numpy()) * len(idx), cnt + len(idx)
+            hist['loss'].append(tot / max(cnt, 1))
+        return hist
+
+    def train_on_batch(self, x, y=None):
+        yb = Tensor.from_numpy(np.asarray(y.numpy() if isinstance(y, Tensor) else y, np.float32))
+        return float(self._trainer().step(lambda: self._loss_tensor(x, yb, True)).numpy())
+
+    def evaluate(self, x, y=None, batch_size=32, verbose=0):
+        n = self._n_rows(x)
+        y = np.asarray(y.numpy() if isinstance(y, Tensor) else y, np.float32)
+        tot = 0.0
+        for i in range(0, n, batch_size):
+            idx = np.arange(i, min(i + batch_size, n))
+            tot += float(self._loss_tensor(self._batch(x, idx), Tensor.from_numpy(y[idx]), False).numpy()) * len(idx)
+        return tot / max(n, 1)
+
+    def predict(self, x, batch_size=32, verbose=0):
+        n = self._n_rows(x)
+        outs = [self.predict_step(self._batch(x, np.arange(i, min(i + batch_size, n)))).numpy()
+                for i in range(0, n, batch_size)]
+        return np.concatenate(outs, axis=0)
+
+    def get_config(self):
+        config = super(BackmappingOnly, self).get_config()
+        config.update({"mask_and_embed": self.mask_and_embed, "decode_dist": self.decode_dist})
         return config
 
 
