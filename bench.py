@@ -62,6 +62,7 @@ def parse():
     ap.add_argument('--collective', default='auto', choices=['auto', 'peer', 'nccl'],
                     help='N > 1: fused NVLink peer-memory allreduce+Adam kernel (peer), NCCL allreduce + Adam (nccl)')
     ap.add_argument('--c4b-only', action='store_true', help='development aid: run only the C4b MC leg and print it')
+    ap.add_argument('--backmap-only', action='store_true', help='development aid: run only the backmapping leg and print it')
     ap.add_argument('--mc-only', action='store_true', help='development aid: run only the MC leg and print it')
     return ap.parse_args()
 
@@ -436,6 +437,151 @@ def c3_leg(v, grp, peak_hbm, reps=10):
         res['parity_vs_oracle'] = bool(np.array_equal(got[0][:n_cpu], want[0]) and np.array_equal(got[1][:n_cpu], want[1])
                                        and np.array_equal(got[2][:n_cpu], want[2]))
     return res
+
+
+# --------------------------------------------------------------- backmapping descriptors (GAA embedding)
+def backmap_leg(v, grp, ffma_peak, reps=5):
+    """Local descriptors of the C3 box: 4,096 sites select their k nearest of 10,000 particles (shared frame) and embed the
+    selected cloud with `ParticleEmbedding(20)` (2 attention blocks + the permutation-invariant final attention, hidden 40,
+    mappings.py:564-688) -- one fused kernel per attention layer.  `value` = sites/s device-resident at k = 50 (the layer's
+    default `max_included`), sites sharded over the ranks; k = 10 (the backmapping notebook) beside it; the op-by-op
+    (training) path timed on 256 sites; a `BackmappingOnly` training step at the shape of tests/test_models.py:265-308."""
+    from vaemolsim_b200 import parallel
+    from oracle import gaa as ogaa
+    from oracle import mappings as omap
+    c = v._abi.ctx()
+    M = v.mappings
+    lo, hi = parallel.shard_rows(C3['rows'], grp.rank, grp.world)
+    B, N, P, E, H = hi - lo, C3['N'], C3['P'], 20, 40
+    L = np.float32(C3['L'])
+    rng = np.random.default_rng(3001)
+    frame = rng.uniform(-L / 2, L / 2, (N, 3)).astype(np.float32)
+    kinds = np.eye(2, dtype=np.float32)[rng.integers(0, 2, N)]
+    ref = np.random.default_rng(3002).uniform(-L / 2, L / 2, (C3['rows'], 3)).astype(np.float32)[lo:hi]
+    box = np.array([L, L, L], np.float32)
+    frame_d, kinds_d, ref_d = v.Tensor.from_numpy(frame), v.Tensor.from_numpy(kinds), v.Tensor.from_numpy(ref)
+    v.set_seed(8)
+    ev = Events(c, 1)
+    res = {}
+    flop_pair = 2 * (2 * H + H * E + 2 * E * E + E * H + H)  # value net, two join products, score net (per pair and layer)
+    for k in (50, 10):
+        sel = M.DistanceSelection(C3['cutoff'], max_included=k, box_lengths=box)
+        pe = M.ParticleEmbedding(E, hidden_dim=H)
+        xyz, info = sel.select_from_frame(frame_d, ref_d, particle_info=kinds_d)
+        for _ in range(2):
+            out = pe(xyz, info)
+        c.synchronize()
+        grp.barrier()
+        l0 = v._abi.launch_count()
+        ms = 0.0
+        for _ in range(reps):
+            ev.record(0)
+            out = pe(xyz, info)
+            ev.record(1)
+            c.synchronize()
+            ms += ev.elapsed_ms(0, 1)
+        launches = (v._abi.launch_count() - l0) / reps
+        ms = grp.max(ms) / reps
+        ms_all = 0.0
+        for _ in range(reps):  # selection + embedding (LocalParticleDescriptors on a shared frame)
+            ev.record(0)
+            xyz2, info2 = sel.select_from_frame(frame_d, ref_d, particle_info=kinds_d)
+            out2 = pe(xyz2, info2)
+            ev.record(1)
+            c.synchronize()
+            ms_all += ev.elapsed_ms(0, 1)
+        ms_all = grp.max(ms_all) / reps
+        flop = B * k * k * 3 * flop_pair
+        rec = {'sites_per_gpu': B, 'ms_embedding': ms, 'ms_select_and_embed': ms_all, 'gpu_launches': launches,
+               'sites_per_s': C3['rows'] / (ms * 1e-3), 'sites_per_s_with_selection': C3['rows'] / (ms_all * 1e-3),
+               'tflops': flop / (ms * 1e-3) / 1e12, 'frac_of_fp32_ffma_measured': flop / (ms * 1e-3) / 1e12 / ffma_peak}
+        # the op-by-op (training) path on a slice, same weights: pair tensors in HBM
+        nb = min(256, B)
+        xs, is_ = v.Tensor.from_numpy(xyz.numpy()[:nb]), v.Tensor.from_numpy(info.numpy()[:nb])
+        os.environ['VMS_GAA_FUSED'] = '0'
+        try:
+            o_ops = pe(xs, is_)
+            c.synchronize()
+            l0 = v._abi.launch_count()
+            ev.record(0)
+            o_ops = pe(xs, is_)
+            ev.record(1)
+            c.synchronize()
+            rec['op_by_op'] = {'sites': nb, 'ms': ev.elapsed_ms(0, 1), 'gpu_launches': v._abi.launch_count() - l0,
+                               'sites_per_s': nb / (ev.elapsed_ms(0, 1) * 1e-3)}
+        finally:
+            del os.environ['VMS_GAA_FUSED']
+        rec['fused_equals_op_by_op_1e-5'] = bool(np.allclose(out.numpy()[:nb], o_ops.numpy(), rtol=1e-5,
+                                                            atol=1e-5 * float(np.abs(o_ops.numpy()).max())))
+        if grp.rank == 0:  # oracle on a bounded sample: parity flag and CPU baseline
+            n_cpu = 64 if k == 50 else 256
+            w = {'info': [pe.info_net.kernel.numpy(), pe.info_net.bias.numpy()], 'blocks': [], 'final': None}
+
+            def att_w(va):
+                s_, v_ = va.score_net.layers, va.value_net.layers
+                return {'merge': [t.numpy() for t in va.merge_kernels], 'join': [t.numpy() for t in va.join_kernels],
+                        'score': [s_[0].kernel.numpy(), s_[0].bias.numpy(), s_[1].kernel.numpy(), s_[1].bias.numpy()],
+                        'value': [v_[0].kernel.numpy(), v_[0].bias.numpy(), v_[1].gamma.numpy(), v_[1].beta.numpy(),
+                                  v_[3].kernel.numpy(), v_[3].bias.numpy()]}
+
+            for blk in pe.block_list:
+                wb = att_w(blk.attn)
+                nl = blk.nonlinearity.layers
+                wb['nonlin'] = [nl[0].kernel.numpy(), nl[0].bias.numpy(), nl[1].gamma.numpy(), nl[1].beta.numpy(),
+                                nl[3].kernel.numpy(), nl[3].bias.numpy()]
+                w['blocks'].append(wb)
+            w['final'] = att_w(pe.final_attn)
+            xh, ih = xyz.numpy()[:n_cpu], info.numpy()[:n_cpu]
+            t0 = time.perf_counter()
+            want32 = ogaa.particle_embedding(xh, ih, w)
+            dt = time.perf_counter() - t0
+            want = ogaa.particle_embedding(xh.astype(np.float64), ih.astype(np.float64), ogaa.cast(w, np.float64))
+            err = float(np.abs(out.numpy()[:n_cpu] - want).max() / np.abs(want).max())
+            rec['max_rel_err_vs_float64_oracle'] = err
+            rec['parity_vs_oracle_1e-5'] = bool(err < 1e-5)
+            rec['cpu_baseline'] = {'value': n_cpu / dt, 'unit': 'sites/s', 'cores': cpu_threads(), 'kind': 'port',
+                                   'sample': '%d sites, float32 NumPy oracle/gaa.py (restatement of the published '
+                                             'geometric-algebra-attention algorithm; parity unpinned)' % n_cpu}
+        res['k_%d' % k] = rec
+    # one training step of BackmappingOnly at the reference test's shape (tests/test_models.py:265-308; the backmapping
+    # notebook's progress bar shows 37-39 ms/step at batch 32 with a 3-block conditional MAF decoder, BASELINE.md 2)
+    D = v.dists
+    n_b = 32
+    r2 = np.random.default_rng(9)
+    coords = [r2.uniform(-5, 5, (40, 3)).astype(np.float32) for _ in range(n_b)]
+    infos = [np.eye(2, dtype=np.float32)[r2.integers(0, 2, 40)] for _ in range(n_b)]
+    x = [r2.uniform(-5, 5, (n_b, 1, 3)).astype(np.float32), M.RaggedTensor.from_rows(coords, inner=3),
+         M.RaggedTensor.from_rows(infos, inner=2)]
+    y = r2.uniform(-3, 3, (n_b, 6)).astype(np.float32)
+    bm = v.models.BackmappingOnly(
+        M.LocalParticleDescriptors(M.DistanceSelection(3.0, max_included=10, box_lengths=[10.0, 10.0, 10.0]),
+                                   M.ParticleEmbedding(20)),
+        v.models.MappingToDistribution(D.AutoregressiveBlockwise(6, [D.Normal] * 3 + [D.VonMises] * 3), name='decoder'))
+    bm.compile(optimizer=v.models.Adam(1e-3), loss=v.losses.LogProbLoss())
+    bm(x)
+    losses = [bm.train_on_batch(x, y) for _ in range(5)]
+    c.synchronize()
+    l0 = v._abi.launch_count()
+    t0 = time.perf_counter()
+    n_st = 20
+    for _ in range(n_st):
+        losses.append(bm.train_on_batch(x, y))
+    c.synchronize()
+    dt = (time.perf_counter() - t0) / n_st
+    res['train_step'] = {'batch': n_b, 'particles_per_frame': 40, 'max_included': 10, 'ms_per_step': dt * 1e3,
+                         'configs_per_s': n_b / dt, 'gpu_launches_per_step': (v._abi.launch_count() - l0) / n_st,
+                         'loss_first': losses[0], 'loss_last': losses[-1], 'loss_finite': bool(np.isfinite(losses).all()),
+                         'reference_notebook': 'Molecular_Backmapping.ipynb progress bar: 37-39 ms/step at batch 32 (other '
+                                               'hardware, 3-block conditional MAF decoder; orientation only)'}
+    k50 = res['k_50']
+    return {'metric': 'sites/sec (local descriptors: ParticleEmbedding over the selected cloud)', 'value': k50['sites_per_s'],
+            'unit': 'sites/s', 'scaling': 'strong (sites sharded, no collective)',
+            'workload': 'C3 box (N = 10,000, L = 46.416, cutoff 3.0): %d sites x k nearest particles -> ParticleEmbedding(20, '
+                        'hidden 40, 2 blocks), fused forward' % C3['rows'],
+            'roofline': {'bound': 'ffma', 'kernel': 'gaa_attention_fwd_kernel<40, 20>', 'achieved': k50['tflops'], 'peak': ffma_peak,
+                         'unit': 'TFLOP/s', 'frac': k50['frac_of_fp32_ffma_measured'], 'traffic': None,
+                         'algorithmic_flop_per_pair_and_layer': flop_pair},
+            'cpu_baseline': k50.get('cpu_baseline'), **res}
 
 
 # ------------------------------------------------------------------------------ FlowModel NLL training (generic tape path)
@@ -1057,6 +1203,12 @@ def run_b200(args, w):
     grp = parallel.Group()
     rank, world = grp.rank, grp.world
     c = v._abi.ctx()
+    if args.backmap_only:
+        line = backmap_leg(v, grp, measured_peaks(v)['fp32_ffma_tflops'])
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        grp.close()
+        return
     if args.mc_only or args.c4b_only:
         line = (c4b_bench if args.c4b_only else mc_bench)(v, grp, measured_peaks(v)['fp32_ffma_tflops'])
         if rank == 0:
@@ -1094,6 +1246,10 @@ def run_b200(args, w):
             legs['c3'] = c3_leg(v, grp, peaks['hbm_gbs'])
         except Exception as ex:
             legs['c3'] = {'error': '%s: %s' % (type(ex).__name__, ex)}
+        try:
+            legs['backmap'] = backmap_leg(v, grp, peaks['fp32_ffma_tflops'])
+        except Exception as ex:
+            legs['backmap'] = {'error': '%s: %s' % (type(ex).__name__, ex)}
         try:
             if args.workload != 'c1':
                 r1 = elbo_leg(v, WORKLOADS['c1'], grp, WORKLOADS['c1']['batch'], min(K, 100), 5, args.collective)
