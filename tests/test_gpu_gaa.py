@@ -163,7 +163,7 @@ def test_vector_attention_both_paths_match_oracle(vms, B, n, D, H, reduce, act, 
     assert_close(out_ops, want, rtol=1e-5, atol=1e-5 * scale, what='op-by-op attention vs float64 oracle')
     n0 = v._abi.launch_count()
     out_f = va.call([v.Tensor.from_numpy(r), v.Tensor.from_numpy(vals)], mask=mask).numpy()
-    assert v._abi.launch_count() - n0 == 1, 'the fused forward is one launch'
+    assert v._abi.launch_count() - n0 == 2, 'the fused forward is two launches: weight image + attention kernel'
     assert_close(out_f, want, rtol=1e-5, atol=1e-5 * scale, what='fused attention vs float64 oracle')
     assert_close(out_f, out_ops, rtol=1e-5, atol=1e-5 * scale, what='fused vs op-by-op')
 

@@ -14,6 +14,7 @@
 //     weighted value per thread, merged per output row in a fixed order) -- no pair tensor ever reaches HBM.
 #include "common.cuh"
 #include "dense.cuh"
+#include <stdlib.h>
 
 namespace vms {
 namespace {
@@ -352,14 +353,16 @@ __global__ void gaa_zero_mask_kernel(const float* __restrict__ coords, int64_t t
 }
 
 // ===================================================================================== fused forward (one attention layer)
-// One CTA per cloud (grid-stride).  Shared memory: the layer's weights (zero padded to HP / DP columns, rows 16-byte
-// aligned), coordinates, mask, the per-particle halves of the merged values u = v M0, w = v M1, and the per-thread online
-// softmax states when they are merged.  Thread t owns output row i = t / TPR and walks j = t % TPR, + TPR, ...:
+// One CTA per cloud (grid-stride).  A pack kernel lays the layer's weights out as ONE zero-padded image (HP / DP columns);
+// the attention kernel reads it either from the CONSTANT bank (CW: every FFMA takes its weight as a c[bank][offset]
+// operand -- no load instruction, no shared-memory wavefront; the image travels by cudaMemcpyToSymbolAsync on the stream)
+// or from shared memory (16-byte broadcasts).  Shared memory also holds the coordinates, the mask, the per-particle halves
+// of the merged values u = v M0, w = v M1, and the per-thread online-softmax states when they are merged.
+// Thread t owns output row i = t / TPR and walks j = t % TPR, + TPR, ...:
 //   inv(2) -> h = inv Wv1 + bv1 -> LayerNorm -> act -> iv = . Wv2 + bv2 -> joined = iv J1 + (u_j + w_i) J2
 //   -> score = act(joined Ws1 + bs1) Ws2 + bs2  -> running (max, sum, sum of exp x joined).
 template <int HP, int DP>
-struct GaaSmem {
-  // weights (floats)
+struct GaaImg {
   static constexpr int oWv1 = 0;                  // [2][HP]
   static constexpr int obv1 = oWv1 + 2 * HP;      // [HP]
   static constexpr int oLg = obv1 + HP;           // [HP]
@@ -371,10 +374,14 @@ struct GaaSmem {
   static constexpr int oWs1 = oJ2 + DP * DP;      // [DP][HP]
   static constexpr int obs1 = oWs1 + DP * HP;     // [HP]
   static constexpr int oWs2 = obs1 + HP;          // [HP]
-  static constexpr int oM0 = oWs2 + HP;           // [DP][DP]
+  static constexpr int obs2 = oWs2 + HP;          // [4] (one value)
+  static constexpr int nPair = obs2 + 4;          // what the pair loop reads
+  static constexpr int oM0 = nPair;               // [DP][DP]
   static constexpr int oM1 = oM0 + DP * DP;       // [DP][DP]
   static constexpr int nW = oM1 + DP * DP;
 };
+constexpr int kGaaConstFloats = GaaImg<64, 32>::nPair;
+__constant__ float c_gaa_w[kGaaConstFloats];
 
 struct GaaFwdParams {
   const float* coords; const float* v; int64_t ldv; const uint8_t* mask;
@@ -382,44 +389,58 @@ struct GaaFwdParams {
   const float *M0, *M1, *J1, *J2, *Ws1, *bs1, *Ws2, *bs2, *Wv1, *bv1, *lg, *lb, *Wv2, *bv2;
   float ln_eps;
   float* out;
+  float* img;  // the packed weight image in global memory
 };
 
 template <int HP, int DP>
+__global__ void gaa_pack_kernel(GaaFwdParams p) {
+  using L = GaaImg<HP, DP>;
+  float* W = p.img;
+  const int D = p.D, H = p.H;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L::nW; k += gridDim.x * blockDim.x) {
+    float val = 0.f;
+    int o = k;
+    if (o < L::obv1) { const int r = o / HP, c = o % HP; if (c < H) val = p.Wv1[r * H + c]; }
+    else if (o < L::oLg) { o -= L::obv1; if (o < H) val = p.bv1[o]; }
+    else if (o < L::oLb) { o -= L::oLg; if (o < H) val = p.lg[o]; }
+    else if (o < L::oWv2) { o -= L::oLb; if (o < H) val = p.lb[o]; }
+    else if (o < L::obv2) { o -= L::oWv2; const int r = o / DP, c = o % DP; if (r < H && c < D) val = p.Wv2[r * D + c]; }
+    else if (o < L::oJ1) { o -= L::obv2; if (o < D) val = p.bv2[o]; }
+    else if (o < L::oJ2) { o -= L::oJ1; const int r = o / DP, c = o % DP; if (r < D && c < D) val = p.J1[r * D + c]; }
+    else if (o < L::oWs1) { o -= L::oJ2; const int r = o / DP, c = o % DP; if (r < D && c < D) val = p.J2[r * D + c]; }
+    else if (o < L::obs1) { o -= L::oWs1; const int r = o / HP, c = o % HP; if (r < D && c < H) val = p.Ws1[r * H + c]; }
+    else if (o < L::oWs2) { o -= L::obs1; if (o < H) val = p.bs1[o]; }
+    else if (o < L::obs2) { o -= L::oWs2; if (o < H) val = p.Ws2[o]; }
+    else if (o < L::oM0) { o -= L::obs2; if (o == 0) val = p.bs2[0]; }
+    else if (o < L::oM1) { o -= L::oM0; const int r = o / DP, c = o % DP; if (r < D && c < D) val = p.M0[r * D + c]; }
+    else { o -= L::oM1; const int r = o / DP, c = o % DP; if (r < D && c < D) val = p.M1[r * D + c]; }
+    W[k] = val;
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+  return ACT == VMS_ACT_RELU ? fmaxf(x, 0.f) : (ACT == VMS_ACT_TANH ? tanhf(x) : x);
+}
+
+template <int HP, int DP, int ACT, bool CW, int NP>
 __global__ void __launch_bounds__(256) gaa_attention_fwd_kernel(GaaFwdParams p) {
-  using L = GaaSmem<HP, DP>;
+  using L = GaaImg<HP, DP>;
   extern __shared__ __align__(16) float smem[];
-  float* W = smem;
   const int n = p.n, D = p.D, H = p.H;
-  float* s_r = W + L::nW;               // [n][3] (+ pad to a multiple of 4)
-  float* s_u = s_r + ((3 * n + 3) & ~3);  // [n][DP]
-  float* s_w = s_u + n * DP;            // [n][DP]
-  float* s_v = s_w + n * DP;            // [n][DP]
-  float* s_st = s_v + n * DP;           // [blockDim][DP + 2] online-softmax states
+  float* W = smem;                                  // !CW: the pair-loop part of the image
+  float* s_r = smem + (CW ? 0 : L::nPair);          // [n][3] (+ pad to a multiple of 4)
+  float* s_u = s_r + ((3 * n + 3) & ~3);            // [n][DP]
+  float* s_w = s_u + n * DP;                        // [n][DP]
+  float* s_v = s_w + n * DP;                        // [n][DP]
+  float* s_st = s_v + n * DP;                       // [blockDim][DP + 2] online-softmax states
   uint8_t* s_m = reinterpret_cast<uint8_t*>(s_st + blockDim.x * (DP + 2));  // [n]
   const int t = threadIdx.x;
-
-  // weights -> shared memory, zero padded
-  for (int k = t; k < L::nW; k += blockDim.x) W[k] = 0.f;
-  __syncthreads();
-  for (int k = t; k < 2 * H; k += blockDim.x) W[L::oWv1 + (k / H) * HP + k % H] = p.Wv1[k];
-  for (int k = t; k < H; k += blockDim.x) {
-    W[L::obv1 + k] = p.bv1[k];
-    W[L::oLg + k] = p.lg[k];
-    W[L::oLb + k] = p.lb[k];
-    W[L::obs1 + k] = p.bs1[k];
-    W[L::oWs2 + k] = p.Ws2[k];
-  }
-  for (int k = t; k < H * D; k += blockDim.x) W[L::oWv2 + (k / D) * DP + k % D] = p.Wv2[k];
-  for (int k = t; k < D * H; k += blockDim.x) W[L::oWs1 + (k / H) * HP + k % H] = p.Ws1[k];
-  for (int k = t; k < D; k += blockDim.x) W[L::obv2 + k] = p.bv2[k];
-  for (int k = t; k < D * D; k += blockDim.x) {
-    const int o = (k / D) * DP + k % D;
-    W[L::oJ1 + o] = p.J1[k];
-    W[L::oJ2 + o] = p.J2[k];
-    W[L::oM0 + o] = p.M0[k];
-    W[L::oM1 + o] = p.M1[k];
-  }
-  const float bs2 = p.bs2[0];
+  if (!CW)
+    for (int k = t; k < L::nPair; k += blockDim.x) W[k] = p.img[k];
+#define WT(off) (CW ? c_gaa_w[(off)] : W[(off)])
+  const float* gM0 = p.img + L::oM0;
+  const float* gM1 = p.img + L::oM1;
   const float inv_H = 1.f / (float)H;
   const int tpr = p.tpr;
   const int rows_per_pass = blockDim.x / tpr;
@@ -438,16 +459,16 @@ __global__ void __launch_bounds__(256) gaa_attention_fwd_kernel(GaaFwdParams p) 
       float su = 0.f, sw = 0.f;
       for (int c = 0; c < D; ++c) {
         const float vv = s_v[q * DP + c];
-        su = fmaf(vv, W[L::oM0 + c * DP + d], su);
-        sw = fmaf(vv, W[L::oM1 + c * DP + d], sw);
+        su = fmaf(vv, __ldg(gM0 + c * DP + d), su);
+        sw = fmaf(vv, __ldg(gM1 + c * DP + d), sw);
       }
       s_u[k] = su;
       s_w[k] = sw;
     }
     __syncthreads();
 
-    float red_m = -INFINITY, red_l = 0.f;  // reduce = 1: thread 0 accumulates the cloud's state over the passes
-    float red_o = 0.f;                     // (threads 0 .. DP-1 each keep m / l and column t of the weighted sum)
+    float red_m = -INFINITY, red_l = 0.f;  // reduce = 1: threads 0 .. DP-1 accumulate the cloud's state over the passes
+    float red_o = 0.f;                     // (each keeps m / l redundantly and column t of the weighted sum)
 
     for (int i0 = 0; i0 < n; i0 += rows_per_pass) {
       const int i = i0 + t / tpr;
@@ -460,108 +481,145 @@ __global__ void __launch_bounds__(256) gaa_attention_fwd_kernel(GaaFwdParams p) 
       if (active) {
         const float* ri = s_r + 3 * i;
         const bool mi = s_m[i];
-        for (int j = sub; j < n; j += tpr) {
-          // the weights are loop-invariant shared-memory loads: without this fence the compiler hoists all ~3,000 of them
-          // out of the pair loop and spills them to local memory (12 KB of stack per thread)
+        // NP pairs per trip: every weight load feeds NP FMAs (the shared-memory pipe, not the FMA pipe, bounds NP = 1)
+        for (int j0 = sub; j0 < n; j0 += NP * tpr) {
+          // the weights are loop-invariant loads: without this fence the compiler hoists all ~3,000 of them out of the pair
+          // loop and spills them to local memory (12 KB of stack per thread)
           asm volatile("" ::: "memory");
-          float dot, nrm;
-          pair_invariants(s_r + 3 * j, ri, dot, nrm);
+          int jj[NP];
+          bool ok[NP];
+          float dot[NP], nrm[NP];
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            ok[q] = j0 + q * tpr < n;
+            jj[q] = ok[q] ? j0 + q * tpr : j0;
+            pair_invariants(s_r + 3 * jj[q], ri, dot[q], nrm[q]);
+          }
           // value net, first layer + layer normalisation (two-pass moments over the H true columns)
-          float h[HP];
-          float mean = 0.f;
-#pragma unroll
-          for (int k = 0; k < HP; k += 4) {
-            const float4 w0 = *reinterpret_cast<const float4*>(W + L::oWv1 + k);
-            const float4 w1 = *reinterpret_cast<const float4*>(W + L::oWv1 + HP + k);
-            const float4 bb = *reinterpret_cast<const float4*>(W + L::obv1 + k);
-            h[k] = fmaf(nrm, w1.x, fmaf(dot, w0.x, bb.x));
-            h[k + 1] = fmaf(nrm, w1.y, fmaf(dot, w0.y, bb.y));
-            h[k + 2] = fmaf(nrm, w1.z, fmaf(dot, w0.z, bb.z));
-            h[k + 3] = fmaf(nrm, w1.w, fmaf(dot, w0.w, bb.w));
-          }
-#pragma unroll
-          for (int k = 0; k < HP; ++k) mean += (k < H) ? h[k] : 0.f;
-          mean *= inv_H;
-          float var = 0.f;
+          float h[NP][HP];
 #pragma unroll
           for (int k = 0; k < HP; ++k) {
-            const float dlt = h[k] - mean;
-            var += (k < H) ? dlt * dlt : 0.f;
-          }
-          const float rstd = rsqrtf(var * inv_H + p.ln_eps);
-          float iv[DP];
+            const float w0 = WT(L::oWv1 + k), w1 = WT(L::oWv1 + HP + k), bb = WT(L::obv1 + k);
 #pragma unroll
-          for (int d = 0; d < DP; d += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(W + L::obv2 + d);
-            iv[d] = bb.x; iv[d + 1] = bb.y; iv[d + 2] = bb.z; iv[d + 3] = bb.w;
+            for (int q = 0; q < NP; ++q) h[q][k] = fmaf(nrm[q], w1, fmaf(dot[q], w0, bb));
+          }
+          float mean[NP], rstd[NP];
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            float mu = 0.f;
+#pragma unroll
+            for (int k = 0; k < HP; ++k) mu += (k < H) ? h[q][k] : 0.f;
+            mu *= inv_H;
+            float var = 0.f;
+#pragma unroll
+            for (int k = 0; k < HP; ++k) {
+              const float dlt = h[q][k] - mu;
+              var += (k < H) ? dlt * dlt : 0.f;
+            }
+            mean[q] = mu;
+            rstd[q] = rsqrtf(var * inv_H + p.ln_eps);
+          }
+          float iv[NP][DP];
+#pragma unroll
+          for (int d = 0; d < DP; ++d) {
+            const float bb = WT(L::obv2 + d);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) iv[q][d] = bb;
           }
 #pragma unroll
           for (int k = 0; k < HP; ++k) {
-            const float a = act_apply((h[k] - mean) * rstd * W[L::oLg + k] + W[L::oLb + k], p.act);  // padded columns: gamma = beta = 0
+            const float lg = WT(L::oLg + k), lb = WT(L::oLb + k);  // padded columns: gamma = beta = 0
+            float a[NP];
 #pragma unroll
-            for (int d = 0; d < DP; d += 4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(W + L::oWv2 + k * DP + d);
-              iv[d] = fmaf(a, w4.x, iv[d]); iv[d + 1] = fmaf(a, w4.y, iv[d + 1]);
-              iv[d + 2] = fmaf(a, w4.z, iv[d + 2]); iv[d + 3] = fmaf(a, w4.w, iv[d + 3]);
+            for (int q = 0; q < NP; ++q) a[q] = act_t<ACT>((h[q][k] - mean[q]) * rstd[q] * lg + lb);
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+              const float w = WT(L::oWv2 + k * DP + d);
+#pragma unroll
+              for (int q = 0; q < NP; ++q) iv[q][d] = fmaf(a[q], w, iv[q][d]);
             }
           }
           // joined = iv J1 + (u_j + w_i) J2
-          float jn[DP];
+          float jn[NP][DP];
 #pragma unroll
-          for (int d = 0; d < DP; ++d) jn[d] = 0.f;
+          for (int q = 0; q < NP; ++q)
+#pragma unroll
+            for (int d = 0; d < DP; ++d) jn[q][d] = 0.f;
 #pragma unroll
           for (int c = 0; c < DP; ++c) {
-            const float a = iv[c];
 #pragma unroll
-            for (int d = 0; d < DP; d += 4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(W + L::oJ1 + c * DP + d);
-              jn[d] = fmaf(a, w4.x, jn[d]); jn[d + 1] = fmaf(a, w4.y, jn[d + 1]);
-              jn[d + 2] = fmaf(a, w4.z, jn[d + 2]); jn[d + 3] = fmaf(a, w4.w, jn[d + 3]);
+            for (int d = 0; d < DP; ++d) {
+              const float w = WT(L::oJ1 + c * DP + d);
+#pragma unroll
+              for (int q = 0; q < NP; ++q) jn[q][d] = fmaf(iv[q][c], w, jn[q][d]);
             }
           }
           {
-            float j2[DP];
+            float j2[NP][DP];
 #pragma unroll
-            for (int d = 0; d < DP; ++d) j2[d] = 0.f;
+            for (int q = 0; q < NP; ++q)
+#pragma unroll
+              for (int d = 0; d < DP; ++d) j2[q][d] = 0.f;
 #pragma unroll
             for (int c = 0; c < DP; ++c) {
-              const float a = s_u[j * DP + c] + s_w[i * DP + c];
+              float a[NP];
 #pragma unroll
-              for (int d = 0; d < DP; d += 4) {
-                const float4 w4 = *reinterpret_cast<const float4*>(W + L::oJ2 + c * DP + d);
-                j2[d] = fmaf(a, w4.x, j2[d]); j2[d + 1] = fmaf(a, w4.y, j2[d + 1]);
-                j2[d + 2] = fmaf(a, w4.z, j2[d + 2]); j2[d + 3] = fmaf(a, w4.w, j2[d + 3]);
+              for (int q = 0; q < NP; ++q) a[q] = s_u[jj[q] * DP + c] + s_w[i * DP + c];
+#pragma unroll
+              for (int d = 0; d < DP; ++d) {
+                const float w = WT(L::oJ2 + c * DP + d);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) j2[q][d] = fmaf(a[q], w, j2[q][d]);
               }
             }
 #pragma unroll
-            for (int d = 0; d < DP; ++d) jn[d] += j2[d];
+            for (int q = 0; q < NP; ++q)
+#pragma unroll
+              for (int d = 0; d < DP; ++d) jn[q][d] += j2[q][d];
           }
           // score net
-          float sc = bs2;
+          float sc[NP];
+#pragma unroll
+          for (int q = 0; q < NP; ++q) sc[q] = WT(L::obs2);
 #pragma unroll
           for (int k0 = 0; k0 < HP; k0 += 4) {
-            float4 hh = *reinterpret_cast<const float4*>(W + L::obs1 + k0);
+            float hh[NP][4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float bb = WT(L::obs1 + k0 + e);
+#pragma unroll
+              for (int q = 0; q < NP; ++q) hh[q][e] = bb;
+            }
 #pragma unroll
             for (int c = 0; c < DP; ++c) {
-              const float4 w4 = *reinterpret_cast<const float4*>(W + L::oWs1 + c * HP + k0);
-              hh.x = fmaf(jn[c], w4.x, hh.x); hh.y = fmaf(jn[c], w4.y, hh.y);
-              hh.z = fmaf(jn[c], w4.z, hh.z); hh.w = fmaf(jn[c], w4.w, hh.w);
-            }
-            const float4 w2 = *reinterpret_cast<const float4*>(W + L::oWs2 + k0);
-            sc = fmaf(act_apply(hh.x, p.act), w2.x, sc);
-            sc = fmaf(act_apply(hh.y, p.act), w2.y, sc);
-            sc = fmaf(act_apply(hh.z, p.act), w2.z, sc);
-            sc = fmaf(act_apply(hh.w, p.act), w2.w, sc);
-          }
-          if (!(mi && s_m[j])) sc = kMaskedScore;
-          // online softmax
-          const float mn = fmaxf(m, sc);
-          const float scale = expf(m - mn);  // first pair: exp(-inf) = 0
-          const float e = expf(sc - mn);
-          l = l * scale + e;
 #pragma unroll
-          for (int d = 0; d < DP; ++d) acc[d] = acc[d] * scale + e * jn[d];
-          m = mn;
+              for (int e = 0; e < 4; ++e) {
+                const float w = WT(L::oWs1 + c * HP + k0 + e);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) hh[q][e] = fmaf(jn[q][c], w, hh[q][e]);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float w = WT(L::oWs2 + k0 + e);
+#pragma unroll
+              for (int q = 0; q < NP; ++q) sc[q] = fmaf(act_t<ACT>(hh[q][e]), w, sc[q]);
+            }
+          }
+          // online softmax, pair by pair in ascending j (the same order as NP = 1)
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            if (!ok[q]) continue;
+            float s1 = sc[q];
+            if (!(mi && s_m[jj[q]])) s1 = kMaskedScore;
+            const float mn = fmaxf(m, s1);
+            const float scale = expf(m - mn);  // first pair: exp(-inf) = 0
+            const float e = expf(s1 - mn);
+            l = l * scale + e;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) acc[d] = acc[d] * scale + e * jn[q][d];
+            m = mn;
+          }
         }
       }
       // merge the states of the threads of a row (reduce = 0) or of the pass (reduce = 1) in ascending thread order
@@ -571,7 +629,6 @@ __global__ void __launch_bounds__(256) gaa_attention_fwd_kernel(GaaFwdParams p) 
       for (int d = 0; d < DP; ++d) st[2 + d] = acc[d];
       __syncthreads();
       if (!p.reduce) {
-        // thread (row, d): d = sub index over DP when tpr >= DP is not guaranteed -> loop
         if (active) {
           const int first = (t / tpr) * tpr;
           float M = -INFINITY;
@@ -611,24 +668,81 @@ __global__ void __launch_bounds__(256) gaa_attention_fwd_kernel(GaaFwdParams p) 
     }
     if (p.reduce && t < D) p.out[b * D + t] = red_o / red_l;
   }
+#undef WT
 }
 
-template <int HP, int DP>
-vms_status gaa_fused_launch(const GaaFwdParams& p, cudaStream_t st) {
-  using L = GaaSmem<HP, DP>;
+// the packed image (global memory), one buffer per device, reused by successive launches on the library's stream
+float* gaa_image_buffer() {
+  static float* buf[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!buf[dev] && cudaMalloc(&buf[dev], sizeof(float) * GaaImg<64, 32>::nW) != cudaSuccess) buf[dev] = nullptr;
+  return buf[dev];
+}
+
+bool gaa_const_weights() {  // VMS_GAA_CONST=1 (and a build with -DVMS_GAA_WITH_CONST): weights as constant-bank operands
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VMS_GAA_CONST");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
+// pairs per trip of the pair loop: 2 when a thread walks at least four pairs (k = 50: 5.6 vs 6.4 ms per 4,096-site embedding;
+// every weight broadcast then feeds two FMAs), 1 for small clouds (k = 10: 0.56 vs 0.93 ms); VMS_GAA_NP=1|2 forces it
+int gaa_pairs_per_trip(int n, int tpr) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("VMS_GAA_NP");
+    forced = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  }
+  if (forced) return forced;
+  return (n + tpr - 1) / tpr >= 4 ? 2 : 1;
+}
+
+template <int HP, int DP, int ACT, bool CW, int NP>
+vms_status gaa_fused_launch2(GaaFwdParams& p, cudaStream_t st) {
+  using L = GaaImg<HP, DP>;
   int threads = ((p.n * p.tpr + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   if (threads < DP) threads = ((DP + 31) / 32) * 32;
-  const size_t fl = (size_t)L::nW + ((3 * p.n + 3) & ~3) + (size_t)3 * p.n * DP + (size_t)threads * (DP + 2);
+  const size_t fl = (size_t)(CW ? 0 : L::nPair) + ((3 * p.n + 3) & ~3) + (size_t)3 * p.n * DP + (size_t)threads * (DP + 2);
   const size_t smem = fl * sizeof(float) + (size_t)((p.n + 15) & ~15);
   VMS_REQUIRE(smem <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "gaa_attention_forward: cloud of %d particles does not fit",
               p.n);
-  VMS_CUDA(cudaFuncSetAttribute(gaa_attention_fwd_kernel<HP, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t cap = 4 * (int64_t)sm_count();
+  p.img = gaa_image_buffer();
+  VMS_REQUIRE(p.img, VMS_ERR_CUDA, "gaa_attention_forward: cannot allocate the weight image");
+  gaa_pack_kernel<HP, DP><<<(L::nW + 255) / 256, 256, 0, st>>>(p);
+  VMS_LAUNCH_CHECK("gaa_pack_kernel");
+  if (CW) VMS_CUDA(cudaMemcpyToSymbolAsync(c_gaa_w, p.img, sizeof(float) * L::nPair, 0, cudaMemcpyDeviceToDevice, st));
+  VMS_CUDA(cudaFuncSetAttribute(gaa_attention_fwd_kernel<HP, DP, ACT, CW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t cap = 8 * (int64_t)sm_count();
   const int grid = (int)(p.B < cap ? p.B : cap);
-  gaa_attention_fwd_kernel<HP, DP><<<grid, threads, smem, st>>>(p);
+  gaa_attention_fwd_kernel<HP, DP, ACT, CW, NP><<<grid, threads, smem, st>>>(p);
   VMS_LAUNCH_CHECK("gaa_attention_fwd_kernel");
   return VMS_OK;
+}
+
+template <int HP, int DP>
+vms_status gaa_fused_launch(GaaFwdParams& p, cudaStream_t st) {
+  const bool two = gaa_pairs_per_trip(p.n, p.tpr) == 2;
+#ifdef VMS_GAA_WITH_CONST  // constant-bank weights: measured slower than shared-memory broadcasts (7.4 vs 6.4 ms), not built by default
+  if (gaa_const_weights()) {
+#define VMS_GAA_ACT(A) if (p.act == A) return gaa_fused_launch2<HP, DP, A, true, 1>(p, st)
+    VMS_GAA_ACT(VMS_ACT_NONE);
+    VMS_GAA_ACT(VMS_ACT_RELU);
+    VMS_GAA_ACT(VMS_ACT_TANH);
+#undef VMS_GAA_ACT
+  }
+#endif
+#define VMS_GAA_ACT(A)                                                      \
+  if (p.act == A) return two ? gaa_fused_launch2<HP, DP, A, false, 2>(p, st) : gaa_fused_launch2<HP, DP, A, false, 1>(p, st)
+  VMS_GAA_ACT(VMS_ACT_NONE);
+  VMS_GAA_ACT(VMS_ACT_RELU);
+  VMS_GAA_ACT(VMS_ACT_TANH);
+#undef VMS_GAA_ACT
+  return VMS_ERR_INVALID_ARG;
 }
 
 }  // namespace
@@ -768,7 +882,7 @@ vms_status vms_gaa_attention_forward(const float* coords, const float* values, i
               VMS_ERR_INVALID_ARG, "gaa_attention_forward: NULL weight");
   VMS_REQUIRE(act >= 0 && act <= 2, VMS_ERR_INVALID_ARG, "gaa_attention_forward: unknown activation");
   if (B == 0) return VMS_OK;
-  GaaFwdParams p;
+  GaaFwdParams p = {};
   p.coords = coords; p.v = values; p.ldv = ld_v; p.mask = mask; p.B = B; p.n = n; p.D = D; p.H = H; p.reduce = reduce; p.act = act;
   p.M0 = w->merge0; p.M1 = w->merge1; p.J1 = w->join1; p.J2 = w->join2;
   p.Ws1 = w->score_w1; p.bs1 = w->score_b1; p.Ws2 = w->score_w2; p.bs2 = w->score_b2;
@@ -779,14 +893,9 @@ vms_status vms_gaa_attention_forward(const float* coords, const float* values, i
   if (tpr > n) tpr = n;
   p.tpr = tpr;
   cudaStream_t st = as_stream(stream);
-  const int HP = H <= 24 ? 24 : (H <= 40 ? 40 : 64);
-  const int DP = D <= 12 ? 12 : (D <= 20 ? 20 : 32);
-#define VMS_GAA(HH, DD) if (HP == HH && DP == DD) return gaa_fused_launch<HH, DD>(p, st)
-  VMS_GAA(24, 12); VMS_GAA(24, 20); VMS_GAA(24, 32);
-  VMS_GAA(40, 12); VMS_GAA(40, 20); VMS_GAA(40, 32);
-  VMS_GAA(64, 12); VMS_GAA(64, 20); VMS_GAA(64, 32);
-#undef VMS_GAA
-  return VMS_ERR_UNSUPPORTED;
+  // register arrays are compile-time: the widths of the reference's defaults (hidden 40, embedding 20) or the maximum
+  if (H <= 40 && D <= 20) return gaa_fused_launch<40, 20>(p, st);
+  return gaa_fused_launch<64, 32>(p, st);
 }
 
 }  // extern "C"
