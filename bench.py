@@ -990,8 +990,7 @@ def large_batch_leg(v, w, opt, grp, peaks, collective='auto', global_batch=26214
         if world == 1:
             f.train_step(x, e, opt)
         elif peer is not None:
-            f.forward_backward(x, e, grad_ptr=peer.next_slot())
-            peer.allreduce_adam(f, opt)
+            peer.train_step(f, x, e, x.shape[0], opt)
         else:
             f.forward_backward(x, e)
             grp.allreduce_sum_device_(f.grad.ptr, f.n_params, c.stream)
@@ -1096,8 +1095,7 @@ def elbo_leg(v, w, grp, batch, K, W, collective, sampler=None):
         elif peer is not None:
             # gradient straight into this step's slot of the exchange buffer, then ONE kernel: flags + peer reads over
             # NVLink + rank-ordered sum + Adam
-            f.forward_backward(xs[i % n_sets], es[i % n_sets], grad_ptr=peer.next_slot())
-            peer.allreduce_adam(f, opt)
+            peer.train_step(f, xs[i % n_sets], es[i % n_sets], batch, opt)
         else:
             f.forward_backward(xs[i % n_sets], es[i % n_sets])
             grp.allreduce_sum_device_(f.grad.ptr, f.n_params, c.stream)  # fallback: NCCL allreduce on the library's stream

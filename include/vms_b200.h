@@ -390,6 +390,16 @@ vms_status vms_elbo_forward_backward(vms_elbo_plan plan, const float* theta, con
 vms_status vms_elbo_train_step(vms_elbo_plan plan, float* theta, const float* x, const float* eps, int64_t B, float* grad,
                                float* scalars, float* m, float* v, int64_t t, double lr, double beta1, double beta2,
                                double eps_adam, vms_stream stream);
+/* One DATA-PARALLEL training step (one process per GPU, peer buffers as for vms_peer_allreduce_adam below): forward + backward
+ * on this rank's shard, gradient sum over the ranks through NVLink peer memory, Adam with 1 / world.  When the whole-step
+ * tensor-core kernel serves the batch its finish kernel performs the exchange itself -- it sums the tile partials into this
+ * rank's slot, the last block raises the rank's flag, and after the (bounded) wait every thread pulls its parameter from all
+ * ranks, updates theta / m / v and writes the next step's weight images: two launches per step, as on one GPU.  Every other
+ * plan runs vms_elbo_forward_backward into the slot followed by vms_peer_allreduce_adam.  `step` = 1, 2, 3, ... (the slot is
+ * step & 1), identical on all ranks. */
+vms_status vms_elbo_train_step_peer(vms_elbo_plan plan, float* theta, const float* x, const float* eps, int64_t B, float* scalars,
+                                    float* m, float* v, int64_t t, double lr, double beta1, double beta2, double eps_adam,
+                                    int world, int rank, void* const* peer_bases, unsigned long long step, vms_stream stream);
 
 /* ------------------------------------------------------------------------------- fused MC run (C4a)
  * n_steps complete VAE-proposal MC steps (mcmc.py:68-130, the loop of mcmc.py:133-159) of B independent chains in ONE

@@ -167,3 +167,78 @@ def test_data_parallel_training_of_a_tape_model_two_gpus(tmp_path):
     assert all(float(r[3]) > 1e-3 for r in res), res          # the six steps moved the weights
     assert all(float(r[2]) < 2e-5 for r in res), res          # sharded == whole batch up to float32 summation order
     assert res[0][4] == res[1][4], 'replicas diverged'
+
+
+ELBO_DP_WORKER = r'''
+import os, sys, hashlib
+import numpy as np
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+import vaemolsim_b200 as v
+from vaemolsim_b200 import parallel
+from oracle import vae as ovae
+from helpers import vae_from_oracle
+
+grp = parallel.Group()
+rank, world = grp.rank, grp.world
+P = ovae.init_vae(5, dx=6, dz=2, hidden=200, prior='realnvp', num_blocks=4, num_bins=32, flow_hidden=100)
+B = 4096
+rng = np.random.default_rng(17)
+x = rng.standard_normal((world * B, 6), dtype=np.float32)
+eps = rng.standard_normal((world * B, 2), dtype=np.float32)
+lo, hi = rank * B, (rank + 1) * B
+xd, ed = v.Tensor.from_numpy(x[lo:hi]), v.Tensor.from_numpy(eps[lo:hi])
+opt = v.models.Adam(1e-3)
+res = {}
+for name in ('fused', 'separate'):
+    model = vae_from_oracle(v, P, max_batch=B, weight=1.0)
+    f = model.fused(B)
+    assert f.path(B) == 'tensor-core-fused'
+    pe = parallel.PeerExchange(grp, f.n_params)
+    n0 = v._abi.launch_count()
+    for step in range(5):
+        if name == 'fused':
+            pe.train_step(f, xd, ed, B, opt)            # tile kernel + finish / exchange / Adam kernel
+        else:
+            f.forward_backward(xd, ed, grad_ptr=pe.next_slot())
+            pe.allreduce_adam(f, opt)                   # the separate exchange kernel
+    v.synchronize()
+    res[name] = (f.theta.numpy().copy(), f.scalars.numpy().copy(), v._abi.launch_count() - n0)
+    assert not pe.timed_out()
+    pe.close()
+same = bool(np.array_equal(res['fused'][0], res['separate'][0]))
+print('RESULT %%d %%d %%d %%d %%s' %% (rank, int(same), res['fused'][2], res['separate'][2],
+                                     hashlib.sha1(res['fused'][0].tobytes()).hexdigest()), flush=True)
+grp.close()
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_elbo_data_parallel_step_with_exchange_in_the_finish_kernel_two_gpus(tmp_path):
+    """`vms_elbo_train_step_peer` at the C2 shape on two GPUs: the finish kernel of the whole-step tensor-core plan performs
+    the NVLink exchange + Adam + next weight images itself (two launches per step after the first) -- bit-identical parameters
+    to forward_backward + the separate `vms_peer_allreduce_adam` kernel, replicas bit-identical."""
+    import ctypes
+    from vaemolsim_b200 import _abi
+    n = ctypes.c_int(0)
+    _abi.load().vms_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip('needs 2 GPUs')
+    script = tmp_path / 'elbo_dp_worker.py'
+    script.write_text(ELBO_DP_WORKER % {'root': ROOT})
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1',
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=280)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    res = [[ln for ln in o.splitlines() if ln.startswith('RESULT')][0].split() for o in outs]
+    assert all(r[2] == '1' for r in res), res                 # fused finish + exchange == separate kernels, bit for bit
+    assert all(int(r[3]) == 11 for r in res), res             # 5 steps x 2 launches + the first step's pre-pack
+    assert all(int(r[4]) == 20 for r in res), res             # separate path: pre-pack, tile, finish, exchange per step
+    assert res[0][5] == res[1][5], 'replicas diverged'

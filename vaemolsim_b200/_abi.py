@@ -168,6 +168,8 @@ _SIGS = {
     'vms_ipc_get_handle': (None, [c_vp, c_vp]),
     'vms_ipc_open_handle': (None, [c_vp, C.POINTER(c_vp)]),
     'vms_ipc_close_handle': (None, [c_vp]),
+    'vms_elbo_train_step_peer': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_int,
+                                        c_int, C.POINTER(c_vp), C.c_ulonglong, c_vp]),
     'vms_peer_allreduce_adam': (None, [c_int, c_int, C.POINTER(c_vp), c_i64, C.c_ulonglong, c_f32, c_vp, c_vp, c_vp, c_i64,
                                        c_f64, c_f64, c_f64, c_f64, c_vp, c_vp]),
     'vms_mc_param_count': (c_i64, [C.POINTER(McDesc)]),

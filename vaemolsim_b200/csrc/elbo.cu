@@ -12,6 +12,7 @@
 // sized once for max_batch -- and replays the whole step as ONE CUDA graph per (batch, pointer set): the step is
 // ~60 small kernels whose launch overhead would otherwise dominate at the named batch of 4096.
 #include "elbo_plan.cuh"
+#include "peer.cuh"
 #include "flow_tc.cuh"
 #include "mlp_stream.cuh"
 #include <math.h>
@@ -609,6 +610,34 @@ vms_status vms_elbo_forward_backward(vms_elbo_plan pl, const float* theta, const
     VMS_TRY(forward_body(pl, theta, x, eps, B, scalars, st));
     return backward_body(pl, theta, x, eps, B, grad, st);
   });
+}
+
+/* One DATA-PARALLEL training step: forward + backward, the gradient exchange over NVLink peer memory and Keras Adam.  When the
+ * whole-step tensor-core kernel serves the batch, its finish kernel does the exchange itself (two launches per step); every
+ * other plan writes its gradient into this rank's slot and launches vms_peer_allreduce_adam.  step / peer_bases as there. */
+vms_status vms_elbo_train_step_peer(vms_elbo_plan pl, float* theta, const float* x, const float* eps, int64_t B, float* scalars,
+                                    float* m, float* v, int64_t t, double lr, double beta1, double beta2, double eps_adam,
+                                    int world, int rank, void* const* peer_bases, unsigned long long step, vms_stream stream) {
+  VMS_RANGE("vms_elbo_train_step_peer");
+  vms_status s = check_call(pl, theta, x, eps, B);
+  if (s) return s;
+  VMS_REQUIRE(m && v && t >= 1, VMS_ERR_INVALID_ARG, "elbo_train_step_peer: NULL m / v or t < 1");
+  const int64_t P = pl->off.total;
+  if (use_tcf(pl, B) && tcf_peer_ok(pl)) {
+    PeerArgs a = {};
+    if ((s = peer_fill_args(a, world, rank, peer_bases, P, step, 1.0f / (float)world))) return s;
+    a.theta = theta; a.m = m; a.v = v;
+    a.lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
+    a.one_minus_b1 = (float)(1.0 - beta1);
+    a.one_minus_b2 = (float)(1.0 - beta2);
+    a.eps = (float)eps_adam;
+    return tcf_run(pl, theta, x, eps, B, nullptr, scalars, as_stream(stream), nullptr, &a);
+  }
+  VMS_REQUIRE(peer_bases && rank >= 0 && rank < world && peer_bases[rank], VMS_ERR_INVALID_ARG, "elbo_train_step_peer: bad peers");
+  float* slot = (float*)peer_bases[rank] + (int64_t)(step & 1ull) * P;
+  if ((s = vms_elbo_forward_backward(pl, theta, x, eps, B, slot, scalars, stream))) return s;
+  return vms_peer_allreduce_adam(world, rank, peer_bases, P, step, 1.0f / (float)world, theta, m, v, t, lr, beta1, beta2, eps_adam,
+                                 nullptr, stream);
 }
 
 /* One training step: ELBO forward + backward + Keras Adam (tests/test_models.py:181) on the flat buffers.  On the fused

@@ -105,8 +105,10 @@ bool tcf_available(const vms_elbo_plan_s* pl, int64_t B);
 void tcf_invalidate(vms_elbo_plan_s* pl);  // the packed weight images no longer describe theta
 vms_status tcf_set_timing(vms_elbo_plan_s* pl, int max_launches);
 vms_status tcf_kernel_ms(vms_elbo_plan_s* pl, double* total_ms, int* launches);  // ADDS to both outputs
+struct PeerArgs;
+bool tcf_peer_ok(vms_elbo_plan_s* pl);
 vms_status tcf_run(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B, float* grad,
-                   float* scalars, cudaStream_t st, const FusedAdam* adam = nullptr);
+                   float* scalars, cudaStream_t st, const FusedAdam* adam = nullptr, const PeerArgs* peer = nullptr);
 vms_status fused_run(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B, bool backward,
                      float* z, float* logq, float* logpz, float* logpx, float* grad, float* scalars, cudaStream_t st,
                      const FusedAdam* adam = nullptr);

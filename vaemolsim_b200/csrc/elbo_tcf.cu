@@ -36,6 +36,7 @@
 // The helper functions up to issue_product are the ones of flow_tc.cu (kept in step by hand until both kernels settle).
 #include "elbo_plan.cuh"
 #include "flow_tc.cuh"
+#include "peer.cuh"
 #include "rqs_device.cuh"
 #include <math.h>
 #include <string.h>
@@ -847,6 +848,87 @@ __global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_kernel(const float* 
   }
 }
 
+// Data-parallel step: the finish kernel and the NVLink exchange in ONE launch.  Phase 1 (never blocks): the tile partials are
+// summed exactly as above and this rank's gradient lands in its slot of the peer buffer; the block that finishes last raises
+// this rank's flag in every peer's buffer.  Phase 2: block 0 waits (bounded) for every rank's flag and decides for the grid,
+// the other blocks wait for its decision.  Phase 3: every parameter's gradient is pulled from all ranks' slots over NVLink,
+// summed in rank order, scaled, and the Adam update writes theta AND the next step's weight images -- a data-parallel step is
+// two launches (tile kernel + this one), like the single-GPU step.  The whole grid must be co-resident (phase 2 waits for
+// blocks of phase 1): the launcher checks it and otherwise keeps the separate finish / exchange kernels.
+__global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_peer_kernel(const float* __restrict__ gpart, int n_part, int P, int P2,
+                                                                        const int* __restrict__ part_map,
+                                                                        const float* __restrict__ spart, int64_t B, float klw,
+                                                                        float* __restrict__ scalars, const PeerArgs a,
+                                                                        const unsigned* __restrict__ pack_map,
+                                                                        float* __restrict__ fpk, unsigned short* __restrict__ wpk,
+                                                                        size_t part) {
+  __shared__ float sh[kFinG][kFinP];
+  __shared__ int failed;
+  const int tx = threadIdx.x & (kFinP - 1), g = threadIdx.x / kFinP;
+  const int i = blockIdx.x * kFinP + tx;
+  const bool live = i < P;
+  // timeline of the last step in flag slots 56 .. 59 (nanoseconds of %globaltimer: entry of block 0, gradient complete, exchange
+  // decided, block 0 done) -- read by scripts/time_dp_step.py
+  unsigned long long* trace = flags_of(a.base[a.rank], a.P) + 56;
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace[0] = globaltimer_ns();
+  float th = 0.f, mi = 0.f, vi = 0.f;
+  if (live && g == 0) { th = a.theta[i]; mi = a.m[i]; vi = a.v[i]; }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    const int per = (n_part + kFinG - 1) / kFinG;
+    const int c0 = g * per, c1 = min(n_part, c0 + per);
+    const float* src = gpart + __ldg(part_map + i);
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += src[(size_t)(c + u) * P2];
+    }
+    for (; c < c1; ++c) acc[0] += src[(size_t)c * P2];
+  }
+  sh[g][tx] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  __syncthreads();
+  if (g == 0 && live) {
+    const float t = (sh[0][tx] + sh[1][tx]) + (sh[2][tx] + sh[3][tx]);
+    a.base[a.rank][(int64_t)(a.step & 1ull) * a.P + i] = t;  // my slot of this step
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && scalars) {
+    float sa = 0.f, sc = 0.f;
+    for (int c = 0; c < n_part; ++c) { sa += spart[2 * c]; sc += spart[2 * c + 1]; }
+    const float kl = sa / (float)B, nll = sc / (float)B;
+    scalars[0] = nll + klw * kl;
+    scalars[1] = nll;
+    scalars[2] = kl;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // release pattern: the block's slot stores happen before this barrier; ONE device-scope fence by thread 0 (fences are
+    // cumulative) orders them before the counter increment, and the block that observes the final count issues the
+    // system-scope fence before it raises the flags (a fence.sys per writing thread cost ~10 us per step)
+    unsigned long long* counter = flags_of(a.base[a.rank], a.P) + 41;
+    __threadfence();
+    const unsigned long long done = atomicAdd(counter, 1ull) + 1ull;
+    if (done == (unsigned long long)gridDim.x) {  // the whole gradient of this rank is in its slot
+      *counter = 0ull;
+      trace[1] = globaltimer_ns();
+      peer_raise_flags(a);
+    }
+    failed = blockIdx.x == 0 ? peer_wait_and_decide(a) : peer_wait_decision(a);
+    if (blockIdx.x == 0) trace[2] = globaltimer_ns();
+  }
+  __syncthreads();
+  if (failed || !(g == 0 && live)) return;
+  const float gsum = peer_pull_sum(a, i);
+  if (a.grad_out) a.grad_out[i] = gsum;
+  mi = mi + (gsum - mi) * a.one_minus_b1;
+  vi = vi + (gsum * gsum - vi) * a.one_minus_b2;
+  a.m[i] = mi;
+  a.v[i] = vi;
+  th = th - a.lr_t * mi / (sqrtf(vi) + a.eps);
+  a.theta[i] = th;
+  pack_store(th, __ldg(pack_map + i), fpk, wpk, part);
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace[3] = globaltimer_ns();
+}
+
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
@@ -855,6 +937,7 @@ struct TcfCfg {
   TParams p;
   size_t smem;
   int max_tiles;
+  int peer_ok = -1;  // fused finish + exchange kernel usable (grid co-resident): -1 = not probed yet
   bool exact;       // MLP images in the C2 widths (DI, DO) = (8, 4) / (4, 12); else padded to (8, 16) / (8, 16)
   float *gpart, *spart, *fpk;
   unsigned short* wpk;
@@ -1056,8 +1139,20 @@ vms_status tcf_kernel_ms(vms_elbo_plan_s* pl, double* total_ms, int* launches) {
 
 // forward + backward (+ Adam when `adam`): the tile kernel and the finish kernel; the pre-pack kernel only when the
 // images are not known to match theta (first call, parameters changed behind the plan's back)
+bool tcf_peer_ok(vms_elbo_plan_s* pl) {
+  TcfCfg* f = pl->tcf;
+  if (!f) return false;
+  if (f->peer_ok < 0) {  // phase 2 of the fused finish + exchange kernel needs the whole grid resident
+    int per_sm = 0;
+    const bool ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tcf_finish_peer_kernel, kFinP * kFinG, 0) == cudaSuccess;
+    const char* e = getenv("VMS_TCF_PEER_FINISH");
+    f->peer_ok = (ok && (int64_t)per_sm * sm_count() >= (f->p.P + kFinP - 1) / kFinP && !(e && e[0] == '0')) ? 1 : 0;
+  }
+  return f->peer_ok == 1;
+}
+
 vms_status tcf_run(vms_elbo_plan_s* pl, const float* theta, const float* x, const float* eps, int64_t B, float* grad,
-                   float* scalars, cudaStream_t st, const FusedAdam* adam) {
+                   float* scalars, cudaStream_t st, const FusedAdam* adam, const PeerArgs* peer) {
   TcfCfg* f = pl->tcf;
   VMS_REQUIRE(f && tcf_available(pl, B), VMS_ERR_UNSUPPORTED, "elbo (mode 3): shape or batch not supported");
   TParams p = f->p;
@@ -1084,6 +1179,15 @@ vms_status tcf_run(vms_elbo_plan_s* pl, const float* theta, const float* x, cons
 #undef VMS_TCF_LAUNCH
   VMS_LAUNCH_CHECK("tcf_kernel");
   if (timed) VMS_CUDA(cudaEventRecord(f->ev[f->ev_used++].second, st));
+  if (peer) {  // data-parallel: finish + exchange + Adam + next images in one launch
+    tcf_finish_peer_kernel<<<(p.P + kFinP - 1) / kFinP, kFinP * kFinG, 0, st>>>(f->gpart, n_tiles, p.P, p.P2, f->part_map, f->spart, B,
+                                                                                 p.klw, scalars ? scalars : pl->scalars, *peer,
+                                                                                 f->pack_map, f->fpk, f->wpk, f->part);
+    VMS_LAUNCH_CHECK("tcf_finish_peer_kernel");
+    f->pack_valid = peer->theta == theta;
+    f->pack_theta = theta;
+    return VMS_OK;
+  }
   TcfAdam ad = {};
   if (adam) {
     ad.theta = adam->theta; ad.m = adam->m; ad.v = adam->v;

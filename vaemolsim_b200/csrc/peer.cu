@@ -21,107 +21,62 @@
 // at step s + 2, after it has passed the barrier of step s + 1, which every peer can only have signalled after its own
 // step-s kernel -- the last reader of slot s & 1 -- completed.
 // One process per GPU: the kernel waits on OTHER GPUs' kernels, never on another kernel of the same GPU.
-#include "common.cuh"
+#include "peer.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
 namespace vms {
 
-constexpr int kMaxPeers = 8;
-constexpr int kFlagSlots = 64;
-
-struct PeerArgs {
-  int world, rank;
-  float* base[kMaxPeers];  // every rank's buffer as mapped into THIS process ([rank] = own allocation)
-  int64_t P;
-  unsigned long long step;  // 1, 2, 3, ... (monotonic)
-  float grad_scale;
-  float *theta, *m, *v;
-  float lr_t, one_minus_b1, one_minus_b2, eps;
-  float* grad_out;  // optional: the reduced, scaled gradient [P]
-  unsigned long long timeout_ns;
-};
-
-__device__ __forceinline__ unsigned long long* flags_of(float* base, int64_t P) {
-  return reinterpret_cast<unsigned long long*>(base + 2 * P);
-}
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
-// Flag slots of a rank's buffer (uint64 each):  [0, 8) arrival flags written by the ranks;  32 + r: rank r gave up waiting
-// at that step (written by r into its own buffer);  40: this rank's grid-wide decision for the current step (2 step + failed,
-// written by block 0, read by the other blocks);  48: POISON -- some rank of the job timed out (written by that rank into
-// every buffer): from then on no rank updates its parameters, so replicas differ by at most the one step in flight and the
-// host (`PeerExchange.check`) raises instead of training on.
 __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(const PeerArgs a) {
   __shared__ int failed;
-  volatile unsigned long long* mine = flags_of(a.base[a.rank], a.P);
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) {
       // the gradient of this step was written by the preceding kernel on this stream; make it visible system-wide,
-      // then raise my flag in every rank's buffer (including my own)
-      __threadfence_system();
-      for (int r = 0; r < a.world; ++r) {
-        volatile unsigned long long* f = flags_of(a.base[r], a.P) + a.rank;
-        *f = a.step;
-      }
-      __threadfence_system();
-      // wait for every rank's flag in MY buffer.  Bounded (wall-clock nanoseconds, independent of the SM clock): a rank
-      // that never arrives must not hang this GPU.  ONE block decides for the grid, so all blocks agree.
-      int bad = mine[48] != 0ull ? 1 : 0;
-      const unsigned long long t0 = globaltimer_ns();
-      for (int r = 0; r < a.world && !bad; ++r) {
-        while (mine[r] < a.step) {
-          __nanosleep(64);
-          if (globaltimer_ns() - t0 > a.timeout_ns || mine[48] != 0ull) {
-            bad = 1;
-            break;
-          }
-        }
-      }
-      if (bad) {
-        mine[32 + a.rank] = a.step;
-        for (int r = 0; r < a.world; ++r) flags_of(a.base[r], a.P)[48] = a.step;  // poison every replica
-      }
-      __threadfence_system();
-      mine[40] = 2ull * a.step + (unsigned long long)bad;
-      failed = bad;
+      // then raise my flag in every rank's buffer (including my own) and wait for every rank's flag in MY buffer.
+      // Bounded (wall-clock nanoseconds, independent of the SM clock): a rank that never arrives must not hang this GPU.
+      // ONE block decides for the grid, so all blocks agree.
+      peer_raise_flags(a);
+      failed = peer_wait_and_decide(a);
     } else {
       // block 0 is always dispatched first and waits on nothing of this grid: no co-residency requirement
-      unsigned long long d;
-      while ((d = mine[40]) < 2ull * a.step) __nanosleep(32);
-      __threadfence();
-      failed = (int)(d & 1ull);
+      failed = peer_wait_decision(a);
     }
   }
   __syncthreads();
   if (failed) return;  // no update on a failed exchange: theta / m / v keep the last consistent state
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.P) return;
-  const int64_t off = (int64_t)(a.step & 1ull) * a.P + i;
-  // peer memory over NVLink: volatile = never served from this SM's L1 (the slot is reused every second step).  All loads
-  // are issued before the first addition: a `load; add` loop over the ranks serialises one NVLink round trip per rank
-  // (in-order issue stalls on each add), ~12 us of a 140 us step at 8 GPUs.  The sum stays in rank order, identical on
-  // every rank (trailing + 0.0f for absent ranks changes nothing).
-  float val[kMaxPeers];
-#pragma unroll
-  for (int r = 0; r < kMaxPeers; ++r)
-    val[r] = r < a.world ? *reinterpret_cast<volatile const float*>(a.base[r] + off) : 0.f;
-  float g = 0.f;
-#pragma unroll
-  for (int r = 0; r < kMaxPeers; ++r) g += val[r];
-  g *= a.grad_scale;
+  const float g = peer_pull_sum(a, i);
   if (a.grad_out) a.grad_out[i] = g;
   const float mi = a.m[i] + (g - a.m[i]) * a.one_minus_b1;
   const float vi = a.v[i] + (g * g - a.v[i]) * a.one_minus_b2;
   a.m[i] = mi;
   a.v[i] = vi;
   a.theta[i] = a.theta[i] - a.lr_t * mi / (sqrtf(vi) + a.eps);
+}
+
+unsigned long long peer_timeout_ns() {
+  static unsigned long long timeout_ms = 0;
+  if (!timeout_ms) {
+    const char* e = getenv("VMS_PEER_TIMEOUT_MS");
+    timeout_ms = e && atoll(e) > 0 ? (unsigned long long)atoll(e) : 2000ull;
+  }
+  return timeout_ms * 1000000ull;
+}
+
+vms_status peer_fill_args(PeerArgs& a, int world, int rank, void* const* peer_bases, int64_t n_params, unsigned long long step,
+                          float grad_scale) {
+  VMS_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, VMS_ERR_INVALID_ARG,
+              "peer exchange: world must be in [1, %d] and 0 <= rank < world", kMaxPeers);
+  VMS_REQUIRE(peer_bases && n_params >= 1 && step >= 1, VMS_ERR_INVALID_ARG, "peer exchange: bad arguments");
+  a.world = world; a.rank = rank; a.P = n_params; a.step = step; a.grad_scale = grad_scale;
+  for (int r = 0; r < world; ++r) {
+    VMS_REQUIRE(peer_bases[r], VMS_ERR_INVALID_ARG, "peer exchange: NULL peer buffer %d", r);
+    a.base[r] = (float*)peer_bases[r];
+  }
+  a.timeout_ns = peer_timeout_ns();
+  return VMS_OK;
 }
 
 }  // namespace vms
@@ -159,27 +114,15 @@ vms_status vms_peer_allreduce_adam(int world, int rank, void* const* peer_bases,
                                    float grad_scale, float* theta, float* m, float* v, int64_t t, double lr, double beta1,
                                    double beta2, double eps, float* grad_out, vms_stream stream) {
   VMS_RANGE("vms_peer_allreduce_adam");
-  VMS_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, VMS_ERR_INVALID_ARG,
-              "peer_allreduce_adam: world must be in [1, %d] and 0 <= rank < world", kMaxPeers);
-  VMS_REQUIRE(peer_bases && theta && m && v && n_params >= 1 && step >= 1 && t >= 1, VMS_ERR_INVALID_ARG,
-              "peer_allreduce_adam: bad arguments");
+  VMS_REQUIRE(theta && m && v && t >= 1, VMS_ERR_INVALID_ARG, "peer_allreduce_adam: bad arguments");
   PeerArgs a = {};
-  a.world = world; a.rank = rank; a.P = n_params; a.step = step; a.grad_scale = grad_scale;
-  for (int r = 0; r < world; ++r) {
-    VMS_REQUIRE(peer_bases[r], VMS_ERR_INVALID_ARG, "peer_allreduce_adam: NULL peer buffer %d", r);
-    a.base[r] = (float*)peer_bases[r];
-  }
+  vms_status fs = peer_fill_args(a, world, rank, peer_bases, n_params, step, grad_scale);
+  if (fs) return fs;
   a.theta = theta; a.m = m; a.v = v; a.grad_out = grad_out;
   a.lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
   a.one_minus_b1 = (float)(1.0 - beta1);
   a.one_minus_b2 = (float)(1.0 - beta2);
   a.eps = (float)eps;
-  static unsigned long long timeout_ms = 0;
-  if (!timeout_ms) {
-    const char* e = getenv("VMS_PEER_TIMEOUT_MS");
-    timeout_ms = e && atoll(e) > 0 ? (unsigned long long)atoll(e) : 2000ull;
-  }
-  a.timeout_ns = timeout_ms * 1000000ull;
   peer_allreduce_adam_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, as_stream(stream)>>>(a);
   VMS_LAUNCH_CHECK("peer_allreduce_adam_kernel");
   return VMS_OK;

@@ -672,9 +672,7 @@ class FusedELBO(object):
                                         L['ring'].ptr + 16 * slot, self.m.ptr, self.v.ptr, self.t, opt.learning_rate,
                                         opt.beta_1, opt.beta_2, opt.epsilon, c.stream)
             else:
-                lib.vms_elbo_forward_backward(self.handle, self.theta.ptr, L['xd'][b].ptr, L['ed'][b].ptr, n,
-                                              exchange.next_slot(), L['ring'].ptr + 16 * slot, c.stream)
-                exchange.allreduce_adam(self, opt)  # advances self.t
+                exchange.train_step(self, L['xd'][b], L['ed'][b], n, opt, scalars_ptr=L['ring'].ptr + 16 * slot)  # advances self.t
             lib.vms_event_record(L['free'][b], c.stream)
             used[b] = True
             if slot == R - 1 or i == len(starts) - 1:

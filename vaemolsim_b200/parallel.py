@@ -339,6 +339,24 @@ class PeerExchange(object):
                                              opt.beta_1, opt.beta_2, opt.epsilon, None if grad_out is None else grad_out.ptr,
                                              self.ctx.stream)
 
+    def train_step(self, fused, x, eps, n, opt, scalars_ptr=None):
+        """One data-parallel training step in one C call (`vms_elbo_train_step_peer`): forward + backward on this rank's
+        batch (device tensors / pointers x, eps with n rows), the NVLink gradient exchange and Adam -- two launches when the
+        whole-step tensor-core kernel serves the batch (its finish kernel does the exchange), otherwise the plan's own
+        launches + `vms_peer_allreduce_adam`.  All ranks must call it once per step."""
+        self.step += 1
+        fused.t += 1
+        from . import _abi
+        _abi.bump_param_epoch()
+        if self.check_every and self.step % self.check_every == 0:
+            self.check()
+        xp = x.ptr if hasattr(x, 'ptr') else x
+        ep = eps.ptr if hasattr(eps, 'ptr') else eps
+        self.ctx.lib.vms_elbo_train_step_peer(fused.handle, fused.theta.ptr, xp, ep, int(n),
+                                              fused.scalars.ptr if scalars_ptr is None else scalars_ptr, fused.m.ptr,
+                                              fused.v.ptr, fused.t, opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon,
+                                              self.world, self.rank, self.bases, self.step, self.ctx.stream)
+
     check_every = 256  # steps between host-side failure checks inside allreduce_adam (0: never)
 
     def timed_out(self):
