@@ -558,3 +558,26 @@ def test_deterministic_log_prob_on_device(vms):
     x[2, 1] += 1.0
     lp = d.log_prob(v.Tensor.from_numpy(x)).numpy()
     assert np.array_equal(lp, np.array([0.0, 0.0, -np.inf, 0.0], np.float32))
+
+
+@pytest.mark.parametrize('D,B,accumulate', [(6, 3 * 65536 + 77, 0), (3, 65536 + 256, 1), (2, 65536, 0), (8, 70001, 0)])
+def test_normal_rows_log_prob_streaming_ring(vms, D, B, accumulate):
+    """Planar Normal rows at streaming sizes: full 256-row chunks go through the bulk-copy ring (`normal_rows_lp_ring_kernel`),
+    the ragged tail through the thread-per-row kernel; float64 evaluation of tfp's Normal.log_prob with the softplus + eps
+    scale of dists.py:56-78 on every row."""
+    v = vms
+    c = v._abi.ctx()
+    rng = np.random.default_rng(D * 1000 + B % 1000)
+    x = rng.standard_normal((B, D), dtype=np.float32)
+    p = rng.standard_normal((B, 2 * D), dtype=np.float32)
+    lp0 = rng.standard_normal(B).astype(np.float32)
+    xd, pd, lp = v.Tensor.from_numpy(x), v.Tensor.from_numpy(p), v.Tensor.from_numpy(lp0)
+    i32 = lambda a: (C.c_int32 * len(a))(*a)
+    c.lib.vms_blockwise_log_prob(xd.ptr, D, pd.ptr, 2 * D, B, D, i32([0] * D), i32(list(range(D))), i32([-1] * D),
+                                 i32(list(range(D, 2 * D))), 2, lp.ptr, accumulate, c.stream)
+    x64, p64 = x.astype(np.float64), p.astype(np.float64)
+    sc = np.logaddexp(0.0, p64[:, D:]) + float(np.finfo(np.float32).eps)
+    want = (-0.5 * ((x64 - p64[:, :D]) / sc)**2 - 0.5 * np.log(2 * np.pi) - np.log(sc)).sum(axis=1)
+    if accumulate:
+        want = want + lp0
+    assert_close(lp.numpy(), want, rtol=1e-5, atol=2e-5, what='normal rows log_prob, ring + tail')
