@@ -24,6 +24,10 @@ are pushed through the reference's own layers; every output the oracle restates 
                      three log-probabilities per row, loss terms and the flat gradient by GradientTape
   tfp_distsel.npz    mappings.DistanceSelection on dense / ragged inputs with and without particle_info: values and top_k
                      indices
+  tfp_gaa.npz        mappings.AttentionBlock / ParticleEmbedding (mappings.py:480-688) over the REAL geometric_algebra_attention
+                     package (un-vendored, unpinned): inputs with zero-padded particles, every Keras variable of the layer by
+                     NAME (so the oracle's weight mapping can be checked without knowing Keras' creation order), outputs with
+                     and without mask_zero.  This is what pins oracle/gaa.py.
 The weight layouts are the oracle's (`oracle/vae.py::param_list`, `oracle/flows.py`), assigned into the Keras layers with
 `set_weights`, so the oracle consumes the same arrays unchanged.
 """
@@ -240,6 +244,46 @@ def dump_distsel(tf, tfp, vms, out):
                         select=sel.numpy(), select_info=sinfo.numpy(), indices=idx.numpy())
 
 
+def dump_gaa(tf, tfp, vms, out):
+    """Needs `geometric_algebra_attention` (pip install geometric-algebra-attention), as `vaemolsim.mappings` itself does."""
+    rng = np.random.default_rng(600)
+    res = {}
+    B, n, P = 5, 12, 9
+    coords = rng.uniform(-3, 3, (B, n, 3)).astype(np.float32)
+    info = np.round(rng.uniform(0, 1, (B, n, P))).astype(np.float32)
+    for b in range(B):  # DistanceSelection-style zero padding; cloud 1 is padding only
+        k = n if b == 1 else b
+        if k:
+            coords[b, n - k:] = 0
+            info[b, n - k:] = 0
+    res['coords'], res['info'] = coords, info
+
+    def randomise(layer):  # Keras initialisers give LayerNormalization gamma = 1, beta = 0 and zero biases: exercise them
+        for var in layer.variables:
+            var.assign(var + tf.constant(rng.normal(0, 0.1, var.shape).astype(np.float32)))
+
+    def store(prefix, layer):
+        res[prefix + '_names'] = np.array([v_.name for v_ in layer.variables])
+        for i, var in enumerate(layer.variables):
+            res['%s_var%d' % (prefix, i)] = var.numpy()
+
+    blk = vms.mappings.AttentionBlock(hidden_dim=16)
+    blk([tf.constant(coords), tf.constant(info)])
+    randomise(blk)
+    store('block', blk)
+    res['block_out'] = blk([tf.constant(coords), tf.constant(info)]).numpy()
+    mask = tf.reduce_any(tf.not_equal(tf.constant(coords), 0.0), axis=-1)
+    res['block_out_masked'] = blk([tf.constant(coords), tf.constant(info)], mask=[mask, None]).numpy()
+    for mz in (True, False):
+        pe = vms.mappings.ParticleEmbedding(10, hidden_dim=16, num_blocks=2, mask_zero=mz)
+        pe(tf.constant(coords), tf.constant(info))
+        randomise(pe)
+        tag = 'embed_mask' if mz else 'embed_nomask'
+        store(tag, pe)
+        res[tag + '_out'] = pe(tf.constant(coords), tf.constant(info)).numpy()
+    np.savez_compressed(os.path.join(out, 'tfp_gaa.npz'), **res)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reference', default='/root/reference')
@@ -248,9 +292,12 @@ def main():
     tf, tfp, vms = need_tf(args.reference)
     sys.path.insert(0, ROOT)
     os.makedirs(args.out, exist_ok=True)
-    for fn in (dump_rqs, dump_realnvp, dump_maf, dump_dists, dump_vae, dump_distsel):
-        fn(tf, tfp, vms, args.out)
-        print('wrote', fn.__name__)
+    for fn in (dump_rqs, dump_realnvp, dump_maf, dump_dists, dump_vae, dump_distsel, dump_gaa):
+        try:
+            fn(tf, tfp, vms, args.out)
+            print('wrote', fn.__name__)
+        except ImportError as ex:  # dump_gaa without geometric_algebra_attention installed
+            print('skipped %s: %s' % (fn.__name__, ex))
 
 
 if __name__ == '__main__':

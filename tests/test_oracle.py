@@ -475,6 +475,40 @@ def test_oracle_matches_tfp_goldens_dists_and_selection():
     assert np.array_equal(sel, d['select']) and np.array_equal(sinfo, d['select_info']) and np.array_equal(idx, d['indices'])
 
 
+def _gaa_weights_by_name(g, prefix):
+    """Keras variables of a dumped layer -> oracle/gaa.py weight dicts, matched by variable NAME (geometric_algebra_attention
+    names its projections merge_kernel_<i> / join_kernel_<i>; Dense / LayerNormalization variables keep Keras' kernel / bias /
+    gamma / beta names in creation order inside each Sequential)."""
+    names = [str(n) for n in g[prefix + '_names']]
+    arrs = [g['%s_var%d' % (prefix, i)] for i in range(len(names))]
+
+    def take(pred):
+        return [a for n, a in zip(names, arrs) if pred(n)]
+
+    return names, arrs, take
+
+
+def test_oracle_matches_real_geometric_algebra_attention_goldens():
+    """oracle/gaa.py against outputs of the real geometric_algebra_attention + Keras layers (tfp_gaa.npz, written by
+    oracle/dump_tfp_goldens.py where the package exists): pins the pair layout, the invariants, the concat merge / join, the
+    masked softmax and LayerNormalization of the restatement.  Only the AttentionBlock is mapped here (one attention layer:
+    merge_kernel_0/1, join_kernel_1/2, then the three Sequentials in creation order score, value, nonlinearity)."""
+    from oracle import gaa as ogaa
+    g = _tfp_golden('tfp_gaa.npz')
+    names, arrs, take = _gaa_weights_by_name(g, 'block')
+    merge = sorted([(n, a) for n, a in zip(names, arrs) if 'merge_kernel' in n], key=lambda t: t[0])
+    join = sorted([(n, a) for n, a in zip(names, arrs) if 'join_kernel' in n], key=lambda t: t[0])
+    rest = [a for n, a in zip(names, arrs) if 'merge_kernel' not in n and 'join_kernel' not in n]
+    assert len(merge) == 2 and len(join) == 2 and len(rest) == 4 + 6 + 6, names
+    w = {'merge': [a for _, a in merge], 'join': [a for _, a in join], 'score': rest[0:4], 'value': rest[4:10],
+         'nonlin': rest[10:16]}
+    r, info = g['coords'].astype(np.float64), g['info'].astype(np.float64)
+    w64 = ogaa.cast(w, np.float64)
+    np.testing.assert_allclose(ogaa.attention_block(r, info, w64), g['block_out'], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(ogaa.attention_block(r, info, w64, mask=ogaa.keras_mask(g['coords'])), g['block_out_masked'],
+                               rtol=2e-5, atol=2e-5)
+
+
 def test_vonmises_cdf_gradient_restatement_matches_scipy_finite_differences():
     """oracle.dists.vonmises_cdf_and_dconcentration (tfp von_mises_cdf + its concentration derivative, the quantity behind
     the implicit reparameterisation gradient of von Mises samples): CDF against scipy, derivative against central
@@ -492,3 +526,35 @@ def test_vonmises_cdf_gradient_restatement_matches_scipy_finite_differences():
     s = np.array([-2.0, -0.5, 0.5, 2.0])
     ds = dists.vonmises_sample_dconcentration(s, 2.0)
     assert (ds[:2] > 0).all() and (ds[2:] < 0).all()
+
+
+def test_gaa_restatement_has_the_published_symmetries():
+    """oracle/gaa.py (restatement of geometric_algebra_attention's rank-2 VectorAttention, mappings.py:480-688): the
+    properties the reference's docstrings promise -- rotation invariance, permutation equivariance of AttentionBlock,
+    permutation invariance of ParticleEmbedding -- and masking: the information carried by masked particles cannot reach
+    the embedding."""
+    from oracle import gaa as ogaa
+    rng = np.random.default_rng(12)
+    B, n, P, E = 3, 9, 4, 10
+    r = rng.uniform(-3, 3, (B, n, 3))
+    info = rng.normal(size=(B, n, P))
+    r[0, 6:] = 0
+    w = ogaa.cast(ogaa.init_embedding(rng, P, E, hidden=12, num_blocks=2), np.float64)
+    out = ogaa.particle_embedding(r, info, w, 'tanh')
+    Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    np.testing.assert_allclose(ogaa.particle_embedding(r @ Q, info, w, 'tanh'), out, rtol=1e-9, atol=1e-10)
+    perm = rng.permutation(n)
+    np.testing.assert_allclose(ogaa.particle_embedding(r[:, perm], info[:, perm], w, 'tanh'), out, rtol=1e-9, atol=1e-10)
+    blk = w['blocks'][0]
+    vals = info @ w['info'][0] + w['info'][1]
+    a = ogaa.attention_block(r, vals, blk, 'tanh')
+    np.testing.assert_allclose(ogaa.attention_block(r[:, perm], vals[:, perm], blk, 'tanh'), a[:, perm], rtol=1e-9, atol=1e-10)
+    info2 = info.copy()
+    info2[0, 6:] += 5.0  # cloud 0: particles 6.. are padding (zero coordinates): masked out of every softmax
+    np.testing.assert_allclose(ogaa.particle_embedding(r, info2, w, 'tanh'), out, rtol=1e-9, atol=1e-10)
+    # attention weights are a distribution over j (reduce=False) / over all pairs (reduce=True)
+    _, att = ogaa.vector_attention(r, vals, blk, False, 'tanh', ogaa.keras_mask(r), return_attention=True)
+    np.testing.assert_allclose(att.sum(-1), 1.0, rtol=1e-12)
+    _, att = ogaa.vector_attention(r, vals, blk, True, 'tanh', ogaa.keras_mask(r), return_attention=True)
+    np.testing.assert_allclose(att.sum((1, 2)), 1.0, rtol=1e-12)
+    assert att[0, :, 6:].max() < 1e-300 and att[0, 6:, :].max() < 1e-300
