@@ -491,9 +491,20 @@ def backmap_leg(v, grp, ffma_peak, reps=5):
             c.synchronize()
             ms_all += ev.elapsed_ms(0, 1)
         ms_all = grp.max(ms_all) / reps
+        # end to end from HOST arrays: upload of the frame / sites, selection, embedding, descriptors read back
+        d_host = pe(*sel.select_from_frame(frame, ref, particle_info=kinds)).numpy()
+        grp.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            d_host = pe(*sel.select_from_frame(frame, ref, particle_info=kinds)).numpy()
+        e2e_s = grp.max(time.perf_counter() - t0) / reps
         flop = B * k * k * 3 * flop_pair
         rec = {'sites_per_gpu': B, 'ms_embedding': ms, 'ms_select_and_embed': ms_all, 'gpu_launches': launches,
                'sites_per_s': C3['rows'] / (ms * 1e-3), 'sites_per_s_with_selection': C3['rows'] / (ms_all * 1e-3),
+               'e2e': {'value': C3['rows'] / e2e_s, 'unit': 'sites/s', 'ms_per_call': e2e_s * 1e3,
+                       'h2d_bytes_per_step': int(frame.nbytes + kinds.nbytes + ref.nbytes), 'd2h_bytes_per_step': int(B * E * 4),
+                       'api': 'ParticleEmbedding(*DistanceSelection.select_from_frame(frame, ref, particle_info=...)).numpy() '
+                              'from host arrays (the shared-frame form of LocalParticleDescriptors)'},
                'tflops': flop / (ms * 1e-3) / 1e12, 'frac_of_fp32_ffma_measured': flop / (ms * 1e-3) / 1e12 / ffma_peak}
         # the op-by-op (training) path on a slice, same weights: pair tensors in HBM
         nb = min(256, B)
@@ -581,7 +592,7 @@ def backmap_leg(v, grp, ffma_peak, reps=5):
             'roofline': {'bound': 'ffma', 'kernel': 'gaa_attention_fwd_kernel<40, 20>', 'achieved': k50['tflops'], 'peak': ffma_peak,
                          'unit': 'TFLOP/s', 'frac': k50['frac_of_fp32_ffma_measured'], 'traffic': None,
                          'algorithmic_flop_per_pair_and_layer': flop_pair},
-            'cpu_baseline': k50.get('cpu_baseline'), **res}
+            'e2e': k50['e2e'], 'cpu_baseline': k50.get('cpu_baseline'), **res}
 
 
 # ------------------------------------------------------------------------------ FlowModel NLL training (generic tape path)
