@@ -251,6 +251,22 @@ vms_status vms_broadcast_scalar(const float* scalar, int64_t n, float* out, vms_
  *   g_ldj_total (nullable, device scalar): sum over the rows of the upstream gradient of the bijector's per-row log-det
  *   sum_d log gamma_d - 0.5 log(var_d + eps).   g_x += ..., g_gamma += ..., g_beta += ... (g_gamma / g_beta nullable).
  * workspace: vms_batchnorm_backward_workspace(D) bytes of device memory.  Fixed-order column sums (deterministic). */
+/* Cross-replica batch statistics for data-parallel training: each rank computes the moments of its shard
+ * (vms_batch_moments), packs n mean_r (stage 1) or n (var_r + (mean_r - mean)^2) (stage 2, mean_g = the global mean) plus n
+ * into buf [D + 1], the caller sums buf over the ranks (one small allreduce per stage) and vms_bn_sync_unpack divides by the
+ * summed count: the global mean / biased variance, i.e. tf.nn.moments of the whole batch.  Reverse mode: _backward_sums
+ * writes this rank's [s1 | s2 | G | B] as floats (2 D + 2), the caller sums a copy over the ranks, and _backward_apply uses
+ * the GLOBAL sums for g_x and the LOCAL ones for g_gamma / g_beta (the trainer sums parameter gradients over the ranks). */
+vms_status vms_bn_sync_pack(const float* mean_r, const float* var_r, const float* mean_g, int64_t n_rows, int D, float* buf,
+                            vms_stream stream);
+vms_status vms_bn_sync_unpack(const float* buf, int D, float* out, vms_stream stream);
+vms_status vms_batchnorm_backward_sums(const float* x, int64_t ld_x, int64_t B, int D, const float* mean, const float* var,
+                                       float eps, const float* g_out, int64_t ld_g, const float* g_ldj_total, float* sums,
+                                       void* workspace, vms_stream stream);
+vms_status vms_batchnorm_backward_apply(const float* x, int64_t ld_x, int64_t B, int D, const float* mean, const float* var,
+                                        const float* gamma, float eps, const float* g_out, int64_t ld_g, const float* local_sums,
+                                        const float* global_sums, float* g_x, int64_t ld_gx, float* g_gamma, float* g_beta,
+                                        vms_stream stream);
 size_t vms_batchnorm_backward_workspace(int D);
 vms_status vms_batchnorm_backward(const float* x, int64_t ld_x, int64_t B, int D, const float* mean, const float* var,
                                   const float* gamma, float eps, int batch_stats, const float* g_out, int64_t ld_g,

@@ -242,3 +242,82 @@ def test_elbo_data_parallel_step_with_exchange_in_the_finish_kernel_two_gpus(tmp
     assert all(int(r[3]) == 11 for r in res), res             # 5 steps x 2 launches + the first step's pre-pack
     assert all(int(r[4]) == 20 for r in res), res             # separate path: pre-pack, tile, finish, exchange per step
     assert res[0][5] == res[1][5], 'replicas diverged'
+
+
+DP_BN_WORKER = r'''
+import os, sys, hashlib
+import numpy as np
+sys.path.insert(0, %(root)r)
+import vaemolsim_b200 as v
+from vaemolsim_b200 import parallel
+import vaemolsim_b200._protocols as PR
+
+grp = parallel.Group()
+rank, world = grp.rank, grp.world
+d = v.dists
+
+
+def make():
+    v.set_seed(4)
+    flow = v.flows.RQSSplineRealNVP(num_blocks=2, batch_norm=True, rqs_params={'hidden_dim': 16, 'num_bins': 8})
+    dist = d.FlowedDistribution(flow, d.IndependentBlockwise(4, [d.Normal] * 4))
+    dist.flow(np.ones((1, 4), np.float32))
+    m = v.models.MappingToDistribution(dist, mapping=v.mappings.FCDeepNN(dist.params_size(), hidden_dim=24, activation='tanh',
+                                                                         batch_norm=True), name='decoder')
+    m.compile(optimizer=v.models.Adam(2e-3), loss=v.losses.LogProbLoss())
+    return m
+
+
+rng = np.random.default_rng(3)
+B = 128
+z = rng.normal(size=(B, 3)).astype(np.float32) * 2 + 1
+x = rng.normal(size=(B, 4)).astype(np.float32)
+lo, hi = parallel.shard_rows(B, rank, world)
+model = make()
+model(z[:2])
+w0 = np.concatenate([w.numpy().ravel() for w in model.weights])
+model.distribute(grp)
+for step in range(5):
+    model.train_on_batch(z[lo:hi], x[lo:hi])
+got = np.concatenate([w.numpy().ravel() for w in model.weights])
+ref = make()
+ref(z[:2])
+for step in range(5):
+    ref.train_on_batch(z, x)
+want = np.concatenate([w.numpy().ravel() for w in ref.weights])
+err = float(np.abs(got - want).max())
+moved = float(np.abs(want - w0).max())
+print('RESULT %%d %%.3e %%.3e %%s' %% (rank, err, moved, hashlib.sha1(got.tobytes()).hexdigest()), flush=True)
+grp.close()
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_cross_replica_batch_norm_statistics_two_gpus(tmp_path):
+    """Batch normalisation under data-parallel training (SURVEY 8f-3): the Keras layer inside FCDeepNN and the tfp bijector
+    between flow blocks normalise with the moments of the WHOLE batch (two small allreduces forward, one in the reverse mode),
+    so five sharded steps on two GPUs equal five steps on the whole batch in one process -- weights AND moving statistics --
+    and the replicas stay bit-identical."""
+    import ctypes
+    from vaemolsim_b200 import _abi
+    n = ctypes.c_int(0)
+    _abi.load().vms_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip('needs 2 GPUs')
+    script = tmp_path / 'dp_bn_worker.py'
+    script.write_text(DP_BN_WORKER % {'root': ROOT})
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1',
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=280)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    res = [[ln for ln in o.splitlines() if ln.startswith('RESULT')][0].split() for o in outs]
+    assert all(float(r[3]) > 1e-3 for r in res), res          # the steps moved the weights
+    assert all(float(r[2]) < 5e-5 for r in res), res          # sharded == whole batch up to float32 summation order
+    assert res[0][4] == res[1][4], 'replicas diverged'

@@ -123,6 +123,11 @@ _SIGS = {
     'vms_batch_moments': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vms_batchnorm_coeffs': (None, [c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vms_broadcast_scalar': (None, [c_vp, c_i64, c_vp, c_vp]),
+    'vms_bn_sync_pack': (None, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
+    'vms_bn_sync_unpack': (None, [c_vp, c_int, c_vp, c_vp]),
+    'vms_batchnorm_backward_sums': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'vms_batchnorm_backward_apply': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64,
+                                            c_vp, c_vp, c_vp]),
     'vms_batchnorm_backward_workspace': (c_size, [c_int]),
     'vms_batchnorm_backward': (None, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_f32, c_int, c_vp, c_i64, c_vp, c_vp, c_i64,
                                       c_vp, c_vp, c_vp, c_vp]),

@@ -126,9 +126,14 @@ class Trainer(object):
 
     def step(self, fn):
         c = ctx()
-        with Tape() as tape:
-            loss = fn()
-            tape.backward(loss)
+        from . import _protocols
+        _protocols._dp_group = self.group  # batch-normalisation layers: cross-replica batch statistics while this step runs
+        try:
+            with Tape() as tape:
+                loss = fn()
+                tape.backward(loss)
+        finally:
+            _protocols._dp_group = None
         self.t += 1
         seen = set()
         todo = []  # (weight, gradient, mask or None)

@@ -61,6 +61,16 @@ def _ptr(t):
     return None if t is None else t.ptr
 
 
+# data-parallel group of the training step in progress (set by _autodiff.Trainer.step): batch-normalisation layers then use
+# CROSS-REPLICA batch statistics, so that sharded training equals training on the whole batch
+_dp_group = None
+
+
+def _sync_group():
+    g = _dp_group
+    return g if (g is not None and getattr(g, 'world', 1) > 1) else None
+
+
 # ================================================================================================ layers
 class Layer(object):
     """Minimal stand-in for tf.keras.layers.Layer: lazy build on first call, named, get_config, weights."""
@@ -344,6 +354,16 @@ class _BatchNormState(object):
         B = x.shape[0]
         ws = Tensor(((int(c.lib.vms_batch_moments_workspace(B, self.D)) + 3) // 4,))
         c.lib.vms_batch_moments(x.ptr, x.ld, B, self.D, self._mean.ptr, self._var.ptr, ws.ptr, c.stream)
+        grp = _sync_group()
+        if grp is not None:  # global moments: two small allreduces (means, then the parallel-variance combination)
+            D = self.D
+            buf, mean_r = Tensor((D + 1,)), self._mean.copy()
+            c.lib.vms_bn_sync_pack(mean_r.ptr, None, None, B, D, buf.ptr, c.stream)
+            grp.allreduce_sum_device_(buf.ptr, D + 1, c.stream)
+            c.lib.vms_bn_sync_unpack(buf.ptr, D, self._mean.ptr, c.stream)
+            c.lib.vms_bn_sync_pack(mean_r.ptr, self._var.ptr, self._mean.ptr, B, D, buf.ptr, c.stream)
+            grp.allreduce_sum_device_(buf.ptr, D + 1, c.stream)
+            c.lib.vms_bn_sync_unpack(buf.ptr, D, self._var.ptr, c.stream)
         for mov, cur in ((self.moving_mean, self._mean), (self.moving_variance, self._var)):
             c.lib.vms_axpby(mov.ptr, cur.ptr, self.momentum, 1.0 - self.momentum, self.D, mov.ptr, c.stream)
         c.synchronize()  # the workspace is released when this frame returns
@@ -381,6 +401,17 @@ class _BatchNormState(object):
                     c.lib.vms_sum_all(tp.grad(ldj).ptr, B, 1.0, G.ptr, c.stream)
                 ws = Tensor((int(c.lib.vms_batchnorm_backward_workspace(D)) // 4 + 1, ))
                 g_x = tp.grad(x)
+                grp = _sync_group() if batch_stats else None
+                if grp is not None:  # cross-replica statistics: the reverse mode needs the column sums of ALL ranks
+                    loc, glob = Tensor((2 * D + 2,)), Tensor((2 * D + 2,))
+                    c.lib.vms_batchnorm_backward_sums(x.ptr, x.ld, B, D, m_.ptr, v_.ptr, eps, g_out.ptr, g_out.ld, _ptr(G), loc.ptr,
+                                                      ws.ptr, c.stream)
+                    c.lib.vms_memcpy_d2d(glob.ptr, loc.ptr, 4 * (2 * D + 2), c.stream)
+                    grp.allreduce_sum_device_(glob.ptr, 2 * D + 2, c.stream)
+                    c.lib.vms_batchnorm_backward_apply(x.ptr, x.ld, B, D, m_.ptr, v_.ptr, gamma.ptr, eps, g_out.ptr, g_out.ld,
+                                                       loc.ptr, glob.ptr, g_x.ptr, g_x.ld, tp.grad(gamma).ptr, tp.grad(beta).ptr,
+                                                       c.stream)
+                    return
                 c.lib.vms_batchnorm_backward(x.ptr, x.ld, B, D, m_.ptr, v_.ptr, gamma.ptr, eps, 1 if batch_stats else 0,
                                              g_out.ptr, g_out.ld, _ptr(G), g_x.ptr, g_x.ld, tp.grad(gamma).ptr,
                                              tp.grad(beta).ptr, ws.ptr, c.stream)

@@ -137,6 +137,58 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, int64_t ld_x, c
   }
 }
 
+// ---- cross-replica statistics (data-parallel training: SURVEY 8f-3 "extra allreduce of per-feature mean / var")
+// stage 1: buf[d] = n mean_r[d];  stage 2 (mean_g given): buf[d] = n (var_r[d] + (mean_r[d] - mean_g[d])^2);  buf[D] = n.
+// After a sum over the ranks, buf[d] / buf[D] is the global mean (stage 1) / the global biased variance (stage 2: the
+// parallel-variance combination, no E[x^2] - mean^2 cancellation).
+__global__ void bn_sync_pack_kernel(const float* __restrict__ mean_r, const float* __restrict__ var_r,
+                                    const float* __restrict__ mean_g, float n, int D, float* __restrict__ buf) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) {
+    if (!mean_g) buf[d] = n * mean_r[d];
+    else {
+      const float dm = mean_r[d] - mean_g[d];
+      buf[d] = n * (var_r[d] + dm * dm);
+    }
+  }
+  if (d == D) buf[D] = n;
+}
+__global__ void bn_sync_unpack_kernel(const float* __restrict__ buf, int D, float* __restrict__ out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) out[d] = buf[d] / buf[D];
+}
+// local sums of the reverse mode as floats: [s1 (D) | s2 (D) | G | B]
+__global__ void bn_bwd_pack_sums_kernel(const double* __restrict__ s1, const double* __restrict__ s2, const float* __restrict__ G,
+                                        float B, int D, float* __restrict__ out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) { out[d] = (float)s1[d]; out[D + d] = (float)s2[d]; }
+  if (d == D) { out[2 * D] = G ? *G : 0.f; out[2 * D + 1] = B; }
+}
+// g_x += gamma r (g - (S1 + xhat S2) / N) - G_all (x - mean) r^2 / N  with the GLOBAL sums S1, S2, G_all, N (summed over the
+// ranks); the parameter gradients take the LOCAL sums (the trainer sums them over the ranks afterwards).
+__global__ void bn_bwd_apply_sync_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ g, int64_t ld_g,
+                                         int64_t B, int D, const float* __restrict__ mean, const float* __restrict__ var,
+                                         const float* __restrict__ gamma, float eps, const float* __restrict__ loc,
+                                         const float* __restrict__ glob, float* __restrict__ g_x, int64_t ld_gx,
+                                         float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int64_t b = i / D;
+  const int d = (int)(i - b * D);
+  const float gm = gamma ? gamma[d] : 1.f;
+  const float r = 1.0f / sqrtf(var[d] + eps);
+  const float xc = x[b * ld_x + d] - mean[d];
+  const float N = glob[2 * D + 1], G_all = glob[2 * D];
+  float dx = g[b * ld_g + d] - (glob[d] + (xc * r) * glob[D + d]) / N;
+  dx *= gm * r;
+  dx -= G_all * xc * r * r / N;
+  g_x[b * ld_gx + d] += dx;
+  if (b == 0) {
+    if (g_beta) g_beta[d] += loc[d];
+    if (g_gamma) g_gamma[d] += loc[D + d] + loc[2 * D] / gm;
+  }
+}
+
 __global__ void broadcast_scalar_kernel(const float* __restrict__ s, int64_t n, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = *s;
@@ -196,6 +248,49 @@ vms_status vms_batchnorm_backward(const float* x, int64_t ld_x, int64_t B, int D
                                                                        batch_stats, s1, s2, g_ldj_total, g_x, ld_gx, g_gamma,
                                                                        g_beta);
   VMS_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_bn_sync_pack(const float* mean_r, const float* var_r, const float* mean_g, int64_t n_rows, int D, float* buf,
+                            vms_stream stream) {
+  VMS_REQUIRE(mean_r && buf && D >= 1 && n_rows >= 0 && (!mean_g || var_r), VMS_ERR_INVALID_ARG, "bn_sync_pack: bad arguments");
+  bn_sync_pack_kernel<<<(D + 1 + 127) / 128, 128, 0, as_stream(stream)>>>(mean_r, var_r, mean_g, (float)n_rows, D, buf);
+  VMS_LAUNCH_CHECK("bn_sync_pack_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_bn_sync_unpack(const float* buf, int D, float* out, vms_stream stream) {
+  VMS_REQUIRE(buf && out && D >= 1, VMS_ERR_INVALID_ARG, "bn_sync_unpack: bad arguments");
+  bn_sync_unpack_kernel<<<(D + 127) / 128, 128, 0, as_stream(stream)>>>(buf, D, out);
+  VMS_LAUNCH_CHECK("bn_sync_unpack_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_batchnorm_backward_sums(const float* x, int64_t ld_x, int64_t B, int D, const float* mean, const float* var,
+                                       float eps, const float* g_out, int64_t ld_g, const float* g_ldj_total, float* sums,
+                                       void* workspace, vms_stream stream) {
+  VMS_REQUIRE(x && mean && var && g_out && sums && workspace, VMS_ERR_INVALID_ARG, "batchnorm_backward_sums: NULL pointer");
+  VMS_REQUIRE(B >= 1 && D >= 1, VMS_ERR_SHAPE, "batchnorm_backward_sums: need B >= 1, D >= 1");
+  cudaStream_t st = as_stream(stream);
+  double* s1 = (double*)workspace;
+  double* s2 = s1 + D;
+  bn_bwd_sums_kernel<<<(D + 31) / 32, 256, 0, st>>>(x, ld_x, g_out, ld_g, B, D, mean, var, eps, s1, s2);
+  VMS_LAUNCH_CHECK("bn_bwd_sums_kernel");
+  bn_bwd_pack_sums_kernel<<<(D + 1 + 127) / 128, 128, 0, st>>>(s1, s2, g_ldj_total, (float)B, D, sums);
+  VMS_LAUNCH_CHECK("bn_bwd_pack_sums_kernel");
+  return VMS_OK;
+}
+
+vms_status vms_batchnorm_backward_apply(const float* x, int64_t ld_x, int64_t B, int D, const float* mean, const float* var,
+                                        const float* gamma, float eps, const float* g_out, int64_t ld_g, const float* local_sums,
+                                        const float* global_sums, float* g_x, int64_t ld_gx, float* g_gamma, float* g_beta,
+                                        vms_stream stream) {
+  VMS_REQUIRE(x && mean && var && g_out && g_x && local_sums && global_sums, VMS_ERR_INVALID_ARG,
+              "batchnorm_backward_apply: NULL pointer");
+  VMS_REQUIRE(B >= 1 && D >= 1, VMS_ERR_SHAPE, "batchnorm_backward_apply: need B >= 1, D >= 1");
+  bn_bwd_apply_sync_kernel<<<(unsigned)((B * D + 255) / 256), 256, 0, as_stream(stream)>>>(
+      x, ld_x, g_out, ld_g, B, D, mean, var, gamma, eps, local_sums, global_sums, g_x, ld_gx, g_gamma, g_beta);
+  VMS_LAUNCH_CHECK("bn_bwd_apply_sync_kernel");
   return VMS_OK;
 }
 

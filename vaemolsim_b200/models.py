@@ -64,8 +64,8 @@ class Model(P.Layer):
     def distribute(self, group):
         """Data-parallel training over `group` (`parallel.Group`, one process per GPU): `fit` / `train_on_batch` run on this
         rank's shard of the data and every step sums the gradients of all weights over the ranks (one NCCL allreduce) before
-        Adam, so the replicas stay identical.  Batch-normalisation layers keep per-replica batch statistics, as Keras'
-        BatchNormalization does under a mirrored strategy.  Pass None to go back to single-process training."""
+        Adam, so the replicas stay identical.  Batch-normalisation layers use cross-replica batch statistics (the moments of
+        the whole batch: two small allreduces per layer forward, one in the reverse mode), i.e. single-device semantics.  Pass None to go back to single-process training."""
         self._dp_group = group
         return self
 
