@@ -257,6 +257,8 @@ def measured_peaks(v):
     c.lib.vms_probe_ffma(2048, 3, C.byref(t), C.byref(ms), c.stream)
     out['fp32_ffma_tflops'] = t.value
     out['fp32_ffma_nominal_tflops'] = c.sm_count * 128 * 2 * 1.965e9 / 1e12
+    c.lib.vms_probe_ffma2(2048, 3, C.byref(t), C.byref(ms), c.stream)
+    out['fp32_ffma2_packed_tflops'] = t.value  # fma.rn.f32x2: the same FLOP rate with half the issue slots
     for kind, name in ((0, 'bf16'), (1, 'tf32')):
         for M, N in ((128, 256), (64, 96)):
             c.lib.vms_probe_mma(kind, M, N, 8000, 3, C.byref(t), C.byref(ms), c.stream)
@@ -589,7 +591,7 @@ def backmap_leg(v, grp, ffma_peak, reps=5):
             'unit': 'sites/s', 'scaling': 'strong (sites sharded, no collective)',
             'workload': 'C3 box (N = 10,000, L = 46.416, cutoff 3.0): %d sites x k nearest particles -> ParticleEmbedding(20, '
                         'hidden 40, 2 blocks), fused forward' % C3['rows'],
-            'roofline': {'bound': 'ffma', 'kernel': 'gaa_attention_fwd_kernel<40, 20>', 'achieved': k50['tflops'], 'peak': ffma_peak,
+            'roofline': {'bound': 'ffma', 'kernel': 'gaa_attention_fwd_x2_kernel<40, 20, relu> (packed fma.rn.f32x2, two pairs per trip)', 'achieved': k50['tflops'], 'peak': ffma_peak,
                          'unit': 'TFLOP/s', 'frac': k50['frac_of_fp32_ffma_measured'], 'traffic': None,
                          'algorithmic_flop_per_pair_and_layer': flop_pair},
             'e2e': k50['e2e'], 'cpu_baseline': k50.get('cpu_baseline'), **res}

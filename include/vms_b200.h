@@ -634,6 +634,8 @@ vms_status vms_gaa_attention_forward(const float* coords, const float* values, i
  *                   kind::tf32 (K = 8): one CTA per SM issues n_mma back-to-back M x N x K MMAs on shared-memory-resident
  *                   operands into two alternating TMEM accumulators; nothing is loaded or stored in the timed region.     */
 vms_status vms_probe_ffma(int iters, int reps, double* tflops, double* ms, vms_stream stream);
+/* The same with the packed instruction fma.rn.f32x2 (SASS FFMA2: two float32 FMAs per instruction and register pair). */
+vms_status vms_probe_ffma2(int iters, int reps, double* tflops, double* ms, vms_stream stream);
 vms_status vms_probe_mma(int kind, int M, int N, int n_mma, int reps, double* tflops, double* ms, vms_stream stream);
 
 #ifdef __cplusplus

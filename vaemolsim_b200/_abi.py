@@ -215,6 +215,7 @@ _SIGS = {
     'vms_gaa_attention_forward': (None, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, C.POINTER(GaaWeights), c_int,
                                          c_int, c_f32, c_vp, c_vp]),
     'vms_probe_ffma': (None, [c_int, c_int, C.POINTER(c_f64), C.POINTER(c_f64), c_vp]),
+    'vms_probe_ffma2': (None, [c_int, c_int, C.POINTER(c_f64), C.POINTER(c_f64), c_vp]),
     'vms_probe_mma': (None, [c_int, c_int, c_int, c_int, c_int, C.POINTER(c_f64), C.POINTER(c_f64), c_vp]),
     'vms_elbo_forward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_elbo_forward_backward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),

@@ -671,6 +671,328 @@ __global__ void __launch_bounds__(256) gaa_attention_fwd_kernel(GaaFwdParams p) 
 #undef WT
 }
 
+// ---- the same kernel with PACKED float32 arithmetic (fma.rn.f32x2 = SASS FFMA2: two independent round-to-nearest FMAs per
+// instruction on a 64-bit register pair; measured by vms_probe_ffma2: the same FLOP rate as FFMA with half the issue slots).
+// Two pairs per trip; every per-pair vector lives as (column d, column d + 1) register pairs, the weight pair of two adjacent
+// columns is one 8-byte half of a 16-byte shared-memory broadcast, the per-pair scalar multiplier is duplicated once per row
+// of the weight matrix.  Same operations in the same order as the scalar kernels above (results agree to the last bits; the
+// softmax update's multiply-adds may contract differently).
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+  f2_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+  f2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+  f2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+template <int HP, int DP, int ACT>
+__global__ void __launch_bounds__(256) gaa_attention_fwd_x2_kernel(GaaFwdParams p) {
+  using L = GaaImg<HP, DP>;
+  constexpr int NP = 2, H2 = HP / 2, D2 = DP / 2;
+  extern __shared__ __align__(16) float smem[];
+  const int n = p.n, D = p.D, H = p.H;
+  float* W = smem;
+  float* s_r = smem + L::nPair;
+  float* s_u = s_r + ((3 * n + 3) & ~3);
+  float* s_w = s_u + n * DP;
+  float* s_v = s_w + n * DP;
+  float* s_st = s_v + n * DP;
+  uint8_t* s_m = reinterpret_cast<uint8_t*>(s_st + blockDim.x * (DP + 2));
+  const int t = threadIdx.x;
+  for (int k = t; k < L::nPair; k += blockDim.x) W[k] = p.img[k];
+  const f2_t* W2 = reinterpret_cast<const f2_t*>(W);  // (every image offset is a multiple of four floats)
+  const float* gM0 = p.img + L::oM0;
+  const float* gM1 = p.img + L::oM1;
+  const float inv_H = 1.f / (float)H;
+  const int tpr = p.tpr;
+  const int rows_per_pass = blockDim.x / tpr;
+
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    __syncthreads();
+    for (int k = t; k < 3 * n; k += blockDim.x) s_r[k] = p.coords[b * n * 3 + k];
+    for (int k = t; k < n; k += blockDim.x) s_m[k] = p.mask ? p.mask[b * n + k] : 1;
+    for (int k = t; k < n * DP; k += blockDim.x) {
+      const int q = k / DP, d = k % DP;
+      s_v[k] = d < D ? p.v[(b * n + q) * p.ldv + d] : 0.f;
+    }
+    __syncthreads();
+    for (int k = t; k < n * DP; k += blockDim.x) {
+      const int q = k / DP, d = k % DP;
+      float su = 0.f, sw = 0.f;
+      for (int c = 0; c < D; ++c) {
+        const float vv = s_v[q * DP + c];
+        su = fmaf(vv, __ldg(gM0 + c * DP + d), su);
+        sw = fmaf(vv, __ldg(gM1 + c * DP + d), sw);
+      }
+      s_u[k] = su;
+      s_w[k] = sw;
+    }
+    __syncthreads();
+
+    float red_m = -INFINITY, red_l = 0.f, red_o = 0.f;
+    for (int i0 = 0; i0 < n; i0 += rows_per_pass) {
+      const int i = i0 + t / tpr;
+      const int sub = t % tpr;
+      const bool active = (t / tpr) < rows_per_pass && i < n;
+      float m = -INFINITY, l = 0.f;
+      f2_t acc[D2];
+#pragma unroll
+      for (int d = 0; d < D2; ++d) acc[d] = 0ull;
+      if (active) {
+        const float* ri = s_r + 3 * i;
+        const bool mi = s_m[i];
+        const f2_t* wi2 = reinterpret_cast<const f2_t*>(s_w + i * DP);
+        for (int j0 = sub; j0 < n; j0 += NP * tpr) {
+          asm volatile("" ::: "memory");  // (keeps the loop-invariant weight loads inside the loop, see above)
+          int jj[NP];
+          bool ok[NP];
+          f2_t dot2[NP], nrm2[NP];
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            ok[q] = j0 + q * tpr < n;
+            jj[q] = ok[q] ? j0 + q * tpr : j0;
+            float dt, nr;
+            pair_invariants(s_r + 3 * jj[q], ri, dt, nr);
+            dot2[q] = f2_pack(dt, dt);
+            nrm2[q] = f2_pack(nr, nr);
+          }
+          // value net, first layer: h = nrm w1 + (dot w0 + b)
+          f2_t h[NP][H2];
+#pragma unroll
+          for (int k = 0; k < H2; ++k) {
+            const f2_t w0 = W2[(L::oWv1 >> 1) + k], w1 = W2[((L::oWv1 + HP) >> 1) + k], bb = W2[(L::obv1 >> 1) + k];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) h[q][k] = f2_fma(nrm2[q], w1, f2_fma(dot2[q], w0, bb));
+          }
+          // layer normalisation over the H true columns (scalar sums in column order, as the scalar kernel)
+          f2_t mean2[NP], rstd2[NP];
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            float mu = 0.f;
+#pragma unroll
+            for (int k = 0; k < H2; ++k) {
+              float a0, a1;
+              f2_unpack(h[q][k], a0, a1);
+              mu += (2 * k < H) ? a0 : 0.f;
+              mu += (2 * k + 1 < H) ? a1 : 0.f;
+            }
+            mu *= inv_H;
+            float var = 0.f;
+#pragma unroll
+            for (int k = 0; k < H2; ++k) {
+              float a0, a1;
+              f2_unpack(h[q][k], a0, a1);
+              const float d0 = a0 - mu, d1 = a1 - mu;
+              var += (2 * k < H) ? d0 * d0 : 0.f;
+              var += (2 * k + 1 < H) ? d1 * d1 : 0.f;
+            }
+            const float rs = rsqrtf(var * inv_H + p.ln_eps);
+            mean2[q] = f2_pack(-mu, -mu);
+            rstd2[q] = f2_pack(rs, rs);
+          }
+          f2_t iv[NP][D2];
+#pragma unroll
+          for (int d = 0; d < D2; ++d) {
+            const f2_t bb = W2[(L::obv2 >> 1) + d];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) iv[q][d] = bb;
+          }
+#pragma unroll
+          for (int k = 0; k < H2; ++k) {
+            const f2_t lg = W2[(L::oLg >> 1) + k], lb = W2[(L::oLb >> 1) + k];
+            f2_t a_lo[NP], a_hi[NP];  // activations of hidden units 2k, 2k + 1, each duplicated into a pair
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+              // ((h - mean) rstd) gamma + beta, the scalar kernel's operation order
+              const f2_t y = f2_fma(f2_mul(f2_add(h[q][k], mean2[q]), rstd2[q]), lg, lb);
+              float y0, y1;
+              f2_unpack(y, y0, y1);
+              y0 = act_t<ACT>(y0);
+              y1 = act_t<ACT>(y1);
+              a_lo[q] = f2_pack(y0, y0);
+              a_hi[q] = f2_pack(y1, y1);
+            }
+#pragma unroll
+            for (int d = 0; d < D2; ++d) {
+              const f2_t w0 = W2[((L::oWv2 + (2 * k) * DP) >> 1) + d], w1 = W2[((L::oWv2 + (2 * k + 1) * DP) >> 1) + d];
+#pragma unroll
+              for (int q = 0; q < NP; ++q) iv[q][d] = f2_fma(a_hi[q], w1, f2_fma(a_lo[q], w0, iv[q][d]));
+            }
+          }
+          // joined = iv J1 + (u_j + w_i) J2
+          f2_t jn[NP][D2];
+#pragma unroll
+          for (int q = 0; q < NP; ++q)
+#pragma unroll
+            for (int d = 0; d < D2; ++d) jn[q][d] = 0ull;
+#pragma unroll
+          for (int c = 0; c < D2; ++c) {
+            f2_t a_lo[NP], a_hi[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+              float x0, x1;
+              f2_unpack(iv[q][c], x0, x1);
+              a_lo[q] = f2_pack(x0, x0);
+              a_hi[q] = f2_pack(x1, x1);
+            }
+#pragma unroll
+            for (int d = 0; d < D2; ++d) {
+              const f2_t w0 = W2[((L::oJ1 + (2 * c) * DP) >> 1) + d], w1 = W2[((L::oJ1 + (2 * c + 1) * DP) >> 1) + d];
+#pragma unroll
+              for (int q = 0; q < NP; ++q) jn[q][d] = f2_fma(a_hi[q], w1, f2_fma(a_lo[q], w0, jn[q][d]));
+            }
+          }
+          {
+            f2_t j2[NP][D2];
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+#pragma unroll
+              for (int d = 0; d < D2; ++d) j2[q][d] = 0ull;
+#pragma unroll
+            for (int c = 0; c < D2; ++c) {
+              f2_t a_lo[NP], a_hi[NP];
+              const f2_t wi = wi2[c];
+#pragma unroll
+              for (int q = 0; q < NP; ++q) {
+                const f2_t mg = f2_add(reinterpret_cast<const f2_t*>(s_u + jj[q] * DP)[c], wi);
+                float x0, x1;
+                f2_unpack(mg, x0, x1);
+                a_lo[q] = f2_pack(x0, x0);
+                a_hi[q] = f2_pack(x1, x1);
+              }
+#pragma unroll
+              for (int d = 0; d < D2; ++d) {
+                const f2_t w0 = W2[((L::oJ2 + (2 * c) * DP) >> 1) + d], w1 = W2[((L::oJ2 + (2 * c + 1) * DP) >> 1) + d];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) j2[q][d] = f2_fma(a_hi[q], w1, f2_fma(a_lo[q], w0, j2[q][d]));
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+#pragma unroll
+              for (int d = 0; d < D2; ++d) jn[q][d] = f2_add(jn[q][d], j2[q][d]);
+          }
+          // score net: eight hidden units (four pairs) at a time
+          float sc[NP];
+#pragma unroll
+          for (int q = 0; q < NP; ++q) sc[q] = W[L::obs2];
+#pragma unroll
+          for (int k0 = 0; k0 < H2; k0 += 2) {
+            f2_t hh[NP][2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const f2_t bb = W2[(L::obs1 >> 1) + k0 + e];
+#pragma unroll
+              for (int q = 0; q < NP; ++q) hh[q][e] = bb;
+            }
+#pragma unroll
+            for (int c = 0; c < D2; ++c) {
+              f2_t a_lo[NP], a_hi[NP];
+#pragma unroll
+              for (int q = 0; q < NP; ++q) {
+                float x0, x1;
+                f2_unpack(jn[q][c], x0, x1);
+                a_lo[q] = f2_pack(x0, x0);
+                a_hi[q] = f2_pack(x1, x1);
+              }
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const f2_t w0 = W2[((L::oWs1 + (2 * c) * HP) >> 1) + k0 + e], w1 = W2[((L::oWs1 + (2 * c + 1) * HP) >> 1) + k0 + e];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) hh[q][e] = f2_fma(a_hi[q], w1, f2_fma(a_lo[q], w0, hh[q][e]));
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float w0, w1;
+              f2_unpack(W2[(L::oWs2 >> 1) + k0 + e], w0, w1);
+#pragma unroll
+              for (int q = 0; q < NP; ++q) {
+                float x0, x1;
+                f2_unpack(hh[q][e], x0, x1);
+                sc[q] = fmaf(act_t<ACT>(x0), w0, sc[q]);
+                sc[q] = fmaf(act_t<ACT>(x1), w1, sc[q]);
+              }
+            }
+          }
+          // online softmax, pair by pair in ascending j
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            if (!ok[q]) continue;
+            float s1 = sc[q];
+            if (!(mi && s_m[jj[q]])) s1 = kMaskedScore;
+            const float mn = fmaxf(m, s1);
+            const float scale = expf(m - mn);
+            const float e = expf(s1 - mn);
+            l = l * scale + e;
+            const f2_t sc2 = f2_pack(scale, scale), e2 = f2_pack(e, e);
+#pragma unroll
+            for (int d = 0; d < D2; ++d) acc[d] = f2_fma(acc[d], sc2, f2_mul(e2, jn[q][d]));
+            m = mn;
+          }
+        }
+      }
+      float* st = s_st + t * (DP + 2);
+      st[0] = m; st[1] = l;
+#pragma unroll
+      for (int d = 0; d < D2; ++d) f2_unpack(acc[d], st[2 + 2 * d], st[3 + 2 * d]);
+      __syncthreads();
+      if (!p.reduce) {
+        if (active) {
+          const int first = (t / tpr) * tpr;
+          float M = -INFINITY;
+          for (int q = 0; q < tpr; ++q) M = fmaxf(M, s_st[(first + q) * (DP + 2)]);
+          float Ls = 0.f;
+          for (int q = 0; q < tpr; ++q) {
+            const float* sq = s_st + (first + q) * (DP + 2);
+            if (sq[1] > 0.f) Ls += sq[1] * expf(sq[0] - M);
+          }
+          for (int d = sub; d < D; d += tpr) {
+            float o = 0.f;
+            for (int q = 0; q < tpr; ++q) {
+              const float* sq = s_st + (first + q) * (DP + 2);
+              if (sq[1] > 0.f) o += sq[2 + d] * expf(sq[0] - M);
+            }
+            p.out[(b * n + i) * D + d] = o / Ls;
+          }
+        }
+      } else if (t < DP) {
+        const int nact = min(rows_per_pass, n - i0) * tpr;
+        float M = red_m;
+        for (int q = 0; q < nact; ++q) M = fmaxf(M, s_st[q * (DP + 2)]);
+        const float sc0 = red_l > 0.f ? expf(red_m - M) : 0.f;
+        float Ls = red_l * sc0, o = red_o * sc0;
+        for (int q = 0; q < nact; ++q) {
+          const float* sq = s_st + q * (DP + 2);
+          if (sq[1] > 0.f) {
+            const float f = expf(sq[0] - M);
+            Ls += sq[1] * f;
+            o += sq[2 + t] * f;
+          }
+        }
+        red_m = M; red_l = Ls; red_o = o;
+      }
+      __syncthreads();
+    }
+    if (p.reduce && t < D) p.out[b * D + t] = red_o / red_l;
+  }
+}
+
 // the packed image (global memory), one buffer per device, reused by successive launches on the library's stream
 float* gaa_image_buffer() {
   static float* buf[64] = {};
@@ -689,8 +1011,9 @@ bool gaa_const_weights() {  // VMS_GAA_CONST=1 (and a build with -DVMS_GAA_WITH_
   return on == 1;
 }
 
-// pairs per trip of the pair loop: 2 when a thread walks at least four pairs (k = 50: 5.6 vs 6.4 ms per 4,096-site embedding;
-// every weight broadcast then feeds two FMAs), 1 for small clouds (k = 10: 0.56 vs 0.93 ms); VMS_GAA_NP=1|2 forces it
+// pairs per trip of the pair loop: 2 when a thread walks at least four pairs (k = 50, scalar arithmetic: 5.6 vs 6.4 ms per
+// 4,096-site embedding -- every weight broadcast then feeds two FMAs; packed arithmetic on top: 4.7 ms), 1 for small clouds
+// (k = 10: 0.56 vs 0.93 ms); VMS_GAA_NP=1|2 forces it
 int gaa_pairs_per_trip(int n, int tpr) {
   static int forced = -1;
   if (forced < 0) {
@@ -724,9 +1047,40 @@ vms_status gaa_fused_launch2(GaaFwdParams& p, cudaStream_t st) {
   return VMS_OK;
 }
 
+template <int HP, int DP, int ACT>
+vms_status gaa_fused_launch_x2(GaaFwdParams& p, cudaStream_t st) {
+  using L = GaaImg<HP, DP>;
+  int threads = ((p.n * p.tpr + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (threads < DP) threads = ((DP + 31) / 32) * 32;
+  const size_t fl = (size_t)L::nPair + ((3 * p.n + 3) & ~3) + (size_t)3 * p.n * DP + (size_t)threads * (DP + 2);
+  const size_t smem = fl * sizeof(float) + (size_t)((p.n + 15) & ~15);
+  VMS_REQUIRE(smem <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "gaa_attention_forward: cloud of %d particles does not fit",
+              p.n);
+  p.img = gaa_image_buffer();
+  VMS_REQUIRE(p.img, VMS_ERR_CUDA, "gaa_attention_forward: cannot allocate the weight image");
+  gaa_pack_kernel<HP, DP><<<(L::nW + 255) / 256, 256, 0, st>>>(p);
+  VMS_LAUNCH_CHECK("gaa_pack_kernel");
+  VMS_CUDA(cudaFuncSetAttribute(gaa_attention_fwd_x2_kernel<HP, DP, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t cap = 8 * (int64_t)sm_count();
+  const int grid = (int)(p.B < cap ? p.B : cap);
+  gaa_attention_fwd_x2_kernel<HP, DP, ACT><<<grid, threads, smem, st>>>(p);
+  VMS_LAUNCH_CHECK("gaa_attention_fwd_x2_kernel");
+  return VMS_OK;
+}
+
 template <int HP, int DP>
 vms_status gaa_fused_launch(GaaFwdParams& p, cudaStream_t st) {
-  const bool two = gaa_pairs_per_trip(p.n, p.tpr) == 2;
+  static int x2 = -1;  // VMS_GAA_X2=0: the scalar two-pair kernel instead of the packed one
+  if (x2 < 0) {
+    const char* e = getenv("VMS_GAA_X2");
+    x2 = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (x2 && gaa_pairs_per_trip(p.n, p.tpr) == 2) {
+    if (p.act == VMS_ACT_NONE) return gaa_fused_launch_x2<HP, DP, VMS_ACT_NONE>(p, st);
+    if (p.act == VMS_ACT_RELU) return gaa_fused_launch_x2<HP, DP, VMS_ACT_RELU>(p, st);
+    if (p.act == VMS_ACT_TANH) return gaa_fused_launch_x2<HP, DP, VMS_ACT_TANH>(p, st);
+  }
 #ifdef VMS_GAA_WITH_CONST  // constant-bank weights: measured slower than shared-memory broadcasts (7.4 vs 6.4 ms), not built by default
   if (gaa_const_weights()) {
 #define VMS_GAA_ACT(A) if (p.act == A) return gaa_fused_launch2<HP, DP, A, true, 1>(p, st)
@@ -736,8 +1090,8 @@ vms_status gaa_fused_launch(GaaFwdParams& p, cudaStream_t st) {
 #undef VMS_GAA_ACT
   }
 #endif
-#define VMS_GAA_ACT(A)                                                      \
-  if (p.act == A) return two ? gaa_fused_launch2<HP, DP, A, false, 2>(p, st) : gaa_fused_launch2<HP, DP, A, false, 1>(p, st)
+  // small clouds (a thread walks fewer than four pairs) and VMS_GAA_X2=0: the scalar one-pair-per-trip kernel
+#define VMS_GAA_ACT(A) if (p.act == A) return gaa_fused_launch2<HP, DP, A, false, 1>(p, st)
   VMS_GAA_ACT(VMS_ACT_NONE);
   VMS_GAA_ACT(VMS_ACT_RELU);
   VMS_GAA_ACT(VMS_ACT_TANH);

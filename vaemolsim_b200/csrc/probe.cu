@@ -32,6 +32,37 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, int iters, 
   if (s == 123.456f) out[0] = s;  // never true for the arguments used: keeps the chains alive
 }
 
+// the packed form: fma.rn.f32x2 (SASS FFMA2), two independent float32 FMAs per instruction on a 64-bit register pair
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2f(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__global__ void __launch_bounds__(256) ffma2_probe_kernel(float* out, int iters, float a, float b) {
+  const float t = threadIdx.x * 1e-3f;
+  unsigned long long x[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) x[u] = pack2f(t + u, t + u + 0.5f);
+  const unsigned long long aa = pack2f(a, a), bb = pack2f(b, b);
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = ffma2(x[q], aa, bb);
+    }
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s ^= x[q];
+  if (s == 0x123456789abcdefull) out[0] = 1.f;
+}
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ unsigned long long make_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
@@ -170,6 +201,21 @@ vms_status vms_probe_ffma(int iters, int reps, double* tflops, double* ms, vms_s
   if (s != VMS_OK) return s;
   VMS_LAUNCH_CHECK("ffma_probe_kernel");
   const double fma = (double)grid * 256.0 * (double)iters * 16.0 * 8.0;
+  *tflops = 2.0 * fma / (*ms * 1e-3) / 1e12;
+  return VMS_OK;
+}
+
+vms_status vms_probe_ffma2(int iters, int reps, double* tflops, double* ms, vms_stream stream) {
+  VMS_REQUIRE(iters >= 1 && reps >= 1 && tflops && ms, VMS_ERR_INVALID_ARG, "probe_ffma2: bad arguments");
+  float* out = nullptr;
+  VMS_CUDA(cudaMalloc(&out, 16));
+  const int grid = sm_count() * 8;
+  cudaStream_t st = as_stream(stream);
+  vms_status s = best_of([&] { ffma2_probe_kernel<<<grid, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); count_launch(); }, reps, st, ms);
+  cudaFree(out);
+  if (s != VMS_OK) return s;
+  VMS_LAUNCH_CHECK("ffma2_probe_kernel");
+  const double fma = (double)grid * 256.0 * (double)iters * 16.0 * 8.0 * 2.0;  // two FMAs per instruction
   *tflops = 2.0 * fma / (*ms * 1e-3) / 1e12;
   return VMS_OK;
 }
