@@ -67,6 +67,14 @@ vms_status vms_event_record(vms_event ev, vms_stream stream);
 vms_status vms_stream_wait_event(vms_stream stream, vms_event ev); /* later work on `stream` waits for `ev` (device side) */
 vms_status vms_event_synchronize(vms_event ev);
 vms_status vms_event_elapsed_ms(vms_event start, vms_event stop, float* ms);
+/* CUDA graphs for launch-bound host loops (the tape-based training step issues ~100 small kernels from the host): begin puts
+ * the stream into capture (relaxed mode), end instantiates what was captured and reports the number of this library's kernel
+ * launches in it (they did not run; vms_launch_count advances per replay), abort discards a capture, launch replays. */
+vms_status vms_graph_begin_capture(vms_stream stream);
+vms_status vms_graph_end_capture(vms_stream stream, void** graph_exec, int* n_kernels);
+vms_status vms_graph_abort_capture(vms_stream stream);
+vms_status vms_graph_launch(void* graph_exec, int n_kernels, vms_stream stream);
+vms_status vms_graph_destroy(void* graph_exec);
 /* counts kernels launched by this library in this process (bench.py's `gpu_launches`) */
 unsigned long long vms_launch_count(void);
 
@@ -336,6 +344,10 @@ typedef struct {
 } vms_adam_tensor;
 vms_status vms_adam_step_multi(const vms_adam_tensor* tensors, int n_tensors, float grad_scale, int64_t t, double lr,
                                double beta1, double beta2, double eps, vms_stream stream);
+/* The same with the step count t and the bias-corrected learning rate in DEVICE memory (t_dev: int64, advanced by the call;
+ * lr_t_dev: float scratch), so that a training step captured in a CUDA graph (vms_graph_*) stays valid from step to step. */
+vms_status vms_adam_step_multi_dev(const vms_adam_tensor* tensors, int n_tensors, float grad_scale, long long* t_dev,
+                                   float* lr_t_dev, double lr, double beta1, double beta2, double eps, vms_stream stream);
 
 /* ------------------------------------------------------------------------------- fused ELBO step (C1 / C2)
  * One handle = one VAE of the family used by the reference's tests (tests/test_models.py:161-228):

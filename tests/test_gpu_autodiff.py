@@ -407,3 +407,50 @@ def test_batch_norm_models_train(vms):
     y = np.concatenate([rng.normal(size=(96, 2)), rng.uniform(-3, 3, (96, 2))], axis=1).astype(np.float32)
     dec(z)
     _directional_check(v, dec, z, y, rtol=2e-2, training=True)
+
+
+def test_graph_replayed_training_steps_equal_eager_steps(vms):
+    """The tape trainer captures a whole step (forward, reverse mode, Adam with the step count in device memory) in a CUDA
+    graph after two eager steps and replays it: same weights, bit for bit, as eager training; a model whose step draws host
+    noise (a VAE's reparameterised sample) falls back to eager steps."""
+    v = vms
+    import vaemolsim_b200._protocols as PR
+
+    def make():
+        v.set_seed(21)
+        flow = v.flows.RQSSplineRealNVP(num_blocks=3, rqs_params=dict(bin_range=[-10.0, 10.0], num_bins=16, hidden_dim=32))
+        fm = v.models.FlowModel(flow, PR.DistributionLambda(lambda t: PR.StandardNormal(t.shape[0], 2)))
+        fm.compile(optimizer=v.models.Adam(2e-3), loss=v.losses.LogProbLoss())
+        return fm
+
+    rng = np.random.default_rng(8)
+    xs = [(rng.normal(size=(64, 2)) * 1.5 + 0.3).astype(np.float32) for _ in range(9)]
+    a = make()  # (the spline networks draw their weights at the first log_prob, i.e. inside the first step: train a to the
+    la = [a.train_on_batch(x, x) for x in xs]  # end before b is seeded and built)
+    n0 = v._abi.launch_count()
+    la.append(a.train_on_batch(xs[0], xs[0]))
+    per_step = v._abi.launch_count() - n0
+    a.train_on_batch(xs[0][:32], xs[0][:32])
+    b = make()
+    b._trainer()._graph_off = True
+    lb = [b.train_on_batch(x, x) for x in xs + [xs[0]]]
+    b.train_on_batch(xs[0][:32], xs[0][:32])
+    tr = a._trainer()
+    assert len(getattr(tr, '_graphs', {})) >= 1, 'the step was not captured'
+    assert per_step > 20  # the replay accounts for the kernels it launches
+    assert la == lb
+    assert len(a.weights) == len(b.weights) > 0
+    for wa, wb in zip(a.weights, b.weights):  # (includes one step at another batch size: its own capture)
+        assert np.array_equal(wa.numpy(), wb.numpy())
+    assert len(tr._graphs) == 2
+    # host-drawn noise inside the step: no graph, training still works
+    d = v.dists
+    enc = v.models.MappingToDistribution(PR.IndependentNormal(2), name='encoder')
+    dec = v.models.MappingToDistribution(d.IndependentBlockwise(4, [d.Normal] * 4), name='decoder')
+    vae = v.models.VAE(enc, dec, PR.DistributionLambda(lambda t: PR.StandardNormal(t.shape[0], 2)))
+    vae.compile(optimizer=v.models.Adam(1e-3), loss=v.losses.LogProbLoss())
+    x4 = rng.normal(size=(32, 4)).astype(np.float32)
+    m = v.models.Model.train_on_batch
+    losses = [m(vae, x4, x4) for _ in range(5)]
+    assert np.isfinite(losses).all()
+    assert not getattr(vae._trainer(), '_graphs', {})

@@ -102,6 +102,11 @@ _SIGS = {
     'vms_stream_wait_event': (None, [c_vp, c_vp]),
     'vms_event_synchronize': (None, [c_vp]),
     'vms_event_elapsed_ms': (None, [c_vp, c_vp, C.POINTER(c_f32)]),
+    'vms_graph_begin_capture': (None, [c_vp]),
+    'vms_graph_end_capture': (None, [c_vp, C.POINTER(c_vp), C.POINTER(c_int)]),
+    'vms_graph_abort_capture': (None, [c_vp]),
+    'vms_graph_launch': (None, [c_vp, c_int, c_vp]),
+    'vms_graph_destroy': (None, [c_vp]),
     'vms_rqs_forward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_f32, c_vp, c_vp, c_vp]),
     'vms_rqs_inverse': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_f32, c_vp, c_vp, c_vp]),
     'vms_rqs_backward': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp,
@@ -154,6 +159,7 @@ _SIGS = {
     'vms_energy_quadratic': (None, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     'vms_energy_gmm': (None, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vms_adam_step_multi': (None, [C.POINTER(AdamTensor), c_int, c_f32, c_i64, c_f64, c_f64, c_f64, c_f64, c_vp]),
+    'vms_adam_step_multi_dev': (None, [C.POINTER(AdamTensor), c_int, c_f32, c_vp, c_vp, c_f64, c_f64, c_f64, c_f64, c_vp]),
     'vms_adam_step': (None, [c_vp, c_vp, c_int, c_f32, c_vp, c_vp, c_i64, c_i64, c_f64, c_f64, c_f64, c_f64, c_vp]),
     'vms_sum_partials': (None, [c_vp, c_int, c_i64, c_f32, c_vp, c_vp]),
     'vms_elbo_plan_create': (None, [C.POINTER(ElboDesc), C.POINTER(c_vp)]),
@@ -227,6 +233,17 @@ _lib = None
 _lock = threading.Lock()
 
 
+class CaptureUnsupported(RuntimeError):
+    """An operation that cannot be part of a CUDA graph (host <-> device copy, synchronisation) was issued while a training
+    step was being captured: the trainer discards the capture and runs the step eagerly."""
+
+
+# [0]: a CUDA-graph capture of the library's stream is in progress (set by _autodiff.Trainer)
+_capturing = [False]
+_NOT_CAPTURABLE = ('vms_memcpy_h2d', 'vms_memcpy_d2h', 'vms_stream_synchronize', 'vms_device_synchronize', 'vms_event_synchronize',
+                   'vms_malloc_host')
+
+
 class _Lib(object):
     """Attribute access returns checked callables: lib.vms_xxx(...) raises on a non-zero status."""
 
@@ -236,7 +253,20 @@ class _Lib(object):
             fn = getattr(cdll, name)
             fn.argtypes = args
             fn.restype = c_int if res is None else res
-            setattr(self, name, self._checked(fn, name) if res is None else fn)
+            call = self._checked(fn, name) if res is None else fn
+            if name in _NOT_CAPTURABLE:
+                call = self._guarded(call, name)
+            setattr(self, name, call)
+
+    @staticmethod
+    def _guarded(call, name):
+        def guarded(*a):
+            if _capturing[0]:
+                raise CaptureUnsupported(name)
+            return call(*a)
+
+        guarded.__name__ = name
+        return guarded
 
     def _checked(self, fn, name):
         cdll = self._cdll

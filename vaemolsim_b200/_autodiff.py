@@ -93,9 +93,8 @@ class Tape(object):
 
     def backward(self, loss):
         c = ctx()
-        g = self.grad(loss)
-        one = np.ones(max(loss.size, 1), np.float32)
-        c.lib.vms_memcpy_h2d(g.ptr, one.ctypes.data, one.nbytes, c.stream)  # (pageable source: staged before the call returns)
+        g = self.grad(loss)  # (zero-initialised)
+        c.lib.vms_add_scalar(g.ptr, max(loss.size, 1), None, 1.0, c.stream)  # d loss = 1, on the device (capturable)
         for fn in reversed(self.ops):
             fn()
 
@@ -123,6 +122,99 @@ class Trainer(object):
         # on the library's stream, Adam then applies sum / world -- identical on every rank, so replicas stay in step
         self.group = group if (group is not None and group.world > 1) else None
         self._flat = None
+
+    # ---- CUDA-graph replay of the whole step (forward, reverse mode, Adam) for fixed-shape batches
+    # The tape path is launch-bound: ~100 small kernels per step, ~10 us of Python each.  After two eager steps the trainer
+    # captures one step on the library's stream -- inputs in static device buffers, Adam's step count in device memory
+    # (vms_adam_step_multi_dev) -- and from then on a step is: copy the batch into the input buffers, ONE graph launch.
+    # Anything that cannot be captured (host-drawn noise, host <-> device copies or synchronisation inside an op: raises
+    # _abi.CaptureUnsupported; a failed capture) makes the trainer fall back to eager steps for good.  VMS_TAPE_GRAPH=0
+    # disables it.
+    graph_warmup = 2
+
+    def step_arrays(self, x, y, loss_of):
+        """One optimiser step on host arrays x, y; `loss_of(xb, yb)` builds the scalar loss Tensor from device tensors."""
+        import os
+        c = ctx()
+        key = (x.shape, y.shape)
+        graphs = self.__dict__.setdefault('_graphs', {})
+        g = graphs.get(key)
+        if g is not None:
+            for dst, src in ((g['x'], x), (g['y'], y)):
+                c.lib.vms_memcpy_h2d(dst.ptr, src.ctypes.data, src.nbytes, c.stream)
+            tbuf = np.array([self.t], np.int64)
+            c.lib.vms_memcpy_h2d(g['t_dev'].ptr, tbuf.ctypes.data, 8, c.stream)
+            c.lib.vms_graph_launch(g['exec'], g['n_kernels'], c.stream)
+            self.t += 1
+            _abi.bump_param_epoch()
+            return g['loss']
+        eligible = (self.group is None and self.t >= self.graph_warmup and not self.__dict__.get('_graph_off', False) and
+                    os.environ.get('VMS_TAPE_GRAPH', '1') != '0' and len(graphs) < 4)
+        xb, yb = Tensor.from_numpy(x), Tensor.from_numpy(y)
+        if not eligible:
+            return self.step(lambda: loss_of(xb, yb))
+        g = self._capture(xb, yb, loss_of)
+        if g is None:
+            self._graph_off = True
+            return self.step(lambda: loss_of(xb, yb))
+        graphs[key] = g
+        tbuf = np.array([self.t], np.int64)
+        c.lib.vms_memcpy_h2d(g['t_dev'].ptr, tbuf.ctypes.data, 8, c.stream)
+        c.lib.vms_graph_launch(g['exec'], g['n_kernels'], c.stream)  # the captured kernels have not run yet: this is the step
+        self.t += 1
+        _abi.bump_param_epoch()
+        return g['loss']
+
+    def _capture(self, xb, yb, loss_of):
+        c = ctx()
+        from . import _protocols
+        todo = None
+        c.synchronize()
+        t_dev, lr_dev = Tensor.zeros((2, ), np.int32), Tensor.zeros((1, ))  # (int64 step count as two int32 words)
+        c.lib.vms_graph_begin_capture(c.stream)
+        _abi._capturing[0] = True
+        ok, tape, loss = True, None, None
+        try:
+            with Tape() as tape:
+                loss = loss_of(xb, yb)
+                tape.backward(loss)
+            table, keep = [], []
+            seen = set()
+            for w in self.model.weights:
+                if id(w) in seen or not tape.has(w):
+                    continue
+                seen.add(id(w))
+                gr = tape.grad(w)
+                if not (w.contiguous and gr.contiguous):
+                    raise _abi.CaptureUnsupported('strided weight view')
+                st = self.state.get(id(w))
+                if st is None:
+                    raise _abi.CaptureUnsupported('a weight without optimiser state (it received no gradient in the eager steps)')
+                mask = getattr(w, '_grad_mask', None)
+                table.append(_abi.AdamTensor(w.ptr, gr.ptr, None if mask is None else mask.ptr, st[1].ptr, st[2].ptr, w.size))
+                keep.append(gr)
+            o = self.opt
+            arr = (_abi.AdamTensor * len(table))(*table)
+            c.lib.vms_adam_step_multi_dev(arr, len(table), 1.0, t_dev.ptr, lr_dev.ptr, o.learning_rate, o.beta_1, o.beta_2,
+                                          o.epsilon, c.stream)
+        except Exception:
+            ok = False
+        finally:
+            _abi._capturing[0] = False
+        if not ok:
+            c.lib.vms_graph_abort_capture(c.stream)
+            if tape is not None:
+                tape.release()
+            return None
+        ex, nk = C.c_void_p(), C.c_int(0)
+        try:
+            c.lib.vms_graph_end_capture(c.stream, C.byref(ex), C.byref(nk))
+        except Exception:
+            tape.release()
+            return None
+        # the graph reads and writes every tensor of the captured step: they stay allocated as long as the graph lives
+        return {'exec': ex.value, 'n_kernels': nk.value, 'x': xb, 'y': yb, 'loss': loss, 't_dev': t_dev, 'lr_dev': lr_dev,
+                'keep': (tape, keep, table)}
 
     def step(self, fn):
         c = ctx()

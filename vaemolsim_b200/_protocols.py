@@ -36,6 +36,8 @@ def set_seed(seed):
 
 
 def rng():
+    if _abi._capturing[0]:  # host-drawn noise cannot be part of a captured training step
+        raise _abi.CaptureUnsupported('host random numbers')
     return _rng
 
 

@@ -168,6 +168,60 @@ vms_status vms_event_synchronize(vms_event e) {
   VMS_CUDA(cudaEventSynchronize((cudaEvent_t)e));
   return VMS_OK;
 }
+// ---- CUDA graphs for launch-bound host loops (the tape-based training step: ~100 small kernels issued from Python)
+// begin: the stream starts capturing (relaxed mode: allocations are legal while capturing);  end: instantiates the captured
+// work and reports how many of this library's kernel launches it holds (they did NOT run: the launch counter is rolled back
+// and advanced per replay instead);  abort: ends a capture and discards it.
+static thread_local unsigned long long g_capture_count0 = 0;
+vms_status vms_graph_begin_capture(vms_stream s) {
+  VMS_REQUIRE(s, VMS_ERR_INVALID_ARG, "graph_begin_capture: the legacy default stream cannot capture");
+  g_capture_count0 = vms_launch_count();
+  VMS_CUDA(cudaStreamBeginCapture(as_stream(s), cudaStreamCaptureModeRelaxed));
+  return VMS_OK;
+}
+vms_status vms_graph_abort_capture(vms_stream s) {
+  cudaGraph_t g = nullptr;
+  cudaStreamEndCapture(as_stream(s), &g);
+  if (g) cudaGraphDestroy(g);
+  cudaGetLastError();  // an invalidated capture must not poison later launch checks
+  count_launch(-(int)(vms_launch_count() - g_capture_count0));
+  return VMS_OK;
+}
+vms_status vms_graph_end_capture(vms_stream s, void** graph_exec, int* n_kernels) {
+  VMS_REQUIRE(graph_exec && n_kernels, VMS_ERR_INVALID_ARG, "graph_end_capture: NULL argument");
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(as_stream(s), &g);
+  const int n = (int)(vms_launch_count() - g_capture_count0);
+  count_launch(-n);
+  if (e != cudaSuccess || !g) {
+    cudaGetLastError();
+    if (g) cudaGraphDestroy(g);
+    set_error("graph capture failed: %s", cudaGetErrorString(e));
+    return VMS_ERR_CUDA;
+  }
+  cudaGraphExec_t ex = nullptr;
+  e = cudaGraphInstantiate(&ex, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("graph instantiation failed: %s", cudaGetErrorString(e));
+    return VMS_ERR_CUDA;
+  }
+  *graph_exec = (void*)ex;
+  *n_kernels = n;
+  return VMS_OK;
+}
+vms_status vms_graph_launch(void* graph_exec, int n_kernels, vms_stream s) {
+  VMS_REQUIRE(graph_exec, VMS_ERR_INVALID_ARG, "graph_launch: NULL graph");
+  VMS_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, as_stream(s)));
+  count_launch(n_kernels);
+  return VMS_OK;
+}
+vms_status vms_graph_destroy(void* graph_exec) {
+  if (graph_exec) VMS_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  return VMS_OK;
+}
+
 vms_status vms_event_elapsed_ms(vms_event a, vms_event b, float* ms) {
   VMS_REQUIRE(ms, VMS_ERR_INVALID_ARG, "ms is NULL");
   VMS_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));

@@ -85,8 +85,8 @@ class Model(P.Layer):
             tot, n = 0.0, 0
             for i in range(0, len(x), batch_size):
                 idx = order[i:i + batch_size]
-                xb, yb = Tensor.from_numpy(x[idx]), Tensor.from_numpy(y[idx])
-                loss = tr.step(lambda: self._loss_tensor(xb, yb, True))
+                loss = tr.step_arrays(np.ascontiguousarray(x[idx]), np.ascontiguousarray(y[idx]),
+                                      lambda xb, yb: self._loss_tensor(xb, yb, True))
                 tot, n = tot + float(loss.numpy()) * len(idx), n + len(idx)
             hist['loss'].append(tot / max(n, 1))
         return hist
@@ -94,9 +94,9 @@ class Model(P.Layer):
     def train_on_batch(self, x, y=None):
         """One optimiser step on one batch; returns the loss (the inner call of `fit`)."""
         x, y = self._prep_xy(x, y)
-        xb, yb = Tensor.from_numpy(x), Tensor.from_numpy(y)
         self._check_trainable()
-        return float(self._trainer().step(lambda: self._loss_tensor(xb, yb, True)).numpy())
+        return float(self._trainer().step_arrays(np.ascontiguousarray(x), np.ascontiguousarray(y),
+                                                 lambda xb, yb: self._loss_tensor(xb, yb, True)).numpy())
 
     def evaluate(self, x, y=None, batch_size=32, verbose=0):
         x, y = self._prep_xy(x, y)
