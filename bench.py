@@ -625,6 +625,31 @@ def flow_model_leg(v, grp):
         dt = (time.perf_counter() - t0) / n
         out['batch_%d' % B] = {'ms_per_step': dt * 1e3, 'configs_per_s': B / dt,
                                'gpu_launches_per_step': (v._abi.launch_count() - l0) / n}
+    # the decoder-only model of examples/Training_VAEs_and_Decoders.ipynb cells 39-43 (FCDeepNN + conditional autoregressive von
+    # Mises decoder, MADE hidden [10, 100, 10], 3,938 parameters; Keras progress bar: 471-555 us per step at batch 32)
+    d = v.dists
+    v.set_seed(9)
+    dec = v.models.MappingToDistribution(d.AutoregressiveBlockwise(2, [d.VonMises] * 2, conditional=True,
+                                                                    conditional_event_shape=(1, ),
+                                                                    auto_net_params={'hidden_units': [10, 100, 10]}))
+    dec.compile(optimizer=v.models.Adam(1e-3), loss=v.losses.LogProbLoss())
+    cg = rng.uniform(-np.pi, np.pi, (32, 1)).astype(np.float32)
+    ang = rng.uniform(-np.pi, np.pi, (32, 2)).astype(np.float32)
+    for _ in range(5):
+        dec.train_on_batch(cg, ang)
+    c.synchronize()
+    l0 = v._abi.launch_count()
+    t0 = time.perf_counter()
+    dl = [dec.train_on_batch(cg, ang) for _ in range(60)]
+    c.synchronize()
+    dt = (time.perf_counter() - t0) / 60
+    out['decoder_only_batch_32'] = {'ms_per_step': dt * 1e3, 'configs_per_s': 32 / dt, 'params': dec.count_params(),
+                                    'gpu_launches_per_step': (v._abi.launch_count() - l0) / 60,
+                                    'graph_replay': bool(getattr(dec._trainer(), '_graphs', {})),
+                                    'loss_finite': bool(np.isfinite(dl).all()),
+                                    'reference_notebook': 'Training_VAEs_and_Decoders.ipynb:648-666: 471-555 us/step at batch 32 '
+                                                          '(Apple M-series CPU, orientation only)'}
+    out['graph_replay'] = bool(getattr(fm._trainer(), '_graphs', {}))
     return {'metric': 'FlowModel NLL training steps (tape path)', 'value': out['batch_4096']['configs_per_s'], 'unit': 'configs/s',
             'workload': 'Using_Normalizing_Flows.ipynb FlowModel: 1-D RQSSplineRealNVP 4 blocks K=32 H=100 over N(0,1), NLL + Adam',
             'scaling': 'replicas (every rank runs the same steps)', **out, 'loss_finite': bool(np.isfinite(losses).all()),

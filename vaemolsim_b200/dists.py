@@ -172,7 +172,10 @@ class AutoregressiveBlockwise(IndependentBlockwise):
             raw_params = flat_in + shift.reshape(B, self.num_dofs * pmax)
             return Blockwise(raw_params, kinds, loc, loc2, scale, mode)
 
-        sample0 = Tensor.from_numpy(np.ones((B, self.num_dofs), np.float32))
+        cache = self.__dict__.setdefault('_ones', {})  # (a device constant per batch size: no upload inside a training step,
+        sample0 = cache.get(B)                         # which keeps the step capturable in a CUDA graph)
+        if sample0 is None:
+            sample0 = cache[B] = Tensor.from_numpy(np.ones((B, self.num_dofs), np.float32))
         return Autoregressive(_make_dist, sample0=sample0, num_steps=self.num_dofs)
 
     def params_size(self):
