@@ -533,12 +533,16 @@ def _mc_noise(seed, n_steps, B, dz, dx):
     return out
 
 
+@pytest.mark.parametrize('lanes', ['1', '8'])
 @pytest.mark.parametrize('device_rng', [False, True])
-def test_fused_mc_matches_reference_mcmc_py_goldens(vms, device_rng):
+def test_fused_mc_matches_reference_mcmc_py_goldens(vms, device_rng, lanes, monkeypatch):
     """`vms_mc_run` / `vms_mc_run_pcg64` against the decisions of the REFERENCE's own vaemolsim/mcmc.py
     (tests/golden/make_goldens.py): every step restarted from the golden state, same sampling noise, same PCG64 uniform
-    stream -- drawn by NumPy on the host (device_rng False) or regenerated on the device by LCG jump-ahead (True)."""
+    stream -- drawn by NumPy on the host (device_rng False) or regenerated on the device by LCG jump-ahead (True).
+    Both summation orders of the chain kernel: the 1 / 2 / 4-lane kernel (`lanes` 1) and the 8-lane kernel that shards
+    of a multi-GPU job run (`lanes` 8)."""
     v = vms
+    monkeypatch.setenv('VMS_MC_TPC', lanes)
     g = np.load(os.path.join(GOLD, 'mcmc_reference_c4a.npz'))
     P = ovae.init_vae(1003, prior='normal', hidden=32)
     model = vae_from_oracle(v, P)
@@ -758,6 +762,28 @@ def test_fused_mc_chain_kernel_lane_counts_are_bitwise_equal(vms, monkeypatch):
             assert np.array_equal(res[tpc][2][key], res['1'][2][key]), (tpc, key)
         assert res[tpc][3] == res['1'][3]
     assert 0 < res['1'][3] < B * n_steps
+    # the 8-lane kernel sums the hidden units in its own order: log-probabilities to float32 rounding, the same decision
+    # wherever the margin exceeds that rounding, then identical chains
+    monkeypatch.setenv('VMS_MC_TPC', '8')
+    mc = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=12)
+    x8, e8 = mc.run_fused(x0, n_steps=1, trace=True)
+    t8 = mc._last_trace
+    monkeypatch.setenv('VMS_MC_TPC', '1')
+    mc = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=12)
+    x1_, e1_ = mc.run_fused(x0, n_steps=1, trace=True)
+    t1 = mc._last_trace
+    assert np.array_equal(t8['log_u'], t1['log_u'])
+    assert_close(t8['fwd'], t1['fwd'], rtol=1e-5, atol=2e-5, what='8-lane forward_log_p')
+    assert_close(t8['rev'], t1['rev'], rtol=1e-5, atol=2e-5, what='8-lane reverse_log_p')
+    assert_close(t8['e_new'], t1['e_new'], rtol=1e-5, atol=1e-5, what='8-lane proposal energy')
+    e_old = np.zeros(B)
+    for d in range(6):  # the kernel's float64 order (tests/test_mcmc.py:28-32 on six coordinates)
+        e_old = e_old + (x0[:, d].astype(np.float64) - np.linspace(-2, 2, 6)[d]) ** 2
+    want = omc.accept(t8['e_new'][0], e_old, t8['fwd'][0], t8['rev'][0], t8['log_u'][0])
+    assert np.array_equal(t8['acc'][0].astype(bool), want)  # bit-exact acceptance arithmetic given ITS log-probabilities
+    same = t8['acc'][0] == t1['acc'][0]
+    assert same.sum() >= B - 2
+    assert_close(x8[same], x1_[same], rtol=1e-5, atol=2e-5, what='8-lane configs')
 
 
 def test_fused_mc_notebook_kernel_lane_counts_are_bitwise_equal(vms, monkeypatch):

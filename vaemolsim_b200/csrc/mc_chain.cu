@@ -308,6 +308,290 @@ __global__ void __launch_bounds__(CT, MINB) mc_chain_kernel(const ChainParams p)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ a warp per four chains
+// One shard of an 8-GPU job holds 8,192 chains: 55 per SM.  With 1 - 4 lanes per chain that is 2 - 7 warps per SM, every
+// warp a latency-bound chain of ~10,000 instructions per MC step (ncu at 8,192 chains, two lanes: 4 warps per SM, IPC 0.43
+// per warp; four lanes: MORE warp instructions, since every lane repeats the per-chain scalar work -- 0.47 strong-scaling
+// efficiency at N = 8).  A first wide variant (8 lanes per chain, unit j -> lane j % 8) cut the warp instructions per
+// step to 2,900 but ran at the same 11.4 us per step: the four chains of a warp read the same weight rows, a 16-byte
+// shared-memory load is served quarter-warp by quarter-warp (3.7 wavefronts per LDS.128 measured), and the kernel sat at
+// 87 % of the shared-memory wavefront peak.  This variant removes that redundancy through registers:
+//   * a warp owns FOUR chains; lane l walks the hidden units j = l, l + 32, ... (ascending) and applies each weight row it
+//     loads to all four chains (112 FFMAs per 7 loads, every wavefront carries distinct data);
+//   * the 4 x 16 head outputs are reduce-scattered over the 32 lanes (xor 16, 8, 4, 2, 1: 62 shuffles), which leaves lane
+//     l = 8 k + s with (loc, raw scale) of ONE degree of freedom of chain k: s = 0, 1 the encoder's two latents, s = 2..7
+//     the decoder's six coordinates -- softplus, the sample and the per-dof log-probability run once per dof;
+//   * each lane runs one Philox call (its own eps) instead of three;
+//   * samples and log-probability terms are gathered with indexed shuffles and summed in dof order by the eight lanes of
+//     a chain, so the decision (float64, mcmc.py:116-120) is the same in all of them; the current configurations of the
+//     four chains live in shared memory (24 floats per warp), read back as broadcasts for the next encoder pass.
+// Summation order of a hidden layer here: 32 streams (unit j -> stream j % 32) met by the xor-16-8-4-2-1 tree -- NOT the
+// four-stream order of the 1 / 2 / 4-lane kernel: log-probabilities agree to float32 rounding, decisions wherever the
+// margin exceeds that rounding (both orders are tested against the reference's goldens; VMS_MC_TPC pins one of them when
+// bit-identical chains across different shard sizes matter more than speed).
+constexpr int WC = 4;        // chains per warp
+constexpr int WL = 8;        // lanes that finish a chain (one per degree of freedom)
+constexpr int kWideMaxChainsPerSm = 96;  // chains per SM below which the launcher takes this variant
+
+template <int N>
+__device__ __forceinline__ void scatter_step(const float (&v)[N], float (&w)[N / 2], bool upper, int lane_mask) {
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    const float snd = upper ? v[i] : v[i + N / 2];
+    const float kp = upper ? v[i + N / 2] : v[i];
+    w[i] = kp + __shfl_xor_sync(0xffffffffu, snd, lane_mask);
+  }
+}
+
+// enc(xe[k]) | dec(zd[k]) for the warp's four chains k; lane 8 k + s returns (loc, raw scale) of dof s of chain k
+__device__ __forceinline__ void mlp_pair_warp(const float* __restrict__ wsm, int Hp32, int lane,
+                                              const float (&xe)[WC][kMaxDx], const float (&zd)[WC][kMaxDz], float& out_loc,
+                                              float& out_raw) {
+  float ae[WC][2 * kMaxDz], ad[WC][2 * kMaxDx];
+#pragma unroll
+  for (int k = 0; k < WC; ++k) {
+#pragma unroll
+    for (int n = 0; n < 2 * kMaxDz; ++n) ae[k][n] = 0.f;
+#pragma unroll
+    for (int n = 0; n < 2 * kMaxDx; ++n) ad[k][n] = 0.f;
+  }
+#pragma unroll 1
+  for (int j = lane; j < Hp32; j += 32) {
+    const float4* row = reinterpret_cast<const float4*>(wsm + j * WROW);
+    {
+      const float4 a = row[0], b = row[1], c = row[2];
+#pragma unroll
+      for (int k = 0; k < WC; ++k) {
+        float he = 0.f;
+        he = fmaf(xe[k][0], a.x, he); he = fmaf(xe[k][1], a.y, he); he = fmaf(xe[k][2], a.z, he);
+        he = fmaf(xe[k][3], a.w, he); he = fmaf(xe[k][4], b.x, he); he = fmaf(xe[k][5], b.y, he);
+        he = fmaxf(he + b.z, 0.f);
+        ae[k][0] = fmaf(he, b.w, ae[k][0]); ae[k][1] = fmaf(he, c.x, ae[k][1]);
+        ae[k][2] = fmaf(he, c.y, ae[k][2]); ae[k][3] = fmaf(he, c.z, ae[k][3]);
+      }
+    }
+    {
+      const float w0d0 = wsm[j * WROW + 11];
+      const float4 d = row[3], e = row[4], f = row[5], g = row[6];
+#pragma unroll
+      for (int k = 0; k < WC; ++k) {
+        float hd = 0.f;
+        hd = fmaf(zd[k][0], w0d0, hd); hd = fmaf(zd[k][1], d.x, hd);
+        hd = fmaxf(hd + d.y, 0.f);
+        ad[k][0] = fmaf(hd, d.z, ad[k][0]); ad[k][1] = fmaf(hd, d.w, ad[k][1]);
+        ad[k][2] = fmaf(hd, e.x, ad[k][2]); ad[k][3] = fmaf(hd, e.y, ad[k][3]);
+        ad[k][4] = fmaf(hd, e.z, ad[k][4]); ad[k][5] = fmaf(hd, e.w, ad[k][5]);
+        ad[k][6] = fmaf(hd, f.x, ad[k][6]); ad[k][7] = fmaf(hd, f.y, ad[k][7]);
+        ad[k][8] = fmaf(hd, f.z, ad[k][8]); ad[k][9] = fmaf(hd, f.w, ad[k][9]);
+        ad[k][10] = fmaf(hd, g.x, ad[k][10]); ad[k][11] = fmaf(hd, g.y, ad[k][11]);
+      }
+    }
+  }
+  // lane l ends with entries 2 l, 2 l + 1 of this order: per chain the (loc, raw) pairs of its eight dofs
+  float v[64];
+#pragma unroll
+  for (int k = 0; k < WC; ++k) {
+    v[16 * k + 0] = ae[k][0]; v[16 * k + 1] = ae[k][2]; v[16 * k + 2] = ae[k][1]; v[16 * k + 3] = ae[k][3];
+#pragma unroll
+    for (int d = 0; d < kMaxDx; ++d) {
+      v[16 * k + 4 + 2 * d] = ad[k][d];
+      v[16 * k + 5 + 2 * d] = ad[k][kMaxDx + d];
+    }
+  }
+  float w32[32], w16[16], w8[8], w4[4], w2[2];
+  scatter_step<64>(v, w32, (lane & 16) != 0, 16);
+  scatter_step<32>(w32, w16, (lane & 8) != 0, 8);
+  scatter_step<16>(w16, w8, (lane & 4) != 0, 4);
+  scatter_step<8>(w8, w4, (lane & 2) != 0, 2);
+  scatter_step<4>(w4, w2, (lane & 1) != 0, 1);
+  out_loc = w2[0];
+  out_raw = w2[1];
+}
+
+template <int CTW, int MINB>
+__global__ void __launch_bounds__(CTW, MINB) mc_chain_warp_kernel(const ChainParams p) {
+  extern __shared__ __align__(16) float wsm[];  // [Hp32][WROW] + enc b1 [4] + dec b1 [12] + per warp x [WC][8]
+  const int tid = threadIdx.x;
+  const int H = p.hidden, Hp32 = (H + 31) & ~31;
+  constexpr int dx = kMaxDx, dz = kMaxDz, nn = 2 * kMaxDz + kMaxDx;
+  for (int e = tid; e < Hp32 * WROW; e += CTW) {
+    const int j = e / WROW, c = e - j * WROW;
+    float v = 0.f;
+    if (j >= H) v = 0.f;
+    else if (c < 6) v = __ldg(p.theta + p.enc0W + c * H + j);
+    else if (c == 6) v = __ldg(p.theta + p.enc0b + j);
+    else if (c < 11) v = __ldg(p.theta + p.enc1W + j * 4 + (c - 7));
+    else if (c < 13) v = __ldg(p.theta + p.dec0W + (c - 11) * H + j);
+    else if (c == 13) v = __ldg(p.theta + p.dec0b + j);
+    else if (c < 26) v = __ldg(p.theta + p.dec1W + j * 12 + (c - 14));
+    wsm[e] = v;
+  }
+  float* b1e = wsm + Hp32 * WROW;
+  float* b1d = b1e + 4;
+  if (tid < 4) b1e[tid] = __ldg(p.theta + p.enc1b + tid);
+  if (tid < 12) b1d[tid] = __ldg(p.theta + p.dec1b + tid);
+  __syncthreads();
+
+  const int lane = tid & 31;
+  float* xs = b1d + 12 + (tid >> 5) * (WC * 8);  // this warp's current configurations: [WC][8] (6 used), 16-byte rows
+  const int64_t chain = ((int64_t)blockIdx.x * CTW + tid) / WL;
+  const int sub = lane & (WL - 1), kc = lane >> 3;
+  const int base = lane & ~(WL - 1);         // first lane of this chain
+  const bool enc_lane = sub < dz;            // lanes 0-1: encoder dof `sub`; lanes 2-7: decoder dof `sub - 2`
+  const int dof = enc_lane ? sub : sub - dz;
+  const bool live = chain < p.B;
+  const int64_t cc = live ? chain : p.B - 1;  // idle slots shadow the last chain (full-warp shuffles), writes predicated off
+  const float bias_loc = enc_lane ? b1e[dof] : b1d[dof];
+  const float bias_raw = enc_lane ? b1e[dz + dof] : b1d[dx + dof];
+  float x1_mine = enc_lane ? 0.f : __ldg(p.x + cc * dx + dof);
+  xs[kc * 8 + sub] = 0.f;
+  __syncwarp();
+  if (!enc_lane) xs[kc * 8 + dof] = x1_mine;
+  __syncwarp();
+  double e_old;
+  if (p.energies_valid) {
+    e_old = p.E[cc];
+  } else {
+    e_old = 0.0;
+#pragma unroll
+    for (int d = 0; d < dx; ++d) {
+      const double t = __dsub_rn((double)xs[kc * 8 + d], p.means[d]);
+      e_old = __dadd_rn(e_old, __dmul_rn(t, t));
+    }
+  }
+  U128 rs = {0ull, 0ull};
+  const U128 jm = {p.jm_hi, p.jm_lo}, ja = {p.ja_hi, p.ja_lo};
+  if (p.use_pcg)
+    rs = pcg_advance(U128{p.s0_hi, p.s0_lo}, U128{p.inc_hi, p.inc_lo}, (unsigned long long)(p.chain0 + cc) + 1ull);
+  unsigned n_accept = 0, n_unc = 0;
+  // noise layout of a step: eps(z1) [dz] | eps(z2) [dz] | eps(x2) [dx]; this lane's own eps is entry `eps_idx`, which is
+  // component `eps_idx & 3` of Philox call `eps_idx >> 2`
+  const int eps_idx = enc_lane ? sub : sub + dz;
+
+#pragma unroll 1
+  for (int step = 0; step < p.n_steps; ++step) {
+    float eps_mine, z2a, z2b;  // z2 of this lane's chain
+    if (p.noise) {
+      const float* nrow = p.noise + ((int64_t)step * p.B + cc) * nn;
+      eps_mine = __ldg(nrow + eps_idx);
+      z2a = __ldg(nrow + dz);
+      z2b = __ldg(nrow + dz + 1);
+    } else {
+      const unsigned long long st = p.step0 + (unsigned long long)step;
+      const uint2 key = make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32) ^ (unsigned)(st >> 32));
+      const unsigned long long gc = (unsigned long long)(p.chain0 + cc);  // GLOBAL chain index: sharding-invariant noise
+      const uint4 rnd = philox4x32(make_uint4((unsigned)gc, (unsigned)(gc >> 32), (unsigned)st, (unsigned)(eps_idx >> 2)), key);
+      float n0, n1, n2, n3;
+      box_muller(rnd.x, rnd.y, n0, n1);
+      box_muller(rnd.z, rnd.w, n2, n3);
+      const int comp = eps_idx & 3;
+      eps_mine = comp == 0 ? n0 : (comp == 1 ? n1 : (comp == 2 ? n2 : n3));
+      z2a = __shfl_sync(0xffffffffu, n2, base);  // lane 0 of the chain ran call 0: entries 2, 3 are eps(z2)
+      z2b = __shfl_sync(0xffffffffu, n3, base);
+    }
+    float loc, raw;
+    {
+      // ---- encoder(x1) || decoder(z2) of the four chains
+      float xe[WC][dx], zd[WC][dz];
+#pragma unroll
+      for (int k = 0; k < WC; ++k) {
+        const float4 lo = *reinterpret_cast<const float4*>(xs + k * 8);
+        const float2 hi = *reinterpret_cast<const float2*>(xs + k * 8 + 4);
+        xe[k][0] = lo.x; xe[k][1] = lo.y; xe[k][2] = lo.z; xe[k][3] = lo.w; xe[k][4] = hi.x; xe[k][5] = hi.y;
+        zd[k][0] = __shfl_sync(0xffffffffu, z2a, 8 * k);
+        zd[k][1] = __shfl_sync(0xffffffffu, z2b, 8 * k);
+      }
+      mlp_pair_warp(wsm, Hp32, lane, xe, zd, loc, raw);
+    }
+    loc += bias_loc;
+    float sc = softplus_tf(raw + bias_raw);
+    const float smp = __fadd_rn(__fmul_rn(eps_mine, sc), loc);  // z1_d (encoder lanes) or x2_d (decoder lanes)
+    const float t_fwd = normal_lp(smp, loc, sc);                 // term of log q(z1 | x1) or of log p(x2 | z2)
+    const float z2_mine = sub == 0 ? z2a : z2b;
+    const float t_z1 = normal_lp(smp, 0.f, 1.f);                 // encoder lanes: term of log p(z1)
+    const float t_z2 = normal_lp(z2_mine, 0.f, 1.f);             // encoder lanes: term of log p(z2)
+    float lq1 = 0.f, lz1 = 0.f, lz2 = 0.f, lx2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < dz; ++d) {
+      lq1 += __shfl_sync(0xffffffffu, t_fwd, base + d);
+      lz1 += __shfl_sync(0xffffffffu, t_z1, base + d);
+      lz2 += __shfl_sync(0xffffffffu, t_z2, base + d);
+    }
+#pragma unroll
+    for (int d = 0; d < dx; ++d) lx2 += __shfl_sync(0xffffffffu, t_fwd, base + dz + d);
+    double e_new = 0.0;
+#pragma unroll
+    for (int d = 0; d < dx; ++d) {
+      const double t = __dsub_rn((double)__shfl_sync(0xffffffffu, smp, base + dz + d), p.means[d]);
+      e_new = __dadd_rn(e_new, __dmul_rn(t, t));
+    }
+    {
+      // ---- encoder(x2) || decoder(z1) of the four chains
+      float xe[WC][dx], zd[WC][dz];
+#pragma unroll
+      for (int k = 0; k < WC; ++k) {
+#pragma unroll
+        for (int d = 0; d < dz; ++d) zd[k][d] = __shfl_sync(0xffffffffu, smp, 8 * k + d);
+#pragma unroll
+        for (int d = 0; d < dx; ++d) xe[k][d] = __shfl_sync(0xffffffffu, smp, 8 * k + dz + d);
+      }
+      mlp_pair_warp(wsm, Hp32, lane, xe, zd, loc, raw);
+    }
+    loc += bias_loc;
+    sc = softplus_tf(raw + bias_raw);
+    const float t_rev = normal_lp(enc_lane ? z2_mine : x1_mine, loc, sc);  // term of log q(z2 | x2) or of log p(x1 | z1)
+    float lq2 = 0.f, lx1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < dz; ++d) lq2 += __shfl_sync(0xffffffffu, t_rev, base + d);
+#pragma unroll
+    for (int d = 0; d < dx; ++d) lx1 += __shfl_sync(0xffffffffu, t_rev, base + dz + d);
+    // ---- accept / reject (mcmc.py:103, :109, :116-120): every lane of the chain computes the same decision
+    const float fwd = __fadd_rn(__fadd_rn(lq1, lz2), lx2);
+    const float rev = __fadd_rn(__fadd_rn(lq2, lz1), lx1);
+    const int64_t g = (int64_t)step * p.B + cc;
+    const double la = __dsub_rn(__dsub_rn(__dadd_rn(e_new, (double)rev), e_old), (double)fwd);
+    const bool mine = live && sub == 0;
+    double lu;
+    if (p.use_pcg) {
+      lu = log(pcg_uniform(rs));
+      rs = add128(mul128(jm, rs), ja);  // this chain's draw of the next MC step: B_global draws further down the stream
+      if (fabs(la - lu) <= 1e-13 * fmax(1.0, fabs(lu))) n_unc += mine ? 1u : 0u;
+    } else {
+      lu = __ldg(p.log_u + g);
+    }
+    const bool a = la >= lu;
+    if (mine) {
+      if (p.log_u_trace) p.log_u_trace[g] = lu;
+      if (p.acc_trace) p.acc_trace[g] = a ? 1 : 0;
+      if (p.fwd_trace) p.fwd_trace[g] = fwd;
+      if (p.rev_trace) p.rev_trace[g] = rev;
+      if (p.e_new_trace) p.e_new_trace[g] = e_new;
+      n_accept += a ? 1u : 0u;
+    }
+    if (a) {
+      e_old = e_new;
+      if (!enc_lane) {
+        x1_mine = smp;
+        xs[kc * 8 + dof] = smp;
+      }
+    }
+    __syncwarp();
+  }
+  if (live && !enc_lane) p.x[chain * dx + dof] = x1_mine;
+  if (live && sub == 0) p.E[chain] = e_old;
+  unsigned w = n_accept;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+  if (lane == 0 && w) atomicAdd(p.n_acc, (unsigned long long)w);
+  if (p.use_pcg && p.n_uncertain) {
+    unsigned q = n_unc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0 && q) atomicAdd(p.n_uncertain, (unsigned long long)q);
+  }
+}
+
 }  // namespace
 
 bool mc_chain_enabled(int dx, int dz) {
@@ -344,7 +628,8 @@ vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x
   p.B = B; p.n_steps = n_steps; p.theta = theta; p.x = x; p.E = E; p.energies_valid = energies_valid;
   p.noise = noise; p.seed = seed; p.step0 = step0; p.log_u = log_u; p.means = means; p.n_acc = n_acc;
   p.acc_trace = acc_trace; p.fwd_trace = fwd_trace; p.rev_trace = rev_trace; p.e_new_trace = e_new_trace;
-  const size_t smem = (size_t)(((hidden + 3) & ~3) * WROW + 16) * sizeof(float);
+  // rows padded for the warp-per-four-chains variant too, plus its per-warp configuration slots (up to 8 warps)
+  const size_t smem = (size_t)(((hidden + 31) & ~31) * WROW + 16 + 8 * WC * 8) * sizeof(float);
   VMS_REQUIRE(smem <= (size_t)max_smem_optin(), VMS_ERR_UNSUPPORTED, "mc_chain: hidden too large for shared memory");
   // lanes per chain by the number of chains (identical results for every choice, see `combine`)
   int sms = 148;
@@ -352,10 +637,28 @@ vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x
   // (B200, 65,536 chains x 100 steps: 4 lanes 799 M proposals/s, 2 lanes 1,270 M, 1 lane 1,241 M at 128 registers, 1 lane
   //  with two chains per lane 1,469 M; 32,768 chains: 2 lanes 1,106 M; 8,192: 2 lanes 678 M, 4 lanes 510 M)
   const bool full = B >= (int64_t)sms * 256;  // enough chains for one lane per chain and two chains per lane
-  int tpc = full ? 1 : (B >= (int64_t)sms * 40 ? 2 : 4);
-  if (const char* e = getenv("VMS_MC_TPC")) {  // cross-checks: force a lane count
+  //  8 lanes (mc_chain_warp_kernel, its own summation order): see the numbers at the launch below
+  int tpc = full ? 1 : (B >= (int64_t)sms * kWideMaxChainsPerSm ? 2 : 8);
+  if (const char* e = getenv("VMS_MC_TPC")) {  // cross-checks / pinning one summation order: force a lane count
     const int t = atoi(e);
-    if (t == 1 || t == 2 || t == 4) tpc = t;
+    if (t == 1 || t == 2 || t == 4 || t == 8) tpc = t;
+  }
+  if (tpc == 8) {
+    // CTAs of 64 threads (8 chains) while they are all co-resident (finest balance over the SMs), else 128 / 256
+    const int64_t lanes = B * WL;
+    const int ctw = lanes <= (int64_t)sms * 8 * 64 ? 64 : (lanes <= (int64_t)sms * 8 * 128 ? 128 : 256);
+    const unsigned gridw = (unsigned)((lanes + ctw - 1) / ctw);
+#define VMS_WIDE_LAUNCH(C, M)                                                                                          \
+  do {                                                                                                                 \
+    VMS_CUDA(cudaFuncSetAttribute(mc_chain_warp_kernel<C, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mc_chain_warp_kernel<C, M><<<gridw, C, smem, st>>>(p);                                                             \
+  } while (0)
+    if (ctw == 64) VMS_WIDE_LAUNCH(64, 7);
+    else if (ctw == 128) VMS_WIDE_LAUNCH(128, 3);
+    else VMS_WIDE_LAUNCH(256, 1);
+#undef VMS_WIDE_LAUNCH
+    VMS_LAUNCH_CHECK("mc_chain_warp_kernel");
+    return VMS_OK;
   }
   int cpl = full ? 2 : 1;
   if (const char* e = getenv("VMS_MC_CPL")) {  // cross-checks: chains per lane group
