@@ -330,6 +330,12 @@ __global__ void __launch_bounds__(CT, MINB) mc_chain_kernel(const ChainParams p)
 // four-stream order of the 1 / 2 / 4-lane kernel: log-probabilities agree to float32 rounding, decisions wherever the
 // margin exceeds that rounding (both orders are tested against the reference's goldens; VMS_MC_TPC pins one of them when
 // bit-identical chains across different shard sizes matter more than speed).
+// Measured (B200, 100 steps): 8,192 chains 686 M proposals/s (two lanes) -> 858 M; 16,384: 956 -> 962 M; 32,768: the
+// two-lane kernel stays ahead (1,122 vs 987 M), so the launcher takes this variant below 96 chains per SM only.  ncu at
+// 8,192 chains: 3,440 warp instructions per warp and MC step (45 % of them the FFMAs of the two passes, 18 % the
+// reduce-scatter), issue-active 63 % with 3.5 warps per scheduler.  Tried and dropped: packed FFMA2 head accumulation
+// (801 M at 8,192 chains: fewer issue slots, longer dependent chains), two units in flight per lane (832 M), a 144-register
+// budget without the residual spills (789 M).
 constexpr int WC = 4;        // chains per warp
 constexpr int WL = 8;        // lanes that finish a chain (one per degree of freedom)
 constexpr int kWideMaxChainsPerSm = 96;  // chains per SM below which the launcher takes this variant
