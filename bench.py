@@ -108,6 +108,90 @@ def time_cpu(w, rows, steps, warmup):
     return rows * steps / dt, dt / steps
 
 
+# The same step with the rows of the batch split over worker PROCESSES (one per host core, BLAS pinned to one thread
+# each): NumPy's elementwise arithmetic is single-threaded, so a single process leaves most of the host idle.  Every worker
+# runs the oracle's forward + analytic backward on its rows and writes its share of the mean gradient into a shared
+# buffer; the parent sums the shares in worker order and applies Adam -- data-parallel training on the CPU.
+_PAR = {}
+
+
+def _par_init(w, x, eps, shm, n_params):
+    try:
+        from threadpoolctl import threadpool_limits
+        _PAR['limit'] = threadpool_limits(1)
+    except Exception:  # noqa: BLE001 -- without threadpoolctl the workers keep their BLAS pools
+        pass
+    from oracle import vae as ovae
+    _PAR['ovae'] = ovae
+    _PAR['P'] = ovae.init_vae(2003, dx=w['dx'], dz=w['dz'], hidden=w['hidden'], prior=w['prior'], num_blocks=w['num_blocks'],
+                              num_bins=w['num_bins'], flow_hidden=w['flow_hidden'])
+    _PAR['x'], _PAR['eps'] = x, eps
+    _PAR['g'] = np.frombuffer(shm, np.float32).reshape(-1, n_params)
+
+
+def _par_task(task):
+    i, lo, hi, n = task
+    ovae, P = _PAR['ovae'], _PAR['P']
+    out, G = ovae.elbo_backward(P, _PAR['x'][lo:hi], _PAR['eps'][lo:hi])
+    share = np.float32((hi - lo) / n)
+    _PAR['g'][i][:] = ovae.flatten(ovae.grad_list(P, G)) * share
+    return float(out['loss']) * float(share)
+
+
+def time_cpu_parallel(w, rows, steps, warmup, workers):
+    import multiprocessing as mp
+    from oracle import vae as ovae
+    P = ovae.init_vae(2003, dx=w['dx'], dz=w['dz'], hidden=w['hidden'], prior=w['prior'], num_blocks=w['num_blocks'],
+                      num_bins=w['num_bins'], flow_hidden=w['flow_hidden'])
+    theta = ovae.flatten(ovae.param_list(P))
+    m, v = np.zeros_like(theta), np.zeros_like(theta)
+    rng = np.random.default_rng(1001)
+    x = rng.standard_normal((rows, w['dx']), dtype=np.float32)
+    eps = rng.standard_normal((rows, w['dz']), dtype=np.float32)
+    workers = max(1, min(workers, rows // 32))
+    ctx = mp.get_context('fork')
+    shm = ctx.RawArray('f', workers * theta.size)
+    g_all = np.frombuffer(shm, np.float32).reshape(workers, theta.size)
+    cuts = [rows * i // workers for i in range(workers + 1)]
+    tasks = [(i, cuts[i], cuts[i + 1], rows) for i in range(workers)]
+    with ctx.Pool(workers, initializer=_par_init, initargs=(w, x, eps, shm, theta.size)) as pool:
+        t = 0
+
+        def step():
+            nonlocal t
+            losses = pool.map_async(_par_task, tasks, chunksize=1).get(timeout=300)
+            t += 1
+            ovae.adam_step(theta, g_all.sum(axis=0), m, v, t)
+            return sum(losses)
+
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t0
+    return rows * steps / dt, dt / steps, workers
+
+
+def cpu_baseline_subprocess(args, w, batch):
+    """The main workload's CPU baseline for the GPU arm: the reference arm itself (worker processes over all host cores) in a
+    child interpreter -- this process holds a CUDA context and must not fork workers."""
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE')}
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '20', '--warmup', '3',
+                            '--workload', args.workload, '--batch', str(batch), '--no-extras'],
+                           env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        ref = json.loads(r.stdout.strip().splitlines()[-1])
+        cb = dict(ref['cpu_baseline'])
+        cb['ms_per_step'] = ref['ms_per_step']
+        return cb
+    except Exception as ex:  # noqa: BLE001 -- fall back to one process in this interpreter
+        cpu_val, cpu_sec = time_cpu(w, batch, 10, 2)
+        return {'value': cpu_val, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                'sample': '10 steps of %d configs, NumPy oracle in one process (child interpreter failed: %s)' % (batch, ex),
+                'ms_per_step': cpu_sec * 1e3}
+
+
 def run_reference(args, w):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -117,10 +201,17 @@ def run_reference(args, w):
     _, t_full = time_cpu(w, batch, 1, 1)
     budget = 120.0
     rows = batch
-    total = (args.steps + args.warmup) * t_full
-    if total > budget:
-        rows = max(32, int(batch * budget / total) // 32 * 32)
-    value, sec = time_cpu(w, rows, args.steps, args.warmup)
+    cores = cpu_threads()
+    how = 'rows split over %d worker processes (one BLAS thread each), shares of the mean gradient summed by the parent'
+    try:
+        value, sec, used = time_cpu_parallel(w, rows, args.steps, args.warmup, cores)
+        how = how % used
+    except Exception as ex:  # noqa: BLE001 -- a host that cannot fork workers still gets the single-process number
+        total = (args.steps + args.warmup) * t_full
+        if total > budget:
+            rows = max(32, int(batch * budget / total) // 32 * 32)
+        value, sec = time_cpu(w, rows, args.steps, args.warmup)
+        used, how = 1, 'single process (worker pool failed: %s: %s)' % (type(ex).__name__, ex)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
@@ -128,14 +219,16 @@ def run_reference(args, w):
         'config': {'workload': w['label'], 'rows_per_step': rows,
                    'note': 'CPU NumPy restatement of the reference path (oracle/); TF<=2.15 / TFP<=0.23 are not '
                            'installable in this image (Python 3.12, no network)'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
-                         'sample': '%d steps of %d configs (of the %d-config batch)' % (args.steps, rows, batch)},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': 'port',
+                         'sample': '%d steps of %d configs (of the %d-config batch); %s; one process alone: %.1f ms per '
+                                   '%d-config step' % (args.steps, rows, batch, how, t_full * 1e3, batch)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    mcb = mc_cpu_baseline()
-    line['mc'] = {'metric': 'MC proposals/sec', 'value': mcb['value'], 'unit': 'proposals/s', 'workload': MC_LABEL,
-                  'cpu_baseline': mcb}
+    if not args.no_extras:
+        mcb = mc_cpu_baseline()
+        line['mc'] = {'metric': 'MC proposals/sec', 'value': mcb['value'], 'unit': 'proposals/s', 'workload': MC_LABEL,
+                      'cpu_baseline': mcb}
     print(json.dumps(line), flush=True)
 
 
@@ -1383,10 +1476,7 @@ def run_b200(args, w):
                               for k, d in legs.items() if 'error' not in d}
         line['mc'] = legs.get('c4a_mc')
         line['large_batch'] = legs.get('c5')
-        cpu_val, cpu_sec = time_cpu(w, batch, 10, 2)
-        line['cpu_baseline'] = {'value': cpu_val, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
-                                'sample': '10 steps of %d configs, NumPy oracle (ELBO fwd + analytic bwd + Adam)' % batch,
-                                'ms_per_step': cpu_sec * 1e3}
+        line['cpu_baseline'] = cpu_baseline_subprocess(args, w, batch)
     print(json.dumps(line), flush=True)
     grp.close()
 
