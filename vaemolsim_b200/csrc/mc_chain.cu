@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(CT, MINB) mc_chain_kernel(const ChainParams p)
 // shared-memory load is served quarter-warp by quarter-warp (3.7 wavefronts per LDS.128 measured), and the kernel sat at
 // 87 % of the shared-memory wavefront peak.  This variant removes that redundancy through registers:
 //   * a warp owns FOUR chains; lane l walks the hidden units j = l, l + 32, ... (ascending) and applies each weight row it
-//     loads to all four chains (112 FFMAs per 7 loads, every wavefront carries distinct data);
+//     loads to all four chains (112 FFMAs per 7 loads, every wavefront carries distinct data); a remainder of up to
+//     eight units (H = 200) is shared out one unit per lane of each chain instead of a mostly padded round;
 //   * the 4 x 16 head outputs are reduce-scattered over the 32 lanes (xor 16, 8, 4, 2, 1: 62 shuffles), which leaves lane
 //     l = 8 k + s with (loc, raw scale) of ONE degree of freedom of chain k: s = 0, 1 the encoder's two latents, s = 2..7
 //     the decoder's six coordinates -- softplus, the sample and the per-dof log-probability run once per dof;
@@ -350,8 +351,13 @@ __device__ __forceinline__ void scatter_step(const float (&v)[N], float (&w)[N /
   }
 }
 
-// enc(xe[k]) | dec(zd[k]) for the warp's four chains k; lane 8 k + s returns (loc, raw scale) of dof s of chain k
-__device__ __forceinline__ void mlp_pair_warp(const float* __restrict__ wsm, int Hp32, int lane,
+// enc(xe[s]) | dec(zd[s]) for the warp's four chains; lane 8 k + d returns (loc, raw scale) of dof d of chain k.
+// SLOT s of lane l holds chain s ^ (l >> 3) (slot 0 = the lane's own chain): the partner of the xor-16 / xor-8 exchange then
+// needs exactly the upper slots, whatever the lane -- those two levels of the reduce-scatter are a shuffle and an add per
+// value, no selects.  Hidden units: `n_full` rounds of 32 units (lane l: unit 32 i + l) for all four chains; when 1..8 units
+// remain (H = 200: 6 x 32 + 8) the eight lanes of a chain take one each for their OWN chain only, and those terms join
+// after the chain levels of the reduction (a full round for them would be 3/4 padding).
+__device__ __forceinline__ void mlp_pair_warp(const float* __restrict__ wsm, int n_full, int tail_base, int lane,
                                               const float (&xe)[WC][kMaxDx], const float (&zd)[WC][kMaxDz], float& out_loc,
                                               float& out_raw) {
   float ae[WC][2 * kMaxDz], ad[WC][2 * kMaxDx];
@@ -362,9 +368,10 @@ __device__ __forceinline__ void mlp_pair_warp(const float* __restrict__ wsm, int
 #pragma unroll
     for (int n = 0; n < 2 * kMaxDx; ++n) ad[k][n] = 0.f;
   }
+  const float* rowp = wsm + lane * WROW;
 #pragma unroll 1
-  for (int j = lane; j < Hp32; j += 32) {
-    const float4* row = reinterpret_cast<const float4*>(wsm + j * WROW);
+  for (int it = 0; it < n_full; ++it, rowp += 32 * WROW) {
+    const float4* row = reinterpret_cast<const float4*>(rowp);
     {
       const float4 a = row[0], b = row[1], c = row[2];
 #pragma unroll
@@ -378,7 +385,7 @@ __device__ __forceinline__ void mlp_pair_warp(const float* __restrict__ wsm, int
       }
     }
     {
-      const float w0d0 = wsm[j * WROW + 11];
+      const float w0d0 = rowp[11];
       const float4 d = row[3], e = row[4], f = row[5], g = row[6];
 #pragma unroll
       for (int k = 0; k < WC; ++k) {
@@ -394,7 +401,7 @@ __device__ __forceinline__ void mlp_pair_warp(const float* __restrict__ wsm, int
       }
     }
   }
-  // lane l ends with entries 2 l, 2 l + 1 of this order: per chain the (loc, raw) pairs of its eight dofs
+  // entries 16 s + i of v: slot s, then the (loc, raw) pairs of the chain's eight dofs
   float v[64];
 #pragma unroll
   for (int k = 0; k < WC; ++k) {
@@ -405,9 +412,32 @@ __device__ __forceinline__ void mlp_pair_warp(const float* __restrict__ wsm, int
       v[16 * k + 5 + 2 * d] = ad[k][kMaxDx + d];
     }
   }
+  // chain levels: slots 2, 3 go to lane ^ 16 (whose slots 2, 3 are this lane's slots 0, 1), then slot 1 to lane ^ 8
   float w32[32], w16[16], w8[8], w4[4], w2[2];
-  scatter_step<64>(v, w32, (lane & 16) != 0, 16);
-  scatter_step<32>(w32, w16, (lane & 8) != 0, 8);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) w32[i] = v[i] + __shfl_xor_sync(0xffffffffu, v[32 + i], 16);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w16[i] = w32[i] + __shfl_xor_sync(0xffffffffu, w32[16 + i], 8);
+  if (tail_base >= 0) {  // own chain (slot 0), unit tail_base + (lane & 7); rows beyond H are zero
+    const float* rp = wsm + (tail_base + (lane & (WL - 1))) * WROW;
+    const float4* row = reinterpret_cast<const float4*>(rp);
+    const float4 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4], f = row[5], g = row[6];
+    float he = 0.f;
+    he = fmaf(xe[0][0], a.x, he); he = fmaf(xe[0][1], a.y, he); he = fmaf(xe[0][2], a.z, he);
+    he = fmaf(xe[0][3], a.w, he); he = fmaf(xe[0][4], b.x, he); he = fmaf(xe[0][5], b.y, he);
+    he = fmaxf(he + b.z, 0.f);
+    float hd = 0.f;
+    hd = fmaf(zd[0][0], c.w, hd); hd = fmaf(zd[0][1], d.x, hd);
+    hd = fmaxf(hd + d.y, 0.f);
+    w16[0] = fmaf(he, b.w, w16[0]); w16[1] = fmaf(he, c.y, w16[1]); w16[2] = fmaf(he, c.x, w16[2]); w16[3] = fmaf(he, c.z, w16[3]);
+    w16[4] = fmaf(hd, d.z, w16[4]);   w16[5] = fmaf(hd, f.x, w16[5]);
+    w16[6] = fmaf(hd, d.w, w16[6]);   w16[7] = fmaf(hd, f.y, w16[7]);
+    w16[8] = fmaf(hd, e.x, w16[8]);   w16[9] = fmaf(hd, f.z, w16[9]);
+    w16[10] = fmaf(hd, e.y, w16[10]); w16[11] = fmaf(hd, f.w, w16[11]);
+    w16[12] = fmaf(hd, e.z, w16[12]); w16[13] = fmaf(hd, g.x, w16[13]);
+    w16[14] = fmaf(hd, e.w, w16[14]); w16[15] = fmaf(hd, g.y, w16[15]);
+  }
+  // dof levels: lane 8 k + d ends with entries 2 d, 2 d + 1
   scatter_step<16>(w16, w8, (lane & 4) != 0, 4);
   scatter_step<8>(w8, w4, (lane & 2) != 0, 2);
   scatter_step<4>(w4, w2, (lane & 1) != 0, 1);
@@ -440,6 +470,9 @@ __global__ void __launch_bounds__(CTW, MINB) mc_chain_warp_kernel(const ChainPar
   __syncthreads();
 
   const int lane = tid & 31;
+  const int rem = H & 31;
+  const int n_full = (H >> 5) + (rem > WL ? 1 : 0);
+  const int tail_base = (rem > 0 && rem <= WL) ? (H & ~31) : -1;
   float* xs = b1d + 12 + (tid >> 5) * (WC * 8);  // this warp's current configurations: [WC][8] (6 used), 16-byte rows
   const int64_t chain = ((int64_t)blockIdx.x * CTW + tid) / WL;
   const int sub = lane & (WL - 1), kc = lane >> 3;
@@ -501,14 +534,15 @@ __global__ void __launch_bounds__(CTW, MINB) mc_chain_warp_kernel(const ChainPar
       // ---- encoder(x1) || decoder(z2) of the four chains
       float xe[WC][dx], zd[WC][dz];
 #pragma unroll
-      for (int k = 0; k < WC; ++k) {
-        const float4 lo = *reinterpret_cast<const float4*>(xs + k * 8);
-        const float2 hi = *reinterpret_cast<const float2*>(xs + k * 8 + 4);
+      for (int k = 0; k < WC; ++k) {  // slot k = chain k ^ kc
+        const int ch = k ^ kc;
+        const float4 lo = *reinterpret_cast<const float4*>(xs + ch * 8);
+        const float2 hi = *reinterpret_cast<const float2*>(xs + ch * 8 + 4);
         xe[k][0] = lo.x; xe[k][1] = lo.y; xe[k][2] = lo.z; xe[k][3] = lo.w; xe[k][4] = hi.x; xe[k][5] = hi.y;
-        zd[k][0] = __shfl_sync(0xffffffffu, z2a, 8 * k);
-        zd[k][1] = __shfl_sync(0xffffffffu, z2b, 8 * k);
+        zd[k][0] = __shfl_sync(0xffffffffu, z2a, 8 * ch);
+        zd[k][1] = __shfl_sync(0xffffffffu, z2b, 8 * ch);
       }
-      mlp_pair_warp(wsm, Hp32, lane, xe, zd, loc, raw);
+      mlp_pair_warp(wsm, n_full, tail_base, lane, xe, zd, loc, raw);
     }
     loc += bias_loc;
     float sc = softplus_tf(raw + bias_raw);
@@ -536,13 +570,14 @@ __global__ void __launch_bounds__(CTW, MINB) mc_chain_warp_kernel(const ChainPar
       // ---- encoder(x2) || decoder(z1) of the four chains
       float xe[WC][dx], zd[WC][dz];
 #pragma unroll
-      for (int k = 0; k < WC; ++k) {
+      for (int k = 0; k < WC; ++k) {  // slot k = chain k ^ kc
+        const int src = 8 * (k ^ kc);
 #pragma unroll
-        for (int d = 0; d < dz; ++d) zd[k][d] = __shfl_sync(0xffffffffu, smp, 8 * k + d);
+        for (int d = 0; d < dz; ++d) zd[k][d] = __shfl_sync(0xffffffffu, smp, src + d);
 #pragma unroll
-        for (int d = 0; d < dx; ++d) xe[k][d] = __shfl_sync(0xffffffffu, smp, 8 * k + dz + d);
+        for (int d = 0; d < dx; ++d) xe[k][d] = __shfl_sync(0xffffffffu, smp, src + dz + d);
       }
-      mlp_pair_warp(wsm, Hp32, lane, xe, zd, loc, raw);
+      mlp_pair_warp(wsm, n_full, tail_base, lane, xe, zd, loc, raw);
     }
     loc += bias_loc;
     sc = softplus_tf(raw + bias_raw);
