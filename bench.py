@@ -1081,8 +1081,8 @@ def mc_bench(v, grp, ffma_peak, reps=3):
                    'd2h_bytes_per_step': int(B * 32 / MC_STEPS), 'ms_per_mc_step': e2e_s / (reps * MC_STEPS) * 1e3,
                    'api': 'MCMC.run(configs, n_steps=%d) from host arrays' % MC_STEPS},
            'roofline': {'bound': 'ffma',
-                        'kernel': ('mc_chain_warp_kernel (a warp per four chains: fewer than 96 chains per SM)'
-                                   if B < 96 * 148 and not os.environ.get('VMS_MC_TPC') else 'mc_chain_kernel'),
+                        'kernel': ('mc_chain_warp_kernel (a warp per four chains: fewer than 128 chains per SM)'
+                                   if B < 128 * 148 and not os.environ.get('VMS_MC_TPC') else 'mc_chain_kernel'),
                         'achieved': tflops / grp.world, 'peak': ffma_peak,
                         'unit': 'TFLOP/s', 'frac': tflops / grp.world / ffma_peak, 'traffic': None,
                         'algorithmic_flop_per_proposal': 19200,

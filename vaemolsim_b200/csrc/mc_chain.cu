@@ -331,15 +331,17 @@ __global__ void __launch_bounds__(CT, MINB) mc_chain_kernel(const ChainParams p)
 // four-stream order of the 1 / 2 / 4-lane kernel: log-probabilities agree to float32 rounding, decisions wherever the
 // margin exceeds that rounding (both orders are tested against the reference's goldens; VMS_MC_TPC pins one of them when
 // bit-identical chains across different shard sizes matter more than speed).
-// Measured (B200, 100 steps): 8,192 chains 686 M proposals/s (two lanes) -> 858 M; 16,384: 956 -> 962 M; 32,768: the
-// two-lane kernel stays ahead (1,122 vs 987 M), so the launcher takes this variant below 96 chains per SM only.  ncu at
-// 8,192 chains: 3,440 warp instructions per warp and MC step (45 % of them the FFMAs of the two passes, 18 % the
-// reduce-scatter), issue-active 63 % with 3.5 warps per scheduler.  Tried and dropped: packed FFMA2 head accumulation
-// (801 M at 8,192 chains: fewer issue slots, longer dependent chains), two units in flight per lane (832 M), a 144-register
-// budget without the residual spills (789 M).
+// Measured (B200, 100 steps; two-lane kernel -> this one): 4,096 chains 348 -> 733 M proposals/s, 8,192: 686 -> 952 M,
+// 16,384: 956 -> 1,095 M; from 20,480 chains on the two-lane kernel is ahead again (918 vs 893 M; 24,576: 1,094 vs 900 M;
+// 32,768: 1,122 vs 1,027 M), so the launcher takes this variant below 128 chains per SM.  ncu at 8,192 chains, first
+// version (858 M): 3,440 warp instructions per warp and MC step (45 % of them the FFMAs of the two passes, 18 % the
+// reduce-scatter), issue-active 70 % with 3.5 warps per scheduler; the slot permutation and the shared-out remainder round
+// then removed ~10 % of the instructions (952 M).  Tried and dropped: packed FFMA2 head accumulation (801 vs 858 M: fewer
+// issue slots, longer dependent chains), two units in flight per lane (832 M), a 144-register budget without the residual
+// spills (789 M).
 constexpr int WC = 4;        // chains per warp
 constexpr int WL = 8;        // lanes that finish a chain (one per degree of freedom)
-constexpr int kWideMaxChainsPerSm = 96;  // chains per SM below which the launcher takes this variant
+constexpr int kWideMaxChainsPerSm = 128;  // chains per SM below which the launcher takes this variant
 
 template <int N>
 __device__ __forceinline__ void scatter_step(const float (&v)[N], float (&w)[N / 2], bool upper, int lane_mask) {
