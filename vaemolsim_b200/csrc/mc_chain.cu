@@ -331,12 +331,12 @@ __global__ void __launch_bounds__(CT, MINB) mc_chain_kernel(const ChainParams p)
 // four-stream order of the 1 / 2 / 4-lane kernel: log-probabilities agree to float32 rounding, decisions wherever the
 // margin exceeds that rounding (both orders are tested against the reference's goldens; VMS_MC_TPC pins one of them when
 // bit-identical chains across different shard sizes matter more than speed).
-// Measured (B200, 100 steps; two-lane kernel -> this one): 4,096 chains 348 -> 733 M proposals/s, 8,192: 686 -> 952 M,
-// 16,384: 956 -> 1,095 M; from 20,480 chains on the two-lane kernel is ahead again (918 vs 893 M; 24,576: 1,094 vs 900 M;
+// Measured (B200, 100 steps; two-lane kernel -> this one): 4,096 chains 348 -> 749 M proposals/s, 8,192: 686 -> 983 M,
+// 16,384: 956 -> 1,115 M; from 20,480 chains on the two-lane kernel is ahead again (918 vs 893 M; 24,576: 1,094 vs 900 M;
 // 32,768: 1,122 vs 1,027 M), so the launcher takes this variant below 128 chains per SM.  ncu at 8,192 chains, first
 // version (858 M): 3,440 warp instructions per warp and MC step (45 % of them the FFMAs of the two passes, 18 % the
 // reduce-scatter), issue-active 70 % with 3.5 warps per scheduler; the slot permutation and the shared-out remainder round
-// then removed ~10 % of the instructions (952 M).  Tried and dropped: packed FFMA2 head accumulation (801 vs 858 M: fewer
+// then removed ~10 % of the instructions (952 M), the accept uniforms drawn by lane d for step 8 r + d another 3 % (983 M).  Tried and dropped: packed FFMA2 head accumulation (801 vs 858 M: fewer
 // issue slots, longer dependent chains), two units in flight per lane (832 M), a 144-register budget without the residual
 // spills (789 M).
 constexpr int WC = 4;        // chains per warp
@@ -501,10 +501,20 @@ __global__ void __launch_bounds__(CTW, MINB) mc_chain_warp_kernel(const ChainPar
       e_old = __dadd_rn(e_old, __dmul_rn(t, t));
     }
   }
+  // accept uniforms: lane d of a chain draws for the MC steps 8 r + d, once per eight steps -- the PCG64 step, the output
+  // function and the double log run once per eight steps per warp instead of every step
   U128 rs = {0ull, 0ull};
-  const U128 jm = {p.jm_hi, p.jm_lo}, ja = {p.ja_hi, p.ja_lo};
-  if (p.use_pcg)
+  U128 jm8 = {p.jm_hi, p.jm_lo}, ja8 = {p.ja_hi, p.ja_lo};
+  if (p.use_pcg) {
     rs = pcg_advance(U128{p.s0_hi, p.s0_lo}, U128{p.inc_hi, p.inc_lo}, (unsigned long long)(p.chain0 + cc) + 1ull);
+    for (int q = 0; q < sub; ++q) rs = add128(mul128(jm8, rs), ja8);  // this lane's first step: `sub` strides further
+#pragma unroll 1
+    for (int q = 0; q < 3; ++q) {  // (m, a) -> (m^2, a (m + 1)): the stride of eight MC steps
+      ja8 = mul128(add128(jm8, U128{0ull, 1ull}), ja8);
+      jm8 = mul128(jm8, jm8);
+    }
+  }
+  double lu_lane = 0.0;
   unsigned n_accept = 0, n_unc = 0;
   // noise layout of a step: eps(z1) [dz] | eps(z2) [dz] | eps(x2) [dx]; this lane's own eps is entry `eps_idx`, which is
   // component `eps_idx & 3` of Philox call `eps_idx >> 2`
@@ -597,8 +607,11 @@ __global__ void __launch_bounds__(CTW, MINB) mc_chain_warp_kernel(const ChainPar
     const bool mine = live && sub == 0;
     double lu;
     if (p.use_pcg) {
-      lu = log(pcg_uniform(rs));
-      rs = add128(mul128(jm, rs), ja);  // this chain's draw of the next MC step: B_global draws further down the stream
+      if ((step & (WL - 1)) == 0) {
+        lu_lane = log(pcg_uniform(rs));
+        rs = add128(mul128(jm8, rs), ja8);  // this lane's draw eight MC steps on: 8 B_global draws further down the stream
+      }
+      lu = __shfl_sync(0xffffffffu, lu_lane, base + (step & (WL - 1)));
       if (fabs(la - lu) <= 1e-13 * fmax(1.0, fabs(lu))) n_unc += mine ? 1u : 0u;
     } else {
       lu = __ldg(p.log_u + g);
