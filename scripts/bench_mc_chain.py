@@ -17,7 +17,10 @@ for arg in sys.argv[1:] or ['auto']:
     tpc, _, nch = arg.partition(':')
     nch, _, cpl = nch.partition(':')
     nch = int(nch or 65536)
-    os.environ['VMS_MC_CPL'] = cpl or '1'
+    if cpl or tpc != 'auto':
+        os.environ['VMS_MC_CPL'] = cpl or '1'
+    else:
+        os.environ.pop('VMS_MC_CPL', None)  # `auto` without a third field: the launcher's own choice
     tpc_label = tpc
     if tpc == 'auto':
         os.environ.pop('VMS_MC_TPC', None)

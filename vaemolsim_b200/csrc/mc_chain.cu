@@ -717,6 +717,16 @@ vms_status mc_chain_run(int dx, int dz, int hidden, const float* theta, float* x
     return VMS_OK;
   }
   int cpl = full ? 2 : 1;
+  if (!full && tpc == 2) {
+    // two chains per lane pair halve the weight loads per FFMA (32,768 chains: 1,118 -> 1,207 M proposals/s) but double the
+    // chains per CTA: taken when the fullest SM then holds no more chains than before (24,576 chains: 3 CTAs of 64 chains
+    // against 2 of 128 on the fullest SM -- 1,094 vs 905 M)
+    auto fullest = [&](int c) {
+      const int64_t per_cta = (int64_t)(CT / 2) * c, n_cta = (B + per_cta - 1) / per_cta;
+      return (n_cta + sms - 1) / sms * per_cta;
+    };
+    if (fullest(2) <= fullest(1)) cpl = 2;
+  }
   if (const char* e = getenv("VMS_MC_CPL")) {  // cross-checks: chains per lane group
     const int t = atoi(e);
     if (t == 1 || t == 2) cpl = t;
