@@ -442,7 +442,11 @@ vms_status vms_elbo_train_step_peer(vms_elbo_plan plan, float* theta, const floa
  *   do not depend on the grid or on how chains are sharded over GPUs;  else float32 [n_steps, B, 2 dz + dx] =
  *   eps(z1) | eps(z2) | eps(x2) per chain-step (parity mode: the reference draws in this order, mcmc.py:100-102).
  *   n_acc (device u64) += number of accepted proposals.  Optional traces [n_steps, B]: acc (uint8), forward_log_p,
- *   reverse_log_p (float32), proposal energies (float64).  All pointers are device pointers.                                                   */
+ *   reverse_log_p (float32), proposal energies (float64).  All pointers are device pointers.
+ *   The launcher picks the kernel by B: below 128 chains per SM a warp owns four chains and the hidden layers are summed as
+ *   32 unit streams, above it 1 / 2 / 4 lanes own a chain and sum four streams -- noise and uniforms are the same, the
+ *   log-probabilities agree to float32 rounding.  VMS_MC_TPC = 1 | 2 | 4 (four streams) or 8 (32 streams) pins one order
+ *   when runs with different chain counts per GPU must reproduce each other bit for bit.                                   */
 typedef struct {
   int32_t dx, dz, hidden;
 } vms_mc_desc;
