@@ -406,7 +406,7 @@ __device__ void finish_row(const DistSelParams& p, RowSmem& sm, int64_t b, int64
 
 
 template <bool PREF>
-__global__ void __launch_bounds__(DT, 5) dist_select_kernel(const DistSelParams p) {
+__global__ void __launch_bounds__(DT, 6) dist_select_kernel(const DistSelParams p) {
   __shared__ RowSmem sm;
   unsigned long long* keys = sm.keys;
   unsigned& s_count = sm.s_count;
