@@ -213,6 +213,33 @@ __device__ void bitonic_sort(unsigned long long* keys, int n_pow2) {
   __syncthreads();
 }
 
+// The same network for up to 64 keys in ONE warp (two keys per lane, exchanges by shuffle): the usual C3 row ends with ~60
+// candidates, and 21 CTA barriers for 32 compare-exchanges each were ~8 % of the kernel's stall samples.  Call from warp 0
+// between two CTA barriers; keys[n_pow2 .. 64) are not read.
+__device__ __forceinline__ void warp_sort64(unsigned long long* keys, int n_pow2) {
+  const int lane = threadIdx.x;  // < 32
+  unsigned long long r0 = lane < n_pow2 ? keys[lane] : ~0ull;
+  unsigned long long r1 = lane + 32 < n_pow2 ? keys[lane + 32] : ~0ull;
+#pragma unroll
+  for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride == 32) {  // size 64, ascending: element `lane` against element `lane + 32`
+        const unsigned long long lo = r0 < r1 ? r0 : r1, hi = r0 < r1 ? r1 : r0;
+        r0 = lo; r1 = hi;
+      } else {
+        const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, r0, stride), p1 = __shfl_xor_sync(0xffffffffu, r1, stride);
+        const bool lower = (lane & stride) == 0;
+        const bool up0 = (lane & size) == 0, up1 = ((lane + 32) & size) == 0;
+        r0 = (lower == up0) ? (r0 < p0 ? r0 : p0) : (r0 < p0 ? p0 : r0);
+        r1 = (lower == up1) ? (r1 < p1 ? r1 : p1) : (r1 < p1 ? p1 : r1);
+      }
+    }
+  }
+  if (lane < n_pow2) keys[lane] = r0;
+  if (lane + 32 < n_pow2) keys[lane + 32] = r1;
+}
+
 // Shared state of a CTA (both kernels)
 struct RowSmem {
   unsigned long long keys[kCap];
@@ -375,8 +402,13 @@ __device__ void finish_row(const DistSelParams& p, RowSmem& sm, int64_t b, int64
   int n_pow2 = 1;
   while (n_pow2 < n_list) n_pow2 <<= 1;
   for (int j = n_list + threadIdx.x; j < n_pow2; j += DT) keys[j] = ~0ull;
-  if (n_pow2 > 1) bitonic_sort(keys, n_pow2);
-  else __syncthreads();
+  if (n_pow2 > 64) {
+    bitonic_sort(keys, n_pow2);
+  } else {
+    __syncthreads();
+    if (threadIdx.x < 32 && n_pow2 > 1) warp_sort64(keys, n_pow2);
+    __syncthreads();
+  }
 
   // ---- emit the first k
   float* oxyz = p.out_xyz + b * (int64_t)k * 3;
