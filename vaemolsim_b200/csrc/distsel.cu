@@ -471,18 +471,42 @@ __global__ void __launch_bounds__(DT, 6) dist_select_kernel(const DistSelParams 
   constexpr int kSample = 1024;
   const bool want_k = p.out_idx != nullptr && n >= kSample && k <= 512;
   unsigned thr_bits = 0u;
+  // the tiled call on an aligned row: the sample IS the first round of the stream (kSample = 4 DT: one quad per thread, the
+  // same exact arithmetic) -- its d^2 stay in registers, are pushed once the threshold is known, and the stream starts at
+  // the second round (the first version evaluated the sample particle by particle and then streamed it again)
+  static_assert(kSample == 4 * DT, "the sample is one quad per thread");
+  const bool reuse_sample = want_k && !PREF && (reinterpret_cast<uintptr_t>(crow) & 15u) == 0;
   if (want_k) {
     for (int i = threadIdx.x; i < 1024; i += DT) sm.hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < kSample; i += DT) {
-      const Local l = local_of_v(__ldg(crow + (size_t)i * 3), __ldg(crow + (size_t)i * 3 + 1), __ldg(crow + (size_t)i * 3 + 2), rx,
-                                 ry, rz, bo);
-      atomicAdd(&sm.hist[__float_as_uint(l.d2) >> 21], 1u);
+    float sd2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (reuse_sample) {
+      const float4* c4 = reinterpret_cast<const float4*>(crow);
+      const size_t g = threadIdx.x;
+      const float4 f0 = __ldg(c4 + 3 * g), f1 = __ldg(c4 + 3 * g + 1), f2 = __ldg(c4 + 3 * g + 2);
+      quad_d2(f0, f1, f2, rx, ry, rz, bo, sd2);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) atomicAdd(&sm.hist[__float_as_uint(sd2[u]) >> 21], 1u);
+    } else {
+      for (int i = threadIdx.x; i < kSample; i += DT) {
+        const Local l = local_of_v(__ldg(crow + (size_t)i * 3), __ldg(crow + (size_t)i * 3 + 1), __ldg(crow + (size_t)i * 3 + 2),
+                                   rx, ry, rz, bo);
+        atomicAdd(&sm.hist[__float_as_uint(l.d2) >> 21], 1u);
+      }
     }
     __syncthreads();
     if (threadIdx.x < 32) sample_threshold(sm, k);
     __syncthreads();
     thr_bits = sm.s_thr;
+    if (reuse_sample) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (sd2[u] <= p.sq_cut || __float_as_uint(sd2[u]) <= thr_bits) {
+          const unsigned pos = atomicAdd(&s_count, 1u);
+          if (pos < (unsigned)kCap) keys[pos] = make_key(sd2[u], (unsigned)(4 * threadIdx.x + u));
+        }
+      }
+    }
   }
   auto consider = [&](float cx, float cy, float cz, int i) {
     const Local l = local_of_v(cx, cy, cz, rx, ry, rz, bo);
@@ -558,7 +582,7 @@ __global__ void __launch_bounds__(DT, 6) dist_select_kernel(const DistSelParams 
       // (more than kCap recorded: s_count > kCap sends finish_row to its exact radix selection over the row)
     } else {
 #pragma unroll 2
-      for (int g = threadIdx.x; g < n4; g += DT) {
+      for (int g = threadIdx.x + (reuse_sample ? DT : 0); g < n4; g += DT) {
         const float4 f0 = __ldg(c4 + 3 * (size_t)g), f1 = __ldg(c4 + 3 * (size_t)g + 1), f2 = __ldg(c4 + 3 * (size_t)g + 2);
         float d2[4];
         quad_d2(f0, f1, f2, rx, ry, rz, bo, d2);
