@@ -762,6 +762,20 @@ def test_fused_mc_chain_kernel_lane_counts_are_bitwise_equal(vms, monkeypatch):
             assert np.array_equal(res[tpc][2][key], res['1'][2][key]), (tpc, key)
         assert res[tpc][3] == res['1'][3]
     assert 0 < res['1'][3] < B * n_steps
+    # two chains per lane group (what a full GPU runs: one lane x two chains; a half-full one: two lanes x two chains) share
+    # every weight load and nothing else: bit-identical again (1,500 chains: the last group is half empty)
+    for tpc in ('1', '2', '4'):
+        monkeypatch.setenv('VMS_MC_TPC', tpc)
+        monkeypatch.setenv('VMS_MC_CPL', '2')
+        mc = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=12)
+        x, e = mc.run_fused(x0[:B - 1], n_steps=n_steps, trace=True)   # odd chain count
+        monkeypatch.setenv('VMS_MC_CPL', '1')
+        mc1 = v.mcmc.MCMC(model, v.mcmc.QuadraticEnergy(6), random_seed=12)
+        x1c, e1c = mc1.run_fused(x0[:B - 1], n_steps=n_steps, trace=True)
+        assert np.array_equal(x, x1c) and np.array_equal(e, e1c) and mc._num_acc == mc1._num_acc, tpc
+        for key in ('acc', 'fwd', 'rev', 'e_new', 'log_u'):
+            assert np.array_equal(mc._last_trace[key], mc1._last_trace[key]), (tpc, key)
+    monkeypatch.delenv('VMS_MC_CPL')
     # the 8-lane kernel sums the hidden units in its own order: log-probabilities to float32 rounding, the same decision
     # wherever the margin exceeds that rounding, then identical chains
     monkeypatch.setenv('VMS_MC_TPC', '8')
