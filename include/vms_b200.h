@@ -403,6 +403,9 @@ vms_status vms_elbo_plan_set_tc_auto_batch(vms_elbo_plan plan, int64_t batch);
  * events on the launching stream for the next max_launches calls; vms_elbo_plan_kernel_ms synchronises, returns the
  * summed device time of that kernel and the number of launches measured, and resets the counter. */
 vms_status vms_elbo_plan_set_timing(vms_elbo_plan plan, int max_launches);
+/* The same, measuring every `every`-th call only (1 = every call): the two event records around the kernel cost the step
+ * ~5 us (0.111 -> 0.1055 ms per C2 step without them), so a bench that also reports the step time samples the launches. */
+vms_status vms_elbo_plan_set_timing_every(vms_elbo_plan plan, int max_launches, int every);
 vms_status vms_elbo_plan_kernel_ms(vms_elbo_plan plan, double* total_ms, int* launches);
 /* Forward only.  x [B, dx], eps [B, dz] (the reparameterisation noise is an INPUT in parity mode).  Outputs (any
  * nullable): z [B, dz], logq [B], logpz [B], logpx [B], scalars[3] = {loss, nll, kl} (kl unweighted mean).      */

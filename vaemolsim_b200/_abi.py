@@ -172,6 +172,7 @@ _SIGS = {
     'vms_elbo_plan_invalidate': (None, [c_vp]),
     'vms_elbo_plan_set_tc_auto_batch': (None, [c_vp, c_i64]),
     'vms_elbo_plan_set_timing': (None, [c_vp, c_int]),
+    'vms_elbo_plan_set_timing_every': (None, [c_vp, c_int, c_int]),
     'vms_elbo_plan_kernel_ms': (None, [c_vp, C.POINTER(c_f64), C.POINTER(c_int)]),
     'vms_elbo_train_step': (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64,
                                    c_vp]),

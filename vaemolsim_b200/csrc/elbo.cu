@@ -554,7 +554,13 @@ vms_status vms_elbo_plan_set_tc_auto_batch(vms_elbo_plan pl, int64_t batch) {
 }
 
 vms_status vms_elbo_plan_set_timing(vms_elbo_plan pl, int max_launches) {
+  return vms_elbo_plan_set_timing_every(pl, max_launches, 1);
+}
+
+vms_status vms_elbo_plan_set_timing_every(vms_elbo_plan pl, int max_launches, int every) {
   VMS_REQUIRE(pl, VMS_ERR_INVALID_ARG, "elbo_plan_set_timing: NULL plan");
+  pl->timing_every = every > 1 ? every : 1;
+  pl->timing_calls = 0;
   vms_status s = fused_set_timing(pl, max_launches);
   return s ? s : tcf_set_timing(pl, max_launches);
 }

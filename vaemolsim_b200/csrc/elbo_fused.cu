@@ -736,7 +736,7 @@ vms_status fused_run(vms_elbo_plan_s* pl, const float* theta, const float* x, co
     VMS_LAUNCH_CHECK("prepack_kernel");
   }
   const int grid = p.n_tiles < f->max_grid ? p.n_tiles : f->max_grid;
-  const bool timed = f->timing && f->ev_used < f->ev.size();
+  const bool timed = f->timing && f->ev_used < f->ev.size() && (pl->timing_calls++ % (unsigned)pl->timing_every) == 0u;
   if (timed) VMS_CUDA(cudaEventRecord(f->ev[f->ev_used].first, st));
   if (backward)
     elbo_fused_kernel<true><<<grid, FT, f->smem_bytes, st>>>(p);

@@ -86,6 +86,9 @@ struct vms_elbo_plan_s {
   int64_t tc_auto_batch = 8192;
   bool tc_auto_user = false;  // threshold set by the caller / environment (overrides the whole-step kernel's multi-wave range)
   vms::TcfCfg* tcf = nullptr;  // whole-step tensor-core kernel; NULL when the shape does not fit
+  // kernel timing (vms_elbo_plan_set_timing_every): every `timing_every`-th call of the fused paths is measured
+  int timing_every = 1;
+  unsigned timing_calls = 0;
 };
 
 namespace vms {

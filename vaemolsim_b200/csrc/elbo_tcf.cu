@@ -1164,7 +1164,7 @@ vms_status tcf_run(vms_elbo_plan_s* pl, const float* theta, const float* x, cons
     tcf_prepack_kernel<<<(p.P + 255) / 256, 256, 0, st>>>(theta, f->pack_map, p.P, f->fpk, f->wpk, f->part);
     VMS_LAUNCH_CHECK("tcf_prepack_kernel");
   }
-  const bool timed = f->timing && f->ev_used < f->ev.size();
+  const bool timed = f->timing && f->ev_used < f->ev.size() && (pl->timing_calls++ % (unsigned)pl->timing_every) == 0u;
   if (timed) VMS_CUDA(cudaEventRecord(f->ev[f->ev_used].first, st));
 #define VMS_TCF_LAUNCH(RPV, EX)                                                                                             \
   do {                                                                                                                      \
