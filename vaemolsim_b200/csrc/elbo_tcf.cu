@@ -794,6 +794,23 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
 // grad[i] = sum over the tiles' partials in a fixed order (+ Keras Adam + the next step's weight images), and the three
 // loss scalars.  Block = 4 groups x 128 parameters: group g sums its quarter of the partials with eight independent
 // running sums (all loads of a thread in flight at once), the four group sums meet in shared memory in a fixed order.
+constexpr int kFinScal = 1024;  // shared-memory slots for the tiles' scalar partials (2 per tile: up to 512 tiles)
+// {loss, nll, kl} from the tiles' partial sums, added in tile order (deterministic).  Call after the barrier that follows the
+// staging of `ssc` (block 0); the last thread of the block adds them from shared memory.  Batches of more than 512 tiles
+// (never staged) fall back to thread 0 reading global memory.
+__device__ __forceinline__ void finish_scalars(bool staged, const float* ssc, const float* __restrict__ spart, int n_part,
+                                               int64_t B, float klw, float* __restrict__ scalars) {
+  if (blockIdx.x != 0 || scalars == nullptr) return;
+  const float* src = staged ? ssc : spart;
+  if (threadIdx.x != (staged ? blockDim.x - 1 : 0u)) return;
+  float sa = 0.f, sc = 0.f;
+  for (int c = 0; c < n_part; ++c) { sa += src[2 * c]; sc += src[2 * c + 1]; }
+  const float kl = sa / (float)B, nll = sc / (float)B;
+  scalars[0] = nll + klw * kl;
+  scalars[1] = nll;
+  scalars[2] = kl;
+}
+
 struct TcfAdam {
   float *theta, *m, *v;
   float lr_t, one_minus_b1, one_minus_b2, eps;
@@ -806,11 +823,19 @@ __global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_kernel(const float* 
                                                                    const unsigned* __restrict__ pack_map, float* __restrict__ fpk,
                                                                    unsigned short* __restrict__ wpk, size_t part) {
   __shared__ float sh[kFinG][kFinP];
+  __shared__ float ssc[kFinScal];
   const int tx = threadIdx.x & (kFinP - 1), g = threadIdx.x / kFinP;
   const int i = blockIdx.x * kFinP + tx;
   const bool live = i < P;
+  // block 0 also owns the three loss scalars: the tiles' partial sums are fetched by the whole block up front and added in
+  // tile order by its LAST thread after the first barrier (one thread fetching and adding 2 x 128 values after its own
+  // Adam update was the tail of the kernel)
+  const bool scal = blockIdx.x == 0 && scalars != nullptr && 2 * n_part <= kFinScal;
+  if (scal)
+    for (int c = threadIdx.x; c < 2 * n_part; c += kFinP * kFinG) ssc[c] = spart[c];
   float th = 0.f, mi = 0.f, vi = 0.f;
-  if (live && g == 0 && ad.theta) { th = ad.theta[i]; mi = ad.m[i]; vi = ad.v[i]; }  // in flight beside the partial loads
+  unsigned pm = 0u;
+  if (live && g == 0 && ad.theta) { th = ad.theta[i]; mi = ad.m[i]; vi = ad.v[i]; pm = __ldg(pack_map + i); }  // in flight beside the partial loads
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (live) {
     const int per = (n_part + kFinG - 1) / kFinG;
@@ -835,17 +860,10 @@ __global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_kernel(const float* 
       ad.v[i] = vi;
       th = th - ad.lr_t * mi / (sqrtf(vi) + ad.eps);
       ad.theta[i] = th;
-      pack_store(th, __ldg(pack_map + i), fpk, wpk, part);  // the next step's images, written by the optimiser itself
+      pack_store(th, pm, fpk, wpk, part);  // the next step's images, written by the optimiser itself
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && scalars) {
-    float sa = 0.f, sc = 0.f;
-    for (int c = 0; c < n_part; ++c) { sa += spart[2 * c]; sc += spart[2 * c + 1]; }
-    const float kl = sa / (float)B, nll = sc / (float)B;
-    scalars[0] = nll + klw * kl;
-    scalars[1] = nll;
-    scalars[2] = kl;
-  }
+  finish_scalars(scal, ssc, spart, n_part, B, klw, scalars);
 }
 
 // Data-parallel step: the finish kernel and the NVLink exchange in ONE launch.  Phase 1 (never blocks): the tile partials are
@@ -863,16 +881,21 @@ __global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_peer_kernel(const fl
                                                                         float* __restrict__ fpk, unsigned short* __restrict__ wpk,
                                                                         size_t part) {
   __shared__ float sh[kFinG][kFinP];
+  __shared__ float ssc[kFinScal];
   __shared__ int failed;
   const int tx = threadIdx.x & (kFinP - 1), g = threadIdx.x / kFinP;
   const int i = blockIdx.x * kFinP + tx;
   const bool live = i < P;
+  const bool scal = blockIdx.x == 0 && scalars != nullptr && 2 * n_part <= kFinScal;  // see tcf_finish_kernel
+  if (scal)
+    for (int c = threadIdx.x; c < 2 * n_part; c += kFinP * kFinG) ssc[c] = spart[c];
   // timeline of the last step in flag slots 56 .. 59 (nanoseconds of %globaltimer: entry of block 0, gradient complete, exchange
   // decided, block 0 done) -- read by scripts/time_dp_step.py
   unsigned long long* trace = flags_of(a.base[a.rank], a.P) + 56;
   if (blockIdx.x == 0 && threadIdx.x == 0) trace[0] = globaltimer_ns();
   float th = 0.f, mi = 0.f, vi = 0.f;
-  if (live && g == 0) { th = a.theta[i]; mi = a.m[i]; vi = a.v[i]; }
+  unsigned pm = 0u;
+  if (live && g == 0) { th = a.theta[i]; mi = a.m[i]; vi = a.v[i]; pm = __ldg(pack_map + i); }
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (live) {
     const int per = (n_part + kFinG - 1) / kFinG;
@@ -891,14 +914,7 @@ __global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_peer_kernel(const fl
     const float t = (sh[0][tx] + sh[1][tx]) + (sh[2][tx] + sh[3][tx]);
     a.base[a.rank][(int64_t)(a.step & 1ull) * a.P + i] = t;  // my slot of this step
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && scalars) {
-    float sa = 0.f, sc = 0.f;
-    for (int c = 0; c < n_part; ++c) { sa += spart[2 * c]; sc += spart[2 * c + 1]; }
-    const float kl = sa / (float)B, nll = sc / (float)B;
-    scalars[0] = nll + klw * kl;
-    scalars[1] = nll;
-    scalars[2] = kl;
-  }
+  finish_scalars(scal, ssc, spart, n_part, B, klw, scalars);
   __syncthreads();
   if (threadIdx.x == 0) {
     // release pattern: the block's slot stores happen before this barrier; ONE device-scope fence by thread 0 (fences are
@@ -925,7 +941,7 @@ __global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_peer_kernel(const fl
   a.v[i] = vi;
   th = th - a.lr_t * mi / (sqrtf(vi) + a.eps);
   a.theta[i] = th;
-  pack_store(th, __ldg(pack_map + i), fpk, wpk, part);
+  pack_store(th, pm, fpk, wpk, part);
   if (blockIdx.x == 0 && threadIdx.x == 0) trace[3] = globaltimer_ns();
 }
 
