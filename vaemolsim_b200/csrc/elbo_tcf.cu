@@ -385,6 +385,9 @@ __global__ void __launch_bounds__(FT, 1) tcf_kernel(const __grid_constant__ TPar
   __shared__ unsigned tmem_base_s;
   __shared__ float red[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // programmatic dependent launch: the finish kernel of this step may be scheduled (and run its prologue: parameter, Adam
+  // moment and map loads) while the tiles are still at work; it reads the partials only behind griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int H = p.fh, Hp = p.Hp, K = p.K, R = p.R, LDS = p.LDS, dz = p.dz, dx = p.dx, nb = p.nb;
   const int nchH = Hp / 8;
   constexpr int nchR = RP / 8;
@@ -831,16 +834,20 @@ __global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_kernel(const float* 
   // tile order by its LAST thread after the first barrier (one thread fetching and adding 2 x 128 values after its own
   // Adam update was the tail of the kernel)
   const bool scal = blockIdx.x == 0 && scalars != nullptr && 2 * n_part <= kFinScal;
-  if (scal)
-    for (int c = threadIdx.x; c < 2 * n_part; c += kFinP * kFinG) ssc[c] = spart[c];
   float th = 0.f, mi = 0.f, vi = 0.f;
   unsigned pm = 0u;
   if (live && g == 0 && ad.theta) { th = ad.theta[i]; mi = ad.m[i]; vi = ad.v[i]; pm = __ldg(pack_map + i); }  // in flight beside the partial loads
+  const int poff = live ? __ldg(part_map + i) : 0;
+  // everything above is independent of the tile kernel; its partials are read behind this (programmatic dependent launch;
+  // returns at once when the kernel was launched the ordinary way)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (scal)
+    for (int c = threadIdx.x; c < 2 * n_part; c += kFinP * kFinG) ssc[c] = spart[c];
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (live) {
     const int per = (n_part + kFinG - 1) / kFinG;
     const int c0 = g * per, c1 = min(n_part, c0 + per);
-    const float* src = gpart + __ldg(part_map + i);
+    const float* src = gpart + poff;
     int c = c0;
     for (; c + 8 <= c1; c += 8) {
 #pragma unroll
@@ -887,8 +894,6 @@ __global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_peer_kernel(const fl
   const int i = blockIdx.x * kFinP + tx;
   const bool live = i < P;
   const bool scal = blockIdx.x == 0 && scalars != nullptr && 2 * n_part <= kFinScal;  // see tcf_finish_kernel
-  if (scal)
-    for (int c = threadIdx.x; c < 2 * n_part; c += kFinP * kFinG) ssc[c] = spart[c];
   // timeline of the last step in flag slots 56 .. 59 (nanoseconds of %globaltimer: entry of block 0, gradient complete, exchange
   // decided, block 0 done) -- read by scripts/time_dp_step.py
   unsigned long long* trace = flags_of(a.base[a.rank], a.P) + 56;
@@ -896,11 +901,15 @@ __global__ void __launch_bounds__(kFinP * kFinG) tcf_finish_peer_kernel(const fl
   float th = 0.f, mi = 0.f, vi = 0.f;
   unsigned pm = 0u;
   if (live && g == 0) { th = a.theta[i]; mi = a.m[i]; vi = a.v[i]; pm = __ldg(pack_map + i); }
+  const int poff = live ? __ldg(part_map + i) : 0;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // see tcf_finish_kernel
+  if (scal)
+    for (int c = threadIdx.x; c < 2 * n_part; c += kFinP * kFinG) ssc[c] = spart[c];
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (live) {
     const int per = (n_part + kFinG - 1) / kFinG;
     const int c0 = g * per, c1 = min(n_part, c0 + per);
-    const float* src = gpart + __ldg(part_map + i);
+    const float* src = gpart + poff;
     int c = c0;
     for (; c + 8 <= c1; c += 8) {
 #pragma unroll
@@ -1155,6 +1164,27 @@ vms_status tcf_kernel_ms(vms_elbo_plan_s* pl, double* total_ms, int* launches) {
 
 // forward + backward (+ Adam when `adam`): the tile kernel and the finish kernel; the pre-pack kernel only when the
 // images are not known to match theta (first call, parameters changed behind the plan's back)
+// launch configuration of the finish kernels: programmatic stream serialisation (the kernel may start while the tile kernel
+// is still running and waits for it at griddepcontrol.wait); VMS_TCF_PDL=0 launches them the ordinary way
+static cudaLaunchConfig_t finish_launch_config(unsigned grid, cudaStream_t st) {
+  static cudaLaunchAttribute attr[1];
+  static int pdl = -1;
+  if (pdl < 0) {
+    const char* e = getenv("VMS_TCF_PDL");
+    pdl = (e && e[0] == '0') ? 0 : 1;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kFinP * kFinG);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cfg;
+}
+
 bool tcf_peer_ok(vms_elbo_plan_s* pl) {
   TcfCfg* f = pl->tcf;
   if (!f) return false;
@@ -1196,9 +1226,10 @@ vms_status tcf_run(vms_elbo_plan_s* pl, const float* theta, const float* x, cons
   VMS_LAUNCH_CHECK("tcf_kernel");
   if (timed) VMS_CUDA(cudaEventRecord(f->ev[f->ev_used++].second, st));
   if (peer) {  // data-parallel: finish + exchange + Adam + next images in one launch
-    tcf_finish_peer_kernel<<<(p.P + kFinP - 1) / kFinP, kFinP * kFinG, 0, st>>>(f->gpart, n_tiles, p.P, p.P2, f->part_map, f->spart, B,
-                                                                                 p.klw, scalars ? scalars : pl->scalars, *peer,
-                                                                                 f->pack_map, f->fpk, f->wpk, f->part);
+    cudaLaunchConfig_t cfg = finish_launch_config((p.P + kFinP - 1) / kFinP, st);
+    VMS_CUDA(cudaLaunchKernelEx(&cfg, tcf_finish_peer_kernel, (const float*)f->gpart, n_tiles, p.P, p.P2, (const int*)f->part_map,
+                                (const float*)f->spart, B, p.klw, scalars ? scalars : pl->scalars, *peer,
+                                (const unsigned*)f->pack_map, f->fpk, f->wpk, f->part));
     VMS_LAUNCH_CHECK("tcf_finish_peer_kernel");
     f->pack_valid = peer->theta == theta;
     f->pack_theta = theta;
@@ -1209,9 +1240,10 @@ vms_status tcf_run(vms_elbo_plan_s* pl, const float* theta, const float* x, cons
     ad.theta = adam->theta; ad.m = adam->m; ad.v = adam->v;
     ad.lr_t = adam->lr_t; ad.one_minus_b1 = adam->one_minus_b1; ad.one_minus_b2 = adam->one_minus_b2; ad.eps = adam->eps;
   }
-  tcf_finish_kernel<<<(p.P + kFinP - 1) / kFinP, kFinP * kFinG, 0, st>>>(f->gpart, n_tiles, p.P, p.P2, f->part_map, grad,
-                                                                          f->spart, B, p.klw, scalars ? scalars : pl->scalars,
-                                                                          ad, f->pack_map, f->fpk, f->wpk, f->part);
+  cudaLaunchConfig_t cfg = finish_launch_config((p.P + kFinP - 1) / kFinP, st);
+  VMS_CUDA(cudaLaunchKernelEx(&cfg, tcf_finish_kernel, (const float*)f->gpart, n_tiles, p.P, p.P2, (const int*)f->part_map, grad,
+                              (const float*)f->spart, B, p.klw, scalars ? scalars : pl->scalars, ad,
+                              (const unsigned*)f->pack_map, f->fpk, f->wpk, f->part));
   VMS_LAUNCH_CHECK("tcf_finish_kernel");
   // after a fused Adam step the images describe the updated parameters; without it nothing is known about what the caller
   // does to theta next (e.g. the data-parallel exchange updates it in its own kernel)
