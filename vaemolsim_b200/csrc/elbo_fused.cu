@@ -246,6 +246,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(FT, 1) elbo_fused_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the finish kernel may be scheduled early (it waits)
   const int dx = p.dx, dz = p.dz, H = p.hidden, nb = p.nb, fh = p.fh;
   const int ldh = p.ldh, ldrm = p.ldrm;
   // shared-memory map (offsets in floats; see fused_create):
@@ -526,6 +527,9 @@ __global__ void __launch_bounds__(32 * kFinGroups) fused_finish_kernel(const flo
                                                                        const AdamArgs ad) {
   __shared__ float sh[kFinGroups][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  // programmatic dependent launch (elbo_tcf.cu has the same pair): this kernel may be scheduled while the tile kernel is
+  // still running and reads its partials behind this; returns at once after an ordinary launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (grad) {
     const int i = blockIdx.x * 32 + lane;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -751,8 +755,24 @@ vms_status fused_run(vms_elbo_plan_s* pl, const float* theta, const float* x, co
     ad.theta = adam->theta; ad.m = adam->m; ad.v = adam->v;
     ad.lr_t = adam->lr_t; ad.one_minus_b1 = adam->one_minus_b1; ad.one_minus_b2 = adam->one_minus_b2; ad.eps = adam->eps;
   }
-  fused_finish_kernel<<<nblk, 32 * kFinGroups, 0, st>>>(f->gpart, grid, p.P, backward ? grad : nullptr, f->spart, B, p.klw, sc,
-                                                        ad);
+  {
+    static cudaLaunchAttribute attr[1];
+    static int pdl = -1;
+    if (pdl < 0) {
+      const char* e = getenv("VMS_TCF_PDL");  // 0: ordinary launches (also for the tensor-core plan's finish kernels)
+      pdl = (e && e[0] == '0') ? 0 : 1;
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nblk);
+    cfg.blockDim = dim3(32 * kFinGroups);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    VMS_CUDA(cudaLaunchKernelEx(&cfg, fused_finish_kernel, (const float*)f->gpart, grid, p.P, backward ? grad : (float*)nullptr,
+                                (const float*)f->spart, B, p.klw, sc, ad));
+  }
   VMS_LAUNCH_CHECK("fused_finish_kernel");
   return VMS_OK;
 }
